@@ -1,0 +1,278 @@
+/*
+ * vivit_b200.h -- C ABI of libvivit_b200.so (hand-written sm_100a CUDA kernels
+ * for ViViT's low-rank GGN hot path).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - tensors are dense, row-major, in the layout written next to them;
+ *   - `dtype` is VVT_F32 or VVT_F64 and applies to every floating-point buffer
+ *     of the call; index buffers are int64;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - the caller owns every buffer, including `workspace`; the matching
+ *     *_workspace_bytes() function says how large it must be;
+ *   - every entry point returns 0 on success and a non-zero vvt_status
+ *     otherwise and never throws; vvt_last_error() (host string, thread-local)
+ *     describes the last failure.
+ *
+ * R = C * N_ggn is the Gram dimension ("rows" of V^T), D_p the number of
+ * entries of one parameter, K the number of kept directions.
+ *
+ * Each entry point names the reference call site it replaces; paths are
+ * relative to the f-dangel/vivit v1.0.0 source tree. "[BackPACK]" marks
+ * behaviour of the un-vendored dependency backpack-for-pytorch>=1.5,<2
+ * (setup.cfg:36) that the reference reaches through the cited line.
+ */
+#ifndef VIVIT_B200_H
+#define VIVIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef enum { VVT_F32 = 0, VVT_F64 = 1 } vvt_dtype;
+
+typedef enum {
+  VVT_OK = 0,
+  VVT_ERR_INVALID = 1,   /* bad argument (size, dtype, null pointer)     */
+  VVT_ERR_CUDA = 2,      /* a CUDA runtime call or kernel launch failed  */
+  VVT_ERR_WORKSPACE = 3, /* workspace too small                          */
+  VVT_ERR_NOCONV = 4,    /* eigensolver hit the sweep limit              */
+  VVT_ERR_UNSUPPORTED = 5
+} vvt_status;
+
+/* element-wise Jacobian kinds for vvt_sqrt_backprop_elementwise */
+typedef enum {
+  VVT_ACT_RELU = 0,    /* ref = layer input : S * (ref > 0)            */
+  VVT_ACT_SIGMOID = 1, /* ref = layer output: S * ref * (1 - ref)      */
+  VVT_ACT_TANH = 2,    /* ref = layer output: S * (1 - ref^2)          */
+  VVT_ACT_DROPOUT = 3, /* ref = layer output: S * (ref != 0) * scale   */
+  VVT_ACT_MUL = 4      /* ref = derivative  : S * ref                  */
+} vvt_act;
+
+int vvt_abi_version(void);
+const char* vvt_last_error(void); /* host string */
+/* number of kernel launches issued by this library since process start (host counter) */
+int64_t vvt_launch_count(void);
+
+/* ------------------------------------------------------------------------ *
+ * (1) symmetric factor of the loss Hessian                                  *
+ * ------------------------------------------------------------------------ */
+
+/* S[v,n,c] = tau[n,c] (delta_vc - tau[n,v] tau[n,c]) * scale,  tau = sqrt(softmax(logits[sub[n]]))
+ * S: [C, n_sub, C]; logits: [n_total, C]; sub: [n_sub] or NULL (= identity).
+ * scale = 1/sqrt(n_total) for reduction='mean', 1 for 'sum'.
+ * Replaces [BackPACK] CrossEntropyLossDerivatives.sqrt_hessian, reached via
+ * vivit/extensions/secondorder/vivit/__init__.py:86. */
+int vvt_loss_sqrt_hessian_ce(void* S, const void* logits, const int64_t* sub, int64_t n_total,
+                             int64_t n_sub, int64_t C, double scale, int dtype, void* stream);
+
+/* S[m,n,c] = (softmax(logits[sub[n]])[c] - 1[class_ids[m,n]==c]) * scale
+ * S: [M, n_sub, C]; class_ids: [M, n_sub]. scale = 1/sqrt(M) (/sqrt(n_total) for 'mean').
+ * Replaces [BackPACK] CrossEntropyLossDerivatives.sqrt_hessian_sampled (same line,
+ * strategy switch at __init__.py:122-128,173). */
+int vvt_loss_sqrt_hessian_ce_mc(void* S, const void* logits, const int64_t* sub,
+                                const int64_t* class_ids, int64_t n_total, int64_t n_sub, int64_t C,
+                                int64_t M, double scale, int dtype, void* stream);
+
+/* S[v,n,c] = scale * delta_vc;  S: [C, n_sub, C].
+ * Replaces [BackPACK] MSELossDerivatives.sqrt_hessian (__init__.py:85). */
+int vvt_loss_sqrt_hessian_mse(void* S, int64_t n_sub, int64_t C, double scale, int dtype,
+                              void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * (1) back-propagation of the factor through layers ([BackPACK] jac_t_mat_prod,*
+ *     called by MatToJacMat.backpropagate, base class at base.py:8,19)       *
+ * ------------------------------------------------------------------------ */
+
+/* out[r, i] = sum_o S[r, o] W[o, i];  S: [rows, n_out], W: [n_out, n_in], out: [rows, n_in] */
+int vvt_sqrt_backprop_linear(void* out, const void* S, const void* W, int64_t rows, int64_t n_out,
+                             int64_t n_in, int dtype, void* stream);
+
+/* data gradient of a 2d cross-correlation, applied to `rows` = V*N stacked maps.
+ * S: [rows, c_out, h_out, w_out], W: [c_out, c_in, kh, kw], out: [rows, c_in, h_in, w_in].
+ * groups = 1. */
+int vvt_sqrt_backprop_conv2d(void* out, const void* S, const void* W, int64_t rows, int64_t c_out,
+                             int64_t h_out, int64_t w_out, int64_t c_in, int64_t h_in, int64_t w_in,
+                             int64_t kh, int64_t kw, int64_t stride_h, int64_t stride_w,
+                             int64_t pad_h, int64_t pad_w, int64_t dil_h, int64_t dil_w, int dtype,
+                             void* stream);
+
+/* out[v, n, f] = S[v, n, f] * J(ref[n, f]); S/out: [V, n*feat], ref: [n, feat] (see vvt_act). */
+int vvt_sqrt_backprop_elementwise(void* out, const void* S, const void* ref, int64_t V,
+                                  int64_t n_feat, int act, double scale, int dtype, void* stream);
+
+/* max-pool: out[r, ch, p] = sum over output positions q whose arg-max is p of S[r, ch, q].
+ * S: [V*N, ch, h_out*w_out]; argmax: [N, ch, h_out*w_out] flat index into h_in*w_in;
+ * out: [V*N, ch, h_in*w_in]; row r belongs to sample r % N. */
+int vvt_sqrt_backprop_maxpool2d(void* out, const void* S, const int64_t* argmax, int64_t V,
+                                int64_t N, int64_t ch, int64_t h_out, int64_t w_out, int64_t h_in,
+                                int64_t w_in, int64_t kh, int64_t kw, int64_t stride_h,
+                                int64_t stride_w, int64_t pad_h, int64_t pad_w, int64_t dil_h,
+                                int64_t dil_w, int dtype, void* stream);
+
+/* average pool (count_include_pad = true): out[r,ch,p] = sum_{q: p in window q} S[r,ch,q]/(kh kw) */
+int vvt_sqrt_backprop_avgpool2d(void* out, const void* S, int64_t rows, int64_t ch, int64_t h_out,
+                                int64_t w_out, int64_t h_in, int64_t w_in, int64_t kh, int64_t kw,
+                                int64_t stride_h, int64_t stride_w, int64_t pad_h, int64_t pad_w,
+                                int dtype, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * (1) emitting V^T of a parameter in the coalesced [R, D_p] layout          *
+ *     ([BackPACK] param_mjp(sum_batch=False), called at base.py:84-92)       *
+ * ------------------------------------------------------------------------ */
+
+/* Vt[(v,n), (o, ci, ky, kx)] = sum_{oy,ox} S[v,n,o,oy,ox] X[n, ci, oy*sh+ky*dh-ph, ox*sw+kx*dw-pw]
+ * S: [V, N, c_out, h_out, w_out], X: [N, c_in, h_in, w_in] (already sub-sampled),
+ * Vt: [V*N, c_out*c_in*kh*kw] */
+int vvt_v_emit_conv2d(void* Vt, const void* S, const void* X, int64_t V, int64_t N, int64_t c_out,
+                      int64_t h_out, int64_t w_out, int64_t c_in, int64_t h_in, int64_t w_in,
+                      int64_t kh, int64_t kw, int64_t stride_h, int64_t stride_w, int64_t pad_h,
+                      int64_t pad_w, int64_t dil_h, int64_t dil_w, int dtype, void* stream);
+
+/* Vt[r, o] = sum_x S[r, o, x];  S: [rows, c_out, spatial] */
+int vvt_v_emit_bias(void* Vt, const void* S, int64_t rows, int64_t c_out, int64_t spatial,
+                    int dtype, void* stream);
+
+/* materialised Linear weight factor Vt[(v,n), o, i] = S[(v,n), o] Z[n, i]
+ * (only for users who ask for the tensor; the Computations never call it). */
+int vvt_v_emit_linear(void* Vt, const void* S, const void* Z, int64_t V, int64_t N, int64_t n_out,
+                      int64_t n_in, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * (2) Gram assembly                                                          *
+ * ------------------------------------------------------------------------ */
+
+/* split-K scratch for a [rows, depth] x [cols, depth]^T product (0 if none is needed) */
+int64_t vvt_gram_workspace_bytes(int64_t rows, int64_t cols, int64_t depth, int dtype);
+
+/* General strided (optionally batched) product on the same tensor-core main loop:
+ *   C[b] = alpha * opA(A[b]) opB(B[b])^T + beta * C[b],   C: [M, N] with leading dimension ldc
+ *   transA == 0: A is [M, K] (lda >= K)   transA != 0: A is [K, M] (lda >= M)
+ *   transB == 0: B is [N, K] (ldb >= K)   transB != 0: B is [K, N] (ldb >= N)
+ * fp32 uses the 3xTF32 split (fp32-grade accuracy), fp64 uses DMMA.  Stands in for the
+ * torch.einsum calls of vivit/utils/gram.py and vivit/utils/ggn.py that are not named below. */
+int vvt_gemm(void* C, const void* A, const void* B, int64_t M, int64_t N, int64_t K, int transA,
+             int transB, int64_t lda, int64_t ldb, int64_t ldc, double alpha, double beta,
+             int64_t batch, int64_t strideA, int64_t strideB, int64_t strideC, void* workspace,
+             int64_t workspace_bytes, int dtype, void* stream);
+
+/* G[R,R] += V V^T, V: [R, D].  Replaces pairwise_dot(V_t, 2) at base.py:118-124 and
+ * partial_contract(V, V, (2,2)) at directional_derivatives.py:245 / directional_damped_newton.py:254
+ * (vivit/utils/gram.py:206-232). */
+int vvt_gram_dense_accum(void* G, const void* V, int64_t R, int64_t D, void* workspace,
+                         int64_t workspace_bytes, int dtype, void* stream);
+
+/* X[R, n_g] += V g^T, V: [R, D], g: [n_g, D].  Replaces partial_contract(V, g, (2,1)) at
+ * directional_derivatives.py:246; also V_t_mat_prod (vivit/utils/gram.py:182-203). */
+int vvt_gram_cross_accum(void* X, const void* V, const void* g, int64_t R, int64_t n_g, int64_t D,
+                         void* workspace, int64_t workspace_bytes, int dtype, void* stream);
+
+/* G[(c,n),(d,m)] += (sum_i Z[n,i] Z[m,i] + with_bias) * sum_o S[(c,n),o] S[(d,m),o]
+ * S: [C*N, n_out], Z: [N, n_in].  Replaces ViViTGGNLinear.weight::gram_mat (linear.py:66-75);
+ * with_bias=1 also folds in the bias Gram S S^T (base.py:118-124 on the bias), so S S^T is
+ * formed once.  workspace >= vvt_gram_linear_workspace_bytes. */
+int64_t vvt_gram_linear_workspace_bytes(int64_t C, int64_t N, int64_t n_out, int64_t n_in,
+                                        int64_t n_g, int dtype);
+int vvt_gram_linear_accum(void* G, const void* S, const void* Z, int64_t C, int64_t N,
+                          int64_t n_out, int64_t n_in, int with_bias, void* workspace,
+                          int64_t workspace_bytes, int dtype, void* stream);
+
+/* X[(c,n), m] += (sum_i Z[n,i] Zg[m,i] + with_bias) * sum_o S[(c,n),o] Dl[m,o]
+ * structured form of partial_contract(V, grad_batch, (2,1)) for a Linear layer whose
+ * per-sample gradient is Dl[m,:] (x) Zg[m,:]; Dl: [n_g, n_out], Zg: [n_g, n_in]. */
+int vvt_gram_cross_linear_accum(void* X, const void* S, const void* Z, const void* Dl,
+                                const void* Zg, int64_t C, int64_t N, int64_t n_g, int64_t n_out,
+                                int64_t n_in, int with_bias, void* workspace,
+                                int64_t workspace_bytes, int dtype, void* stream);
+
+/* T[i] *= alpha  (the N/len(subsampling) rescale at eigh.py:245-246, eigvalsh.py:218-219) */
+int vvt_scale(void* T, int64_t numel, double alpha, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * (3) symmetric eigensolver: parallel-order block Jacobi                    *
+ * ------------------------------------------------------------------------ */
+
+int64_t vvt_syevj_workspace_bytes(int64_t R, int jobz, int dtype);
+
+/* Eigendecomposition of the symmetric matrix G [R, R] (upper triangle is read, as symeig(upper=True)).
+ * evals: [R] ascending; evecs: [R, R] with eigenvectors as COLUMNS (ignored if jobz == 0).
+ * G is not modified.  info_host (host int[2], may be NULL): {sweeps used, converged flag}.
+ * Replaces Tensor.symeig at eigh.py:248, eigvalsh.py:221, directional_derivatives.py:291,
+ * directional_damped_newton.py:315.  Synchronises `stream` (convergence is checked on the host). */
+int vvt_syevj(void* evals, void* evecs, const void* G, int64_t R, int jobz, void* workspace,
+              int64_t workspace_bytes, int* info_host, int dtype, void* stream);
+
+/* same, for `batch` matrices given as host arrays of device pointers (block-diagonal groups) */
+int vvt_syevj_batched(void* const* evals, void* const* evecs, const void* const* G,
+                      const int64_t* R, int64_t batch, int jobz, void* workspace,
+                      int64_t workspace_bytes, int* info_host, int dtype, void* stream);
+
+/* mask[i] = !isclose(evals[i], 0, rtol, atol) = |evals[i]| > atol  (vivit/utils/eig.py:111-134);
+ * mask: uint8 [R]; count_host (host, may be NULL) receives the number kept (synchronises). */
+int vvt_filter_nonzero(uint8_t* mask, const void* evals, int64_t R, double atol, double rtol,
+                       int64_t* count_host, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * (4) back-transform, normalisation, directional derivatives, Newton step   *
+ * ------------------------------------------------------------------------ */
+
+/* E[K, D] = U[K, R] V[R, D];  norm2[k] += sum_d E[k,d]^2  (norm2: float64 [K] for either dtype,
+ * initialised by the caller; may be NULL).
+ * Replaces Vmp (vivit/utils/ggn.py:94-115) at base.py:96-105 / eigh.py:268-269 and the squared-norm
+ * pass of normalize (vivit/linalg/utils.py:73). */
+int vvt_backtransform_dense(void* E, void* norm2, const void* U, const void* V, int64_t K,
+                            int64_t R, int64_t D, int dtype, void* stream);
+
+/* E[k, o, i] = sum_{c,n} U[k,(c,n)] S[(c,n),o] Z[n,i]  (linear.py:44-53), norm2 as above.
+ * Eb [K, n_out] (may be NULL) additionally receives the bias part sum_{c,n} U S.
+ * workspace: K*N*n_out elements. */
+int vvt_backtransform_linear(void* E, void* Eb, void* norm2, const void* U, const void* S,
+                             const void* Z, int64_t K, int64_t C, int64_t N, int64_t n_out,
+                             int64_t n_in, void* workspace, int64_t workspace_bytes, int dtype,
+                             void* stream);
+
+/* out[f,(c,n)] = sum_{o,i} S[(c,n),o] Mat[f,o,i] Z[n,i]  -- V^T applied to F stacked vectors
+ * (ViViTGGNLinear.weight::V_t_mat_prod, linear.py:55-64).  workspace: F*N*n_out elements. */
+int vvt_vt_mat_prod_linear(void* out, const void* S, const void* Z, const void* Mat, int64_t F,
+                           int64_t C, int64_t N, int64_t n_out, int64_t n_in, void* workspace,
+                           int64_t workspace_bytes, int dtype, void* stream);
+
+/* inv[k] = 1/sqrt(norm2[k]) applied: E[k, :] *= inv[k]  (vivit/linalg/utils.py:75-76) */
+int vvt_scale_rows_rsqrt(void* E, const void* norm2 /* float64 [K] */, int64_t K, int64_t D, int dtype, void* stream);
+
+/* gammas[m,k]  = corr*N * sum_r X[r,m] U[r,k] / sqrt(evals[k])                  (directional_derivatives.py:302-317)
+ * lambdas[n,k] = N_ggn * sum_c ( sum_j corr^2 G[(c,n),j] U[j,k] )^2 / evals[k]  (directional_derivatives.py:322-325)
+ * G: [R,R] un-rescaled accumulation V^T V, X: [R, n_g] un-rescaled V^T g, U: [R, K] kept Gram eigenvectors
+ * (columns), evals: [K]; corr = sqrt(N / N_ggn). gammas: [n_g, K], lambdas: [N_ggn, K]. */
+int vvt_dirderiv_epilogue(void* gammas, void* lambdas, const void* G, const void* X, const void* U,
+                          const void* evals, int64_t C, int64_t N_ggn, int64_t n_g, int64_t K,
+                          int64_t N, void* workspace, int64_t workspace_bytes, int dtype,
+                          void* stream);
+
+/* coef[k] = -mean_m gammas[m,k] / (mean_n lambdas[n,k] + deltas[k]) / sqrt(evals[k])
+ * v[r]    = corr * sum_k U[r,k] coef[k]            (directional_damped_newton.py:353-366) */
+int vvt_newton_coeff(void* v, const void* U, const void* gammas, const void* lambdas,
+                     const void* deltas, const void* evals, int64_t R, int64_t K, int64_t n_g,
+                     int64_t N_ggn, double corr, int dtype, void* stream);
+
+/* step[d] = sum_r v[r] V[r, d]  (directional_damped_newton.py:370-373) */
+int vvt_v_apply_dense(void* step, const void* v, const void* V, int64_t R, int64_t D, int dtype,
+                      void* stream);
+
+/* step[o,i] = sum_{c,n} v[(c,n)] S[(c,n),o] Z[n,i]; stepb[o] (may be NULL) = sum v S */
+int vvt_v_apply_linear(void* step, void* stepb, const void* v, const void* S, const void* Z,
+                       int64_t C, int64_t N, int64_t n_out, int64_t n_in, void* workspace,
+                       int64_t workspace_bytes, int dtype, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIVIT_B200_H */

@@ -1,0 +1,291 @@
+"""Per-entry-point checks of the C ABI on a real GPU.
+
+Every kernel of ``libvivit_b200.so`` is called through ``vivit_b200.kernels``
+(ctypes -> C ABI) and compared with the plain-torch test double evaluated in
+float64 on the same inputs.  Tolerances: fp32 kernels use the 3xTF32 split and
+must reach fp32-grade accuracy (``north_star``: rtol 1e-4; here 2e-5 of the
+result scale), fp64 kernels 1e-10.
+"""
+
+import math
+
+import pytest
+import torch
+
+import tests._torch_kernels as ref
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.float64]
+
+
+@pytest.fixture(scope="module")
+def k():
+    import vivit_b200.kernels as kernels
+
+    return kernels
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g, dtype=torch.float64) * scale).to(dtype).to(dev())
+
+
+def close(got, want, dtype, what=""):
+    want = want.to(torch.float64)
+    got = got.to(torch.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    scale = max(want.abs().max().item(), 1e-30)
+    tol = 2e-5 if dtype == torch.float32 else 1e-10
+    err = (got - want).abs().max().item() / scale
+    assert err <= tol, f"{what}: rel-to-scale error {err:.3e} > {tol:.1e}"
+
+
+def f64(*ts):
+    return [None if t is None else (t.double() if t.is_floating_point() else t) for t in ts]
+
+
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("N,C,sub", [(7, 5, None), (32, 10, [3, 0, 9]), (5, 100, None), (4, 1, None)])
+def test_loss_factor_ce(k, dtype, N, C, sub):
+    logits = rnd(N, C, dtype=dtype, scale=3.0)
+    subt = None if sub is None else torch.tensor(sub, device=dev())
+    for mean in (True, False):
+        close(k.loss_sqrt_hessian_ce(logits, subt, mean), ref.loss_sqrt_hessian_ce(logits.double(), subt, mean), dtype, "ce")
+    n_sub = N if sub is None else len(sub)
+    ids = torch.randint(0, C, (3, n_sub), generator=torch.Generator().manual_seed(1)).to(dev())
+    close(k.loss_sqrt_hessian_ce_mc(logits, subt, ids, True), ref.loss_sqrt_hessian_ce_mc(logits.double(), subt, ids, True), dtype, "ce_mc")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_loss_factor_mse_and_scale(k, dtype):
+    like = torch.zeros(1, dtype=dtype, device=dev())
+    close(k.loss_sqrt_hessian_mse(6, 5, 0.37, like), ref.loss_sqrt_hessian_mse(6, 5, 0.37, like.double()), dtype)
+    t = rnd(1000, 7, dtype=dtype)
+    want = t.double() * 1.7
+    close(k.scale_(t, 1.7), want, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows,n_out,n_in", [(30, 10, 32), (320, 64, 784), (1280, 256, 10), (17, 3, 5), (1, 1, 1)])
+def test_backprop_linear(k, dtype, rows, n_out, n_in):
+    S, W = rnd(rows, n_out, dtype=dtype), rnd(n_out, n_in, dtype=dtype, seed=1)
+    close(k.sqrt_backprop_linear(S, W), ref.sqrt_backprop_linear(*f64(S, W)), dtype)
+    S3 = S.reshape(1, rows, n_out)
+    assert k.sqrt_backprop_linear(S3, W).shape == (1, rows, n_in)
+
+
+CONV_CASES = [
+    # V, N, ci, h, w, co, k, stride, pad, dil
+    (2, 3, 3, 6, 6, 2, 3, 1, 1, 1),
+    (3, 2, 2, 11, 11, 3, 3, 1, 0, 1),
+    (2, 2, 4, 8, 8, 4, 3, 2, 1, 1),
+    (2, 2, 3, 9, 7, 5, 5, 1, 0, 1),
+    (1, 3, 4, 5, 5, 6, 1, 1, 0, 1),
+    (2, 2, 2, 9, 9, 3, 3, 2, 0, 1),
+    (2, 2, 2, 9, 9, 3, 3, 1, 2, 2),
+    (10, 4, 16, 12, 12, 24, 3, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_backprop_and_emit(k, dtype, case):
+    V, N, ci, h, w, co, ks, st, pd, dl = case
+    ho = (h + 2 * pd - dl * (ks - 1) - 1) // st + 1
+    wo = (w + 2 * pd - dl * (ks - 1) - 1) // st + 1
+    S = rnd(V, N, co, ho, wo, dtype=dtype)
+    W = rnd(co, ci, ks, ks, dtype=dtype, seed=1)
+    X = rnd(N, ci, h, w, dtype=dtype, seed=2)
+    args = ((st, st), (pd, pd), (dl, dl))
+    close(k.sqrt_backprop_conv2d(S, W, (h, w), *args), ref.sqrt_backprop_conv2d(*f64(S, W), (h, w), *args), dtype, "dgrad")
+    close(k.v_emit_conv2d(S, X, (ks, ks), *args), ref.v_emit_conv2d(*f64(S, X), (ks, ks), *args), dtype, "emit")
+    close(k.v_emit_bias(S), ref.v_emit_bias(S.double()), dtype, "bias")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_elementwise_and_pools(k, dtype):
+    S = rnd(3, 4, 5, 7, 7, dtype=dtype)
+    r = rnd(4, 5, 7, 7, dtype=dtype, seed=3)
+    for act in range(5):
+        close(k.sqrt_backprop_elementwise(S, r, act, 2.0), ref.sqrt_backprop_elementwise(S.double(), r.double(), act, 2.0), dtype, f"act{act}")
+    x = rnd(4, 5, 9, 9, dtype=dtype, seed=4)
+    for kern, st, pd, ceil in [(3, 2, 0, False), (3, 2, 0, True), (2, 2, 0, False), (3, 1, 1, False), (3, 2, 1, True)]:
+        y, idx = torch.nn.functional.max_pool2d(x, kern, st, pd, 1, ceil, return_indices=True)
+        Sp = rnd(3, *y.shape, dtype=dtype, seed=5)
+        a = ((9, 9), (kern, kern), (st, st), (pd, pd), (1, 1))
+        close(k.sqrt_backprop_maxpool2d(Sp, idx, *a), ref.sqrt_backprop_maxpool2d(Sp.double(), idx, *a), dtype, "maxpool")
+    for kern, st, pd in [(3, 3, 0), (2, 2, 0), (3, 1, 1), (9, 9, 0)]:
+        y = torch.nn.functional.avg_pool2d(x, kern, st, pd)
+        Sp = rnd(2, *y.shape, dtype=dtype, seed=6)
+        a = ((9, 9), (kern, kern), (st, st), (pd, pd))
+        close(k.sqrt_backprop_avgpool2d(Sp, *a), ref.sqrt_backprop_avgpool2d(Sp.double(), *a), dtype, "avgpool")
+    Sl, Z = rnd(3, 4, 6, dtype=dtype), rnd(4, 5, dtype=dtype, seed=7)
+    close(k.v_emit_linear(Sl, Z), ref.v_emit_linear(Sl.double(), Z.double()), dtype, "emit_linear")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (130, 70, 33), (1, 5, 7), (257, 129, 1000), (40, 300, 5)])
+def test_gemm(k, dtype, ta, tb, M, N, K):
+    A = rnd(*((K, M) if ta else (M, K)), dtype=dtype)
+    B = rnd(*((K, N) if tb else (N, K)), dtype=dtype, seed=1)
+    close(k.gemm(A, B, ta, tb), ref.gemm(A.double(), B.double(), ta, tb), dtype)
+    out = rnd(M, N, dtype=dtype, seed=2)
+    want = ref.gemm(A.double(), B.double(), ta, tb, out=out.double().clone(), alpha=0.5, beta=2.0)
+    close(k.gemm(A, B, ta, tb, out=out, alpha=0.5, beta=2.0), want, dtype, "alpha/beta")
+    Ab = rnd(3, *A.shape, dtype=dtype, seed=3)
+    Bb = rnd(3, *B.shape, dtype=dtype, seed=4)
+    close(k.gemm(Ab, Bb, ta, tb), ref.gemm(Ab.double(), Bb.double(), ta, tb), dtype, "batched")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("R,D", [(320, 640), (1280, 5000), (50, 7), (129, 100000), (32, 1)])
+def test_gram_dense_and_cross(k, dtype, R, D):
+    V = rnd(R, D, dtype=dtype)
+    G0 = rnd(R, R, dtype=dtype, seed=1)
+    G0 = G0 + G0.t()
+    close(k.gram_dense_accum(G0.clone(), V), ref.gram_dense_accum(G0.double(), V.double()), dtype, "dense")
+    g = rnd(37, D, dtype=dtype, seed=2)
+    X0 = rnd(R, 37, dtype=dtype, seed=3)
+    close(k.gram_cross_accum(X0.clone(), V, g), ref.gram_cross_accum(X0.double(), V.double(), g.double()), dtype, "cross")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,N,n_out,n_in", [(10, 32, 64, 784), (10, 32, 10, 32), (5, 3, 5, 6), (3, 50, 300, 17), (10, 128, 512, 1152)])
+@pytest.mark.parametrize("bias", [False, True])
+def test_gram_linear(k, dtype, C, N, n_out, n_in, bias):
+    S, Z = rnd(C, N, n_out, dtype=dtype), rnd(N, n_in, dtype=dtype, seed=1)
+    G0 = torch.zeros(C * N, C * N, dtype=dtype, device=dev())
+    close(k.gram_linear_accum(G0.clone(), S, Z, bias), ref.gram_linear_accum(G0.double(), S.double(), Z.double(), bias), dtype, "gram_linear")
+    Dl, Zg = rnd(9, n_out, dtype=dtype, seed=2), rnd(9, n_in, dtype=dtype, seed=3)
+    X0 = rnd(C * N, 9, dtype=dtype, seed=4)
+    close(
+        k.gram_cross_linear_accum(X0.clone(), S, Z, Dl, Zg, bias),
+        ref.gram_cross_linear_accum(X0.double(), *f64(S, Z, Dl, Zg), bias),
+        dtype,
+        "cross_linear",
+    )
+
+
+def _psd(R, rank, dtype, seed=0):
+    B = rnd(R, rank, dtype=torch.float64, seed=seed)
+    return (B @ B.t() / rank).to(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("R,rank", [(1, 1), (5, 5), (32, 3), (33, 33), (100, 40), (320, 288), (640, 64), (1280, 1152)])
+def test_syevj(k, dtype, R, rank):
+    G = _psd(R, rank, dtype, seed=R)
+    evals, evecs = k.syevj(G, True)
+    assert k.last_syevj_info["converged"]
+    want = torch.linalg.eigvalsh(G.double())
+    tol = 2e-5 if dtype == torch.float32 else 1e-11
+    assert (evals.double() - want).abs().max() <= tol * want.abs().max(), (evals.double() - want).abs().max()
+    assert (evals[1:] >= evals[:-1]).all()
+    U = evecs.double()
+    eye = torch.eye(R, dtype=torch.float64, device=dev())
+    orth = (U.t() @ U - eye).abs().max().item()
+    resid = (G.double() @ U - U * evals.double()[None]).norm().item() / max(G.double().norm().item(), 1e-30)
+    lim = 5e-5 if dtype == torch.float32 else 1e-11
+    assert orth <= lim and resid <= lim, (orth, resid, k.last_syevj_info)
+    ev_only, none = k.syevj(G, False)
+    assert none is None
+    assert (ev_only.double() - want).abs().max() <= tol * want.abs().max()
+
+
+def test_syevj_reads_upper_triangle_and_keeps_input(k):
+    G = _psd(40, 40, torch.float64)
+    Gu = torch.triu(G) + torch.tril(torch.full_like(G, 123.0), -1)  # garbage below the diagonal
+    before = Gu.clone()
+    evals, _ = k.syevj(Gu, True)
+    assert torch.equal(Gu, before)
+    assert torch.allclose(evals, torch.linalg.eigvalsh(G), rtol=1e-10, atol=1e-12)
+
+
+def test_syevj_lapack_killer(k):
+    """The reference's only binary fixture: LAPACK syevd does not converge on it
+    (test/utils/test_stable_symeig.py:25-45); Jacobi must, without a shift."""
+    import os
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "symeig_killer.pt")
+    G = torch.load(path).to(dev())
+    evals, evecs = k.syevj(G, True)
+    assert k.last_syevj_info["converged"]
+    top = evals[-1].double().item()
+    Gd = G.double()
+    sym = torch.triu(Gd) + torch.triu(Gd, 1).t()
+    assert abs(top - 6.28e7) / 6.28e7 < 1e-2
+    v = evecs[:, -1].double()
+    assert ((sym @ v) - top * v).norm() / abs(top) < 1e-5
+    assert (evecs.double().t() @ evecs.double() - torch.eye(128, device=dev(), dtype=torch.float64)).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_filter_nonzero(k, dtype):
+    ev = torch.tensor([0.0, 5e-8, -5e-8, 2e-7, 1e-3, -1.0], dtype=dtype, device=dev())
+    assert torch.equal(k.filter_nonzero(ev), ref.filter_nonzero(ev))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("K,R,D", [(1, 50, 33), (10, 1280, 4803), (3, 320, 100000), (20, 64, 300), (40, 32, 1000)])
+def test_backtransform_dense(k, dtype, K, R, D):
+    U, V = rnd(K, R, dtype=dtype), rnd(R, D, dtype=dtype, seed=1)
+    n2 = torch.zeros(K, dtype=torch.float64, device=dev())
+    n2r = torch.zeros(K, dtype=torch.float64, device=dev())
+    E = k.backtransform_dense(U, V, n2)
+    Er = ref.backtransform_dense(U.double(), V.double(), n2r)
+    close(E, Er, dtype, "E")
+    close(n2, n2r, dtype, "norm2")
+    close(k.scale_rows_rsqrt(E, n2), ref.scale_rows_rsqrt(Er, n2r), dtype, "normalised")
+    close(k.v_apply_dense(U[0].contiguous(), V), ref.v_apply_dense(U[0].double(), V.double()), dtype, "v_apply")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("K,C,N,n_out,n_in", [(1, 3, 4, 5, 6), (10, 10, 32, 64, 784), (4, 10, 128, 10, 256), (7, 2, 9, 130, 3)])
+def test_structured_linear_products(k, dtype, K, C, N, n_out, n_in):
+    U, S, Z = rnd(K, C * N, dtype=dtype), rnd(C, N, n_out, dtype=dtype, seed=1), rnd(N, n_in, dtype=dtype, seed=2)
+    n2 = torch.zeros(K, dtype=torch.float64, device=dev())
+    n2r = torch.zeros(K, dtype=torch.float64, device=dev())
+    close(k.backtransform_linear(U, S, Z, n2), ref.backtransform_linear(*f64(U, S, Z), n2r), dtype, "E")
+    close(n2, n2r, dtype, "norm2")
+    close(k.v_apply_linear(U[0].contiguous(), S, Z), ref.v_apply_linear(*f64(U[0], S, Z)), dtype, "v_apply_linear")
+    M = rnd(K, n_out, n_in, dtype=dtype, seed=3)
+    close(k.vt_mat_prod_linear(S, Z, M), ref.vt_mat_prod_linear(*f64(S, Z, M)), dtype, "vt_mat_prod")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,N_ggn,n_g,K,N", [(10, 32, 32, 10, 32), (5, 2, 3, 1, 4), (1, 32, 128, 7, 128), (10, 128, 128, 10, 128)])
+def test_dirderiv_and_newton(k, dtype, C, N_ggn, n_g, K, N):
+    R = C * N_ggn
+    G = _psd(R, max(R // 2, K), dtype, seed=3)
+    X = rnd(R, n_g, dtype=dtype, seed=4)
+    ev, evec = torch.linalg.eigh(G.double() * (N / N_ggn))
+    evals = ev[-K:].to(dtype).contiguous()
+    U = evec[:, -K:].to(dtype).contiguous()
+    gam, lam = k.dirderiv_epilogue(G, X, U, evals, C, N_ggn, N)
+    gam_r, lam_r = ref.dirderiv_epilogue(*f64(G, X, U, evals), C, N_ggn, N)
+    close(gam, gam_r, dtype, "gammas")
+    close(lam, lam_r, dtype, "lambdas")
+    deltas = torch.full((K,), 0.5, dtype=dtype, device=dev())
+    corr = math.sqrt(N / N_ggn)
+    close(k.newton_coeff(U, gam, lam, deltas, evals, corr), ref.newton_coeff(*f64(U, gam_r, lam_r, deltas, evals), corr), dtype, "newton v")
+
+
+def test_cpu_tensor_is_refused(k):
+    from vivit_b200._lib import KernelLibraryError
+
+    with pytest.raises(KernelLibraryError):
+        k.scale_(torch.ones(3), 2.0)
+
+
+def test_launch_counter_moves(k):
+    before = k.launch_count()
+    k.scale_(torch.ones(3, device=dev()), 2.0)
+    assert k.launch_count() == before + 1

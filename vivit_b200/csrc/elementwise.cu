@@ -1,0 +1,481 @@
+// Bandwidth-bound kernels: loss-Hessian factors, element-wise / pooling Jacobians,
+// bias emit, dense back-transform, Newton step, filters.  All grid-stride, coalesced
+// along the innermost (feature / parameter) dimension.
+#include "common.cuh"
+
+namespace vvt {
+
+thread_local char g_err[512] = {0};
+char* last_error_buffer() { return g_err; }
+std::atomic<int64_t> g_launches{0};
+
+static inline int ew_blocks(int64_t total, int per_thread = 1) {
+  return int(vmax<int64_t>(1, vmin<int64_t>(ceil_div(total, 256 * per_thread), 16 * num_sms())));
+}
+
+#define GRID_STRIDE(i, total)                                                      \
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < (total); \
+       i += int64_t(gridDim.x) * blockDim.x)
+
+// ---- loss factors -----------------------------------------------------------
+// one warp per sample: softmax in registers (strided over C), then write C x C block
+template <typename T, bool MC>
+__global__ void ce_factor_kernel(T* S, const T* logits, const int64_t* sub, const int64_t* cls,
+                                 int64_t n_sub, int64_t C, int64_t M, T scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t n = warp; n < n_sub; n += nwarps) {
+    const T* row = logits + (sub ? sub[n] : n) * C;
+    T mx = -INFINITY;
+    for (int64_t c = lane; c < C; c += 32) mx = max(mx, row[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    T sum = 0;
+    for (int64_t c = lane; c < C; c += 32) sum += exp(row[c] - mx);
+    sum = warp_sum(sum);
+    const T inv = T(1) / sum;
+    if (MC) {
+      // S[m, n, c] = (p_c - [cls[m,n] == c]) * scale
+      for (int64_t m = 0; m < M; ++m) {
+        const int64_t y = cls[m * n_sub + n];
+        for (int64_t c = lane; c < C; c += 32) {
+          const T p = exp(row[c] - mx) * inv;
+          S[(m * n_sub + n) * C + c] = (p - (c == y ? T(1) : T(0))) * scale;
+        }
+      }
+    } else {
+      // S[v, n, c] = tau_c (delta_vc - tau_v tau_c) * scale
+      for (int64_t v = 0; v < C; ++v) {
+        const T tv = sqrt(exp(row[v] - mx) * inv);
+        for (int64_t c = lane; c < C; c += 32) {
+          const T tc = sqrt(exp(row[c] - mx) * inv);
+          S[(v * n_sub + n) * C + c] = tc * ((c == v ? T(1) : T(0)) - tv * tc) * scale;
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void mse_factor_kernel(T* S, int64_t n_sub, int64_t C, T scale) {
+  const int64_t total = C * n_sub * C;
+  GRID_STRIDE(i, total) {
+    const int64_t c = i % C, v = i / (C * n_sub);
+    S[i] = (c == v) ? scale : T(0);
+  }
+}
+
+template <typename T>
+__global__ void scale_kernel(T* t, int64_t n, T alpha) {
+  GRID_STRIDE(i, n) t[i] *= alpha;
+}
+
+// ---- element-wise Jacobians -------------------------------------------------
+template <typename T>
+__global__ void act_kernel(T* out, const T* S, const T* ref, int64_t V, int64_t nf, int act, T scale) {
+  const int64_t total = V * nf;
+  GRID_STRIDE(i, total) {
+    const T r = ldg(ref + i % nf);
+    T d;
+    switch (act) {
+      case VVT_ACT_RELU: d = r > T(0) ? T(1) : T(0); break;
+      case VVT_ACT_SIGMOID: d = r * (T(1) - r); break;
+      case VVT_ACT_TANH: d = T(1) - r * r; break;
+      case VVT_ACT_DROPOUT: d = r != T(0) ? scale : T(0); break;
+      default: d = r;
+    }
+    out[i] = S[i] * d;
+  }
+}
+
+// gather form of the max-pool scatter: every input position sums the outputs that chose it
+template <typename T>
+__global__ void maxpool_bwd_kernel(T* out, const T* S, const int64_t* argmax, int64_t rows, int64_t N,
+                                   int64_t ch, int ho, int wo, int hi, int wi, int kh, int kw, int sh,
+                                   int sw, int ph, int pw, int dh, int dw) {
+  const int64_t total = rows * ch * hi * wi;
+  GRID_STRIDE(i, total) {
+    const int x = int(i % wi), y = int((i / wi) % hi);
+    const int64_t c = (i / (int64_t(wi) * hi)) % ch, r = i / (int64_t(wi) * hi * ch);
+    const int64_t n = r % N;
+    const int64_t pos = int64_t(y) * wi + x;
+    const T* s = S + (r * ch + c) * int64_t(ho) * wo;
+    const int64_t* am = argmax + (n * ch + c) * int64_t(ho) * wo;
+    T acc = 0;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int ty = y + ph - ky * dh;
+      if (ty < 0 || ty % sh) continue;
+      const int oy = ty / sh;
+      if (oy >= ho) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int tx = x + pw - kx * dw;
+        if (tx < 0 || tx % sw) continue;
+        const int ox = tx / sw;
+        if (ox >= wo) continue;
+        if (am[oy * wo + ox] == pos) acc += s[oy * wo + ox];
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+template <typename T>
+__global__ void avgpool_bwd_kernel(T* out, const T* S, int64_t rows, int64_t ch, int ho, int wo, int hi,
+                                   int wi, int kh, int kw, int sh, int sw, int ph, int pw) {
+  const int64_t total = rows * ch * hi * wi;
+  const T inv = T(1) / T(kh * kw);
+  GRID_STRIDE(i, total) {
+    const int x = int(i % wi), y = int((i / wi) % hi);
+    const int64_t rc = i / (int64_t(wi) * hi);
+    const T* s = S + rc * int64_t(ho) * wo;
+    T acc = 0;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int ty = y + ph - ky;
+      if (ty < 0 || ty % sh) continue;
+      const int oy = ty / sh;
+      if (oy >= ho) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int tx = x + pw - kx;
+        if (tx < 0 || tx % sw) continue;
+        const int ox = tx / sw;
+        if (ox >= wo) continue;
+        acc += s[oy * wo + ox];
+      }
+    }
+    out[i] = acc * inv;
+  }
+}
+
+// ---- V emit ---------------------------------------------------------------
+// Vt[r, o] = sum_x S[r, o, x]: one warp per (r, o)
+template <typename T>
+__global__ void bias_emit_kernel(T* Vt, const T* S, int64_t ro, int64_t spatial) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t w = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5; w < ro; w += nwarps) {
+    const T* s = S + w * spatial;
+    T acc = 0;
+    for (int64_t x = lane; x < spatial; x += 32) acc += s[x];
+    acc = warp_sum(acc);
+    if (lane == 0) Vt[w] = acc;
+  }
+}
+
+template <typename T>
+__global__ void linear_emit_kernel(T* Vt, const T* S, const T* Z, int64_t V, int64_t N, int64_t n_out,
+                                   int64_t n_in) {
+  const int64_t total = V * N * n_out * n_in;
+  GRID_STRIDE(i, total) {
+    const int64_t ii = i % n_in, o = (i / n_in) % n_out, rn = i / (n_in * n_out);
+    Vt[i] = ldg(S + rn * n_out + o) * ldg(Z + (rn % N) * n_in + ii);
+  }
+}
+
+// ---- dense back-transform: E[K, D] = U[K, R] V[R, D] -------------------------
+// Streams V exactly once.  Each thread owns one column d (coalesced across the warp) and
+// KT direction accumulators; U is staged through shared memory in row chunks.
+template <typename T, int KT>
+__global__ void __launch_bounds__(256)
+backtransform_dense_kernel(T* E, double* norm2, const T* U, const T* V, int64_t K, int64_t R, int64_t D,
+                           int64_t k0) {
+  constexpr int RC = 64;  // rows of V per U chunk
+  __shared__ T Us[KT][RC];
+  __shared__ double red[KT][8];
+  const int64_t d = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int kn = int(vmin<int64_t>(KT, K - k0));
+  T acc[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) acc[k] = 0;
+  for (int64_t r0 = 0; r0 < R; r0 += RC) {
+    const int rn = int(vmin<int64_t>(RC, R - r0));
+    __syncthreads();
+    for (int i = threadIdx.x; i < KT * RC; i += blockDim.x) {
+      const int k = i / RC, r = i % RC;
+      Us[k][r] = (k < kn && r < rn) ? U[(k0 + k) * R + r0 + r] : T(0);
+    }
+    __syncthreads();
+    if (d < D) {
+      const T* vp = V + r0 * D + d;
+#pragma unroll 8
+      for (int r = 0; r < rn; ++r) {
+        const T v = ldg(vp + int64_t(r) * D);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) acc[k] += Us[k][r] * v;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    if (k < kn && d < D) E[(k0 + k) * D + d] = acc[k];
+  }
+  if (norm2) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      double s = (d < D) ? double(acc[k]) * double(acc[k]) : 0.0;
+      s = warp_sum(s);
+      if (lane == 0) red[k][warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < kn) {
+      double s = 0;
+      for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+      atomicAdd(norm2 + k0 + threadIdx.x, s);
+    }
+  }
+}
+
+template <typename T>
+__global__ void scale_rows_rsqrt_kernel(T* E, const double* norm2, int64_t K, int64_t D) {
+  const int64_t total = K * D;
+  GRID_STRIDE(i, total) { E[i] = T(double(E[i]) / sqrt(norm2[i / D])); }
+}
+
+template <typename T>
+__global__ void filter_nonzero_kernel(uint8_t* mask, const T* ev, int64_t R, T atol, T rtol,
+                                      unsigned long long* count) {
+  GRID_STRIDE(i, R) {
+    // torch.isclose(ev, 0): |ev - 0| <= atol + rtol * |0|
+    const bool keep = !(fabs(ev[i]) <= atol + rtol * T(0));
+    mask[i] = keep;
+    if (keep && count) atomicAdd(count, 1ull);
+  }
+}
+
+// coef[k] = -mean(gammas[:,k]) / (mean(lambdas[:,k]) + deltas[k]) / sqrt(evals[k]);  v = corr * U coef
+template <typename T>
+__global__ void newton_coeff_kernel(T* v, const T* U, const T* gam, const T* lam, const T* del,
+                                    const T* ev, int64_t R, int64_t K, int64_t n_g, int64_t n_l, T corr) {
+  extern __shared__ unsigned char sm[];
+  T* coef = reinterpret_cast<T*>(sm);
+  for (int64_t k = threadIdx.x; k < K; k += blockDim.x) {
+    T g = 0, l = 0;
+    for (int64_t m = 0; m < n_g; ++m) g += gam[m * K + k];
+    for (int64_t n = 0; n < n_l; ++n) l += lam[n * K + k];
+    g /= T(n_g);
+    l /= T(n_l);
+    coef[k] = -g / (l + del[k]) / sqrt(ev[k]);
+  }
+  __syncthreads();
+  for (int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; r < R;
+       r += int64_t(gridDim.x) * blockDim.x) {
+    T acc = 0;
+    for (int64_t k = 0; k < K; ++k) acc += U[r * K + k] * coef[k];
+    v[r] = acc * corr;
+  }
+}
+
+}  // namespace vvt
+
+using namespace vvt;
+
+extern "C" {
+
+int vvt_abi_version(void) { return 1; }
+const char* vvt_last_error(void) { return last_error_buffer(); }
+int64_t vvt_launch_count(void) { return g_launches.load(); }
+
+int vvt_loss_sqrt_hessian_ce(void* S, const void* logits, const int64_t* sub, int64_t n_total,
+                             int64_t n_sub, int64_t C, double scale, int dtype, void* stream) {
+  VVT_REQUIRE(n_total >= 0 && n_sub >= 0 && C >= 0, "negative size");
+  if (n_sub == 0 || C == 0) return VVT_OK;
+  VVT_REQUIRE(S && logits, "null pointer");
+  VVT_DISPATCH(dtype, {
+    ce_factor_kernel<T, false><<<ew_blocks(n_sub * 32), 256, 0, as_stream(stream)>>>(
+        (T*)S, (const T*)logits, sub, nullptr, n_sub, C, 0, T(scale));
+    return launched(__func__);
+  });
+}
+
+int vvt_loss_sqrt_hessian_ce_mc(void* S, const void* logits, const int64_t* sub,
+                                const int64_t* class_ids, int64_t n_total, int64_t n_sub, int64_t C,
+                                int64_t M, double scale, int dtype, void* stream) {
+  VVT_REQUIRE(n_total >= 0 && n_sub >= 0 && C >= 0 && M >= 0, "negative size");
+  if (n_sub == 0 || C == 0 || M == 0) return VVT_OK;
+  VVT_REQUIRE(S && logits && class_ids, "null pointer");
+  VVT_DISPATCH(dtype, {
+    ce_factor_kernel<T, true><<<ew_blocks(n_sub * 32), 256, 0, as_stream(stream)>>>(
+        (T*)S, (const T*)logits, sub, class_ids, n_sub, C, M, T(scale));
+    return launched(__func__);
+  });
+}
+
+int vvt_loss_sqrt_hessian_mse(void* S, int64_t n_sub, int64_t C, double scale, int dtype,
+                              void* stream) {
+  VVT_REQUIRE(n_sub >= 0 && C >= 0, "negative size");
+  if (n_sub == 0 || C == 0) return VVT_OK;
+  VVT_REQUIRE(S, "null pointer");
+  VVT_DISPATCH(dtype, {
+    mse_factor_kernel<T><<<ew_blocks(C * n_sub * C), 256, 0, as_stream(stream)>>>((T*)S, n_sub, C, T(scale));
+    return launched(__func__);
+  });
+}
+
+int vvt_scale(void* t, int64_t numel, double alpha, int dtype, void* stream) {
+  VVT_REQUIRE(numel >= 0, "negative size");
+  if (numel == 0) return VVT_OK;
+  VVT_REQUIRE(t, "null pointer");
+  VVT_DISPATCH(dtype, {
+    scale_kernel<T><<<ew_blocks(numel), 256, 0, as_stream(stream)>>>((T*)t, numel, T(alpha));
+    return launched(__func__);
+  });
+}
+
+int vvt_sqrt_backprop_elementwise(void* out, const void* S, const void* ref, int64_t V,
+                                  int64_t n_feat, int act, double scale, int dtype, void* stream) {
+  VVT_REQUIRE(V >= 0 && n_feat >= 0, "negative size");
+  VVT_REQUIRE(act >= 0 && act <= VVT_ACT_MUL, "unknown activation");
+  if (V * n_feat == 0) return VVT_OK;
+  VVT_REQUIRE(out && S && ref, "null pointer");
+  VVT_DISPATCH(dtype, {
+    act_kernel<T><<<ew_blocks(V * n_feat), 256, 0, as_stream(stream)>>>(
+        (T*)out, (const T*)S, (const T*)ref, V, n_feat, act, T(scale));
+    return launched(__func__);
+  });
+}
+
+int vvt_sqrt_backprop_maxpool2d(void* out, const void* S, const int64_t* argmax, int64_t V,
+                                int64_t N, int64_t ch, int64_t h_out, int64_t w_out, int64_t h_in,
+                                int64_t w_in, int64_t kh, int64_t kw, int64_t stride_h,
+                                int64_t stride_w, int64_t pad_h, int64_t pad_w, int64_t dil_h,
+                                int64_t dil_w, int dtype, void* stream) {
+  VVT_REQUIRE(V >= 0 && N >= 0 && ch >= 0, "negative size");
+  VVT_REQUIRE(stride_h > 0 && stride_w > 0 && dil_h > 0 && dil_w > 0 && kh > 0 && kw > 0, "bad window");
+  const int64_t total = V * N * ch * h_in * w_in;
+  if (total == 0) return VVT_OK;
+  VVT_REQUIRE(out && S && argmax, "null pointer");
+  VVT_DISPATCH(dtype, {
+    maxpool_bwd_kernel<T><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+        (T*)out, (const T*)S, argmax, V * N, N, ch, int(h_out), int(w_out), int(h_in), int(w_in),
+        int(kh), int(kw), int(stride_h), int(stride_w), int(pad_h), int(pad_w), int(dil_h), int(dil_w));
+    return launched(__func__);
+  });
+}
+
+int vvt_sqrt_backprop_avgpool2d(void* out, const void* S, int64_t rows, int64_t ch, int64_t h_out,
+                                int64_t w_out, int64_t h_in, int64_t w_in, int64_t kh, int64_t kw,
+                                int64_t stride_h, int64_t stride_w, int64_t pad_h, int64_t pad_w,
+                                int dtype, void* stream) {
+  VVT_REQUIRE(rows >= 0 && ch >= 0, "negative size");
+  VVT_REQUIRE(stride_h > 0 && stride_w > 0 && kh > 0 && kw > 0, "bad window");
+  const int64_t total = rows * ch * h_in * w_in;
+  if (total == 0) return VVT_OK;
+  VVT_REQUIRE(out && S, "null pointer");
+  VVT_DISPATCH(dtype, {
+    avgpool_bwd_kernel<T><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+        (T*)out, (const T*)S, rows, ch, int(h_out), int(w_out), int(h_in), int(w_in), int(kh), int(kw),
+        int(stride_h), int(stride_w), int(pad_h), int(pad_w));
+    return launched(__func__);
+  });
+}
+
+int vvt_v_emit_bias(void* Vt, const void* S, int64_t rows, int64_t c_out, int64_t spatial,
+                    int dtype, void* stream) {
+  VVT_REQUIRE(rows >= 0 && c_out >= 0 && spatial >= 0, "negative size");
+  if (rows * c_out == 0) return VVT_OK;
+  VVT_REQUIRE(Vt && S, "null pointer");
+  VVT_DISPATCH(dtype, {
+    bias_emit_kernel<T><<<ew_blocks(rows * c_out * 32), 256, 0, as_stream(stream)>>>(
+        (T*)Vt, (const T*)S, rows * c_out, spatial);
+    return launched(__func__);
+  });
+}
+
+int vvt_v_emit_linear(void* Vt, const void* S, const void* Z, int64_t V, int64_t N, int64_t n_out,
+                      int64_t n_in, int dtype, void* stream) {
+  VVT_REQUIRE(V >= 0 && N >= 0 && n_out >= 0 && n_in >= 0, "negative size");
+  const int64_t total = V * N * n_out * n_in;
+  if (total == 0) return VVT_OK;
+  VVT_REQUIRE(Vt && S && Z, "null pointer");
+  VVT_DISPATCH(dtype, {
+    linear_emit_kernel<T><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+        (T*)Vt, (const T*)S, (const T*)Z, V, N, n_out, n_in);
+    return launched(__func__);
+  });
+}
+
+int vvt_backtransform_dense(void* E, void* norm2, const void* U, const void* V, int64_t K,
+                            int64_t R, int64_t D, int dtype, void* stream) {
+  VVT_REQUIRE(K >= 0 && R >= 0 && D >= 0, "negative size");
+  if (K == 0 || D == 0) return VVT_OK;
+  VVT_REQUIRE(E && U && V, "null pointer");
+  constexpr int KT = 8;
+  VVT_DISPATCH(dtype, {
+    const unsigned blocks = unsigned(ceil_div(D, 256));
+    for (int64_t k0 = 0; k0 < K; k0 += KT) {
+      backtransform_dense_kernel<T, KT><<<blocks, 256, 0, as_stream(stream)>>>(
+          (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);
+      VVT_TRY(launched(__func__));
+    }
+    return VVT_OK;
+  });
+}
+
+int vvt_v_apply_dense(void* step, const void* v, const void* V, int64_t R, int64_t D, int dtype,
+                      void* stream) {
+  VVT_REQUIRE(R >= 0 && D >= 0, "negative size");
+  if (D == 0) return VVT_OK;
+  VVT_REQUIRE(step && v && V, "null pointer");
+  VVT_DISPATCH(dtype, {
+    backtransform_dense_kernel<T, 1><<<unsigned(ceil_div(D, 256)), 256, 0, as_stream(stream)>>>(
+        (T*)step, nullptr, (const T*)v, (const T*)V, 1, R, D, 0);
+    return launched(__func__);
+  });
+}
+
+int vvt_scale_rows_rsqrt(void* E, const void* norm2, int64_t K, int64_t D, int dtype, void* stream) {
+  VVT_REQUIRE(K >= 0 && D >= 0, "negative size");
+  if (K * D == 0) return VVT_OK;
+  VVT_REQUIRE(E && norm2, "null pointer");
+  VVT_DISPATCH(dtype, {
+    scale_rows_rsqrt_kernel<T><<<ew_blocks(K * D), 256, 0, as_stream(stream)>>>((T*)E, (const double*)norm2, K, D);
+    return launched(__func__);
+  });
+}
+
+int vvt_filter_nonzero(uint8_t* mask, const void* evals, int64_t R, double atol, double rtol,
+                       int64_t* count_host, int dtype, void* stream) {
+  VVT_REQUIRE(R >= 0, "negative size");
+  if (R == 0) {
+    if (count_host) *count_host = 0;
+    return VVT_OK;
+  }
+  VVT_REQUIRE(mask && evals, "null pointer");
+  cudaStream_t s = as_stream(stream);
+  unsigned long long* dcount = nullptr;
+  if (count_host) {
+    VVT_TRY(check_cuda(cudaMallocAsync((void**)&dcount, sizeof(unsigned long long), s), __func__));
+    VVT_TRY(check_cuda(cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), s), __func__));
+  }
+  VVT_DISPATCH(dtype, {
+    filter_nonzero_kernel<T><<<ew_blocks(R), 256, 0, s>>>(mask, (const T*)evals, R, T(atol), T(rtol), dcount);
+    VVT_TRY(launched(__func__));
+  });
+  if (count_host) {
+    unsigned long long h = 0;
+    VVT_TRY(check_cuda(cudaMemcpyAsync(&h, dcount, sizeof(h), cudaMemcpyDeviceToHost, s), __func__));
+    VVT_TRY(check_cuda(cudaStreamSynchronize(s), __func__));
+    VVT_TRY(check_cuda(cudaFreeAsync(dcount, s), __func__));
+    *count_host = int64_t(h);
+  }
+  return VVT_OK;
+}
+
+int vvt_newton_coeff(void* v, const void* U, const void* gammas, const void* lambdas,
+                     const void* deltas, const void* evals, int64_t R, int64_t K, int64_t n_g,
+                     int64_t N_ggn, double corr, int dtype, void* stream) {
+  VVT_REQUIRE(R >= 0 && K >= 0 && n_g > 0 && N_ggn > 0, "bad size");
+  if (R == 0) return VVT_OK;
+  VVT_REQUIRE(v && U && gammas && lambdas && deltas && evals, "null pointer");
+  VVT_REQUIRE(K * 8 <= 48 * 1024, "too many directions for the coefficient kernel");
+  VVT_DISPATCH(dtype, {
+    const int blocks = int(vmax<int64_t>(1, vmin<int64_t>(ceil_div(R, 256), num_sms())));
+    newton_coeff_kernel<T><<<blocks, 256, size_t(K) * sizeof(T), as_stream(stream)>>>(
+        (T*)v, (const T*)U, (const T*)gammas, (const T*)lambdas, (const T*)deltas, (const T*)evals, R,
+        K, n_g, N_ggn, T(corr));
+    return launched(__func__);
+  });
+}
+
+}  // extern "C"
