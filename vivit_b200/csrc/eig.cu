@@ -10,10 +10,13 @@
 //     the eigenvector accumulator J gets J[:, b] <- J[:, b] Qb (jacobi_tile_kernel);
 //   * nb-1 rounds make a sweep; sweeps repeat until a whole sweep applies no rotation.
 //
-// Rotations are skipped when |a_pq| <= max(eps*sqrt(|a_pp a_qq|), eps*||G||_F/R), which bounds the
-// final off-diagonal Frobenius norm by eps*||G||_F (LAPACK-grade absolute accuracy) and
-// terminates on the exactly rank-deficient Grams this path produces.
+// Rotations are skipped when |a_pq| <= max(eps*sqrt(|a_pp a_qq|), eps*||G||_F/sqrt(R)), which bounds
+// the final off-diagonal Frobenius norm by sqrt(R)*eps*||G||_F (LAPACK-grade absolute accuracy),
+// terminates on the exactly rank-deficient Grams this path produces, and avoids spending sweeps
+// on diagonalising the rounding noise that fills their null space.
 // Pure Jacobi: converges on the reference's LAPACK-killer fixture without a diagonal shift.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vvt {
@@ -81,10 +84,11 @@ __global__ void jacobi_init_kernel(T* A, T* J, const T* G, int64_t R, int64_t Rp
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-jacobi_diag_kernel(T* A, T* Qbuf, int* flags, int Rp, int nb, int round, int64_t R, JacobiScalars* sc) {
+jacobi_diag_kernel(T* A, T* dlo, T* Qbuf, int* flags, int Rp, int nb, int round, int64_t R, JacobiScalars* sc) {
   __shared__ T W[JT][JT + 1];
   __shared__ T Q[JT][JT + 1];
-  __shared__ T cs[JB][2];
+  __shared__ T rot[JB][4];  // s, tau = s/(1+c), new a_pp, new a_qq
+  __shared__ T dl[JT];      // low words of the compensated diagonal
   __shared__ int pq[JB][2];
   const int tid = threadIdx.x;
   int bp, bq;
@@ -94,9 +98,13 @@ jacobi_diag_kernel(T* A, T* Qbuf, int* flags, int Rp, int nb, int round, int64_t
     W[i][j] = A[int64_t(tile_index(bp, bq, i)) * Rp + tile_index(bp, bq, j)];
     Q[i][j] = (i == j) ? T(1) : T(0);
   }
-  const T thr_abs = T(Eps<T>::v * sqrt(sc->norm2) / double(R));
+  if (tid < JT) dl[tid] = dlo[tile_index(bp, bq, tid)];
+  const T thr_abs = T(Eps<T>::v * sqrt(sc->norm2 / double(R)));
   __syncthreads();
 
+  // Rotations are applied in Rutishauser's form  x' = x - s (y + tau x),  y' = y + s (x - tau y):
+  // cos(theta) - 1 = -s tau is never rounded to zero, so thousands of small-angle rotations do not
+  // inflate the Frobenius norm (c = 1/sqrt(1+t^2) rounds to 1 for |t| < sqrt(eps)).
   bool rotated_any = false;
   for (int sweep = 0; sweep < kMaxInnerSweeps; ++sweep) {
     bool rotated_sweep = false;
@@ -106,17 +114,31 @@ jacobi_diag_kernel(T* A, T* Qbuf, int* flags, int Rp, int nb, int round, int64_t
         int p, q;
         rr_pair(JT, rr, tid, p, q);
         const T app = W[p][p], aqq = W[q][q], apq = W[p][q];
-        T c = 1, s = 0;
+        T sn = 0, tau = 0, dpp = app, dqq = aqq;
         const T lim = max(thr_abs, Eps<T>::v * sqrt(fabs(app) * fabs(aqq)));
         if (fabs(apq) > lim) {
-          const T tau = (aqq - app) / (T(2) * apq);
-          const T t = (tau >= T(0) ? T(1) : T(-1)) / (fabs(tau) + sqrt(T(1) + tau * tau));
-          c = T(1) / sqrt(T(1) + t * t);
-          s = t * c;
+          const T theta = (aqq - app) / (T(2) * apq);
+          const T t = (theta >= T(0) ? T(1) : T(-1)) / (fabs(theta) + sqrt(T(1) + theta * theta));
+          const T c = T(1) / sqrt(T(1) + t * t);
+          sn = t * c;
+          tau = sn / (T(1) + c);
+          // The diagonal is kept as an unevaluated sum hi + lo (error-free TwoSum): rotations move
+          // t*a_pq from the smaller to the larger pivot, and without the low word every increment
+          // below half an ulp of the large one would be dropped -- a systematic loss of trace.
+          const T delta = t * apq;
+          const T xp = dl[p] - delta, xq = dl[q] + delta;
+          dpp = app + xp;
+          dqq = aqq + xq;
+          T bb = dpp - app;
+          dl[p] = (app - (dpp - bb)) + (xp - bb);
+          bb = dqq - aqq;
+          dl[q] = (aqq - (dqq - bb)) + (xq - bb);
           did = 1;
         }
-        cs[tid][0] = c;
-        cs[tid][1] = s;
+        rot[tid][0] = sn;
+        rot[tid][1] = tau;
+        rot[tid][2] = dpp;
+        rot[tid][3] = dqq;
         pq[tid][0] = p;
         pq[tid][1] = q;
       }
@@ -125,28 +147,28 @@ jacobi_diag_kernel(T* A, T* Qbuf, int* flags, int Rp, int nb, int round, int64_t
       // columns: W <- W Jrot, Q <- Q Jrot
       for (int it = tid; it < JT * JB; it += 256) {
         const int k = it & (JT - 1), t = it / JT;
-        const T c = cs[t][0], s = cs[t][1];
-        if (s != T(0)) {
+        const T sn = rot[t][0], tau = rot[t][1];
+        if (sn != T(0)) {
           const int p = pq[t][0], q = pq[t][1];
           const T wp = W[k][p], wq = W[k][q];
-          W[k][p] = c * wp - s * wq;
-          W[k][q] = s * wp + c * wq;
+          W[k][p] = wp - sn * (wq + tau * wp);
+          W[k][q] = wq + sn * (wp - tau * wq);
           const T qp = Q[k][p], qq = Q[k][q];
-          Q[k][p] = c * qp - s * qq;
-          Q[k][q] = s * qp + c * qq;
+          Q[k][p] = qp - sn * (qq + tau * qp);
+          Q[k][q] = qq + sn * (qp - tau * qq);
         }
       }
       __syncthreads();
-      // rows: W <- Jrot^T W, and the annihilated entry is set to exactly zero
+      // rows: W <- Jrot^T W; the 2x2 pivot block gets its closed-form values
       for (int it = tid; it < JT * JB; it += 256) {
         const int k = it & (JT - 1), t = it / JT;
-        const T c = cs[t][0], s = cs[t][1];
-        if (s != T(0)) {
+        const T sn = rot[t][0], tau = rot[t][1];
+        if (sn != T(0)) {
           const int p = pq[t][0], q = pq[t][1];
           const T wp = W[p][k], wq = W[q][k];
-          T np = c * wp - s * wq, nq = s * wp + c * wq;
-          if (k == q) np = T(0);
-          if (k == p) nq = T(0);
+          T np = wp - sn * (wq + tau * wp), nq = wq + sn * (wp - tau * wq);
+          if (k == p) np = rot[t][2], nq = T(0);
+          if (k == q) np = T(0), nq = rot[t][3];
           W[p][k] = np;
           W[q][k] = nq;
         }
@@ -163,6 +185,7 @@ jacobi_diag_kernel(T* A, T* Qbuf, int* flags, int Rp, int nb, int round, int64_t
       A[int64_t(tile_index(bp, bq, i)) * Rp + tile_index(bp, bq, j)] = W[i][j];
       Qbuf[int64_t(blockIdx.x) * JT * JT + idx] = Q[i][j];
     }
+    if (tid < JT) dlo[tile_index(bp, bq, tid)] = dl[tid];
   }
   if (tid == 0) {
     flags[blockIdx.x] = rotated_any ? 1 : 0;
@@ -263,20 +286,20 @@ jacobi_tile_kernel(T* A, T* J, const T* Qbuf, const int* flags, int Rp, int nb, 
 }
 
 template <typename T>
-__global__ void jacobi_rank_kernel(int* rank, T* ev, const T* A, int64_t R, int64_t Rp) {
+__global__ void jacobi_rank_kernel(int* rank, T* ev, const T* A, const T* dlo, int64_t R, int64_t Rp) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= R) return;
-  const T vi = A[i * Rp + i];
+  const T vi = A[i * Rp + i] + dlo[i];
   ev[i] = vi;
   int r = 0;
   for (int64_t j = 0; j < R; ++j) {
-    const T vj = ldg(A + j * Rp + j);
+    const T vj = ldg(A + j * Rp + j) + ldg(dlo + j);
     r += (vj < vi) || (vj == vi && j < i) || (vj != vj && vi == vi);  // NaNs sort first, stable
   }
   if (vi != vi) {  // NaN: order among NaNs by index
     r = 0;
     for (int64_t j = 0; j < i; ++j) {
-      const T vj = ldg(A + j * Rp + j);
+      const T vj = ldg(A + j * Rp + j) + ldg(dlo + j);
       r += (vj != vj);
     }
   }
@@ -297,7 +320,7 @@ __global__ void jacobi_permute_kernel(T* evals, T* evecs, const T* ev, const T* 
 }
 
 struct JacobiLayout {
-  int64_t Rp, nb, off_A, off_J, off_Q, off_ev, off_rank, off_flags, off_sc, total;
+  int64_t Rp, nb, off_A, off_J, off_Q, off_ev, off_dlo, off_rank, off_flags, off_sc, total;
 };
 
 static JacobiLayout jacobi_layout(int64_t R, int jobz, int64_t es) {
@@ -314,6 +337,7 @@ static JacobiLayout jacobi_layout(int64_t R, int jobz, int64_t es) {
   L.off_J = jobz ? take(L.Rp * L.Rp * es) : -1;
   L.off_Q = take((L.nb / 2) * JT * JT * es);
   L.off_ev = take(L.Rp * es);
+  L.off_dlo = take(L.Rp * es);
   L.off_rank = take(L.Rp * 4);
   L.off_flags = take((L.nb / 2) * 4);
   L.off_sc = take(sizeof(JacobiScalars));
@@ -329,12 +353,15 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   T* J = jobz ? (T*)(ws + L.off_J) : nullptr;
   T* Qbuf = (T*)(ws + L.off_Q);
   T* ev = (T*)(ws + L.off_ev);
+  T* dlo = (T*)(ws + L.off_dlo);
   int* rank = (int*)(ws + L.off_rank);
   int* flags = (int*)(ws + L.off_flags);
   JacobiScalars* sc = (JacobiScalars*)(ws + L.off_sc);
   const int Rp = int(L.Rp), nb = int(L.nb), half = nb / 2;
 
   VVT_TRY(check_cuda(cudaMemsetAsync(sc, 0, sizeof(JacobiScalars), s), "vvt_syevj"));
+  VVT_TRY(check_cuda(cudaMemsetAsync(dlo, 0, L.Rp * sizeof(T), s), "vvt_syevj"));
+  const bool debug = getenv("VVT_SYEVJ_DEBUG") != nullptr;
   const int init_blocks = int(vmin<int64_t>(ceil_div(L.Rp * L.Rp, 256), 8 * num_sms()));
   jacobi_init_kernel<T><<<init_blocks, 256, 0, s>>>(A, J, G, R, L.Rp, sc);
   VVT_TRY(launched("vvt_syevj(init)"));
@@ -343,7 +370,7 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   for (; sweeps < kMaxSweeps;) {
     VVT_TRY(check_cuda(cudaMemsetAsync(&sc->rotations, 0, sizeof(unsigned long long), s), "vvt_syevj"));
     for (int round = 0; round < nb - 1; ++round) {
-      jacobi_diag_kernel<T><<<half, 256, 0, s>>>(A, Qbuf, flags, Rp, nb, round, R, sc);
+      jacobi_diag_kernel<T><<<half, 256, 0, s>>>(A, dlo, Qbuf, flags, Rp, nb, round, R, sc);
       VVT_TRY(launched("vvt_syevj(diag)"));
       const unsigned gy = unsigned(half + (jobz ? Rp / JT : 0));
       if (half > 1 || jobz) {
@@ -356,12 +383,13 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
     VVT_TRY(check_cuda(cudaMemcpyAsync(&rot, &sc->rotations, sizeof(rot), cudaMemcpyDeviceToHost, s),
                        "vvt_syevj"));
     VVT_TRY(check_cuda(cudaStreamSynchronize(s), "vvt_syevj"));
+    if (debug) fprintf(stderr, "[vvt_syevj] R=%lld sweep %d: %llu of %d block solves rotated\n", (long long)R, sweeps, rot, half * (nb - 1));
     if (rot == 0) {
       converged = 1;
       break;
     }
   }
-  jacobi_rank_kernel<T><<<unsigned(ceil_div(R, 128)), 128, 0, s>>>(rank, ev, A, R, L.Rp);
+  jacobi_rank_kernel<T><<<unsigned(ceil_div(R, 128)), 128, 0, s>>>(rank, ev, A, dlo, R, L.Rp);
   VVT_TRY(launched("vvt_syevj(rank)"));
   const int64_t total = jobz ? R * R : R;
   const int pblocks = int(vmin<int64_t>(ceil_div(total, 256), 8 * num_sms()));
