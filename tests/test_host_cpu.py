@@ -1,0 +1,255 @@
+"""Host-side logic on CPU: backprop engine, factors, parameter-group hooks, the four
+Computations and their error contract.
+
+There is no GPU here and the product has no CPU path, so the kernel layer is replaced by
+the plain-torch test double (``tests/_torch_kernels.py``, installed with ``monkeypatch``);
+everything above it is the shipped code.  Results are compared with the oracle restatement
+of the reference on the same seeded inputs (float64) and with the autograd ground truth.
+"""
+
+import warnings
+
+import pytest
+import torch
+from torch import nn
+
+import tests._torch_kernels as double
+from oracle import reference_path as ref
+from oracle.autograd_ggn import AutogradGGN
+from tests.problems import (
+    GROUPING_IDS,
+    GROUPINGS,
+    IDS,
+    PROBLEM_SUM,
+    PROBLEMS,
+    constant_damping,
+    keep_all,
+    keep_nonzero,
+    make_top_k,
+)
+
+
+@pytest.fixture(autouse=True)
+def torch_kernels(monkeypatch):
+    double.install(monkeypatch)
+
+
+def run_backward(model, loss_fn, x, y, exts, hook):
+    from vivit_b200 import backpack, extend
+
+    model, loss_fn = extend(model), extend(loss_fn)
+    loss = loss_fn(model(x), y)
+    with backpack(*exts, extension_hook=hook):
+        loss.backward()
+    for p in model.parameters():
+        p.grad = None
+
+
+def close(a, b, rtol=1e-8, atol=1e-11):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert torch.allclose(a, b, rtol=rtol, atol=atol), (a - b).abs().max()
+
+
+SUBS = [None, [1, 0]]
+
+
+@pytest.mark.parametrize("grouping", GROUPINGS, ids=GROUPING_IDS)
+@pytest.mark.parametrize("sub", SUBS, ids=["full", "sub10"])
+@pytest.mark.parametrize("problem", PROBLEMS, ids=IDS)
+def test_eigvalsh_matches_oracle(problem, sub, grouping):
+    from vivit_b200 import EigvalshComputation
+
+    model, loss, x, y = problem.make(torch.float64)
+    groups = grouping(model)
+    comp = EigvalshComputation(subsampling=sub)
+    run_backward(model, loss, x, y, [comp.get_extension()], comp.get_extension_hook(groups))
+    want = ref.eigvalsh(model, loss, x, y, groups, subsampling=sub)
+    for g, w in zip(groups, want):
+        close(comp.get_result(g), w)
+
+
+@pytest.mark.parametrize("grouping", GROUPINGS, ids=GROUPING_IDS)
+@pytest.mark.parametrize("sub", SUBS, ids=["full", "sub10"])
+@pytest.mark.parametrize("problem", PROBLEMS, ids=IDS)
+def test_eigh_matches_oracle_and_ground_truth(problem, sub, grouping):
+    from vivit_b200 import EighComputation
+
+    model, loss, x, y = problem.make(torch.float64)
+    groups = grouping(model, criterion=keep_nonzero)
+    comp = EighComputation(subsampling=sub)
+    run_backward(model, loss, x, y, comp.get_extensions(), comp.get_extension_hook(groups))
+    want = ref.eigh(model, loss, x, y, groups, subsampling=sub)
+    truth = AutogradGGN(model, loss, x, y)
+    for g, (w_evals, w_evecs) in zip(groups, want):
+        evals, evecs = comp.get_result(g)
+        close(evals, w_evals)
+        assert [e.shape for e in evecs] == [(evals.numel(), *p.shape) for p in g["params"]]
+        # eigenvectors up to sign: compare projectors  e e^T
+        flat = torch.cat([e.flatten(1) for e in evecs], 1)
+        wflat = torch.cat([e.flatten(1) for e in w_evecs], 1)
+        close(flat.t() @ flat, wflat.t() @ wflat, 1e-6, 1e-9)
+        Ge = truth.ggn_mat_prod(g["params"], evecs, sub)
+        for a, e in zip(Ge, evecs):
+            close(a, torch.einsum("i,i...->i...", evals, e), 1e-6, 1e-9)
+    for p in model.parameters():
+        assert not hasattr(p, "vivit_ggn_exact")  # savefields are freed (eigh.py:270)
+
+
+@pytest.mark.parametrize("k", [1, 10])
+@pytest.mark.parametrize("sub_ggn", [None, [0, 1]], ids=["ggn-full", "ggn-01"])
+@pytest.mark.parametrize("sub_grad", [None, [0, 1]], ids=["grad-full", "grad-01"])
+@pytest.mark.parametrize("grouping", GROUPINGS, ids=GROUPING_IDS)
+@pytest.mark.parametrize("problem", PROBLEMS, ids=IDS)
+def test_optim_computations_match_oracle(problem, grouping, sub_grad, sub_ggn, k):
+    from vivit_b200 import DirectionalDampedNewtonComputation, DirectionalDerivativesComputation
+
+    model, loss, x, y = problem.make(torch.float64)
+    groups = grouping(model, criterion=make_top_k(k), damping=constant_damping(1.0))
+    comp = DirectionalDerivativesComputation(subsampling_grad=sub_grad, subsampling_ggn=sub_ggn)
+    run_backward(model, loss, x, y, comp.get_extensions(), comp.get_extension_hook(groups))
+    want = ref.directional_derivatives(model, loss, x, y, groups, sub_grad, sub_ggn)
+    for g, (wg, wl) in zip(groups, want):
+        gam, lam = comp.get_result(g)
+        close(gam.abs(), wg.abs(), 1e-7, 1e-10)
+        close(lam, wl, 1e-7, 1e-10)
+    newton = DirectionalDampedNewtonComputation(subsampling_grad=sub_grad, subsampling_ggn=sub_ggn)
+    run_backward(model, loss, x, y, newton.get_extensions(), newton.get_extension_hook(groups))
+    want = ref.directional_damped_newton(model, loss, x, y, groups, sub_grad, sub_ggn)
+    for g, w in zip(groups, want):
+        steps = newton.get_result(g)
+        assert [s.shape for s in steps] == [p.shape for p in g["params"]]
+        for s, t in zip(steps, w):
+            close(s, t, 1e-7, 1e-10)
+    for p in model.parameters():
+        assert not hasattr(p, "sqrt_ggn_exact") and not hasattr(p, "grad_batch")
+
+
+@pytest.mark.parametrize("problem", PROBLEMS[:2], ids=IDS[:2])
+def test_mc_computations_on_pinned_samples(problem):
+    """MC factor with the class ids pinned on both sides."""
+    from vivit_b200 import DirectionalDampedNewtonComputation, EighComputation
+
+    model, loss, x, y = problem.make(torch.float64)
+    sub = [0, 2]
+    with torch.no_grad():
+        ids = ref.sample_ce_classes(model(x), sub, 1)
+    groups = [{"params": list(model.parameters()), "criterion": make_top_k(2), "damping": constant_damping(1.0)}]
+    comp = EighComputation(subsampling=sub, mc_samples=1)
+    comp._mc_state = ids
+    run_backward(model, loss, x, y, comp.get_extensions(), comp.get_extension_hook(groups))
+    (w_evals, _), = ref.eigh(model, loss, x, y, groups, subsampling=sub, mc_samples=1, mc_state=ids)
+    close(comp.get_result(groups[0])[0], w_evals)
+    newton = DirectionalDampedNewtonComputation(subsampling_ggn=sub, mc_samples_ggn=1)
+    newton._mc_state = ids
+    run_backward(model, loss, x, y, newton.get_extensions(), newton.get_extension_hook(groups))
+    (want,) = ref.directional_damped_newton(model, loss, x, y, groups, None, sub, 1, ids)
+    for s, t in zip(newton.get_result(groups[0]), want):
+        close(s, t, 1e-7, 1e-10)
+
+
+@pytest.mark.parametrize("problem", PROBLEMS + [PROBLEM_SUM], ids=IDS + ["mlp-ce-sum"])
+def test_savefield_closures_and_materialised_extensions(problem):
+    """Lower-level functional API and the [BackPACK]-shaped tensors."""
+    from vivit_b200 import BatchGrad, SqrtGGNExact, ViViTGGNExact
+
+    model, loss, x, y = problem.make(torch.float64)
+    sub = [0, 0, 1] if x.shape[0] >= 2 else None
+    run_backward(model, loss, x, y, [ViViTGGNExact(subsampling=sub), SqrtGGNExact(subsampling=sub), BatchGrad()], None)
+    sweep = ref.backward_sweep(model, loss, x, y, subsampling_ggn=sub, want_vivit=True, want_sqrt_ggn=True, want_grad_batch=True)
+    torch.manual_seed(3)
+    for p in model.parameters():
+        close(p.sqrt_ggn_exact, sweep.sqrt_ggn[id(p)])
+        close(p.grad_batch, sweep.grad_batch[id(p)])
+        cl, want = p.vivit_ggn_exact, sweep.vivit[id(p)]
+        close(cl["gram_mat"](), want["gram_mat"]())
+        C, N = p.sqrt_ggn_exact.shape[:2]
+        mat = torch.rand(3, C, N, dtype=torch.float64)
+        close(cl["V_mat_prod"](mat), want["V_mat_prod"](mat))
+        pm = torch.rand(4, *p.shape, dtype=torch.float64)
+        close(cl["V_t_mat_prod"](pm), want["V_t_mat_prod"](pm))
+
+
+def test_hook_fires_group_when_last_param_arrives():
+    """Per-layer groups finish layer by layer, a full-network group only at the first layer
+    (vivit/utils/hooks.py:309-330)."""
+    from vivit_b200 import EigvalshComputation, backpack, extend
+
+    torch.manual_seed(0)
+    model = extend(nn.Sequential(nn.Linear(5, 4), nn.ReLU(), nn.Linear(4, 3)).double())
+    loss_fn = extend(nn.CrossEntropyLoss())
+    x, y = torch.rand(4, 5, dtype=torch.float64), torch.randint(0, 3, (4,))
+    layers = [model[0], model[2]]
+    groups = [{"params": list(l.parameters())} for l in layers]
+    comp = EigvalshComputation()
+    hook = comp.get_extension_hook(groups)
+    seen = []
+
+    def spy(module):
+        hook(module)
+        seen.append((type(module).__name__, [id(g) in comp._evals for g in groups]))
+
+    with backpack(comp.get_extension(), extension_hook=spy):
+        loss_fn(model(x), y).backward()
+    names = [n for n, _ in seen]
+    assert names == ["CrossEntropyLoss", "Linear", "ReLU", "Linear"]
+    assert seen[1][1] == [False, True] and seen[3][1] == [True, True]
+
+
+def test_error_contract():
+    from vivit_b200 import (
+        DirectionalDampedNewtonComputation,
+        DirectionalDerivativesComputation,
+        EighComputation,
+        EigvalshComputation,
+        ViViTGGNExact,
+        backpack,
+        extend,
+    )
+
+    for cls in (EigvalshComputation, EighComputation, DirectionalDerivativesComputation, DirectionalDampedNewtonComputation):
+        with pytest.raises(KeyError):
+            cls().get_result({"params": []})  # test_eigh.py:179-184 et al.
+    with pytest.raises(ValueError):
+        EighComputation(subsampling=[0, 0])
+    with pytest.raises(ValueError):
+        DirectionalDerivativesComputation(subsampling_ggn=[1, 1])
+    with pytest.raises(AssertionError):
+        DirectionalDampedNewtonComputation(mc_samples_ggn=2)
+    p = nn.Parameter(torch.zeros(2))
+    with pytest.raises(ValueError):
+        EighComputation().get_extension_hook([{"params": [p]}])  # no criterion
+    with pytest.raises(ValueError):
+        EigvalshComputation().get_extension_hook([{"criterion": keep_all}])  # no params
+    with pytest.raises(ValueError):
+        EigvalshComputation().get_extension_hook([{"params": [p]}, {"params": [p]}])
+    with pytest.raises(ValueError):
+        DirectionalDampedNewtonComputation().get_extension_hook([{"params": [p], "criterion": keep_all}])
+    with pytest.raises(ValueError):
+        backpack(ViViTGGNExact)  # class instead of instance
+    model = extend(nn.Sequential(nn.Linear(3, 2), nn.Softplus()))
+    loss_fn = extend(nn.CrossEntropyLoss())
+    with pytest.raises(NotImplementedError):
+        with backpack(ViViTGGNExact()):
+            loss_fn(model(torch.rand(2, 3)), torch.tensor([0, 1])).backward()
+
+
+def test_small_eigenvalue_warning():
+    from vivit_b200 import EighComputation
+
+    model, loss, x, y = PROBLEMS[0].make(torch.float64)
+    groups = [{"params": list(model.parameters()), "criterion": keep_all}]
+    comp = EighComputation()
+    with pytest.warns(UserWarning, match="small eigenvalues"):
+        run_backward(model, loss, x, y, comp.get_extensions(), comp.get_extension_hook(groups))
+    comp = EighComputation(warn_small_eigvals=0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        run_backward(model, loss, x, y, comp.get_extensions(), comp.get_extension_hook(groups))
+
+
+def test_no_context_no_side_effects():
+    from vivit_b200 import extend
+
+    model = extend(nn.Linear(3, 2))
+    model(torch.rand(2, 3)).sum().backward()
+    assert not hasattr(model.weight, "vivit_ggn_exact")

@@ -1,0 +1,365 @@
+"""Extensions of the native backprop engine: the sqrt-GGN factor and per-sample gradients.
+
+Public classes mirror what the reference hands to ``with backpack(...)``:
+
+* ``ViViTGGNExact`` / ``ViViTGGNMC`` (``vivit/extensions/secondorder/vivit/__init__.py:136-181``):
+  per parameter, ``param.vivit_ggn_{exact,mc}`` = dict of closures ``gram_mat``,
+  ``V_mat_prod``, ``V_t_mat_prod``;
+* ``SqrtGGNExact`` / ``SqrtGGNMC`` and ``BatchGrad`` ([BackPACK], used by
+  ``vivit/optim/utils.py:8-25`` and ``vivit/optim/directional_derivatives.py:127-132``):
+  ``param.sqrt_ggn_{exact,mc}`` ``[C, N, *p]`` and ``param.grad_batch`` ``[N, *p]``.  With
+  ``lazy=True`` (what the Computations use) the savefield holds a ``Factor`` /
+  ``GradFactor`` object instead of the materialised tensor.
+
+Module coverage: ``CrossEntropyLoss``, ``MSELoss``, ``Linear``, ``Conv2d``, ``ReLU``,
+``Sigmoid``, ``Tanh``, ``MaxPool2d``, ``AvgPool2d``, ``Flatten``, ``Dropout``, ``Identity``.
+Anything else raises ``NotImplementedError`` (the reference's ``fail_mode="ERROR"``,
+``__init__.py:83``).
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from vivit_b200 import kernels
+from vivit_b200.factors import DenseFactor, DenseGrad, Factor, LinearWeightFactor, LinearWeightGrad
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+class Extension:
+    """Base class: dispatches a module to its handler and owns a savefield name."""
+
+    savefield: str = ""
+
+    def __init__(self, subsampling: Optional[List[int]] = None):
+        self._subsampling = None if subsampling is None else list(subsampling)
+        self._sub_cache: Dict[torch.device, Tensor] = {}
+        self._shard = None  # (rank, world): this rank owns a dim-0 slice of every parameter
+
+    def _own(self, size: int):
+        """``[lo, hi)`` of a parameter's leading dimension owned by this rank (``vivit_b200.dist``)."""
+        if self._shard is None:
+            return 0, size
+        from vivit_b200.dist import shard_bounds
+
+        return shard_bounds(size, *self._shard)
+
+    def get_subsampling(self) -> Optional[List[int]]:
+        return self._subsampling
+
+    def _sub_index(self, device) -> Optional[Tensor]:
+        if self._subsampling is None:
+            return None
+        if device not in self._sub_cache:
+            self._sub_cache[device] = torch.tensor(self._subsampling, dtype=torch.int64, device=device)
+        return self._sub_cache[device]
+
+    def _subsample(self, t: Tensor) -> Tensor:
+        """``backpack.utils.subsampling.subsample`` along the batch axis."""
+        idx = self._sub_index(t.device)
+        return t if idx is None else t.index_select(0, idx)
+
+    def _begin(self) -> None:  # called when a backpack context is entered
+        pass
+
+    def _apply(self, module: nn.Module, g_out: Tensor) -> None:
+        raise NotImplementedError
+
+    @staticmethod
+    def _unsupported(ext, module):
+        raise NotImplementedError(f"Extension {type(ext).__name__} does not support {type(module)}")
+
+
+def _trainable(module: nn.Module, name: str):
+    p = getattr(module, name, None)
+    return p if isinstance(p, nn.Parameter) and p.requires_grad else None
+
+
+# --------------------------------------------------------------------------
+# second-order: symmetric factor of the GGN
+# --------------------------------------------------------------------------
+
+
+class _SqrtFactorExtension(Extension):
+    """Back-propagates ``S`` (``[V, N_sub, *features]``) and leaves a factor per parameter."""
+
+    def __init__(self, savefield: str, subsampling, mc_samples: int, lazy: bool, closures: bool):
+        super().__init__(subsampling)
+        self.savefield = savefield
+        self._field = "_vvt_S_" + savefield  # attribute carrying S on activations
+        self._mc_samples = mc_samples
+        self._lazy = lazy
+        self._closures = closures
+        self.mc_state: Optional[Tensor] = None  # tests may pin the random draw here
+
+    def get_loss_hessian_strategy(self) -> str:
+        return "sampling" if self._mc_samples else "exact"
+
+    def get_num_mc_samples(self) -> int:
+        return self._mc_samples
+
+    # ---- engine entry ---------------------------------------------------------
+    def _apply(self, module: nn.Module, g_out: Tensor) -> None:
+        if isinstance(module, (nn.CrossEntropyLoss, nn.MSELoss)):
+            S = self._loss_factor(module)
+            setattr(module.input0, self._field, S)
+            return
+        out = module.output
+        S = getattr(out, self._field, None)
+        if S is None:
+            raise RuntimeError(
+                f"{type(self).__name__}: no back-propagated factor at the output of {module}. "
+                "Extend the loss function too and call it on the model output."
+            )
+        delattr(out, self._field)
+        handler = _FACTOR_HANDLERS.get(type(module))
+        if handler is None:
+            for cls, h in _FACTOR_HANDLERS.items():
+                if isinstance(module, cls):
+                    handler = h
+                    break
+        if handler is None:
+            self._unsupported(self, module)
+        need_in = isinstance(module.input0, Tensor) and module.input0.requires_grad
+        S_in = handler(self, module, S, need_in)
+        if need_in and S_in is not None:
+            setattr(module.input0, self._field, S_in)
+
+    # ---- loss ---------------------------------------------------------------------
+    def _loss_factor(self, module) -> Tensor:
+        out = module.input0.detach()
+        mean = module.reduction == "mean"
+        if module.reduction not in ("mean", "sum"):
+            raise NotImplementedError("loss reduction must be 'mean' or 'sum'")
+        if out.dim() != 2:
+            raise NotImplementedError("loss factors support [N, C] model outputs only")
+        sub = self._sub_index(out.device)
+        n_total, C = out.shape
+        n_sub = n_total if sub is None else sub.numel()
+        M = self._mc_samples
+        if isinstance(module, nn.CrossEntropyLoss):
+            if M == 0:
+                return kernels.loss_sqrt_hessian_ce(out, sub, mean)
+            ids = self.mc_state
+            if ids is None:
+                # the one random draw of the MC factor, with torch's generator as in [BackPACK]
+                probs = self._subsample(F.softmax(out, dim=1))
+                ids = torch.multinomial(probs, M, replacement=True).t().contiguous()
+            return kernels.loss_sqrt_hessian_ce_mc(out, sub, ids.to(out.device), mean)
+        scale = math.sqrt(2.0) / (math.sqrt(out.numel()) if mean else 1.0)
+        if M == 0:
+            return kernels.loss_sqrt_hessian_mse(n_sub, C, scale, out)
+        normal = self.mc_state
+        if normal is None:
+            normal = torch.randn(M, n_sub, C, dtype=out.dtype, device=out.device)
+        return kernels.scale_(normal.to(out).clone(), scale / math.sqrt(M))
+
+    # ---- parameters ---------------------------------------------------------------
+    def _save(self, param: nn.Parameter, factor: Factor) -> None:
+        if self._closures:
+            value = {
+                "V_mat_prod": lambda mat, f=factor: f.backtransform(mat.reshape(mat.shape[0], -1), None),
+                "V_t_mat_prod": lambda mat, f=factor: f.vt_mat_prod(mat),
+                "gram_mat": lambda f=factor: f.gram_mat(),
+                "_factor": factor,
+            }
+        elif self._lazy:
+            value = factor
+        else:
+            value = factor.materialize()
+        setattr(param, self.savefield, value)
+
+
+def _linear_check(module: nn.Linear):
+    if module.input0.dim() != 2:
+        # the reference falls back to a materialised factor here (linear.py:26-27,38-39);
+        # SURVEY 8(f3) lists it as a follow-up
+        raise NotImplementedError("Linear with additional input dimensions is not supported yet")
+
+
+def _factor_linear(ext: _SqrtFactorExtension, module: nn.Linear, S: Tensor, need_in: bool):
+    _linear_check(module)
+    z = ext._subsample(module.input0.detach())
+    w, b = _trainable(module, "weight"), _trainable(module, "bias")
+    lo, hi = ext._own(S.shape[-1])
+    S_own = S if hi - lo == S.shape[-1] else S[..., lo:hi].contiguous()
+    if b is not None:  # bias first, as [BackPACK] does (params=["bias", "weight"], linear.py:24)
+        ext._save(b, DenseFactor(S_own, (hi - lo,)))
+    if w is not None:
+        ext._save(w, LinearWeightFactor(S_own, z.contiguous()))
+    return kernels.sqrt_backprop_linear(S, module.weight.detach()) if need_in else None
+
+
+def _conv_check(module: nn.Conv2d):
+    if module.groups != 1:
+        raise NotImplementedError("grouped Conv2d is not supported")
+    if module.padding_mode != "zeros" or isinstance(module.padding, str):
+        raise NotImplementedError("Conv2d needs numeric zero padding")
+
+
+def _factor_conv2d(ext: _SqrtFactorExtension, module: nn.Conv2d, S: Tensor, need_in: bool):
+    _conv_check(module)
+    x = ext._subsample(module.input0.detach())
+    w, b = _trainable(module, "weight"), _trainable(module, "bias")
+    geom = (_pair(module.stride), _pair(module.padding), _pair(module.dilation))
+    lo, hi = ext._own(S.shape[2])
+    S_own = S if hi - lo == S.shape[2] else S[:, :, lo:hi].contiguous()
+    if b is not None:
+        ext._save(b, DenseFactor(kernels.v_emit_bias(S_own), (hi - lo,)))
+    if w is not None:
+        Vt = kernels.v_emit_conv2d(S_own, x, _pair(module.kernel_size), *geom)
+        ext._save(w, DenseFactor(Vt, (hi - lo, *w.shape[1:])))
+    if not need_in:
+        return None
+    return kernels.sqrt_backprop_conv2d(S, module.weight.detach(), tuple(x.shape[2:]), *geom)
+
+
+def _factor_act(act, use_output):
+    def handler(ext, module, S, need_in):
+        if not need_in:
+            return None
+        ref = module.output if use_output else module.input0
+        return kernels.sqrt_backprop_elementwise(S, ext._subsample(ref.detach()), act)
+
+    return handler
+
+
+def _factor_dropout(ext, module: nn.Dropout, S, need_in):
+    if not module.training or module.p == 0.0:
+        return S
+    ref = ext._subsample(module.output.detach())
+    return kernels.sqrt_backprop_elementwise(S, ref, kernels.ACT_DROPOUT, 1.0 / (1.0 - module.p))
+
+
+def _factor_flatten(ext, module, S, need_in):
+    x = module.input0
+    return S.reshape(S.shape[0], S.shape[1], *x.shape[1:])
+
+
+def _factor_identity(ext, module, S, need_in):
+    return S
+
+
+def _factor_maxpool2d(ext, module: nn.MaxPool2d, S, need_in):
+    if not need_in:
+        return None
+    x = ext._subsample(module.input0.detach())
+    k, s = _pair(module.kernel_size), _pair(module.stride if module.stride is not None else module.kernel_size)
+    p, d = _pair(module.padding), _pair(module.dilation)
+    # arg-max positions of the forward pass (index plumbing; [BackPACK] recomputes them the same way)
+    _, idx = F.max_pool2d(x, k, s, p, d, module.ceil_mode, return_indices=True)
+    return kernels.sqrt_backprop_maxpool2d(S, idx, tuple(x.shape[2:]), k, s, p, d)
+
+
+def _factor_avgpool2d(ext, module: nn.AvgPool2d, S, need_in):
+    if not need_in:
+        return None
+    if module.ceil_mode or not module.count_include_pad or module.divisor_override is not None:
+        raise NotImplementedError("AvgPool2d: ceil_mode / count_include_pad=False / divisor_override")
+    x = module.input0
+    k = _pair(module.kernel_size)
+    s = _pair(module.stride if module.stride is not None else module.kernel_size)
+    return kernels.sqrt_backprop_avgpool2d(S, tuple(x.shape[2:]), k, s, _pair(module.padding))
+
+
+_FACTOR_HANDLERS = {
+    nn.Linear: _factor_linear,
+    nn.Conv2d: _factor_conv2d,
+    nn.ReLU: _factor_act(kernels.ACT_RELU, use_output=False),
+    nn.Sigmoid: _factor_act(kernels.ACT_SIGMOID, use_output=True),
+    nn.Tanh: _factor_act(kernels.ACT_TANH, use_output=True),
+    nn.Dropout: _factor_dropout,
+    nn.Flatten: _factor_flatten,
+    nn.Identity: _factor_identity,
+    nn.MaxPool2d: _factor_maxpool2d,
+    nn.AvgPool2d: _factor_avgpool2d,
+}
+
+
+class ViViTGGNExact(_SqrtFactorExtension):
+    """Functional access to the exact GGN factor (``__init__.py:136-152``)."""
+
+    def __init__(self, subsampling: List[int] = None):
+        super().__init__("vivit_ggn_exact", subsampling, 0, lazy=True, closures=True)
+
+
+class ViViTGGNMC(_SqrtFactorExtension):
+    """Functional access to the MC-sampled GGN factor (``__init__.py:155-181``)."""
+
+    def __init__(self, mc_samples: int = 1, subsampling: List[int] = None):
+        super().__init__("vivit_ggn_mc", subsampling, mc_samples, lazy=True, closures=True)
+
+
+class SqrtGGNExact(_SqrtFactorExtension):
+    """[BackPACK] ``SqrtGGNExact``: ``param.sqrt_ggn_exact`` of shape ``[C, N, *param.shape]``."""
+
+    def __init__(self, subsampling: List[int] = None, lazy: bool = False):
+        super().__init__("sqrt_ggn_exact", subsampling, 0, lazy=lazy, closures=False)
+
+
+class SqrtGGNMC(_SqrtFactorExtension):
+    """[BackPACK] ``SqrtGGNMC``: ``param.sqrt_ggn_mc`` of shape ``[M, N, *param.shape]``."""
+
+    def __init__(self, mc_samples: int = 1, subsampling: List[int] = None, lazy: bool = False):
+        super().__init__("sqrt_ggn_mc", subsampling, mc_samples, lazy=lazy, closures=False)
+
+
+# --------------------------------------------------------------------------
+# first-order: per-sample gradients
+# --------------------------------------------------------------------------
+
+
+class BatchGrad(Extension):
+    """[BackPACK] ``BatchGrad``: ``param.grad_batch[n] = d loss / d param`` of sample ``n``
+    (carries the ``1/N`` of a mean reduction), optionally sub-sampled."""
+
+    savefield = "grad_batch"
+
+    def __init__(self, subsampling: List[int] = None, lazy: bool = False):
+        super().__init__(subsampling)
+        self._lazy = lazy
+
+    def _save(self, param, grad):
+        setattr(param, self.savefield, grad if self._lazy else grad.materialize())
+
+    def _apply(self, module: nn.Module, g_out: Tensor) -> None:
+        if isinstance(module, nn.Linear):
+            w, b = _trainable(module, "weight"), _trainable(module, "bias")
+            if w is None and b is None:
+                return
+            _linear_check(module)
+            g = self._subsample(g_out.detach())
+            lo, hi = self._own(g.shape[-1])
+            g = g[:, lo:hi].contiguous()
+            z = self._subsample(module.input0.detach())
+            if b is not None:
+                self._save(b, DenseGrad(g, (hi - lo,)))
+            if w is not None:
+                self._save(w, LinearWeightGrad(g, z.contiguous()))
+        elif isinstance(module, nn.Conv2d):
+            w, b = _trainable(module, "weight"), _trainable(module, "bias")
+            if w is None and b is None:
+                return
+            _conv_check(module)
+            g = self._subsample(g_out.detach())
+            lo, hi = self._own(g.shape[1])
+            g = g[:, lo:hi].contiguous()[None]  # one "class": [1, N, Co, Ho, Wo]
+            x = self._subsample(module.input0.detach())
+            if b is not None:
+                self._save(b, DenseGrad(kernels.v_emit_bias(g)[0], (hi - lo,)))
+            if w is not None:
+                gw = kernels.v_emit_conv2d(
+                    g, x, _pair(module.kernel_size), _pair(module.stride), _pair(module.padding),
+                    _pair(module.dilation),
+                )[0]
+                self._save(w, DenseGrad(gw, (hi - lo, *w.shape[1:])))
+        elif any(p.requires_grad for p in module.parameters(recurse=False)):
+            self._unsupported(self, module)

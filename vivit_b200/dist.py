@@ -1,0 +1,91 @@
+"""Parameter-sharded Gram assembly across the GPUs of one box.
+
+``G = sum_p V_p^T V_p`` and ``V^T g = sum_p V_p^T g_p`` are sums over parameter entries,
+so each rank takes a slice of every parameter's leading (output-channel) dimension,
+assembles a partial Gram from its slice, and the partial Grams are summed with ONE
+all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests).  Everything after the
+all-reduce that lives in Gram space (eigensolver, directional derivatives, Newton
+coefficients) is computed redundantly and deterministically on every rank; results in
+parameter space (eigenvectors, Newton steps) stay sharded along dim 0 unless
+``gather=True``.
+
+The factor back-propagation itself is replicated (activations and ``S`` are
+``O(R x width)``).  Block-diagonal groups need no communication at all; they can be
+assigned to ranks whole (``assign_groups``).
+"""
+
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+
+def shard_bounds(size: int, rank: int, world: int) -> Tuple[int, int]:
+    """``[lo, hi)`` of ``range(size)`` owned by ``rank`` (balanced, contiguous)."""
+    return (size * rank) // world, (size * (rank + 1)) // world
+
+
+class ShardedReduce:
+    """All-reduce plumbing for one process group (``None`` = single process, no-ops)."""
+
+    def __init__(self, process_group=None, gather: bool = False):
+        self.group = process_group
+        self.gather = gather
+        if process_group is None:
+            self.rank, self.world = 0, 1
+        else:
+            import torch.distributed as dist
+
+            self.rank = dist.get_rank(process_group)
+            self.world = dist.get_world_size(process_group)
+
+    @property
+    def shard(self) -> Optional[Tuple[int, int]]:
+        return None if self.world == 1 else (self.rank, self.world)
+
+    def allreduce_(self, *tensors: Tensor) -> None:
+        """Sum the given tensors over ranks, in place, with a single collective."""
+        if self.world == 1 or not tensors:
+            return
+        import torch.distributed as dist
+
+        if len(tensors) == 1:
+            dist.all_reduce(tensors[0], group=self.group)
+            return
+        flat = torch.cat([t.reshape(-1) for t in tensors])
+        dist.all_reduce(flat, group=self.group)
+        offset = 0
+        for t in tensors:
+            t.copy_(flat[offset : offset + t.numel()].reshape(t.shape))
+            offset += t.numel()
+
+    def allgather_dim0(self, t: Tensor, full_size: int) -> Tensor:
+        """Concatenate dim-0 shards of a parameter-shaped tensor (leading stack axis kept)."""
+        if self.world == 1:
+            return t
+        import torch.distributed as dist
+
+        # shards may differ by one row: pad to the largest
+        sizes = [shard_bounds(full_size, r, self.world) for r in range(self.world)]
+        width = max(hi - lo for lo, hi in sizes)
+        pad_shape = list(t.shape)
+        pad_shape[1] = width
+        buf = torch.zeros(pad_shape, dtype=t.dtype, device=t.device)
+        buf[:, : t.shape[1]] = t
+        out = [torch.empty_like(buf) for _ in range(self.world)]
+        dist.all_gather(out, buf, group=self.group)
+        return torch.cat([o[:, : hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=1)
+
+
+def assign_groups(costs: Sequence[float], world: int) -> List[int]:
+    """Greedy longest-processing-time assignment of independent (block-diagonal) groups
+    to ranks; returns the owning rank of each group."""
+    loads = [0.0] * world
+    owner = [0] * len(costs)
+    for i in sorted(range(len(costs)), key=lambda i: -costs[i]):
+        r = min(range(world), key=lambda r: loads[r])
+        owner[i] = r
+        loads[r] += costs[i]
+    return owner

@@ -1,0 +1,6 @@
+"""GGN spectra during back-propagation."""
+
+from vivit_b200.linalg.eigh import EighComputation
+from vivit_b200.linalg.eigvalsh import EigvalshComputation
+
+__all__ = ["EighComputation", "EigvalshComputation"]

@@ -1,0 +1,123 @@
+"""GGN eigenvalues during back-propagation (``vivit/linalg/eigvalsh.py``)."""
+
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, List, Optional
+
+import torch
+from torch import Tensor
+from torch.nn import Module, Parameter
+
+from vivit_b200 import kernels
+from vivit_b200.linalg.utils import get_hook_store_batch_size, get_vivit_extension
+from vivit_b200.utils import delete_savefield
+from vivit_b200.utils.checks import check_key_exists, check_subsampling_unique, check_unique_params
+from vivit_b200.utils.hooks import ParameterGroupsHook
+
+
+class EigvalshComputation:
+    """Provide the extension and hook to compute GGN eigenvalues
+    (``vivit/linalg/eigvalsh.py:20``).  The loss must use ``reduction='mean'``."""
+
+    def __init__(
+        self,
+        subsampling: Optional[List[int]] = None,
+        mc_samples: int = 0,
+        verbose: bool = False,
+        process_group=None,
+    ):
+        check_subsampling_unique(subsampling)
+        self._subsampling = subsampling
+        self._mc_samples = mc_samples
+        self._verbose = verbose
+        self._dist = _make_dist(process_group)
+        self._savefield = self.get_extension().savefield
+        self._mc_state = None  # tests may pin the MC draw
+        # filled during the backward pass, keys are group ids
+        self._batch_size: Dict[int, int] = {}
+        self._evals: Dict[int, Tensor] = {}
+
+    def get_result(self, group: Dict) -> Tensor:
+        """Ascending Gram eigenvalues of the group's GGN block (``eigvalsh.py:53-68``)."""
+        try:
+            return self._evals[id(group)]
+        except KeyError as e:
+            raise KeyError("No results available for this group") from e
+
+    def get_extension(self):
+        """Extension for the ``with backpack(...)`` context (``eigvalsh.py:70-77``)."""
+        ext = get_vivit_extension(self._subsampling, self._mc_samples, self._dist.shard)
+        ext.mc_state = getattr(self, "_mc_state", None)
+        return ext
+
+    def get_extensions(self):
+        """Plural form named by the north star; a one-element list."""
+        return [self.get_extension()]
+
+    def get_extension_hook(self, param_groups: List[Dict]) -> Callable[[Module], None]:
+        """Hook computing the eigenvalues during back-propagation (``eigvalsh.py:79-131``)."""
+        self._check_param_groups(param_groups)
+        hook_store_batch_size = get_hook_store_batch_size(
+            param_groups, self._batch_size, verbose=self._verbose
+        )
+        savefield, verbose = self._savefield, self._verbose
+        subsampling, batch_sizes, evals, dist = self._subsampling, self._batch_size, self._evals, self._dist
+
+        def param_computation(hook: ParameterGroupsHook, param: Parameter):
+            # eager: evaluate this parameter's Gram and drop its factor (eigvalsh.py:145-158)
+            factor = getattr(param, savefield)["_factor"]
+            delete_savefield(param, savefield, verbose=verbose)
+            return factor
+
+        def accumulate(hook: ParameterGroupsHook, existing, update):
+            # (eigvalsh.py:170-183): G_existing + G_update, done in place on one buffer
+            if not isinstance(existing, Tensor):
+                existing = _accumulate_gram(None, existing)
+            return _accumulate_gram(existing, update)
+
+        def group_hook(hook: ParameterGroupsHook, accumulation, group: Dict):
+            gid = id(group)
+            if verbose:
+                print(f"Group {gid}: Delete 'batch_size'")
+            batch_size = batch_sizes.pop(gid)
+            gram = accumulation if isinstance(accumulation, Tensor) else _accumulate_gram(None, accumulation)
+            if subsampling is not None:  # eigvalsh.py:218-219
+                kernels.scale_(gram, batch_size / len(subsampling))
+            dist.allreduce_(gram)
+            gram_evals, _ = kernels.syevj(gram, vectors=False)  # eigvalsh.py:221
+            if verbose:
+                print(f"Group {gid}: Store 'gram_evals'")
+            evals[gid] = gram_evals
+
+        hook = ParameterGroupsHook.from_functions(param_groups, param_computation, group_hook, accumulate)
+
+        def extension_hook(module: Module) -> None:
+            if verbose:
+                print(f"Extension hook on module {id(module)} {module}")
+            hook_store_batch_size(module)
+            hook(module)
+
+        if verbose:
+            print("ID map groups → params")
+            for group in param_groups:
+                print(f"{id(group)} → {[id(p) for p in group['params']]}")
+        return extension_hook
+
+    @staticmethod
+    def _check_param_groups(param_groups: List[Dict]) -> None:
+        check_key_exists(param_groups, "params")
+        check_unique_params(param_groups)
+
+
+def _accumulate_gram(gram: Optional[Tensor], factor) -> Tensor:
+    if gram is None:
+        like = factor._like()
+        gram = torch.zeros(factor.R, factor.R, dtype=like.dtype, device=like.device)
+    factor.gram_accum(gram)
+    return gram
+
+
+def _make_dist(process_group):
+    from vivit_b200.dist import ShardedReduce
+
+    return ShardedReduce(process_group)
