@@ -1,0 +1,528 @@
+#!/usr/bin/env python
+"""Benchmark of the low-rank GGN hot path (BASELINE.json: "ms per GGN eigh step + Gram TFLOP/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--dtype f32]
+    python bench.py --impl reference ...      # the reference's algorithm on the host cores
+
+A *step* is one pass of the hot path over one batch of synthetic input.  The default
+workload is BASELINE ``configs[1]``: cifar10_3c3d, N=128, C=10, exact GGN --
+``EighComputation`` (top-10 eigenpairs) followed by ``DirectionalDerivativesComputation``
+(top-10 directions): two forward/backward passes with extension + hook through
+``get_result``, as in the reference.
+
+Prints ONE JSON line (rank 0).  ``value`` is device-timed with inputs resident in HBM;
+``e2e`` is the same step through the public API with host buffers (pinned H2D of the batch,
+D2H of every result) inside the timed region.  At N>1 the parameter dimension is sharded
+over the ranks (``process_group=``) and the partial Grams are summed with one NCCL
+all-reduce: the total work is fixed, so ``scaling`` is "strong".
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+from torch import nn  # noqa: E402
+
+METRIC = "ms_per_ggn_curvature_step"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+# --------------------------------------------------------------------------
+# workloads (BASELINE.json configs; model shapes from DeepOBS)
+# --------------------------------------------------------------------------
+
+
+def mlp_c1():
+    return nn.Sequential(nn.Linear(784, 64), nn.ReLU(), nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 10))
+
+
+def cnn_3c3d():
+    """cifar10_3c3d: tf 'same' 3x3/2 pooling == ceil-mode pooling on post-ReLU maps."""
+    return nn.Sequential(
+        nn.Conv2d(3, 64, 5), nn.ReLU(), nn.MaxPool2d(3, 2, ceil_mode=True),
+        nn.Conv2d(64, 96, 3), nn.ReLU(), nn.MaxPool2d(3, 2, ceil_mode=True),
+        nn.Conv2d(96, 128, 3, padding=1), nn.ReLU(), nn.MaxPool2d(3, 2, ceil_mode=True),
+        nn.Flatten(), nn.Linear(1152, 512), nn.ReLU(), nn.Linear(512, 256), nn.ReLU(),
+        nn.Linear(256, 10),
+    )
+
+
+def allcnnc():
+    """cifar100_allcnnc without dropout: 9 convolutions + global average pooling."""
+    def c(i, o, k, s=1, p=0):
+        return [nn.Conv2d(i, o, k, stride=s, padding=p), nn.ReLU()]
+    layers = (
+        c(3, 96, 3, p=1) + c(96, 96, 3, p=1) + c(96, 96, 3, s=2, p=1)
+        + c(96, 192, 3, p=1) + c(192, 192, 3, p=1) + c(192, 192, 3, s=2, p=1)
+        + c(192, 192, 3) + c(192, 192, 1) + c(192, 100, 1)
+    )
+    return nn.Sequential(*layers, nn.AvgPool2d(6), nn.Flatten())
+
+
+def mlp_c4():
+    return nn.Sequential(
+        nn.Linear(784, 4096), nn.ReLU(), nn.Linear(4096, 4096), nn.ReLU(),
+        nn.Linear(4096, 4096), nn.ReLU(), nn.Linear(4096, 10),
+    )
+
+
+def top_k(k):
+    return lambda ev: list(range(max(0, ev.numel() - k), ev.numel()))
+
+
+def const_damping(evals, evecs, gammas, lambdas):
+    return torch.ones_like(evals)
+
+
+WORKLOADS = {
+    "c1": dict(name="mlp_784-64-32-10 N=32 C=10 EigvalshComputation exact, one group",
+               model=mlp_c1, n=32, in_shape=(784,), classes=10, calls=("eigvalsh",), grouping="one"),
+    "c2": dict(name="cifar10_3c3d N=128 C=10 EighComputation top-10 + DirectionalDerivativesComputation, exact GGN, one group",
+               model=cnn_3c3d, n=128, in_shape=(3, 32, 32), classes=10, calls=("eigh", "dirderiv"), grouping="one"),
+    "c3": dict(name="cifar100_allcnnc N=128 C=100 mc_samples=1 subsampling_ggn=[0..31] DirectionalDampedNewtonComputation",
+               model=allcnnc, n=128, in_shape=(3, 32, 32), classes=100, calls=("newton",), grouping="one",
+               mc=1, sub_ggn=list(range(32))),
+    "c4": dict(name="mlp_784-4096x3-10 N=512 C=10 EighComputation top-10, per-layer block-diagonal groups",
+               model=mlp_c4, n=512, in_shape=(784,), classes=10, calls=("eigh",), grouping="layer"),
+}
+
+
+def make_groups(model, grouping):
+    extra = {"criterion": top_k(10), "damping": const_damping}
+    if grouping == "one":
+        return [{"params": list(model.parameters()), **extra}]
+    return [{"params": list(m.parameters()), **extra} for m in model if list(m.parameters())]
+
+
+def make_problem(w, dtype):
+    torch.manual_seed(0)
+    model = w["model"]().to(dtype)
+    x = torch.rand(w["n"], *w["in_shape"]).to(dtype)
+    y = torch.randint(0, w["classes"], (w["n"],))
+    return model, x, y
+
+
+# --------------------------------------------------------------------------
+# the step through the public API
+# --------------------------------------------------------------------------
+
+
+class Stepper:
+    def __init__(self, w, dtype, device, process_group=None):
+        from vivit_b200 import extend
+
+        self.w, self.device, self.pg = w, device, process_group
+        model, x, y = make_problem(w, dtype)
+        self.model = extend(model.to(device))
+        self.loss_fn = extend(nn.CrossEntropyLoss())
+        self.groups = make_groups(self.model, w["grouping"])
+        self.x_host, self.y_host = x.pin_memory(), y.pin_memory()
+        self.x, self.y = x.to(device), y.to(device)
+        self.host_out = None
+        self.h2d_bytes = x.numel() * x.element_size() + y.numel() * y.element_size()
+        self.d2h_bytes = 0
+        self.mc_ids = None
+        if w.get("mc"):
+            g = torch.Generator().manual_seed(1)
+            self.mc_ids = torch.randint(0, w["classes"], (w["mc"], len(w["sub_ggn"])), generator=g).to(device)
+
+    def _pass(self, comp, x, y):
+        from vivit_b200 import backpack
+
+        hook = comp.get_extension_hook(self.groups)
+        exts = comp.get_extensions()
+        with backpack(*exts, extension_hook=hook):
+            self.loss_fn(self.model(x), y).backward()
+        for p in self.model.parameters():
+            p.grad = None
+        return [comp.get_result(g) for g in self.groups]
+
+    def run(self, x, y):
+        """One step on device-resident ``x, y``; returns the flat list of result tensors."""
+        import vivit_b200 as vv
+
+        w, out = self.w, []
+        kw = {"process_group": self.pg} if self.pg is not None else {}
+        for call in w["calls"]:
+            if call == "eigvalsh":
+                res = self._pass(vv.EigvalshComputation(**kw), x, y)
+                out += list(res)
+            elif call == "eigh":
+                res = self._pass(vv.EighComputation(**kw), x, y)
+                for evals, evecs in res:
+                    out += [evals, *evecs]
+            elif call == "dirderiv":
+                res = self._pass(vv.DirectionalDerivativesComputation(**kw), x, y)
+                for g, l in res:
+                    out += [g, l]
+            elif call == "newton":
+                comp = vv.DirectionalDampedNewtonComputation(
+                    subsampling_ggn=w.get("sub_ggn"), mc_samples_ggn=w.get("mc", 0), **kw)
+                comp._mc_state = self.mc_ids  # class ids pre-sampled on the host
+                res = self._pass(comp, x, y)
+                for steps in res:
+                    out += list(steps)
+        return out
+
+    def step_device(self):
+        return self.run(self.x, self.y)
+
+    def step_e2e(self):
+        x = self.x_host.to(self.device, non_blocking=True)
+        y = self.y_host.to(self.device, non_blocking=True)
+        out = self.run(x, y)
+        if self.host_out is None:
+            self.host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in out]
+            self.d2h_bytes = sum(t.numel() * t.element_size() for t in out)
+        for h, t in zip(self.host_out, out):
+            h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.host_out
+
+
+# --------------------------------------------------------------------------
+# roofline bookkeeping
+# --------------------------------------------------------------------------
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                p = json.load(f)
+            return {
+                "hbm_gbs": float(p.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"])),
+                "bf16_tflops": float(p.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"])),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 0.0))),
+            }, "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+def algorithmic_work(name, shapes, es):
+    """(kind, amount): algorithmic flops ("tensor") or bytes ("hbm") of one call of a kernel
+    entry point, from its tensor-argument shapes.
+    Symmetric-aware minimum for the Gram kernels, one read of each operand + one write of each
+    result for the bandwidth-bound ones."""
+    prod = lambda s: int(torch.Size(s).numel())  # noqa: E731
+    if name == "gram_dense_accum":
+        (R, _), (_, D) = shapes[0], shapes[1]
+        return "tensor", R * (R + 1) * D
+    if name == "gram_cross_accum":
+        (R, ng), (_, D) = shapes[0], shapes[1]
+        return "tensor", 2 * R * ng * D
+    if name == "gram_linear_accum":
+        (R, _), (C, N, out), (_, n_in) = shapes[0], shapes[1], shapes[2]
+        return "tensor", R * (R + 1) * out + N * (N + 1) * n_in + R * (R + 1) // 2
+    if name == "gram_cross_linear_accum":
+        (R, ng), (C, N, out), (_, n_in) = shapes[0], shapes[1], shapes[2]
+        return "tensor", 2 * R * ng * out + 2 * N * ng * n_in + R * ng
+    if name == "sqrt_backprop_linear":
+        S, W = shapes[0], shapes[1]
+        return "tensor", 2 * (prod(S) // W[0]) * W[0] * W[1]
+    if name == "sqrt_backprop_conv2d":
+        S, W = shapes[0], shapes[1]  # [V,N,Co,Ho,Wo], [Co,Ci,kh,kw]
+        return "tensor", 2 * prod(S) * W[1] * W[2] * W[3]
+    if name == "v_emit_conv2d":
+        S, X = shapes[0], shapes[1]  # [V,N,Co,Ho,Wo], [N,Ci,H,W]; J unknown here -> bytes of S + X only
+        return "hbm", es * (prod(S) + prod(X))
+    if name in ("backtransform_dense", "v_apply_dense"):
+        U, V = shapes[0], shapes[1]
+        K = prod(U) // V[0]
+        return "hbm", es * (prod(V) + prod(U) + K * V[1])
+    if name in ("sqrt_backprop_elementwise", "sqrt_backprop_maxpool2d", "sqrt_backprop_avgpool2d"):
+        return "hbm", es * 2 * prod(shapes[0])
+    if name == "scale_rows_rsqrt":
+        return "hbm", es * 2 * prod(shapes[0])
+    return None, 0
+
+
+def summarize_kernels(records, steps, es, peaks):
+    agg = {}
+    for name, ms, shapes, launches in records:
+        a = agg.setdefault(name, {"ms": 0.0, "calls": 0, "launches": 0, "tensor": 0, "hbm": 0})
+        a["ms"] += ms
+        a["calls"] += 1
+        a["launches"] += launches
+        kind, amount = algorithmic_work(name, shapes, es)
+        if kind:
+            a[kind] += amount
+    total = sum(a["ms"] for a in agg.values()) or 1.0
+    rows = []
+    for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        row = {"kernel": name, "ms_per_step": round(a["ms"] / steps, 4), "share": round(a["ms"] / total, 4),
+               "calls_per_step": a["calls"] / steps, "launches_per_step": a["launches"] / steps}
+        sec = a["ms"] / 1e3
+        if a["tensor"] and sec > 0:
+            row.update(bound="tensor", achieved=round(a["tensor"] / sec / 1e12, 3), unit="TFLOP/s")
+        elif a["hbm"] and sec > 0:
+            row.update(bound="hbm", achieved=round(a["hbm"] / sec / 1e9, 1), unit="GB/s")
+        rows.append(row)
+    return rows
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+
+_CLOCK_FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.proc, self.path = None, f"/tmp/vvt_clocks_{os.getpid()}.csv"
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={_CLOCK_FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+# the reference's algorithm on the host cores (oracle; the one place bench.py runs oracle/)
+# --------------------------------------------------------------------------
+
+
+def reference_step(w, model, x, y):
+    from oracle import reference_path as ref
+
+    loss = nn.CrossEntropyLoss()
+    groups = make_groups(model, w["grouping"])
+    for call in w["calls"]:
+        if call == "eigvalsh":
+            ref.eigvalsh(model, loss, x, y, groups)
+        elif call == "eigh":
+            ref.eigh(model, loss, x, y, groups)
+        elif call == "dirderiv":
+            ref.directional_derivatives(model, loss, x, y, groups)
+        elif call == "newton":
+            ref.directional_damped_newton(model, loss, x, y, groups, None, w.get("sub_ggn"),
+                                          mc_samples_ggn=w.get("mc", 0))
+
+
+def time_reference(w, dtype, steps, warmup, budget_s):
+    """Median ms per step of the oracle on the host cores; stops early once ``budget_s`` of CPU
+    time is spent (each step is the full workload, the sample is the number of steps)."""
+    model, x, y = make_problem(w, dtype)
+    times, t_all = [], time.time()
+    for i in range(warmup + steps):
+        t0 = time.time()
+        reference_step(w, model, x, y)
+        dt = (time.time() - t0) * 1e3
+        if i >= warmup:
+            times.append(dt)
+        elif time.time() - t_all > budget_s / 2:
+            times.append(dt)  # budget nearly gone in warm-up already: keep what we have
+            break
+        if time.time() - t_all > budget_s and times:
+            break
+    return statistics.median(times), len(times)
+
+
+# --------------------------------------------------------------------------
+# main
+# --------------------------------------------------------------------------
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    w = WORKLOADS[args.workload]
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    es = 4 if args.dtype == "f32" else 8
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": w["name"], "batch": w["n"], "l2": "flushed (256 MiB write) between timed steps"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = torch.get_num_threads()
+        ms, n = time_reference(w, dtype, args.steps, args.warmup, args.cpu_budget_s * 1.5)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": round(ms, 3), "unit": "ms", "n_gpus": args.gpus,
+            "steps": n, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": config,
+            "cpu_baseline": {"value": round(ms, 3), "unit": "ms", "cores": cores, "kind": "port",
+                             "sample": f"{n} full step(s) of the workload (oracle/reference_path.py, torch CPU)"},
+            "e2e": {"value": round(ms, 3), "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; vivit_b200 has no CPU path (use --impl reference)")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+        pg = dist.group.WORLD
+
+    from vivit_b200 import kernels
+
+    stepper = Stepper(w, dtype, device, pg)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, with_kernels=False):
+        evs = []
+        barrier()
+        if with_kernels:
+            kernels.timing_start()
+        l0 = kernels.launch_count()
+        t0 = time.time()
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        wall = (time.time() - t0) * 1e3 / steps
+        launches = kernels.launch_count() - l0
+        recs = kernels.timing_stop() if with_kernels else []
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, wall, launches, recs
+
+    for _ in range(args.warmup):
+        stepper.step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, wall, launches, recs = timed(stepper.step_device, args.steps, with_kernels=True)
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        stepper.step_e2e()
+    ms_e2e, _, _, _ = timed(stepper.step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = load_peaks()
+    rows = summarize_kernels(recs, args.steps, es, peaks)
+    # roofline of the dominant kernel that has a roofline (the eigensolver is reported in ms only)
+    roof = None
+    for row in rows:
+        if "bound" in row:
+            if row["bound"] == "tensor":
+                peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+                derate = 6.0 if args.dtype == "f32" else None  # TF32 = bf16/2, three MMAs per product
+                roof = {"kernel": row["kernel"], "bound": "tensor", "achieved": row["achieved"], "peak": peak,
+                        "unit": "TFLOP/s", "frac": round(row["achieved"] / peak, 4), "traffic": None,
+                        "peak_source": f"{peak_src} dense bf16 (sustained)",
+                        "share_of_step": row["share"]}
+                if derate:
+                    roof["peak_3xtf32"] = round(peak / derate, 1)
+                    roof["frac_of_3xtf32_peak"] = round(row["achieved"] / (peak / derate), 4)
+            else:
+                peak = peaks["hbm_gbs"]
+                roof = {"kernel": row["kernel"], "bound": "hbm", "achieved": row["achieved"], "peak": peak,
+                        "unit": "GB/s", "frac": round(row["achieved"] / peak, 4), "traffic": None,
+                        "peak_source": f"{peak_src} HBM copy", "share_of_step": row["share"]}
+            break
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cms, n = time_reference(w, dtype, 1, 0, args.cpu_budget_s)
+        cpu = {"value": round(cms, 3), "unit": "ms", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n} full step(s) of the workload (oracle/reference_path.py, torch CPU)"}
+
+    line = {
+        "metric": METRIC, "value": round(ms, 4), "unit": "ms", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms, 4), "wall_ms_per_step": round(wall, 4),
+        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
+        "data": "synthetic", "config": config,
+        "e2e": {"value": round(ms_e2e, 4), "unit": "ms", "h2d_bytes_per_step": stepper.h2d_bytes,
+                "d2h_bytes_per_step": stepper.d2h_bytes},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "kernels": rows,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

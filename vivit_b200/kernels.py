@@ -555,3 +555,63 @@ def v_apply_linear(v: Tensor, S: Tensor, Z: Tensor) -> Tensor:
         )
     _lib.check(st, "vvt_v_apply_linear")
     return step
+
+
+# --------------------------------------------------------------------------
+# per-kernel device timing (used by bench.py; off by default, no cost when off)
+# --------------------------------------------------------------------------
+
+TIMED = [
+    "loss_sqrt_hessian_ce", "loss_sqrt_hessian_ce_mc", "loss_sqrt_hessian_mse", "scale_",
+    "sqrt_backprop_linear", "sqrt_backprop_conv2d", "sqrt_backprop_elementwise",
+    "sqrt_backprop_maxpool2d", "sqrt_backprop_avgpool2d", "v_emit_conv2d", "v_emit_bias",
+    "v_emit_linear", "gemm", "gram_dense_accum", "gram_cross_accum", "gram_linear_accum",
+    "gram_cross_linear_accum", "syevj", "filter_nonzero", "backtransform_dense",
+    "backtransform_linear", "vt_mat_prod_linear", "scale_rows_rsqrt", "dirderiv_epilogue",
+    "newton_coeff", "v_apply_dense", "v_apply_linear",
+]
+
+
+class _Timing:
+    enabled = False
+    records = []  # (name, start_event, end_event, [tensor shapes], launches)
+
+
+def timing_start() -> None:
+    """Bracket every kernel entry point with CUDA events on the launching stream."""
+    _Timing.records = []
+    _Timing.enabled = True
+
+
+def timing_stop():
+    """Stop timing; returns ``[(name, ms, shapes, launches)]`` (synchronises the device)."""
+    _Timing.enabled = False
+    torch.cuda.synchronize()
+    out = [(n, e0.elapsed_time(e1), shp, nl) for n, e0, e1, shp, nl in _Timing.records]
+    _Timing.records = []
+    return out
+
+
+def _timed(name, fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        if not _Timing.enabled:
+            return fn(*args, **kwargs)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        l0 = launch_count()
+        e0.record()
+        out = fn(*args, **kwargs)
+        e1.record()
+        shapes = [tuple(a.shape) for a in args if isinstance(a, Tensor)]
+        _Timing.records.append((name, e0, e1, shapes, launch_count() - l0))
+        return out
+
+    return wrapper
+
+
+for _name in TIMED:
+    globals()[_name] = _timed(_name, globals()[_name])
+del _name
