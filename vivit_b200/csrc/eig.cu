@@ -1,30 +1,51 @@
-// Symmetric eigensolver for the per-group Gram matrices: two-sided block Jacobi with a
-// round-robin (tournament) parallel ordering.
+// Symmetric eigensolver for the per-group Gram matrices: one-sided (Hestenes) block Jacobi.
 //
-//   * the matrix is cut into 16-wide blocks; in every round the nb blocks are paired
-//     (nb/2 disjoint pairs), each pair's 32x32 diagonal block is diagonalised by one CTA with
-//     a parallel-order cyclic Jacobi held in shared memory (jacobi_diag_kernel), giving an
-//     orthogonal Q per pair;
-//   * all off-diagonal 32x32 tiles are then updated independently, tile (a, b) <- Qa^T X Qb,
-//     exploiting symmetry (only a < b is computed, the mirror tile is written transposed), and
-//     the eigenvector accumulator J gets J[:, b] <- J[:, b] Qb (jacobi_tile_kernel);
-//   * nb-1 rounds make a sweep; sweeps repeat until a whole sweep applies no rotation.
+// The Gram matrices of this path are positive semi-definite, so G = U diag(lambda) U^T is also
+// the SVD of G.  The solver orthogonalises the columns of W = G J by plane rotations applied from
+// the right, accumulating the same rotations in J (J = I at the start):  at convergence the
+// columns of W are mutually orthogonal, W = U diag(lambda), and J = U.
 //
-// Rotations are skipped when |a_pq| <= max(eps*sqrt(|a_pp a_qq|), eps*||G||_F/sqrt(R)), which bounds
-// the final off-diagonal Frobenius norm by sqrt(R)*eps*||G||_F (LAPACK-grade absolute accuracy),
-// terminates on the exactly rank-deficient Grams this path produces, and avoids spending sweeps
-// on diagonalising the rounding noise that fills their null space.
-// Pure Jacobi: converges on the reference's LAPACK-killer fixture without a diagonal shift.
+//   * columns are cut into blocks of OB = 16; a round pairs the nb blocks into nb/2 disjoint
+//     pairs (round-robin tournament), nb-1 rounds visit every pair of blocks once, one extra
+//     "intra" round rotates the column pairs inside each block: together one sweep rotates every
+//     column pair exactly once;
+//   * one kernel launch per round.  A thread-block CLUSTER owns one block pair; its CTAs split the
+//     rows.  Each CTA streams its rows of the 32-column panel through shared memory and forms
+//     a partial 32x32 Gram matrix H = P^T P; partial Grams are summed over the cluster through
+//     distributed shared memory (deterministic reduce-scatter + all-gather);
+//   * every CTA then runs the same 16 (15) rotation rounds on H in shared memory -- a two-sided
+//     update of H, exactly what the column rotations do to P^T P -- accumulating the 32x32
+//     orthogonal Q.  One thread owns one 2x2 block of H per round and derives the two rotations
+//     it needs itself, so a round costs a single barrier (H is double-buffered);
+//   * finally the CTA applies Q to its rows of W and of J (P <- P Q) and writes them back.
+//
+// A rotation is skipped when |h_pq| <= max(tol sqrt(h_pp h_qq), (eps ||G||_F)^2): columns whose
+// norm is below eps ||G||_F are numerically zero (these Grams are rank deficient) and are not
+// rotated against each other.  Eigenvalues are Rayleigh quotients j^T G j / j^T j of the final
+// columns of J with the ORIGINAL matrix (second-order accurate in the eigenvector error and free
+// of the rounding drift of W), eigenvectors the normalised columns of J.
+//
+// Converges without a diagonal shift on the reference's LAPACK-killer fixture.  For a symmetric
+// INDEFINITE input, eigenvalues +l and -l of equal magnitude cannot be separated by a one-sided
+// method; the path never produces such matrices (Grams are PSD up to rounding).
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace vvt {
 
-constexpr int JB = 16;        // block width
-constexpr int JT = 2 * JB;    // tile width (a pair of blocks)
-constexpr int kMaxSweeps = 40;
-constexpr int kMaxInnerSweeps = 12;
+constexpr int OB = 16;       // block width (columns)
+constexpr int OP = 2 * OB;   // panel width: a pair of blocks
+constexpr int OT = 256;      // threads per CTA
+constexpr int CH = 128;      // rows per streamed chunk
+constexpr int LDP = OP + 4;  // padded row pitch of a chunk in shared memory (16-byte aligned)
+constexpr int LDH = OP + 1;  // padded pitch of H
+constexpr int LDQ = OP + 4;  // padded pitch of Q (16-byte aligned rows for the apply phase)
+constexpr int kMaxSweeps = 60;
 
 __host__ __device__ inline void rr_pair(int n, int round, int idx, int& a, int& b) {
   const int m = n - 1;
@@ -37,38 +58,76 @@ __host__ __device__ inline void rr_pair(int n, int round, int idx, int& a, int& 
   }
 }
 
-__device__ __forceinline__ int tile_index(int bp, int bq, int i) {
-  return i < JB ? bp * JB + i : bq * JB + (i - JB);
-}
-
 template <typename T>
 struct Eps;
 template <>
 struct Eps<float> {
   static constexpr float v = 1.1920929e-7f;
+  static constexpr float tol = 1e-5f;  // cosine below which two columns count as orthogonal
 };
 template <>
 struct Eps<double> {
   static constexpr double v = 2.220446049250313e-16;
+  static constexpr double tol = 1e-13;
 };
 
 struct JacobiScalars {
-  double norm2;                 // ||G||_F^2
-  unsigned long long rotations; // CTAs that rotated in the current sweep
+  double norm2;                  // ||G||_F^2
+  unsigned long long rotations;  // clusters that rotated in the current sweep
+  long long t[8];                // VVT_SYEVJ_DEBUG: phase time stamps of CTA 0 (last launch)
 };
+#define VVT_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) sc->t[i] = clock64(); } while (0)
 
-// A = sym(G) padded with zeros, J = I, and ||G||_F^2
+// ---- small vector helpers (16-byte shared/global accesses, packed fp32 FMA) ----------------------
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
+  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
+  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+// acc[i][j] += a[i] * b[j]; fp32 uses the packed FFMA2 of sm_100 (two FMAs per issue slot)
+__device__ __forceinline__ void outer4(float (&acc)[4][4], const float (&a)[4], const float (&b)[4]) {
+  const float2 b01 = make_float2(b[0], b[1]), b23 = make_float2(b[2], b[3]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 ai = make_float2(a[i], a[i]);
+    const float2 c01 = __ffma2_rn(ai, b01, make_float2(acc[i][0], acc[i][1]));
+    const float2 c23 = __ffma2_rn(ai, b23, make_float2(acc[i][2], acc[i][3]));
+    acc[i][0] = c01.x, acc[i][1] = c01.y, acc[i][2] = c23.x, acc[i][3] = c23.y;
+  }
+}
+__device__ __forceinline__ void outer4(double (&acc)[4][4], const double (&a)[4], const double (&b)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+}
+
+// Block-major storage Y[blk][2*Np][OB]: rows [0, Np) hold W = G J, rows [Np, 2 Np) hold J.
 template <typename T>
-__global__ void jacobi_init_kernel(T* A, T* J, const T* G, int64_t R, int64_t Rp, JacobiScalars* sc) {
-  const int64_t total = Rp * Rp;
+__device__ __forceinline__ T* y_ptr(T* Y, int Np, int blk, int row) {
+  return Y + (size_t(blk) * 2 * Np + row) * OB;
+}
+
+// Gs = sym(G) (upper triangle, as symeig(upper=True)) and ||G||_F^2
+template <typename T>
+__global__ void onesided_sym_kernel(T* Gs, const T* G, int64_t R, JacobiScalars* sc) {
+  const int64_t total = R * R;
   double s = 0.0;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t i = idx / Rp, j = idx % Rp;
-    T v = 0;
-    if (i < R && j < R) v = (i <= j) ? G[i * R + j] : G[j * R + i];  // upper triangle, as symeig(upper=True)
-    A[idx] = v;
-    if (J) J[idx] = (i == j) ? T(1) : T(0);
+    const int64_t i = idx / R, j = idx % R;
+    const T v = (i <= j) ? G[idx] : G[j * R + i];
+    Gs[idx] = v;
     s += double(v) * double(v);
   }
   __shared__ double red[32];
@@ -82,318 +141,610 @@ __global__ void jacobi_init_kernel(T* A, T* J, const T* G, int64_t R, int64_t Rp
   }
 }
 
+// W = Gs / ||G||_F zero-padded to Np (the solver squares magnitudes: keep them near 1), J = I
 template <typename T>
-__global__ void __launch_bounds__(256)
-jacobi_diag_kernel(T* A, T* dlo, T* Qbuf, int* flags, int Rp, int nb, int round, int64_t R, JacobiScalars* sc) {
-  __shared__ T W[JT][JT + 1];
-  __shared__ T Q[JT][JT + 1];
-  __shared__ T rot[JB][4];  // s, tau = s/(1+c), new a_pp, new a_qq
-  __shared__ T dl[JT];      // low words of the compensated diagonal
-  __shared__ int pq[JB][2];
-  const int tid = threadIdx.x;
-  int bp, bq;
-  rr_pair(nb, round, blockIdx.x, bp, bq);
-  for (int idx = tid; idx < JT * JT; idx += 256) {
-    const int i = idx / JT, j = idx % JT;
-    W[i][j] = A[int64_t(tile_index(bp, bq, i)) * Rp + tile_index(bp, bq, j)];
-    Q[i][j] = (i == j) ? T(1) : T(0);
-  }
-  if (tid < JT) dl[tid] = dlo[tile_index(bp, bq, tid)];
-  const T thr_abs = T(Eps<T>::v * sqrt(sc->norm2 / double(R)));
-  __syncthreads();
-
-  // Rotations are applied in Rutishauser's form  x' = x - s (y + tau x),  y' = y + s (x - tau y):
-  // cos(theta) - 1 = -s tau is never rounded to zero, so thousands of small-angle rotations do not
-  // inflate the Frobenius norm (c = 1/sqrt(1+t^2) rounds to 1 for |t| < sqrt(eps)).
-  bool rotated_any = false;
-  for (int sweep = 0; sweep < kMaxInnerSweeps; ++sweep) {
-    bool rotated_sweep = false;
-    for (int rr = 0; rr < JT - 1; ++rr) {
-      int did = 0;
-      if (tid < JB) {
-        int p, q;
-        rr_pair(JT, rr, tid, p, q);
-        const T app = W[p][p], aqq = W[q][q], apq = W[p][q];
-        T sn = 0, tau = 0, dpp = app, dqq = aqq;
-        const T lim = max(thr_abs, Eps<T>::v * sqrt(fabs(app) * fabs(aqq)));
-        if (fabs(apq) > lim) {
-          const T theta = (aqq - app) / (T(2) * apq);
-          const T t = (theta >= T(0) ? T(1) : T(-1)) / (fabs(theta) + sqrt(T(1) + theta * theta));
-          const T c = T(1) / sqrt(T(1) + t * t);
-          sn = t * c;
-          tau = sn / (T(1) + c);
-          // The diagonal is kept as an unevaluated sum hi + lo (error-free TwoSum): rotations move
-          // t*a_pq from the smaller to the larger pivot, and without the low word every increment
-          // below half an ulp of the large one would be dropped -- a systematic loss of trace.
-          const T delta = t * apq;
-          const T xp = dl[p] - delta, xq = dl[q] + delta;
-          dpp = app + xp;
-          dqq = aqq + xq;
-          T bb = dpp - app;
-          dl[p] = (app - (dpp - bb)) + (xp - bb);
-          bb = dqq - aqq;
-          dl[q] = (aqq - (dqq - bb)) + (xq - bb);
-          did = 1;
-        }
-        rot[tid][0] = sn;
-        rot[tid][1] = tau;
-        rot[tid][2] = dpp;
-        rot[tid][3] = dqq;
-        pq[tid][0] = p;
-        pq[tid][1] = q;
-      }
-      if (!__syncthreads_or(did)) continue;  // uniform
-      rotated_sweep = true;
-      // columns: W <- W Jrot, Q <- Q Jrot
-      for (int it = tid; it < JT * JB; it += 256) {
-        const int k = it & (JT - 1), t = it / JT;
-        const T sn = rot[t][0], tau = rot[t][1];
-        if (sn != T(0)) {
-          const int p = pq[t][0], q = pq[t][1];
-          const T wp = W[k][p], wq = W[k][q];
-          W[k][p] = wp - sn * (wq + tau * wp);
-          W[k][q] = wq + sn * (wp - tau * wq);
-          const T qp = Q[k][p], qq = Q[k][q];
-          Q[k][p] = qp - sn * (qq + tau * qp);
-          Q[k][q] = qq + sn * (qp - tau * qq);
-        }
-      }
-      __syncthreads();
-      // rows: W <- Jrot^T W; the 2x2 pivot block gets its closed-form values
-      for (int it = tid; it < JT * JB; it += 256) {
-        const int k = it & (JT - 1), t = it / JT;
-        const T sn = rot[t][0], tau = rot[t][1];
-        if (sn != T(0)) {
-          const int p = pq[t][0], q = pq[t][1];
-          const T wp = W[p][k], wq = W[q][k];
-          T np = wp - sn * (wq + tau * wp), nq = wq + sn * (wp - tau * wq);
-          if (k == p) np = rot[t][2], nq = T(0);
-          if (k == q) np = T(0), nq = rot[t][3];
-          W[p][k] = np;
-          W[q][k] = nq;
-        }
-      }
-      __syncthreads();
-    }
-    if (!rotated_sweep) break;
-    rotated_any = true;
-  }
-  // write back the (now diagonal up to threshold) block and this pair's rotation
-  if (rotated_any) {
-    for (int idx = tid; idx < JT * JT; idx += 256) {
-      const int i = idx / JT, j = idx % JT;
-      A[int64_t(tile_index(bp, bq, i)) * Rp + tile_index(bp, bq, j)] = W[i][j];
-      Qbuf[int64_t(blockIdx.x) * JT * JT + idx] = Q[i][j];
-    }
-    if (tid < JT) dlo[tile_index(bp, bq, tid)] = dl[tid];
-  }
-  if (tid == 0) {
-    flags[blockIdx.x] = rotated_any ? 1 : 0;
-    if (rotated_any) atomicAdd(&sc->rotations, 1ull);
+__global__ void onesided_init_kernel(T* Y, const T* Gs, int64_t R, int Np, const JacobiScalars* sc) {
+  const int64_t total = int64_t(Np) * Np;
+  const double n2 = sc->norm2;
+  const T scale = n2 > 0.0 ? T(1.0 / sqrt(n2)) : T(0);
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int i = int(idx / Np), j = int(idx % Np);  // row i, column j
+    const T v = (i < R && j < R) ? Gs[int64_t(i) * R + j] * scale : T(0);
+    *(y_ptr(Y, Np, j / OB, i) + (j % OB)) = v;
+    *(y_ptr(Y, Np, j / OB, Np + i) + (j % OB)) = (i == j) ? T(1) : T(0);
   }
 }
 
-// 32x32x32 product helpers on shared tiles (256 threads, 4 outputs each)
-template <typename T>
-__device__ __forceinline__ void tile_mul_nn(T (*Out)[JT + 1], const T (*X)[JT + 1], const T (*Qm)[JT + 1], int tid) {
-  const int i = tid >> 3, j0 = (tid & 7) * 4;
-  T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll 8
-  for (int k = 0; k < JT; ++k) {
-    const T x = X[i][k];
-    a0 += x * Qm[k][j0];
-    a1 += x * Qm[k][j0 + 1];
-    a2 += x * Qm[k][j0 + 2];
-    a3 += x * Qm[k][j0 + 3];
-  }
-  Out[i][j0] = a0;
-  Out[i][j0 + 1] = a1;
-  Out[i][j0 + 2] = a2;
-  Out[i][j0 + 3] = a3;
-}
-// Out = Qm^T X
-template <typename T>
-__device__ __forceinline__ void tile_mul_tn(T (*Out)[JT + 1], const T (*Qm)[JT + 1], const T (*X)[JT + 1], int tid) {
-  const int i = tid >> 3, j0 = (tid & 7) * 4;
-  T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll 8
-  for (int k = 0; k < JT; ++k) {
-    const T q = Qm[k][i];
-    a0 += q * X[k][j0];
-    a1 += q * X[k][j0 + 1];
-    a2 += q * X[k][j0 + 2];
-    a3 += q * X[k][j0 + 3];
-  }
-  Out[i][j0] = a0;
-  Out[i][j0 + 1] = a1;
-  Out[i][j0 + 2] = a2;
-  Out[i][j0 + 3] = a3;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-jacobi_tile_kernel(T* A, T* J, const T* Qbuf, const int* flags, int Rp, int nb, int round) {
-  __shared__ T X[JT][JT + 1];
-  __shared__ T Qa[JT][JT + 1];
-  __shared__ T Qb[JT][JT + 1];
-  __shared__ T Tm[JT][JT + 1];
-  const int half = nb / 2, tid = threadIdx.x;
-  const int pc = blockIdx.x, y = blockIdx.y;
-  int cp, cq;
-  rr_pair(nb, round, pc, cp, cq);
-  if (y < half) {
-    const int pr = y;
-    if (pr >= pc) return;
-    const int fa = flags[pr], fb = flags[pc];
-    if (!fa && !fb) return;
-    int rp, rq;
-    rr_pair(nb, round, pr, rp, rq);
-    for (int idx = tid; idx < JT * JT; idx += 256) {
-      const int i = idx / JT, j = idx % JT;
-      X[i][j] = A[int64_t(tile_index(rp, rq, i)) * Rp + tile_index(cp, cq, j)];
-      Qa[i][j] = fa ? Qbuf[int64_t(pr) * JT * JT + idx] : (i == j ? T(1) : T(0));
-      Qb[i][j] = fb ? Qbuf[int64_t(pc) * JT * JT + idx] : (i == j ? T(1) : T(0));
-    }
-    __syncthreads();
-    tile_mul_nn<T>(Tm, X, Qb, tid);
-    __syncthreads();
-    tile_mul_tn<T>(X, Qa, Tm, tid);
-    __syncthreads();
-    for (int idx = tid; idx < JT * JT; idx += 256) {
-      const int i = idx / JT, j = idx % JT;
-      A[int64_t(tile_index(rp, rq, i)) * Rp + tile_index(cp, cq, j)] = X[i][j];
-    }
-    for (int idx = tid; idx < JT * JT; idx += 256) {
-      const int j = idx / JT, i = idx % JT;  // i fastest: coalesced rows of the mirror tile
-      A[int64_t(tile_index(cp, cq, j)) * Rp + tile_index(rp, rq, i)] = X[i][j];
-    }
+// Column pair (p, q) of the 32-column panel rotated by inner round `r`, pair index a in [0, 16).
+//   cross rounds: p in block A, q in block B, every (i, j) once over 16 rounds;
+//   intra rounds: round-robin inside each block (8 pairs per block), 15 rounds.
+__device__ __forceinline__ void inner_pair(bool intra, int r, int a, int& p, int& q) {
+  if (!intra) {
+    p = a;
+    q = OB + ((a + r) & (OB - 1));
   } else {
-    if (!J || !flags[pc]) return;
-    const int64_t r0 = int64_t(y - half) * JT;
-    for (int idx = tid; idx < JT * JT; idx += 256) {
-      const int i = idx / JT, j = idx % JT;
-      X[i][j] = J[(r0 + i) * Rp + tile_index(cp, cq, j)];
-      Qb[i][j] = Qbuf[int64_t(pc) * JT * JT + idx];
+    const int half = a >> 3, idx = a & 7;
+    int x, y;
+    rr_pair(OB, r, idx, x, y);
+    p = half * OB + min(x, y);
+    q = half * OB + max(x, y);
+  }
+}
+
+// Rotation that orthogonalises columns p, q with Gram entries (hpp, hqq, hpq):
+// [w_p' w_q'] = [w_p w_q] [[c, s], [-s, c]];  identity when the pair is already orthogonal.
+// c^2 + s^2 = 1 only to a few ulp: a rotation scaled by (1 + d) scales W and J columns alike, and
+// both the convergence tests and the final Rayleigh quotients / normalisation are scale free.
+template <typename T>
+__device__ __forceinline__ bool needs_rotation(T hpp, T hqq, T hpq, T tol2, T abs2) {
+  return (hpq * hpq > tol2 * fabs(hpp * hqq)) && (fabs(hpq) > abs2);
+}
+
+__device__ __forceinline__ bool make_rotation(float hpp, float hqq, float hpq, float tol2, float abs2,
+                                              float& c, float& s) {
+  c = 1.f;
+  s = 0.f;
+  if (!needs_rotation(hpp, hqq, hpq, tol2, abs2)) return false;
+  const float zeta = __fdividef(hqq - hpp, 2.f * hpq);
+  const float az = fabsf(zeta);
+  float t;
+  if (az > 1e8f) {
+    t = __fdividef(0.5f, zeta);
+  } else {
+    const float x = fmaf(zeta, zeta, 1.f);
+    t = copysignf(__fdividef(1.f, az + x * rsqrtf(x)), zeta);
+  }
+  c = rsqrtf(fmaf(t, t, 1.f));
+  s = t * c;
+  return true;
+}
+
+__device__ __forceinline__ bool make_rotation(double hpp, double hqq, double hpq, double tol2, double abs2,
+                                              double& c, double& s) {
+  c = 1.0;
+  s = 0.0;
+  if (!needs_rotation(hpp, hqq, hpq, tol2, abs2)) return false;
+  const double zeta = (hqq - hpp) / (2.0 * hpq);
+  const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  c = rsqrt(1.0 + t * t);
+  s = t * c;
+  return true;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t dst = uint32_t(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <typename T>
+struct RotSmem {
+  T H[2][OP][LDH];  // Gram of the panel (double-buffered by the rotation rounds)
+  T Q[OP][LDQ];     // accumulated rotations; before that: this CTA's partial Gram
+};
+
+// H[0] = sum over the CTAs of the cluster of their partial Grams (left in Q), in a fixed order:
+// reduce-scatter + all-gather through distributed shared memory.  Ends with Q = I.
+template <typename T>
+__device__ __forceinline__ void cluster_reduce_gram(RotSmem<T>& rs, cg::cluster_group& cluster, int tid) {
+  const int CL = int(cluster.num_blocks()), crank = int(cluster.block_rank());
+  if (CL > 1) {
+    cluster.sync();  // every partial Gram is in its CTA's Q
+    for (int idx = crank + tid * CL; idx < OP * OP; idx += OT * CL) {
+      const int i = idx / OP, j = idx % OP;
+      T part[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) part[p] = p < CL ? *cluster.map_shared_rank(&rs.Q[i][j], p) : T(0);
+      const T s = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+        if (p < CL) *cluster.map_shared_rank(&rs.H[0][i][j], p) = s;
+    }
+    cluster.sync();  // H[0] complete everywhere; nobody reads a remote Q any more
+  } else {
+    __syncthreads();
+    for (int idx = tid; idx < OP * OP; idx += OT) rs.H[0][idx / OP][idx % OP] = rs.Q[idx / OP][idx % OP];
+    __syncthreads();
+  }
+  for (int idx = tid; idx < OP * OP; idx += OT) rs.Q[idx / OP][idx % OP] = (idx / OP == idx % OP) ? T(1) : T(0);
+}
+
+// Does any column pair this round is responsible for still need a rotation?  (block-uniform)
+template <typename T>
+__device__ __forceinline__ bool any_rotation_needed(const RotSmem<T>& rs, bool intra, T tol2, T abs2, int tid) {
+  const int i = tid >> 4, j = tid & 15;
+  bool need;
+  if (!intra) {
+    need = needs_rotation(rs.H[0][i][i], rs.H[0][OB + j][OB + j], rs.H[0][i][OB + j], tol2, abs2);
+  } else {
+    need = i < j && (needs_rotation(rs.H[0][i][i], rs.H[0][j][j], rs.H[0][i][j], tol2, abs2) ||
+                     needs_rotation(rs.H[0][OB + i][OB + i], rs.H[0][OB + j][OB + j], rs.H[0][OB + i][OB + j],
+                                    tol2, abs2));
+  }
+  return __syncthreads_or(need ? 1 : 0) != 0;
+}
+
+// The 16 (cross) or 15 (intra) rotation rounds on H, accumulating Q.  Thread (a, b) owns the 2x2
+// block H[{pa,qa}][{pb,qb}] (H' = Ra^T H Rb); lane b & 15 of every warp derives rotation b and
+// rotation a comes from lane a of the same warp by shuffle.  Returns with the result in Q.
+template <typename T>
+__device__ __forceinline__ void rotation_rounds(RotSmem<T>& rs, bool intra, T tol2, T abs2, int tid) {
+  const int a = tid >> 4, b = tid & 15;
+  const int n_rounds = intra ? OB - 1 : OB;
+  int cur = 0;
+  for (int r = 0; r < n_rounds; ++r, cur ^= 1) {
+    T(*Hc)[LDH] = rs.H[cur];
+    T(*Hn)[LDH] = rs.H[cur ^ 1];
+    int pa, qa, pb, qb;
+    inner_pair(intra, r, a, pa, qa);
+    inner_pair(intra, r, b, pb, qb);
+    T cb, sb;
+    const bool db = make_rotation(Hc[pb][pb], Hc[qb][qb], Hc[pb][qb], tol2, abs2, cb, sb);
+    const T ca = __shfl_sync(0xffffffffu, cb, a), sa = __shfl_sync(0xffffffffu, sb, a);
+    // X = H[{pa,qa}][{pb,qb}];  T = X Rb;  H' = Ra^T T,  R = [[c, s], [-s, c]]
+    const T x00 = Hc[pa][pb], x01 = Hc[pa][qb], x10 = Hc[qa][pb], x11 = Hc[qa][qb];
+    const T t00 = cb * x00 - sb * x01, t01 = sb * x00 + cb * x01;
+    const T t10 = cb * x10 - sb * x11, t11 = sb * x10 + cb * x11;
+    T h00 = ca * t00 - sa * t10, h01 = ca * t01 - sa * t11;
+    T h10 = sa * t00 + ca * t10, h11 = sa * t01 + ca * t11;
+    if (a == b && db) h01 = h10 = T(0);  // annihilated by construction
+    Hn[pa][pb] = h00;
+    Hn[pa][qb] = h01;
+    Hn[qa][pb] = h10;
+    Hn[qa][qb] = h11;
+    // Q <- Q R: rows k = b, b + 16 of column pair a (in place: one owner per element and round)
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int k = b + kk * OB;
+      const T qp = rs.Q[k][pa], qq = rs.Q[k][qa];
+      rs.Q[k][pa] = ca * qp - sa * qq;
+      rs.Q[k][qa] = sa * qp + ca * qq;
     }
     __syncthreads();
-    tile_mul_nn<T>(Tm, X, Qb, tid);
-    __syncthreads();
-    for (int idx = tid; idx < JT * JT; idx += 256) {
-      const int i = idx / JT, j = idx % JT;
-      J[(r0 + i) * Rp + tile_index(cp, cq, j)] = Tm[i][j];
+  }
+}
+
+// Rotation rounds on the cluster's rank-0 CTA only (the other CTAs would repeat identical work and
+// steal issue slots from co-resident clusters); the resulting Q is pushed into every CTA's Q through
+// distributed shared memory.  Ends with a cluster barrier: Q is valid everywhere afterwards.
+template <typename T>
+__device__ __forceinline__ void rotate_and_broadcast(RotSmem<T>& rs, cg::cluster_group& cluster, bool intra,
+                                                     T tol2, T abs2, int tid) {
+  const int CL = int(cluster.num_blocks()), crank = int(cluster.block_rank());
+  if (crank == 0) {
+    rotation_rounds<T>(rs, intra, tol2, abs2, tid);
+    for (int idx = tid; idx < OP * OP; idx += OT) {
+      const int i = idx / OP, j = idx % OP;
+      const T v = rs.Q[i][j];
+      for (int p = 1; p < CL; ++p) *cluster.map_shared_rank(&rs.Q[i][j], p) = v;
+    }
+  }
+  if (CL > 1) cluster.sync();
+}
+
+// this thread's share of a 4x4 tile of P^T P: rows r = ks, ks + 4, ... < nrows of a row-major chunk
+template <typename T>
+__device__ __forceinline__ void gram_rows(T (&acc)[4][4], const T* P, int ldp, int nrows, int ks, int ti, int tj) {
+  int r = ks;
+  for (; r + 4 < nrows; r += 8) {  // 2 rows in flight
+    T a[2][4], b[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      ld4(P + size_t(r + 4 * u) * ldp + 4 * ti, a[u]);
+      ld4(P + size_t(r + 4 * u) * ldp + 4 * tj, b[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) outer4(acc, a[u], b[u]);
+  }
+  for (; r < nrows; r += 4) {
+    T a[4], b[4];
+    ld4(P + size_t(r) * ldp + 4 * ti, a);
+    ld4(P + size_t(r) * ldp + 4 * tj, b);
+    outer4(acc, a, b);
+  }
+}
+
+// sum the 4 k-split partial tiles (lanes ks = tid & 3) and store the tile into Q
+template <typename T>
+__device__ __forceinline__ void gram_store(RotSmem<T>& rs, T (&acc)[4][4], int ks, int ti, int tj) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      T v = acc[i][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (ks == 0) rs.Q[4 * ti + i][4 * tj + j] = v;
+    }
+}
+
+// out rows (4 per thread: tr + 32 i) = P rows * Q, written to global memory
+template <typename T>
+__device__ __forceinline__ void apply_rows(const RotSmem<T>& rs, const T* P, int ldp, int r_base, int n_rows,
+                                           T* Y, int Np, int ba, int bb, int grow0, int tr, int tc) {
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+  int rows[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rows[i] = min(r_base + tr + 32 * i, n_rows - 1);  // clamp: read valid memory
+#pragma unroll 2
+  for (int k4 = 0; k4 < OP; k4 += 4) {
+    T pv[4][4];  // pv[i][kk] = P[row_i][k4 + kk]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld4(P + size_t(rows[i]) * ldp + k4, pv[i]);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      T qv[4];
+      ld4(&rs.Q[k4 + kk][4 * tc], qv);
+      const T a[4] = {pv[0][kk], pv[1][kk], pv[2][kk], pv[3][kk]};
+      outer4(acc, a, qv);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r_base + tr + 32 * i;
+    if (r < n_rows) {
+      const int col = 4 * tc;
+      st4(y_ptr(Y, Np, col < OB ? ba : bb, grow0 + r) + (col & (OB - 1)), acc[i]);
     }
   }
 }
 
+__device__ __forceinline__ void round_blocks(int nb, int round, int pair, int& ba, int& bb) {
+  if (round < 0) {
+    ba = 2 * pair;
+    bb = 2 * pair + 1;
+  } else {
+    rr_pair(nb, round, pair, ba, bb);
+  }
+}
+
+// ---- resident variant: this CTA's rows of W and J are loaded once (cp.async) and stay in smem ----
 template <typename T>
-__global__ void jacobi_rank_kernel(int* rank, T* ev, const T* A, const T* dlo, int64_t R, int64_t Rp) {
+__global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 3 : 1))
+onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, JacobiScalars* sc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RotSmem<T>& rs = *reinterpret_cast<RotSmem<T>*>(smem_raw);
+  T* P = reinterpret_cast<T*>(smem_raw + ((sizeof(RotSmem<T>) + 15) / 16) * 16);  // [2 * rows][LDP]: W rows, J rows
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = int(cluster.num_blocks()), crank = int(cluster.block_rank());
+  const int tid = threadIdx.x;
+  const bool intra = round < 0;
+  int ba, bb;
+  round_blocks(nb, round, blockIdx.x / CL, ba, bb);
+  const int w0 = crank * rows_per_cta, nrows = max(0, min(Np, w0 + rows_per_cta) - w0);
+  const T tol2 = Eps<T>::tol * Eps<T>::tol;
+  const T abs2 = Eps<T>::v * Eps<T>::v;  // W is scaled to unit Frobenius norm
+
+  VVT_STAMP(0);
+  // all loads are issued up front: group 0 = W rows (needed now), group 1 = J rows (needed last)
+  {
+    constexpr int V = 16 / sizeof(T), VPR = OB / V;  // elements per 16 bytes, vectors per block row
+    for (int part = 0; part < 2; ++part) {
+      for (int idx = tid; idx < nrows * 2 * VPR; idx += OT) {
+        const int r = idx / (2 * VPR), v = idx % (2 * VPR);
+        const int blk = v < VPR ? ba : bb, col = (v % VPR) * V;
+        cp_async16(P + size_t(part * nrows + r) * LDP + (v < VPR ? 0 : OB) + col,
+                   y_ptr(Y, Np, blk, part * Np + w0 + r) + col);
+      }
+      cp_async_commit();
+    }
+  }
+  cp_async_wait<1>();
+  __syncthreads();
+  VVT_STAMP(1);
+
+  {  // phase 1: partial Gram of this CTA's rows of W
+    const int ks = tid & 3, ti = tid >> 5, tj = (tid >> 2) & 7;
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    gram_rows<T>(acc, P, LDP, nrows, ks, ti, tj);
+    gram_store<T>(rs, acc, ks, ti, tj);
+  }
+  VVT_STAMP(2);
+  cluster_reduce_gram<T>(rs, cluster, tid);
+  __syncthreads();
+  VVT_STAMP(3);
+  if (!any_rotation_needed<T>(rs, intra, tol2, abs2, tid)) {  // uniform over the cluster (same H)
+    cp_async_wait<0>();
+    return;
+  }
+  if (crank == 0 && tid == 0) atomicAdd(&sc->rotations, 1ull);
+  rotate_and_broadcast<T>(rs, cluster, intra, tol2, abs2, tid);  // phase 2
+  VVT_STAMP(4);
+  cp_async_wait<0>();
+  __syncthreads();
+  VVT_STAMP(5);
+  {  // phase 3: P <- P Q for the W rows and the J rows, straight to global memory
+    const int tr = tid >> 3, tc = tid & 7;
+    for (int part = 0; part < 2; ++part)
+      for (int r_base = 0; r_base < nrows; r_base += 128)
+        apply_rows<T>(rs, P + size_t(part) * nrows * LDP, LDP, r_base, nrows, Y, Np, ba, bb, part * Np + w0, tr, tc);
+  }
+  VVT_STAMP(6);
+}
+
+// ---- streaming variant (any size): rows pass through two chunk buffers, W is read twice -----------
+template <typename T>
+struct StreamSmem {
+  RotSmem<T> rs;
+  T chunk[2][CH][LDP];
+};
+
+template <typename T>
+__device__ __forceinline__ void load_chunk(T (*dst)[LDP], const T* Y, int Np, int ba, int bb, int row0,
+                                           int nrows, int tid) {
+  constexpr int V = 16 / sizeof(T), VPR = OB / V;
+  for (int idx = tid; idx < nrows * 2 * VPR; idx += OT) {
+    const int r = idx / (2 * VPR), v = idx % (2 * VPR);
+    const int blk = v < VPR ? ba : bb, col = (v % VPR) * V;
+    cp_async16(&dst[r][(v < VPR ? 0 : OB) + col], y_ptr(const_cast<T*>(Y), Np, blk, row0 + r) + col);
+  }
+  cp_async_commit();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
+onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, JacobiScalars* sc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  StreamSmem<T>& sm = *reinterpret_cast<StreamSmem<T>*>(smem_raw);
+  RotSmem<T>& rs = sm.rs;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = int(cluster.num_blocks()), crank = int(cluster.block_rank());
+  const int tid = threadIdx.x;
+  const bool intra = round < 0;
+  int ba, bb;
+  round_blocks(nb, round, blockIdx.x / CL, ba, bb);
+  const int w0 = crank * rows_per_cta, nrows = max(0, min(Np, w0 + rows_per_cta) - w0);
+  const int n_chunks = (nrows + CH - 1) / CH;
+  const T tol2 = Eps<T>::tol * Eps<T>::tol;
+  const T abs2 = Eps<T>::v * Eps<T>::v;
+
+  {  // phase 1: partial Gram, chunks of W rows double-buffered
+    const int ks = tid & 3, ti = tid >> 5, tj = (tid >> 2) & 7;
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    if (n_chunks > 0) load_chunk<T>(sm.chunk[0], Y, Np, ba, bb, w0, min(CH, nrows), tid);
+    for (int c = 0; c < n_chunks; ++c) {
+      if (c + 1 < n_chunks) {
+        load_chunk<T>(sm.chunk[(c + 1) & 1], Y, Np, ba, bb, w0 + (c + 1) * CH, min(CH, nrows - (c + 1) * CH), tid);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      gram_rows<T>(acc, &sm.chunk[c & 1][0][0], LDP, min(CH, nrows - c * CH), ks, ti, tj);
+      __syncthreads();
+    }
+    gram_store<T>(rs, acc, ks, ti, tj);
+  }
+  cluster_reduce_gram<T>(rs, cluster, tid);
+  __syncthreads();
+  if (!any_rotation_needed<T>(rs, intra, tol2, abs2, tid)) return;
+  if (crank == 0 && tid == 0) atomicAdd(&sc->rotations, 1ull);
+  // first chunk of phase 3 travels while the rotation rounds run
+  if (n_chunks > 0) load_chunk<T>(sm.chunk[0], Y, Np, ba, bb, w0, min(CH, nrows), tid);
+  rotate_and_broadcast<T>(rs, cluster, intra, tol2, abs2, tid);  // phase 2
+  {  // phase 3: chunks of W rows, then of J rows
+    const int tr = tid >> 3, tc = tid & 7;
+    const int total = 2 * n_chunks;
+    for (int c = 0; c < total; ++c) {
+      if (c + 1 < total) {
+        const int part = (c + 1) >= n_chunks, cc = (c + 1) - part * n_chunks;
+        load_chunk<T>(sm.chunk[(c + 1) & 1], Y, Np, ba, bb, part * Np + w0 + cc * CH, min(CH, nrows - cc * CH), tid);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      const int part = c >= n_chunks, cc = c - part * n_chunks;
+      apply_rows<T>(rs, &sm.chunk[c & 1][0][0], LDP, 0, min(CH, nrows - cc * CH), Y, Np, ba, bb,
+                    part * Np + w0 + cc * CH, tr, tc);
+      __syncthreads();
+    }
+  }
+}
+
+// Jm[r][c] (row-major n x n) <- J part of Y
+template <typename T>
+__global__ void onesided_gather_j_kernel(T* Jm, const T* Y, int64_t R, int Np) {
+  const int64_t total = R * R;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int r = int(idx / R), c = int(idx % R);
+    Jm[idx] = *(y_ptr(const_cast<T*>(Y), Np, c / OB, Np + r) + (c % OB));
+  }
+}
+
+// ev[c] = (j_c . t_c) / (j_c . j_c),  inv[c] = 1/||j_c||   (one warp per column; T = G J)
+template <typename T>
+__global__ void onesided_rayleigh_kernel(T* ev, T* inv, const T* Jm, const T* Tm, int64_t R) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (c >= R) return;
+  double num = 0.0, den = 0.0;
+  for (int64_t r = lane; r < R; r += 32) {
+    const double j = double(Jm[r * R + c]);
+    num += j * double(Tm[r * R + c]);
+    den += j * j;
+  }
+  num = warp_sum(num);
+  den = warp_sum(den);
+  if (lane == 0) {
+    ev[c] = den > 0.0 ? T(num / den) : T(0);
+    inv[c] = den > 0.0 ? T(1.0 / sqrt(den)) : T(0);
+  }
+}
+
+template <typename T>
+__global__ void jacobi_rank_kernel(int* rank, const T* ev, int64_t R) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= R) return;
-  const T vi = A[i * Rp + i] + dlo[i];
-  ev[i] = vi;
+  const T vi = ev[i];
   int r = 0;
-  for (int64_t j = 0; j < R; ++j) {
-    const T vj = ldg(A + j * Rp + j) + ldg(dlo + j);
-    r += (vj < vi) || (vj == vi && j < i) || (vj != vj && vi == vi);  // NaNs sort first, stable
-  }
-  if (vi != vi) {  // NaN: order among NaNs by index
-    r = 0;
-    for (int64_t j = 0; j < i; ++j) {
-      const T vj = ldg(A + j * Rp + j) + ldg(dlo + j);
-      r += (vj != vj);
+  if (vi != vi) {  // NaNs sort first, by index
+    for (int64_t j = 0; j < i; ++j) r += (ldg(ev + j) != ldg(ev + j));
+  } else {
+    for (int64_t j = 0; j < R; ++j) {
+      const T vj = ldg(ev + j);
+      r += (vj < vi) || (vj == vi && j < i) || (vj != vj);
     }
   }
   rank[i] = r;
 }
 
 template <typename T>
-__global__ void jacobi_permute_kernel(T* evals, T* evecs, const T* ev, const T* J, const int* rank,
-                                      int64_t R, int64_t Rp) {
+__global__ void jacobi_permute_kernel(T* evals, T* evecs, const T* ev, const T* inv, const T* Jm,
+                                      const int* rank, int64_t R) {
   const int64_t total = evecs ? R * R : R;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
     const int64_t r = idx / R, i = idx % R;
     const int dst = rank[i];
     if (r == 0) evals[dst] = ev[i];
-    if (evecs) evecs[r * R + dst] = J[r * Rp + i];
+    if (evecs) evecs[r * R + dst] = Jm[r * R + i] * inv[i];
   }
 }
 
 struct JacobiLayout {
-  int64_t Rp, nb, off_A, off_J, off_Q, off_ev, off_dlo, off_rank, off_flags, off_sc, total;
+  int64_t Np, nb, off_Y, off_Gs, off_Jm, off_Tm, off_ev, off_inv, off_rank, off_sc, off_gemm, gemm_bytes, total;
 };
 
-static JacobiLayout jacobi_layout(int64_t R, int jobz, int64_t es) {
+static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
   JacobiLayout L;
-  L.Rp = align_up(R, JT);
-  L.nb = L.Rp / JB;
+  L.Np = align_up(R, OP);
+  L.nb = L.Np / OB;
   int64_t o = 0;
   auto take = [&](int64_t bytes) {
     const int64_t at = o;
     o += align_up(bytes, 256);
     return at;
   };
-  L.off_A = take(L.Rp * L.Rp * es);
-  L.off_J = jobz ? take(L.Rp * L.Rp * es) : -1;
-  L.off_Q = take((L.nb / 2) * JT * JT * es);
-  L.off_ev = take(L.Rp * es);
-  L.off_dlo = take(L.Rp * es);
-  L.off_rank = take(L.Rp * 4);
-  L.off_flags = take((L.nb / 2) * 4);
+  L.off_Y = take(L.nb * 2 * L.Np * OB * es);
+  L.off_Gs = take(R * R * es);
+  L.off_Jm = take(R * R * es);
+  L.off_Tm = take(R * R * es);
+  L.off_ev = take(R * es);
+  L.off_inv = take(R * es);
+  L.off_rank = take(R * 4);
   L.off_sc = take(sizeof(JacobiScalars));
+  L.gemm_bytes = vvt_gram_workspace_bytes(R, R, R, dtype);
+  L.off_gemm = take(L.gemm_bytes);
   L.total = o;
   return L;
 }
 
 template <typename T>
-static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char* ws, int* info,
+static size_t resident_smem_bytes(int rows_per_cta) {
+  return align_up(sizeof(RotSmem<T>), 16) + size_t(2) * rows_per_cta * LDP * sizeof(T);
+}
+
+template <typename T>
+static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_cta, bool resident,
+                        JacobiScalars* sc, cudaStream_t s) {
+  auto kern = resident ? onesided_round_resident_kernel<T> : onesided_round_stream_kernel<T>;
+  const size_t smem = resident ? resident_smem_bytes<T>(rows_per_cta) : sizeof(StreamSmem<T>);
+  static size_t attr_done[2] = {0, 0};  // per instantiation: largest size configured so far
+  if (attr_done[resident] < smem) {
+    VVT_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
+                       "vvt_syevj(attr)"));
+    attr_done[resident] = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(nb / 2 * CL));
+  cfg.blockDim = dim3(OT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(CL);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, sc), "vvt_syevj(round)"));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return VVT_OK;
+}
+
+template <typename T>
+static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char* ws, int* info, int dtype,
                       cudaStream_t s) {
-  const JacobiLayout L = jacobi_layout(R, jobz, sizeof(T));
-  T* A = (T*)(ws + L.off_A);
-  T* J = jobz ? (T*)(ws + L.off_J) : nullptr;
-  T* Qbuf = (T*)(ws + L.off_Q);
+  const JacobiLayout L = jacobi_layout(R, sizeof(T), dtype);
+  T* Y = (T*)(ws + L.off_Y);
+  T* Gs = (T*)(ws + L.off_Gs);
+  T* Jm = (T*)(ws + L.off_Jm);
+  T* Tm = (T*)(ws + L.off_Tm);
   T* ev = (T*)(ws + L.off_ev);
-  T* dlo = (T*)(ws + L.off_dlo);
+  T* inv = (T*)(ws + L.off_inv);
   int* rank = (int*)(ws + L.off_rank);
-  int* flags = (int*)(ws + L.off_flags);
   JacobiScalars* sc = (JacobiScalars*)(ws + L.off_sc);
-  const int Rp = int(L.Rp), nb = int(L.nb), half = nb / 2;
+  const int Np = int(L.Np), nb = int(L.nb), pairs = nb / 2;
+
+  // rows of the panel are split over the CTAs of a cluster: as many as leave >= 16 rows per CTA
+  int CL = 8;
+  while (CL > 1 && Np / CL < 16) CL /= 2;
+  const int rows_per_cta = int(ceil_div(Np, CL));
+  const bool resident = resident_smem_bytes<T>(rows_per_cta) <= size_t(200) * 1024;
 
   VVT_TRY(check_cuda(cudaMemsetAsync(sc, 0, sizeof(JacobiScalars), s), "vvt_syevj"));
-  VVT_TRY(check_cuda(cudaMemsetAsync(dlo, 0, L.Rp * sizeof(T), s), "vvt_syevj"));
   const bool debug = getenv("VVT_SYEVJ_DEBUG") != nullptr;
-  const int init_blocks = int(vmin<int64_t>(ceil_div(L.Rp * L.Rp, 256), 8 * num_sms()));
-  jacobi_init_kernel<T><<<init_blocks, 256, 0, s>>>(A, J, G, R, L.Rp, sc);
+  const int init_blocks = int(vmin<int64_t>(ceil_div(L.Np * L.Np, 256), 8 * num_sms()));
+  onesided_sym_kernel<T><<<int(vmin<int64_t>(ceil_div(R * R, 256), 8 * num_sms())), 256, 0, s>>>(Gs, G, R, sc);
+  VVT_TRY(launched("vvt_syevj(sym)"));
+  onesided_init_kernel<T><<<init_blocks, 256, 0, s>>>(Y, Gs, R, Np, sc);
   VVT_TRY(launched("vvt_syevj(init)"));
 
   int sweeps = 0, converged = 0;
   for (; sweeps < kMaxSweeps;) {
     VVT_TRY(check_cuda(cudaMemsetAsync(&sc->rotations, 0, sizeof(unsigned long long), s), "vvt_syevj"));
-    for (int round = 0; round < nb - 1; ++round) {
-      jacobi_diag_kernel<T><<<half, 256, 0, s>>>(A, dlo, Qbuf, flags, Rp, nb, round, R, sc);
-      VVT_TRY(launched("vvt_syevj(diag)"));
-      const unsigned gy = unsigned(half + (jobz ? Rp / JT : 0));
-      if (half > 1 || jobz) {
-        jacobi_tile_kernel<T><<<dim3(half, gy), 256, 0, s>>>(A, J, Qbuf, flags, Rp, nb, round);
-        VVT_TRY(launched("vvt_syevj(tile)"));
-      }
-    }
+    for (int round = -1; round < nb - 1; ++round)
+      VVT_TRY(launch_round<T>(Y, Np, nb, round, CL, rows_per_cta, resident, sc, s));
     ++sweeps;
     unsigned long long rot = 0;
     VVT_TRY(check_cuda(cudaMemcpyAsync(&rot, &sc->rotations, sizeof(rot), cudaMemcpyDeviceToHost, s),
                        "vvt_syevj"));
     VVT_TRY(check_cuda(cudaStreamSynchronize(s), "vvt_syevj"));
-    if (debug) fprintf(stderr, "[vvt_syevj] R=%lld sweep %d: %llu of %d block solves rotated\n", (long long)R, sweeps, rot, half * (nb - 1));
+    if (debug) {
+      JacobiScalars h;
+      cudaMemcpy(&h, sc, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[vvt_syevj] R=%lld CL=%d sweep %d: %llu of %d block pairs rotated; CTA0 clocks:", (long long)R,
+              CL, sweeps, rot, pairs * nb);
+      for (int i = 1; i < 7; ++i) fprintf(stderr, " %lld", h.t[i] - h.t[i - 1]);
+      fprintf(stderr, "\n");
+    }
     if (rot == 0) {
       converged = 1;
       break;
     }
   }
-  jacobi_rank_kernel<T><<<unsigned(ceil_div(R, 128)), 128, 0, s>>>(rank, ev, A, dlo, R, L.Rp);
+  const int gblocks = int(vmin<int64_t>(ceil_div(R * R, 256), 8 * num_sms()));
+  onesided_gather_j_kernel<T><<<gblocks, 256, 0, s>>>(Jm, Y, R, Np);
+  VVT_TRY(launched("vvt_syevj(gather)"));
+  // Tm = Gs Jm (3xTF32 / DMMA GEMM of gemm.cu)
+  VVT_TRY(vvt_gemm(Tm, Gs, Jm, R, R, R, 0, 1, R, R, R, 1.0, 0.0, 1, 0, 0, 0, ws + L.off_gemm, L.gemm_bytes,
+                   dtype, (void*)s));
+  onesided_rayleigh_kernel<T><<<unsigned(ceil_div(R * 32, 256)), 256, 0, s>>>(ev, inv, Jm, Tm, R);
+  VVT_TRY(launched("vvt_syevj(rayleigh)"));
+  jacobi_rank_kernel<T><<<unsigned(ceil_div(R, 128)), 128, 0, s>>>(rank, ev, R);
   VVT_TRY(launched("vvt_syevj(rank)"));
   const int64_t total = jobz ? R * R : R;
   const int pblocks = int(vmin<int64_t>(ceil_div(total, 256), 8 * num_sms()));
-  jacobi_permute_kernel<T><<<pblocks, 256, 0, s>>>(evals, jobz ? evecs : nullptr, ev, J, rank, R, L.Rp);
+  jacobi_permute_kernel<T><<<pblocks, 256, 0, s>>>(evals, jobz ? evecs : nullptr, ev, inv, Jm, rank, R);
   VVT_TRY(launched("vvt_syevj(permute)"));
   if (info) {
     info[0] = sweeps;
@@ -409,8 +760,9 @@ using namespace vvt;
 extern "C" {
 
 int64_t vvt_syevj_workspace_bytes(int64_t R, int jobz, int dtype) {
+  (void)jobz;
   if (R <= 0) return 0;
-  return jacobi_layout(R, jobz, dtype == VVT_F32 ? 4 : 8).total;
+  return jacobi_layout(R, dtype == VVT_F32 ? 4 : 8, dtype).total;
 }
 
 int vvt_syevj(void* evals, void* evecs, const void* G, int64_t R, int jobz, void* workspace,
@@ -418,12 +770,12 @@ int vvt_syevj(void* evals, void* evecs, const void* G, int64_t R, int jobz, void
   VVT_REQUIRE(R >= 0, "negative size");
   if (info_host) info_host[0] = 0, info_host[1] = 1;
   if (R == 0) return VVT_OK;
-  VVT_REQUIRE(R <= (int64_t(1) << 20), "matrix too large");
+  VVT_REQUIRE(R <= (int64_t(1) << 15), "matrix too large");
   VVT_REQUIRE(evals && G && workspace && (!jobz || evecs), "null pointer");
   if (workspace_bytes < vvt_syevj_workspace_bytes(R, jobz, dtype))
     return fail(VVT_ERR_WORKSPACE, "%s: workspace too small", __func__);
   VVT_DISPATCH(dtype, {
-    return syevj_impl<T>((T*)evals, (T*)evecs, (const T*)G, R, jobz, (char*)workspace, info_host,
+    return syevj_impl<T>((T*)evals, (T*)evecs, (const T*)G, R, jobz, (char*)workspace, info_host, dtype,
                          as_stream(stream));
   });
 }
