@@ -74,6 +74,7 @@ struct Eps<double> {
 struct JacobiScalars {
   double norm2;                  // ||G||_F^2
   unsigned long long rotations;  // clusters that rotated in the current sweep
+  unsigned long long evmax_bits; // bit pattern of max |eigenvalue| as a double (atomicMax on non-negatives)
   long long t[8];                // VVT_SYEVJ_DEBUG: phase time stamps of CTA 0 (last launch)
 };
 #define VVT_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) sc->t[i] = clock64(); } while (0)
@@ -559,34 +560,72 @@ onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, 
   }
 }
 
-// Jm[r][c] (row-major n x n) <- J part of Y
+// Jm[r][c] (row-major) and Jt[c][r] (its transpose) <- J part of Y
 template <typename T>
-__global__ void onesided_gather_j_kernel(T* Jm, const T* Y, int64_t R, int Np) {
+__global__ void onesided_gather_j_kernel(T* Jm, T* Jt, const T* Y, int64_t R, int Np) {
   const int64_t total = R * R;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
     const int r = int(idx / R), c = int(idx % R);
     Jm[idx] = *(y_ptr(const_cast<T*>(Y), Np, c / OB, Np + r) + (c % OB));
+    // second pass with r fastest so that the Jt writes coalesce
+    const int c2 = int(idx / R), r2 = int(idx % R);
+    Jt[int64_t(c2) * R + r2] = *(y_ptr(const_cast<T*>(Y), Np, c2 / OB, Np + r2) + (c2 % OB));
   }
 }
 
-// ev[c] = (j_c . t_c) / (j_c . j_c),  inv[c] = 1/||j_c||   (one warp per column; T = G J)
+// ev[c] = (j_c . G j_c) / (j_c . j_c)  (one warp per column; rows of Jt and of Tt = Jt G, float64 sums)
 template <typename T>
-__global__ void onesided_rayleigh_kernel(T* ev, T* inv, const T* Jm, const T* Tm, int64_t R) {
+__global__ void onesided_rayleigh_kernel(T* ev, const T* Jt, const T* Tt, int64_t R, JacobiScalars* sc) {
   const int lane = threadIdx.x & 31;
   const int64_t c = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (c >= R) return;
   double num = 0.0, den = 0.0;
   for (int64_t r = lane; r < R; r += 32) {
-    const double j = double(Jm[r * R + c]);
-    num += j * double(Tm[r * R + c]);
+    const double j = double(Jt[c * R + r]);
+    num += j * double(Tt[c * R + r]);
     den += j * j;
   }
   num = warp_sum(num);
   den = warp_sum(den);
   if (lane == 0) {
-    ev[c] = den > 0.0 ? T(num / den) : T(0);
-    inv[c] = den > 0.0 ? T(1.0 / sqrt(den)) : T(0);
+    const double lam = den > 0.0 ? num / den : 0.0;
+    ev[c] = T(lam);
+    if (lam == lam) atomicMax(&sc->evmax_bits, (unsigned long long)__double_as_longlong(fabs(lam)));
+  }
+}
+
+// One step of the Ogita-Aishima refinement of an approximate eigenvector matrix J:
+//   S = J^T G J,  M = J^T J,  R = I - M,  lam_i = S_ii / M_ii,
+//   E_ij = (S_ij + lam_j R_ij) / (lam_j - lam_i)   (i != j, eigenvalues separated),   E_ii = R_ii / 2,
+//   J <- J + J E.
+// It restores orthonormality and removes the first-order eigenvector error left by the Jacobi
+// threshold; every product is a tensor-core GEMM.  This kernel writes Et[j][i] = E[i][j].
+template <typename T>
+__global__ void onesided_refine_coeff_kernel(T* Et, const T* S, const T* Mm, const T* ev, int64_t R,
+                                             const JacobiScalars* sc) {
+  const int64_t total = R * R;
+  // eigenvalue gaps below the rounding noise of S carry no information about the eigenvectors
+  const T gap_min = T(256.0 * double(Eps<T>::v) * __longlong_as_double((long long)sc->evmax_bits));
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t j = idx / R, i = idx % R;  // Et[j][i] = E[i][j]
+    T e;
+    if (i == j) {
+      e = (T(1) - Mm[i * R + i]) / T(2);
+    } else {
+      // both (i, j) and (j, i) read the same upper-triangle entries, so that they take the same
+      // decision and E + E^T = R holds exactly (that is what restores orthonormality)
+      const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+      const T r = -Mm[lo * R + hi], sij = S[lo * R + hi], gap = ev[j] - ev[i];
+      e = r / T(2);
+      if (fabs(gap) > gap_min) {
+        const T cand = (sij + ev[j] * r) / gap, other = r - cand;  // other = E[j][i]
+        // larger: near-degenerate pair (noise over gap) -> orthogonality fix only
+        if (fabs(cand) <= T(1e-3) && fabs(other) <= T(1e-3)) e = cand;
+      }
+    }
+    Et[idx] = e;
   }
 }
 
@@ -607,21 +646,21 @@ __global__ void jacobi_rank_kernel(int* rank, const T* ev, int64_t R) {
   rank[i] = r;
 }
 
+// evals[rank[i]] = ev[i];  evecs[r][rank[i]] = Jt[i][r]
 template <typename T>
-__global__ void jacobi_permute_kernel(T* evals, T* evecs, const T* ev, const T* inv, const T* Jm,
-                                      const int* rank, int64_t R) {
+__global__ void jacobi_permute_kernel(T* evals, T* evecs, const T* ev, const T* Jt, const int* rank, int64_t R) {
   const int64_t total = evecs ? R * R : R;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
     const int64_t r = idx / R, i = idx % R;
     const int dst = rank[i];
     if (r == 0) evals[dst] = ev[i];
-    if (evecs) evecs[r * R + dst] = Jm[r * R + i] * inv[i];
+    if (evecs) evecs[r * R + dst] = Jt[i * R + r];
   }
 }
 
 struct JacobiLayout {
-  int64_t Np, nb, off_Y, off_Gs, off_Jm, off_Tm, off_ev, off_inv, off_rank, off_sc, off_gemm, gemm_bytes, total;
+  int64_t Np, nb, off_Y, off_Gs, off_Jm, off_Jt, off_Tt, off_S, off_M, off_Et, off_ev, off_rank, off_sc, off_gemm, gemm_bytes, total;
 };
 
 static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
@@ -637,9 +676,12 @@ static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
   L.off_Y = take(L.nb * 2 * L.Np * OB * es);
   L.off_Gs = take(R * R * es);
   L.off_Jm = take(R * R * es);
-  L.off_Tm = take(R * R * es);
+  L.off_Jt = take(R * R * es);
+  L.off_Tt = take(R * R * es);
+  L.off_S = take(R * R * es);
+  L.off_M = take(R * R * es);
+  L.off_Et = L.off_Y;  // Y is dead once J has been gathered (nb * 2 * Np * OB >= R * R elements)
   L.off_ev = take(R * es);
-  L.off_inv = take(R * es);
   L.off_rank = take(R * 4);
   L.off_sc = take(sizeof(JacobiScalars));
   L.gemm_bytes = vvt_gram_workspace_bytes(R, R, R, dtype);
@@ -688,9 +730,12 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   T* Y = (T*)(ws + L.off_Y);
   T* Gs = (T*)(ws + L.off_Gs);
   T* Jm = (T*)(ws + L.off_Jm);
-  T* Tm = (T*)(ws + L.off_Tm);
+  T* Jt = (T*)(ws + L.off_Jt);
+  T* Tt = (T*)(ws + L.off_Tt);
+  T* Sm = (T*)(ws + L.off_S);
+  T* Mm = (T*)(ws + L.off_M);
+  T* Et = (T*)(ws + L.off_Et);
   T* ev = (T*)(ws + L.off_ev);
-  T* inv = (T*)(ws + L.off_inv);
   int* rank = (int*)(ws + L.off_rank);
   JacobiScalars* sc = (JacobiScalars*)(ws + L.off_sc);
   const int Np = int(L.Np), nb = int(L.nb), pairs = nb / 2;
@@ -733,18 +778,28 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
     }
   }
   const int gblocks = int(vmin<int64_t>(ceil_div(R * R, 256), 8 * num_sms()));
-  onesided_gather_j_kernel<T><<<gblocks, 256, 0, s>>>(Jm, Y, R, Np);
+  onesided_gather_j_kernel<T><<<gblocks, 256, 0, s>>>(Jm, Jt, Y, R, Np);
   VVT_TRY(launched("vvt_syevj(gather)"));
-  // Tm = Gs Jm (3xTF32 / DMMA GEMM of gemm.cu)
-  VVT_TRY(vvt_gemm(Tm, Gs, Jm, R, R, R, 0, 1, R, R, R, 1.0, 0.0, 1, 0, 0, 0, ws + L.off_gemm, L.gemm_bytes,
-                   dtype, (void*)s));
-  onesided_rayleigh_kernel<T><<<unsigned(ceil_div(R * 32, 256)), 256, 0, s>>>(ev, inv, Jm, Tm, R);
+  // every product below is C = A B^T with K-contiguous operands: the tcgen05 (fp32) / DMMA (fp64) GEMM
+  auto gemm_nt = [&](T* C, const T* A, const T* B, double beta) {
+    return vvt_gemm(C, A, B, R, R, R, 0, 0, R, R, R, 1.0, beta, 1, 0, 0, 0, ws + L.off_gemm, L.gemm_bytes, dtype,
+                    (void*)s);
+  };
+  VVT_TRY(gemm_nt(Tt, Jt, Gs, 0.0));  // Tt = J^T G   (G symmetric)
+  onesided_rayleigh_kernel<T><<<unsigned(ceil_div(R * 32, 256)), 256, 0, s>>>(ev, Jt, Tt, R, sc);
   VVT_TRY(launched("vvt_syevj(rayleigh)"));
+  if (jobz) {
+    VVT_TRY(gemm_nt(Sm, Jt, Tt, 0.0));  // S = J^T G J
+    VVT_TRY(gemm_nt(Mm, Jt, Jt, 0.0));  // M = J^T J
+    onesided_refine_coeff_kernel<T><<<gblocks, 256, 0, s>>>(Et, Sm, Mm, ev, R, sc);
+    VVT_TRY(launched("vvt_syevj(refine)"));
+    VVT_TRY(gemm_nt(Jt, Et, Jm, 1.0));  // J^T += E^T J^T
+  }
   jacobi_rank_kernel<T><<<unsigned(ceil_div(R, 128)), 128, 0, s>>>(rank, ev, R);
   VVT_TRY(launched("vvt_syevj(rank)"));
   const int64_t total = jobz ? R * R : R;
   const int pblocks = int(vmin<int64_t>(ceil_div(total, 256), 8 * num_sms()));
-  jacobi_permute_kernel<T><<<pblocks, 256, 0, s>>>(evals, jobz ? evecs : nullptr, ev, inv, Jm, rank, R);
+  jacobi_permute_kernel<T><<<pblocks, 256, 0, s>>>(evals, jobz ? evecs : nullptr, ev, Jt, rank, R);
   VVT_TRY(launched("vvt_syevj(permute)"));
   if (info) {
     info[0] = sweeps;

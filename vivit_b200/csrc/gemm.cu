@@ -4,6 +4,29 @@
 
 namespace vvt {
 
+// tcgen05 + TMA path for fp32 products with K-contiguous operands (gram_tc.cu)
+bool gram_tc_eligible(const float* A, const float* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                      int64_t batch);
+int64_t gram_tc_workspace_bytes(int64_t M, int64_t N, int64_t K, bool symmetric);
+int launch_gram_tc(const float* A, const float* B, StdStore<float> st, int64_t M, int64_t N, int64_t K, int64_t lda,
+                   int64_t ldb, bool symmetric, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
+                   const char* what);
+
+template <typename T>
+static bool tc_path(int& status, const T*, const T*, StdStore<T>, int64_t, int64_t, int64_t, int64_t, int64_t, bool,
+                    int64_t, void*, int64_t, cudaStream_t, const char*) {
+  (void)status;
+  return false;
+}
+template <>
+bool tc_path<float>(int& status, const float* A, const float* B, StdStore<float> st, int64_t M, int64_t N, int64_t K,
+                    int64_t lda, int64_t ldb, bool symmetric, int64_t batch, void* ws, int64_t wsb, cudaStream_t s,
+                    const char* what) {
+  if (!gram_tc_eligible(A, B, M, N, K, lda, ldb, batch)) return false;
+  status = launch_gram_tc(A, B, st, M, N, K, lda, ldb, symmetric, ws, wsb, s, what);
+  return true;
+}
+
 template <typename T>
 static StdStore<T> plain_store(T* C, int64_t ldc, int64_t batch_stride, double alpha, double beta) {
   StdStore<T> st{};
@@ -27,6 +50,8 @@ static int gemm_any(T* C, const T* A, const T* B, int64_t M, int64_t N, int64_t 
                     int64_t sa, int64_t sb, void* ws, int64_t wsb, cudaStream_t s, const char* what) {
   (void)C;
   if (!ta && !tb) {
+    int status = VVT_OK;
+    if (tc_path<T>(status, A, B, st, M, N, K, lda, ldb, symmetric, batch, ws, wsb, s, what)) return status;
     StridedLoader<T, true> la{A, lda, sa, M, K}, lb{B, ldb, sb, N, K};
     return launch_gemm_std<T>(la, lb, st, M, N, K, symmetric, batch, ws, wsb, s, what);
   } else if (!ta && tb) {
@@ -157,8 +182,17 @@ int vvt_gemm(void* C, const void* A, const void* B, int64_t M, int64_t N, int64_
 
 int64_t vvt_gram_workspace_bytes(int64_t rows, int64_t cols, int64_t depth, int dtype) {
   if (rows <= 0 || cols <= 0) return 0;
-  if (dtype == VVT_F32) return gemm_workspace_bytes<float>(rows, cols, depth, false);
-  return gemm_workspace_bytes<double>(rows, cols, depth, false);
+  if (dtype == VVT_F32) {
+    int64_t b = vmax(gemm_workspace_bytes<float>(rows, cols, depth, false),
+                     gram_tc_workspace_bytes(rows, cols, depth, false));
+    if (rows == cols)
+      b = vmax(b, vmax(gemm_workspace_bytes<float>(rows, cols, depth, true),
+                       gram_tc_workspace_bytes(rows, cols, depth, true)));
+    return b;
+  }
+  int64_t b = gemm_workspace_bytes<double>(rows, cols, depth, false);
+  if (rows == cols) b = vmax(b, gemm_workspace_bytes<double>(rows, cols, depth, true));
+  return b;
 }
 
 int vvt_gram_dense_accum(void* G, const void* V, int64_t R, int64_t D, void* workspace,
