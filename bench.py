@@ -34,6 +34,11 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 from torch import nn  # noqa: E402
 
+# torch's own convolutions (the model's forward/backward, not part of the hot path) default to TF32;
+# the metric is quoted for fp32 arithmetic, so they are pinned to fp32 for both arms
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 METRIC = "ms_per_ggn_curvature_step"
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
