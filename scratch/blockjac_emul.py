@@ -1,7 +1,7 @@
 """numpy emulation of one-sided block Jacobi variants on the real c2 Gram: sweeps to convergence."""
 import sys, numpy as np, time
 f = np.float32
-G = np.load('gpurun_out/G_c2.npy').astype(np.float64)
+G = np.load('scratch/G_c2.npy').astype(np.float64)
 G = (G + G.T) / 2
 R = G.shape[0]
 wref = np.linalg.eigvalsh(G)

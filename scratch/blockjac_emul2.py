@@ -1,7 +1,7 @@
 """Accuracy per sweep of one-sided Jacobi (scalar rotations, parallel round-robin order) on
 W=G versus W=chol(G+eps I); fp32; real c2 Gram.  Vectorised: one round = 640 disjoint column pairs."""
 import sys, numpy as np, time
-G = np.load('gpurun_out/G_c2.npy').astype(np.float64); G = (G + G.T) / 2
+G = np.load('scratch/G_c2.npy').astype(np.float64); G = (G + G.T) / 2
 R = G.shape[0]
 wref, Uref = np.linalg.eigh(G)
 lmax = wref[-1]
@@ -61,6 +61,11 @@ elif which == 'L3':
     shift = 1e-6 * lmax
     L = np.linalg.cholesky(G + shift * np.eye(R))
     run(L, True, shift, 1e-3, label='L3 W=chol tol 1e-3')
+elif which.startswith('S'):
+    shift = float(which[1:]) * np.linalg.norm(G)
+    print('shift/lmax', shift/lmax)
+    L = np.linalg.cholesky(G + shift * np.eye(R))
+    run(L, True, shift, 1e-5, label=which)
 elif which == 'Lt':
     shift = 1e-6 * lmax
     L = np.linalg.cholesky(G + shift * np.eye(R))

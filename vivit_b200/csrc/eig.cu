@@ -310,22 +310,13 @@ __device__ __forceinline__ void rotation_rounds(RotSmem<T>& rs, bool intra, T to
   }
 }
 
-// Rotation rounds on the cluster's rank-0 CTA only (the other CTAs would repeat identical work and
-// steal issue slots from co-resident clusters); the resulting Q is pushed into every CTA's Q through
-// distributed shared memory.  Ends with a cluster barrier: Q is valid everywhere afterwards.
+// Every CTA of the cluster runs the rotation rounds itself on its copy of H (identical inputs, identical
+// arithmetic => identical Q): nothing to broadcast and no cluster barrier after the Gram reduction.
 template <typename T>
 __device__ __forceinline__ void rotate_and_broadcast(RotSmem<T>& rs, cg::cluster_group& cluster, bool intra,
                                                      T tol2, T abs2, int tid) {
-  const int CL = int(cluster.num_blocks()), crank = int(cluster.block_rank());
-  if (crank == 0) {
-    rotation_rounds<T>(rs, intra, tol2, abs2, tid);
-    for (int idx = tid; idx < OP * OP; idx += OT) {
-      const int i = idx / OP, j = idx % OP;
-      const T v = rs.Q[i][j];
-      for (int p = 1; p < CL; ++p) *cluster.map_shared_rank(&rs.Q[i][j], p) = v;
-    }
-  }
-  if (CL > 1) cluster.sync();
+  (void)cluster;
+  rotation_rounds<T>(rs, intra, tol2, abs2, tid);
 }
 
 // this thread's share of a 4x4 tile of P^T P: rows r = ks, ks + 4, ... < nrows of a row-major chunk
@@ -411,10 +402,10 @@ __device__ __forceinline__ void round_blocks(int nb, int round, int pair, int& b
 // ---- resident variant: this CTA's rows of W and J are loaded once (cp.async) and stay in smem ----
 template <typename T>
 __global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 3 : 1))
-onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, JacobiScalars* sc) {
+onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RotSmem<T>& rs = *reinterpret_cast<RotSmem<T>*>(smem_raw);
-  T* P = reinterpret_cast<T*>(smem_raw + ((sizeof(RotSmem<T>) + 15) / 16) * 16);  // [2 * rows][LDP]: W rows, J rows
+  T* P = reinterpret_cast<T*>(smem_raw + ((sizeof(RotSmem<T>) + 15) / 16) * 16);  // [parts * rows][LDP]: W rows(, J rows)
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = int(cluster.num_blocks()), crank = int(cluster.block_rank());
   const int tid = threadIdx.x;
@@ -429,7 +420,7 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
   // all loads are issued up front: group 0 = W rows (needed now), group 1 = J rows (needed last)
   {
     constexpr int V = 16 / sizeof(T), VPR = OB / V;  // elements per 16 bytes, vectors per block row
-    for (int part = 0; part < 2; ++part) {
+    for (int part = 0; part < parts; ++part) {
       for (int idx = tid; idx < nrows * 2 * VPR; idx += OT) {
         const int r = idx / (2 * VPR), v = idx % (2 * VPR);
         const int blk = v < VPR ? ba : bb, col = (v % VPR) * V;
@@ -439,7 +430,7 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
       cp_async_commit();
     }
   }
-  cp_async_wait<1>();
+  if (parts == 2) cp_async_wait<1>(); else cp_async_wait<0>();
   __syncthreads();
   VVT_STAMP(1);
 
@@ -469,7 +460,7 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
   VVT_STAMP(5);
   {  // phase 3: P <- P Q for the W rows and the J rows, straight to global memory
     const int tr = tid >> 3, tc = tid & 7;
-    for (int part = 0; part < 2; ++part)
+    for (int part = 0; part < parts; ++part)
       for (int r_base = 0; r_base < nrows; r_base += 128)
         apply_rows<T>(rs, P + size_t(part) * nrows * LDP, LDP, r_base, nrows, Y, Np, ba, bb, part * Np + w0, tr, tc);
   }
@@ -497,7 +488,7 @@ __device__ __forceinline__ void load_chunk(T (*dst)[LDP], const T* Y, int Np, in
 
 template <typename T>
 __global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
-onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, JacobiScalars* sc) {
+onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StreamSmem<T>& sm = *reinterpret_cast<StreamSmem<T>*>(smem_raw);
   RotSmem<T>& rs = sm.rs;
@@ -542,7 +533,7 @@ onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, 
   rotate_and_broadcast<T>(rs, cluster, intra, tol2, abs2, tid);  // phase 2
   {  // phase 3: chunks of W rows, then of J rows
     const int tr = tid >> 3, tc = tid & 7;
-    const int total = 2 * n_chunks;
+    const int total = parts * n_chunks;
     for (int c = 0; c < total; ++c) {
       if (c + 1 < total) {
         const int part = (c + 1) >= n_chunks, cc = (c + 1) - part * n_chunks;
@@ -557,6 +548,139 @@ onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, 
                     part * Np + w0 + cc * CH, tr, tc);
       __syncthreads();
     }
+  }
+}
+
+// ---- Cholesky preconditioner ------------------------------------------------------------------------
+// G + eps I = L L^T with eps = 1e-3 ||G||_F.  The shift keeps the factor defined for rank-deficient or
+// slightly indefinite (rounding) Grams and leaves the eigenvectors untouched; because the rotation
+// threshold is relative (cosine <= tol), eigenvalue pairs far below eps are still separated to
+// tol * eps / gap, finer than the input precision allows, and a larger shift converges faster.  The
+// one-sided Jacobi is then run on the columns of L instead of G:  L J = U Sigma  gives
+// G + eps I = U Sigma^2 U^T, so the eigenvectors are the normalised columns of L J -- no J is
+// accumulated (half the traffic and flops per round) and the spectrum the rotations see is that of G,
+// not of G^2, which cuts the number of sweeps (19 -> 12 on the cifar10_3c3d Gram in fp32).
+// The factor only has to be a good starting point: eigenvalues are Rayleigh quotients with the
+// original G and the refinement step below works with the original G as well.
+constexpr int CB = 64;    // Cholesky block width
+constexpr int CROWS = 256;  // rows of the panel solved per CTA (one thread per row)
+
+template <typename T>
+__device__ __forceinline__ T chol_shift(const JacobiScalars* sc) {
+  return T(1e-3 * sqrt(sc->norm2));
+}
+
+// One step of the blocked right-looking factorisation on A (row-major, ld = R, lower triangle):
+// every CTA factors the diagonal block A[k:k+b, k:k+b] in shared memory (redundantly -- it is tiny),
+// CTA 0 writes it back, and the CTAs split the rows below it:  L21 = A21 L11^{-T}  by substitution.
+template <typename T>
+__global__ void __launch_bounds__(CROWS) chol_panel_kernel(T* A, int64_t R, int k, int b, const JacobiScalars* sc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T(*D)[CB + 1] = reinterpret_cast<T(*)[CB + 1]>(smem_raw);
+  T* diag = reinterpret_cast<T*>(smem_raw) + CB * (CB + 1);
+  T(*X)[CB + 1] = reinterpret_cast<T(*)[CB + 1]>(diag + CB);
+  const int tid = threadIdx.x;
+  const T floor_piv = chol_shift<T>(sc);
+  for (int idx = tid; idx < b * b; idx += CROWS) {
+    const int i = idx / b, j = idx % b;
+    D[i][j] = (j <= i) ? A[(int64_t(k) + i) * R + k + j] : T(0);
+  }
+  // this CTA's rows of the panel travel while the diagonal block is factored
+  const int64_t row0 = int64_t(k) + b + int64_t(blockIdx.x) * CROWS;
+  const int nrows = int(vmax<int64_t>(0, vmin<int64_t>(CROWS, R - row0)));
+  for (int idx = tid; idx < nrows * b; idx += CROWS) {
+    const int r = idx / b, c = idx % b;
+    X[r][c] = A[(row0 + r) * R + k + c];
+  }
+  for (int j = 0; j < b; ++j) {
+    __syncthreads();
+    const T piv = sqrt(vmax(D[j][j], floor_piv));  // D[j][j] itself is never overwritten
+    const T inv = T(1) / piv;
+    if (tid == j) diag[j] = piv;
+    if (tid > j && tid < b) D[tid][j] *= inv;
+    __syncthreads();
+    const int m = b - j - 1;
+    for (int idx = tid; idx < m * m; idx += CROWS) {
+      const int i = j + 1 + idx / m, l = j + 1 + idx % m;
+      if (l <= i) D[i][l] -= D[i][j] * D[l][j];
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int idx = tid; idx < b * b; idx += CROWS) {
+      const int i = idx / b, j = idx % b;
+      if (j <= i) A[(int64_t(k) + i) * R + k + j] = (i == j) ? diag[i] : D[i][j];
+    }
+  }
+  if (tid < nrows) {  // x L11^T = a
+    for (int c = 0; c < b; ++c) {
+      T s = X[tid][c];
+      for (int m = 0; m < c; ++m) s -= X[tid][m] * D[c][m];
+      X[tid][c] = s / diag[c];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nrows * b; idx += CROWS) {
+    const int r = idx / b, c = idx % b;
+    A[(row0 + r) * R + k + c] = X[r][c];
+  }
+}
+
+template <typename T>
+static size_t chol_smem_bytes() {
+  return (size_t(CB) * (CB + 1) + CB + size_t(CROWS) * (CB + 1)) * sizeof(T);
+}
+
+// A = Gs + eps I (the factorisation works in place on this copy)
+template <typename T>
+__global__ void chol_prepare_kernel(T* A, const T* Gs, int64_t R, const JacobiScalars* sc) {
+  const int64_t total = R * R;
+  const T eps = chol_shift<T>(sc);
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x)
+    A[idx] = Gs[idx] + ((idx / R == idx % R) ? eps : T(0));
+}
+
+// W = L / ||L||_F (lower triangle of A, zero above and in the padding); ||L||_F^2 = tr(G) + R eps <= sqrt(R) ||G||_F + R eps
+template <typename T>
+__global__ void onesided_init_chol_kernel(T* Y, const T* A, int64_t R, int Np, const JacobiScalars* sc) {
+  const int64_t total = int64_t(Np) * Np;
+  // any scale of the right magnitude will do (the rotations are scale free; thresholds assume O(1) columns)
+  const double bound = sqrt(double(R)) * sqrt(sc->norm2) + double(R) * double(chol_shift<T>(sc));
+  const T scale = bound > 0.0 ? T(1.0 / sqrt(bound)) : T(0);
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int i = int(idx / Np), j = int(idx % Np);  // row i, column j
+    const T v = (i < R && j <= i) ? A[int64_t(i) * R + j] * scale : T(0);
+    *(y_ptr(Y, Np, j / OB, i) + (j % OB)) = v;
+  }
+}
+
+// inv[c] = 1 / ||W[:, c]||  (one warp per column)
+template <typename T>
+__global__ void onesided_colnorm_kernel(T* inv, const T* Y, int64_t R, int Np) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (c >= R) return;
+  double s = 0.0;
+  for (int r = lane; r < R; r += 32) {
+    const double v = double(*(y_ptr(const_cast<T*>(Y), Np, int(c) / OB, r) + (int(c) % OB)));
+    s += v * v;
+  }
+  s = warp_sum(s);
+  if (lane == 0) inv[c] = s > 0.0 ? T(1.0 / sqrt(s)) : T(0);
+}
+
+// Jm[r][c] and Jt[c][r] <- normalised columns of the W part of Y
+template <typename T>
+__global__ void onesided_gather_w_kernel(T* Jm, T* Jt, const T* Y, const T* inv, int64_t R, int Np) {
+  const int64_t total = R * R;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int r = int(idx / R), c = int(idx % R);
+    Jm[idx] = *(y_ptr(const_cast<T*>(Y), Np, c / OB, r) + (c % OB)) * inv[c];
+    const int c2 = int(idx / R), r2 = int(idx % R);
+    Jt[int64_t(c2) * R + r2] = *(y_ptr(const_cast<T*>(Y), Np, c2 / OB, r2) + (c2 % OB)) * inv[c2];
   }
 }
 
@@ -660,7 +784,7 @@ __global__ void jacobi_permute_kernel(T* evals, T* evecs, const T* ev, const T* 
 }
 
 struct JacobiLayout {
-  int64_t Np, nb, off_Y, off_Gs, off_Jm, off_Jt, off_Tt, off_S, off_M, off_Et, off_ev, off_rank, off_sc, off_gemm, gemm_bytes, total;
+  int64_t Np, nb, off_Y, off_Gs, off_Jm, off_Jt, off_Tt, off_S, off_M, off_Et, off_ev, off_cn, off_rank, off_sc, off_gemm, gemm_bytes, total;
 };
 
 static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
@@ -682,6 +806,7 @@ static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
   L.off_M = take(R * R * es);
   L.off_Et = L.off_Y;  // Y is dead once J has been gathered (nb * 2 * Np * OB >= R * R elements)
   L.off_ev = take(R * es);
+  L.off_cn = take(R * es);
   L.off_rank = take(R * 4);
   L.off_sc = take(sizeof(JacobiScalars));
   L.gemm_bytes = vvt_gram_workspace_bytes(R, R, R, dtype);
@@ -691,15 +816,15 @@ static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
 }
 
 template <typename T>
-static size_t resident_smem_bytes(int rows_per_cta) {
-  return align_up(sizeof(RotSmem<T>), 16) + size_t(2) * rows_per_cta * LDP * sizeof(T);
+static size_t resident_smem_bytes(int rows_per_cta, int parts) {
+  return align_up(sizeof(RotSmem<T>), 16) + size_t(parts) * rows_per_cta * LDP * sizeof(T);
 }
 
 template <typename T>
-static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_cta, bool resident,
+static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_cta, int parts, bool resident,
                         JacobiScalars* sc, cudaStream_t s) {
   auto kern = resident ? onesided_round_resident_kernel<T> : onesided_round_stream_kernel<T>;
-  const size_t smem = resident ? resident_smem_bytes<T>(rows_per_cta) : sizeof(StreamSmem<T>);
+  const size_t smem = resident ? resident_smem_bytes<T>(rows_per_cta, parts) : sizeof(StreamSmem<T>);
   static size_t attr_done[2] = {0, 0};  // per instantiation: largest size configured so far
   if (attr_done[resident] < smem) {
     VVT_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
@@ -718,7 +843,7 @@ static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_ct
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, sc), "vvt_syevj(round)"));
+  VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, parts, sc), "vvt_syevj(round)"));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return VVT_OK;
 }
@@ -740,25 +865,64 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   JacobiScalars* sc = (JacobiScalars*)(ws + L.off_sc);
   const int Np = int(L.Np), nb = int(L.nb), pairs = nb / 2;
 
+  // Cholesky-preconditioned variant (default): rotate the columns of L, no J; VVT_SYEVJ_NOCHOL=1 selects
+  // the plain W = G J variant
+  static const bool use_chol = getenv("VVT_SYEVJ_NOCHOL") == nullptr;
+  const int parts = use_chol ? 1 : 2;
+  T* cn = (T*)(ws + L.off_cn);
+
   // rows of the panel are split over the CTAs of a cluster: as many as leave >= 16 rows per CTA
-  int CL = 8;
+  // (few CTAs per cluster: every CTA repeats the rotation rounds, and the cluster barriers of the Gram
+  // reduction are the main cost of a round; 640 rows per CTA measured best at R = 1280)
+  int CL = 1;
+  while (CL < 8 && Np / CL > 640) CL *= 2;
+  if (const char* e = getenv("VVT_SYEVJ_CL")) CL = vmax(1, vmin(8, atoi(e)));
   while (CL > 1 && Np / CL < 16) CL /= 2;
   const int rows_per_cta = int(ceil_div(Np, CL));
-  const bool resident = resident_smem_bytes<T>(rows_per_cta) <= size_t(200) * 1024;
+  const bool resident = resident_smem_bytes<T>(rows_per_cta, parts) <= size_t(200) * 1024;
 
   VVT_TRY(check_cuda(cudaMemsetAsync(sc, 0, sizeof(JacobiScalars), s), "vvt_syevj"));
   const bool debug = getenv("VVT_SYEVJ_DEBUG") != nullptr;
   const int init_blocks = int(vmin<int64_t>(ceil_div(L.Np * L.Np, 256), 8 * num_sms()));
-  onesided_sym_kernel<T><<<int(vmin<int64_t>(ceil_div(R * R, 256), 8 * num_sms())), 256, 0, s>>>(Gs, G, R, sc);
+  const int rr_blocks = int(vmin<int64_t>(ceil_div(R * R, 256), 8 * num_sms()));
+  onesided_sym_kernel<T><<<rr_blocks, 256, 0, s>>>(Gs, G, R, sc);
   VVT_TRY(launched("vvt_syevj(sym)"));
-  onesided_init_kernel<T><<<init_blocks, 256, 0, s>>>(Y, Gs, R, Np, sc);
-  VVT_TRY(launched("vvt_syevj(init)"));
+  if (use_chol) {
+    T* A = Jm;  // free until the gather
+    chol_prepare_kernel<T><<<rr_blocks, 256, 0, s>>>(A, Gs, R, sc);
+    VVT_TRY(launched("vvt_syevj(chol prepare)"));
+    static bool attr_done = false;  // per instantiation
+    if (!attr_done) {
+      VVT_TRY(check_cuda(cudaFuncSetAttribute(chol_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              int(chol_smem_bytes<T>())),
+                         "vvt_syevj(chol attr)"));
+      attr_done = true;
+    }
+    for (int64_t k = 0; k < R; k += CB) {
+      const int b = int(vmin<int64_t>(CB, R - k));
+      const int64_t below = R - k - b;
+      const unsigned ctas = unsigned(vmax<int64_t>(1, ceil_div(below, CROWS)));
+      chol_panel_kernel<T><<<ctas, CROWS, chol_smem_bytes<T>(), s>>>(A, R, int(k), b, sc);
+      VVT_TRY(launched("vvt_syevj(chol panel)"));
+      if (below > 0) {  // A22 -= L21 L21^T
+        T* A22 = A + (k + b) * R + (k + b);
+        const T* L21 = A + (k + b) * R + k;
+        VVT_TRY(vvt_gemm(A22, L21, L21, below, below, b, 0, 0, R, R, R, -1.0, 1.0, 1, 0, 0, 0, ws + L.off_gemm,
+                         L.gemm_bytes, dtype, (void*)s));
+      }
+    }
+    onesided_init_chol_kernel<T><<<init_blocks, 256, 0, s>>>(Y, A, R, Np, sc);
+    VVT_TRY(launched("vvt_syevj(init)"));
+  } else {
+    onesided_init_kernel<T><<<init_blocks, 256, 0, s>>>(Y, Gs, R, Np, sc);
+    VVT_TRY(launched("vvt_syevj(init)"));
+  }
 
   int sweeps = 0, converged = 0;
   for (; sweeps < kMaxSweeps;) {
     VVT_TRY(check_cuda(cudaMemsetAsync(&sc->rotations, 0, sizeof(unsigned long long), s), "vvt_syevj"));
     for (int round = -1; round < nb - 1; ++round)
-      VVT_TRY(launch_round<T>(Y, Np, nb, round, CL, rows_per_cta, resident, sc, s));
+      VVT_TRY(launch_round<T>(Y, Np, nb, round, CL, rows_per_cta, parts, resident, sc, s));
     ++sweeps;
     unsigned long long rot = 0;
     VVT_TRY(check_cuda(cudaMemcpyAsync(&rot, &sc->rotations, sizeof(rot), cudaMemcpyDeviceToHost, s),
@@ -778,7 +942,13 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
     }
   }
   const int gblocks = int(vmin<int64_t>(ceil_div(R * R, 256), 8 * num_sms()));
-  onesided_gather_j_kernel<T><<<gblocks, 256, 0, s>>>(Jm, Jt, Y, R, Np);
+  if (use_chol) {
+    onesided_colnorm_kernel<T><<<unsigned(ceil_div(R * 32, 256)), 256, 0, s>>>(cn, Y, R, Np);
+    VVT_TRY(launched("vvt_syevj(colnorm)"));
+    onesided_gather_w_kernel<T><<<gblocks, 256, 0, s>>>(Jm, Jt, Y, cn, R, Np);
+  } else {
+    onesided_gather_j_kernel<T><<<gblocks, 256, 0, s>>>(Jm, Jt, Y, R, Np);
+  }
   VVT_TRY(launched("vvt_syevj(gather)"));
   // every product below is C = A B^T with K-contiguous operands: the tcgen05 (fp32) / DMMA (fp64) GEMM
   auto gemm_nt = [&](T* C, const T* A, const T* B, double beta) {
