@@ -93,14 +93,20 @@ int vvt_loss_sqrt_hessian_mse(void* S, int64_t n_sub, int64_t C, double scale, i
 int vvt_sqrt_backprop_linear(void* out, const void* S, const void* W, int64_t rows, int64_t n_out,
                              int64_t n_in, int dtype, void* stream);
 
+/* Scratch for the fp32 tensor-core path of the two Conv2d entry points below: op = 0 for
+ * vvt_v_emit_conv2d (V, N as given there), op = 1 for vvt_sqrt_backprop_conv2d (V * N = rows).
+ * 0 for fp64.  Without (enough) workspace both fall back to the generic implicit-GEMM kernel. */
+int64_t vvt_conv2d_workspace_bytes(int op, int64_t V, int64_t N, int64_t c_out, int64_t h_out,
+                                   int64_t w_out, int64_t c_in, int64_t kh, int64_t kw, int dtype);
+
 /* data gradient of a 2d cross-correlation, applied to `rows` = V*N stacked maps.
  * S: [rows, c_out, h_out, w_out], W: [c_out, c_in, kh, kw], out: [rows, c_in, h_in, w_in].
- * groups = 1. */
+ * groups = 1.  fp32 with workspace: transpose (c_out contiguous) -> tcgen05 GEMM -> col2im gather. */
 int vvt_sqrt_backprop_conv2d(void* out, const void* S, const void* W, int64_t rows, int64_t c_out,
                              int64_t h_out, int64_t w_out, int64_t c_in, int64_t h_in, int64_t w_in,
                              int64_t kh, int64_t kw, int64_t stride_h, int64_t stride_w,
-                             int64_t pad_h, int64_t pad_w, int64_t dil_h, int64_t dil_w, int dtype,
-                             void* stream);
+                             int64_t pad_h, int64_t pad_w, int64_t dil_h, int64_t dil_w,
+                             void* workspace, int64_t workspace_bytes, int dtype, void* stream);
 
 /* out[v, n, f] = S[v, n, f] * J(ref[n, f]); S/out: [V, n*feat], ref: [n, feat] (see vvt_act). */
 int vvt_sqrt_backprop_elementwise(void* out, const void* S, const void* ref, int64_t V,
@@ -128,11 +134,13 @@ int vvt_sqrt_backprop_avgpool2d(void* out, const void* S, int64_t rows, int64_t 
 
 /* Vt[(v,n), (o, ci, ky, kx)] = sum_{oy,ox} S[v,n,o,oy,ox] X[n, ci, oy*sh+ky*dh-ph, ox*sw+kx*dw-pw]
  * S: [V, N, c_out, h_out, w_out], X: [N, c_in, h_in, w_in] (already sub-sampled),
- * Vt: [V*N, c_out*c_in*kh*kw] */
+ * Vt: [V*N, c_out*c_in*kh*kw]
+ * fp32 with workspace: im2col + re-layout (spatial index contiguous) -> batched tcgen05 GEMM per sample. */
 int vvt_v_emit_conv2d(void* Vt, const void* S, const void* X, int64_t V, int64_t N, int64_t c_out,
                       int64_t h_out, int64_t w_out, int64_t c_in, int64_t h_in, int64_t w_in,
                       int64_t kh, int64_t kw, int64_t stride_h, int64_t stride_w, int64_t pad_h,
-                      int64_t pad_w, int64_t dil_h, int64_t dil_w, int dtype, void* stream);
+                      int64_t pad_w, int64_t dil_h, int64_t dil_w, void* workspace,
+                      int64_t workspace_bytes, int dtype, void* stream);
 
 /* Vt[r, o] = sum_x S[r, o, x];  S: [rows, c_out, spatial] */
 int vvt_v_emit_bias(void* Vt, const void* S, int64_t rows, int64_t c_out, int64_t spatial,

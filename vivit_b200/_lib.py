@@ -25,11 +25,12 @@ SIGNATURES = {
     "vvt_loss_sqrt_hessian_ce_mc": (INT, [P, P, P, P, I64, I64, I64, I64, DBL, INT, P]),
     "vvt_loss_sqrt_hessian_mse": (INT, [P, I64, I64, DBL, INT, P]),
     "vvt_sqrt_backprop_linear": (INT, [P, P, P, I64, I64, I64, INT, P]),
-    "vvt_sqrt_backprop_conv2d": (INT, [P, P, P] + [I64] * 15 + [INT, P]),
+    "vvt_conv2d_workspace_bytes": (I64, [INT] + [I64] * 8 + [INT]),
+    "vvt_sqrt_backprop_conv2d": (INT, [P, P, P] + [I64] * 15 + [P, I64, INT, P]),
     "vvt_sqrt_backprop_elementwise": (INT, [P, P, P, I64, I64, INT, DBL, INT, P]),
     "vvt_sqrt_backprop_maxpool2d": (INT, [P, P, P] + [I64] * 15 + [INT, P]),
     "vvt_sqrt_backprop_avgpool2d": (INT, [P, P] + [I64] * 12 + [INT, P]),
-    "vvt_v_emit_conv2d": (INT, [P, P, P] + [I64] * 16 + [INT, P]),
+    "vvt_v_emit_conv2d": (INT, [P, P, P] + [I64] * 16 + [P, I64, INT, P]),
     "vvt_v_emit_bias": (INT, [P, P, I64, I64, I64, INT, P]),
     "vvt_v_emit_linear": (INT, [P, P, P, I64, I64, I64, I64, INT, P]),
     "vvt_gemm": (INT, [P, P, P, I64, I64, I64, INT, INT, I64, I64, I64, DBL, DBL, I64, I64, I64, I64, P, I64, INT, P]),

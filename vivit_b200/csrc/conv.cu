@@ -1,7 +1,9 @@
 // Conv2d pieces of the sqrt-GGN factor as implicit GEMMs on the shared main loop:
 //   * V emit: per-sample  Vt[(v,n), (o, j)] = sum_x S[v,n,o,x] * patch[n, j, x]
 //   * data gradient of the factor ("virtual batch" of V*N maps)
-#include "gemm_core.cuh"
+#include <cstdlib>
+
+#include "gemm_tc.cuh"
 
 namespace vvt {
 
@@ -95,6 +97,156 @@ struct DgradStore {
   }
 };
 
+
+// ---- fp32 fast path: bandwidth-bound re-layout kernels around the batched tcgen05 GEMM ---------------
+// HBM is plentiful on B200 (180 GB, ~6.5 TB/s), so the convolution is made explicit: patches are
+// unfolded, the factor is re-laid out so that the contraction index is contiguous (what TMA + UMMA
+// want), and every flop runs in gemm_tc.cuh.  Each helper reads and writes its operands once.
+
+#define VVT_GRID_STRIDE(i, total)                                              \
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < (total); \
+       i += int64_t(gridDim.x) * blockDim.x)
+
+static inline int ew_blocks(int64_t total) {
+  return int(vmax<int64_t>(1, vmin<int64_t>(ceil_div(total, 256), 32 * num_sms())));
+}
+
+// Sn[n][(v, o)][x] (row pitch Xp) <- S[v][n][o][x]
+__global__ void emit_permute_kernel(float* Sn, const float* S, int V, int N, int CoX_rows, int X, int Xp) {
+  const int64_t total = int64_t(N) * V * CoX_rows * Xp;
+  VVT_GRID_STRIDE(i, total) {
+    const int x = int(i % Xp);
+    int64_t t = i / Xp;
+    const int o = int(t % CoX_rows);
+    t /= CoX_rows;
+    const int v = int(t % V), n = int(t / V);
+    Sn[i] = x < X ? ldg(S + ((int64_t(v) * N + n) * CoX_rows + o) * X + x) : 0.f;
+  }
+}
+
+// Un[n][j = (ci, ky, kx)][x = (oy, ox)] (row pitch Xp) <- unfolded input patches
+__global__ void im2col_kernel(float* Un, const float* Xin, ConvGeom g, int N, int J, int X, int Xp) {
+  const int64_t total = int64_t(N) * J * Xp;
+  VVT_GRID_STRIDE(i, total) {
+    const int x = int(i % Xp);
+    const int64_t t = i / Xp;
+    const int j = int(t % J), n = int(t / J);
+    float val = 0.f;
+    if (x < X) {
+      const int kx = j % g.kw, ky = (j / g.kw) % g.kh, ci = j / (g.kw * g.kh);
+      const int ox = x % g.w_out, oy = x / g.w_out;
+      const int iy = oy * g.sh + ky * g.dh - g.ph, ix = ox * g.sw + kx * g.dw - g.pw;
+      if (iy >= 0 && iy < g.h_in && ix >= 0 && ix < g.w_in)
+        val = ldg(Xin + ((int64_t(n) * g.c_in + ci) * g.h_in + iy) * g.w_in + ix);
+    }
+    Un[i] = val;
+  }
+}
+
+struct EmitStoreTc {
+  float* Vt;
+  int64_t N, c_out, J, batch0;
+  __device__ __forceinline__ void operator()(int n, int64_t m, int64_t j, float val, int) const {
+    const int64_t v = m / c_out, o = m % c_out;
+    Vt[((v * N + (batch0 + n)) * c_out + o) * J + j] = val;
+  }
+};
+
+// St[(r, x)][o] (row pitch Cop) <- S[r][o][x]: one 32x32 tile per block, transposed through shared memory
+__global__ void __launch_bounds__(256) dgrad_transpose_kernel(float* St, const float* S, int Co, int X, int Cop) {
+  __shared__ float tile[32][33];
+  const int64_t r = blockIdx.x;
+  const int x0 = blockIdx.y * 32, o0 = blockIdx.z * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = ty; k < 32; k += 8) {
+    const int o = o0 + k, x = x0 + tx;
+    tile[k][tx] = (o < Co && x < X) ? ldg(S + (r * Co + o) * X + x) : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int x = x0 + k, o = o0 + tx;
+    if (x < X && o < Cop) St[(r * X + x) * Cop + o] = tile[tx][k];  // o in [Co, Cop) is zero
+  }
+}
+
+// Wt[j][o] (row pitch Cop) <- W[o][j]
+__global__ void weight_transpose_kernel(float* Wt, const float* W, int Co, int J, int Cop) {
+  const int64_t total = int64_t(J) * Cop;
+  VVT_GRID_STRIDE(i, total) {
+    const int o = int(i % Cop), j = int(i / Cop);
+    Wt[i] = o < Co ? ldg(W + int64_t(o) * J + j) : 0.f;
+  }
+}
+
+// T2[r][j][x] <- C[(r, x), j]
+struct DgradStoreTc {
+  float* T2;
+  int64_t X, J, batch0;
+  __device__ __forceinline__ void operator()(int, int64_t m, int64_t j, float val, int) const {
+    const int64_t r = m / X, x = m % X;
+    T2[(r * J + j) * X + x] = val;
+  }
+};
+
+// out[r][ci][iy][ix] = sum over (ky, kx) of T2[r][(ci, ky, kx)][(oy, ox)] with oy*sh + ky*dh - ph = iy, ...
+__global__ void col2im_kernel(float* out, const float* T2, ConvGeom g, int64_t rows, int J, int X) {
+  const int hw = g.h_in * g.w_in;
+  const int64_t total = rows * g.c_in * hw;
+  VVT_GRID_STRIDE(i, total) {
+    const int p = int(i % hw);
+    const int64_t t = i / hw;
+    const int ci = int(t % g.c_in);
+    const int64_t r = t / g.c_in;
+    const int iy = p / g.w_in, ix = p % g.w_in;
+    const float* base = T2 + (r * J + int64_t(ci) * g.kh * g.kw) * X;
+    float acc = 0.f;
+    for (int ky = 0; ky < g.kh; ++ky) {
+      const int ty = iy + g.ph - ky * g.dh;
+      if (ty < 0 || ty % g.sh) continue;
+      const int oy = ty / g.sh;
+      if (oy >= g.h_out) continue;
+      for (int kx = 0; kx < g.kw; ++kx) {
+        const int tx = ix + g.pw - kx * g.dw;
+        if (tx < 0 || tx % g.sw) continue;
+        const int ox = tx / g.sw;
+        if (ox >= g.w_out) continue;
+        acc += ldg(base + int64_t(ky * g.kw + kx) * X + oy * g.w_out + ox);
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+struct ConvWorkspace {
+  int64_t a, b, c, total;  // byte offsets of up to three regions
+};
+static inline int64_t pad4(int64_t v) { return align_up(v, 4); }
+// emit: Sn [N][V*Co][Xp] | Un [N][J][Xp]
+static ConvWorkspace emit_workspace(int64_t V, int64_t N, int64_t Co, int64_t J, int64_t X) {
+  ConvWorkspace w;
+  const int64_t Xp = pad4(X);
+  w.a = 0;
+  w.b = align_up(N * V * Co * Xp * 4, 256);
+  w.c = w.b + align_up(N * J * Xp * 4, 256);
+  w.total = w.c;
+  return w;
+}
+// dgrad: St [rows*X][Cop] | Wt [J][Cop] | T2 [rows][J][X]
+static ConvWorkspace dgrad_workspace(int64_t rows, int64_t Co, int64_t Jd, int64_t X) {
+  ConvWorkspace w;
+  const int64_t Cop = pad4(Co);
+  w.a = 0;
+  w.b = align_up(rows * X * Cop * 4, 256);
+  w.c = w.b + align_up(Jd * Cop * 4, 256);
+  w.total = w.c + align_up(rows * Jd * X * 4, 256);
+  return w;
+}
+
+static bool tc_conv_enabled() {
+  static const bool off = getenv("VVT_CONV_IMPLICIT") != nullptr || getenv("VVT_NO_TCGEN05") != nullptr;
+  return !off && tc::encode_fn() != nullptr;
+}
+
 }  // namespace vvt
 
 using namespace vvt;
@@ -115,10 +267,18 @@ static int make_geom(ConvGeom& g, int64_t c_out, int64_t h_out, int64_t w_out, i
 
 extern "C" {
 
+int64_t vvt_conv2d_workspace_bytes(int op, int64_t V, int64_t N, int64_t c_out, int64_t h_out, int64_t w_out,
+                                   int64_t c_in, int64_t kh, int64_t kw, int dtype) {
+  if (dtype != VVT_F32 || V <= 0 || N <= 0 || c_out <= 0 || h_out * w_out <= 0 || c_in * kh * kw <= 0) return 0;
+  const int64_t X = h_out * w_out, J = c_in * kh * kw;
+  return op == 0 ? emit_workspace(V, N, c_out, J, X).total : dgrad_workspace(V * N, c_out, J, X).total;
+}
+
 int vvt_v_emit_conv2d(void* Vt, const void* S, const void* X, int64_t V, int64_t N, int64_t c_out,
                       int64_t h_out, int64_t w_out, int64_t c_in, int64_t h_in, int64_t w_in,
                       int64_t kh, int64_t kw, int64_t stride_h, int64_t stride_w, int64_t pad_h,
-                      int64_t pad_w, int64_t dil_h, int64_t dil_w, int dtype, void* stream) {
+                      int64_t pad_w, int64_t dil_h, int64_t dil_w, void* workspace, int64_t workspace_bytes,
+                      int dtype, void* stream) {
   VVT_REQUIRE(V >= 0 && N >= 0, "negative size");
   ConvGeom g;
   VVT_TRY(make_geom(g, c_out, h_out, w_out, c_in, h_in, w_in, kh, kw, stride_h, stride_w, pad_h, pad_w,
@@ -126,6 +286,23 @@ int vvt_v_emit_conv2d(void* Vt, const void* S, const void* X, int64_t V, int64_t
   const int64_t M = V * c_out, J = c_in * kh * kw, Xn = h_out * w_out;
   if (M == 0 || J == 0 || N == 0) return VVT_OK;
   VVT_REQUIRE(Vt && S && X, "null pointer");
+  if (dtype == VVT_F32 && Xn > 0 && workspace && tc_conv_enabled() &&
+      workspace_bytes >= emit_workspace(V, N, c_out, J, Xn).total && M < (int64_t(1) << 31)) {
+    // unfold + re-layout + batched tcgen05 GEMM (one batch entry per sample)
+    const ConvWorkspace w = emit_workspace(V, N, c_out, J, Xn);
+    const int64_t Xp = pad4(Xn);
+    float* Sn = (float*)((char*)workspace + w.a);
+    float* Un = (float*)((char*)workspace + w.b);
+    cudaStream_t s = as_stream(stream);
+    emit_permute_kernel<<<ew_blocks(N * M * Xp), 256, 0, s>>>(Sn, (const float*)S, int(V), int(N), int(c_out),
+                                                             int(Xn), int(Xp));
+    VVT_TRY(launched("vvt_v_emit_conv2d(permute)"));
+    im2col_kernel<<<ew_blocks(N * J * Xp), 256, 0, s>>>(Un, (const float*)X, g, int(N), int(J), int(Xn), int(Xp));
+    VVT_TRY(launched("vvt_v_emit_conv2d(im2col)"));
+    EmitStoreTc st{(float*)Vt, N, c_out, J, 0};
+    return tc::launch_gemm_tc_batched<EmitStoreTc, true>(Sn, Un, st, M, J, Xn, Xp, Xp, N, M * Xp, J * Xp, s,
+                                                         "vvt_v_emit_conv2d");
+  }
   VVT_DISPATCH(dtype, {
     if (Xn == 0) return check_cuda(cudaMemsetAsync(Vt, 0, V * N * c_out * J * sizeof(T), as_stream(stream)), __func__);
     EmitLoaderS<T> la{(const T*)S, N, c_out, Xn, M};
@@ -138,8 +315,8 @@ int vvt_v_emit_conv2d(void* Vt, const void* S, const void* X, int64_t V, int64_t
 int vvt_sqrt_backprop_conv2d(void* out, const void* S, const void* W, int64_t rows, int64_t c_out,
                              int64_t h_out, int64_t w_out, int64_t c_in, int64_t h_in, int64_t w_in,
                              int64_t kh, int64_t kw, int64_t stride_h, int64_t stride_w,
-                             int64_t pad_h, int64_t pad_w, int64_t dil_h, int64_t dil_w, int dtype,
-                             void* stream) {
+                             int64_t pad_h, int64_t pad_w, int64_t dil_h, int64_t dil_w, void* workspace,
+                             int64_t workspace_bytes, int dtype, void* stream) {
   VVT_REQUIRE(rows >= 0, "negative size");
   ConvGeom g;
   VVT_TRY(make_geom(g, c_out, h_out, w_out, c_in, h_in, w_in, kh, kw, stride_h, stride_w, pad_h, pad_w,
@@ -147,6 +324,29 @@ int vvt_sqrt_backprop_conv2d(void* out, const void* S, const void* W, int64_t ro
   const int64_t hw = h_in * w_in, M = rows * hw, Kd = c_out * kh * kw;
   if (M == 0 || c_in == 0) return VVT_OK;
   VVT_REQUIRE(out && S && W, "null pointer");
+  const int64_t Xo = h_out * w_out, Jd = c_in * kh * kw;
+  if (dtype == VVT_F32 && Xo > 0 && c_out > 0 && workspace && tc_conv_enabled() &&
+      workspace_bytes >= dgrad_workspace(rows, c_out, Jd, Xo).total && rows * Xo < (int64_t(1) << 31)) {
+    // transpose (contraction index c_out contiguous) + one tcgen05 GEMM + col2im gather
+    const ConvWorkspace w = dgrad_workspace(rows, c_out, Jd, Xo);
+    const int64_t Cop = pad4(c_out);
+    float* St = (float*)((char*)workspace + w.a);
+    float* Wt = (float*)((char*)workspace + w.b);
+    float* T2 = (float*)((char*)workspace + w.c);
+    cudaStream_t s = as_stream(stream);
+    const int64_t ybl = ceil_div(Xo, 32), zbl = ceil_div(Cop, 32);
+    if (ybl > 65535 || zbl > 65535) return fail(VVT_ERR_UNSUPPORTED, "%s", "conv2d: map too large");
+    dgrad_transpose_kernel<<<dim3(unsigned(rows), unsigned(ybl), unsigned(zbl)), 256, 0, s>>>(
+        St, (const float*)S, int(c_out), int(Xo), int(Cop));
+    VVT_TRY(launched("vvt_sqrt_backprop_conv2d(transpose)"));
+    weight_transpose_kernel<<<ew_blocks(Jd * Cop), 256, 0, s>>>(Wt, (const float*)W, int(c_out), int(Jd), int(Cop));
+    VVT_TRY(launched("vvt_sqrt_backprop_conv2d(weights)"));
+    DgradStoreTc st{T2, Xo, Jd, 0};
+    VVT_TRY((tc::launch_gemm_tc_batched<DgradStoreTc, false>(St, Wt, st, rows * Xo, Jd, c_out, Cop, Cop, 1, 0, 0, s,
+                                                             "vvt_sqrt_backprop_conv2d")));
+    col2im_kernel<<<ew_blocks(M * c_in), 256, 0, s>>>((float*)out, T2, g, rows, int(Jd), int(Xo));
+    return launched("vvt_sqrt_backprop_conv2d(col2im)");
+  }
   VVT_DISPATCH(dtype, {
     DgradLoaderS<T> la{(const T*)S, g, M, Kd};
     DgradLoaderW<T> lb{(const T*)W, g, Kd};

@@ -89,19 +89,22 @@ __global__ void act_kernel(T* out, const T* S, const T* ref, int64_t V, int64_t 
   }
 }
 
-// gather form of the max-pool scatter: every input position sums the outputs that chose it
-template <typename T>
+// gather form of the max-pool scatter: every input position sums the outputs that chose it.
+// I = index type (32-bit whenever the output has < 2^31 elements: 64-bit div/mod is what this
+// kernel would otherwise spend its time on)
+template <typename T, typename I>
 __global__ void maxpool_bwd_kernel(T* out, const T* S, const int64_t* argmax, int64_t rows, int64_t N,
                                    int64_t ch, int ho, int wo, int hi, int wi, int kh, int kw, int sh,
                                    int sw, int ph, int pw, int dh, int dw) {
-  const int64_t total = rows * ch * hi * wi;
-  GRID_STRIDE(i, total) {
-    const int x = int(i % wi), y = int((i / wi) % hi);
-    const int64_t c = (i / (int64_t(wi) * hi)) % ch, r = i / (int64_t(wi) * hi * ch);
-    const int64_t n = r % N;
-    const int64_t pos = int64_t(y) * wi + x;
-    const T* s = S + (r * ch + c) * int64_t(ho) * wo;
-    const int64_t* am = argmax + (n * ch + c) * int64_t(ho) * wo;
+  const I total = I(rows * ch * hi * wi);
+  const I hw_in = I(hi) * I(wi), hw_out = I(ho) * I(wo), chI = I(ch), NI = I(N);
+  for (I i = I(blockIdx.x) * I(blockDim.x) + I(threadIdx.x); i < total; i += I(gridDim.x) * I(blockDim.x)) {
+    const I pl = i / hw_in;  // plane = r * ch + c
+    const int pos = int(i - pl * hw_in);
+    const int y = pos / wi, x = pos - y * wi;
+    const I r = pl / chI, c = pl - r * chI, n = r % NI;
+    const T* s = S + pl * hw_out;
+    const int64_t* am = argmax + (n * chI + c) * hw_out;
     T acc = 0;
     for (int ky = 0; ky < kh; ++ky) {
       const int ty = y + ph - ky * dh;
@@ -113,7 +116,7 @@ __global__ void maxpool_bwd_kernel(T* out, const T* S, const int64_t* argmax, in
         if (tx < 0 || tx % sw) continue;
         const int ox = tx / sw;
         if (ox >= wo) continue;
-        if (am[oy * wo + ox] == pos) acc += s[oy * wo + ox];
+        if (int(am[oy * wo + ox]) == pos) acc += s[oy * wo + ox];
       }
     }
     out[i] = acc;
@@ -272,7 +275,7 @@ using namespace vvt;
 
 extern "C" {
 
-int vvt_abi_version(void) { return 1; }
+int vvt_abi_version(void) { return 2; }
 const char* vvt_last_error(void) { return last_error_buffer(); }
 int64_t vvt_launch_count(void) { return g_launches.load(); }
 
@@ -346,9 +349,15 @@ int vvt_sqrt_backprop_maxpool2d(void* out, const void* S, const int64_t* argmax,
   if (total == 0) return VVT_OK;
   VVT_REQUIRE(out && S && argmax, "null pointer");
   VVT_DISPATCH(dtype, {
-    maxpool_bwd_kernel<T><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
-        (T*)out, (const T*)S, argmax, V * N, N, ch, int(h_out), int(w_out), int(h_in), int(w_in),
-        int(kh), int(kw), int(stride_h), int(stride_w), int(pad_h), int(pad_w), int(dil_h), int(dil_w));
+    if (total < (int64_t(1) << 31) - (int64_t(1) << 24)) {
+      maxpool_bwd_kernel<T, unsigned><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+          (T*)out, (const T*)S, argmax, V * N, N, ch, int(h_out), int(w_out), int(h_in), int(w_in),
+          int(kh), int(kw), int(stride_h), int(stride_w), int(pad_h), int(pad_w), int(dil_h), int(dil_w));
+    } else {
+      maxpool_bwd_kernel<T, int64_t><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+          (T*)out, (const T*)S, argmax, V * N, N, ch, int(h_out), int(w_out), int(h_in), int(w_in),
+          int(kh), int(kw), int(stride_h), int(stride_w), int(pad_h), int(pad_w), int(dil_h), int(dil_w));
+    }
     return launched(__func__);
   });
 }

@@ -1,339 +1,18 @@
-// fp32 Gram / NT-GEMM on the 5th-generation tensor cores (tcgen05), fed by TMA.
-//
-//   acc[m, n] = sum_k A[m, k] * B[n, k]          A: [M, K], B: [N, K], both K-contiguous (fp32)
-//
-// fp32-grade accuracy comes from the 3xTF32 split  a*b ~= ah*bh + ah*bl + al*bh, where ah is the
-// tf32 the tensor core sees when it reads an fp32 word (the 13 low mantissa bits are ignored) and
-// al = rna_tf32(a - ah) is produced in shared memory by four converter warps.  Nothing is split in
-// global memory: one TMA load per operand tile and k-block, the raw tile doubles as the "hi" operand.
-//
-// CTA = one 128x128 output tile x one K range (split-K), 6 warps:
-//   warp 0      TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, 128 rows x 32 floats per tile)
-//   warp 1      MMA issuer     (tcgen05.mma.cta_group::1.kind::tf32, M = N = 128, K = 8; accumulators
-//                               in 128 TMEM columns); hi*hi is issued as soon as the tile lands,
-//                               hi*lo + lo*hi after the converters are done
-//   warps 2..5  converters     (raw -> lo tiles), then the epilogue (tcgen05.ld -> registers -> store)
-// Pipeline: 3 stages of {A raw, B raw, A lo, B lo} = 64 KB each; mbarriers tma_full / conv_full /
-// empty per stage.  Diagonal tiles of a symmetric product load A only.
-//
-// Two-level accumulation: the tensor core adds into its fp32 accumulator with truncation, a bias of
-// about -2^-24 of the running sum per MMA (measured: -1e-4 on Gram diagonals after 2300 steps).  The
-// MMA warp therefore accumulates only PROMOTE k-blocks (48 MMAs) into one of two TMEM buffers; the
-// converter warps drain the finished buffer into fp32 registers (round-to-nearest adds) while the
-// next group runs in the other buffer.  Residual bias on sums of same-sign products: about -3e-6.
-#include <cuda.h>
-
+// fp32 Gram / NT-GEMM entry points on the tcgen05 + TMA kernel of gemm_tc.cuh (StdStore epilogue, split-K).
 #include <cstdlib>
 
-#include "gemm_core.cuh"
+#include "gemm_tc.cuh"
 
 namespace vvt {
-namespace tc {
-
-constexpr int BM = 128, BN = 128, BK = 32;  // BK floats = 128 bytes = one swizzle row
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 4;     // 16 KB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES; // A raw | B raw | A lo | B lo
-constexpr int THREADS = 192;
-constexpr int TMEM_COLS = 256;  // two accumulator buffers of 128 columns
-constexpr int PROMOTE = 4;      // k-blocks accumulated in the tensor core before promotion to registers
-constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// bounded wait (~2 s): a protocol bug traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  long long t0 = 0;
-  for (uint32_t spins = 0; !done; ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && (spins & 63) == 63) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major operand tile [rows][32 floats], 128-byte swizzle, 8-row groups 1024 bytes apart
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);  // start address
-  d |= uint64_t(1) << 16;                     // leading byte offset (ignored for swizzled K-major)
-  d |= uint64_t(1024 >> 4) << 32;             // stride byte offset
-  d |= uint64_t(1) << 46;                     // descriptor version (Blackwell)
-  d |= uint64_t(2) << 61;                     // SWIZZLE_128B
-  return d;
-}
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
-
-template <typename ST>
-__global__ void __launch_bounds__(THREADS, 1)
-gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, ST st,
-               int64_t M, int64_t N, int tiles_n, int symmetric, int kblocks_total, int kblocks_per_split) {
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // tiles must be 1024-byte aligned
-  unsigned char* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bars = base + STAGES * STAGE_BYTES;
-  // barrier slots (8 bytes each): tma_full[S] | conv_full[S] | empty[S] | acc_full[2] | acc_empty[2]; then the
-  // TMEM address
-  auto bar_tma = [&](int s) { return bars + 8u * s; };
-  auto bar_conv = [&](int s) { return bars + 8u * (STAGES + s); };
-  auto bar_empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-  auto bar_acc_full = [&](int b) { return bars + 8u * (3 * STAGES + b); };
-  auto bar_acc_empty = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
-
-  int tm, tn;
-  if (symmetric) {  // upper-triangular tile pairs, row by row
-    int rem = blockIdx.x, len = tiles_n;
-    tm = 0;
-    while (rem >= len) {
-      rem -= len;
-      ++tm;
-      --len;
-    }
-    tn = tm + rem;
-  } else {
-    tm = blockIdx.x / tiles_n;
-    tn = blockIdx.x % tiles_n;
-  }
-  const bool diag = symmetric && tm == tn;
-  const int split = blockIdx.y;
-  const int kb0 = split * kblocks_per_split, kb1 = min(kblocks_total, kb0 + kblocks_per_split);
-  const int nkb = kb1 - kb0;  // >= 1 (host guarantees)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_tma(s), 1);
-      mbar_init(bar_conv(s), 128);
-      mbar_init(bar_empty(s), 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_acc_full(b), 1);
-      mbar_init(bar_acc_empty(b), 128);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, use = i / STAGES;
-        if (use > 0) mbar_wait(bar_empty(s), (use - 1) & 1);
-        const uint32_t stage = base + s * STAGE_BYTES;
-        mbar_expect_tx(bar_tma(s), diag ? TILE_BYTES : 2 * TILE_BYTES);
-        const int k0 = (kb0 + i) * BK;
-        tma_load_2d(stage, &mapA, bar_tma(s), k0, tm * BM);
-        if (!diag) tma_load_2d(stage + TILE_BYTES, &mapB, bar_tma(s), k0, tn * BN);
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, use = i / STAGES;
-        const int grp = i / PROMOTE, first = (i % PROMOTE) == 0;
-        const uint32_t acc = tmem_base + uint32_t((grp & 1) * BN);
-        const uint32_t stage = base + s * STAGE_BYTES;
-        const uint32_t a_hi = stage, b_hi = diag ? stage : stage + TILE_BYTES;
-        const uint32_t a_lo = stage + 2 * TILE_BYTES, b_lo = diag ? a_lo : stage + 3 * TILE_BYTES;
-        if (first && grp >= 2) {  // the buffer was drained two groups ago?
-          mbar_wait(bar_acc_empty(grp & 1), ((grp >> 1) - 1) & 1);
-          tcgen05_fence_after();
-        }
-        mbar_wait(bar_tma(s), use & 1);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int k = 0; k < BK / 8; ++k)  // 8 tf32 = 32 bytes per MMA along K
-          umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_hi + 32 * k), kIdesc, !(first && k == 0));
-        mbar_wait(bar_conv(s), use & 1);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_lo + 32 * k), kIdesc, 1);
-          umma_tf32(acc, make_desc(a_lo + 32 * k), make_desc(b_hi + 32 * k), kIdesc, 1);
-        }
-        umma_commit(bar_empty(s));  // frees the stage once these MMAs have read it
-        if ((i % PROMOTE) == PROMOTE - 1 || i == nkb - 1) umma_commit(bar_acc_full(grp & 1));
-      }
-    }
-  } else {
-    // ===== converters: lo = rna_tf32(x - trunc_tf32(x)); promotion of finished accumulator groups =====
-    const int ct = threadIdx.x - 64;  // 0..127
-    const int n_vec = (diag ? 1 : 2) * (TILE_BYTES / 16);
-    const int lane_grp = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-    const int n_groups = (nkb + PROMOTE - 1) / PROMOTE;
-    float total[BN];  // this thread's row of the output tile, summed with round-to-nearest adds
-#pragma unroll
-    for (int j = 0; j < BN; ++j) total[j] = 0.f;
-    auto drain = [&](int grp) {
-      mbar_wait(bar_acc_full(grp & 1), (grp >> 1) & 1);
-      tcgen05_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t((grp & 1) * BN + c0), r);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) total[c0 + j] += __uint_as_float(r[j]);
-      }
-      tcgen05_fence_before();
-      mbar_arrive(bar_acc_empty(grp & 1));
-    };
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % STAGES, use = i / STAGES;
-      unsigned char* stage = base_ptr + s * STAGE_BYTES;
-      mbar_wait(bar_tma(s), use & 1);
-      // lo buffers of this stage are free: the MMAs that read them committed to `empty` before the
-      // producer refilled the stage, and that refill is what we just waited for
-#pragma unroll 4
-      for (int v = ct; v < n_vec; v += 128) {
-        const float4 x = *reinterpret_cast<const float4*>(stage + size_t(v) * 16);
-        float4 lo;
-        {
-          const float e[4] = {x.x, x.y, x.z, x.w};
-          float o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float hi = __uint_as_float(__float_as_uint(e[j]) & 0xFFFFE000u);
-            o[j] = __uint_as_float(to_tf32(e[j] - hi));
-          }
-          lo = make_float4(o[0], o[1], o[2], o[3]);
-        }
-        *reinterpret_cast<float4*>(stage + 2 * TILE_BYTES + size_t(v) * 16) = lo;
-      }
-      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(bar_conv(s));
-      // one group behind the conversions, so that the wait is (almost) never a stall
-      if ((i % PROMOTE) == PROMOTE - 1 && i / PROMOTE >= 1) drain(i / PROMOTE - 1);
-    }
-    // groups not drained yet: the last one, and the one before it if the last group was complete
-    for (int g = (nkb % PROMOTE == 0) ? n_groups - 1 : vmax(0, n_groups - 2); g < n_groups; ++g) drain(g);
-    // ===== epilogue: registers -> store =====
-    const int64_t row = int64_t(tm) * BM + lane_grp * 32 + lane;
-    const bool mirror = symmetric && !diag;
-    if (row < M) {
-#pragma unroll
-      for (int j = 0; j < BN; ++j) {
-        const int64_t col = int64_t(tn) * BN + j;
-        if (col < N) {
-          st(0, row, col, total[j], split);
-          if (mirror) st(0, col, row, total[j], split);
-        }
-      }
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-  }
-}
-
-// ---- host side --------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// 2-d map over a row-major [rows, cols] fp32 matrix with leading dimension ld; box = 128 rows x 32 floats
-static bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  const cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
-  const cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
-  const cuuint32_t box[2] = {BK, BM};
-  const cuuint32_t estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-}  // namespace tc
 
 bool gram_tc_eligible(const float* A, const float* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                       int64_t batch) {
   static const bool disabled = getenv("VVT_NO_TCGEN05") != nullptr;
   if (disabled || batch != 1) return false;
   if (K < 4 * tc::BK || M < 32 || N < 32) return false;  // tiny products: the SIMT-fed path has less overhead
-  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) return false;
-  if ((lda | ldb) & 3) return false;  // TMA row pitch must be a multiple of 16 bytes
+  if (!tc::operands_ok(A, B, lda, ldb, 0, 0)) return false;  // TMA alignment rules
   if (M >= (int64_t(1) << 31) || N >= (int64_t(1) << 31) || K >= (int64_t(1) << 31)) return false;
-  return tc::encode_fn() != nullptr;
+  return true;
 }
 
 // Split-K factor: one CTA per SM is resident, so the kernel runs in waves of num_sms CTAs; pick the
@@ -362,14 +41,14 @@ int launch_gram_tc(const float* A, const float* B, StdStore<float> st, int64_t M
                    int64_t ldb, bool symmetric, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
                    const char* what) {
   using namespace tc;
-  auto kern = gram_tc_kernel<StdStore<float>>;
+  auto kern = gram_tc_kernel<StdStore<float>, false>;
   static bool attr_done = false;
   if (!attr_done) {
     VVT_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)), what));
     attr_done = true;
   }
   CUtensorMap mapA, mapB;
-  if (!make_map(&mapA, A, M, K, lda) || !make_map(&mapB, B, N, K, ldb))
+  if (!make_map(&mapA, A, M, K, lda, 1, 0) || !make_map(&mapB, B, N, K, ldb, 1, 0))
     return fail(VVT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", what);
   const int tiles_m = int(ceil_div(M, BM)), tiles_n = int(ceil_div(N, BN));
   const int tiles = symmetric ? tiles_n * (tiles_n + 1) / 2 : tiles_m * tiles_n;

@@ -159,11 +159,13 @@ def sqrt_backprop_conv2d(
     _, ci, kh, kw = W.shape
     h, w = in_hw
     out = torch.empty(V, N, ci, h, w, dtype=S.dtype, device=S.device)
+    lib = _lib.load()
+    ws = _ws(lib.vvt_conv2d_workspace_bytes(1, V, N, co, ho, wo, ci, kh, kw, _dt(S)), S)
     with torch.cuda.device(S.device):
-        st = _lib.load().vvt_sqrt_backprop_conv2d(
+        st = lib.vvt_sqrt_backprop_conv2d(
             _p(out), _p(S), _p(W), V * N, co, ho, wo, ci, h, w, kh, kw,
             stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1],
-            _dt(S), _stream(S),
+            _p(ws), ws.numel(), _dt(S), _stream(S),
         )
     _lib.check(st, "vvt_sqrt_backprop_conv2d")
     return out
@@ -231,11 +233,13 @@ def v_emit_conv2d(S: Tensor, X: Tensor, kernel, stride, padding, dilation) -> Te
     _, ci, h, w = X.shape
     kh, kw = kernel
     Vt = torch.empty(V, N, co, ci, kh, kw, dtype=S.dtype, device=S.device)
+    lib = _lib.load()
+    ws = _ws(lib.vvt_conv2d_workspace_bytes(0, V, N, co, ho, wo, ci, kh, kw, _dt(S)), S)
     with torch.cuda.device(S.device):
-        st = _lib.load().vvt_v_emit_conv2d(
+        st = lib.vvt_v_emit_conv2d(
             _p(Vt), _p(S), _p(X), V, N, co, ho, wo, ci, h, w, kh, kw,
             stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1],
-            _dt(S), _stream(S),
+            _p(ws), ws.numel(), _dt(S), _stream(S),
         )
     _lib.check(st, "vvt_v_emit_conv2d")
     return Vt
