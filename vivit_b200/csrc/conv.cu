@@ -146,9 +146,13 @@ __global__ void im2col_kernel(float* Un, const float* Xin, ConvGeom g, int N, in
 struct EmitStoreTc {
   float* Vt;
   int64_t N, c_out, J, batch0;
+  __device__ __forceinline__ int64_t row_offset(int n, int64_t m) const {
+    const int64_t v = m / c_out, o = m - v * c_out;
+    return ((v * N + (batch0 + n)) * c_out + o) * J;
+  }
+  __device__ __forceinline__ void store(int64_t off, int64_t, int64_t j, float val, int) const { Vt[off + j] = val; }
   __device__ __forceinline__ void operator()(int n, int64_t m, int64_t j, float val, int) const {
-    const int64_t v = m / c_out, o = m % c_out;
-    Vt[((v * N + (batch0 + n)) * c_out + o) * J + j] = val;
+    Vt[row_offset(n, m) + j] = val;
   }
 };
 
@@ -182,9 +186,13 @@ __global__ void weight_transpose_kernel(float* Wt, const float* W, int Co, int J
 struct DgradStoreTc {
   float* T2;
   int64_t X, J, batch0;
-  __device__ __forceinline__ void operator()(int, int64_t m, int64_t j, float val, int) const {
-    const int64_t r = m / X, x = m % X;
-    T2[(r * J + j) * X + x] = val;
+  __device__ __forceinline__ int64_t row_offset(int, int64_t m) const {
+    const int64_t r = m / X, x = m - r * X;
+    return r * J * X + x;
+  }
+  __device__ __forceinline__ void store(int64_t off, int64_t, int64_t j, float val, int) const { T2[off + j * X] = val; }
+  __device__ __forceinline__ void operator()(int b, int64_t m, int64_t j, float val, int) const {
+    T2[row_offset(b, m) + j * X] = val;
   }
 };
 

@@ -32,7 +32,7 @@
 
 #include <cstdlib>
 
-#include "common.cuh"
+#include "gemm_core.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -46,6 +46,10 @@ constexpr int LDP = OP + 4;  // padded row pitch of a chunk in shared memory (16
 constexpr int LDH = OP + 1;  // padded pitch of H
 constexpr int LDQ = OP + 4;  // padded pitch of Q (16-byte aligned rows for the apply phase)
 constexpr int kMaxSweeps = 60;
+#ifndef VVT_JACOBI_MMA
+#define VVT_JACOBI_MMA 1
+#endif
+constexpr bool kJacobiMma = VVT_JACOBI_MMA != 0;  // fp32 Gram / apply phases on mma.sync (3xTF32) instead of FFMA
 
 __host__ __device__ inline void rr_pair(int n, int round, int idx, int& a, int& b) {
   const int m = n - 1;
@@ -63,7 +67,9 @@ struct Eps;
 template <>
 struct Eps<float> {
   static constexpr float v = 1.1920929e-7f;
-  static constexpr float tol = 1e-5f;  // cosine below which two columns count as orthogonal
+  // cosine below which two columns count as orthogonal (a looser 1e-4 was measured to need MORE sweeps:
+  // the skipped rotations leave couplings that keep re-exciting their neighbours)
+  static constexpr float tol = 1e-5f;
 };
 template <>
 struct Eps<double> {
@@ -390,6 +396,216 @@ __device__ __forceinline__ void apply_rows(const RotSmem<T>& rs, const T* P, int
   }
 }
 
+// ---- fp32 fast paths for the two O(rows) phases of a round ----------------------------------------------
+// Gram: one 8x8 register tile of H per warp (upper triangle of the 4x4 tile grid: 10 tiles), the 32 lanes
+// split the rows; per row and lane 4 LDS.128 feed 64 FMAs (the 4x4 variant above is shared-memory bound).
+__device__ __forceinline__ void gram_tile8_accum(float (&acc)[64], const float* P, int ldp, int nrows, int lane,
+                                                 int ti, int tj) {
+  for (int r = lane; r < nrows; r += 32) {
+    float a[8], b[8];
+    const float* row = P + size_t(r) * ldp;
+    {
+      float lo[4], hi[4];
+      ld4(row + 8 * ti, lo);
+      ld4(row + 8 * ti + 4, hi);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = lo[i], a[4 + i] = hi[i];
+    }
+    if (ti != tj) {  // warp-uniform
+      float lo[4], hi[4];
+      ld4(row + 8 * tj, lo);
+      ld4(row + 8 * tj + 4, hi);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = lo[i], b[4 + i] = hi[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) b[i] = a[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[8 * i + j] = fmaf(a[i], b[j], acc[8 * i + j]);
+  }
+}
+
+// Sum the tile over the 32 lanes by recursive halving (62 shuffles for 64 values: lane L ends up with the
+// entries 2L and 2L+1 of the row-major tile) and store it, mirrored, into Q.
+__device__ __forceinline__ void gram_tile8_store(RotSmem<float>& rs, float (&v)[64], int lane, int ti, int tj) {
+#pragma unroll
+  for (int half = 32; half >= 2; half >>= 1) {
+    const int mask = half >> 1;
+    const bool up = (lane & mask) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = up ? v[i + half] : v[i];
+      const float send = up ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+  }
+  const int i = 8 * ti + (lane >> 2), j = 8 * tj + 2 * (lane & 3);
+  rs.Q[i][j] = v[0];
+  rs.Q[i][j + 1] = v[1];
+  if (ti != tj) {
+    rs.Q[j][i] = v[0];
+    rs.Q[j + 1][i] = v[1];
+  }
+}
+
+__device__ __forceinline__ void gram_phase_fast(RotSmem<float>& rs, const float* P, int ldp, int nrows, int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int t = warp; t < 10; t += OT / 32) {
+    // t -> (ti, tj), ti <= tj, row by row over the upper triangle of the 4x4 tile grid
+    int ti = 0, rem = t;
+    while (rem >= 4 - ti) rem -= 4 - ti, ++ti;
+    const int tj = ti + rem;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    gram_tile8_accum(acc, P, ldp, nrows, lane, ti, tj);
+    gram_tile8_store(rs, acc, lane, ti, tj);
+  }
+}
+
+// Apply: thread = (row, 16-column half); the row of P sits in registers, Q rows are broadcast reads.
+__device__ __forceinline__ void apply_phase_fast(const RotSmem<float>& rs, const float* P, int ldp, int nrows, float* Y,
+                                                 int Np, int ba, int bb, int grow0, int tid) {
+  const int h = tid & 1;
+  for (int r = tid >> 1; r < nrows; r += OT / 2) {
+    float acc[OB];
+    const float* row = P + size_t(r) * ldp;
+#pragma unroll
+    for (int j = 0; j < OB; ++j) acc[j] = 0.f;
+#pragma unroll 2
+    for (int k4 = 0; k4 < OP; k4 += 4) {
+      float p[4];
+      ld4(row + k4, p);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int j4 = 0; j4 < OB; j4 += 4) {
+          float q[4];
+          ld4(&rs.Q[k4 + kk][OB * h + j4], q);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[j4 + i] = fmaf(p[kk], q[i], acc[j4 + i]);
+        }
+      }
+    }
+    float* dst = y_ptr(Y, Np, h ? bb : ba, grow0 + r);
+#pragma unroll
+    for (int j4 = 0; j4 < OB; j4 += 4) {
+      const float t[4] = {acc[j4], acc[j4 + 1], acc[j4 + 2], acc[j4 + 3]};
+      st4(dst + j4, t);
+    }
+  }
+}
+
+// ---- fp32 tensor-core paths for the two O(rows) phases (mma.sync m16n8k8, 3xTF32 split: fp32-grade) -------
+constexpr int kGramStageFloats = (OT / 32) * OP * OP;  // per-warp partial Grams, summed in a fixed order
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma3(float (&acc)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                     const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+  mma_tf32(acc, al, bh);
+  mma_tf32(acc, ah, bl);
+  mma_tf32(acc, ah, bh);
+}
+
+// H = P^T P for this CTA's rows: the warps split the rows in steps of 8; the same eight shared-memory
+// values per lane serve as A and B fragments (H is symmetric: only tiles on or above the diagonal).
+__device__ __forceinline__ void gram_phase_mma(RotSmem<float>& rs, float* stage, const float* P, int ldp, int nrows,
+                                               int tid) {
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  float acc[6][4];  // (mt 0, nt 0..3), (mt 1, nt 2..3)
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
+  for (int k0 = 8 * warp; k0 < nrows; k0 += 8 * (OT / 32)) {
+    const int r0 = k0 + t, r1 = k0 + t + 4;
+    uint32_t hi[4][2], lo[4][2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float x0 = r0 < nrows ? P[size_t(r0) * ldp + 8 * c + g] : 0.f;
+      const float x1 = r1 < nrows ? P[size_t(r1) * ldp + 8 * c + g] : 0.f;
+      split_tf32(x0, hi[c][0], lo[c][0]);
+      split_tf32(x1, hi[c][1], lo[c][1]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const uint32_t ah[4] = {hi[2 * mt][0], hi[2 * mt + 1][0], hi[2 * mt][1], hi[2 * mt + 1][1]};
+      const uint32_t al[4] = {lo[2 * mt][0], lo[2 * mt + 1][0], lo[2 * mt][1], lo[2 * mt + 1][1]};
+#pragma unroll
+      for (int nt = 2 * mt; nt < 4; ++nt) mma3(acc[mt == 0 ? nt : 2 + nt], ah, al, hi[nt], lo[nt]);
+    }
+  }
+  float* mine = stage + warp * (OP * OP);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 2 * mt; nt < 4; ++nt) {
+      const float(&a)[4] = acc[mt == 0 ? nt : 2 + nt];
+      const int row = 16 * mt + g, col = 8 * nt + 2 * t;
+      mine[row * OP + col] = a[0];
+      mine[row * OP + col + 1] = a[1];
+      mine[(row + 8) * OP + col] = a[2];
+      mine[(row + 8) * OP + col + 1] = a[3];
+    }
+  __syncthreads();
+  for (int e = tid; e < OP * OP; e += OT) {
+    const int row = e / OP, col = e % OP;
+    if (row > col) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < OT / 32; ++w) s += stage[w * (OP * OP) + e];
+    rs.Q[row][col] = s;
+    rs.Q[col][row] = s;
+  }
+}
+
+// out = P Q for this CTA's rows, straight to global memory; Q fragments (hi/lo) stay in registers
+__device__ __forceinline__ void apply_phase_mma(const RotSmem<float>& rs, const float* P, int ldp, int nrows, float* Y,
+                                                int Np, int ba, int bb, int grow0, int tid) {
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  uint32_t qh[4][4][2], ql[4][4][2];  // [k-step][n-tile]
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      split_tf32(rs.Q[8 * ks + t][8 * nt + g], qh[ks][nt][0], ql[ks][nt][0]);
+      split_tf32(rs.Q[8 * ks + t + 4][8 * nt + g], qh[ks][nt][1], ql[ks][nt][1]);
+    }
+  for (int m0 = 16 * warp; m0 < nrows; m0 += 16 * (OT / 32)) {
+    const int ra = m0 + g, rb = m0 + g + 8;
+    const bool va = ra < nrows, vb = rb < nrows;
+    const float* pa = P + size_t(va ? ra : 0) * ldp;
+    const float* pb = P + size_t(vb ? rb : 0) * ldp;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], al[4];
+      split_tf32(va ? pa[8 * ks + t] : 0.f, ah[0], al[0]);
+      split_tf32(vb ? pb[8 * ks + t] : 0.f, ah[1], al[1]);
+      split_tf32(va ? pa[8 * ks + t + 4] : 0.f, ah[2], al[2]);
+      split_tf32(vb ? pb[8 * ks + t + 4] : 0.f, ah[3], al[3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma3(acc[nt], ah, al, qh[ks][nt], ql[ks][nt]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int blk = nt < 2 ? ba : bb, col = (8 * nt + 2 * t) & (OB - 1);
+      if (va) *reinterpret_cast<float2*>(y_ptr(Y, Np, blk, grow0 + ra) + col) = make_float2(acc[nt][0], acc[nt][1]);
+      if (vb) *reinterpret_cast<float2*>(y_ptr(Y, Np, blk, grow0 + rb) + col) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+  }
+}
+
 __device__ __forceinline__ void round_blocks(int nb, int round, int pair, int& ba, int& bb) {
   if (round < 0) {
     ba = 2 * pair;
@@ -401,7 +617,7 @@ __device__ __forceinline__ void round_blocks(int nb, int round, int pair, int& b
 
 // ---- resident variant: this CTA's rows of W and J are loaded once (cp.async) and stay in smem ----
 template <typename T>
-__global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 3 : 1))
+__global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
 onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RotSmem<T>& rs = *reinterpret_cast<RotSmem<T>*>(smem_raw);
@@ -434,7 +650,11 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
   __syncthreads();
   VVT_STAMP(1);
 
-  {  // phase 1: partial Gram of this CTA's rows of W
+  if constexpr (sizeof(T) == 4) {  // phase 1: partial Gram of this CTA's rows of W
+    float* stage = P + size_t(parts) * rows_per_cta * LDP;  // behind the resident rows
+    if (kJacobiMma) gram_phase_mma(rs, stage, P, LDP, nrows, tid);
+    else gram_phase_fast(rs, P, LDP, nrows, tid);
+  } else {
     const int ks = tid & 3, ti = tid >> 5, tj = (tid >> 2) & 7;
     T acc[4][4];
 #pragma unroll
@@ -458,7 +678,12 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
   cp_async_wait<0>();
   __syncthreads();
   VVT_STAMP(5);
-  {  // phase 3: P <- P Q for the W rows and the J rows, straight to global memory
+  if constexpr (sizeof(T) == 4) {  // phase 3: P <- P Q for the W rows (and the J rows), straight to global memory
+    for (int part = 0; part < parts; ++part) {
+      if (kJacobiMma) apply_phase_mma(rs, P + size_t(part) * nrows * LDP, LDP, nrows, Y, Np, ba, bb, part * Np + w0, tid);
+      else apply_phase_fast(rs, P + size_t(part) * nrows * LDP, LDP, nrows, Y, Np, ba, bb, part * Np + w0, tid);
+    }
+  } else {
     const int tr = tid >> 3, tc = tid & 7;
     for (int part = 0; part < parts; ++part)
       for (int r_base = 0; r_base < nrows; r_base += 128)
@@ -599,10 +824,10 @@ __global__ void __launch_bounds__(CROWS) chol_panel_kernel(T* A, int64_t R, int 
     if (tid == j) diag[j] = piv;
     if (tid > j && tid < b) D[tid][j] *= inv;
     __syncthreads();
-    const int m = b - j - 1;
-    for (int idx = tid; idx < m * m; idx += CROWS) {
-      const int i = j + 1 + idx / m, l = j + 1 + idx % m;
-      if (l <= i) D[i][l] -= D[i][j] * D[l][j];
+    // rank-1 update of the trailing lower triangle, 16 x 16 thread grid (no index divisions)
+    for (int i = j + 1 + (tid >> 4); i < b; i += CROWS / 16) {
+      const T dij = D[i][j];
+      for (int l = j + 1 + (tid & 15); l <= i; l += 16) D[i][l] -= dij * D[l][j];
     }
   }
   __syncthreads();
@@ -817,7 +1042,8 @@ static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
 
 template <typename T>
 static size_t resident_smem_bytes(int rows_per_cta, int parts) {
-  return align_up(sizeof(RotSmem<T>), 16) + size_t(parts) * rows_per_cta * LDP * sizeof(T);
+  const size_t stage = sizeof(T) == 4 && kJacobiMma ? size_t(kGramStageFloats) * 4 : 0;
+  return align_up(sizeof(RotSmem<T>), 16) + size_t(parts) * rows_per_cta * LDP * sizeof(T) + stage;
 }
 
 template <typename T>

@@ -105,17 +105,17 @@ __global__ void maxpool_bwd_kernel(T* out, const T* S, const int64_t* argmax, in
     const I r = pl / chI, c = pl - r * chI, n = r % NI;
     const T* s = S + pl * hw_out;
     const int64_t* am = argmax + (n * chI + c) * hw_out;
+    // candidate windows: oy*sh <= y+ph <= oy*sh + (kh-1)*dh  (two divisions per axis instead of
+    // a modulo per kernel offset)
+    const int ay = y + ph, ax = x + pw;
+    const int oy_hi = min(ho - 1, ay / sh), ox_hi = min(wo - 1, ax / sw);
+    const int by = ay - (kh - 1) * dh, bx = ax - (kw - 1) * dw;
+    const int oy_lo = by > 0 ? (by + sh - 1) / sh : 0, ox_lo = bx > 0 ? (bx + sw - 1) / sw : 0;
     T acc = 0;
-    for (int ky = 0; ky < kh; ++ky) {
-      const int ty = y + ph - ky * dh;
-      if (ty < 0 || ty % sh) continue;
-      const int oy = ty / sh;
-      if (oy >= ho) continue;
-      for (int kx = 0; kx < kw; ++kx) {
-        const int tx = x + pw - kx * dw;
-        if (tx < 0 || tx % sw) continue;
-        const int ox = tx / sw;
-        if (ox >= wo) continue;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      if (dh > 1 && (ay - oy * sh) % dh) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        if (dw > 1 && (ax - ox * sw) % dw) continue;
         if (int(am[oy * wo + ox]) == pos) acc += s[oy * wo + ox];
       }
     }

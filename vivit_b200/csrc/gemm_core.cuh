@@ -289,6 +289,11 @@ struct StdStore {
   __device__ __forceinline__ T weight(int64_t r, int64_t c) const {
     return P ? ldg(P + (r % pr) * ldp + (c % pc)) + padd : T(1);
   }
+  // two-step form used by the tcgen05 epilogue (nothing to precompute here)
+  __device__ __forceinline__ int64_t row_offset(int, int64_t r) const { return r; }
+  __device__ __forceinline__ void store(int64_t, int64_t r, int64_t c, T v, int split) const {
+    (*this)(0, r, c, v, split);
+  }
   __device__ __forceinline__ void operator()(int b, int64_t r, int64_t c, T v, int split) const {
     if (partial) {
       partial[int64_t(split) * slab + r * N + c] = v;

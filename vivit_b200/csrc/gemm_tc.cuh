@@ -275,15 +275,18 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // groups not drained yet: the last one, and the one before it if the last group was complete
     for (int g = (nkb % PROMOTE == 0) ? n_groups - 1 : vmax(0, n_groups - 2); g < n_groups; ++g) drain(g);
     // ===== epilogue: registers -> store =====
+    // ST provides  row_offset(batch, row) -> int64 (may divide: called once per row and thread) and
+    //              store(row_offset, row, col, value, split) (cheap), plus operator() for mirrored entries
     if constexpr (!COL_LANES) {
       const int64_t row = int64_t(tm) * BM + lane_grp * 32 + lane;
       const bool mirror = symmetric && !diag;
       if (row < M) {
+        const int64_t off = st.row_offset(batch, row);
 #pragma unroll
         for (int j = 0; j < BN; ++j) {
           const int64_t col = int64_t(tn) * BN + j;
           if (col < N) {
-            st(batch, row, col, total[j], split);
+            st.store(off, row, col, total[j], split);
             if (mirror) st(batch, col, row, total[j], split);
           }
         }
@@ -296,14 +299,19 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < BN; ++j) tile[trow * (BN + 1) + j] = total[j];
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int cw = warp - 2;  // 0..3
-      for (int r = cw; r < BM; r += 4) {
+      const int cw = warp - 2;  // 0..3: this warp stores rows cw, cw + 4, ...
+      // lane l prepares the offset of row cw + 4 l; the others fetch it by shuffle
+      const int64_t my_row = int64_t(tm) * BM + cw + 4 * lane;
+      const int64_t my_off = my_row < M ? st.row_offset(batch, my_row) : 0;
+      for (int i = 0; i < BM / 4; ++i) {
+        const int r = cw + 4 * i;
         const int64_t row = int64_t(tm) * BM + r;
-        if (row >= M) break;
+        const int64_t off = __shfl_sync(0xffffffffu, my_off, i);
+        if (row >= M) break;  // warp-uniform
 #pragma unroll
         for (int c = lane; c < BN; c += 32) {
           const int64_t col = int64_t(tn) * BN + c;
-          if (col < N) st(batch, row, col, tile[r * (BN + 1) + c], split);
+          if (col < N) st.store(off, row, col, tile[r * (BN + 1) + c], split);
         }
       }
     }

@@ -9,7 +9,8 @@ bool gram_tc_eligible(const float* A, const float* B, int64_t M, int64_t N, int6
                       int64_t batch) {
   static const bool disabled = getenv("VVT_NO_TCGEN05") != nullptr;
   if (disabled || batch != 1) return false;
-  if (K < 4 * tc::BK || M < 32 || N < 32) return false;  // tiny products: the SIMT-fed path has less overhead
+  // tiny products: the SIMT-fed path has less overhead (two k-blocks are enough when the output is large)
+  if (K < 2 * tc::BK || M < 32 || N < 32 || (K < 4 * tc::BK && M * N < 512 * 512)) return false;
   if (!tc::operands_ok(A, B, lda, ldb, 0, 0)) return false;  // TMA alignment rules
   if (M >= (int64_t(1) << 31) || N >= (int64_t(1) << 31) || K >= (int64_t(1) << 31)) return false;
   return true;
