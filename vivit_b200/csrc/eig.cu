@@ -1162,7 +1162,9 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
       for (int i = 1; i < 7; ++i) fprintf(stderr, " %lld", h.t[i] - h.t[i - 1]);
       fprintf(stderr, "\n");
     }
-    if (rot == 0) {
+    // a sweep that rotated (almost) nothing ends the iteration: the last few block pairs only carry
+    // cosines barely above the threshold, which the refinement step below removes anyway
+    if (rot <= (unsigned long long)(pairs * nb) / 256) {
       converged = 1;
       break;
     }

@@ -176,54 +176,95 @@ __global__ void linear_emit_kernel(T* Vt, const T* S, const T* Z, int64_t V, int
 }
 
 // ---- dense back-transform: E[K, D] = U[K, R] V[R, D] -------------------------
-// Streams V exactly once.  Each thread owns one column d (coalesced across the warp) and
-// KT direction accumulators; U is staged through shared memory in row chunks.
-template <typename T, int KT>
-__global__ void __launch_bounds__(256)
+// Streams V exactly once per KT directions.  Each thread owns VW consecutive columns (one 16-byte
+// load per row, coalesced across the warp) and KT x VW accumulators; U is staged through shared
+// memory in row chunks; loads of 4 rows are in flight per thread.
+template <typename T, int KT, int VW>
+__global__ void __launch_bounds__(128)
 backtransform_dense_kernel(T* E, double* norm2, const T* U, const T* V, int64_t K, int64_t R, int64_t D,
                            int64_t k0) {
   constexpr int RC = 64;  // rows of V per U chunk
-  __shared__ T Us[KT][RC];
-  __shared__ double red[KT][8];
-  const int64_t d = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  __shared__ T Us[RC][KT];
+  __shared__ double red[KT][4];
+  const int64_t d0 = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) * VW;
   const int kn = int(vmin<int64_t>(KT, K - k0));
-  T acc[KT];
+  const bool vec = (D % VW == 0) && d0 + VW <= D && (reinterpret_cast<uintptr_t>(V) & 15) == 0;  // aligned full vector
+  T acc[KT][VW];
 #pragma unroll
-  for (int k = 0; k < KT; ++k) acc[k] = 0;
+  for (int k = 0; k < KT; ++k)
+#pragma unroll
+    for (int v = 0; v < VW; ++v) acc[k][v] = 0;
   for (int64_t r0 = 0; r0 < R; r0 += RC) {
     const int rn = int(vmin<int64_t>(RC, R - r0));
     __syncthreads();
     for (int i = threadIdx.x; i < KT * RC; i += blockDim.x) {
       const int k = i / RC, r = i % RC;
-      Us[k][r] = (k < kn && r < rn) ? U[(k0 + k) * R + r0 + r] : T(0);
+      Us[r][k] = (k < kn && r < rn) ? U[(k0 + k) * R + r0 + r] : T(0);
     }
     __syncthreads();
-    if (d < D) {
-      const T* vp = V + r0 * D + d;
-#pragma unroll 8
-      for (int r = 0; r < rn; ++r) {
-        const T v = ldg(vp + int64_t(r) * D);
+    if (d0 < D) {
+      const T* vp = V + r0 * D + d0;
+      constexpr int RB = 8;  // rows whose loads are in flight together (RB x 16 bytes per thread)
+      for (int rb = 0; rb < rn; rb += RB) {
+        T x[RB][VW];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) acc[k] += Us[k][r] * v;
+        for (int i = 0; i < RB; ++i) {
+          const int r = rb + i;
+          if (r < rn) {
+            if (vec) {
+              if constexpr (sizeof(T) * VW == 16) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(vp + int64_t(r) * D));
+                const T* tp = reinterpret_cast<const T*>(&t);
+#pragma unroll
+                for (int v = 0; v < VW; ++v) x[i][v] = tp[v];
+              } else {
+#pragma unroll
+                for (int v = 0; v < VW; ++v) x[i][v] = ldg(vp + int64_t(r) * D + v);
+              }
+            } else {
+#pragma unroll
+              for (int v = 0; v < VW; ++v) x[i][v] = d0 + v < D ? ldg(vp + int64_t(r) * D + v) : T(0);
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < VW; ++v) x[i][v] = T(0);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          const int r = vmin(rb + i, RC - 1);
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            const T u = Us[r][k];
+#pragma unroll
+            for (int v = 0; v < VW; ++v) acc[k][v] += u * x[i][v];
+          }
+        }
       }
     }
   }
 #pragma unroll
   for (int k = 0; k < KT; ++k) {
-    if (k < kn && d < D) E[(k0 + k) * D + d] = acc[k];
+    if (k < kn) {
+#pragma unroll
+      for (int v = 0; v < VW; ++v)
+        if (d0 + v < D) E[(k0 + k) * D + d0 + v] = acc[k][v];
+    }
   }
   if (norm2) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
-      double s = (d < D) ? double(acc[k]) * double(acc[k]) : 0.0;
+      double s = 0.0;
+#pragma unroll
+      for (int v = 0; v < VW; ++v) s += (d0 + v < D) ? double(acc[k][v]) * double(acc[k][v]) : 0.0;
       s = warp_sum(s);
       if (lane == 0) red[k][warp] = s;
     }
     __syncthreads();
     if (threadIdx.x < kn) {
       double s = 0;
-      for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+      for (int w = 0; w < 4; ++w) s += red[threadIdx.x][w];
       atomicAdd(norm2 + k0 + threadIdx.x, s);
     }
   }
@@ -409,12 +450,29 @@ int vvt_backtransform_dense(void* E, void* norm2, const void* U, const void* V, 
   VVT_REQUIRE(K >= 0 && R >= 0 && D >= 0, "negative size");
   if (K == 0 || D == 0) return VVT_OK;
   VVT_REQUIRE(E && U && V, "null pointer");
-  constexpr int KT = 8;
   VVT_DISPATCH(dtype, {
-    const unsigned blocks = unsigned(ceil_div(D, 256));
-    for (int64_t k0 = 0; k0 < K; k0 += KT) {
-      backtransform_dense_kernel<T, KT><<<blocks, 256, 0, as_stream(stream)>>>(
-          (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);
+    constexpr int VW = 16 / int(sizeof(T));  // one 16-byte load per row and thread
+    const unsigned blocks = unsigned(ceil_div(D, 128 * VW));
+    int64_t k0 = 0;
+    while (k0 < K) {  // 16 directions per pass over V while that many remain, then 8 / 4 / 2 / 1
+      const int64_t left = K - k0;
+      if (left > 8) {
+        backtransform_dense_kernel<T, 16, VW><<<blocks, 128, 0, as_stream(stream)>>>(
+            (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);
+        k0 += 16;
+      } else if (left > 4) {
+        backtransform_dense_kernel<T, 8, VW><<<blocks, 128, 0, as_stream(stream)>>>(
+            (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);
+        k0 += 8;
+      } else if (left > 1) {
+        backtransform_dense_kernel<T, 4, VW><<<blocks, 128, 0, as_stream(stream)>>>(
+            (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);
+        k0 += 4;
+      } else {
+        backtransform_dense_kernel<T, 1, VW><<<blocks, 128, 0, as_stream(stream)>>>(
+            (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);
+        k0 += 1;
+      }
       VVT_TRY(launched(__func__));
     }
     return VVT_OK;
@@ -427,7 +485,8 @@ int vvt_v_apply_dense(void* step, const void* v, const void* V, int64_t R, int64
   if (D == 0) return VVT_OK;
   VVT_REQUIRE(step && v && V, "null pointer");
   VVT_DISPATCH(dtype, {
-    backtransform_dense_kernel<T, 1><<<unsigned(ceil_div(D, 256)), 256, 0, as_stream(stream)>>>(
+    constexpr int VW = 16 / int(sizeof(T));
+    backtransform_dense_kernel<T, 1, VW><<<unsigned(ceil_div(D, 128 * VW)), 128, 0, as_stream(stream)>>>(
         (T*)step, nullptr, (const T*)v, (const T*)V, 1, R, D, 0);
     return launched(__func__);
   });
