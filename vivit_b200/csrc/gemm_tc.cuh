@@ -274,44 +274,64 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     // groups not drained yet: the last one, and the one before it if the last group was complete
     for (int g = (nkb % PROMOTE == 0) ? n_groups - 1 : vmax(0, n_groups - 2); g < n_groups; ++g) drain(g);
-    // ===== epilogue: registers -> store =====
-    // ST provides  row_offset(batch, row) -> int64 (may divide: called once per row and thread) and
-    //              store(row_offset, row, col, value, split) (cheap), plus operator() for mirrored entries
-    if constexpr (!COL_LANES) {
-      const int64_t row = int64_t(tm) * BM + lane_grp * 32 + lane;
-      const bool mirror = symmetric && !diag;
-      if (row < M) {
-        const int64_t off = st.row_offset(batch, row);
-#pragma unroll
-        for (int j = 0; j < BN; ++j) {
-          const int64_t col = int64_t(tn) * BN + j;
-          if (col < N) {
-            st.store(off, row, col, total[j], split);
-            if (mirror) st(batch, col, row, total[j], split);
-          }
-        }
-      }
-    } else {
-      // every MMA of this CTA has completed (the last group was drained) and so has every TMA load:
-      // the pipeline stages are free and hold the staged tile [BM][BN + 1]
+    // ===== epilogue: registers -> shared memory -> global =====
+    // ST provides  row_offset(batch, row) -> int64 (may divide: called a few times per thread),
+    //              store(row_offset, row, col, value, split) (cheap) and operator() for mirrored entries.
+    // Every MMA of this CTA has completed (the last group was drained) and so has every TMA load: the
+    // pipeline stages are free and hold the staged tile [BM][BN + 1].  The store loops are NOT unrolled
+    // over the tile (a fully unrolled 128-store epilogue thrashes the instruction cache: 50% no_inst stalls).
+    {
       float* tile = reinterpret_cast<float*>(base_ptr);
       const int trow = lane_grp * 32 + lane;
 #pragma unroll
       for (int j = 0; j < BN; ++j) tile[trow * (BN + 1) + j] = total[j];
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int cw = warp - 2;  // 0..3: this warp stores rows cw, cw + 4, ...
-      // lane l prepares the offset of row cw + 4 l; the others fetch it by shuffle
-      const int64_t my_row = int64_t(tm) * BM + cw + 4 * lane;
-      const int64_t my_off = my_row < M ? st.row_offset(batch, my_row) : 0;
-      for (int i = 0; i < BM / 4; ++i) {
-        const int r = cw + 4 * i;
-        const int64_t row = int64_t(tm) * BM + r;
-        const int64_t off = __shfl_sync(0xffffffffu, my_off, i);
-        if (row >= M) break;  // warp-uniform
+      const int cw = warp - 2;  // 0..3
+      const int64_t row0 = int64_t(tm) * BM, col0 = int64_t(tn) * BN;
+      if constexpr (COL_LANES) {
+        // lanes = consecutive columns (row-major outputs): this warp stores rows cw, cw + 4, ...;
+        // lane l prepares the offset of row cw + 4 l, the others fetch it by shuffle
+        const int64_t my_row = row0 + cw + 4 * lane;
+        const int64_t my_off = my_row < M ? st.row_offset(batch, my_row) : 0;
+        for (int i = 0; i < BM / 4; ++i) {
+          const int r = cw + 4 * i;
+          const int64_t row = row0 + r;
+          const int64_t off = __shfl_sync(0xffffffffu, my_off, i);
+          if (row >= M) break;  // warp-uniform
 #pragma unroll
-        for (int c = lane; c < BN; c += 32) {
-          const int64_t col = int64_t(tn) * BN + c;
-          if (col < N) st.store(off, row, col, tile[r * (BN + 1) + c], split);
+          for (int c = lane; c < BN; c += 32) {
+            const int64_t col = col0 + c;
+            if (col < N) st.store(off, row, col, tile[r * (BN + 1) + c], split);
+          }
+        }
+      } else {
+        // lanes = consecutive rows (outputs contiguous along the row index): this warp stores columns
+        // cw, cw + 4, ...
+        int64_t offs[BM / 32];
+#pragma unroll
+        for (int c = 0; c < BM / 32; ++c) {
+          const int64_t row = row0 + lane + 32 * c;
+          offs[c] = row < M ? st.row_offset(batch, row) : 0;
+        }
+        for (int j = cw; j < BN; j += 4) {
+          const int64_t col = col0 + j;
+          if (col >= N) break;  // warp-uniform
+#pragma unroll
+          for (int c = 0; c < BM / 32; ++c) {
+            const int r = lane + 32 * c;
+            if (row0 + r < M) st.store(offs[c], row0 + r, col, tile[r * (BN + 1) + j], split);
+          }
+        }
+      }
+      if (symmetric && !diag) {  // mirrored entries (col, row): lanes = consecutive rows -> coalesced
+        for (int j = cw; j < BN; j += 4) {
+          const int64_t col = col0 + j;
+          if (col >= N) break;
+#pragma unroll
+          for (int c = 0; c < BM / 32; ++c) {
+            const int r = lane + 32 * c;
+            if (row0 + r < M) st(batch, col, row0 + r, tile[r * (BN + 1) + j], split);
+          }
         }
       }
     }

@@ -42,7 +42,7 @@ int launch_gram_tc(const float* A, const float* B, StdStore<float> st, int64_t M
                    int64_t ldb, bool symmetric, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
                    const char* what) {
   using namespace tc;
-  auto kern = gram_tc_kernel<StdStore<float>, false>;
+  auto kern = gram_tc_kernel<StdStore<float>, true>;
   static bool attr_done = false;
   if (!attr_done) {
     VVT_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)), what));
