@@ -632,6 +632,10 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
   const T tol2 = Eps<T>::tol * Eps<T>::tol;
   const T abs2 = Eps<T>::v * Eps<T>::v;  // W is scaled to unit Frobenius norm
 
+  // programmatic dependent launch: let the next round's CTAs be scheduled while this round runs (they
+  // block in griddepcontrol.wait until this grid has completed and its stores are visible)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   VVT_STAMP(0);
   // all loads are issued up front: group 0 = W rows (needed now), group 1 = J rows (needed last)
   {
@@ -728,6 +732,8 @@ onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, 
   const T tol2 = Eps<T>::tol * Eps<T>::tol;
   const T abs2 = Eps<T>::v * Eps<T>::v;
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   {  // phase 1: partial Gram, chunks of W rows double-buffered
     const int ks = tid & 3, ti = tid >> 5, tj = (tid >> 2) & 7;
     T acc[4][4];
@@ -1062,13 +1068,16 @@ static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_ct
   cfg.blockDim = dim3(OT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  static const bool pdl = getenv("VVT_SYEVJ_NOPDL") == nullptr;
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = unsigned(CL);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, parts, sc), "vvt_syevj(round)"));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return VVT_OK;

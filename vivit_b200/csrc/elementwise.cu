@@ -90,37 +90,57 @@ __global__ void act_kernel(T* out, const T* S, const T* ref, int64_t V, int64_t 
 }
 
 // gather form of the max-pool scatter: every input position sums the outputs that chose it.
-// I = index type (32-bit whenever the output has < 2^31 elements: 64-bit div/mod is what this
-// kernel would otherwise spend its time on)
-template <typename T, typename I>
-__global__ void maxpool_bwd_kernel(T* out, const T* S, const int64_t* argmax, int64_t rows, int64_t N,
-                                   int64_t ch, int ho, int wo, int hi, int wi, int kh, int kw, int sh,
-                                   int sw, int ph, int pw, int dh, int dw) {
-  const I total = I(rows * ch * hi * wi);
-  const I hw_in = I(hi) * I(wi), hw_out = I(ho) * I(wo), chI = I(ch), NI = I(N);
-  for (I i = I(blockIdx.x) * I(blockDim.x) + I(threadIdx.x); i < total; i += I(gridDim.x) * I(blockDim.x)) {
-    const I pl = i / hw_in;  // plane = r * ch + c
-    const int pos = int(i - pl * hw_in);
-    const int y = pos / wi, x = pos - y * wi;
-    const I r = pl / chI, c = pl - r * chI, n = r % NI;
+// One block per (row, channel) plane (grid-stride): the plane decomposition is done once per block and
+// the strides are compile-time constants for the common cases (STRIDE = 1, 2; 0 = run-time), so the
+// inner loop has no 64-bit and no run-time divisions.
+template <typename T, int STRIDE>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(T* out, const T* S, const int64_t* argmax, int64_t planes, int64_t N, int64_t ch, int ho,
+                   int wo, int hi, int wi, int kh, int kw, int sh_rt, int sw_rt, int ph, int pw, int dh, int dw) {
+  const int sh = STRIDE ? STRIDE : sh_rt, sw = STRIDE ? STRIDE : sw_rt;
+  const int hw_in = hi * wi, hw_out = ho * wo;
+  // blockDim = (positions, planes per block): small maps share a block
+  for (int64_t pl = int64_t(blockIdx.x) * blockDim.y + threadIdx.y; pl < planes; pl += int64_t(gridDim.x) * blockDim.y) {
+    const int64_t r = pl / ch, c = pl - r * ch, n = r % N;
     const T* s = S + pl * hw_out;
-    const int64_t* am = argmax + (n * chI + c) * hw_out;
-    // candidate windows: oy*sh <= y+ph <= oy*sh + (kh-1)*dh  (two divisions per axis instead of
-    // a modulo per kernel offset)
-    const int ay = y + ph, ax = x + pw;
-    const int oy_hi = min(ho - 1, ay / sh), ox_hi = min(wo - 1, ax / sw);
-    const int by = ay - (kh - 1) * dh, bx = ax - (kw - 1) * dw;
-    const int oy_lo = by > 0 ? (by + sh - 1) / sh : 0, ox_lo = bx > 0 ? (bx + sw - 1) / sw : 0;
-    T acc = 0;
-    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-      if (dh > 1 && (ay - oy * sh) % dh) continue;
-      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-        if (dw > 1 && (ax - ox * sw) % dw) continue;
-        if (int(am[oy * wo + ox]) == pos) acc += s[oy * wo + ox];
+    const int64_t* am = argmax + (n * ch + c) * hw_out;
+    T* o = out + pl * hw_in;
+    for (int pos = threadIdx.x; pos < hw_in; pos += blockDim.x) {
+      const int y = pos / wi, x = pos - y * wi;
+      // candidate windows: oy*sh <= y+ph <= oy*sh + (kh-1)*dh
+      const int ay = y + ph, ax = x + pw;
+      const int oy_hi = min(ho - 1, ay / sh), ox_hi = min(wo - 1, ax / sw);
+      const int by = ay - (kh - 1) * dh, bx = ax - (kw - 1) * dw;
+      const int oy_lo = by > 0 ? (by + sh - 1) / sh : 0, ox_lo = bx > 0 ? (bx + sw - 1) / sw : 0;
+      T acc = 0;
+      for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        if (dh > 1 && (ay - oy * sh) % dh) continue;
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+          if (dw > 1 && (ax - ox * sw) % dw) continue;
+          if (int(am[oy * wo + ox]) == pos) acc += s[oy * wo + ox];
+        }
       }
+      o[pos] = acc;
     }
-    out[i] = acc;
   }
+}
+
+template <typename T>
+static void launch_maxpool_bwd(T* out, const T* S, const int64_t* argmax, int64_t planes, int64_t N, int64_t ch, int ho,
+                               int wo, int hi, int wi, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                               cudaStream_t s) {
+  const int tx = int(vmin<int64_t>(256, align_up(int64_t(hi) * wi, 32))), ty = 256 / tx;
+  const dim3 threads(tx, ty);
+  const unsigned blocks = unsigned(vmin<int64_t>(ceil_div(planes, ty), int64_t(32) * num_sms()));
+  if (sh == sw && sh == 2)
+    maxpool_bwd_kernel<T, 2><<<blocks, threads, 0, s>>>(out, S, argmax, planes, N, ch, ho, wo, hi, wi, kh, kw, sh, sw, ph,
+                                                       pw, dh, dw);
+  else if (sh == sw && sh == 1)
+    maxpool_bwd_kernel<T, 1><<<blocks, threads, 0, s>>>(out, S, argmax, planes, N, ch, ho, wo, hi, wi, kh, kw, sh, sw, ph,
+                                                       pw, dh, dw);
+  else
+    maxpool_bwd_kernel<T, 0><<<blocks, threads, 0, s>>>(out, S, argmax, planes, N, ch, ho, wo, hi, wi, kh, kw, sh, sw, ph,
+                                                       pw, dh, dw);
 }
 
 template <typename T>
@@ -390,15 +410,9 @@ int vvt_sqrt_backprop_maxpool2d(void* out, const void* S, const int64_t* argmax,
   if (total == 0) return VVT_OK;
   VVT_REQUIRE(out && S && argmax, "null pointer");
   VVT_DISPATCH(dtype, {
-    if (total < (int64_t(1) << 31) - (int64_t(1) << 24)) {
-      maxpool_bwd_kernel<T, unsigned><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
-          (T*)out, (const T*)S, argmax, V * N, N, ch, int(h_out), int(w_out), int(h_in), int(w_in),
-          int(kh), int(kw), int(stride_h), int(stride_w), int(pad_h), int(pad_w), int(dil_h), int(dil_w));
-    } else {
-      maxpool_bwd_kernel<T, int64_t><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
-          (T*)out, (const T*)S, argmax, V * N, N, ch, int(h_out), int(w_out), int(h_in), int(w_in),
-          int(kh), int(kw), int(stride_h), int(stride_w), int(pad_h), int(pad_w), int(dil_h), int(dil_w));
-    }
+    launch_maxpool_bwd<T>((T*)out, (const T*)S, argmax, V * N * ch, N, ch, int(h_out), int(w_out), int(h_in),
+                          int(w_in), int(kh), int(kw), int(stride_h), int(stride_w), int(pad_h), int(pad_w),
+                          int(dil_h), int(dil_w), as_stream(stream));
     return launched(__func__);
   });
 }
