@@ -90,6 +90,9 @@ CONV_CASES = [
     (2, 2, 2, 9, 9, 3, 3, 2, 0, 1),
     (2, 2, 2, 9, 9, 3, 3, 1, 2, 2),
     (10, 4, 16, 12, 12, 24, 3, 1, 1, 1),
+    (3, 5, 7, 11, 13, 130, 3, 2, 1, 1),   # odd sizes, stride 2, c_out > one tile, spatial pitch not a multiple of 4
+    (10, 8, 64, 14, 14, 96, 3, 1, 0, 1),  # cifar10_3c3d conv2 geometry at a small batch
+    (1, 6, 3, 8, 8, 5, 1, 1, 0, 1),       # 1x1 kernel, a single "class" (BatchGrad emit)
 ]
 
 
@@ -108,6 +111,35 @@ def test_conv2d_backprop_and_emit(k, dtype, case):
     close(k.v_emit_bias(S), ref.v_emit_bias(S.double()), dtype, "bias")
 
 
+def test_conv2d_without_workspace_uses_the_generic_kernel(k):
+    """The C ABI accepts a NULL workspace for the Conv2d entry points (generic implicit-GEMM kernel);
+    results agree with the tensor-core path that kernels.py selects."""
+    import ctypes
+
+    from vivit_b200 import _lib
+
+    lib = _lib.load()
+    V, N, ci, h, w, co, ks = 4, 3, 6, 9, 9, 10, 3
+    S = rnd(V, N, co, 7, 7, dtype=torch.float32)
+    W = rnd(co, ci, ks, ks, dtype=torch.float32, seed=1)
+    X = rnd(N, ci, h, w, dtype=torch.float32, seed=2)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    out = torch.empty(V, N, ci, h, w, device=dev())
+    st = lib.vvt_sqrt_backprop_conv2d(P(out), P(S), P(W), V * N, co, 7, 7, ci, h, w, ks, ks, 1, 1, 0, 0, 1, 1,
+                                      None, 0, 0, stream)
+    assert st == 0
+    Vt = torch.empty(V, N, co, ci, ks, ks, device=dev())
+    st = lib.vvt_v_emit_conv2d(P(Vt), P(S), P(X), V, N, co, 7, 7, ci, h, w, ks, ks, 1, 1, 0, 0, 1, 1, None, 0, 0, stream)
+    assert st == 0
+    args = ((1, 1), (0, 0), (1, 1))
+    close(out, ref.sqrt_backprop_conv2d(*f64(S, W), (h, w), *args), torch.float32, "dgrad (generic)")
+    close(Vt, ref.v_emit_conv2d(*f64(S, X), (ks, ks), *args), torch.float32, "emit (generic)")
+    close(out, k.sqrt_backprop_conv2d(S, W, (h, w), *args).double(), torch.float32, "dgrad paths agree")
+    assert lib.vvt_conv2d_workspace_bytes(0, V, N, co, 7, 7, ci, ks, ks, 0) > 0
+    assert lib.vvt_conv2d_workspace_bytes(1, V, N, co, 7, 7, ci, ks, ks, 1) == 0  # fp64: generic kernel
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_elementwise_and_pools(k, dtype):
     S = rnd(3, 4, 5, 7, 7, dtype=dtype)
@@ -115,11 +147,17 @@ def test_elementwise_and_pools(k, dtype):
     for act in range(5):
         close(k.sqrt_backprop_elementwise(S, r, act, 2.0), ref.sqrt_backprop_elementwise(S.double(), r.double(), act, 2.0), dtype, f"act{act}")
     x = rnd(4, 5, 9, 9, dtype=dtype, seed=4)
-    for kern, st, pd, ceil in [(3, 2, 0, False), (3, 2, 0, True), (2, 2, 0, False), (3, 1, 1, False), (3, 2, 1, True)]:
-        y, idx = torch.nn.functional.max_pool2d(x, kern, st, pd, 1, ceil, return_indices=True)
+    for kern, st, pd, ceil, dil in [(3, 2, 0, False, 1), (3, 2, 0, True, 1), (2, 2, 0, False, 1), (3, 1, 1, False, 1),
+                                    (3, 2, 1, True, 1), (3, 3, 0, False, 1), (2, 1, 0, False, 2), (4, 3, 1, False, 1)]:
+        y, idx = torch.nn.functional.max_pool2d(x, kern, st, pd, dil, ceil, return_indices=True)
         Sp = rnd(3, *y.shape, dtype=dtype, seed=5)
-        a = ((9, 9), (kern, kern), (st, st), (pd, pd), (1, 1))
+        a = ((9, 9), (kern, kern), (st, st), (pd, pd), (dil, dil))
         close(k.sqrt_backprop_maxpool2d(Sp, idx, *a), ref.sqrt_backprop_maxpool2d(Sp.double(), idx, *a), dtype, "maxpool")
+    xb = rnd(2, 3, 30, 28, dtype=dtype, seed=8)  # a map larger than one block of threads
+    y, idx = torch.nn.functional.max_pool2d(xb, 3, 2, 0, 1, True, return_indices=True)
+    Sp = rnd(2, *y.shape, dtype=dtype, seed=9)
+    a = ((30, 28), (3, 3), (2, 2), (0, 0), (1, 1))
+    close(k.sqrt_backprop_maxpool2d(Sp, idx, *a), ref.sqrt_backprop_maxpool2d(Sp.double(), idx, *a), dtype, "maxpool big")
     for kern, st, pd in [(3, 3, 0), (2, 2, 0), (3, 1, 1), (9, 9, 0)]:
         y = torch.nn.functional.avg_pool2d(x, kern, st, pd)
         Sp = rnd(2, *y.shape, dtype=dtype, seed=6)

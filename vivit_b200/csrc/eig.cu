@@ -615,10 +615,25 @@ __device__ __forceinline__ void round_blocks(int nb, int round, int pair, int& b
   }
 }
 
+// Bookkeeping that lets converged block pairs skip a round entirely: stamp[b] = last round in which
+// block b was rotated, clean[a][b] = last round in which the pair was found to need no rotation (upper
+// triangle: cross rounds, lower triangle: intra rounds).  A pair that was clean after both of its blocks
+// were last modified is still clean.  Values are written by one thread per cluster and read by later
+// launches only.
+__device__ __forceinline__ int* clean_slot(int* marks, int nb, int ba, int bb, bool intra) {
+  const int lo = min(ba, bb), hi = max(ba, bb);
+  return marks + nb + (intra ? hi * nb + lo : lo * nb + hi);
+}
+__device__ __forceinline__ bool pair_is_clean(int* marks, int nb, int ba, int bb, bool intra) {
+  const int c = *clean_slot(marks, nb, ba, bb, intra);
+  return c > max(marks[ba], marks[bb]);
+}
+
 // ---- resident variant: this CTA's rows of W and J are loaded once (cp.async) and stay in smem ----
 template <typename T>
 __global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
-onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc) {
+onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc,
+                               int* marks, int now) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RotSmem<T>& rs = *reinterpret_cast<RotSmem<T>*>(smem_raw);
   T* P = reinterpret_cast<T*>(smem_raw + ((sizeof(RotSmem<T>) + 15) / 16) * 16);  // [parts * rows][LDP]: W rows(, J rows)
@@ -636,6 +651,7 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
   // block in griddepcontrol.wait until this grid has completed and its stores are visible)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (pair_is_clean(marks, nb, ba, bb, intra)) return;  // same decision in every CTA of the cluster
   VVT_STAMP(0);
   // all loads are issued up front: group 0 = W rows (needed now), group 1 = J rows (needed last)
   {
@@ -673,10 +689,15 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
   __syncthreads();
   VVT_STAMP(3);
   if (!any_rotation_needed<T>(rs, intra, tol2, abs2, tid)) {  // uniform over the cluster (same H)
+    if (crank == 0 && tid == 0) *clean_slot(marks, nb, ba, bb, intra) = now;
     cp_async_wait<0>();
     return;
   }
-  if (crank == 0 && tid == 0) atomicAdd(&sc->rotations, 1ull);
+  if (crank == 0 && tid == 0) {
+    atomicAdd(&sc->rotations, 1ull);
+    marks[ba] = now;
+    marks[bb] = now;
+  }
   rotate_and_broadcast<T>(rs, cluster, intra, tol2, abs2, tid);  // phase 2
   VVT_STAMP(4);
   cp_async_wait<0>();
@@ -717,7 +738,8 @@ __device__ __forceinline__ void load_chunk(T (*dst)[LDP], const T* Y, int Np, in
 
 template <typename T>
 __global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
-onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc) {
+onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc,
+                             int* marks, int now) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StreamSmem<T>& sm = *reinterpret_cast<StreamSmem<T>*>(smem_raw);
   RotSmem<T>& rs = sm.rs;
@@ -734,6 +756,7 @@ onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, 
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (pair_is_clean(marks, nb, ba, bb, intra)) return;
   {  // phase 1: partial Gram, chunks of W rows double-buffered
     const int ks = tid & 3, ti = tid >> 5, tj = (tid >> 2) & 7;
     T acc[4][4];
@@ -757,8 +780,15 @@ onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, 
   }
   cluster_reduce_gram<T>(rs, cluster, tid);
   __syncthreads();
-  if (!any_rotation_needed<T>(rs, intra, tol2, abs2, tid)) return;
-  if (crank == 0 && tid == 0) atomicAdd(&sc->rotations, 1ull);
+  if (!any_rotation_needed<T>(rs, intra, tol2, abs2, tid)) {
+    if (crank == 0 && tid == 0) *clean_slot(marks, nb, ba, bb, intra) = now;
+    return;
+  }
+  if (crank == 0 && tid == 0) {
+    atomicAdd(&sc->rotations, 1ull);
+    marks[ba] = now;
+    marks[bb] = now;
+  }
   // first chunk of phase 3 travels while the rotation rounds run
   if (n_chunks > 0) load_chunk<T>(sm.chunk[0], Y, Np, ba, bb, w0, min(CH, nrows), tid);
   rotate_and_broadcast<T>(rs, cluster, intra, tol2, abs2, tid);  // phase 2
@@ -1015,7 +1045,7 @@ __global__ void jacobi_permute_kernel(T* evals, T* evecs, const T* ev, const T* 
 }
 
 struct JacobiLayout {
-  int64_t Np, nb, off_Y, off_Gs, off_Jm, off_Jt, off_Tt, off_S, off_M, off_Et, off_ev, off_cn, off_rank, off_sc, off_gemm, gemm_bytes, total;
+  int64_t Np, nb, off_Y, off_Gs, off_Jm, off_Jt, off_Tt, off_S, off_M, off_Et, off_ev, off_cn, off_rank, off_sc, off_marks, off_gemm, gemm_bytes, total;
 };
 
 static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
@@ -1040,6 +1070,7 @@ static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
   L.off_cn = take(R * es);
   L.off_rank = take(R * 4);
   L.off_sc = take(sizeof(JacobiScalars));
+  L.off_marks = take((L.nb + L.nb * L.nb) * 4);
   L.gemm_bytes = vvt_gram_workspace_bytes(R, R, R, dtype);
   L.off_gemm = take(L.gemm_bytes);
   L.total = o;
@@ -1054,7 +1085,7 @@ static size_t resident_smem_bytes(int rows_per_cta, int parts) {
 
 template <typename T>
 static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_cta, int parts, bool resident,
-                        JacobiScalars* sc, cudaStream_t s) {
+                        JacobiScalars* sc, int* marks, int now, cudaStream_t s) {
   auto kern = resident ? onesided_round_resident_kernel<T> : onesided_round_stream_kernel<T>;
   const size_t smem = resident ? resident_smem_bytes<T>(rows_per_cta, parts) : sizeof(StreamSmem<T>);
   static size_t attr_done[2] = {0, 0};  // per instantiation: largest size configured so far
@@ -1078,7 +1109,7 @@ static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_ct
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
-  VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, parts, sc), "vvt_syevj(round)"));
+  VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, parts, sc, marks, now), "vvt_syevj(round)"));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return VVT_OK;
 }
@@ -1110,13 +1141,16 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   // (few CTAs per cluster: every CTA repeats the rotation rounds, and the cluster barriers of the Gram
   // reduction are the main cost of a round; 640 rows per CTA measured best at R = 1280)
   int CL = 1;
-  while (CL < 8 && Np / CL > 640) CL *= 2;
+  const int max_rows = sizeof(T) == 4 ? 640 : 320;  // the fp64 phases run on DFMA: keep less work per CTA
+  while (CL < 8 && Np / CL > max_rows) CL *= 2;
   if (const char* e = getenv("VVT_SYEVJ_CL")) CL = vmax(1, vmin(8, atoi(e)));
   while (CL > 1 && Np / CL < 16) CL /= 2;
   const int rows_per_cta = int(ceil_div(Np, CL));
   const bool resident = resident_smem_bytes<T>(rows_per_cta, parts) <= size_t(200) * 1024;
 
   VVT_TRY(check_cuda(cudaMemsetAsync(sc, 0, sizeof(JacobiScalars), s), "vvt_syevj"));
+  int* marks = (int*)(ws + L.off_marks);
+  VVT_TRY(check_cuda(cudaMemsetAsync(marks, 0, size_t(nb + nb * nb) * 4, s), "vvt_syevj"));
   const bool debug = getenv("VVT_SYEVJ_DEBUG") != nullptr;
   const int init_blocks = int(vmin<int64_t>(ceil_div(L.Np * L.Np, 256), 8 * num_sms()));
   const int rr_blocks = int(vmin<int64_t>(ceil_div(R * R, 256), 8 * num_sms()));
@@ -1157,7 +1191,7 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   for (; sweeps < kMaxSweeps;) {
     VVT_TRY(check_cuda(cudaMemsetAsync(&sc->rotations, 0, sizeof(unsigned long long), s), "vvt_syevj"));
     for (int round = -1; round < nb - 1; ++round)
-      VVT_TRY(launch_round<T>(Y, Np, nb, round, CL, rows_per_cta, parts, resident, sc, s));
+      VVT_TRY(launch_round<T>(Y, Np, nb, round, CL, rows_per_cta, parts, resident, sc, marks, sweeps * nb + round + 2, s));
     ++sweeps;
     unsigned long long rot = 0;
     VVT_TRY(check_cuda(cudaMemcpyAsync(&rot, &sc->rotations, sizeof(rot), cudaMemcpyDeviceToHost, s),
