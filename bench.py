@@ -458,6 +458,9 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="warm up, run ONE step between cudaProfilerStart/Stop and exit "
+                         "(for `ncu --profile-from-start off`; prints no bench line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -539,6 +542,13 @@ def main():
 
     for _ in range(args.warmup):
         stepper.step_device()
+    if args.ncu_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        stepper.step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     ms, wall, launches, recs = timed(stepper.step_device, args.steps, with_kernels=True)
     clocks = sampler.stop() if sampler else None

@@ -80,8 +80,8 @@ def main():
     if os.path.exists(lp):
         shutil.copy(lp, os.path.join(OUT, f"{ROUND}_launches_c2.csv"))
         md += ["## ncu launch list of one c2 step", "",
-               "`ncu --metrics gpu__time_duration.sum --clock-control none -s 7400 -c 3400 --csv python bench.py "
-               f"--steps 1 --warmup 3 --no-cpu-baseline` → `{ROUND}_launches_c2.csv`", "", launch_table(lp), ""]
+               "`ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv python bench.py "
+               f"--warmup 3 --ncu-step` (one step between cudaProfilerStart/Stop) → `{ROUND}_launches_c2.csv`", "", launch_table(lp), ""]
     md += ["## ncu --set full captures", "",
            "`profiles/ncu_summary.py <report>` condenses a `.ncu-rep` (raw page + SASS page) into the text files below;",
            "the reports themselves stay in `gpurun_out/` (scratch).", "",
