@@ -424,9 +424,20 @@ def reference_step(w, model, x, y):
                                           mc_samples_ggn=w.get("mc", 0))
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm runs on rank 0 alone and may use every core."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def time_reference(w, dtype, steps, warmup, budget_s):
     """Median ms per step of the oracle on the host cores; stops early once ``budget_s`` of CPU
     time is spent (each step is the full workload, the sample is the number of steps)."""
+    use_all_host_threads()
     model, x, y = make_problem(w, dtype)
     times, t_all = [], time.time()
     for i in range(warmup + steps):
@@ -474,7 +485,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cores = torch.get_num_threads()
+        cores = use_all_host_threads()
         ms, n = time_reference(w, dtype, args.steps, args.warmup, args.cpu_budget_s * 1.5)
         line = {
             "impl": "reference", "metric": METRIC, "value": round(ms, 3), "unit": "ms", "n_gpus": args.gpus,
@@ -609,6 +620,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
+        use_all_host_threads()
         cms, n = time_reference(w, dtype, 1, 0, args.cpu_budget_s)
         cpu = {"value": round(cms, 3), "unit": "ms", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{n} full step(s) of the workload (oracle/reference_path.py, torch CPU)"}
