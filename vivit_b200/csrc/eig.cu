@@ -84,6 +84,8 @@ struct JacobiScalars {
   long long t[8];                // VVT_SYEVJ_DEBUG: phase time stamps of CTA 0 (last launch)
 };
 #define VVT_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) sc->t[i] = clock64(); } while (0)
+__device__ long long g_dbg[16];
+#define VVT_DSTAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_dbg[i] = clock64(); } while (0)
 
 // ---- small vector helpers (16-byte shared/global accesses, packed fp32 FMA) ----------------------
 __device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
@@ -188,23 +190,29 @@ __device__ __forceinline__ bool needs_rotation(T hpp, T hqq, T hpq, T tol2, T ab
   return (hpq * hpq > tol2 * fabs(hpp * hqq)) && (fabs(hpq) > abs2);
 }
 
+__device__ __forceinline__ float rsqrt_fast(float x) {  // one MUFU.RSQ, no denormal rescaling around it
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// fp32: branch-free and division-free.  With d = hqq - hpp, o = 2 hpq, r = sqrt(d^2 + o^2):
+//   cos 2theta = |d| / r,   c = sqrt((1 + cos 2theta) / 2),   s = sign(d) o / (2 r c)
+// (the same inner rotation, |theta| <= pi/4, as t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2))).  Two MUFU.RSQ
+// and six FMA-pipe operations on the dependent chain instead of two reciprocals, two rsqrt and a branch.
 __device__ __forceinline__ bool make_rotation(float hpp, float hqq, float hpq, float tol2, float abs2,
                                               float& c, float& s) {
-  c = 1.f;
-  s = 0.f;
-  if (!needs_rotation(hpp, hqq, hpq, tol2, abs2)) return false;
-  const float zeta = __fdividef(hqq - hpp, 2.f * hpq);
-  const float az = fabsf(zeta);
-  float t;
-  if (az > 1e8f) {
-    t = __fdividef(0.5f, zeta);
-  } else {
-    const float x = fmaf(zeta, zeta, 1.f);
-    t = copysignf(__fdividef(1.f, az + x * rsqrtf(x)), zeta);
-  }
-  c = rsqrtf(fmaf(t, t, 1.f));
-  s = t * c;
-  return true;
+  const bool need = needs_rotation(hpp, hqq, hpq, tol2, abs2);
+  const float d = hqq - hpp, o = hpq + hpq;
+  const float q = fmaf(d, d, o * o);          // > 0 whenever need (|hpq| > eps^2, no underflow of o^2)
+  const float ir = rsqrt_fast(fmaxf(q, 1e-37f));
+  const float c2 = fmaf(0.5f * fabsf(d), ir, 0.5f);  // in [1/2, 1]
+  const float ic = rsqrt_fast(c2);
+  const float cc = c2 * ic;
+  const float ss = copysignf(0.5f, d) * (o * ir) * ic;
+  c = need ? cc : 1.f;
+  s = need ? ss : 0.f;
+  return need;
 }
 
 __device__ __forceinline__ bool make_rotation(double hpp, double hqq, double hpq, double tol2, double abs2,
@@ -232,33 +240,69 @@ __device__ __forceinline__ void cp_async_wait() {
 template <typename T>
 struct RotSmem {
   T H[2][OP][LDH];  // Gram of the panel (double-buffered by the rotation rounds)
-  T Q[OP][LDQ];     // accumulated rotations; before that: this CTA's partial Gram
+  T Q[OP][LDQ];     // accumulated rotations
+  T Gp[OP][LDQ];    // this CTA's partial Gram (read by the other CTAs of the cluster; 16-byte aligned rows)
 };
 
-// H[0] = sum over the CTAs of the cluster of their partial Grams (left in Q), in a fixed order:
-// reduce-scatter + all-gather through distributed shared memory.  Ends with Q = I.
+// H[0] = sum over the CTAs of the cluster of their partial Grams (in Gp), Q = I.  Every CTA reads all the
+// partial Grams through distributed shared memory and adds them in rank order, so that all of them hold
+// bit-identical copies of H (they take the same rotation decisions) after ONE cluster barrier.  The
+// matching "nobody reads my Gp any more" barrier is split: arrive here, wait in cluster_release() just
+// before the CTA exits, off the critical path.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// One float4 / double4 group of H per thread (OP * OP / 4 = OT groups).  `cross`: only the block
+// H[0:OB][OB:OP] is summed (and mirrored); the diagonal blocks were prefetched from the cache into dpre by
+// the threads that own their groups.
 template <typename T>
-__device__ __forceinline__ void cluster_reduce_gram(RotSmem<T>& rs, cg::cluster_group& cluster, int tid) {
-  const int CL = int(cluster.num_blocks()), crank = int(cluster.block_rank());
+__device__ __forceinline__ void cluster_reduce_gram(RotSmem<T>& rs, cg::cluster_group& cluster, int tid, bool cross,
+                                                    const T (&dpre)[4]) {
+  const int CL = int(cluster.num_blocks());
+  const int i = tid >> 3, j = (tid & 7) * 4;
+  const bool in_cross = i < OB && j >= OB, in_diag = (i < OB) == (j < OB);
   if (CL > 1) {
-    cluster.sync();  // every partial Gram is in its CTA's Q
-    for (int idx = crank + tid * CL; idx < OP * OP; idx += OT * CL) {
-      const int i = idx / OP, j = idx % OP;
-      T part[8];
-#pragma unroll
-      for (int p = 0; p < 8; ++p) part[p] = p < CL ? *cluster.map_shared_rank(&rs.Q[i][j], p) : T(0);
-      const T s = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
-#pragma unroll
-      for (int p = 0; p < 8; ++p)
-        if (p < CL) *cluster.map_shared_rank(&rs.H[0][i][j], p) = s;
-    }
-    cluster.sync();  // H[0] complete everywhere; nobody reads a remote Q any more
+    cluster_arrive();  // my partial Gram is written (release) ...
+    cluster_wait();    // ... and so is everybody else's (acquire)
+    VVT_DSTAMP(7);
   } else {
     __syncthreads();
-    for (int idx = tid; idx < OP * OP; idx += OT) rs.H[0][idx / OP][idx % OP] = rs.Q[idx / OP][idx % OP];
-    __syncthreads();
   }
-  for (int idx = tid; idx < OP * OP; idx += OT) rs.Q[idx / OP][idx % OP] = (idx / OP == idx % OP) ? T(1) : T(0);
+  T sum[4] = {T(0), T(0), T(0), T(0)};
+  if (!cross || in_cross) {  // (full mode: Gp is complete, mirrored quadrant included)
+    T part[8][4];
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+      if (p < CL) ld4(CL > 1 ? cluster.map_shared_rank(&rs.Gp[i][j], p) : &rs.Gp[i][j], part[p]);
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+      if (p < CL) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sum[e] += part[p][e];
+      }
+  } else if (in_diag) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sum[e] = dpre[e];
+  }
+  if (!cross || in_cross || in_diag) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) rs.H[0][i][j + e] = sum[e];
+  }
+  if (cross && in_cross) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) rs.H[0][j + e][i] = sum[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) rs.Q[i][j + e] = (i == j + e) ? T(1) : T(0);
+  if (CL > 1) {
+    VVT_DSTAMP(8);
+    cluster_arrive();  // done reading remote shared memory; waited for in cluster_release()
+  }
+}
+
+// A CTA may not exit while another CTA of its cluster can still read its shared memory.
+__device__ __forceinline__ void cluster_release(cg::cluster_group& cluster) {
+  if (cluster.num_blocks() > 1) cluster_wait();
 }
 
 // Does any column pair this round is responsible for still need a rotation?  (block-uniform)
@@ -279,10 +323,10 @@ __device__ __forceinline__ bool any_rotation_needed(const RotSmem<T>& rs, bool i
 // The 16 (cross) or 15 (intra) rotation rounds on H, accumulating Q.  Thread (a, b) owns the 2x2
 // block H[{pa,qa}][{pb,qb}] (H' = Ra^T H Rb); lane b & 15 of every warp derives rotation b and
 // rotation a comes from lane a of the same warp by shuffle.  Returns with the result in Q.
-template <typename T>
-__device__ __forceinline__ void rotation_rounds(RotSmem<T>& rs, bool intra, T tol2, T abs2, int tid) {
+template <typename T, bool intra>
+__device__ __forceinline__ void rotation_rounds(RotSmem<T>& rs, T tol2, T abs2, int tid) {
   const int a = tid >> 4, b = tid & 15;
-  const int n_rounds = intra ? OB - 1 : OB;
+  constexpr int n_rounds = intra ? OB - 1 : OB;
   int cur = 0;
   for (int r = 0; r < n_rounds; ++r, cur ^= 1) {
     T(*Hc)[LDH] = rs.H[cur];
@@ -290,11 +334,16 @@ __device__ __forceinline__ void rotation_rounds(RotSmem<T>& rs, bool intra, T to
     int pa, qa, pb, qb;
     inner_pair(intra, r, a, pa, qa);
     inner_pair(intra, r, b, pb, qb);
+    // every shared-memory read of the round is issued up front (one latency instead of three in a row)
+    const T dpp = Hc[pb][pb], dqq = Hc[qb][qb], dpq = Hc[pb][qb];
+    const T x00 = Hc[pa][pb], x01 = Hc[pa][qb], x10 = Hc[qa][pb], x11 = Hc[qa][qb];
+    T* q0 = &rs.Q[b][0];
+    T* q1 = &rs.Q[b + OB][0];
+    const T q0p = q0[pa], q0q = q0[qa], q1p = q1[pa], q1q = q1[qa];
     T cb, sb;
-    const bool db = make_rotation(Hc[pb][pb], Hc[qb][qb], Hc[pb][qb], tol2, abs2, cb, sb);
+    const bool db = make_rotation(dpp, dqq, dpq, tol2, abs2, cb, sb);
     const T ca = __shfl_sync(0xffffffffu, cb, a), sa = __shfl_sync(0xffffffffu, sb, a);
     // X = H[{pa,qa}][{pb,qb}];  T = X Rb;  H' = Ra^T T,  R = [[c, s], [-s, c]]
-    const T x00 = Hc[pa][pb], x01 = Hc[pa][qb], x10 = Hc[qa][pb], x11 = Hc[qa][qb];
     const T t00 = cb * x00 - sb * x01, t01 = sb * x00 + cb * x01;
     const T t10 = cb * x10 - sb * x11, t11 = sb * x10 + cb * x11;
     T h00 = ca * t00 - sa * t10, h01 = ca * t01 - sa * t11;
@@ -305,13 +354,10 @@ __device__ __forceinline__ void rotation_rounds(RotSmem<T>& rs, bool intra, T to
     Hn[qa][pb] = h10;
     Hn[qa][qb] = h11;
     // Q <- Q R: rows k = b, b + 16 of column pair a (in place: one owner per element and round)
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      const int k = b + kk * OB;
-      const T qp = rs.Q[k][pa], qq = rs.Q[k][qa];
-      rs.Q[k][pa] = ca * qp - sa * qq;
-      rs.Q[k][qa] = sa * qp + ca * qq;
-    }
+    q0[pa] = ca * q0p - sa * q0q;
+    q0[qa] = sa * q0p + ca * q0q;
+    q1[pa] = ca * q1p - sa * q1q;
+    q1[qa] = sa * q1p + ca * q1q;
     __syncthreads();
   }
 }
@@ -322,7 +368,8 @@ template <typename T>
 __device__ __forceinline__ void rotate_and_broadcast(RotSmem<T>& rs, cg::cluster_group& cluster, bool intra,
                                                      T tol2, T abs2, int tid) {
   (void)cluster;
-  rotation_rounds<T>(rs, intra, tol2, abs2, tid);
+  if (intra) rotation_rounds<T, true>(rs, tol2, abs2, tid);
+  else rotation_rounds<T, false>(rs, tol2, abs2, tid);
 }
 
 // this thread's share of a 4x4 tile of P^T P: rows r = ks, ks + 4, ... < nrows of a row-major chunk
@@ -357,7 +404,7 @@ __device__ __forceinline__ void gram_store(RotSmem<T>& rs, T (&acc)[4][4], int k
       T v = acc[i][j];
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (ks == 0) rs.Q[4 * ti + i][4 * tj + j] = v;
+      if (ks == 0) rs.Gp[4 * ti + i][4 * tj + j] = v;
     }
 }
 
@@ -443,11 +490,11 @@ __device__ __forceinline__ void gram_tile8_store(RotSmem<float>& rs, float (&v)[
     }
   }
   const int i = 8 * ti + (lane >> 2), j = 8 * tj + 2 * (lane & 3);
-  rs.Q[i][j] = v[0];
-  rs.Q[i][j + 1] = v[1];
+  rs.Gp[i][j] = v[0];
+  rs.Gp[i][j + 1] = v[1];
   if (ti != tj) {
-    rs.Q[j][i] = v[0];
-    rs.Q[j + 1][i] = v[1];
+    rs.Gp[j][i] = v[0];
+    rs.Gp[j + 1][i] = v[1];
   }
 }
 
@@ -502,10 +549,6 @@ __device__ __forceinline__ void apply_phase_fast(const RotSmem<float>& rs, const
 // ---- fp32 tensor-core paths for the two O(rows) phases (mma.sync m16n8k8, 3xTF32 split: fp32-grade) -------
 constexpr int kGramStageFloats = (OT / 32) * OP * OP;  // per-warp partial Grams, summed in a fixed order
 
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = to_tf32(x);
-  lo = to_tf32(x - __uint_as_float(hi));
-}
 __device__ __forceinline__ void mma3(float (&acc)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
                                      const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
   mma_tf32(acc, al, bh);
@@ -515,12 +558,17 @@ __device__ __forceinline__ void mma3(float (&acc)[4], const uint32_t (&ah)[4], c
 
 // H = P^T P for this CTA's rows: the warps split the rows in steps of 8; the same eight shared-memory
 // values per lane serve as A and B fragments (H is symmetric: only tiles on or above the diagonal).
+// CROSS: only the 16x16 block P_a^T P_b (the diagonal blocks come from the cache, see DiagCache): a third
+// of the tensor-core work.
+template <bool CROSS>
 __device__ __forceinline__ void gram_phase_mma(RotSmem<float>& rs, float* stage, const float* P, int ldp, int nrows,
                                                int tid) {
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  float acc[6][4];  // (mt 0, nt 0..3), (mt 1, nt 2..3)
+  VVT_DSTAMP(0);
+  constexpr int NACC = CROSS ? 2 : 6;
+  float acc[NACC][4];  // full: (mt 0, nt 0..3), (mt 1, nt 2..3);  cross: (mt 0, nt 2..3)
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < NACC; ++i)
 #pragma unroll
     for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
   for (int k0 = 8 * warp; k0 < nrows; k0 += 8 * (OT / 32)) {
@@ -533,42 +581,61 @@ __device__ __forceinline__ void gram_phase_mma(RotSmem<float>& rs, float* stage,
       split_tf32(x0, hi[c][0], lo[c][0]);
       split_tf32(x1, hi[c][1], lo[c][1]);
     }
+    if constexpr (CROSS) {
+      const uint32_t ah[4] = {hi[0][0], hi[1][0], hi[0][1], hi[1][1]};
+      const uint32_t al[4] = {lo[0][0], lo[1][0], lo[0][1], lo[1][1]};
+      mma3(acc[0], ah, al, hi[2], lo[2]);
+      mma3(acc[1], ah, al, hi[3], lo[3]);
+    } else {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const uint32_t ah[4] = {hi[2 * mt][0], hi[2 * mt + 1][0], hi[2 * mt][1], hi[2 * mt + 1][1]};
-      const uint32_t al[4] = {lo[2 * mt][0], lo[2 * mt + 1][0], lo[2 * mt][1], lo[2 * mt + 1][1]};
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t ah[4] = {hi[2 * mt][0], hi[2 * mt + 1][0], hi[2 * mt][1], hi[2 * mt + 1][1]};
+        const uint32_t al[4] = {lo[2 * mt][0], lo[2 * mt + 1][0], lo[2 * mt][1], lo[2 * mt + 1][1]};
 #pragma unroll
-      for (int nt = 2 * mt; nt < 4; ++nt) mma3(acc[mt == 0 ? nt : 2 + nt], ah, al, hi[nt], lo[nt]);
+        for (int nt = 2 * mt; nt < 4; ++nt) mma3(acc[mt == 0 ? nt : 2 + nt], ah, al, hi[nt], lo[nt]);
+      }
     }
   }
+  VVT_DSTAMP(1);
   float* mine = stage + warp * (OP * OP);
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < (CROSS ? 1 : 2); ++mt)
 #pragma unroll
-    for (int nt = 2 * mt; nt < 4; ++nt) {
-      const float(&a)[4] = acc[mt == 0 ? nt : 2 + nt];
+    for (int nt = (CROSS ? 2 : 2 * mt); nt < 4; ++nt) {
+      const float(&a)[4] = acc[CROSS ? nt - 2 : (mt == 0 ? nt : 2 + nt)];
       const int row = 16 * mt + g, col = 8 * nt + 2 * t;
       mine[row * OP + col] = a[0];
       mine[row * OP + col + 1] = a[1];
       mine[(row + 8) * OP + col] = a[2];
       mine[(row + 8) * OP + col + 1] = a[3];
     }
+  VVT_DSTAMP(2);
   __syncthreads();
-  for (int e = tid; e < OP * OP; e += OT) {
-    const int row = e / OP, col = e % OP;
-    if (row > col) continue;
-    float s = 0.f;
+  VVT_DSTAMP(3);
+  // cross-warp sum, one float4 of the tile per thread.  Only the tiles on or above the diagonal of the 2x2
+  // grid of 16x16 quadrants were computed: the upper-right quadrant is mirrored into the lower-left one.
+  {
+    const int row = tid >> 3, col = (tid & 7) * 4;
+    if (CROSS ? (row < OB && col >= OB) : (row < OB || col >= OB)) {
+      float4 sum = *reinterpret_cast<const float4*>(stage + row * OP + col);
 #pragma unroll
-    for (int w = 0; w < OT / 32; ++w) s += stage[w * (OP * OP) + e];
-    rs.Q[row][col] = s;
-    rs.Q[col][row] = s;
+      for (int w = 1; w < OT / 32; ++w) {
+        const float4 v = *reinterpret_cast<const float4*>(stage + w * (OP * OP) + row * OP + col);
+        sum.x += v.x, sum.y += v.y, sum.z += v.z, sum.w += v.w;
+      }
+      *reinterpret_cast<float4*>(&rs.Gp[row][col]) = sum;
+      if (!CROSS && row < OB && col >= OB)
+        rs.Gp[col][row] = sum.x, rs.Gp[col + 1][row] = sum.y, rs.Gp[col + 2][row] = sum.z, rs.Gp[col + 3][row] = sum.w;
+    }
   }
+  VVT_DSTAMP(4);
 }
 
 // out = P Q for this CTA's rows, straight to global memory; Q fragments (hi/lo) stay in registers
 __device__ __forceinline__ void apply_phase_mma(const RotSmem<float>& rs, const float* P, int ldp, int nrows, float* Y,
                                                 int Np, int ba, int bb, int grow0, int tid) {
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  VVT_DSTAMP(5);
   uint32_t qh[4][4][2], ql[4][4][2];  // [k-step][n-tile]
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks)
@@ -577,6 +644,7 @@ __device__ __forceinline__ void apply_phase_mma(const RotSmem<float>& rs, const 
       split_tf32(rs.Q[8 * ks + t][8 * nt + g], qh[ks][nt][0], ql[ks][nt][0]);
       split_tf32(rs.Q[8 * ks + t + 4][8 * nt + g], qh[ks][nt][1], ql[ks][nt][1]);
     }
+  VVT_DSTAMP(6);
   for (int m0 = 16 * warp; m0 < nrows; m0 += 16 * (OT / 32)) {
     const int ra = m0 + g, rb = m0 + g + 8;
     const bool va = ra < nrows, vb = rb < nrows;
@@ -633,7 +701,7 @@ __device__ __forceinline__ bool pair_is_clean(int* marks, int nb, int ba, int bb
 template <typename T>
 __global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
 onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc,
-                               int* marks, int now) {
+                               int* marks, int now, T* Dc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RotSmem<T>& rs = *reinterpret_cast<RotSmem<T>*>(smem_raw);
   T* P = reinterpret_cast<T*>(smem_raw + ((sizeof(RotSmem<T>) + 15) / 16) * 16);  // [parts * rows][LDP]: W rows(, J rows)
@@ -653,6 +721,18 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (pair_is_clean(marks, nb, ba, bb, intra)) return;  // same decision in every CTA of the cluster
   VVT_STAMP(0);
+  // DiagCache: Dc[blk][OB][OB] holds the diagonal block W_blk^T W_blk of every column block as the last
+  // rotation round left it in H.  Cross rounds take both diagonal blocks from there and form only the
+  // OB x OB cross block on the tensor cores; the intra round of every sweep recomputes them exactly, which
+  // bounds the rounding drift of the cached values to one sweep of two-sided updates (~1e-6 relative; the
+  // rotation angles and the convergence test of a cross round depend on them only through h_pp, h_qq).
+  constexpr bool kCache = sizeof(T) == 4 && kJacobiMma;
+  const bool cross = kCache && !intra;
+  const int gi = tid >> 3, gj = (tid & 7) * 4;                 // this thread's group of 4 entries of H
+  const bool g_diag = (gi < OB) == (gj < OB);
+  T* dslot = Dc + (size_t(gi < OB ? ba : bb) * OB + (gi & (OB - 1))) * OB + (gj & (OB - 1));
+  T dpre[4] = {T(0), T(0), T(0), T(0)};
+  if (cross && g_diag) ld4(dslot, dpre);
   // all loads are issued up front: group 0 = W rows (needed now), group 1 = J rows (needed last)
   {
     constexpr int V = 16 / sizeof(T), VPR = OB / V;  // elements per 16 bytes, vectors per block row
@@ -672,8 +752,12 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
 
   if constexpr (sizeof(T) == 4) {  // phase 1: partial Gram of this CTA's rows of W
     float* stage = P + size_t(parts) * rows_per_cta * LDP;  // behind the resident rows
-    if (kJacobiMma) gram_phase_mma(rs, stage, P, LDP, nrows, tid);
-    else gram_phase_fast(rs, P, LDP, nrows, tid);
+    if (kJacobiMma) {
+      if (cross) gram_phase_mma<true>(rs, stage, P, LDP, nrows, tid);
+      else gram_phase_mma<false>(rs, stage, P, LDP, nrows, tid);
+    } else {
+      gram_phase_fast(rs, P, LDP, nrows, tid);
+    }
   } else {
     const int ks = tid & 3, ti = tid >> 5, tj = (tid >> 2) & 7;
     T acc[4][4];
@@ -685,12 +769,17 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
     gram_store<T>(rs, acc, ks, ti, tj);
   }
   VVT_STAMP(2);
-  cluster_reduce_gram<T>(rs, cluster, tid);
+  cluster_reduce_gram<T>(rs, cluster, tid, cross, dpre);
   __syncthreads();
   VVT_STAMP(3);
   if (!any_rotation_needed<T>(rs, intra, tol2, abs2, tid)) {  // uniform over the cluster (same H)
     if (crank == 0 && tid == 0) *clean_slot(marks, nb, ba, bb, intra) = now;
+    if (kCache && intra && crank == 0 && g_diag) {  // exact diagonal blocks: refresh the cache
+      const T v[4] = {rs.H[0][gi][gj], rs.H[0][gi][gj + 1], rs.H[0][gi][gj + 2], rs.H[0][gi][gj + 3]};
+      st4(dslot, v);
+    }
     cp_async_wait<0>();
+    cluster_release(cluster);
     return;
   }
   if (crank == 0 && tid == 0) {
@@ -700,6 +789,11 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
   }
   rotate_and_broadcast<T>(rs, cluster, intra, tol2, abs2, tid);  // phase 2
   VVT_STAMP(4);
+  if (kCache && crank == 0 && g_diag) {  // the rotated diagonal blocks (the rounds end in H[rounds & 1])
+    const int fin = (intra ? OB - 1 : OB) & 1;
+    const T v[4] = {rs.H[fin][gi][gj], rs.H[fin][gi][gj + 1], rs.H[fin][gi][gj + 2], rs.H[fin][gi][gj + 3]};
+    st4(dslot, v);
+  }
   cp_async_wait<0>();
   __syncthreads();
   VVT_STAMP(5);
@@ -715,6 +809,7 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
         apply_rows<T>(rs, P + size_t(part) * nrows * LDP, LDP, r_base, nrows, Y, Np, ba, bb, part * Np + w0, tr, tc);
   }
   VVT_STAMP(6);
+  cluster_release(cluster);
 }
 
 // ---- streaming variant (any size): rows pass through two chunk buffers, W is read twice -----------
@@ -739,7 +834,8 @@ __device__ __forceinline__ void load_chunk(T (*dst)[LDP], const T* Y, int Np, in
 template <typename T>
 __global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
 onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc,
-                             int* marks, int now) {
+                             int* marks, int now, T* Dc) {
+  (void)Dc;  // the streaming variant recomputes the whole panel Gram in every round
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StreamSmem<T>& sm = *reinterpret_cast<StreamSmem<T>*>(smem_raw);
   RotSmem<T>& rs = sm.rs;
@@ -778,10 +874,14 @@ onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, 
     }
     gram_store<T>(rs, acc, ks, ti, tj);
   }
-  cluster_reduce_gram<T>(rs, cluster, tid);
+  {
+    const T none[4] = {T(0), T(0), T(0), T(0)};
+    cluster_reduce_gram<T>(rs, cluster, tid, false, none);
+  }
   __syncthreads();
   if (!any_rotation_needed<T>(rs, intra, tol2, abs2, tid)) {
     if (crank == 0 && tid == 0) *clean_slot(marks, nb, ba, bb, intra) = now;
+    cluster_release(cluster);
     return;
   }
   if (crank == 0 && tid == 0) {
@@ -810,6 +910,7 @@ onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, 
       __syncthreads();
     }
   }
+  cluster_release(cluster);
 }
 
 // ---- Cholesky preconditioner ------------------------------------------------------------------------
@@ -1045,7 +1146,7 @@ __global__ void jacobi_permute_kernel(T* evals, T* evecs, const T* ev, const T* 
 }
 
 struct JacobiLayout {
-  int64_t Np, nb, off_Y, off_Gs, off_Jm, off_Jt, off_Tt, off_S, off_M, off_Et, off_ev, off_cn, off_rank, off_sc, off_marks, off_gemm, gemm_bytes, total;
+  int64_t Np, nb, off_Y, off_Gs, off_Jm, off_Jt, off_Tt, off_S, off_M, off_Et, off_ev, off_cn, off_rank, off_sc, off_marks, off_dc, off_gemm, gemm_bytes, total;
 };
 
 static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
@@ -1071,6 +1172,7 @@ static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
   L.off_rank = take(R * 4);
   L.off_sc = take(sizeof(JacobiScalars));
   L.off_marks = take((L.nb + L.nb * L.nb) * 4);
+  L.off_dc = take(L.nb * OB * OB * es);
   L.gemm_bytes = vvt_gram_workspace_bytes(R, R, R, dtype);
   L.off_gemm = take(L.gemm_bytes);
   L.total = o;
@@ -1085,9 +1187,12 @@ static size_t resident_smem_bytes(int rows_per_cta, int parts) {
 
 template <typename T>
 static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_cta, int parts, bool resident,
-                        JacobiScalars* sc, int* marks, int now, cudaStream_t s) {
+                        JacobiScalars* sc, int* marks, int now, T* Dc, cudaStream_t s) {
   auto kern = resident ? onesided_round_resident_kernel<T> : onesided_round_stream_kernel<T>;
-  const size_t smem = resident ? resident_smem_bytes<T>(rows_per_cta, parts) : sizeof(StreamSmem<T>);
+  size_t smem = resident ? resident_smem_bytes<T>(rows_per_cta, parts) : sizeof(StreamSmem<T>);
+  // a round that fits on the GPU with one CTA per SM asks for more than half of an SM's shared memory, so
+  // that no two CTAs share an SM (and its tensor pipe) while other SMs idle
+  if (int64_t(nb / 2) * CL <= num_sms()) smem = vmax<size_t>(smem, size_t(116) * 1024);
   static size_t attr_done[2] = {0, 0};  // per instantiation: largest size configured so far
   if (attr_done[resident] < smem) {
     VVT_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
@@ -1109,7 +1214,7 @@ static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_ct
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
-  VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, parts, sc, marks, now), "vvt_syevj(round)"));
+  VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, parts, sc, marks, now, Dc), "vvt_syevj(round)"));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return VVT_OK;
 }
@@ -1143,7 +1248,10 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   int CL = 1;
   const int max_rows = sizeof(T) == 4 ? 640 : 320;  // the fp64 phases run on DFMA: keep less work per CTA
   while (CL < 8 && Np / CL > max_rows) CL *= 2;
-  if (const char* e = getenv("VVT_SYEVJ_CL")) CL = vmax(1, vmin(8, atoi(e)));
+  // SMs left idle by a round (pairs * CL < #SMs) are put to work with a larger, possibly odd cluster, as long
+  // as a CTA keeps enough rows for the Gram / apply phases to outweigh the cluster reduction (R = 1280, fp32:
+  // 3 CTAs x 427 rows on 120 SMs, 16.3 ms against 17.7 ms with 2 x 640 on 80 SMs)
+  while (CL < 8 && int64_t(pairs) * (CL + 1) <= num_sms() && Np / (CL + 1) >= max_rows / 2) ++CL;
   while (CL > 1 && Np / CL < 16) CL /= 2;
   const int rows_per_cta = int(ceil_div(Np, CL));
   const bool resident = resident_smem_bytes<T>(rows_per_cta, parts) <= size_t(200) * 1024;
@@ -1191,7 +1299,8 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   for (; sweeps < kMaxSweeps;) {
     VVT_TRY(check_cuda(cudaMemsetAsync(&sc->rotations, 0, sizeof(unsigned long long), s), "vvt_syevj"));
     for (int round = -1; round < nb - 1; ++round)
-      VVT_TRY(launch_round<T>(Y, Np, nb, round, CL, rows_per_cta, parts, resident, sc, marks, sweeps * nb + round + 2, s));
+      VVT_TRY(launch_round<T>(Y, Np, nb, round, CL, rows_per_cta, parts, resident, sc, marks, sweeps * nb + round + 2,
+                              (T*)(ws + L.off_dc), s));
     ++sweeps;
     unsigned long long rot = 0;
     VVT_TRY(check_cuda(cudaMemcpyAsync(&rot, &sc->rotations, sizeof(rot), cudaMemcpyDeviceToHost, s),
@@ -1203,6 +1312,11 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
       fprintf(stderr, "[vvt_syevj] R=%lld CL=%d sweep %d: %llu of %d block pairs rotated; CTA0 clocks:", (long long)R,
               CL, sweeps, rot, pairs * nb);
       for (int i = 1; i < 7; ++i) fprintf(stderr, " %lld", h.t[i] - h.t[i - 1]);
+      long long d[16];
+      cudaMemcpyFromSymbol(d, g_dbg, sizeof(d));
+      fprintf(stderr, " | gram: loop %lld stage %lld bar %lld sum %lld | apply: qfrag %lld (from t5 %lld)", d[1] - d[0],
+              d[2] - d[1], d[3] - d[2], d[4] - d[3], d[6] - d[5], d[5] - h.t[5]);
+      fprintf(stderr, " | reduce: barrier %lld sum %lld", d[7] - h.t[2], d[8] - d[7]);
       fprintf(stderr, "\n");
     }
     // a sweep that rotated (almost) nothing ends the iteration: the last few block pairs only carry

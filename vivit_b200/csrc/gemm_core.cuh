@@ -43,6 +43,25 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   return r;
 }
 
+// 3xTF32 split  x ~= hi + lo  without conversion instructions.  The tensor core reads a tf32 operand by
+// ignoring the 13 low mantissa bits of the fp32 word, so the word itself serves as "hi"; lo = x - trunc(x)
+// is exact in fp32, and adding half a tf32 ulp to its bit pattern turns the hardware's truncation of lo into
+// round-to-nearest (ties away, as cvt.rna).  3 ALU ops per element instead of ~10 for two cvt.rna.tf32.f32
+// (which ptxas expands to compare / add / select / mask on sm_100).  VVT_TF32_TRUNC=0 restores the cvt form.
+#ifndef VVT_TF32_TRUNC
+#define VVT_TF32_TRUNC 1
+#endif
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+#if VVT_TF32_TRUNC
+  const uint32_t b = __float_as_uint(x);
+  hi = b;
+  lo = __float_as_uint(x - __uint_as_float(b & 0xFFFFE000u)) + 0x1000u;
+#else
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+#endif
+}
+
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
@@ -85,8 +104,7 @@ struct WarpMma<float> {
         float a[4] = {p[0], p[8 * Cfg::LDS], p[4], p[8 * Cfg::LDS + 4]};
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          ahi[mi][r] = to_tf32(a[r]);
-          alo[mi][r] = to_tf32(a[r] - __uint_as_float(ahi[mi][r]));
+          split_tf32(a[r], ahi[mi][r], alo[mi][r]);
         }
       }
 #pragma unroll
@@ -95,8 +113,7 @@ struct WarpMma<float> {
         float b[2] = {p[0], p[4]};
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          bhi[ni][r] = to_tf32(b[r]);
-          blo[ni][r] = to_tf32(b[r] - __uint_as_float(bhi[ni][r]));
+          split_tf32(b[r], bhi[ni][r], blo[ni][r]);
         }
       }
 #pragma unroll
