@@ -196,17 +196,21 @@ __global__ void linear_emit_kernel(T* Vt, const T* S, const T* Z, int64_t V, int
 }
 
 // ---- dense back-transform: E[K, D] = U[K, R] V[R, D] -------------------------
-// Streams V exactly once per KT directions.  Each thread owns VW consecutive columns (one 16-byte
-// load per row, coalesced across the warp) and KT x VW accumulators; U is staged through shared
-// memory in row chunks; loads of 4 rows are in flight per thread.
+// Streams V exactly once per KT directions.  A CTA owns 32 x VW consecutive columns (one 16-byte load per
+// row and lane, coalesced across the warp); its 8 warps split the rows (warp w takes rows w*8 .. w*8+7 of
+// every 64-row chunk, all 8 loads in flight), so that narrow factors (biases, small kernels) still spread
+// their rows over 8 warps and wide ones keep 2048 threads x 128 bytes in flight per SM.  U is staged
+// through shared memory in 64-row chunks (double-buffered: one barrier per chunk); the 8 partial sums per
+// column are added in a fixed order through shared memory (deterministic), squared norms fused.
 template <typename T, int KT, int VW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 backtransform_dense_kernel(T* E, double* norm2, const T* U, const T* V, int64_t K, int64_t R, int64_t D,
                            int64_t k0) {
-  constexpr int RC = 64;  // rows of V per U chunk
-  __shared__ T Us[RC][KT];
-  __shared__ double red[KT][4];
-  const int64_t d0 = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) * VW;
+  constexpr int RC = 64, RB = 8, NW = 8;  // rows per U chunk, rows in flight per thread, warps
+  __shared__ T Us[2][RC][KT];
+  __shared__ __align__(16) T red[NW][32][VW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t d0 = (blockIdx.x * int64_t(32) + lane) * VW;
   const int kn = int(vmin<int64_t>(KT, K - k0));
   const bool vec = (D % VW == 0) && d0 + VW <= D && (reinterpret_cast<uintptr_t>(V) & 15) == 0;  // aligned full vector
   T acc[KT][VW];
@@ -214,78 +218,82 @@ backtransform_dense_kernel(T* E, double* norm2, const T* U, const T* V, int64_t 
   for (int k = 0; k < KT; ++k)
 #pragma unroll
     for (int v = 0; v < VW; ++v) acc[k][v] = 0;
-  for (int64_t r0 = 0; r0 < R; r0 += RC) {
+  auto stage_u = [&](int buf, int64_t r0) {
     const int rn = int(vmin<int64_t>(RC, R - r0));
-    __syncthreads();
-    for (int i = threadIdx.x; i < KT * RC; i += blockDim.x) {
+    for (int i = threadIdx.x; i < KT * RC; i += 256) {
       const int k = i / RC, r = i % RC;
-      Us[r][k] = (k < kn && r < rn) ? U[(k0 + k) * R + r0 + r] : T(0);
+      Us[buf][r][k] = (k < kn && r < rn) ? U[(k0 + k) * R + r0 + r] : T(0);
     }
-    __syncthreads();
-    if (d0 < D) {
-      const T* vp = V + r0 * D + d0;
-      constexpr int RB = 8;  // rows whose loads are in flight together (RB x 16 bytes per thread)
-      for (int rb = 0; rb < rn; rb += RB) {
-        T x[RB][VW];
+  };
+  stage_u(0, 0);
+  int buf = 0;
+  for (int64_t r0 = 0; r0 < R; r0 += RC, buf ^= 1) {
+    __syncthreads();  // chunk `buf` is staged; everybody is done with the other buffer
+    if (r0 + RC < R) stage_u(buf ^ 1, r0 + RC);
+    const int rn = int(vmin<int64_t>(RC, R - r0));
+    const int rb = warp * RB;
+    if (d0 < D && rb < rn) {
+      const T* vp = V + (r0 + rb) * D + d0;
+      T x[RB][VW];
 #pragma unroll
-        for (int i = 0; i < RB; ++i) {
-          const int r = rb + i;
-          if (r < rn) {
-            if (vec) {
-              if constexpr (sizeof(T) * VW == 16) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(vp + int64_t(r) * D));
-                const T* tp = reinterpret_cast<const T*>(&t);
+      for (int i = 0; i < RB; ++i) {
+        if (rb + i < rn) {
+          if (vec) {
+            if constexpr (sizeof(T) * VW == 16) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(vp + int64_t(i) * D));
+              const T* tp = reinterpret_cast<const T*>(&t);
 #pragma unroll
-                for (int v = 0; v < VW; ++v) x[i][v] = tp[v];
-              } else {
-#pragma unroll
-                for (int v = 0; v < VW; ++v) x[i][v] = ldg(vp + int64_t(r) * D + v);
-              }
+              for (int v = 0; v < VW; ++v) x[i][v] = tp[v];
             } else {
 #pragma unroll
-              for (int v = 0; v < VW; ++v) x[i][v] = d0 + v < D ? ldg(vp + int64_t(r) * D + v) : T(0);
+              for (int v = 0; v < VW; ++v) x[i][v] = ldg(vp + int64_t(i) * D + v);
             }
           } else {
 #pragma unroll
-            for (int v = 0; v < VW; ++v) x[i][v] = T(0);
+            for (int v = 0; v < VW; ++v) x[i][v] = d0 + v < D ? ldg(vp + int64_t(i) * D + v) : T(0);
           }
+        } else {
+#pragma unroll
+          for (int v = 0; v < VW; ++v) x[i][v] = T(0);
         }
+      }
 #pragma unroll
-        for (int i = 0; i < RB; ++i) {
-          const int r = vmin(rb + i, RC - 1);
+      for (int i = 0; i < RB; ++i) {
 #pragma unroll
-          for (int k = 0; k < KT; ++k) {
-            const T u = Us[r][k];
+        for (int k = 0; k < KT; ++k) {
+          const T u = Us[buf][rb + i][k];  // rows past rn are staged as zero
 #pragma unroll
-            for (int v = 0; v < VW; ++v) acc[k][v] += u * x[i][v];
-          }
+          for (int v = 0; v < VW; ++v) acc[k][v] += u * x[i][v];
         }
       }
     }
   }
+  // cross-warp sum, direction by direction: warp (k mod 8) finishes direction k
 #pragma unroll
   for (int k = 0; k < KT; ++k) {
-    if (k < kn) {
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < VW; ++v) red[warp][lane][v] = acc[k][v];
+    __syncthreads();
+    if (warp == (k & (NW - 1)) && k < kn) {
+      T sum[VW];
+#pragma unroll
+      for (int v = 0; v < VW; ++v) sum[v] = red[0][lane][v];
+#pragma unroll
+      for (int w = 1; w < NW; ++w)
+#pragma unroll
+        for (int v = 0; v < VW; ++v) sum[v] += red[w][lane][v];
+      double sq = 0.0;
 #pragma unroll
       for (int v = 0; v < VW; ++v)
-        if (d0 + v < D) E[(k0 + k) * D + d0 + v] = acc[k][v];
-    }
-  }
-  if (norm2) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-      double s = 0.0;
-#pragma unroll
-      for (int v = 0; v < VW; ++v) s += (d0 + v < D) ? double(acc[k][v]) * double(acc[k][v]) : 0.0;
-      s = warp_sum(s);
-      if (lane == 0) red[k][warp] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < kn) {
-      double s = 0;
-      for (int w = 0; w < 4; ++w) s += red[threadIdx.x][w];
-      atomicAdd(norm2 + k0 + threadIdx.x, s);
+        if (d0 + v < D) {
+          E[(k0 + k) * D + d0 + v] = sum[v];
+          sq += double(sum[v]) * double(sum[v]);
+        }
+      if (norm2) {
+        sq = warp_sum(sq);
+        if (lane == 0) atomicAdd(norm2 + k0 + k, sq);
+      }
     }
   }
 }
@@ -466,24 +474,24 @@ int vvt_backtransform_dense(void* E, void* norm2, const void* U, const void* V, 
   VVT_REQUIRE(E && U && V, "null pointer");
   VVT_DISPATCH(dtype, {
     constexpr int VW = 16 / int(sizeof(T));  // one 16-byte load per row and thread
-    const unsigned blocks = unsigned(ceil_div(D, 128 * VW));
+    const unsigned blocks = unsigned(ceil_div(D, 32 * VW));
     int64_t k0 = 0;
     while (k0 < K) {  // 16 directions per pass over V while that many remain, then 8 / 4 / 2 / 1
       const int64_t left = K - k0;
       if (left > 8) {
-        backtransform_dense_kernel<T, 16, VW><<<blocks, 128, 0, as_stream(stream)>>>(
+        backtransform_dense_kernel<T, 16, VW><<<blocks, 256, 0, as_stream(stream)>>>(
             (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);
         k0 += 16;
       } else if (left > 4) {
-        backtransform_dense_kernel<T, 8, VW><<<blocks, 128, 0, as_stream(stream)>>>(
+        backtransform_dense_kernel<T, 8, VW><<<blocks, 256, 0, as_stream(stream)>>>(
             (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);
         k0 += 8;
       } else if (left > 1) {
-        backtransform_dense_kernel<T, 4, VW><<<blocks, 128, 0, as_stream(stream)>>>(
+        backtransform_dense_kernel<T, 4, VW><<<blocks, 256, 0, as_stream(stream)>>>(
             (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);
         k0 += 4;
       } else {
-        backtransform_dense_kernel<T, 1, VW><<<blocks, 128, 0, as_stream(stream)>>>(
+        backtransform_dense_kernel<T, 1, VW><<<blocks, 256, 0, as_stream(stream)>>>(
             (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);
         k0 += 1;
       }
@@ -500,7 +508,7 @@ int vvt_v_apply_dense(void* step, const void* v, const void* V, int64_t R, int64
   VVT_REQUIRE(step && v && V, "null pointer");
   VVT_DISPATCH(dtype, {
     constexpr int VW = 16 / int(sizeof(T));
-    backtransform_dense_kernel<T, 1, VW><<<unsigned(ceil_div(D, 128 * VW)), 128, 0, as_stream(stream)>>>(
+    backtransform_dense_kernel<T, 1, VW><<<unsigned(ceil_div(D, 32 * VW)), 256, 0, as_stream(stream)>>>(
         (T*)step, nullptr, (const T*)v, (const T*)V, 1, R, D, 0);
     return launched(__func__);
   });
