@@ -935,62 +935,126 @@ __device__ __forceinline__ T chol_shift(const JacobiScalars* sc) {
 // One step of the blocked right-looking factorisation on A (row-major, ld = R, lower triangle):
 // every CTA factors the diagonal block A[k:k+b, k:k+b] in shared memory (redundantly -- it is tiny),
 // CTA 0 writes it back, and the CTAs split the rows below it:  L21 = A21 L11^{-T}  by substitution.
+constexpr int LDD = CB + 4;  // pitch of the diagonal block in shared memory (16-byte aligned rows)
+
+__device__ __forceinline__ float rsqrt_any(float x) { return rsqrt_fast(x); }
+__device__ __forceinline__ double rsqrt_any(double x) { return rsqrt(x); }
+
+// Factors the CB x CB block held in D (lower triangle, zero-padded) in ONE warp, entirely in registers:
+// lane l owns rows l and l + 32; a step broadcasts the pivot and the scaled column by warp shuffles (fully
+// unrolled: every register index is static), so the 64 dependent steps cost a shuffle + rsqrt each instead
+// of two block-wide barriers.  The factor only preconditions the Jacobi iteration: rsqrt accuracy is plenty.
 template <typename T>
-__global__ void __launch_bounds__(CROWS) chol_panel_kernel(T* A, int64_t R, int k, int b, const JacobiScalars* sc) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T(*D)[CB + 1] = reinterpret_cast<T(*)[CB + 1]>(smem_raw);
-  T* diag = reinterpret_cast<T*>(smem_raw) + CB * (CB + 1);
-  T(*X)[CB + 1] = reinterpret_cast<T(*)[CB + 1]>(diag + CB);
-  const int tid = threadIdx.x;
-  const T floor_piv = chol_shift<T>(sc);
-  for (int idx = tid; idx < b * b; idx += CROWS) {
-    const int i = idx / b, j = idx % b;
-    D[i][j] = (j <= i) ? A[(int64_t(k) + i) * R + k + j] : T(0);
+__device__ __forceinline__ void chol_diag_warp(T (*D)[LDD], T* dinv, T floor_piv, int lane) {
+  T r0[CB], r1[CB];
+#pragma unroll
+  for (int c4 = 0; c4 < CB; c4 += 4) {
+    T a[4], b4[4];
+    ld4(&D[lane][c4], a);
+    ld4(&D[lane + 32][c4], b4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r0[c4 + e] = a[e], r1[c4 + e] = b4[e];
   }
-  // this CTA's rows of the panel travel while the diagonal block is factored
-  const int64_t row0 = int64_t(k) + b + int64_t(blockIdx.x) * CROWS;
-  const int nrows = int(vmax<int64_t>(0, vmin<int64_t>(CROWS, R - row0)));
-  for (int idx = tid; idx < nrows * b; idx += CROWS) {
-    const int r = idx / b, c = idx % b;
-    X[r][c] = A[(row0 + r) * R + k + c];
-  }
-  for (int j = 0; j < b; ++j) {
-    __syncthreads();
-    const T piv = sqrt(vmax(D[j][j], floor_piv));  // D[j][j] itself is never overwritten
-    const T inv = T(1) / piv;
-    if (tid == j) diag[j] = piv;
-    if (tid > j && tid < b) D[tid][j] *= inv;
-    __syncthreads();
-    // rank-1 update of the trailing lower triangle, 16 x 16 thread grid (no index divisions)
-    for (int i = j + 1 + (tid >> 4); i < b; i += CROWS / 16) {
-      const T dij = D[i][j];
-      for (int l = j + 1 + (tid & 15); l <= i; l += 16) D[i][l] -= dij * D[l][j];
+#pragma unroll
+  for (int j = 0; j < CB; ++j) {
+    const T djj = __shfl_sync(0xffffffffu, j < 32 ? r0[j] : r1[j], j & 31);
+    const T inv = rsqrt_any(vmax(djj, floor_piv));
+    // column j of L in rows lane, lane + 32; zero above the diagonal, so that nothing grows in the unused half
+    const T c0 = (j < 32 && lane >= j) ? r0[j] * inv : T(0);
+    const T c1 = (lane + 32 >= j) ? r1[j] * inv : T(0);
+    if (lane == 0) dinv[j] = inv;
+    if (j < 32) {
+      r0[j] = (lane == j) ? djj * inv : c0;
+      r1[j] = c1;
+    } else {
+      r1[j] = (lane == j - 32) ? djj * inv : c1;
+    }
+#pragma unroll
+    for (int l = j + 1; l < CB; ++l) {  // A[i][l] -= L[i][j] L[l][j]  (entries right of the diagonal: unused garbage)
+      const T colv = __shfl_sync(0xffffffffu, l < 32 ? c0 : c1, l & 31);
+      if (l < 32) r0[l] -= c0 * colv;
+      r1[l] -= c1 * colv;
     }
   }
-  __syncthreads();
-  if (blockIdx.x == 0) {
-    for (int idx = tid; idx < b * b; idx += CROWS) {
-      const int i = idx / b, j = idx % b;
-      if (j <= i) A[(int64_t(k) + i) * R + k + j] = (i == j) ? diag[i] : D[i][j];
-    }
-  }
-  if (tid < nrows) {  // x L11^T = a
-    for (int c = 0; c < b; ++c) {
-      T s = X[tid][c];
-      for (int m = 0; m < c; ++m) s -= X[tid][m] * D[c][m];
-      X[tid][c] = s / diag[c];
-    }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < nrows * b; idx += CROWS) {
-    const int r = idx / b, c = idx % b;
-    A[(row0 + r) * R + k + c] = X[r][c];
+#pragma unroll
+  for (int c4 = 0; c4 < CB; c4 += 4) {
+    const T a[4] = {r0[c4], r0[c4 + 1], r0[c4 + 2], r0[c4 + 3]};
+    const T b4[4] = {r1[c4], r1[c4 + 1], r1[c4 + 2], r1[c4 + 3]};
+    st4(&D[lane][c4], a);
+    st4(&D[lane + 32][c4], b4);
   }
 }
 
 template <typename T>
+__global__ void __launch_bounds__(CROWS) chol_panel_kernel(T* A, int64_t R, int k, int b, const JacobiScalars* sc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T(*D)[LDD] = reinterpret_cast<T(*)[LDD]>(smem_raw);
+  T* dinv = reinterpret_cast<T*>(smem_raw) + CB * LDD;  // 1 / L_jj
+  T(*X)[CB + 1] = reinterpret_cast<T(*)[CB + 1]>(dinv + CB);
+  const int tid = threadIdx.x;
+  const T floor_piv = chol_shift<T>(sc);
+  const bool dbg = k == 0;
+  if (dbg) VVT_DSTAMP(9);
+#pragma unroll
+  for (int it = 0; it < CB * CB / CROWS; ++it) {  // zero-padded to CB x CB; all loads in flight together
+    const int idx = tid + it * CROWS, i = idx / CB, j = idx % CB;
+    D[i][j] = (j <= i && i < b) ? A[(int64_t(k) + i) * R + k + j] : T(0);
+  }
+  // this CTA's rows of the panel
+  const int64_t row0 = int64_t(k) + b + int64_t(blockIdx.x) * CROWS;
+  const int nrows = int(vmax<int64_t>(0, vmin<int64_t>(CROWS, R - row0)));
+#pragma unroll 8
+  for (int idx = tid; idx < nrows * CB; idx += CROWS) {
+    const int r = idx / CB, c = idx % CB;
+    X[r][c] = c < b ? A[(row0 + r) * R + k + c] : T(0);
+  }
+  __syncthreads();
+  if (dbg) VVT_DSTAMP(10);
+  if (tid < 32) chol_diag_warp<T>(D, dinv, floor_piv, tid);
+  __syncthreads();
+  if (dbg) VVT_DSTAMP(11);
+  if (blockIdx.x == 0) {
+#pragma unroll 4
+    for (int idx = tid; idx < CB * CB; idx += CROWS) {
+      const int i = idx / CB, j = idx % CB;
+      if (j <= i && i < b) A[(int64_t(k) + i) * R + k + j] = D[i][j];
+    }
+  }
+  if (dbg) VVT_DSTAMP(12);
+  if (tid < nrows) {  // x L11^T = a: the row lives in registers, rows of L11 are broadcast 16-byte reads
+    T x[CB];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) x[c] = X[tid][c];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      T s0 = x[c], s1 = T(0), s2 = T(0), s3 = T(0);  // four chains instead of one
+#pragma unroll
+      for (int m4 = 0; m4 < c; m4 += 4) {
+        T d[4];
+        ld4(&D[c][m4], d);
+        if (m4 + 0 < c) s0 -= x[m4 + 0] * d[0];
+        if (m4 + 1 < c) s1 -= x[m4 + 1] * d[1];
+        if (m4 + 2 < c) s2 -= x[m4 + 2] * d[2];
+        if (m4 + 3 < c) s3 -= x[m4 + 3] * d[3];
+      }
+      x[c] = ((s0 + s1) + (s2 + s3)) * dinv[c];  // columns >= b: x = 0 and a finite dinv (zero-padded block)
+    }
+#pragma unroll
+    for (int c = 0; c < CB; ++c) X[tid][c] = x[c];
+  }
+  __syncthreads();
+  if (dbg) VVT_DSTAMP(13);
+#pragma unroll 8
+  for (int idx = tid; idx < nrows * CB; idx += CROWS) {
+    const int r = idx / CB, c = idx % CB;
+    if (c < b) A[(row0 + r) * R + k + c] = X[r][c];
+  }
+  if (dbg) VVT_DSTAMP(14);
+}
+
+template <typename T>
 static size_t chol_smem_bytes() {
-  return (size_t(CB) * (CB + 1) + CB + size_t(CROWS) * (CB + 1)) * sizeof(T);
+  return (size_t(CB) * LDD + CB + size_t(CROWS) * (CB + 1)) * sizeof(T);
 }
 
 // A = Gs + eps I (the factorisation works in place on this copy)
@@ -1317,6 +1381,8 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
       fprintf(stderr, " | gram: loop %lld stage %lld bar %lld sum %lld | apply: qfrag %lld (from t5 %lld)", d[1] - d[0],
               d[2] - d[1], d[3] - d[2], d[4] - d[3], d[6] - d[5], d[5] - h.t[5]);
       fprintf(stderr, " | reduce: barrier %lld sum %lld", d[7] - h.t[2], d[8] - d[7]);
+      fprintf(stderr, " | chol panel (first): load %lld factor %lld store %lld solve %lld store %lld", d[10] - d[9],
+              d[11] - d[10], d[12] - d[11], d[13] - d[12], d[14] - d[13]);
       fprintf(stderr, "\n");
     }
     // a sweep that rotated (almost) nothing ends the iteration: the last few block pairs only carry
