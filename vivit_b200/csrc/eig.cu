@@ -1387,7 +1387,8 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
     }
     // a sweep that rotated (almost) nothing ends the iteration: the last few block pairs only carry
     // cosines barely above the threshold, which the refinement step below removes anyway
-    if (rot <= (unsigned long long)(pairs * nb) / 256) {
+    static const int stop_div = getenv("VVT_SYEVJ_STOPDIV") ? vmax(1, atoi(getenv("VVT_SYEVJ_STOPDIV"))) : 256;
+    if (rot <= (unsigned long long)(pairs * nb) / stop_div) {
       converged = 1;
       break;
     }

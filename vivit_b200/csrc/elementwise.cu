@@ -125,10 +125,58 @@ maxpool_bwd_kernel(T* out, const T* S, const int64_t* argmax, int64_t planes, in
   }
 }
 
+// Fast path: the argmax map is shared by the V rows of a sample (S is [V, N, ch, ho, wo]), so one block
+// takes one (n, c) plane, resolves for every input position which of its (at most 2 x 2) candidate windows
+// chose it ONCE, and then streams the V output planes: per element one coalesced store and up to four
+// predicated loads from a map that sits in L1.  Windows with ceil(k / stride) <= 2 and no dilation.
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_shared_kernel(T* out, const T* S, const int64_t* argmax, int64_t V, int64_t N, int64_t ch, int ho, int wo,
+                          int hi, int wi, int kh, int kw, int sh, int sw, int ph, int pw) {
+  const int hw_in = hi * wi, hw_out = ho * wo;
+  const int64_t planes = N * ch;
+  for (int64_t pl = blockIdx.x; pl < planes; pl += gridDim.x) {
+    const int64_t* am = argmax + pl * hw_out;
+    for (int pos = threadIdx.x; pos < hw_in; pos += blockDim.x) {
+      const int y = pos / wi, x = pos - y * wi;
+      const int ay = y + ph, ax = x + pw;
+      const int oy_hi = min(ho - 1, ay / sh), ox_hi = min(wo - 1, ax / sw);
+      const int by = ay - (kh - 1), bx = ax - (kw - 1);
+      const int oy_lo = by > 0 ? (by + sh - 1) / sh : 0, ox_lo = bx > 0 ? (bx + sw - 1) / sw : 0;
+      int off[4];
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int oy = oy_lo + dy, ox = ox_lo + dx;
+          const bool hit = oy <= oy_hi && ox <= ox_hi && int(am[oy * wo + ox]) == pos;
+          off[2 * dy + dx] = hit ? oy * wo + ox : -1;
+        }
+      const T* s = S + pl * hw_out;
+      T* o = out + pl * hw_in + pos;
+      for (int64_t v = 0; v < V; ++v, s += planes * hw_out, o += planes * hw_in) {
+        T acc = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (off[j] >= 0) acc += s[off[j]];
+        *o = acc;
+      }
+    }
+  }
+}
+
 template <typename T>
 static void launch_maxpool_bwd(T* out, const T* S, const int64_t* argmax, int64_t planes, int64_t N, int64_t ch, int ho,
                                int wo, int hi, int wi, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
                                cudaStream_t s) {
+  if (dh == 1 && dw == 1 && kh <= 2 * sh && kw <= 2 * sw && N * ch > 0) {
+    const int64_t V = planes / (N * ch);
+    const unsigned blocks = unsigned(vmin<int64_t>(N * ch, int64_t(16) * num_sms()));
+    const int threads = int(vmin<int64_t>(256, align_up(int64_t(hi) * wi, 32)));
+    maxpool_bwd_shared_kernel<T><<<blocks, threads, 0, s>>>(out, S, argmax, V, N, ch, ho, wo, hi, wi, kh, kw, sh, sw, ph,
+                                                           pw);
+    return;
+  }
   const int tx = int(vmin<int64_t>(256, align_up(int64_t(hi) * wi, 32))), ty = 256 / tx;
   const dim3 threads(tx, ty);
   const unsigned blocks = unsigned(vmin<int64_t>(ceil_div(planes, ty), int64_t(32) * num_sms()));
