@@ -51,7 +51,11 @@ typedef enum {
   VVT_ACT_SIGMOID = 1, /* ref = layer output: S * ref * (1 - ref)      */
   VVT_ACT_TANH = 2,    /* ref = layer output: S * (1 - ref^2)          */
   VVT_ACT_DROPOUT = 3, /* ref = layer output: S * (ref != 0) * scale   */
-  VVT_ACT_MUL = 4      /* ref = derivative  : S * ref                  */
+  VVT_ACT_MUL = 4,     /* ref = derivative  : S * ref                  */
+  VVT_ACT_LEAKY_RELU = 5, /* ref = layer input : S * (ref > 0 ? 1 : scale)          (scale = negative_slope) */
+  VVT_ACT_ELU = 6,        /* ref = layer input : S * (ref > 0 ? 1 : scale * exp(ref))        (scale = alpha) */
+  VVT_ACT_SELU = 7,       /* ref = layer input : S * lambda * (ref > 0 ? 1 : alpha * exp(ref))               */
+  VVT_ACT_LOGSIGMOID = 8  /* ref = layer input : S / (1 + exp(ref))                                          */
 } vvt_act;
 
 int vvt_abi_version(void);

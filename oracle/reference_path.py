@@ -222,6 +222,12 @@ def jac_t_mat_prod(
         return mat * (out * (1.0 - out))[None]
     if isinstance(module, nn.Tanh):
         return mat * (1.0 - out**2)[None]
+    if isinstance(module, (nn.LeakyReLU, nn.ELU, nn.SELU, nn.LogSigmoid)):
+        # [external] ElementwiseDerivatives: mat * f'(input); f' by autograd of the module itself
+        x = inp.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            (d,) = torch.autograd.grad(module(x).sum(), x)
+        return mat * d[None]
     if isinstance(module, (nn.Flatten,)):
         return mat.reshape(v, n, *inp.shape[1:])
     if isinstance(module, nn.Identity):
@@ -416,12 +422,15 @@ def backward_sweep(
         h = xg
         for m in leaf_modules(model):
             o = m(h)
-            o.retain_grad()
+            if o.requires_grad:  # false up to the first layer with parameters
+                o.retain_grad()
             acts.append((m, h, o))
             h = o
         loss = loss_fn(h, y)
         loss.backward()
-        records = [(m, i.detach(), o.detach(), o.grad.detach()) for m, i, o in acts]
+        records = [
+            (m, i.detach(), o.detach(), None if o.grad is None else o.grad.detach()) for m, i, o in acts
+        ]
         out = h.detach()
         for p in model.parameters():
             p.grad = None

@@ -18,7 +18,8 @@ import torch
 import torch.nn.functional as F
 from torch import einsum
 
-ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_DROPOUT, ACT_MUL = range(5)
+(ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_DROPOUT, ACT_MUL, ACT_LEAKY_RELU, ACT_ELU, ACT_SELU,
+ ACT_LOGSIGMOID) = range(9)
 
 NAMES = [
     "loss_sqrt_hessian_ce", "loss_sqrt_hessian_ce_mc", "loss_sqrt_hessian_mse", "scale_",
@@ -99,6 +100,15 @@ def sqrt_backprop_elementwise(S, ref, act, scale=1.0):
         d = 1 - ref**2
     elif act == ACT_DROPOUT:
         d = (ref != 0).to(S.dtype) * scale
+    elif act == ACT_LEAKY_RELU:
+        d = torch.where(ref > 0, torch.ones_like(ref), torch.full_like(ref, scale))
+    elif act == ACT_ELU:
+        d = torch.where(ref > 0, torch.ones_like(ref), scale * ref.exp())
+    elif act == ACT_SELU:
+        d = 1.0507009873554804934193349852946 * torch.where(
+            ref > 0, torch.ones_like(ref), 1.6732632423543772848170429916717 * ref.exp())
+    elif act == ACT_LOGSIGMOID:
+        d = 1.0 / (1.0 + ref.exp())
     else:
         d = ref
     return (S.reshape(-1, ref.numel()) * d.reshape(1, -1)).reshape(S.shape)

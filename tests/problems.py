@@ -110,6 +110,26 @@ PROBLEMS: List[Problem] = [
         lambda: nn.CrossEntropyLoss(reduction="mean"),
         _cls(5, 6),
     ),
+    # the remaining element-wise / padding modules of the reference's module map
+    # (vivit/extensions/secondorder/vivit/__init__.py:95-117): ZeroPad2d, LeakyReLU, ELU, SELU, LogSigmoid
+    Problem(
+        "pad-acts",
+        lambda: torch.rand(4, 2, 5, 5) - 0.3,
+        lambda: nn.Sequential(
+            nn.ZeroPad2d((1, 0, 2, 1)),
+            nn.Conv2d(2, 3, kernel_size=3),
+            nn.LeakyReLU(0.1),
+            nn.Conv2d(3, 3, kernel_size=2),
+            nn.ELU(alpha=0.7),
+            nn.Flatten(),
+            nn.Linear(45, 6),
+            nn.SELU(),
+            nn.Linear(6, 4),
+            nn.LogSigmoid(),
+        ),
+        lambda: nn.CrossEntropyLoss(reduction="mean"),
+        _cls(4, 4),
+    ),
 ]
 
 # test/settings.py:36-41 -- only used at the extension level (the Computations

@@ -144,7 +144,7 @@ def test_conv2d_without_workspace_uses_the_generic_kernel(k):
 def test_elementwise_and_pools(k, dtype):
     S = rnd(3, 4, 5, 7, 7, dtype=dtype)
     r = rnd(4, 5, 7, 7, dtype=dtype, seed=3)
-    for act in range(5):
+    for act in range(9):
         close(k.sqrt_backprop_elementwise(S, r, act, 2.0), ref.sqrt_backprop_elementwise(S.double(), r.double(), act, 2.0), dtype, f"act{act}")
     x = rnd(4, 5, 9, 9, dtype=dtype, seed=4)
     for kern, st, pd, ceil, dil in [(3, 2, 0, False, 1), (3, 2, 0, True, 1), (2, 2, 0, False, 1), (3, 1, 1, False, 1),

@@ -305,3 +305,29 @@ def test_config2_full_size_properties():
     grads = torch.autograd.grad(loss, list(model.parameters()))
     gflat = torch.cat([g.flatten() for g in grads]).double()
     assert torch.allclose((flat @ gflat).abs(), gam.double().mean(0).abs(), rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("problem", PROBLEMS, ids=IDS)
+def test_savefield_closures_and_materialised_extensions(problem, dtype):
+    """the lower-level functional API of ``ViViTGGNExact`` (``gram_mat`` / ``V_mat_prod`` /
+    ``V_t_mat_prod`` closures per parameter, ``base.py:96-130``, ``linear.py:44-81``) and the
+    [BackPACK]-shaped ``sqrt_ggn_exact`` / ``grad_batch`` tensors, computed by the CUDA kernels."""
+    from vivit_b200 import BatchGrad, SqrtGGNExact, ViViTGGNExact
+
+    (gm, gl, gx, gy), (cm, cl_, cx, cy) = make_pair(problem, dtype)
+    sub = [0, 0, 1] if cx.shape[0] >= 2 else None
+    run_backward(gm, gl, gx, gy, [ViViTGGNExact(subsampling=sub), SqrtGGNExact(subsampling=sub), BatchGrad()], None)
+    sweep = ref.backward_sweep(cm, cl_, cx, cy, subsampling_ggn=sub, want_vivit=True, want_sqrt_ggn=True,
+                               want_grad_batch=True)
+    torch.manual_seed(3)
+    for pg, pc in zip(gm.parameters(), cm.parameters()):
+        close(pg.sqrt_ggn_exact, sweep.sqrt_ggn[id(pc)], dtype, "sqrt_ggn_exact")
+        close(pg.grad_batch, sweep.grad_batch[id(pc)], dtype, "grad_batch")
+        got, want = pg.vivit_ggn_exact, sweep.vivit[id(pc)]
+        close(got["gram_mat"](), want["gram_mat"](), dtype, "gram_mat")
+        C, N = sweep.sqrt_ggn[id(pc)].shape[:2]
+        mat = torch.rand(3, C, N, dtype=dtype)
+        close(got["V_mat_prod"](mat.to(DEV)), want["V_mat_prod"](mat), dtype, "V_mat_prod")
+        pm = torch.rand(4, *pc.shape, dtype=dtype)
+        close(got["V_t_mat_prod"](pm.to(DEV)), want["V_t_mat_prod"](pm), dtype, "V_t_mat_prod")

@@ -222,14 +222,22 @@ def _factor_conv2d(ext: _SqrtFactorExtension, module: nn.Conv2d, S: Tensor, need
     return kernels.sqrt_backprop_conv2d(S, module.weight.detach(), tuple(x.shape[2:]), *geom)
 
 
-def _factor_act(act, use_output):
+def _factor_act(act, use_output, scale_of=None):
     def handler(ext, module, S, need_in):
         if not need_in:
             return None
         ref = module.output if use_output else module.input0
-        return kernels.sqrt_backprop_elementwise(S, ext._subsample(ref.detach()), act)
+        scale = 1.0 if scale_of is None else float(scale_of(module))
+        return kernels.sqrt_backprop_elementwise(S, ext._subsample(ref.detach()), act, scale)
 
     return handler
+
+
+def _factor_zeropad2d(ext, module: nn.ZeroPad2d, S, need_in):
+    """Crop: the Jacobian of zero padding drops the padded border ([BackPACK] ``ZeroPad2dDerivatives``)."""
+    left, right, top, bottom = module.padding
+    h, w = S.shape[-2:]
+    return S[..., top : h - bottom, left : w - right].contiguous()
 
 
 def _factor_dropout(ext, module: nn.Dropout, S, need_in):
@@ -276,6 +284,11 @@ _FACTOR_HANDLERS = {
     nn.ReLU: _factor_act(kernels.ACT_RELU, use_output=False),
     nn.Sigmoid: _factor_act(kernels.ACT_SIGMOID, use_output=True),
     nn.Tanh: _factor_act(kernels.ACT_TANH, use_output=True),
+    nn.LeakyReLU: _factor_act(kernels.ACT_LEAKY_RELU, use_output=False, scale_of=lambda m: m.negative_slope),
+    nn.ELU: _factor_act(kernels.ACT_ELU, use_output=False, scale_of=lambda m: m.alpha),
+    nn.SELU: _factor_act(kernels.ACT_SELU, use_output=False),
+    nn.LogSigmoid: _factor_act(kernels.ACT_LOGSIGMOID, use_output=False),
+    nn.ZeroPad2d: _factor_zeropad2d,
     nn.Dropout: _factor_dropout,
     nn.Flatten: _factor_flatten,
     nn.Identity: _factor_identity,

@@ -83,6 +83,12 @@ __global__ void act_kernel(T* out, const T* S, const T* ref, int64_t V, int64_t 
       case VVT_ACT_SIGMOID: d = r * (T(1) - r); break;
       case VVT_ACT_TANH: d = T(1) - r * r; break;
       case VVT_ACT_DROPOUT: d = r != T(0) ? scale : T(0); break;
+      case VVT_ACT_LEAKY_RELU: d = r > T(0) ? T(1) : scale; break;
+      case VVT_ACT_ELU: d = r > T(0) ? T(1) : scale * exp(r); break;
+      case VVT_ACT_SELU:
+        d = T(1.0507009873554804934193349852946) * (r > T(0) ? T(1) : T(1.6732632423543772848170429916717) * exp(r));
+        break;
+      case VVT_ACT_LOGSIGMOID: d = T(1) / (T(1) + exp(r)); break;
       default: d = r;
     }
     out[i] = S[i] * d;
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(256)
 backtransform_dense_kernel(T* E, double* norm2, const T* U, const T* V, int64_t K, int64_t R, int64_t D,
                            int64_t k0) {
   constexpr int RC = 64, RB = 8, NW = 8;  // rows per U chunk, rows in flight per thread, warps
-  __shared__ T Us[2][RC][KT];
+  __shared__ __align__(16) T Us[2][RC][KT];
   __shared__ __align__(16) T red[NW][32][VW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t d0 = (blockIdx.x * int64_t(32) + lane) * VW;
@@ -306,12 +312,24 @@ backtransform_dense_kernel(T* E, double* norm2, const T* U, const T* V, int64_t 
         }
       }
 #pragma unroll
-      for (int i = 0; i < RB; ++i) {
+      for (int i = 0; i < RB; ++i) {  // rows past rn are staged as zero
+        if constexpr (KT % 4 == 0 && sizeof(T) == 4) {  // 16-byte broadcast reads of the U row
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          const T u = Us[buf][rb + i][k];  // rows past rn are staged as zero
+          for (int k4 = 0; k4 < KT; k4 += 4) {
+            const float4 u4 = *reinterpret_cast<const float4*>(&Us[buf][rb + i][k4]);
+            const T u[4] = {T(u4.x), T(u4.y), T(u4.z), T(u4.w)};
 #pragma unroll
-          for (int v = 0; v < VW; ++v) acc[k][v] += u * x[i][v];
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+              for (int v = 0; v < VW; ++v) acc[k4 + e][v] += u[e] * x[i][v];
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            const T u = Us[buf][rb + i][k];
+#pragma unroll
+            for (int v = 0; v < VW; ++v) acc[k][v] += u * x[i][v];
+          }
         }
       }
     }
@@ -445,7 +463,7 @@ int vvt_scale(void* t, int64_t numel, double alpha, int dtype, void* stream) {
 int vvt_sqrt_backprop_elementwise(void* out, const void* S, const void* ref, int64_t V,
                                   int64_t n_feat, int act, double scale, int dtype, void* stream) {
   VVT_REQUIRE(V >= 0 && n_feat >= 0, "negative size");
-  VVT_REQUIRE(act >= 0 && act <= VVT_ACT_MUL, "unknown activation");
+  VVT_REQUIRE(act >= 0 && act <= VVT_ACT_LOGSIGMOID, "unknown activation");
   if (V * n_feat == 0) return VVT_OK;
   VVT_REQUIRE(out && S && ref, "null pointer");
   VVT_DISPATCH(dtype, {
@@ -524,12 +542,16 @@ int vvt_backtransform_dense(void* E, void* norm2, const void* U, const void* V, 
     constexpr int VW = 16 / int(sizeof(T));  // one 16-byte load per row and thread
     const unsigned blocks = unsigned(ceil_div(D, 32 * VW));
     int64_t k0 = 0;
-    while (k0 < K) {  // 16 directions per pass over V while that many remain, then 8 / 4 / 2 / 1
+    while (k0 < K) {  // 16 directions per pass over V while that many remain, then 12 / 8 / 4 / 1
       const int64_t left = K - k0;
-      if (left > 8) {
+      if (left > 12) {
         backtransform_dense_kernel<T, 16, VW><<<blocks, 256, 0, as_stream(stream)>>>(
             (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);
         k0 += 16;
+      } else if (left > 8) {
+        backtransform_dense_kernel<T, 12, VW><<<blocks, 256, 0, as_stream(stream)>>>(
+            (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);
+        k0 += 12;
       } else if (left > 4) {
         backtransform_dense_kernel<T, 8, VW><<<blocks, 256, 0, as_stream(stream)>>>(
             (T*)E, (double*)norm2, (const T*)U, (const T*)V, K, R, D, k0);

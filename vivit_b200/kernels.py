@@ -21,7 +21,8 @@ from torch import Tensor
 
 from vivit_b200 import _lib
 
-ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_DROPOUT, ACT_MUL = range(5)
+(ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_DROPOUT, ACT_MUL, ACT_LEAKY_RELU, ACT_ELU, ACT_SELU,
+ ACT_LOGSIGMOID) = range(9)
 
 _DTYPES = {torch.float32: 0, torch.float64: 1}
 
