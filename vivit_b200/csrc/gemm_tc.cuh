@@ -260,8 +260,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           float o[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
+            // exact residual; + half a tf32 ulp on its bit pattern: the tensor core's truncation of the low
+            // 13 bits then rounds to nearest (see split_tf32 in gemm_core.cuh) -- 3 ALU ops per element
             const float hi = __uint_as_float(__float_as_uint(e[j]) & 0xFFFFE000u);
-            o[j] = __uint_as_float(to_tf32(e[j] - hi));
+            o[j] = __uint_as_float(__float_as_uint(e[j] - hi) + 0x1000u);
           }
           lo = make_float4(o[0], o[1], o[2], o[3]);
         }
