@@ -633,6 +633,10 @@ def main():
         "e2e": {"value": round(ms_e2e, 4), "unit": "ms", "h2d_bytes_per_step": stepper.h2d_bytes,
                 "d2h_bytes_per_step": stepper.d2h_bytes},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "eigensolver": eig, "cpu_baseline": cpu,
+        # the part of the step that shards over the ranks (factor emit + Gram / cross-term assembly, rank 0) next
+        # to the part that every rank repeats (the eigensolver): SURVEY 8e
+        "gram_assembly_ms_per_step": round(sum(r["ms_per_step"] for r in rows if r["kernel"].startswith(("gram_", "v_emit_"))), 4),
+        "eigensolver_ms_per_step": round(sum(r["ms_per_step"] for r in rows if r["kernel"] == "syevj"), 4),
         "kernels": rows,
     }
     print(json.dumps(line))

@@ -84,14 +84,21 @@ def main():
                f"--warmup 3 --ncu-step` (one step between cudaProfilerStart/Stop) → `{ROUND}_launches_c2.csv`", "", launch_table(lp), ""]
     md += ["## ncu --set full captures", "",
            "`profiles/ncu_summary.py <report>` condenses a `.ncu-rep` (raw page + SASS page) into the text files below;",
-           "the reports themselves stay in `gpurun_out/` (scratch).", "",
+           "the reports themselves stay in `gpurun_out/` (scratch). Captured with `ncu --set full --clock-control none",
+           "--import-source on -k regex:<kernel> -s <skip> -c 1..2` on one GPU.", "",
            f"* `{ROUND}_ncu_gram_tc.txt` — `gram_tc_kernel` (tcgen05 `UTCHMMA` + TMA `UTMALDG`), dense Gram R=1280, "
-           "D=110592: 1.30 ms, tensor pipe active 43.5% of elapsed cycles, DRAM read 666 MB + write 39 MB against "
-           "566 MB + 6.5 MB algorithmic (`profiles/ncu_traffic.json` feeds `roofline.traffic`).",
-           f"* `{ROUND}_ncu_jacobi.txt` — `onesided_round_resident_kernel<float>`: one Jacobi round at R=1280, "
-           "80 CTAs in clusters of 2.",
-           f"* `{ROUND}_ncu_dgrad2.txt` — the conv data-gradient GEMM (`gram_tc_kernel<DgradStoreTc>`, M=184320, "
-           "N=576, K=96): output-write bound.", ""]
+           "D=110592 (`profiles/run_gram.py`): 1.30 ms in the capture (1.20 ms after the cheaper `lo` split), tensor pipe "
+           "active 43.9% of elapsed cycles, DRAM read 666 MB + write 42 MB against 566 MB + 6.5 MB algorithmic "
+           "(`profiles/ncu_traffic.json` feeds `roofline.traffic`).",
+           f"* `{ROUND}_ncu_jacobi.txt` — `onesided_round_resident_kernel<float>`: one cross round of the eigensolver at "
+           "R=1280 (120 CTAs in clusters of 3, one per SM): 15.2-15.6 us cold under ncu, 9.7 us back to back.",
+           f"* `{ROUND}_ncu_backtransform.txt` — `backtransform_dense_kernel<float,12,4>` R=1280, D=110592, K=10: 201 us, "
+           "DRAM read 566 MB = the factor once (566 MB algorithmic).",
+           f"* `{ROUND}_ncu_chol_panel.txt` — the Cholesky panel kernel (one warp factors the 64x64 diagonal block in "
+           "registers): 60 us cold, `stall_no_inst` 44% (the fully unrolled factor / solve code streams through the "
+           "instruction cache once).",
+           f"* `{ROUND}_ncu_dgrad2.txt` — (earlier capture) the conv data-gradient GEMM (`gram_tc_kernel<DgradStoreTc>`, "
+           "M=184320, N=576, K=96): output-write bound.", ""]
     open(os.path.join(OUT, "README.md"), "w").write("\n".join(md))
     print("wrote profiles/README.md")
 
