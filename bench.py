@@ -621,7 +621,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         use_all_host_threads()
-        cms, n = time_reference(w, dtype, 1, 0, args.cpu_budget_s)
+        cms, n = time_reference(w, dtype, 3, 1, args.cpu_budget_s)  # median of <= 3 steps after one warm-up, budget-bounded
         cpu = {"value": round(cms, 3), "unit": "ms", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{n} full step(s) of the workload (oracle/reference_path.py, torch CPU)"}
 
