@@ -151,6 +151,8 @@ struct EmitStoreTc {
     return ((v * N + (batch0 + n)) * c_out + o) * J;
   }
   __device__ __forceinline__ void store(int64_t off, int64_t, int64_t j, float val, int) const { Vt[off + j] = val; }
+  __device__ __forceinline__ float fetch(int64_t, int64_t, int64_t) const { return 0.f; }
+  __device__ __forceinline__ void commit(int64_t off, int64_t, int64_t j, float val, float, int) const { Vt[off + j] = val; }
   __device__ __forceinline__ void operator()(int n, int64_t m, int64_t j, float val, int) const {
     Vt[row_offset(n, m) + j] = val;
   }
@@ -191,6 +193,8 @@ struct DgradStoreTc {
     return r * J * X + x;
   }
   __device__ __forceinline__ void store(int64_t off, int64_t, int64_t j, float val, int) const { T2[off + j * X] = val; }
+  __device__ __forceinline__ float fetch(int64_t, int64_t, int64_t) const { return 0.f; }
+  __device__ __forceinline__ void commit(int64_t off, int64_t, int64_t j, float val, float, int) const { T2[off + j * X] = val; }
   __device__ __forceinline__ void operator()(int b, int64_t m, int64_t j, float val, int) const {
     T2[row_offset(b, m) + j * X] = val;
   }

@@ -306,8 +306,21 @@ struct StdStore {
   __device__ __forceinline__ T weight(int64_t r, int64_t c) const {
     return P ? ldg(P + (r % pr) * ldp + (c % pc)) + padd : T(1);
   }
-  // two-step form used by the tcgen05 epilogue (nothing to precompute here)
+  // forms used by the tcgen05 epilogue: row_offset (nothing to precompute here), and the accumulate split
+  // into fetch (the old value of C, if beta needs it) and commit, so that a batch of independent loads can be
+  // in flight before the first store (one dependent global load per element made small-K products -- the
+  // Cholesky trailing updates -- latency bound: 75 us per launch)
   __device__ __forceinline__ int64_t row_offset(int, int64_t r) const { return r; }
+  __device__ __forceinline__ T fetch(int64_t, int64_t r, int64_t c) const {
+    return (partial || beta == T(0)) ? T(0) : C[r * ldc + c];
+  }
+  __device__ __forceinline__ void commit(int64_t, int64_t r, int64_t c, T v, T old, int split) const {
+    if (partial) {
+      partial[int64_t(split) * slab + r * N + c] = v;
+      return;
+    }
+    C[r * ldc + c] = beta * old + alpha * v * weight(r, c);  // old = 0 when beta = 0
+  }
   __device__ __forceinline__ void store(int64_t, int64_t r, int64_t c, T v, int split) const {
     (*this)(0, r, c, v, split);
   }

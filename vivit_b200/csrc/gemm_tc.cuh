@@ -292,18 +292,34 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int64_t row0 = int64_t(tm) * BM, col0 = int64_t(tn) * BN;
       if constexpr (COL_LANES) {
         // lanes = consecutive columns (row-major outputs): this warp stores rows cw, cw + 4, ...;
-        // lane l prepares the offset of row cw + 4 l, the others fetch it by shuffle
+        // lane l prepares the offset of row cw + 4 l, the others fetch it by shuffle.  Rows go in batches of
+        // 4: the 16 old values an accumulating store needs are fetched before the first store.
         const int64_t my_row = row0 + cw + 4 * lane;
         const int64_t my_off = my_row < M ? st.row_offset(batch, my_row) : 0;
-        for (int i = 0; i < BM / 4; ++i) {
-          const int r = cw + 4 * i;
-          const int64_t row = row0 + r;
-          const int64_t off = __shfl_sync(0xffffffffu, my_off, i);
-          if (row >= M) break;  // warp-uniform
+        for (int i0 = 0; i0 < BM / 4; i0 += 4) {
+          if (row0 + cw + 4 * i0 >= M) break;  // warp-uniform
+          int64_t off[4];
+          float old[4][BN / 32];
 #pragma unroll
-          for (int c = lane; c < BN; c += 32) {
-            const int64_t col = col0 + c;
-            if (col < N) st.store(off, row, col, tile[r * (BN + 1) + c], split);
+          for (int u = 0; u < 4; ++u) {
+            off[u] = __shfl_sync(0xffffffffu, my_off, i0 + u);
+            const int64_t row = row0 + cw + 4 * (i0 + u);
+#pragma unroll
+            for (int q = 0; q < BN / 32; ++q) {
+              const int64_t col = col0 + lane + 32 * q;
+              old[u][q] = (row < M && col < N) ? st.fetch(off[u], row, col) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = cw + 4 * (i0 + u);
+            const int64_t row = row0 + r;
+#pragma unroll
+            for (int q = 0; q < BN / 32; ++q) {
+              const int c = lane + 32 * q;
+              const int64_t col = col0 + c;
+              if (row < M && col < N) st.commit(off[u], row, col, tile[r * (BN + 1) + c], old[u][q], split);
+            }
           }
         }
       } else {
@@ -326,13 +342,28 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       }
       if (symmetric && !diag) {  // mirrored entries (col, row): lanes = consecutive rows -> coalesced
-        for (int j = cw; j < BN; j += 4) {
-          const int64_t col = col0 + j;
-          if (col >= N) break;
+        for (int j0 = cw; j0 < BN; j0 += 16) {  // columns j0, j0 + 4, j0 + 8, j0 + 12 per batch
+          if (col0 + j0 >= N) break;             // warp-uniform
+          float old[4][BM / 32];
 #pragma unroll
-          for (int c = 0; c < BM / 32; ++c) {
-            const int r = lane + 32 * c;
-            if (row0 + r < M) st(batch, col, row0 + r, tile[r * (BN + 1) + j], split);
+          for (int u = 0; u < 4; ++u) {
+            const int64_t col = col0 + j0 + 4 * u;
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c) {
+              const int64_t row = row0 + lane + 32 * c;
+              old[u][c] = (col < N && row < M) ? st.fetch(st.row_offset(batch, col), col, row) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 4 * u;
+            const int64_t col = col0 + j;
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c) {
+              const int r = lane + 32 * c;
+              if (col < N && row0 + r < M)
+                st.commit(st.row_offset(batch, col), col, row0 + r, tile[r * (BN + 1) + j], old[u][c], split);
+            }
           }
         }
       }
