@@ -697,11 +697,43 @@ __device__ __forceinline__ bool pair_is_clean(int* marks, int nb, int ba, int bb
   return c > max(marks[ba], marks[bb]);
 }
 
+// ---- dependencies between rounds: per column block, not per grid ---------------------------------------
+// A round launch only has to wait for the two clusters of the previous launch that wrote ITS two blocks.
+// done[blk] counts the CTAs that have finished with block blk (every launch touches every block exactly once,
+// every CTA signals on every exit path), so launch number L may read block blk once done[blk] >= CL * L.
+// With programmatic dependent launch the next grids are resident early and spin here instead of sitting in
+// griddepcontrol.wait until the whole previous grid has drained: a pair that only checks (tail sweeps) or a
+// cluster that finishes early no longer waits for the slowest cluster of the round.  Deadlock-free: a grid
+// starts only after every CTA of the previous one has started (and therefore holds its resources).
+__device__ __forceinline__ void wait_blocks(const unsigned* done, int ba, int bb, unsigned need, int tid) {
+  if (tid == 0) {
+    const volatile unsigned* d = done;
+    long long t0 = 0;
+    for (unsigned spins = 0; d[ba] < need || d[bb] < need; ++spins) {
+      if ((spins & 1023u) == 1023u) {  // bounded (~2 s): a protocol bug traps instead of hanging the GPU
+        const long long t = clock64();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 4000000000ll) __trap();
+      }
+    }
+    __threadfence();  // acquire: later reads of this CTA see what the signalling CTAs wrote
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void signal_blocks(unsigned* done, int ba, int bb, int tid) {
+  __syncthreads();  // every store of this CTA has been issued
+  if (tid == 0) {
+    __threadfence();  // release
+    atomicAdd(done + ba, 1u);
+    atomicAdd(done + bb, 1u);
+  }
+}
+
 // ---- resident variant: this CTA's rows of W and J are loaded once (cp.async) and stay in smem ----
 template <typename T>
 __global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
 onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc,
-                               int* marks, int now, T* Dc) {
+                               int* marks, int now, T* Dc, unsigned* done) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RotSmem<T>& rs = *reinterpret_cast<RotSmem<T>*>(smem_raw);
   T* P = reinterpret_cast<T*>(smem_raw + ((sizeof(RotSmem<T>) + 15) / 16) * 16);  // [parts * rows][LDP]: W rows(, J rows)
@@ -718,8 +750,12 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
   // programmatic dependent launch: let the next round's CTAs be scheduled while this round runs (they
   // block in griddepcontrol.wait until this grid has completed and its stores are visible)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (pair_is_clean(marks, nb, ba, bb, intra)) return;  // same decision in every CTA of the cluster
+  if (intra || !done) asm volatile("griddepcontrol.wait;" ::: "memory");  // first launch of a sweep: after memsets / init
+  if (done) wait_blocks(done, ba, bb, unsigned(CL) * unsigned(now - 1), tid);
+  if (pair_is_clean(marks, nb, ba, bb, intra)) {  // same decision in every CTA of the cluster
+    if (done) signal_blocks(done, ba, bb, tid);
+    return;
+  }
   VVT_STAMP(0);
   // DiagCache: Dc[blk][OB][OB] holds the diagonal block W_blk^T W_blk of every column block as the last
   // rotation round left it in H.  Cross rounds take both diagonal blocks from there and form only the
@@ -779,6 +815,7 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
       st4(dslot, v);
     }
     cp_async_wait<0>();
+    if (done) signal_blocks(done, ba, bb, tid);
     cluster_release(cluster);
     return;
   }
@@ -809,6 +846,7 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
         apply_rows<T>(rs, P + size_t(part) * nrows * LDP, LDP, r_base, nrows, Y, Np, ba, bb, part * Np + w0, tr, tc);
   }
   VVT_STAMP(6);
+  if (done) signal_blocks(done, ba, bb, tid);
   cluster_release(cluster);
 }
 
@@ -834,7 +872,7 @@ __device__ __forceinline__ void load_chunk(T (*dst)[LDP], const T* Y, int Np, in
 template <typename T>
 __global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
 onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc,
-                             int* marks, int now, T* Dc) {
+                             int* marks, int now, T* Dc, unsigned* done) {
   (void)Dc;  // the streaming variant recomputes the whole panel Gram in every round
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StreamSmem<T>& sm = *reinterpret_cast<StreamSmem<T>*>(smem_raw);
@@ -851,8 +889,12 @@ onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, 
   const T abs2 = Eps<T>::v * Eps<T>::v;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (pair_is_clean(marks, nb, ba, bb, intra)) return;
+  if (intra || !done) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (done) wait_blocks(done, ba, bb, unsigned(CL) * unsigned(now - 1), tid);
+  if (pair_is_clean(marks, nb, ba, bb, intra)) {
+    if (done) signal_blocks(done, ba, bb, tid);
+    return;
+  }
   {  // phase 1: partial Gram, chunks of W rows double-buffered
     const int ks = tid & 3, ti = tid >> 5, tj = (tid >> 2) & 7;
     T acc[4][4];
@@ -881,6 +923,7 @@ onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, 
   __syncthreads();
   if (!any_rotation_needed<T>(rs, intra, tol2, abs2, tid)) {
     if (crank == 0 && tid == 0) *clean_slot(marks, nb, ba, bb, intra) = now;
+    if (done) signal_blocks(done, ba, bb, tid);
     cluster_release(cluster);
     return;
   }
@@ -910,6 +953,7 @@ onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, 
       __syncthreads();
     }
   }
+  if (done) signal_blocks(done, ba, bb, tid);
   cluster_release(cluster);
 }
 
@@ -1210,7 +1254,7 @@ __global__ void jacobi_permute_kernel(T* evals, T* evecs, const T* ev, const T* 
 }
 
 struct JacobiLayout {
-  int64_t Np, nb, off_Y, off_Gs, off_Jm, off_Jt, off_Tt, off_S, off_M, off_Et, off_ev, off_cn, off_rank, off_sc, off_marks, off_dc, off_gemm, gemm_bytes, total;
+  int64_t Np, nb, off_Y, off_Gs, off_Jm, off_Jt, off_Tt, off_S, off_M, off_Et, off_ev, off_cn, off_rank, off_sc, off_marks, off_dc, off_done, off_gemm, gemm_bytes, total;
 };
 
 static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
@@ -1237,6 +1281,7 @@ static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
   L.off_sc = take(sizeof(JacobiScalars));
   L.off_marks = take((L.nb + L.nb * L.nb) * 4);
   L.off_dc = take(L.nb * OB * OB * es);
+  L.off_done = take(L.nb * 4);
   L.gemm_bytes = vvt_gram_workspace_bytes(R, R, R, dtype);
   L.off_gemm = take(L.gemm_bytes);
   L.total = o;
@@ -1251,12 +1296,13 @@ static size_t resident_smem_bytes(int rows_per_cta, int parts) {
 
 template <typename T>
 static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_cta, int parts, bool resident,
-                        JacobiScalars* sc, int* marks, int now, T* Dc, cudaStream_t s) {
+                        JacobiScalars* sc, int* marks, int now, T* Dc, unsigned* done, cudaStream_t s) {
   auto kern = resident ? onesided_round_resident_kernel<T> : onesided_round_stream_kernel<T>;
   size_t smem = resident ? resident_smem_bytes<T>(rows_per_cta, parts) : sizeof(StreamSmem<T>);
   // a round that fits on the GPU with one CTA per SM asks for more than half of an SM's shared memory, so
   // that no two CTAs share an SM (and its tensor pipe) while other SMs idle
-  if (int64_t(nb / 2) * CL <= num_sms()) smem = vmax<size_t>(smem, size_t(116) * 1024);
+  static const bool no_pad = getenv("VVT_SYEVJ_NOPAD") != nullptr;  // experiments
+  if (!no_pad && int64_t(nb / 2) * CL <= num_sms()) smem = vmax<size_t>(smem, size_t(116) * 1024);
   static size_t attr_done[2] = {0, 0};  // per instantiation: largest size configured so far
   if (attr_done[resident] < smem) {
     VVT_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
@@ -1278,7 +1324,7 @@ static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_ct
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
-  VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, parts, sc, marks, now, Dc), "vvt_syevj(round)"));
+  VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, parts, sc, marks, now, Dc, done), "vvt_syevj(round)"));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return VVT_OK;
 }
@@ -1316,6 +1362,7 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   // as a CTA keeps enough rows for the Gram / apply phases to outweigh the cluster reduction (R = 1280, fp32:
   // 3 CTAs x 427 rows on 120 SMs, 16.3 ms against 17.7 ms with 2 x 640 on 80 SMs)
   while (CL < 8 && int64_t(pairs) * (CL + 1) <= num_sms() && Np / (CL + 1) >= max_rows / 2) ++CL;
+  if (const char* e = getenv("VVT_SYEVJ_CL")) CL = vmax(1, vmin(8, atoi(e)));  // experiments
   while (CL > 1 && Np / CL < 16) CL /= 2;
   const int rows_per_cta = int(ceil_div(Np, CL));
   const bool resident = resident_smem_bytes<T>(rows_per_cta, parts) <= size_t(200) * 1024;
@@ -1323,6 +1370,7 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   VVT_TRY(check_cuda(cudaMemsetAsync(sc, 0, sizeof(JacobiScalars), s), "vvt_syevj"));
   int* marks = (int*)(ws + L.off_marks);
   VVT_TRY(check_cuda(cudaMemsetAsync(marks, 0, size_t(nb + nb * nb) * 4, s), "vvt_syevj"));
+  VVT_TRY(check_cuda(cudaMemsetAsync(ws + L.off_done, 0, size_t(nb) * 4, s), "vvt_syevj"));
   const bool debug = getenv("VVT_SYEVJ_DEBUG") != nullptr;
   const int init_blocks = int(vmin<int64_t>(ceil_div(L.Np * L.Np, 256), 8 * num_sms()));
   const int rr_blocks = int(vmin<int64_t>(ceil_div(R * R, 256), 8 * num_sms()));
@@ -1359,12 +1407,18 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
     VVT_TRY(launched("vvt_syevj(init)"));
   }
 
+  // per-block dependencies between rounds (wait_blocks) or the grid-wide dependency of griddepcontrol.wait
+  // (VVT_SYEVJ_GRIDDEP=1 forces the latter).  Spinning CTAs hold SM slots, so block dependencies pay while a
+  // round fits on the GPU a few times over (measured: R=2560 fp32 131 -> 115 ms, R=1280 fp64 110 -> 74 ms,
+  // R=1280 fp32 unchanged) and cost ~7% once a round is many waves (R=5120: 1280 CTAs).
+  static const bool block_deps_env = getenv("VVT_SYEVJ_GRIDDEP") == nullptr;
+  const bool block_deps = block_deps_env && int64_t(pairs) * CL <= 4 * int64_t(num_sms());
   int sweeps = 0, converged = 0;
   for (; sweeps < kMaxSweeps;) {
     VVT_TRY(check_cuda(cudaMemsetAsync(&sc->rotations, 0, sizeof(unsigned long long), s), "vvt_syevj"));
     for (int round = -1; round < nb - 1; ++round)
       VVT_TRY(launch_round<T>(Y, Np, nb, round, CL, rows_per_cta, parts, resident, sc, marks, sweeps * nb + round + 2,
-                              (T*)(ws + L.off_dc), s));
+                              (T*)(ws + L.off_dc), block_deps ? (unsigned*)(ws + L.off_done) : nullptr, s));
     ++sweeps;
     unsigned long long rot = 0;
     VVT_TRY(check_cuda(cudaMemcpyAsync(&rot, &sc->rotations, sizeof(rot), cudaMemcpyDeviceToHost, s),
