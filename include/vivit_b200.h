@@ -202,6 +202,12 @@ int vvt_gram_cross_linear_accum(void* X, const void* S, const void* Z, const voi
                                 int64_t n_in, int with_bias, void* workspace,
                                 int64_t workspace_bytes, int dtype, void* stream);
 
+/* out[n, d] = g[n, d] - (1/N) sum_m g[m, d]; g: [N, D] row-major, out may alias g.
+ * Centering of per-sample gradients: CenteredBatchGrad.param_hook
+ * (vivit/extensions/firstorder/batch_grad/gram_batch_grad.py:25-38) and the in-place
+ * `grad_batch -= grad_batch.mean(0)` of _GramBatchGradBase.param_hook (:88-89). */
+int vvt_center_rows(void* out, const void* g, int64_t N, int64_t D, int dtype, void* stream);
+
 /* T[i] *= alpha  (the N/len(subsampling) rescale at eigh.py:245-246, eigvalsh.py:218-219) */
 int vvt_scale(void* T, int64_t numel, double alpha, int dtype, void* stream);
 

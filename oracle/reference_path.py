@@ -625,3 +625,65 @@ def directional_damped_newton(
             [einsum("cn,cn...->...", v, sweep.sqrt_ggn[id(p)]) for p in group["params"]]
         )
     return out
+
+
+# --------------------------------------------------------------------------
+# f2: Gram hooks on materialised quantities (vivit/extensions/hooks.py)
+# --------------------------------------------------------------------------
+
+
+def centered_batch_grad(model: nn.Module, loss_fn: nn.Module, x: Tensor, y: Tensor) -> List[Tensor]:
+    """``CenteredBatchGrad.param_hook``
+    (``vivit/extensions/firstorder/batch_grad/gram_batch_grad.py:25-38``): per parameter (in
+    ``model.parameters()`` order) ``grad_batch - grad_batch.mean(0)``."""
+    sweep = backward_sweep(model, loss_fn, x, y, want_grad_batch=True)
+    out = []
+    for p in model.parameters():
+        if p.requires_grad:
+            gb = sweep.grad_batch[id(p)]
+            out.append(gb - gb.mean(0))
+    return out
+
+
+def gram_batch_grad(
+    model: nn.Module, loss_fn: nn.Module, x: Tensor, y: Tensor, center: bool = False
+) -> Tuple[Tensor, Dict[int, Tensor]]:
+    """``_GramBatchGradBase.param_hook`` / ``get_result`` (``gram_batch_grad.py:73-123``):
+    the ``[N, N]`` sum over parameters of ``pairwise_dot(grad_batch, start_dim=1)``, after
+    ``grad_batch -= grad_batch.mean(0)`` if ``center``; also the per-parameter (layer-wise)
+    matrices keyed by ``id(param)``, in the order the hook would visit the parameters."""
+    sweep = backward_sweep(model, loss_fn, x, y, want_grad_batch=True)
+    total, layers = None, {}
+    for p in sweep.order:
+        gb = sweep.grad_batch[id(p)]
+        if center:
+            gb = gb - gb.mean(0)
+        gram = reshape_as_square(pairwise_dot(gb, 1))
+        layers[id(p)] = gram
+        total = gram.clone() if total is None else total + gram
+    return total, layers
+
+
+def gram_sqrt_ggn(
+    model: nn.Module,
+    loss_fn: nn.Module,
+    x: Tensor,
+    y: Tensor,
+    mc_samples: int = 0,
+    mc_state: Optional[Tensor] = None,
+    subsampling: Optional[Sequence[int]] = None,
+) -> Tuple[Tensor, Dict[int, Tensor]]:
+    """``GramSqrtGGN.param_hook`` / ``get_result``
+    (``vivit/extensions/secondorder/sqrt_ggn/gram_sqrt_ggn.py:41-74``): the ``[CN, CN]`` sum over
+    parameters of ``pairwise_dot(sqrt_ggn, start_dim=2)`` flattened to a square, plus the
+    layer-wise matrices."""
+    sweep = backward_sweep(
+        model, loss_fn, x, y, subsampling_ggn=subsampling, mc_samples=mc_samples,
+        mc_state=mc_state, want_sqrt_ggn=True,
+    )
+    total, layers = None, {}
+    for p in sweep.order:
+        gram = reshape_as_square(pairwise_dot(sweep.sqrt_ggn[id(p)], 2))
+        layers[id(p)] = gram
+        total = gram.clone() if total is None else total + gram
+    return total, layers

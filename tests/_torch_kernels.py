@@ -28,7 +28,7 @@ NAMES = [
     "v_emit_linear", "gemm", "gram_dense_accum", "gram_cross_accum", "gram_linear_accum",
     "gram_cross_linear_accum", "syevj", "filter_nonzero", "backtransform_dense",
     "backtransform_linear", "vt_mat_prod_linear", "scale_rows_rsqrt", "dirderiv_epilogue",
-    "newton_coeff", "v_apply_dense", "v_apply_linear", "launch_count",
+    "newton_coeff", "v_apply_dense", "v_apply_linear", "launch_count", "center_rows",
 ]
 
 last_syevj_info = {"sweeps": 0, "converged": True}
@@ -76,6 +76,11 @@ def loss_sqrt_hessian_mse(n_sub, C, scale, like):
 
 def scale_(t, alpha):
     return t.mul_(alpha)
+
+
+def center_rows(g, inplace=False):
+    mean = g.mean(0)
+    return g.sub_(mean) if inplace else g - mean
 
 
 def sqrt_backprop_linear(S, W):

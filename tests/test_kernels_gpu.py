@@ -327,3 +327,25 @@ def test_launch_counter_moves(k):
     before = k.launch_count()
     k.scale_(torch.ones(3, device=dev()), 2.0)
     assert k.launch_count() == before + 1
+
+
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(3, 6, 7), (128, 4096), (5, 10), (1, 33), (33, 1), (9, 130), (257, 3, 3, 3)])
+def test_center_rows(k, dtype, shape):
+    """``vvt_center_rows``: vector path (row length a multiple of 16 bytes), scalar path, more rows than
+    warps, single row / single column, empty; out of place and in place."""
+    g = rnd(*shape, dtype=dtype) + 0.5
+    want = ref.center_rows(g.double())
+    keep = g.clone()
+    close(k.center_rows(g), want, dtype, "center_rows")
+    assert torch.equal(g, keep)  # out of place leaves the input alone
+    out = k.center_rows(g, inplace=True)
+    assert out.data_ptr() == g.data_ptr()
+    close(g, want, dtype, "center_rows (in place)")
+    assert k.center_rows(torch.zeros(2, 0, dtype=dtype, device=dev())).shape == (2, 0)
+    # an odd base address (a view starting one element in) must take the scalar path
+    if len(shape) == 2 and shape[1] >= 8:
+        flat = rnd(shape[0] * shape[1] + 1, dtype=dtype)
+        view = flat[1:].reshape(shape)
+        close(k.center_rows(view), ref.center_rows(view.double()), dtype, "center_rows (unaligned)")

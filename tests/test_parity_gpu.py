@@ -331,3 +331,58 @@ def test_savefield_closures_and_materialised_extensions(problem, dtype):
         close(got["V_mat_prod"](mat.to(DEV)), want["V_mat_prod"](mat), dtype, "V_mat_prod")
         pm = torch.rand(4, *pc.shape, dtype=dtype)
         close(got["V_t_mat_prod"](pm.to(DEV)), want["V_t_mat_prod"](pm), dtype, "V_t_mat_prod")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("lazy", [False, True], ids=["tensor", "factor"])
+@pytest.mark.parametrize("problem", PROBLEMS, ids=IDS)
+def test_gram_extension_hooks(problem, lazy, dtype):
+    """``GramBatchGrad`` / ``CenteredGramBatchGrad`` / ``CenteredBatchGrad`` /
+    ``GramSqrtGGNExact`` / ``GramSqrtGGNMC`` (``vivit/extensions/hooks.py``) on the CUDA kernels against
+    the oracle restatement, incl. the layer-wise matrices and the ``free_*`` keyword arguments."""
+    from vivit_b200 import BatchGrad, SqrtGGNExact, SqrtGGNMC
+    from vivit_b200.extensions.hooks import (
+        CenteredBatchGrad,
+        CenteredGramBatchGrad,
+        GramBatchGrad,
+        GramSqrtGGNExact,
+        GramSqrtGGNMC,
+    )
+
+    (gm, gl, gx, gy), (cm, cl_, cx, cy) = make_pair(problem, dtype)
+    table = {id(pg): id(pc) for pg, pc in zip(gm.parameters(), cm.parameters())}
+    for center, cls, field in ((False, GramBatchGrad, "gram_grad_batch"), (True, CenteredGramBatchGrad, "centered_gram_grad_batch")):
+        hook = cls(layerwise=True, free_grad_batch=center)
+        run_backward(gm, gl, gx, gy, [BatchGrad(lazy=lazy)], hook)
+        want, layers = ref.gram_batch_grad(cm, cl_, cx, cy, center=center)
+        scale = want.abs().max().item()
+        close(hook.get_result(), want, dtype, cls.__name__)
+        for pg in gm.parameters():
+            close(getattr(pg, field), layers[table[id(pg)]], dtype, cls.__name__ + " layerwise", floor=scale)
+            assert hasattr(pg, "grad_batch") != center
+    hook = CenteredBatchGrad()
+    run_backward(gm, gl, gx, gy, [BatchGrad(lazy=lazy)], hook)
+    wants = ref.centered_batch_grad(cm, cl_, cx, cy)
+    scale = max(w.abs().max().item() for w in wants)
+    for pg, want in zip(gm.parameters(), wants):
+        close(pg.centered_grad_batch, want, dtype, "centered_grad_batch", floor=scale)
+
+    hook = GramSqrtGGNExact(layerwise=True)
+    run_backward(gm, gl, gx, gy, [SqrtGGNExact(lazy=lazy)], hook)
+    want, layers = ref.gram_sqrt_ggn(cm, cl_, cx, cy)
+    scale = want.abs().max().item()
+    close(hook.get_result(), want, dtype, "GramSqrtGGNExact")
+    for pg in gm.parameters():
+        close(pg.gram_sqrt_ggn_exact, layers[table[id(pg)]], dtype, "GramSqrtGGNExact layerwise", floor=scale)
+    if isinstance(cl_, nn.CrossEntropyLoss):
+        M = 3
+        torch.manual_seed(1)
+        with torch.no_grad():
+            ids = ref.sample_ce_classes(cm(cx), None, M)
+        ext = SqrtGGNMC(mc_samples=M, lazy=lazy)
+        ext.mc_state = ids.to(DEV)
+        hook = GramSqrtGGNMC(free_sqrt_ggn=True)
+        run_backward(gm, gl, gx, gy, [ext], hook)
+        want, _ = ref.gram_sqrt_ggn(cm, cl_, cx, cy, mc_samples=M, mc_state=ids)
+        close(hook.get_result(), want, dtype, "GramSqrtGGNMC")
+        assert not any(hasattr(pg, "sqrt_ggn_mc") for pg in gm.parameters())

@@ -352,6 +352,10 @@ class BatchGrad(Extension):
             g = self._subsample(g_out.detach())
             lo, hi = self._own(g.shape[-1])
             g = g[:, lo:hi].contiguous()
+            if not self._lazy and g.data_ptr() == g_out.data_ptr():
+                # the materialised bias gradient is handed to the user (hooks may centre it in
+                # place): it must not alias the gradient autograd is still back-propagating
+                g = g.clone()
             z = self._subsample(module.input0.detach())
             if b is not None:
                 self._save(b, DenseGrad(g, (hi - lo,)))

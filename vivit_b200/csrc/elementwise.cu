@@ -370,6 +370,65 @@ __global__ void scale_rows_rsqrt_kernel(T* E, const double* norm2, int64_t K, in
   GRID_STRIDE(i, total) { E[i] = T(double(E[i]) / sqrt(norm2[i / D])); }
 }
 
+// out[n, d] = g[n, d] - mean_m g[m, d]  (CenteredBatchGrad / CenteredGramBatchGrad prologue).  A block owns a strip
+// of 32 * VEC columns: its 8 warps split the rows for the column sums (16-byte loads when VEC > 1), the partial sums
+// are added in a fixed order (deterministic), and every warp subtracts the mean from the rows it has just read, so
+// the second read comes from L2 and HBM sees one read and one write of the matrix.  out may alias g.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) center_rows_kernel(T* out, const T* g, int64_t N, int64_t D) {
+  __shared__ T part[8][32 * VEC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t strips = (D + 32 * VEC - 1) / (32 * VEC);
+  for (int64_t strip = blockIdx.x; strip < strips; strip += gridDim.x) {
+    const int64_t d0 = strip * (32 * VEC) + int64_t(lane) * VEC;
+    const bool live = d0 < D;  // D % VEC == 0 whenever VEC > 1
+    T acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = T(0);
+    if (live) {
+      for (int64_t n = warp; n < N; n += 8) {
+        T x[VEC];
+        if constexpr (VEC > 1) {
+          *reinterpret_cast<int4*>(x) = *reinterpret_cast<const int4*>(g + n * D + d0);
+        } else {
+          x[0] = g[n * D + d0];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] += x[v];
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) part[warp][lane * VEC + v] = acc[v];
+    __syncthreads();
+    T mean[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      T s = T(0);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += part[w][lane * VEC + v];
+      mean[v] = s / T(N);
+    }
+    if (live) {
+      for (int64_t n = warp; n < N; n += 8) {
+        T x[VEC];
+        if constexpr (VEC > 1) {
+          *reinterpret_cast<int4*>(x) = *reinterpret_cast<const int4*>(g + n * D + d0);
+        } else {
+          x[0] = g[n * D + d0];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) x[v] -= mean[v];
+        if constexpr (VEC > 1) {
+          *reinterpret_cast<int4*>(out + n * D + d0) = *reinterpret_cast<const int4*>(x);
+        } else {
+          out[n * D + d0] = x[0];
+        }
+      }
+    }
+    __syncthreads();  // part is reused by the next strip
+  }
+}
+
 template <typename T>
 __global__ void filter_nonzero_kernel(uint8_t* mask, const T* ev, int64_t R, T atol, T rtol,
                                       unsigned long long* count) {
@@ -590,6 +649,23 @@ int vvt_scale_rows_rsqrt(void* E, const void* norm2, int64_t K, int64_t D, int d
   VVT_REQUIRE(E && norm2, "null pointer");
   VVT_DISPATCH(dtype, {
     scale_rows_rsqrt_kernel<T><<<ew_blocks(K * D), 256, 0, as_stream(stream)>>>((T*)E, (const double*)norm2, K, D);
+    return launched(__func__);
+  });
+}
+
+int vvt_center_rows(void* out, const void* g, int64_t N, int64_t D, int dtype, void* stream) {
+  VVT_REQUIRE(N >= 0 && D >= 0, "negative size");
+  if (N * D == 0) return VVT_OK;
+  VVT_REQUIRE(out && g, "null pointer");
+  VVT_DISPATCH(dtype, {
+    constexpr int VEC = 16 / int(sizeof(T));
+    const bool vec = D % VEC == 0 && (reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(g)) % 16 == 0;
+    const int64_t strips = ceil_div(D, vec ? 32 * VEC : 32);
+    const unsigned blocks = unsigned(vmin<int64_t>(strips, 16 * int64_t(num_sms())));
+    if (vec)
+      center_rows_kernel<T, VEC><<<blocks, 256, 0, as_stream(stream)>>>((T*)out, (const T*)g, N, D);
+    else
+      center_rows_kernel<T, 1><<<blocks, 256, 0, as_stream(stream)>>>((T*)out, (const T*)g, N, D);
     return launched(__func__);
   });
 }

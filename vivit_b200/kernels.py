@@ -130,6 +130,21 @@ def scale_(t: Tensor, alpha: float) -> Tensor:
     return t
 
 
+def center_rows(g: Tensor, inplace: bool = False) -> Tensor:
+    """``g [N, ...] - g.mean(0)`` (per-sample gradients minus their mean); ``inplace`` overwrites ``g``."""
+    if inplace and not g.is_contiguous():
+        raise ValueError("in-place centering needs a contiguous tensor")
+    g = _c(g)
+    _chk(g)
+    out = g if inplace else torch.empty_like(g)
+    N = g.shape[0]
+    D = g.numel() // N if N else 0
+    with torch.cuda.device(g.device):
+        st = _lib.load().vvt_center_rows(_p(out), _p(g), N, D, _dt(g), _stream(g))
+    _lib.check(st, "vvt_center_rows")
+    return out
+
+
 # --------------------------------------------------------------------------
 # (1) factor back-propagation
 # --------------------------------------------------------------------------
@@ -573,7 +588,7 @@ TIMED = [
     "v_emit_linear", "gemm", "gram_dense_accum", "gram_cross_accum", "gram_linear_accum",
     "gram_cross_linear_accum", "syevj", "filter_nonzero", "backtransform_dense",
     "backtransform_linear", "vt_mat_prod_linear", "scale_rows_rsqrt", "dirderiv_epilogue",
-    "newton_coeff", "v_apply_dense", "v_apply_linear",
+    "newton_coeff", "v_apply_dense", "v_apply_linear", "center_rows",
 ]
 
 

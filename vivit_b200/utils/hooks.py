@@ -104,3 +104,48 @@ class ParameterGroupsHook:
         hook.group_hook = types.MethodType(group_hook_fn, hook)
         hook.accumulate = types.MethodType(accumulate_fn, hook)
         return hook
+
+
+class ModuleHook:
+    """Per-parameter hook with access to the parameter and its module
+    (``vivit/utils/hooks.py:11-109``): runs once on every trainable parameter of every
+    non-``Sequential`` module and stores the returned value under ``param.<savefield>``."""
+
+    def __init__(self, savefield: str = None):
+        self.savefield = savefield
+        self.processed = set()
+
+    def module_hook(self, param: Parameter, module: Module) -> Any:
+        raise NotImplementedError
+
+    def __call__(self, module: Module) -> None:
+        for param in module.parameters():
+            if self.should_run_hook(param, module):
+                self.run_hook(param, module)
+
+    def should_run_hook(self, param: Parameter, module: Module) -> bool:
+        if isinstance(module, Sequential):
+            return False
+        return id(param) not in self.processed and param.requires_grad
+
+    def run_hook(self, param: Parameter, module: Module) -> None:
+        value = self.module_hook(param, module)
+        self._save(value, param)
+        self.processed.add(id(param))
+
+    def _save(self, value: Any, param: Parameter) -> None:
+        should_save = self.savefield is not None
+        if value is not None and not should_save:
+            raise ValueError(f"Hook has no savefield, but produced output of type {type(value)}.")
+        if should_save:
+            setattr(param, self.savefield, value)
+
+
+class ParameterHook(ModuleHook):
+    """Per-parameter hook that only needs the parameter (``vivit/utils/hooks.py:112-143``)."""
+
+    def param_hook(self, param: Parameter) -> Any:
+        raise NotImplementedError
+
+    def module_hook(self, param: Parameter, module: Module) -> Any:
+        return self.param_hook(param)
