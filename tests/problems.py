@@ -130,6 +130,29 @@ PROBLEMS: List[Problem] = [
         lambda: nn.CrossEntropyLoss(reduction="mean"),
         _cls(4, 4),
     ),
+    # nn.Linear with one / two / three additional input dimensions (test/settings.py:66-112): the
+    # reference materialises the weight factor of such layers (linear.py:26-27,38-39)
+    Problem(
+        "one-additional",
+        lambda: torch.rand(3, 4, 5),
+        lambda: nn.Sequential(nn.Linear(5, 3), nn.Sigmoid(), nn.Linear(3, 2), nn.Sigmoid(), nn.Flatten()),
+        lambda: nn.MSELoss(reduction="mean"),
+        lambda: torch.rand(3, 4 * 2),
+    ),
+    Problem(
+        "two-additional",
+        lambda: torch.rand(3, 4, 2, 5),
+        lambda: nn.Sequential(nn.Linear(5, 3), nn.Tanh(), nn.Linear(3, 2), nn.Tanh(), nn.Flatten()),
+        lambda: nn.MSELoss(reduction="mean"),
+        lambda: torch.rand(3, 4 * 2 * 2),
+    ),
+    Problem(
+        "three-additional",
+        lambda: torch.rand(3, 4, 2, 3, 5),
+        lambda: nn.Sequential(nn.Linear(5, 3), nn.ReLU(), nn.Linear(3, 2), nn.Sigmoid(), nn.Flatten()),
+        lambda: nn.MSELoss(reduction="mean"),
+        lambda: torch.rand(3, 4 * 2 * 3 * 2),
+    ),
 ]
 
 # test/settings.py:36-41 -- only used at the extension level (the Computations

@@ -178,23 +178,45 @@ class _SqrtFactorExtension(Extension):
         setattr(param, self.savefield, value)
 
 
-def _linear_check(module: nn.Linear):
-    if module.input0.dim() != 2:
-        # the reference falls back to a materialised factor here (linear.py:26-27,38-39);
-        # SURVEY 8(f3) lists it as a follow-up
-        raise NotImplementedError("Linear with additional input dimensions is not supported yet")
+def _linear_as_conv(S: Tensor, z: Tensor):
+    """A Linear layer whose input has additional dimensions ``[N, *E, in]`` acts as a 1x1 convolution over
+    the ``E`` extra positions: re-lay ``S [V, N, *E, out]`` and ``z [N, *E, in]`` as the channel-major maps
+    ``[V, N, out, E, 1]`` / ``[N, in, E, 1]`` the conv emit kernels read (index plumbing only).  The reference
+    materialises the factor of such a layer through ``param_mjp`` (``linear.py:26-27,38-39``)."""
+    V, N = S.shape[:2]
+    n_out, n_in = S.shape[-1], z.shape[-1]
+    E = z.numel() // max(N * n_in, 1)
+    Sc = S.reshape(V, N, E, n_out).transpose(2, 3).contiguous().reshape(V, N, n_out, E, 1)
+    Xc = z.reshape(N, E, n_in).transpose(1, 2).contiguous().reshape(N, n_in, E, 1)
+    return Sc, Xc
+
+
+_ONE = (1, 1)
+
+
+def _emit_linear_extra(Sc: Tensor, Xc: Tensor) -> Tensor:
+    """``[V, N, out, in]``: sum over the extra positions of ``S (x) z`` (``einsum("vn...o,n...i->vnoi")``)."""
+    Vt = kernels.v_emit_conv2d(Sc, Xc, _ONE, _ONE, (0, 0), _ONE)
+    return Vt.reshape(*Vt.shape[:4])
 
 
 def _factor_linear(ext: _SqrtFactorExtension, module: nn.Linear, S: Tensor, need_in: bool):
-    _linear_check(module)
     z = ext._subsample(module.input0.detach())
     w, b = _trainable(module, "weight"), _trainable(module, "bias")
     lo, hi = ext._own(S.shape[-1])
     S_own = S if hi - lo == S.shape[-1] else S[..., lo:hi].contiguous()
-    if b is not None:  # bias first, as [BackPACK] does (params=["bias", "weight"], linear.py:24)
-        ext._save(b, DenseFactor(S_own, (hi - lo,)))
-    if w is not None:
-        ext._save(w, LinearWeightFactor(S_own, z.contiguous()))
+    if z.dim() > 2:  # additional dimensions: dense factors (SURVEY 8 f3)
+        if w is not None or b is not None:
+            Sc, Xc = _linear_as_conv(S_own, z)
+            if b is not None:
+                ext._save(b, DenseFactor(kernels.v_emit_bias(Sc), (hi - lo,)))
+            if w is not None:
+                ext._save(w, DenseFactor(_emit_linear_extra(Sc, Xc), (hi - lo, z.shape[-1])))
+    else:
+        if b is not None:  # bias first, as [BackPACK] does (params=["bias", "weight"], linear.py:24)
+            ext._save(b, DenseFactor(S_own, (hi - lo,)))
+        if w is not None:
+            ext._save(w, LinearWeightFactor(S_own, z.contiguous()))
     return kernels.sqrt_backprop_linear(S, module.weight.detach()) if need_in else None
 
 
@@ -348,9 +370,15 @@ class BatchGrad(Extension):
             w, b = _trainable(module, "weight"), _trainable(module, "bias")
             if w is None and b is None:
                 return
-            _linear_check(module)
             g = self._subsample(g_out.detach())
             lo, hi = self._own(g.shape[-1])
+            if g.dim() > 2:  # Linear with additional input dimensions
+                Sc, Xc = _linear_as_conv(g[..., lo:hi][None], self._subsample(module.input0.detach()))
+                if b is not None:
+                    self._save(b, DenseGrad(kernels.v_emit_bias(Sc)[0], (hi - lo,)))
+                if w is not None:
+                    self._save(w, DenseGrad(_emit_linear_extra(Sc, Xc)[0], (hi - lo, w.shape[1])))
+                return
             g = g[:, lo:hi].contiguous()
             if not self._lazy and g.data_ptr() == g_out.data_ptr():
                 # the materialised bias gradient is handed to the user (hooks may centre it in
