@@ -263,6 +263,12 @@ def jac_t_mat_prod(
         left, right, top, bottom = module.padding
         h, w = mat.shape[-2:]
         return mat[..., top : h - bottom, left : w - right]
+    if isinstance(module, _BATCHNORM):
+        # [external] BatchNormNdDerivatives._jac_t_mat_prod in evaluation mode: the layer is an affine map
+        # per channel, its Jacobian is diag(weight / sqrt(running_var + eps))
+        _bn_require_eval(module)
+        shape = (1, 1, -1) + (1,) * (mat.dim() - 3)
+        return mat * (module.weight / (module.running_var + module.eps).sqrt()).reshape(shape)
     raise NotImplementedError(f"jac_t_mat_prod for {type(module)}")
 
 
@@ -296,7 +302,25 @@ def param_mjp(
         )  # [N, J, X]
         vt = einsum("vnox,njx->vnoj", mat.reshape(v, n, co, -1), cols)
         return vt.reshape(v, n, *module.weight.shape)
+    if isinstance(module, _BATCHNORM):
+        # [external] BatchNormNdDerivatives._weight_jac_t_mat_prod / _bias_jac_t_mat_prod (evaluation mode),
+        # wired by ``vivit/extensions/secondorder/vivit/batchnormnd.py:8-13`` (params=["bias", "weight"])
+        _bn_require_eval(module)
+        spatial = tuple(range(3, mat.dim()))
+        if name == "bias":
+            return mat.sum(spatial) if spatial else mat
+        x_hat = F.batch_norm(inp, module.running_mean, module.running_var, None, None, False, 0.0, module.eps)
+        prod = mat * x_hat[None]
+        return prod.sum(spatial) if spatial else prod
     raise NotImplementedError(f"param_mjp for {type(module)}")
+
+
+_BATCHNORM = (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)
+
+
+def _bn_require_eval(module: nn.Module) -> None:
+    if module.training or not module.track_running_stats or module.weight is None:
+        raise NotImplementedError("BatchNorm is supported in evaluation mode (affine, running statistics) only")
 
 
 def _has_additional_dims(inp: Tensor) -> bool:

@@ -41,6 +41,18 @@ def _cls(n, c):
     return lambda: torch.randint(size=(n,), low=0, high=c)
 
 
+def _eval_mode(model):
+    """``initialize_training_false_recursive`` (test/utils.py:81-114): random running statistics and
+    affine parameters for every BatchNorm layer, whole model in evaluation mode."""
+    for m in model.modules():
+        if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)):
+            m.running_mean = torch.rand_like(m.running_mean)
+            m.running_var = torch.rand_like(m.running_var)
+            m.weight.data = torch.rand_like(m.weight)
+            m.bias.data = torch.rand_like(m.bias)
+    return model.train(False)
+
+
 PROBLEMS: List[Problem] = [
     # test/settings.py:29-35
     Problem(
@@ -152,6 +164,35 @@ PROBLEMS: List[Problem] = [
         lambda: nn.Sequential(nn.Linear(5, 3), nn.ReLU(), nn.Linear(3, 2), nn.Sigmoid(), nn.Flatten()),
         lambda: nn.MSELoss(reduction="mean"),
         lambda: torch.rand(3, 4 * 2 * 3 * 2),
+    ),
+    # BatchNorm in evaluation mode (test/settings.py:118-160)
+    Problem(
+        "bn1d-mse",
+        lambda: torch.rand(2, 3, 4),
+        lambda: _eval_mode(nn.Sequential(nn.BatchNorm1d(num_features=3), nn.Flatten(), nn.Linear(12, 3), nn.Sigmoid())),
+        lambda: nn.MSELoss(),
+        lambda: torch.rand(2, 3),
+    ),
+    Problem(
+        "bn2d-ce",
+        lambda: torch.rand(3, 2, 4, 3),
+        lambda: _eval_mode(nn.Sequential(nn.BatchNorm2d(num_features=2), nn.Flatten(), nn.Linear(24, 3))),
+        lambda: nn.CrossEntropyLoss(),
+        _cls(3, 3),
+    ),
+    Problem(
+        "bn3d-ce",
+        lambda: torch.rand(3, 3, 4, 1, 2),
+        lambda: _eval_mode(nn.Sequential(nn.BatchNorm3d(num_features=3), nn.Flatten(), nn.Linear(24, 3))),
+        lambda: nn.CrossEntropyLoss(),
+        _cls(3, 3),
+    ),
+    Problem(
+        "linear-bn3d-mse",
+        lambda: torch.rand(3, 3, 4, 1, 2),
+        lambda: _eval_mode(nn.Sequential(nn.Linear(2, 3), nn.BatchNorm3d(num_features=3), nn.Sigmoid(), nn.Flatten())),
+        lambda: nn.MSELoss(),
+        lambda: torch.rand(3, 4 * 1 * 3 * 3),
     ),
 ]
 

@@ -11,8 +11,10 @@ Public classes mirror what the reference hands to ``with backpack(...)``:
   ``lazy=True`` (what the Computations use) the savefield holds a ``Factor`` /
   ``GradFactor`` object instead of the materialised tensor.
 
-Module coverage: ``CrossEntropyLoss``, ``MSELoss``, ``Linear``, ``Conv2d``, ``ReLU``,
-``Sigmoid``, ``Tanh``, ``MaxPool2d``, ``AvgPool2d``, ``Flatten``, ``Dropout``, ``Identity``.
+Module coverage: ``CrossEntropyLoss``, ``MSELoss``, ``Linear`` (also with additional input
+dimensions), ``Conv2d``, ``BatchNorm1d/2d/3d`` (evaluation mode), ``ReLU``, ``Sigmoid``, ``Tanh``,
+``LeakyReLU``, ``ELU``, ``SELU``, ``LogSigmoid``, ``MaxPool2d``, ``AvgPool2d``, ``ZeroPad2d``,
+``Flatten``, ``Dropout``, ``Identity``.
 Anything else raises ``NotImplementedError`` (the reference's ``fail_mode="ERROR"``,
 ``__init__.py:83``).
 """
@@ -255,6 +257,55 @@ def _factor_act(act, use_output, scale_of=None):
     return handler
 
 
+_BATCHNORM = (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)
+
+
+def _bn_check(module) -> None:
+    # [BackPACK] mixes the samples of a batch in training mode; the reference's fixtures and the GGN
+    # factorisation per sample only make sense in evaluation mode (test/settings.py:118-160)
+    if module.training or not module.track_running_stats or module.weight is None:
+        raise NotImplementedError("BatchNorm is supported in evaluation mode (affine, running statistics) only")
+
+
+def _bn_normalized_input(module, x: Tensor) -> Tensor:
+    """``(x - running_mean) / sqrt(running_var + eps)``: a quantity of the user's forward pass, recomputed
+    with torch's own batch-norm op (as the max-pool handler recomputes the arg-max positions)."""
+    return F.batch_norm(x, module.running_mean, module.running_var, None, None, False, 0.0, module.eps)
+
+
+def _bn_param_rows(S: Tensor, x_hat: Tensor):
+    """Per-sample factors of the BatchNorm parameters from ``S [V, N, C, *spatial]``: bias ``sum_x S``,
+    weight ``sum_x S * x_hat`` ([BackPACK] ``BatchNormNdDerivatives`` in evaluation mode)."""
+    V, N, C = S.shape[:3]
+    S3 = S.reshape(V, N, C, -1)
+    prod = kernels.sqrt_backprop_elementwise(S3, x_hat, kernels.ACT_MUL)
+    if S3.shape[3] == 1:
+        return S3.reshape(V, N, C), prod.reshape(V, N, C)
+    return kernels.v_emit_bias(S3), kernels.v_emit_bias(prod)
+
+
+def _factor_batchnorm(ext, module, S, need_in):
+    _bn_check(module)
+    w, b = _trainable(module, "weight"), _trainable(module, "bias")
+    C = S.shape[2]
+    lo, hi = ext._own(C)
+    if w is not None or b is not None:
+        x_hat = _bn_normalized_input(module, ext._subsample(module.input0.detach()))
+        S_own = S if hi - lo == C else S[:, :, lo:hi].contiguous()
+        Vb, Vw = _bn_param_rows(S_own, x_hat if hi - lo == C else x_hat[:, lo:hi].contiguous())
+        if b is not None:
+            ext._save(b, DenseFactor(Vb, (hi - lo,)))
+        if w is not None:
+            ext._save(w, DenseFactor(Vw, (hi - lo,)))
+    if not need_in:
+        return None
+    # Jacobian w.r.t. the input: one factor per channel, laid out over one sample's features
+    per_channel = module.weight.detach() / (module.running_var + module.eps).sqrt()
+    spatial = S[0, 0, 0].numel()
+    ref = per_channel.to(S.dtype).reshape(C, 1).expand(C, spatial).contiguous()
+    return kernels.sqrt_backprop_elementwise(S, ref, kernels.ACT_MUL)
+
+
 def _factor_zeropad2d(ext, module: nn.ZeroPad2d, S, need_in):
     """Crop: the Jacobian of zero padding drops the padded border ([BackPACK] ``ZeroPad2dDerivatives``)."""
     left, right, top, bottom = module.padding
@@ -311,6 +362,9 @@ _FACTOR_HANDLERS = {
     nn.SELU: _factor_act(kernels.ACT_SELU, use_output=False),
     nn.LogSigmoid: _factor_act(kernels.ACT_LOGSIGMOID, use_output=False),
     nn.ZeroPad2d: _factor_zeropad2d,
+    nn.BatchNorm1d: _factor_batchnorm,
+    nn.BatchNorm2d: _factor_batchnorm,
+    nn.BatchNorm3d: _factor_batchnorm,
     nn.Dropout: _factor_dropout,
     nn.Flatten: _factor_flatten,
     nn.Identity: _factor_identity,
@@ -406,5 +460,18 @@ class BatchGrad(Extension):
                     _pair(module.dilation),
                 )[0]
                 self._save(w, DenseGrad(gw, (hi - lo, *w.shape[1:])))
+        elif isinstance(module, _BATCHNORM):
+            w, b = _trainable(module, "weight"), _trainable(module, "bias")
+            if w is None and b is None:
+                return
+            _bn_check(module)
+            g = self._subsample(g_out.detach())
+            lo, hi = self._own(g.shape[1])
+            x_hat = _bn_normalized_input(module, self._subsample(module.input0.detach()))
+            gb, gw = _bn_param_rows(g[:, lo:hi].contiguous()[None], x_hat[:, lo:hi].contiguous())
+            if b is not None:
+                self._save(b, DenseGrad(gb[0].clone() if gb.data_ptr() == g_out.data_ptr() else gb[0], (hi - lo,)))
+            if w is not None:
+                self._save(w, DenseGrad(gw[0], (hi - lo,)))
         elif any(p.requires_grad for p in module.parameters(recurse=False)):
             self._unsupported(self, module)

@@ -1355,13 +1355,18 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   // rows of the panel are split over the CTAs of a cluster: as many as leave >= 16 rows per CTA
   // (few CTAs per cluster: every CTA repeats the rotation rounds, and the cluster barriers of the Gram
   // reduction are the main cost of a round; 640 rows per CTA measured best at R = 1280)
+  // A CTA's time is mostly fixed cost (barriers, rotation rounds, latencies: ~11 us + ~4 ns per row, fp32), so
+  // once a round no longer fits on the GPU the fewest CTAs win: the smallest cluster whose rows still fit in
+  // shared memory (resident variant: 1072 rows fp32, 588 rows fp64).  Measured (fp32, ms): R=2560 CL 3/4/5 =
+  // 94/113/132, R=3840 CL 4/5/8 = 330/360/488, R=5120 CL 5/6/8 = 836/909/1083; fp64 R=2560 CL 4/8 = 458/775.
   int CL = 1;
-  const int max_rows = sizeof(T) == 4 ? 640 : 320;  // the fp64 phases run on DFMA: keep less work per CTA
-  while (CL < 8 && Np / CL > max_rows) CL *= 2;
+  const int max_rows = sizeof(T) == 4 ? 1024 : 576;
+  const int fill_rows = sizeof(T) == 4 ? 320 : 160;
+  while (CL < 8 && ceil_div(Np, CL) > max_rows) ++CL;
   // SMs left idle by a round (pairs * CL < #SMs) are put to work with a larger, possibly odd cluster, as long
   // as a CTA keeps enough rows for the Gram / apply phases to outweigh the cluster reduction (R = 1280, fp32:
   // 3 CTAs x 427 rows on 120 SMs, 16.3 ms against 17.7 ms with 2 x 640 on 80 SMs)
-  while (CL < 8 && int64_t(pairs) * (CL + 1) <= num_sms() && Np / (CL + 1) >= max_rows / 2) ++CL;
+  while (CL < 8 && int64_t(pairs) * (CL + 1) <= num_sms() && Np / (CL + 1) >= fill_rows) ++CL;
   if (const char* e = getenv("VVT_SYEVJ_CL")) CL = vmax(1, vmin(8, atoi(e)));  // experiments
   while (CL > 1 && Np / CL < 16) CL /= 2;
   const int rows_per_cta = int(ceil_div(Np, CL));
