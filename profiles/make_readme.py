@@ -77,8 +77,12 @@ def main():
                       f"{k['launches_per_step']:.0f} | {ach} |")
         md.append("")
     lp = os.path.join(SRC, "launches_c2.csv")
+    kept = os.path.join(OUT, f"{ROUND}_launches_c2.csv")
     if os.path.exists(lp):
-        shutil.copy(lp, os.path.join(OUT, f"{ROUND}_launches_c2.csv"))
+        shutil.copy(lp, kept)
+    elif os.path.exists(kept):  # no fresh capture in this session: keep the committed list
+        lp = kept
+    if os.path.exists(lp):
         md += ["## ncu launch list of one c2 step", "",
                "`ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv python bench.py "
                f"--warmup 3 --ncu-step` (one step between cudaProfilerStart/Stop) → `{ROUND}_launches_c2.csv`", "", launch_table(lp), ""]

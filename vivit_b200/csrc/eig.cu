@@ -1361,12 +1361,13 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   // 94/113/132, R=3840 CL 4/5/8 = 330/360/488, R=5120 CL 5/6/8 = 836/909/1083; fp64 R=2560 CL 4/8 = 458/775.
   int CL = 1;
   const int max_rows = sizeof(T) == 4 ? 1024 : 576;
-  const int fill_rows = sizeof(T) == 4 ? 320 : 160;
+  const int fill_rows = sizeof(T) == 4 ? 80 : 160;  // fp32: R=320 CL 1/4 = 3.8/3.4 ms, R=640 CL 2/4 = 8.6/8.0 ms
+  const int fill_max = sizeof(T) == 4 ? 4 : 8;
   while (CL < 8 && ceil_div(Np, CL) > max_rows) ++CL;
   // SMs left idle by a round (pairs * CL < #SMs) are put to work with a larger, possibly odd cluster, as long
   // as a CTA keeps enough rows for the Gram / apply phases to outweigh the cluster reduction (R = 1280, fp32:
   // 3 CTAs x 427 rows on 120 SMs, 16.3 ms against 17.7 ms with 2 x 640 on 80 SMs)
-  while (CL < 8 && int64_t(pairs) * (CL + 1) <= num_sms() && Np / (CL + 1) >= fill_rows) ++CL;
+  while (CL < fill_max && int64_t(pairs) * (CL + 1) <= num_sms() && Np / (CL + 1) >= fill_rows) ++CL;
   if (const char* e = getenv("VVT_SYEVJ_CL")) CL = vmax(1, vmin(8, atoi(e)));  // experiments
   while (CL > 1 && Np / CL < 16) CL /= 2;
   const int rows_per_cta = int(ceil_div(Np, CL));
