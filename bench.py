@@ -82,6 +82,14 @@ def mlp_c4():
     )
 
 
+def mlp_c5():
+    """config 5: a deep MLP whose full-network Gram has R = C N = 10240."""
+    layers, width = [nn.Linear(784, 2048), nn.ReLU()], 2048
+    for _ in range(3):
+        layers += [nn.Linear(width, width), nn.ReLU()]
+    return nn.Sequential(*layers, nn.Linear(width, 10))
+
+
 def top_k(k):
     return lambda ev: list(range(max(0, ev.numel() - k), ev.numel()))
 
@@ -100,6 +108,9 @@ WORKLOADS = {
                mc=1, sub_ggn=list(range(32))),
     "c4": dict(name="mlp_784-4096x3-10 N=512 C=10 EighComputation top-10, per-layer block-diagonal groups",
                model=mlp_c4, n=512, in_shape=(784,), classes=10, calls=("eigh",), grouping="layer"),
+    "c5": dict(name="deep_mlp_784-2048x4-10 N=1024 C=10 EighComputation top-10, full-network Gram R=10240 "
+                    "(parameter-sharded over the ranks, one all-reduce)",
+               model=mlp_c5, n=1024, in_shape=(784,), classes=10, calls=("eigh",), grouping="one"),
 }
 
 

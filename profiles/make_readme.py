@@ -43,7 +43,7 @@ def main():
           "Everything here was measured on one B200 of the pool through `gpurun` (fresh box, no clock locks; the",
           "`clocks` object of every bench line shows 1965 MHz and no throttle reason). Numbers under a profiler are",
           "never bench values; bench values are CUDA-event timings from `bench.py`.", ""]
-    for w in ("c2", "c1", "c3", "c4"):
+    for w in ("c2", "c1", "c3", "c4", "c5"):
         p = os.path.join(SRC, f"bench_{w}.json")
         if not os.path.exists(p):
             continue
