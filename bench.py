@@ -143,6 +143,20 @@ class Stepper:
         self.model = extend(model.to(device))
         self.loss_fn = extend(nn.CrossEntropyLoss())
         self.groups = make_groups(self.model, w["grouping"])
+        self.parallelism = "single GPU"
+        if process_group is not None:
+            import torch.distributed as dist
+
+            world = dist.get_world_size(process_group)
+            if w["grouping"] == "layer":
+                # block-diagonal groups are independent: whole groups per rank, no collective
+                from vivit_b200.dist import local_groups
+
+                self.groups, owner = local_groups(self.groups, process_group)
+                self.pg = None
+                self.parallelism = f"{len(owner)} block-diagonal groups assigned to {world} ranks, no collective"
+            else:
+                self.parallelism = f"parameter-sharded Gram over {world} ranks, one all-reduce per group"
         self.x_host, self.y_host = x.pin_memory(), y.pin_memory()
         self.x, self.y = x.to(device), y.to(device)
         self.host_out = None
@@ -520,12 +534,16 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
         pg = dist.group.WORLD
 
     from vivit_b200 import kernels
 
     stepper = Stepper(w, dtype, device, pg)
+    config["parallelism"] = stepper.parallelism
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
 
     def barrier():

@@ -168,3 +168,69 @@ def test_shard_bounds_and_group_assignment():
     owner = assign_groups([5.0, 1.0, 1.0, 1.0, 4.0], 2)
     loads = [sum(c for c, o in zip([5.0, 1.0, 1.0, 1.0, 4.0], owner) if o == r) for r in range(2)]
     assert sorted(loads) == [6.0, 6.0]
+
+
+def _worker_groups(rank, world, port, errors):
+    try:
+        if ROOT not in sys.path:
+            sys.path.insert(0, ROOT)
+        import torch.distributed as dist
+
+        import tests._torch_kernels as double
+        from oracle import reference_path as ref
+
+        double.install(_MonkeyPatch())
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        import vivit_b200 as vv
+        from vivit_b200.dist import local_groups
+
+        model, x, y = _problem()
+        groups = _groups(model, "layer")
+        own, owner = local_groups(groups, dist.group.WORLD)
+        assert sorted(set(owner)) == list(range(world)) and len(owner) == len(groups)
+        assert [g for g, o in zip(groups, owner) if o == rank] == own
+        comp = vv.EighComputation()  # no process group: whole groups, no collective
+        m, lf = vv.extend(model), vv.extend(nn.CrossEntropyLoss())
+        with vv.backpack(*comp.get_extensions(), extension_hook=comp.get_extension_hook(own)):
+            lf(m(x), y).backward()
+        model0, x0, y0 = _problem()
+        want = ref.eigh(model0, nn.CrossEntropyLoss(), x0, y0, _groups(model0, "layer"))
+        for g, (wev, wvecs), o in zip(groups, want, owner):
+            if o != rank:
+                with pytest.raises(KeyError):
+                    comp.get_result(g)
+                continue
+            ev, evecs = comp.get_result(g)
+            assert torch.allclose(ev, wev, rtol=1e-9, atol=1e-12)
+            for e, w_ in zip(evecs, wvecs):
+                for k in range(e.shape[0]):
+                    sign = torch.sign((e[k] * w_[k]).sum())
+                    assert torch.allclose(e[k] * sign, w_[k], rtol=1e-6, atol=1e-9)
+        # every group is solved by exactly one rank
+        mine = torch.tensor([float(o == rank) for o in owner])
+        dist.all_reduce(mine)
+        assert torch.equal(mine, torch.ones(len(groups)))
+        dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        errors.put((rank, traceback.format_exc()))
+
+
+def test_two_rank_block_diagonal_groups_need_no_collective():
+    """block-diagonal groups are assigned to ranks whole (``dist.local_groups``)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    errors = ctx.Queue()
+    procs = [ctx.Process(target=_worker_groups, args=(r, world, port, errors)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            pytest.fail("a rank hung")
+    msgs = []
+    while not errors.empty():
+        msgs.append(errors.get())
+    assert not msgs, "\n".join(f"rank {r}:\n{t}" for r, t in msgs)
+    assert all(p.exitcode == 0 for p in procs)

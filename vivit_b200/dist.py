@@ -89,3 +89,24 @@ def assign_groups(costs: Sequence[float], world: int) -> List[int]:
         owner[i] = r
         loads[r] += costs[i]
     return owner
+
+
+def local_groups(param_groups: Sequence[Dict], process_group=None, costs: Optional[Sequence[float]] = None):
+    """Block-diagonal parameter groups are independent (``vivit/utils/hooks.py:214-219``): give every rank
+    whole groups and run the Computations WITHOUT ``process_group`` on them -- no collective at all.
+
+    Returns ``(own, owner)``: the sub-list of ``param_groups`` (the same dict objects, for ``get_result``)
+    this rank is responsible for, and the owning rank of every group.  ``costs`` default to one unit per
+    group (the eigensolver, which depends on ``C N`` only) plus the group's share of the parameters.
+    """
+    if process_group is None:
+        return list(param_groups), [0] * len(param_groups)
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+    if costs is None:
+        numel = [sum(p.numel() for p in g["params"]) for g in param_groups]
+        total = float(max(sum(numel), 1))
+        costs = [1.0 + n / total for n in numel]
+    owner = assign_groups(costs, world)
+    return [g for g, o in zip(param_groups, owner) if o == rank], owner
