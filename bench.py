@@ -484,7 +484,27 @@ def time_reference(w, dtype, steps, warmup, budget_s):
 # --------------------------------------------------------------------------
 
 
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """The contract is ONE JSON line on stdout: libraries that print banners there (NCCL's version line at
+    NCCL_DEBUG=VERSION/WARN) are sent to stderr by pointing fd 1 at fd 2 for the duration of the run."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -522,7 +542,7 @@ def main():
             "e2e": {"value": round(ms, 3), "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        _emit(line)
         return
 
     if not torch.cuda.is_available():
@@ -534,9 +554,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
         pg = dist.group.WORLD
 
@@ -668,7 +685,7 @@ def main():
         "eigensolver_ms_per_step": round(sum(r["ms_per_step"] for r in rows if r["kernel"] == "syevj"), 4),
         "kernels": rows,
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         import torch.distributed as dist
 

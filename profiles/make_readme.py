@@ -76,6 +76,26 @@ def main():
             md.append(f"| `{k['kernel']}` | {k['ms_per_step']} | {100 * k['share']:.1f}% | {k['calls_per_step']:.0f} | "
                       f"{k['launches_per_step']:.0f} | {ach} |")
         md.append("")
+    multi = []
+    for w, n in (("c2", 2), ("c4", 2)):
+        p = os.path.join(SRC, f"bench_{w}_n{n}.json")
+        kept_json = os.path.join(OUT, f"{ROUND}_bench_{w}_n{n}.json")
+        if os.path.exists(p):
+            lines = [l for l in open(p) if l.startswith("{")]  # NCCL may have printed its version banner first
+            if lines:
+                open(kept_json, "w").write(lines[-1])
+        if os.path.exists(kept_json):
+            d = json.load(open(kept_json))
+            one = json.load(open(os.path.join(OUT, f"{ROUND}_bench_{w}.json")))
+            multi.append(f"| {w} | {n} | {d['config'].get('parallelism', 'parameter-sharded Gram, one all-reduce per group')} | "
+                         f"{one['value']} | {d['value']} | {d['e2e']['value']} | {d.get('gram_assembly_ms_per_step')} "
+                         f"(1 GPU: {one.get('gram_assembly_ms_per_step')}) | {d.get('eigensolver_ms_per_step')} |")
+    if multi:
+        md += ["## 2 GPUs (`torchrun --nproc-per-node 2 bench.py --gpus 2`, NCCL, max over ranks)", "",
+               "| workload | GPUs | parallelism | 1-GPU step ms | step ms | end to end ms | Gram assembly ms (rank 0) | eigensolver ms (rank 0) |",
+               "|---|---|---|---|---|---|---|---|"] + multi + [
+               "", "c2 shards the contraction dimension: the factor emit and Gram assembly shrink, the eigensolver (two calls per",
+               "step, 55% of the step) is replicated on every rank. c4's four block-diagonal groups are independent: two eigensolves per rank, no collective.", ""]
     lp = os.path.join(SRC, "launches_c2.csv")
     kept = os.path.join(OUT, f"{ROUND}_launches_c2.csv")
     if os.path.exists(lp):
