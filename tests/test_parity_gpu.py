@@ -386,3 +386,30 @@ def test_gram_extension_hooks(problem, lazy, dtype):
         want, _ = ref.gram_sqrt_ggn(cm, cl_, cx, cy, mc_samples=M, mc_state=ids)
         close(hook.get_result(), want, dtype, "GramSqrtGGNMC")
         assert not any(hasattr(pg, "sqrt_ggn_mc") for pg in gm.parameters())
+
+
+def test_hessianfree_operator_and_device_lanczos():
+    """the GGN operator on the GPU equals the dense autograd GGN, the Lanczos recurrence runs on
+    the device and its tridiagonal matrix is decomposed by ``vvt_syevj``; the top of the matrix-free spectrum
+    equals the top Gram eigenvalue of ``EigvalshComputation``."""
+    import numpy as np
+
+    from oracle.autograd_ggn import AutogradGGN
+    from vivit_b200 import EigvalshComputation
+    from vivit_b200.hessianfree import GGNLinearOperator
+    from vivit_b200.hessianfree.lanczos import fast_lanczos
+
+    (gm, gl, gx, gy), (cm, cl_, cx, cy) = make_pair(PROBLEMS[0], torch.float64)
+    G = GGNLinearOperator(gm, gl, [(gx, gy)], torch.device(DEV), dtype=np.float64, check_deterministic=False)
+    ggn = AutogradGGN(cm, cl_, cx, cy).ggn().numpy()
+    v = np.random.default_rng(0).standard_normal(ggn.shape[0])
+    assert np.allclose(G @ v, ggn @ v, rtol=1e-9, atol=1e-12)
+    np.random.seed(0)
+    ritz, vecs = fast_lanczos(G, 24)
+    top = np.linalg.eigvalsh(ggn)[-1]
+    assert abs(ritz[-1] - top) <= 1e-8 * top
+    assert abs((vecs[0] ** 2).sum() - 1.0) < 1e-8
+    comp = EigvalshComputation()
+    groups = [{"params": list(gm.parameters())}]
+    run_backward(gm, gl, gx, gy, [comp.get_extension()], comp.get_extension_hook(groups))
+    assert abs(comp.get_result(groups[0])[-1].item() - top) <= 1e-8 * top

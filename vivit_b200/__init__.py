@@ -23,7 +23,7 @@ from vivit_b200.backprop import (
     disable,
     extend,
 )
-from vivit_b200 import extensions
+from vivit_b200 import extensions, hessianfree
 from vivit_b200.linalg import EighComputation, EigvalshComputation
 from vivit_b200.optim import DirectionalDampedNewtonComputation, DirectionalDerivativesComputation
 
@@ -31,6 +31,7 @@ __version__ = "0.1.0"
 
 __all__ = [
     "extensions",
+    "hessianfree",
     "EigvalshComputation",
     "EighComputation",
     "DirectionalDerivativesComputation",
