@@ -133,3 +133,20 @@ def test_device_recurrence_on_operator():
     ritz, vecs = fast_lanczos(G, 25)
     assert abs(ritz[-1] - np.linalg.eigvalsh((dense + dense.T) / 2)[-1]) < 1e-8 * max(1.0, abs(ritz[-1]))
     assert np.allclose((vecs[0] ** 2).sum(), 1.0)
+
+
+def test_tridiagonal_decomposition_through_the_library_solver(monkeypatch):
+    """The GPU branch of ``fast_lanczos`` (dense Lanczos matrix -> ``kernels.syevj``), exercised on CPU through
+    the test double: an indefinite matrix is shifted to positive semi-definite and shifted back."""
+    import tests._torch_kernels as double
+    from scipy.linalg import eigh_tridiagonal
+    from vivit_b200.hessianfree.lanczos import _eigh_tridiagonal_device
+
+    double.install(monkeypatch)
+    rng = np.random.default_rng(3)
+    alphas, betas = rng.standard_normal(12) - 0.5, rng.standard_normal(11)
+    evals, evecs = _eigh_tridiagonal_device(torch.from_numpy(alphas), torch.from_numpy(betas))
+    want, wvecs = eigh_tridiagonal(alphas, betas)
+    assert want[0] < 0 < want[-1]
+    assert np.allclose(evals, want, rtol=1e-10, atol=1e-12)
+    assert np.allclose(np.abs(evecs[0]), np.abs(wvecs[0]), rtol=1e-8, atol=1e-10)

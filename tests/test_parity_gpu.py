@@ -413,3 +413,15 @@ def test_hessianfree_operator_and_device_lanczos():
     groups = [{"params": list(gm.parameters())}]
     run_backward(gm, gl, gx, gy, [comp.get_extension()], comp.get_extension_hook(groups))
     assert abs(comp.get_result(groups[0])[-1].item() - top) <= 1e-8 * top
+    # an indefinite Lanczos matrix (Hessian operators) goes through the same solver, shifted
+    from scipy.linalg import eigh_tridiagonal
+
+    from vivit_b200.hessianfree.lanczos import _eigh_tridiagonal_device
+
+    rng = np.random.default_rng(3)
+    alphas, betas = rng.standard_normal(20) - 0.5, rng.standard_normal(19)
+    evals, evecs = _eigh_tridiagonal_device(torch.from_numpy(alphas).to(DEV), torch.from_numpy(betas).to(DEV))
+    want, wvecs = eigh_tridiagonal(alphas, betas)
+    scale = np.abs(want).max()
+    assert np.abs(evals - want).max() <= 1e-10 * scale
+    assert np.abs(np.abs(evecs[0]) - np.abs(wvecs[0])).max() <= 1e-7

@@ -64,10 +64,18 @@ def _eigh_tridiagonal_device(alphas, betas) -> Tuple[np.ndarray, np.ndarray]:
     from vivit_b200 import kernels
 
     T = torch.diag(alphas)
+    radius = torch.zeros_like(alphas)
     if betas.numel():
         T = T + torch.diag(betas, 1) + torch.diag(betas, -1)
+        radius[:-1] += betas.abs()
+        radius[1:] += betas.abs()
+    # vvt_syevj is written for Gram matrices (positive semi-definite; it factors G + eps I).  A Hessian's
+    # Lanczos matrix is indefinite: shift it by its Gershgorin lower bound, which moves every eigenvalue by
+    # exactly that amount and leaves the eigenvectors alone.
+    shift = torch.clamp(-(alphas - radius).min(), min=0.0)
+    T = T + shift * torch.eye(T.shape[0], dtype=T.dtype, device=T.device)
     evals, evecs = kernels.syevj(T.contiguous(), vectors=True)
-    return evals.cpu().numpy(), evecs.cpu().numpy()
+    return (evals - shift).cpu().numpy(), evecs.cpu().numpy()
 
 
 def fast_lanczos(A: LinearOperator, ncv: int, use_eigh_tridiagonal: bool = False) -> Tuple[np.ndarray, np.ndarray]:
