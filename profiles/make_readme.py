@@ -76,6 +76,25 @@ def main():
             md.append(f"| `{k['kernel']}` | {k['ms_per_step']} | {100 * k['share']:.1f}% | {k['calls_per_step']:.0f} | "
                       f"{k['launches_per_step']:.0f} | {ach} |")
         md.append("")
+    pk = os.path.join(OUT, f"{ROUND}_peaks_tf32_fp64.json")
+    f64 = os.path.join(OUT, f"{ROUND}_bench_c2_f64.json")
+    if os.path.exists(pk):
+        q = json.load(open(pk))
+        md += ["## measured TF32 / FP64 GEMM peaks of the box (`scratch/measure_peaks.py`, cuBLAS through `torch.matmul`)", "",
+               f"* TF32 {q['tf32_tflops']} TFLOP/s at {q['tf32_n']}^3 (best of 6) ⇒ 3×TF32 peak {q['tf32_tflops'] / 3:.1f} TFLOP/s "
+               "(the bench lines divide by the sustained bf16 peak ÷ 6 = 233.8 TFLOP/s; against this burst figure the dense "
+               "Gram kernel of c2, 152 TFLOP/s, is at 61%)",
+               f"* FP64 {q['fp64_tflops']} TFLOP/s at {q['fp64_n']}^3", ""]
+        if os.path.exists(f64):
+            d = json.load(open(f64))
+            r, e = d["roofline"], d["eigensolver"]
+            md += ["## bench.py --dtype f64 (c2)", "",
+                   f"* device-timed step **{d['value']} ms**, end to end {d['e2e']['value']} ms ({d['steps']} steps)",
+                   f"* dense Gram on DMMA `{r['shapes']}`: {r['achieved']} TFLOP/s = **{100 * r['achieved'] / q['fp64_tflops']:.0f}% of the "
+                   f"measured FP64 peak** ({q['fp64_tflops']} TFLOP/s)",
+                   f"* eigensolver R={e['R']} fp64: {e['ms']} ms, {e['sweeps']} sweeps, eigenvalue error {e['eigenvalue_error_rel_max']:.1e}, "
+                   f"residual {e['residual_fro']:.1e}, orthogonality {e['orthogonality_max_abs']:.1e}; cuSOLVER {e['cusolver_eigh_ms']} ms "
+                   "(the fp64 rotation / Gram / apply phases run on DFMA, not on tensor cores)", ""]
     multi = []
     for w, n in (("c2", 2), ("c4", 2)):
         p = os.path.join(SRC, f"bench_{w}_n{n}.json")
