@@ -138,6 +138,8 @@ def sqrt_backprop_avgpool2d(S, in_hw, kernel, stride, padding):
 
 def v_emit_conv2d(S, X, kernel, stride, padding, dilation):
     V, N, co = S.shape[:3]
+    if co == 0:
+        return S.new_zeros(V, N, 0, X.shape[1], *kernel)
     cols = F.unfold(X, kernel, dilation=dilation, padding=padding, stride=stride)
     vt = einsum("vnox,njx->vnoj", S.reshape(V, N, co, -1), cols)
     return vt.reshape(V, N, co, X.shape[1], *kernel)

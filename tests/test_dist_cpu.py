@@ -234,3 +234,28 @@ def test_two_rank_block_diagonal_groups_need_no_collective():
         msgs.append(errors.get())
     assert not msgs, "\n".join(f"rank {r}:\n{t}" for r, t in msgs)
     assert all(p.exitcode == 0 for p in procs)
+
+
+def test_partial_grams_of_all_shards_sum_to_the_full_gram_even_with_empty_shards():
+    """More ranks than output channels: some ranks own an empty slice of a parameter and contribute nothing.
+    The shards of all eight 'ranks' are evaluated one after the other in this process (test double)."""
+    import tests._torch_kernels as double
+    from oracle import reference_path as ref
+
+    double.install(_MonkeyPatch())
+    import vivit_b200 as vv
+    from vivit_b200.extensions.hooks import GramSqrtGGNExact
+
+    world, total = 8, None
+    for rank in range(world):
+        model, x, y = _problem()  # last layer has 4 outputs, the conv layer 5 channels
+        ext = vv.SqrtGGNExact(lazy=True)
+        ext._shard = (rank, world)
+        hook = GramSqrtGGNExact()
+        m, lf = vv.extend(model), vv.extend(nn.CrossEntropyLoss())
+        with vv.backpack(ext, extension_hook=hook):
+            lf(m(x), y).backward()
+        total = hook.get_result() if total is None else total + hook.get_result()
+    model, x, y = _problem()
+    want, _ = ref.gram_sqrt_ggn(model, nn.CrossEntropyLoss(), x, y)
+    assert torch.allclose(total, want, rtol=1e-9, atol=1e-12), (total - want).abs().max()

@@ -249,6 +249,8 @@ def v_emit_conv2d(S: Tensor, X: Tensor, kernel, stride, padding, dilation) -> Te
     _, ci, h, w = X.shape
     kh, kw = kernel
     Vt = torch.empty(V, N, co, ci, kh, kw, dtype=S.dtype, device=S.device)
+    if Vt.numel() == 0:  # an empty shard of the output channels (more ranks than channels)
+        return Vt
     lib = _lib.load()
     ws = _ws(lib.vvt_conv2d_workspace_bytes(0, V, N, co, ho, wo, ci, kh, kw, _dt(S)), S)
     with torch.cuda.device(S.device):
@@ -266,8 +268,10 @@ def v_emit_bias(S: Tensor) -> Tensor:
     S = _c(S)
     _chk(S)
     V, N, co = S.shape[:3]
-    spatial = S.numel() // (V * N * co)
     Vt = torch.empty(V, N, co, dtype=S.dtype, device=S.device)
+    if Vt.numel() == 0:  # an empty shard of the output channels
+        return Vt
+    spatial = S.numel() // (V * N * co)
     with torch.cuda.device(S.device):
         st = _lib.load().vvt_v_emit_bias(_p(Vt), _p(S), V * N, co, spatial, _dt(S), _stream(S))
     _lib.check(st, "vvt_v_emit_bias")
