@@ -57,3 +57,46 @@ R = G.shape[0]
 A = G + 1e-3 * np.linalg.norm(G) * np.eye(R)
 L = np.linalg.cholesky(A)
 run(L, b, dtype=np.float32 if len(sys.argv) > 3 else np.float64)
+
+
+# ---- variant: inner solve = k cyclic sweeps of scalar two-sided Jacobi on the pair Gram (not a full eigh) ----
+def inner_sweeps_Q(H, k, tol=1e-5):
+    n = H.shape[0]; H = H.copy(); Q = np.eye(n)
+    for _ in range(k):
+        for r in range(n - 1):
+            x, y = rr(n, r)
+            p = np.minimum(x, y); q = np.maximum(x, y)
+            hpp, hqq, hpq = H[p, p], H[q, q], H[p, q]
+            need = (hpq * hpq > tol * tol * np.abs(hpp * hqq))
+            with np.errstate(all='ignore'):
+                z = (hqq - hpp) / (2 * hpq)
+                t = np.where(z >= 0, 1.0, -1.0) / (np.abs(z) + np.sqrt(1 + z * z))
+            c = 1 / np.sqrt(1 + t * t); s = t * c
+            c = np.where(need, c, 1.0); s = np.where(need, s, 0.0)
+            Rm = np.eye(n); Rm[p, p] = c; Rm[q, q] = c; Rm[p, q] = s; Rm[q, p] = -s
+            H = Rm.T @ H @ Rm; Q = Q @ Rm
+    return Q
+
+def run_inner(W, b, k, tol=1e-5, max_sweeps=24):
+    W = (W / np.linalg.norm(W)).astype(np.float32)
+    nb = W.shape[1] // b
+    for sweep in range(1, max_sweeps + 1):
+        t0 = time.time(); nrot = 0
+        for rnd in range(-1, nb - 1):
+            if rnd < 0: a = 2 * np.arange(nb // 2); bb = a + 1
+            else: a, bb = rr(nb, rnd)
+            for pa, pb in zip(a, bb):
+                cols = np.r_[pa * b + np.arange(b), pb * b + np.arange(b)]
+                P = W[:, cols]
+                H = (P.T @ P).astype(np.float64)
+                d = np.sqrt(np.maximum(np.diag(H), 1e-300))
+                C = np.abs(H) / np.outer(d, d); np.fill_diagonal(C, 0)
+                if C.max() <= tol: continue
+                nrot += 1
+                W[:, cols] = P @ inner_sweeps_Q(H, k, tol).astype(np.float32)
+        mc = maxcos(W.astype(np.float64))
+        print(f'b={b} inner={k} sweep {sweep}: pairs rotated {nrot} of {nb//2*nb}  maxcos {mc:.2e}  ({time.time()-t0:.0f}s)', flush=True)
+        if mc < tol or nrot == 0: break
+
+if len(sys.argv) > 4:
+    run_inner(L, b, int(sys.argv[4]))
