@@ -22,7 +22,6 @@ from tests.problems import (
     IDS,
     PROBLEMS,
     constant_damping,
-    keep_all,
     keep_nonzero,
     make_top_k,
 )

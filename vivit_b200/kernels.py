@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import ctypes
 import math
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import torch
 from torch import Tensor
