@@ -42,7 +42,11 @@ def main():
     md = ["# profiles — round 1", "",
           "Everything here was measured on one B200 of the pool through `gpurun` (fresh box, no clock locks; the",
           "`clocks` object of every bench line shows 1965 MHz and no throttle reason). Numbers under a profiler are",
-          "never bench values; bench values are CUDA-event timings from `bench.py`.", ""]
+          "never bench values; bench values are CUDA-event timings from `bench.py`.", "",
+          "`achieved` in the per-kernel tables is algorithmic work ÷ event time of the whole entry point (helpers and",
+          "split-K reductions included). For `v_emit_conv2d` the byte count covers the operands it reads (`S` and the",
+          "layer input) but not the factor it writes, so that figure understates the traffic; the eigensolver has no",
+          "roofline figure (latency-bound, reported in ms / sweeps / residuals next to cuSOLVER).", ""]
     for w in ("c2", "c1", "c3", "c4", "c5"):
         p = os.path.join(SRC, f"bench_{w}.json")
         if not os.path.exists(p):
