@@ -1329,6 +1329,201 @@ static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_ct
   return VVT_OK;
 }
 
+// ======================================================================================================
+// EXPERIMENTAL wide stage (VVT_SYEVJ_WIDE=1; fp32, R a multiple of 128, Cholesky variant) -- DESIGN 5.1.
+// NOT enabled by default and not yet run on a GPU (written at the end of round 1 without GPU time left).
+// Column blocks of 64 (four of the 16-column blocks of Y) are paired by the same round-robin tournament;
+// one round is three launches over ALL pairs: (1) pair Grams H = P^T P (128 x 128, split-K over the rows,
+// the generic mma.sync GEMM with panel loaders), (2) one CTA per pair runs `inner_sweeps` cyclic sweeps of
+// scalar two-sided rotations on H in shared memory and leaves the accumulated Q, (3) P <- P Q (the same
+// GEMM, in place: a CTA owns 128 rows and has read them before its epilogue writes).  A sweep moves the
+// factor R / 64 times instead of R / 16 times.  When few pairs still rotate, the 16-wide kernel above
+// finishes the job (its intra round rebuilds the diagonal-block cache first), so accuracy and the
+// convergence test stay those of the default path.  scratch/two_level_emul.py is the numpy model.
+// ======================================================================================================
+constexpr int WB = 64;       // wide block (columns)
+constexpr int WP = 2 * WB;   // pair panel
+constexpr int LDW = WP + 1;  // padded pitch of the 128 x 128 matrices in shared memory
+
+struct WidePanel {
+  float* Y;
+  int Np, nbw, round;
+  // element (row, c) of the panel [P_a | P_b] of wide pair `pair`, c in [0, 128)
+  __device__ __forceinline__ float* at(int pair, int row, int c) const {
+    int wa, wb;
+    rr_pair(nbw, round, pair, wa, wb);
+    const int w = c < WB ? wa : wb, cc = c & (WB - 1);
+    return y_ptr(Y, Np, w * (WB / OB) + cc / OB, row) + (cc & (OB - 1));
+  }
+};
+
+struct WideGramLoader {  // operand of H = P^T P: A(m, k) = P[k][m]
+  static constexpr bool kContigK = false;
+  WidePanel p;
+  __device__ __forceinline__ float operator()(int b, int64_t m, int64_t k) const {
+    return (m < WP && k < p.Np) ? *p.at(b, int(k), int(m)) : 0.f;
+  }
+};
+
+struct WideGramStore {  // raw split-K partial sums: part[split][pair][128][128]
+  float* part;
+  int pairs;
+  __device__ __forceinline__ void operator()(int b, int64_t r, int64_t c, float v, int split) const {
+    part[((int64_t(split) * pairs + b) * WP + r) * WP + c] = v;
+  }
+};
+
+struct WideApplyLoaderP {  // A(m, k) = P[m][k]
+  static constexpr bool kContigK = true;
+  WidePanel p;
+  __device__ __forceinline__ float operator()(int b, int64_t m, int64_t k) const {
+    return (m < p.Np && k < WP) ? *p.at(b, int(m), int(k)) : 0.f;
+  }
+};
+
+struct WideApplyLoaderQ {  // B(n, k) = Q[k][n]
+  static constexpr bool kContigK = false;
+  const float* Q;
+  __device__ __forceinline__ float operator()(int b, int64_t n, int64_t k) const {
+    return (n < WP && k < WP) ? Q[(int64_t(b) * WP + k) * WP + n] : 0.f;
+  }
+};
+
+struct WideApplyStore {  // in place; pairs whose Gram was already diagonal are left alone
+  WidePanel p;
+  const int* flag;
+  __device__ __forceinline__ void operator()(int b, int64_t r, int64_t c, float v, int) const {
+    if (flag[b]) *p.at(b, int(r), int(c)) = v;
+  }
+};
+
+// One CTA per pair: H = sum of the split-K partials (fixed order), symmetrised; cyclic sweeps of scalar
+// rotations (round-robin over the 128 columns, 64 disjoint rotations per round); Q to global memory.
+__global__ void __launch_bounds__(256) wide_inner_kernel(float* Q, int* flag, const float* part, int pairs, int splits,
+                                                         int inner_sweeps, JacobiScalars* sc) {
+  extern __shared__ __align__(16) unsigned char wide_smem[];
+  float(*H)[LDW] = reinterpret_cast<float(*)[LDW]>(wide_smem);
+  float(*Qs)[LDW] = reinterpret_cast<float(*)[LDW]>(wide_smem + sizeof(float) * WP * LDW);
+  __shared__ float cs[WB][2];
+  __shared__ int pq[WB][2];
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  for (int idx = tid; idx < WP * WP; idx += 256) {
+    const int r = idx / WP, c = idx % WP;
+    float sum = 0.f;
+    for (int k = 0; k < splits; ++k) sum += part[((int64_t(k) * pairs + pair) * WP + r) * WP + c];
+    H[r][c] = sum;
+    Qs[r][c] = (r == c) ? 1.f : 0.f;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < WP * WP; idx += 256) {  // the two triangles differ in the last bits
+    const int r = idx / WP, c = idx % WP;
+    if (r < c) {
+      const float m = 0.5f * (H[r][c] + H[c][r]);
+      H[r][c] = m;
+      H[c][r] = m;
+    }
+  }
+  __syncthreads();
+  const float tol2 = Eps<float>::tol * Eps<float>::tol, abs2 = Eps<float>::v * Eps<float>::v;
+  int need = 0;
+  for (int idx = tid; idx < WP * WP; idx += 256) {
+    const int r = idx / WP, c = idx % WP;
+    if (r < c && needs_rotation(H[r][r], H[c][c], H[r][c], tol2, abs2)) need = 1;
+  }
+  if (__syncthreads_or(need) == 0) {
+    if (tid == 0) flag[pair] = 0;
+    return;
+  }
+  if (tid == 0) {
+    flag[pair] = 1;
+    atomicAdd(&sc->rotations, 1ull);
+  }
+  for (int sw = 0; sw < inner_sweeps; ++sw) {
+    for (int r = 0; r < WP - 1; ++r) {
+      if (tid < WB) {
+        int x, y;
+        rr_pair(WP, r, tid, x, y);
+        const int p = min(x, y), q = max(x, y);
+        float c, s;
+        make_rotation(H[p][p], H[q][q], H[p][q], tol2, abs2, c, s);
+        cs[tid][0] = c;
+        cs[tid][1] = s;
+        pq[tid][0] = p;
+        pq[tid][1] = q;
+      }
+      __syncthreads();
+      for (int it = tid; it < WB * WP; it += 256) {  // columns p, q of H and of Q: [x_p x_q] <- [x_p x_q] R
+        const int i = it / WP, k = it % WP;
+        const float c = cs[i][0], s = cs[i][1];
+        const int p = pq[i][0], q = pq[i][1];
+        const float hp = H[k][p], hq = H[k][q];
+        H[k][p] = c * hp - s * hq;
+        H[k][q] = s * hp + c * hq;
+        const float qp = Qs[k][p], qq = Qs[k][q];
+        Qs[k][p] = c * qp - s * qq;
+        Qs[k][q] = s * qp + c * qq;
+      }
+      __syncthreads();
+      for (int it = tid; it < WB * WP; it += 256) {  // rows p, q of H: H <- R^T H
+        const int i = it / WP, k = it % WP;
+        const float c = cs[i][0], s = cs[i][1];
+        const int p = pq[i][0], q = pq[i][1];
+        const float hp = H[p][k], hq = H[q][k];
+        H[p][k] = c * hp - s * hq;
+        H[q][k] = s * hp + c * hq;
+      }
+      __syncthreads();
+    }
+  }
+  for (int idx = tid; idx < WP * WP; idx += 256) Q[int64_t(pair) * WP * WP + idx] = Qs[idx / WP][idx % WP];
+}
+
+// Runs wide sweeps on Y until few pairs still rotate (or `max_sweeps`); scratch: part (splits * pairs * 128 * 128
+// floats), Q (pairs * 128 * 128 floats), flag (pairs ints).  Returns the number of wide sweeps in *done_sweeps.
+static int wide_stage(float* Y, int Np, float* part, float* Qg, int* flag, JacobiScalars* sc, int inner_sweeps,
+                      int max_sweeps, int* done_sweeps, cudaStream_t s) {
+  const int nbw = Np / WB, pairs = nbw / 2;
+  int splits = int(vmax<int64_t>(1, vmin<int64_t>(8, ceil_div(2 * int64_t(num_sms()), pairs))));
+  const int64_t k_per_split = align_up(ceil_div(Np, splits), MmaCfg<float>::BK);
+  splits = int(ceil_div(Np, k_per_split));
+  auto gram_kern = gemm_kernel<float, WideGramLoader, WideGramLoader, WideGramStore>;
+  const size_t inner_smem = sizeof(float) * 2 * WP * LDW;
+  static bool attr_done = false;
+  if (!attr_done) {
+    VVT_TRY(check_cuda(cudaFuncSetAttribute(gram_kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(gemm_smem_bytes<float>())), "vvt_syevj(wide gram attr)"));
+    VVT_TRY(check_cuda(cudaFuncSetAttribute(wide_inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(inner_smem)), "vvt_syevj(wide inner attr)"));
+    attr_done = true;
+  }
+  int sweeps = 0;
+  while (sweeps < max_sweeps) {
+    VVT_TRY(check_cuda(cudaMemsetAsync(&sc->rotations, 0, sizeof(unsigned long long), s), "vvt_syevj(wide)"));
+    for (int round = 0; round < nbw - 1; ++round) {
+      const WidePanel panel{Y, Np, nbw, round};
+      gram_kern<<<dim3(1, unsigned(splits), unsigned(pairs)), kGemmThreads, gemm_smem_bytes<float>(), s>>>(
+          WideGramLoader{panel}, WideGramLoader{panel}, WideGramStore{part, pairs}, WP, WP, Np, 1, 0, k_per_split);
+      VVT_TRY(launched("vvt_syevj(wide gram)"));
+      wide_inner_kernel<<<unsigned(pairs), 256, inner_smem, s>>>(Qg, flag, part, pairs, splits, inner_sweeps, sc);
+      VVT_TRY(launched("vvt_syevj(wide inner)"));
+      VVT_TRY((launch_gemm_custom<float>(WideApplyLoaderP{panel}, WideApplyLoaderQ{Qg}, WideApplyStore{panel, flag},
+                                         int64_t(Np), int64_t(WP), int64_t(WP), int64_t(pairs), s,
+                                         "vvt_syevj(wide apply)")));
+    }
+    ++sweeps;
+    unsigned long long rot = 0;
+    VVT_TRY(check_cuda(cudaMemcpyAsync(&rot, &sc->rotations, sizeof(rot), cudaMemcpyDeviceToHost, s), "vvt_syevj(wide)"));
+    VVT_TRY(check_cuda(cudaStreamSynchronize(s), "vvt_syevj(wide)"));
+    if (getenv("VVT_SYEVJ_DEBUG"))
+      fprintf(stderr, "[vvt_syevj] wide sweep %d: %llu of %d pair visits rotated (splits %d)\n", sweeps, rot,
+              pairs * (nbw - 1), splits);
+    if (rot <= (unsigned long long)(pairs) * (nbw - 1) / 8) break;  // the 16-wide kernel finishes the tail
+  }
+  *done_sweeps = sweeps;
+  return VVT_OK;
+}
+
+
 template <typename T>
 static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char* ws, int* info, int dtype,
                       cudaStream_t s) {
@@ -1411,6 +1606,17 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   } else {
     onesided_init_kernel<T><<<init_blocks, 256, 0, s>>>(Y, Gs, R, Np, sc);
     VVT_TRY(launched("vvt_syevj(init)"));
+  }
+
+  // experimental wide stage (off unless VVT_SYEVJ_WIDE is set; see the block comment above wide_stage)
+  if constexpr (sizeof(T) == 4) {
+    static const char* wide_env = getenv("VVT_SYEVJ_WIDE");
+    if (wide_env && use_chol && Np % WP == 0 && R >= 1024) {
+      const int inner = vmax(1, atoi(wide_env));
+      int wide_sweeps = 0;
+      // scratch in regions that are idle until the gather: Tt (partials), S (Q), M (flags)
+      VVT_TRY(wide_stage((float*)Y, Np, (float*)Tt, (float*)Sm, (int*)Mm, sc, vmin(inner, 4), 16, &wide_sweeps, s));
+    }
   }
 
   // per-block dependencies between rounds (wait_blocks) or the grid-wide dependency of griddepcontrol.wait
