@@ -211,6 +211,10 @@ int vvt_center_rows(void* out, const void* g, int64_t N, int64_t D, int dtype, v
 /* T[i] *= alpha  (the N/len(subsampling) rescale at eigh.py:245-246, eigvalsh.py:218-219) */
 int vvt_scale(void* T, int64_t numel, double alpha, int dtype, void* stream);
 
+/* Y[i] += alpha * X[i]: the sum of the factors that reach a tensor used by several branches of a model,
+ * ViViTGGN.accumulate_backpropagated_quantities (vivit/extensions/secondorder/vivit/__init__.py:130-133) */
+int vvt_axpy(void* Y, const void* X, int64_t numel, double alpha, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * (3) symmetric eigensolver: parallel-order block Jacobi                    *
  * ------------------------------------------------------------------------ */

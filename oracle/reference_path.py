@@ -23,8 +23,9 @@ their published behaviour and marked ``[external]``:
 ``torch.linalg.eigh(UPLO="U")`` (same ordering and column convention).
 
 The model must be a (possibly nested) ``torch.nn.Sequential`` of supported leaf
-modules; the reference's hook machinery (``vivit/utils/hooks.py``) is replaced
-by an explicit reverse loop, which visits parameters in the same order.
+modules and branching containers (``Parallel``: every branch sees the same input,
+the outputs are summed); the reference's hook machinery (``vivit/utils/hooks.py``)
+is replaced by an explicit reverse loop, which visits parameters in the same order.
 """
 
 from __future__ import annotations
@@ -41,25 +42,37 @@ from torch import Tensor, einsum, nn
 # --------------------------------------------------------------------------
 
 
-def leaf_modules(model: nn.Module) -> List[nn.Module]:
-    """Leaves of a nested ``Sequential`` in execution order."""
+def _is_parallel(model: nn.Module) -> bool:
+    """A branching container ([BackPACK] ``custom_module.branching.Parallel`` [external]; restated for the
+    tests in ``vivit_b200.custom_module``): duck-typed so that the oracle imports nothing of the product."""
+    return hasattr(model, "branches") and hasattr(model, "merge_module")
+
+
+def forward_capture(model: nn.Module, x: Tensor, retain_grad: bool = False):
+    """Run the model, keeping every leaf's input and output (BackPACK's ``module.input0`` /
+    ``module.output`` [external]).  Records are nested like the model: ``("leaf", module, input,
+    output)`` in execution order, and ``("parallel", [records of each branch], input, output)`` for a
+    branching container whose branch outputs are summed."""
     if isinstance(model, nn.Sequential):
-        out: List[nn.Module] = []
+        records = []
         for child in model.children():
-            out += leaf_modules(child)
-        return out
-    return [model]
-
-
-def forward_capture(model: nn.Module, x: Tensor):
-    """Run the model, keeping every leaf's input and output (BackPACK's
-    ``module.input0`` / ``module.output`` [external])."""
-    records = []
-    for m in leaf_modules(model):
-        y = m(x)
-        records.append((m, x, y))
-        x = y
-    return records, x
+            recs, x = forward_capture(child, x, retain_grad)
+            records += recs
+        return records, x
+    if _is_parallel(model):
+        branches, outs = [], []
+        for branch in model.branches():
+            recs, o = forward_capture(branch, x, retain_grad)
+            branches.append(recs)
+            outs.append(o)
+        y = outs[0]
+        for o in outs[1:]:
+            y = y + o
+        return [("parallel", branches, x, y)], y
+    y = model(x)
+    if retain_grad and y.requires_grad:  # false up to the first layer with parameters
+        y.retain_grad()
+    return [("leaf", model, x, y)], y
 
 
 def _sub(t: Tensor, subsampling: Optional[Sequence[int]]) -> Tensor:
@@ -232,6 +245,20 @@ def jac_t_mat_prod(
         return mat.reshape(v, n, *inp.shape[1:])
     if isinstance(module, nn.Identity):
         return mat
+    if type(module).__name__ == "Pad" and hasattr(module, "pad"):
+        # [external] PadDerivatives: constant padding (any fill value) has a zero Jacobian on the border
+        if module.mode != "constant":
+            raise NotImplementedError("Pad: mode='constant' only")
+        res = mat
+        for i in range(len(module.pad) // 2):
+            axis = mat.dim() - 1 - i
+            res = res.narrow(axis, module.pad[2 * i], mat.shape[axis] - module.pad[2 * i] - module.pad[2 * i + 1])
+        return res
+    if type(module).__name__ == "Slicing" and hasattr(module, "slice_info"):
+        # [external] SlicingDerivatives: scatter the rows back, zeros where the slice dropped entries
+        res = torch.zeros(v, n, *inp.shape[1:], dtype=mat.dtype, device=mat.device)
+        res[(slice(None), slice(None)) + tuple(module.slice_info[1:])] = mat
+        return res
     if isinstance(module, nn.Dropout):
         if not module.training or module.p == 0.0:
             return mat
@@ -441,27 +468,17 @@ def backward_sweep(
     res.batch_size = x.shape[0]
 
     if want_grad_batch:
-        xg = x.detach()
-        acts = []
-        h = xg
-        for m in leaf_modules(model):
-            o = m(h)
-            if o.requires_grad:  # false up to the first layer with parameters
-                o.retain_grad()
-            acts.append((m, h, o))
-            h = o
+        records, h = forward_capture(model, x.detach(), retain_grad=True)
         loss = loss_fn(h, y)
         loss.backward()
-        records = [
-            (m, i.detach(), o.detach(), None if o.grad is None else o.grad.detach()) for m, i, o in acts
-        ]
         out = h.detach()
+        grads = _collect_grads(records)
         for p in model.parameters():
             p.grad = None
     else:
         with torch.no_grad():
-            recs, out = forward_capture(model, x)
-        records = [(m, i, o, None) for m, i, o in recs]
+            records, out = forward_capture(model, x)
+        grads = {}
 
     need_s = want_vivit or want_sqrt_ggn
     s = None
@@ -469,35 +486,68 @@ def backward_sweep(
         with torch.no_grad():
             s = loss_sqrt_hessian(loss_fn, out, subsampling_ggn, mc_samples, mc_state)
 
-    with torch.no_grad():
-        for module, inp, outp, gout in reversed(records):
-            inp_s = _sub(inp, subsampling_ggn)
-            out_s = _sub(outp, subsampling_ggn)
-            for name, p in _param_items(module):
-                res.order.append(p)
+    def visit(module, inp, outp, s):
+        inp, outp = inp.detach(), outp.detach()
+        inp_s = _sub(inp, subsampling_ggn)
+        for name, p in _param_items(module):
+            res.order.append(p)
+            if need_s:
+                structured = (
+                    isinstance(module, nn.Linear)
+                    and name == "weight"
+                    and not _has_additional_dims(inp)
+                )
+                if want_vivit:
+                    if structured:
+                        res.vivit[id(p)] = _linear_weight_closures(s, inp_s)
+                    else:
+                        res.vivit[id(p)] = _dense_closures(
+                            param_mjp(module, name, inp_s, s)
+                        )
+                if want_sqrt_ggn:
+                    res.sqrt_ggn[id(p)] = param_mjp(module, name, inp_s, s)
+            if want_grad_batch:
+                g = _sub(grads[id(module)], subsampling_grad)[None]
+                res.grad_batch[id(p)] = param_mjp(
+                    module, name, _sub(inp, subsampling_grad), g
+                )[0]
+
+    def sweep(records, s, first):
+        """Reverse pass over one chain; returns the factor at the chain's input.  The sum over the
+        branches of a ``parallel`` record is ``accumulate_backpropagated_quantities``
+        (``secondorder/vivit/__init__.py:130-133``)."""
+        for rec in reversed(records):
+            is_first = first and rec is records[0]
+            if rec[0] == "parallel":
+                parts = [sweep(branch, s, False) for branch in rec[1]]
                 if need_s:
-                    structured = (
-                        isinstance(module, nn.Linear)
-                        and name == "weight"
-                        and not _has_additional_dims(inp)
-                    )
-                    if want_vivit:
-                        if structured:
-                            res.vivit[id(p)] = _linear_weight_closures(s, inp_s)
-                        else:
-                            res.vivit[id(p)] = _dense_closures(
-                                param_mjp(module, name, inp_s, s)
-                            )
-                    if want_sqrt_ggn:
-                        res.sqrt_ggn[id(p)] = param_mjp(module, name, inp_s, s)
-                if want_grad_batch:
-                    g = _sub(gout, subsampling_grad)[None]
-                    res.grad_batch[id(p)] = param_mjp(
-                        module, name, _sub(inp, subsampling_grad), g
-                    )[0]
-            if need_s and module is not records[0][0]:
-                s = jac_t_mat_prod(module, inp_s, out_s, s)
+                    s = parts[0]
+                    for part in parts[1:]:
+                        s = s + part
+                continue
+            _, module, inp, outp = rec
+            visit(module, inp, outp, s)
+            if need_s and not is_first:
+                s = jac_t_mat_prod(
+                    module, _sub(inp.detach(), subsampling_ggn), _sub(outp.detach(), subsampling_ggn), s
+                )
+        return s
+
+    with torch.no_grad():
+        sweep(records, s, True)
     return res
+
+
+def _collect_grads(records) -> Dict[int, Tensor]:
+    """``d loss / d output`` of every leaf with parameters, keyed by ``id(module)``."""
+    grads: Dict[int, Tensor] = {}
+    for rec in records:
+        if rec[0] == "parallel":
+            for branch in rec[1]:
+                grads.update(_collect_grads(branch))
+        elif rec[3].grad is not None and any(True for _ in _param_items(rec[1])):
+            grads[id(rec[1])] = rec[3].grad.detach()
+    return grads
 
 
 # --------------------------------------------------------------------------

@@ -22,7 +22,7 @@ from torch import einsum
  ACT_LOGSIGMOID) = range(9)
 
 NAMES = [
-    "loss_sqrt_hessian_ce", "loss_sqrt_hessian_ce_mc", "loss_sqrt_hessian_mse", "scale_",
+    "loss_sqrt_hessian_ce", "loss_sqrt_hessian_ce_mc", "loss_sqrt_hessian_mse", "scale_", "axpy_",
     "sqrt_backprop_linear", "sqrt_backprop_conv2d", "sqrt_backprop_elementwise",
     "sqrt_backprop_maxpool2d", "sqrt_backprop_avgpool2d", "v_emit_conv2d", "v_emit_bias",
     "v_emit_linear", "gemm", "gram_dense_accum", "gram_cross_accum", "gram_linear_accum",
@@ -76,6 +76,10 @@ def loss_sqrt_hessian_mse(n_sub, C, scale, like):
 
 def scale_(t, alpha):
     return t.mul_(alpha)
+
+
+def axpy_(y, x, alpha=1.0):
+    return y.add_(x, alpha=alpha)
 
 
 def center_rows(g, inplace=False):

@@ -13,6 +13,8 @@ from typing import Callable, List
 import torch
 from torch import nn
 
+from vivit_b200.custom_module import Pad, Parallel, Slicing
+
 
 @dataclass
 class Problem:
@@ -193,6 +195,24 @@ PROBLEMS: List[Problem] = [
         lambda: _eval_mode(nn.Sequential(nn.Linear(2, 3), nn.BatchNorm3d(num_features=3), nn.Sigmoid(), nn.Flatten())),
         lambda: nn.MSELoss(),
         lambda: torch.rand(3, 4 * 1 * 3 * 3),
+    ),
+    # test/settings.py:160-181 -- branched model: skip connection around Linear -> Slicing, behind a Pad
+    Problem(
+        "branching-linear-slicing-pad",
+        lambda: torch.rand(3, 7),
+        lambda: nn.Sequential(
+            nn.Linear(7, 4),
+            nn.ReLU(),
+            Pad((1, 1), mode="constant", value=0.5),
+            Parallel(
+                nn.Identity(),
+                nn.Sequential(nn.Linear(6, 8), Slicing((slice(None), slice(0, 6)))),
+            ),
+            nn.Sigmoid(),
+            nn.Linear(6, 4),
+        ),
+        lambda: nn.CrossEntropyLoss(),
+        _cls(3, 4),
     ),
 ]
 

@@ -72,6 +72,18 @@ def test_loss_factor_mse_and_scale(k, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("numel", [1, 1000 * 7, 3 * 1024 * 1024 + 5])
+def test_axpy(k, dtype, numel):
+    y, x = rnd(numel, dtype=dtype), rnd(numel, dtype=dtype, seed=1)
+    want = y.double() - 0.25 * x.double()
+    got = k.axpy_(y, x, -0.25)
+    assert got is y
+    close(got, want, dtype)
+    empty = torch.empty(0, dtype=dtype, device=dev())
+    assert k.axpy_(empty, empty.clone()).numel() == 0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("rows,n_out,n_in", [(30, 10, 32), (320, 64, 784), (1280, 256, 10), (17, 3, 5), (1, 1, 1)])
 def test_backprop_linear(k, dtype, rows, n_out, n_in):
     S, W = rnd(rows, n_out, dtype=dtype), rnd(n_out, n_in, dtype=dtype, seed=1)

@@ -33,3 +33,83 @@ def test_unsupported_module_raises():
     x, y = torch.rand(3, 4), torch.randint(0, 2, (3,))
     with pytest.raises(NotImplementedError):
         run_backward(model, nn.CrossEntropyLoss(), x, y, [SqrtGGNExact()], None)
+
+
+# ---- branched models, Pad, Slicing (vivit_b200.custom_module; reference fixture test/settings.py:160-181) ----
+
+
+def _sqrt_ggn_matches_autograd(model, loss_fn, x, y):
+    """``sum_p V_p V_p^T`` of the materialised factors against the autograd GGN."""
+    from oracle.autograd_ggn import AutogradGGN
+    from vivit_b200 import SqrtGGNExact
+
+    run_backward(model, loss_fn, x, y, [SqrtGGNExact()], None)
+    V = torch.cat([p.sqrt_ggn_exact.flatten(2) for p in model.parameters()], 2).flatten(0, 1)  # [C N, D]
+    for p in model.parameters():
+        del p.sqrt_ggn_exact
+    want = AutogradGGN(model, loss_fn, x, y).ggn()
+    assert torch.allclose(V.t() @ V, want, rtol=1e-9, atol=1e-12)
+
+
+def test_two_branches_with_parameters_and_a_shared_factor():
+    """Both branches hold parameters, one of them starts with modules that hand ``S`` through unchanged
+    (Identity, Flatten): the sum at the shared input must not write into a buffer another tensor carries."""
+    from vivit_b200.custom_module import Parallel
+
+    torch.manual_seed(1)
+    model = nn.Sequential(
+        nn.Linear(5, 6),
+        nn.Tanh(),
+        Parallel(
+            nn.Sequential(nn.Identity(), nn.Flatten(), nn.Linear(6, 4)),
+            nn.Sequential(nn.Linear(6, 4), nn.Sigmoid()),
+            nn.Linear(6, 4),
+        ),
+        Parallel(nn.Identity(), nn.Identity(), nn.Sequential(nn.Flatten(), nn.ReLU())),
+        nn.Linear(4, 3),
+    ).double()
+    x, y = torch.rand(4, 5, dtype=torch.float64), torch.randint(0, 3, (4,))
+    _sqrt_ggn_matches_autograd(model, nn.CrossEntropyLoss(), x, y)
+
+
+def test_identity_between_layers_and_repeated_backward():
+    """``nn.Identity`` returns its input object: the engine gives its output an identity of its own.
+    A second backward through a fresh forward pass starts from clean tensors."""
+    torch.manual_seed(2)
+    model = nn.Sequential(nn.Linear(5, 4), nn.Identity(), nn.ReLU(), nn.Identity(), nn.Linear(4, 3)).double()
+    x, y = torch.rand(3, 5, dtype=torch.float64), torch.randint(0, 3, (3,))
+    for _ in range(2):
+        _sqrt_ggn_matches_autograd(model, nn.CrossEntropyLoss(), x, y)
+
+
+def test_pad_and_slicing_over_feature_maps():
+    from vivit_b200.custom_module import Pad, Slicing
+
+    torch.manual_seed(3)
+    model = nn.Sequential(
+        nn.Conv2d(2, 3, 3, padding=1),
+        Pad((1, 0, 2, 1), value=-1.0),
+        nn.Sigmoid(),
+        Slicing((slice(None), slice(0, 2), slice(1, None, 2))),
+        nn.Flatten(),
+        nn.Linear(2 * 4 * 6, 3),
+    ).double()
+    x, y = torch.rand(3, 2, 5, 5, dtype=torch.float64), torch.randint(0, 3, (3,))
+    _sqrt_ggn_matches_autograd(model, nn.CrossEntropyLoss(), x, y)
+
+
+def test_pad_and_slicing_error_contract():
+    from vivit_b200 import SqrtGGNExact
+    from vivit_b200.custom_module import Pad, Slicing
+
+    x, y = torch.rand(4, 6), torch.randint(0, 2, (4,))
+    bad = [
+        nn.Sequential(nn.Linear(6, 4), Pad((1, 1), mode="reflect"), nn.Linear(6, 2)),
+        nn.Sequential(nn.Linear(6, 4), Pad((1, 1, 0, 0)), nn.Linear(6, 2)),  # would pad the batch axis
+    ]
+    for model in bad:
+        with pytest.raises(NotImplementedError):
+            run_backward(model, nn.CrossEntropyLoss(), x, y, [SqrtGGNExact()], None)
+    model = nn.Sequential(nn.Linear(6, 4), Slicing((slice(0, 4, 1), slice(0, 2))), nn.Linear(2, 2))
+    with pytest.raises(NotImplementedError):
+        run_backward(model, nn.CrossEntropyLoss(), x, y, [SqrtGGNExact()], None)

@@ -23,13 +23,14 @@ from vivit_b200.backprop import (
     disable,
     extend,
 )
-from vivit_b200 import extensions, hessianfree
+from vivit_b200 import custom_module, extensions, hessianfree
 from vivit_b200.linalg import EighComputation, EigvalshComputation
 from vivit_b200.optim import DirectionalDampedNewtonComputation, DirectionalDerivativesComputation
 
 __version__ = "0.1.0"
 
 __all__ = [
+    "custom_module",
     "extensions",
     "hessianfree",
     "EigvalshComputation",

@@ -14,7 +14,10 @@ replaces, so the protocol is re-implemented natively:
   ``loss.backward()`` when the gradient w.r.t. that output is known, i.e. in
   reverse execution order, before the module's own backward;
 * a second-order quantity travels from ``module.output`` to ``module.input0`` as a
-  tensor attribute (the same tensor object is the next module's ``output``);
+  tensor attribute (the same tensor object is the next module's ``output``); a tensor
+  consumed by several modules (branched models, ``vivit_b200.custom_module.Parallel``)
+  receives the SUM of their quantities -- its own hook fires only after autograd has
+  visited all its consumers;
 * handlers call ``vivit_b200.kernels`` (the C ABI); nothing falls back to torch
   arithmetic.
 
@@ -116,10 +119,16 @@ def _forward_hook(module, inputs, output):
         return
     for i, inp in enumerate(inputs):
         setattr(module, f"input{i}", inp)
+    aliased = isinstance(output, torch.Tensor) and any(output is inp for inp in inputs)
+    if aliased:
+        # nn.Identity hands its input through: give the output an identity of its own, so that its
+        # tensor hook and its factor attribute are not the producer's (hooks fire in registration order)
+        output = output.view_as(output)
     module.output = output
     if isinstance(output, torch.Tensor) and output.requires_grad:
         ref = weakref.ref(module)
         output.register_hook(lambda g, ref=ref: _backward_hook(ref, g))
+    return output if aliased else None
 
 
 def extend(module: nn.Module, debug: bool = False, use_converter: bool = False) -> nn.Module:

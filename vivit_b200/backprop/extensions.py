@@ -14,7 +14,8 @@ Public classes mirror what the reference hands to ``with backpack(...)``:
 Module coverage: ``CrossEntropyLoss``, ``MSELoss``, ``Linear`` (also with additional input
 dimensions), ``Conv2d``, ``BatchNorm1d/2d/3d`` (evaluation mode), ``ReLU``, ``Sigmoid``, ``Tanh``,
 ``LeakyReLU``, ``ELU``, ``SELU``, ``LogSigmoid``, ``MaxPool2d``, ``AvgPool2d``, ``ZeroPad2d``,
-``Flatten``, ``Dropout``, ``Identity``.
+``Flatten``, ``Dropout``, ``Identity``, and the branching modules of ``vivit_b200.custom_module``
+(``Parallel`` / ``SumModule``, ``Pad``, ``Slicing``).
 Anything else raises ``NotImplementedError`` (the reference's ``fail_mode="ERROR"``,
 ``__init__.py:83``).
 """
@@ -29,6 +30,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from vivit_b200 import kernels
+from vivit_b200.custom_module import Pad, Slicing, SumModule
 from vivit_b200.factors import DenseFactor, DenseGrad, Factor, LinearWeightFactor, LinearWeightGrad
 
 
@@ -122,6 +124,8 @@ class _SqrtFactorExtension(Extension):
                 "Extend the loss function too and call it on the model output."
             )
         delattr(out, self._field)
+        if hasattr(out, self._field + "_sum"):
+            delattr(out, self._field + "_sum")
         handler = _FACTOR_HANDLERS.get(type(module))
         if handler is None:
             for cls, h in _FACTOR_HANDLERS.items():
@@ -130,10 +134,33 @@ class _SqrtFactorExtension(Extension):
                     break
         if handler is None:
             self._unsupported(self, module)
+        if handler is _factor_sum:  # the only handler with several inputs
+            for idx in range(_num_inputs(module)):
+                inp = getattr(module, f"input{idx}")
+                if isinstance(inp, Tensor) and inp.requires_grad:
+                    self._pass_on(inp, S)
+            return
         need_in = isinstance(module.input0, Tensor) and module.input0.requires_grad
         S_in = handler(self, module, S, need_in)
         if need_in and S_in is not None:
-            setattr(module.input0, self._field, S_in)
+            self._pass_on(module.input0, S_in)
+
+    def _pass_on(self, inp: Tensor, S_in: Tensor) -> None:
+        """Attach the factor to the tensor it belongs to.  A tensor that feeds several modules collects
+        the sum (``accumulate_backpropagated_quantities``, ``secondorder/vivit/__init__.py:130-133``)."""
+        existing = getattr(inp, self._field, None)
+        if existing is None:
+            setattr(inp, self._field, S_in)
+            return
+        if existing.shape != S_in.shape:
+            raise RuntimeError(f"branches disagree on the factor shape: {existing.shape} vs {S_in.shape}")
+        # the first sum goes into a fresh buffer: SumModule / Identity / Flatten hand the SAME storage to
+        # several tensors, which must not see each other's contributions
+        if not getattr(inp, self._field + "_sum", False):
+            existing = existing.clone(memory_format=torch.contiguous_format)
+            setattr(inp, self._field, existing)
+            setattr(inp, self._field + "_sum", True)
+        kernels.axpy_(existing, S_in.contiguous())
 
     # ---- loss ---------------------------------------------------------------------
     def _loss_factor(self, module) -> Tensor:
@@ -313,6 +340,46 @@ def _factor_zeropad2d(ext, module: nn.ZeroPad2d, S, need_in):
     return S[..., top : h - bottom, left : w - right].contiguous()
 
 
+def _factor_pad(ext, module: Pad, S, need_in):
+    """Crop: constant padding has no derivative on the padded border, whatever the fill value
+    ([BackPACK] ``PadDerivatives``; fixture ``test/settings.py:167``)."""
+    if module.mode != "constant":
+        raise NotImplementedError("Pad is supported with mode='constant' only")
+    pad = module.pad
+    if len(pad) % 2 or len(pad) // 2 > S.dim() - 2:
+        raise NotImplementedError("Pad must pad feature dimensions only (not the batch axis)")
+    index = [slice(None)] * S.dim()
+    for i in range(len(pad) // 2):
+        axis = S.dim() - 1 - i
+        index[axis] = slice(pad[2 * i], S.shape[axis] - pad[2 * i + 1])
+    return S[tuple(index)].contiguous()
+
+
+def _factor_slicing(ext, module: Slicing, S, need_in):
+    """Embed in zeros: entries of the input that the slice drops do not reach the output
+    ([BackPACK] ``SlicingDerivatives``; fixture ``test/settings.py:171``)."""
+    info = module.slice_info
+    if len(info) == 0:
+        return S
+    if info[0] != slice(None):
+        raise NotImplementedError("Slicing must keep the batch axis whole")
+    x = module.input0
+    S_in = torch.zeros(S.shape[0], S.shape[1], *x.shape[1:], dtype=S.dtype, device=S.device)
+    S_in[(slice(None), slice(None)) + tuple(info[1:])] = S
+    return S_in
+
+
+def _factor_sum(ext, module, S, need_in):  # dispatched in _apply: every summand receives S
+    return S
+
+
+def _num_inputs(module) -> int:
+    n = 0
+    while hasattr(module, f"input{n}"):
+        n += 1
+    return n
+
+
 def _factor_dropout(ext, module: nn.Dropout, S, need_in):
     if not module.training or module.p == 0.0:
         return S
@@ -370,6 +437,9 @@ _FACTOR_HANDLERS = {
     nn.Identity: _factor_identity,
     nn.MaxPool2d: _factor_maxpool2d,
     nn.AvgPool2d: _factor_avgpool2d,
+    Pad: _factor_pad,
+    Slicing: _factor_slicing,
+    SumModule: _factor_sum,
 }
 
 

@@ -71,6 +71,11 @@ __global__ void scale_kernel(T* t, int64_t n, T alpha) {
   GRID_STRIDE(i, n) t[i] *= alpha;
 }
 
+template <typename T>
+__global__ void axpy_kernel(T* y, const T* x, int64_t n, T alpha) {
+  GRID_STRIDE(i, n) y[i] += alpha * x[i];
+}
+
 // ---- element-wise Jacobians -------------------------------------------------
 template <typename T>
 __global__ void act_kernel(T* out, const T* S, const T* ref, int64_t V, int64_t nf, int act, T scale) {
@@ -515,6 +520,16 @@ int vvt_scale(void* t, int64_t numel, double alpha, int dtype, void* stream) {
   VVT_REQUIRE(t, "null pointer");
   VVT_DISPATCH(dtype, {
     scale_kernel<T><<<ew_blocks(numel), 256, 0, as_stream(stream)>>>((T*)t, numel, T(alpha));
+    return launched(__func__);
+  });
+}
+
+int vvt_axpy(void* y, const void* x, int64_t numel, double alpha, int dtype, void* stream) {
+  VVT_REQUIRE(numel >= 0, "negative size");
+  if (numel == 0) return VVT_OK;
+  VVT_REQUIRE(y && x, "null pointer");
+  VVT_DISPATCH(dtype, {
+    axpy_kernel<T><<<ew_blocks(numel), 256, 0, as_stream(stream)>>>((T*)y, (const T*)x, numel, T(alpha));
     return launched(__func__);
   });
 }

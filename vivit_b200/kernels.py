@@ -130,6 +130,17 @@ def scale_(t: Tensor, alpha: float) -> Tensor:
     return t
 
 
+def axpy_(y: Tensor, x: Tensor, alpha: float = 1.0) -> Tensor:
+    """``y += alpha * x`` in place (both contiguous, same shape and dtype)."""
+    _chk(y, x)
+    if y.shape != x.shape or not (y.is_contiguous() and x.is_contiguous()):
+        raise ValueError("axpy_ needs contiguous tensors of one shape")
+    with torch.cuda.device(y.device):
+        st = _lib.load().vvt_axpy(_p(y), _p(x), y.numel(), float(alpha), _dt(y), _stream(y))
+    _lib.check(st, "vvt_axpy")
+    return y
+
+
 def center_rows(g: Tensor, inplace: bool = False) -> Tensor:
     """``g [N, ...] - g.mean(0)`` (per-sample gradients minus their mean); ``inplace`` overwrites ``g``."""
     if inplace and not g.is_contiguous():
