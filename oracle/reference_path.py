@@ -1,8 +1,10 @@
 """Plain-torch CPU restatement of the reference's low-rank GGN hot path.
 
-TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  Parity is pinned by
-relation to the autograd GGN (``oracle/autograd_ggn.py``), exactly the way the
-reference's own tests pin it; there are no golden files upstream.
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  Parity is pinned against
+outputs of the reference's own Computations executed in the build container
+(``tests/golden/reference_run.pt``, made by ``tests/golden/make_reference_run.py``) and by
+relation to the autograd GGN (``oracle/autograd_ggn.py``), the way the reference's own
+tests pin it; there are no golden files upstream.
 
 Every function names the reference lines (relative to ``/root/reference``) it
 follows.  BackPACK (``backpack-for-pytorch>=1.5,<2``, ``setup.cfg:36``) is an

@@ -1,0 +1,233 @@
+"""Golden vectors produced by the REFERENCE'S OWN CODE, executed in the build container.
+
+    python tests/golden/make_reference_run.py        # writes tests/golden/reference_run.pt
+
+``import vivit`` needs BackPACK (absent here) and ``Tensor.symeig`` (removed in
+torch 2).  What BackPACK contributes to this path are per-parameter TENSORS -- ``grad_batch``,
+``sqrt_ggn_exact`` -- which the reference's hooks then consume; everything after that (Gram assembly,
+rescaling, ``symeig``, filtering, gammas, lambdas, Newton coefficients, back-transformation, normalisation,
+the hook and group bookkeeping) is the reference's own code in ``vivit/{linalg,optim,utils}``.  So:
+
+* ``backpack.*`` is replaced by import stubs that carry NAMES only (a meta-path finder that fabricates
+  empty classes; ``savefield`` strings as published: ``grad_batch``, ``sqrt_ggn_exact``, ``sqrt_ggn_mc``);
+* ``Tensor.symeig(eigenvectors, upper)`` is shimmed to ``torch.linalg.eigh(UPLO=...)`` -- the replacement
+  torch's deprecation notice prescribed (same order, same column convention);
+* the per-parameter tensors are computed by plain autograd (per-sample output Jacobians; the loss
+  Hessian of each sample by double backward, factored symmetrically by ``eigh``), independently of
+  ``oracle/reference_path.py``;
+* for the two ``linalg`` classes the savefield is the dict of closures of ``base.py:94-130``, built here
+  from the reference's own ``vivit.utils.gram.pairwise_dot`` / ``mVp`` and ``vivit.utils.ggn.Vmp``;
+* then the reference's ``EigvalshComputation``, ``EighComputation``, ``DirectionalDerivativesComputation``
+  and ``DirectionalDampedNewtonComputation`` run unmodified: ``get_extension_hook(param_groups)`` is called
+  on every leaf module in reverse order, as BackPACK would, and ``get_result(group)`` is stored.
+
+Any symmetric factor of the loss Hessian gives the same GGN, hence the same eigenvalues, directional
+derivatives and Newton steps; eigenvectors are compared through projectors.  ``/root/reference`` does
+not exist on the GPU box: only the committed ``.pt`` file travels.
+"""
+
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import types
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from tests.problems import GROUPING_IDS, GROUPINGS, PROBLEMS, constant_damping, keep_nonzero, make_top_k  # noqa: E402
+
+SAVEFIELDS = {"BatchGrad": "grad_batch", "SqrtGGNExact": "sqrt_ggn_exact", "SqrtGGNMC": "sqrt_ggn_mc"}
+
+
+# ---- import stubs for backpack.* (names only) ------------------------------------------------------
+class _StubMeta(type):
+    def __getattr__(cls, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _StubMeta(name, (_Stub,), {})
+
+
+class _Stub(metaclass=_StubMeta):
+    savefield = None
+
+    def __init__(self, *args, savefield=None, subsampling=None, **kwargs):
+        if savefield is not None:
+            self.savefield = savefield
+        self._subsampling = subsampling
+
+    def get_subsampling(self):
+        return self._subsampling
+
+
+class _StubModule(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        cls = _StubMeta(name, (_Stub,), {"savefield": SAVEFIELDS.get(name)})
+        setattr(self, name, cls)
+        return cls
+
+
+class _BackpackFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path, target=None):
+        if fullname == "backpack" or fullname.startswith("backpack."):
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        module = _StubModule(spec.name)
+        module.__path__ = []
+        return module
+
+    def exec_module(self, module):
+        pass
+
+
+def _symeig(self, eigenvectors=False, upper=True):
+    uplo = "U" if upper else "L"
+    if eigenvectors:
+        return torch.linalg.eigh(self, UPLO=uplo)
+    return torch.linalg.eigvalsh(self, UPLO=uplo), torch.empty(0, dtype=self.dtype, device=self.device)
+
+
+def import_reference():
+    sys.meta_path.insert(0, _BackpackFinder())
+    torch.Tensor.symeig = _symeig  # torch 2 keeps the name only to raise the deprecation error
+    sys.path.insert(0, REFERENCE)
+    import vivit
+
+    assert os.path.realpath(vivit.__file__).startswith(REFERENCE), vivit.__file__
+    return vivit
+
+
+# ---- what BackPACK would have left on the parameters, by autograd -----------------------------------
+def per_parameter_tensors(model, loss_fn, x, y):
+    """``sqrt_ggn_exact`` ``[F, N, *p.shape]`` and ``grad_batch`` ``[N, *p.shape]`` per parameter."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    out = model(x)
+    N = out.shape[0]
+    F = out[0].numel()
+    flat = out.reshape(N, F)
+    jac = [torch.zeros(N, F, *p.shape, dtype=out.dtype) for p in params]  # d out[n, f] / d p
+    for n in range(N):
+        for f in range(F):
+            grads = torch.autograd.grad(flat[n, f], params, retain_graph=True, allow_unused=True)
+            for j, g in zip(jac, grads):
+                if g is not None:
+                    j[n, f] = g
+    o = out.detach().clone().requires_grad_(True)
+    loss = loss_fn(o, y)
+    (g_out,) = torch.autograd.grad(loss, o, create_graph=True)  # includes the 1/N of the mean
+    g_flat = g_out.reshape(N, F)
+    factors = []
+    for n in range(N):
+        rows = []
+        for f in range(F):
+            (h,) = torch.autograd.grad(g_flat[n, f], o, retain_graph=True)
+            rows.append(h.reshape(N, F)[n])
+        H = torch.stack(rows)
+        H = 0.5 * (H + H.t())
+        lam, Q = torch.linalg.eigh(H)
+        S = Q * lam.clamp(min=0.0).sqrt()  # S S^T = H_n (PSD for CE / MSE)
+        assert torch.allclose(S @ S.t(), H, atol=1e-12), "loss Hessian is not PSD?"
+        factors.append(S)
+    S = torch.stack(factors)  # [N, F(out), F(factor column)]
+    sqrt_ggn = [torch.einsum("nov,no...->vn...", S, j) for j in jac]
+    grad_batch = [torch.einsum("no,no...->n...", g_flat.detach(), j) for j in jac]
+    return params, sqrt_ggn, grad_batch
+
+
+def leaf_modules_reversed(model):
+    leaves = [m for m in model.modules() if next(m.children(), None) is None]
+    return leaves[::-1]
+
+
+def run_hook(model, x, hook):
+    for module in leaf_modules_reversed(model):
+        module.input0 = x  # only its batch size is read (linalg/utils.py:31-64)
+        hook(module)
+        del module.input0
+
+
+def main():
+    vivit = import_reference()
+    from vivit.utils.ggn import Vmp as ref_Vmp
+    from vivit.utils.gram import mVp as ref_mVp
+    from vivit.utils.gram import pairwise_dot as ref_pairwise_dot
+
+    def closures(V_t):  # the savefield of ViViTGGNExact for a materialised factor (base.py:94-130)
+        return {
+            "gram_mat": lambda: ref_pairwise_dot(V_t, start_dim=2, flatten=False),
+            "V_mat_prod": lambda mat: ref_Vmp(V_t, mat, 2),
+            "V_t_mat_prod": lambda mat: ref_mVp(V_t, mat, 2),
+        }
+
+    out = {}
+    for problem in PROBLEMS:
+        model, loss_fn, x, y = problem.make(torch.float64)
+        params, sqrt_ggn, grad_batch = per_parameter_tensors(model, loss_fn, x, y)
+        for gname, grouping in zip(GROUPING_IDS, GROUPINGS):
+            for sname, sub in (("full", None), ("sub10", [1, 0])):
+                pick = (lambda t, axis: t) if sub is None else (lambda t, axis: t.index_select(axis, torch.tensor(sub)))
+                case = {}
+
+                def attach(ggn_field=None, grad=False, as_closures=False):
+                    for p, V, g in zip(params, sqrt_ggn, grad_batch):
+                        if ggn_field is not None:
+                            V_sub = pick(V, 1).clone()
+                            setattr(p, ggn_field, closures(V_sub) if as_closures else V_sub)
+                        if grad:
+                            p.grad_batch = pick(g, 0).clone()
+
+                # -- EigvalshComputation (eigvalsh.py:79-225)
+                groups = grouping(model)
+                comp = vivit.EigvalshComputation(subsampling=sub)
+                attach(comp._savefield, as_closures=True)
+                run_hook(model, x, comp.get_extension_hook(groups))
+                case["eigvalsh"] = [comp.get_result(g).clone() for g in groups]
+
+                # -- EighComputation (eigh.py:101-275), criterion keep_nonzero (test/linalg/settings.py:23-44)
+                groups = grouping(model, criterion=keep_nonzero)
+                comp = vivit.EighComputation(subsampling=sub, warn_small_eigvals=0.0)
+                attach(comp._savefield, as_closures=True)
+                run_hook(model, x, comp.get_extension_hook(groups))
+                res = [comp.get_result(g) for g in groups]
+                case["eigh_evals"] = [r[0].clone() for r in res]
+                case["eigh_evecs"] = [torch.cat([e.flatten(1) for e in r[1]], 1) for r in res]
+
+                # -- DirectionalDerivativesComputation (directional_derivatives.py:216-353)
+                groups = grouping(model, criterion=make_top_k(10), damping=constant_damping(1.0))
+                comp = vivit.DirectionalDerivativesComputation(
+                    subsampling_grad=sub, subsampling_ggn=sub, warn_small_eigvals=0.0
+                )
+                attach("sqrt_ggn_exact", grad=True)
+                run_hook(model, x, comp.get_extension_hook(groups))
+                res = [comp.get_result(g) for g in groups]
+                case["gammas_abs"] = [r[0].abs().clone() for r in res]
+                case["lambdas"] = [r[1].clone() for r in res]
+
+                # -- DirectionalDampedNewtonComputation (directional_damped_newton.py:263-379)
+                comp = vivit.DirectionalDampedNewtonComputation(
+                    subsampling_grad=sub, subsampling_ggn=sub, warn_small_eigvals=0.0
+                )
+                attach("sqrt_ggn_exact", grad=True)
+                run_hook(model, x, comp.get_extension_hook(groups))
+                case["newton"] = [torch.cat([s.flatten() for s in comp.get_result(g)]) for g in groups]
+
+                for p in params:  # the reference's hooks delete what they consumed
+                    for field in ("sqrt_ggn_exact", "grad_batch", "vivit_ggn_exact"):
+                        assert not hasattr(p, field), field
+                out[(problem.name, gname, sname)] = case
+        print(problem.name, "done", flush=True)
+    out["__meta__"] = {"batch_sizes": {p.name: p.make()[2].shape[0] for p in PROBLEMS}, "torch": str(torch.__version__)}
+    torch.save(out, os.path.join(HERE, "reference_run.pt"))
+    print(f"wrote {len(out) - 1} cases")
+
+
+if __name__ == "__main__":
+    main()

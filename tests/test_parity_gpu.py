@@ -209,6 +209,53 @@ def test_against_committed_ground_truth(problem, dtype):
                 assert torch.allclose(step, want["newton"][i], rtol=t, atol=1e-9)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("problem", PROBLEMS, ids=IDS)
+def test_against_the_reference_run(problem, dtype):
+    """Outputs of the reference's OWN Computations, executed in the build container on these fixtures
+    (tests/golden/make_reference_run.py; tests/test_reference_run_cpu.py pins the oracle to them)."""
+    from vivit_b200 import (
+        DirectionalDampedNewtonComputation,
+        DirectionalDerivativesComputation,
+        EighComputation,
+        EigvalshComputation,
+    )
+
+    run = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_run.pt"))
+    for gname, grouping in zip(GROUPING_IDS, GROUPINGS):
+        for sname, sub in (("full", None), ("sub10", [1, 0])):
+            want = run[(problem.name, gname, sname)]
+            model, loss, x, y = problem.make(dtype, DEV)
+            groups = grouping(model)
+            comp = EigvalshComputation(subsampling=sub)
+            run_backward(model, loss, x, y, [comp.get_extension()], comp.get_extension_hook(groups))
+            for g, w in zip(groups, want["eigvalsh"]):
+                got = comp.get_result(g)
+                n = min(got.numel(), w.numel())  # another loss-Hessian factor: trailing zeros may differ
+                close(got[-n:], w[-n:], dtype, "evals vs reference run")
+            if dtype == torch.float32:
+                continue  # fp32 against these float64 vectors: eigenvalues only (as the autograd golden test)
+            groups = grouping(model, criterion=keep_nonzero)
+            comp = EighComputation(subsampling=sub, warn_small_eigvals=0.0)
+            run_backward(model, loss, x, y, comp.get_extensions(), comp.get_extension_hook(groups))
+            for g, w_evals, w_evecs in zip(groups, want["eigh_evals"], want["eigh_evecs"]):
+                evals, evecs = comp.get_result(g)
+                close(evals, w_evals, dtype, "eigh evals vs reference run")
+                flat = torch.cat([e.flatten(1) for e in evecs], 1).double().cpu()
+                assert (flat.t() @ flat - w_evecs.t() @ w_evecs).abs().max() <= 1e-7
+            groups = grouping(model, criterion=make_top_k(10), damping=constant_damping(1.0))
+            dd = DirectionalDerivativesComputation(subsampling_grad=sub, subsampling_ggn=sub, warn_small_eigvals=0.0)
+            run_backward(model, loss, x, y, dd.get_extensions(), dd.get_extension_hook(groups))
+            nw = DirectionalDampedNewtonComputation(subsampling_grad=sub, subsampling_ggn=sub, warn_small_eigvals=0.0)
+            run_backward(model, loss, x, y, nw.get_extensions(), nw.get_extension_hook(groups))
+            for i, g in enumerate(groups):
+                gam, lam = dd.get_result(g)
+                assert torch.allclose(gam.abs().cpu(), want["gammas_abs"][i], rtol=1e-6, atol=1e-9)
+                assert torch.allclose(lam.cpu(), want["lambdas"][i], rtol=1e-6, atol=1e-9)
+                step = torch.cat([s.flatten() for s in nw.get_result(g)]).cpu()
+                assert torch.allclose(step, want["newton"][i], rtol=1e-6, atol=1e-9)
+
+
 def mlp_c1():
     return nn.Sequential(nn.Linear(784, 64), nn.ReLU(), nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 10))
 

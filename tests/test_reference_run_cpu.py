@@ -1,0 +1,148 @@
+"""Pinning against outputs of the reference's OWN code.
+
+``tests/golden/reference_run.pt`` holds what f-dangel/vivit's ``EigvalshComputation``,
+``EighComputation``, ``DirectionalDerivativesComputation`` and ``DirectionalDampedNewtonComputation``
+returned when their unmodified hooks ran in the build container on every fixture of
+``tests/problems.py`` (``tests/golden/make_reference_run.py``: BackPACK's per-parameter tensors by
+autograd, import stubs for the BackPACK names, ``Tensor.symeig`` shimmed to ``linalg.eigh``).
+
+* the oracle restatement (``oracle/reference_path.py``) must reproduce them;
+* so must the shipped host code (kernel layer replaced by the test double on this CPU-only machine);
+* and the autograd ground truth of ``tests/golden/ground_truth.pt`` must agree with them.
+
+The reference factorises the loss Hessian its own way; the generator uses a symmetric ``eigh`` factor.
+Eigenvalues, directional derivatives and Newton steps do not depend on that choice, eigenvectors are
+compared through the projector onto the kept eigenspace, and the number of (numerically zero)
+trailing Gram eigenvalues may differ, so spectra are compared from the top.
+"""
+
+import os
+
+import pytest
+import torch
+
+import tests._torch_kernels as double
+from oracle import reference_path as ref
+from tests.problems import (
+    GROUPING_IDS,
+    GROUPINGS,
+    IDS,
+    PROBLEMS,
+    constant_damping,
+    keep_nonzero,
+    make_top_k,
+)
+from tests.test_host_cpu import run_backward
+
+RUN = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_run.pt"))
+TRUTH = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ground_truth.pt"))
+SUBS = [("full", None), ("sub10", [1, 0])]
+
+
+def close(got, want, tol=1e-9, what=""):
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    if want.numel():
+        scale = max(want.abs().max().item(), 1e-300)
+        err = (got - want).abs().max().item() / scale
+        assert err <= tol, f"{what}: {err:.3e} relative to the largest entry"
+
+
+def top(got, want, what):
+    n = min(got.numel(), want.numel())
+    close(got[-n:], want[-n:], what=what)
+    assert got[: got.numel() - n].abs().max().item() <= 1e-12 if got.numel() > n else True
+    assert want[: want.numel() - n].abs().max().item() <= 1e-12 if want.numel() > n else True
+
+
+def projector(evecs_flat):
+    return evecs_flat.t() @ evecs_flat
+
+
+def test_every_fixture_was_run_by_the_reference():
+    cases = {k for k in RUN if k != "__meta__"}
+    assert cases == {(p.name, g, s) for p in PROBLEMS for g in GROUPING_IDS for s, _ in SUBS}
+    assert RUN["__meta__"]["batch_sizes"] == {p.name: p.make()[2].shape[0] for p in PROBLEMS}
+
+
+@pytest.mark.parametrize("grouping,gname", list(zip(GROUPINGS, GROUPING_IDS)), ids=GROUPING_IDS)
+@pytest.mark.parametrize("sname,sub", SUBS, ids=[s for s, _ in SUBS])
+@pytest.mark.parametrize("problem", PROBLEMS, ids=IDS)
+def test_oracle_reproduces_the_reference_run(problem, sname, sub, grouping, gname):
+    want = RUN[(problem.name, gname, sname)]
+    model, loss, x, y = problem.make(torch.float64)
+
+    for got, w in zip(ref.eigvalsh(model, loss, x, y, grouping(model), subsampling=sub), want["eigvalsh"]):
+        top(got, w, "eigvalsh")
+
+    groups = grouping(model, criterion=keep_nonzero)
+    for (evals, evecs), w_evals, w_evecs in zip(
+        ref.eigh(model, loss, x, y, groups, subsampling=sub), want["eigh_evals"], want["eigh_evecs"]
+    ):
+        close(evals, w_evals, what="eigh evals")
+        flat = torch.cat([e.flatten(1) for e in evecs], 1)
+        assert (projector(flat) - projector(w_evecs)).abs().max().item() <= 1e-9
+
+    groups = grouping(model, criterion=make_top_k(10), damping=constant_damping(1.0))
+    derivs = ref.directional_derivatives(model, loss, x, y, groups, sub, sub)
+    for (gam, lam), wg, wl in zip(derivs, want["gammas_abs"], want["lambdas"]):
+        close(gam.abs(), wg, what="gammas")
+        close(lam, wl, what="lambdas")
+    steps = ref.directional_damped_newton(model, loss, x, y, groups, sub, sub)
+    for step, w in zip(steps, want["newton"]):
+        close(torch.cat([s.flatten() for s in step]), w, what="newton")
+
+
+@pytest.mark.parametrize("grouping,gname", list(zip(GROUPINGS, GROUPING_IDS)), ids=GROUPING_IDS)
+@pytest.mark.parametrize("sname,sub", SUBS, ids=[s for s, _ in SUBS])
+@pytest.mark.parametrize("problem", PROBLEMS, ids=IDS)
+def test_host_code_reproduces_the_reference_run(problem, sname, sub, grouping, gname, monkeypatch):
+    from vivit_b200 import (
+        DirectionalDampedNewtonComputation,
+        DirectionalDerivativesComputation,
+        EighComputation,
+        EigvalshComputation,
+    )
+
+    double.install(monkeypatch)
+    want = RUN[(problem.name, gname, sname)]
+    model, loss, x, y = problem.make(torch.float64)
+
+    groups = grouping(model)
+    comp = EigvalshComputation(subsampling=sub)
+    run_backward(model, loss, x, y, [comp.get_extension()], comp.get_extension_hook(groups))
+    for g, w in zip(groups, want["eigvalsh"]):
+        top(comp.get_result(g), w, "eigvalsh")
+
+    groups = grouping(model, criterion=keep_nonzero)
+    comp = EighComputation(subsampling=sub, warn_small_eigvals=0.0)
+    run_backward(model, loss, x, y, comp.get_extensions(), comp.get_extension_hook(groups))
+    for g, w_evals, w_evecs in zip(groups, want["eigh_evals"], want["eigh_evecs"]):
+        evals, evecs = comp.get_result(g)
+        close(evals, w_evals, what="eigh evals")
+        flat = torch.cat([e.flatten(1) for e in evecs], 1)
+        assert (projector(flat) - projector(w_evecs)).abs().max().item() <= 1e-9
+
+    groups = grouping(model, criterion=make_top_k(10), damping=constant_damping(1.0))
+    comp = DirectionalDerivativesComputation(subsampling_grad=sub, subsampling_ggn=sub, warn_small_eigvals=0.0)
+    run_backward(model, loss, x, y, comp.get_extensions(), comp.get_extension_hook(groups))
+    for g, wg, wl in zip(groups, want["gammas_abs"], want["lambdas"]):
+        gam, lam = comp.get_result(g)
+        close(gam.abs(), wg, what="gammas")
+        close(lam, wl, what="lambdas")
+    comp = DirectionalDampedNewtonComputation(subsampling_grad=sub, subsampling_ggn=sub, warn_small_eigvals=0.0)
+    run_backward(model, loss, x, y, comp.get_extensions(), comp.get_extension_hook(groups))
+    for g, w in zip(groups, want["newton"]):
+        close(torch.cat([s.flatten() for s in comp.get_result(g)]), w, what="newton")
+
+
+def test_autograd_ground_truth_agrees_with_the_reference_run():
+    for key, want in RUN.items():
+        if key == "__meta__":
+            continue
+        truth = TRUTH[key]
+        for name in ("gammas_abs", "lambdas", "newton"):
+            for got, w in zip(truth[name], want[name]):
+                close(got, w, what=f"{key} {name}")
+        for got, w in zip(truth["evals_all"], want["eigvalsh"]):
+            n = min(got.numel(), w.numel())  # GGN [D, D] against Gram [R, R]: the non-trivial part is shared
+            close(got[-n:], w[-n:], tol=1e-8, what=f"{key} spectrum")
