@@ -9,7 +9,7 @@ rescaling, ``symeig``, filtering, gammas, lambdas, Newton coefficients, back-tra
 the hook and group bookkeeping) is the reference's own code in ``vivit/{linalg,optim,utils}``.  So:
 
 * ``backpack.*`` is replaced by import stubs that carry NAMES only (a meta-path finder that fabricates
-  empty classes; ``savefield`` strings as published: ``grad_batch``, ``sqrt_ggn_exact``, ``sqrt_ggn_mc``);
+  empty classes; ``savefield`` strings and the ``LossHessianStrategy`` constants as published);
 * ``Tensor.symeig(eigenvectors, upper)`` is shimmed to ``torch.linalg.eigh(UPLO=...)`` -- the replacement
   torch's deprecation notice prescribed (same order, same column convention);
 * the per-parameter tensors are computed by plain autograd (per-sample output Jacobians; the loss
@@ -19,7 +19,11 @@ the hook and group bookkeeping) is the reference's own code in ``vivit/{linalg,o
   from the reference's own ``vivit.utils.gram.pairwise_dot`` / ``mVp`` and ``vivit.utils.ggn.Vmp``;
 * then the reference's ``EigvalshComputation``, ``EighComputation``, ``DirectionalDerivativesComputation``
   and ``DirectionalDampedNewtonComputation`` run unmodified: ``get_extension_hook(param_groups)`` is called
-  on every leaf module in reverse order, as BackPACK would, and ``get_result(group)`` is stored.
+  on every leaf module in reverse order, as BackPACK would, and ``get_result(group)`` is stored;
+* the extension hooks of ``vivit.extensions.hooks`` (``GramBatchGrad``, ``CenteredGramBatchGrad``,
+  ``CenteredBatchGrad``, ``GramSqrtGGNExact``) run the same way on the full batch (``"__gram_hooks__"``);
+* ``vivit/hessianfree/lanczos.py`` and ``utils.py`` need no BackPACK: they run on a seeded dense symmetric
+  matrix with ``numpy.random.seed`` fixed and explicit spectrum boundaries (``"__lanczos__"``).
 
 Any symmetric factor of the loss Hessian gives the same GGN, hence the same eigenvalues, directional
 derivatives and Newton steps; eigenvectors are compared through projectors.  ``/root/reference`` does
@@ -68,7 +72,10 @@ class _StubModule(types.ModuleType):
     def __getattr__(self, name):
         if name.startswith("__"):
             raise AttributeError(name)
-        cls = _StubMeta(name, (_Stub,), {"savefield": SAVEFIELDS.get(name)})
+        attrs = {"savefield": SAVEFIELDS.get(name)}
+        if name == "LossHessianStrategy":  # published string constants of backpack.extensions.secondorder.hbp
+            attrs.update(EXACT="exact", SAMPLING="sampling", SUMMARY="summary")
+        cls = _StubMeta(name, (_Stub,), attrs)
         setattr(self, name, cls)
         return cls
 
@@ -154,6 +161,93 @@ def run_hook(model, x, hook):
         del module.input0
 
 
+def gram_hooks(vivit):
+    """``vivit.extensions.hooks`` on the full batch of every problem (gram_batch_grad.py:7-213,
+    gram_sqrt_ggn.py:9-142)."""
+    from vivit.extensions import hooks as ref_hooks
+
+    out = {}
+    for problem in PROBLEMS:
+        model, loss_fn, x, y = problem.make(torch.float64)
+        params, sqrt_ggn, grad_batch = per_parameter_tensors(model, loss_fn, x, y)
+        case = {}
+        for name, cls in (("gram", ref_hooks.GramBatchGrad), ("centered_gram", ref_hooks.CenteredGramBatchGrad)):
+            for p, g in zip(params, grad_batch):
+                p.grad_batch = g.clone()
+            hook = cls(layerwise=True, free_grad_batch=True)
+            for module in leaf_modules_reversed(model):
+                hook(module)
+            case[name] = hook.get_result().clone()
+            case[name + "_layerwise"] = [getattr(p, hook.savefield).clone() for p in params]
+            for p in params:
+                assert not hasattr(p, "grad_batch")
+                delattr(p, hook.savefield)
+        for p, g in zip(params, grad_batch):
+            p.grad_batch = g.clone()
+        hook = ref_hooks.CenteredBatchGrad()
+        for module in leaf_modules_reversed(model):
+            hook(module)
+        case["centered_grad_batch"] = [getattr(p, hook.savefield).clone() for p in params]
+        for p, V in zip(params, sqrt_ggn):
+            delattr(p, hook.savefield)
+            del p.grad_batch
+            p.sqrt_ggn_exact = V.clone()
+        hook = ref_hooks.GramSqrtGGNExact(free_sqrt_ggn=True)
+        for module in leaf_modules_reversed(model):
+            hook(module)
+        # the Gram matrix depends on the loss-Hessian factor through an orthogonal change of basis per
+        # sample: its spectrum does not
+        case["gram_sqrt_ggn_evals"] = torch.linalg.eigvalsh(hook.get_result())
+        out[problem.name] = case
+    return out
+
+
+def lanczos_vectors():
+    """``vivit/hessianfree/lanczos.py:13-270`` and ``utils.py:7-57`` on a fixed symmetric matrix."""
+    import importlib.util
+
+    import numpy as np
+    from scipy.sparse.linalg import aslinearoperator
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location("ref_" + name, f"{REFERENCE}/vivit/hessianfree/{name}.py")
+        module = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(module)
+        return module
+
+    lanczos, utils = load("lanczos"), load("utils")
+    rng = np.random.RandomState(0)
+    B = rng.randn(48, 48)
+    A = B @ B.T / 48 - 0.3 * np.eye(48)
+    evals = np.linalg.eigvalsh(A)
+    op = aslinearoperator(A)
+    out = {"A": torch.from_numpy(A), "seed": 1}
+    calls = {
+        "fast_lanczos": dict(ncv=14),
+        "fast_lanczos_tridiagonal": dict(ncv=14, use_eigh_tridiagonal=True),
+        "lanczos_approximate_spectrum": dict(
+            ncv=16, num_points=64, num_repeats=3, kappa=3.0, boundaries=(float(evals[0]), float(evals[-1]))
+        ),
+        "lanczos_approximate_log_spectrum": dict(
+            ncv=16, num_points=64, num_repeats=3, kappa=1.04,
+            boundaries=(float(np.abs(evals).min()), float(np.abs(evals).max())),
+        ),
+    }
+    for name, kwargs in calls.items():
+        np.random.seed(out["seed"])
+        fn = getattr(lanczos, "fast_lanczos" if name.startswith("fast_lanczos") else name)
+        res = fn(op, **kwargs)
+        out[name] = {"kwargs": kwargs, "result": [torch.from_numpy(np.asarray(r, dtype=np.float64).copy()) for r in res]}
+    c, V = rng.rand(5), np.linalg.qr(rng.randn(48, 5))[0]
+    probe = rng.randn(48)
+    out["low_rank"] = {
+        "c": torch.from_numpy(c), "A": torch.from_numpy(V), "x": torch.from_numpy(probe),
+        "LowRank": torch.from_numpy(utils.LowRank(c, V) @ probe),
+        "Projector": torch.from_numpy(utils.Projector(V) @ probe),
+    }
+    return out
+
+
 def main():
     vivit = import_reference()
     from vivit.utils.ggn import Vmp as ref_Vmp
@@ -224,9 +318,11 @@ def main():
                         assert not hasattr(p, field), field
                 out[(problem.name, gname, sname)] = case
         print(problem.name, "done", flush=True)
+    out["__gram_hooks__"] = gram_hooks(vivit)
+    out["__lanczos__"] = lanczos_vectors()
     out["__meta__"] = {"batch_sizes": {p.name: p.make()[2].shape[0] for p in PROBLEMS}, "torch": str(torch.__version__)}
     torch.save(out, os.path.join(HERE, "reference_run.pt"))
-    print(f"wrote {len(out) - 1} cases")
+    print(f"wrote {len(out) - 3} cases + gram hooks + lanczos")
 
 
 if __name__ == "__main__":
