@@ -22,6 +22,9 @@ the hook and group bookkeeping) is the reference's own code in ``vivit/{linalg,o
   on every leaf module in reverse order, as BackPACK would, and ``get_result(group)`` is stored;
 * the extension hooks of ``vivit.extensions.hooks`` (``GramBatchGrad``, ``CenteredGramBatchGrad``,
   ``CenteredBatchGrad``, ``GramSqrtGGNExact``) run the same way on the full batch (``"__gram_hooks__"``);
+* ``ViViTGGNLinear.weight`` (``linear.py:29-81``), the structured closures of a Linear weight, runs on
+  seeded tensors (``"__linear_closures__"``; ``backpack.utils.subsampling.subsample`` is the one helper
+  given a body: keep the listed samples);
 * ``vivit/hessianfree/lanczos.py`` and ``utils.py`` need no BackPACK: they run on a seeded dense symmetric
   matrix with ``numpy.random.seed`` fixed and explicit spectrum boundaries (``"__lanczos__"``).
 
@@ -80,6 +83,13 @@ class _StubModule(types.ModuleType):
         return cls
 
 
+def _subsample(tensor, dim=0, subsampling=None):
+    """``backpack.utils.subsampling.subsample`` as published: keep the listed entries along ``dim``."""
+    if subsampling is None:
+        return tensor
+    return tensor.index_select(dim, torch.tensor(subsampling, device=tensor.device))
+
+
 class _BackpackFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
     def find_spec(self, fullname, path, target=None):
         if fullname == "backpack" or fullname.startswith("backpack."):
@@ -89,6 +99,8 @@ class _BackpackFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
     def create_module(self, spec):
         module = _StubModule(spec.name)
         module.__path__ = []
+        if spec.name == "backpack.utils.subsampling":
+            module.subsample = _subsample  # the one BackPACK helper the structured Linear path calls
         return module
 
     def exec_module(self, module):
@@ -199,6 +211,32 @@ def gram_hooks(vivit):
         # sample: its spectrum does not
         case["gram_sqrt_ggn_evals"] = torch.linalg.eigvalsh(hook.get_result())
         out[problem.name] = case
+    return out
+
+
+def linear_closures():
+    """The structured closures of ``ViViTGGNLinear.weight`` (``linear.py:29-81``) on seeded tensors, with and
+    without sub-sampling.  ``derivatives._get_additional_dims`` (BackPACK) is told there are none."""
+    from vivit.extensions.secondorder.vivit.linear import ViViTGGNLinear
+
+    ext_module = ViViTGGNLinear()
+    ext_module.derivatives = types.SimpleNamespace(_get_additional_dims=lambda module: ())
+    out = []
+    gen = torch.Generator().manual_seed(0)
+    for C, N, n_out, n_in, sub in ((3, 4, 5, 6, None), (2, 5, 3, 4, [2, 0, 4]), (10, 7, 10, 33, None)):
+        n_sub = N if sub is None else len(sub)
+        s = torch.randn(C, n_sub, n_out, generator=gen, dtype=torch.float64)
+        x = torch.randn(N, n_in, generator=gen, dtype=torch.float64)
+        mat_v = torch.randn(2, C, n_sub, generator=gen, dtype=torch.float64)
+        mat_vt = torch.randn(2, n_out, n_in, generator=gen, dtype=torch.float64)
+        module = types.SimpleNamespace(input0=x)
+        ext = types.SimpleNamespace(get_subsampling=lambda sub=sub: sub)
+        fns = ext_module.weight(ext, module, None, None, s)
+        out.append({
+            "s": s, "input0": x, "subsampling": sub, "mat_v": mat_v, "mat_vt": mat_vt,
+            "gram_mat": fns["gram_mat"](), "V_mat_prod": fns["V_mat_prod"](mat_v),
+            "V_t_mat_prod": fns["V_t_mat_prod"](mat_vt),
+        })
     return out
 
 
@@ -320,9 +358,10 @@ def main():
         print(problem.name, "done", flush=True)
     out["__gram_hooks__"] = gram_hooks(vivit)
     out["__lanczos__"] = lanczos_vectors()
+    out["__linear_closures__"] = linear_closures()
     out["__meta__"] = {"batch_sizes": {p.name: p.make()[2].shape[0] for p in PROBLEMS}, "torch": str(torch.__version__)}
     torch.save(out, os.path.join(HERE, "reference_run.pt"))
-    print(f"wrote {len(out) - 3} cases + gram hooks + lanczos")
+    print(f"wrote {len(out) - 4} cases + gram hooks + lanczos + linear closures")
 
 
 if __name__ == "__main__":

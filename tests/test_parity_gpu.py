@@ -256,6 +256,25 @@ def test_against_the_reference_run(problem, dtype):
                 assert torch.allclose(step, want["newton"][i], rtol=1e-6, atol=1e-9)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_linear_weight_factor_against_the_reference_run(dtype):
+    """``ViViTGGNLinear.weight`` (``linear.py:29-81``) as run by the reference on seeded tensors
+    (tests/golden/make_reference_run.py) against the structured kernels behind ``LinearWeightFactor``."""
+    from vivit_b200.factors import LinearWeightFactor
+
+    run = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_run.pt"))
+    for case in run["__linear_closures__"]:
+        s, x, sub = case["s"], case["input0"], case["subsampling"]
+        z = x if sub is None else x[sub]
+        factor = LinearWeightFactor(s.to(DEV, dtype).contiguous(), z.to(DEV, dtype).contiguous())
+        mat_v, mat_vt = case["mat_v"].to(DEV, dtype), case["mat_vt"].to(DEV, dtype)
+        close(factor.gram_mat().reshape(case["gram_mat"].shape), case["gram_mat"], dtype, "gram_mat")
+        got = factor.backtransform(mat_v.reshape(mat_v.shape[0], -1).contiguous(), None)
+        close(got.reshape(case["V_mat_prod"].shape), case["V_mat_prod"], dtype, "V_mat_prod")
+        got = factor.vt_mat_prod(mat_vt.contiguous())
+        close(got.reshape(case["V_t_mat_prod"].shape), case["V_t_mat_prod"], dtype, "V_t_mat_prod")
+
+
 def mlp_c1():
     return nn.Sequential(nn.Linear(784, 64), nn.ReLU(), nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 10))
 

@@ -236,3 +236,27 @@ def test_lanczos_functions_reproduce_the_reference_run():
     c, A, x = lr["c"].numpy(), lr["A"].numpy(), lr["x"].numpy()
     close(torch.from_numpy(LowRank(c, A) @ x), lr["LowRank"], what="LowRank")
     close(torch.from_numpy(Projector(A) @ x), lr["Projector"], what="Projector")
+
+
+# ---- structured closures of a Linear weight ------------------------------------------
+
+
+def test_linear_weight_closures_reproduce_the_reference_run(monkeypatch):
+    """``ViViTGGNLinear.weight`` (``linear.py:29-81``) run by the reference on seeded tensors: the oracle's
+    closures and the product's ``LinearWeightFactor`` (kernels replaced by the test double here; the GPU
+    twin is ``test_parity_gpu.py::test_linear_weight_factor_against_the_reference_run``)."""
+    from vivit_b200.factors import LinearWeightFactor
+
+    double.install(monkeypatch)
+    for case in RUN["__linear_closures__"]:
+        s, x, sub = case["s"], case["input0"], case["subsampling"]
+        z = x if sub is None else x[sub]
+        fns = ref._linear_weight_closures(s, z)
+        factor = LinearWeightFactor(s.contiguous(), z.contiguous())
+        mat_v, mat_vt = case["mat_v"], case["mat_vt"]
+        for got in (fns["gram_mat"](), factor.gram_mat()):
+            close(got.reshape(case["gram_mat"].shape), case["gram_mat"], what="gram_mat")
+        for got in (fns["V_mat_prod"](mat_v), factor.backtransform(mat_v.reshape(mat_v.shape[0], -1), None)):
+            close(got.reshape(case["V_mat_prod"].shape), case["V_mat_prod"], what="V_mat_prod")
+        for got in (fns["V_t_mat_prod"](mat_vt), factor.vt_mat_prod(mat_vt)):
+            close(got.reshape(case["V_t_mat_prod"].shape), case["V_t_mat_prod"], what="V_t_mat_prod")
