@@ -471,6 +471,18 @@ class SqrtGGNMC(_SqrtFactorExtension):
         super().__init__("sqrt_ggn_mc", subsampling, mc_samples, lazy=lazy, closures=False)
 
 
+_FACTOR_FAMILIES = {"vivit": (ViViTGGNExact, ViViTGGNMC), "sqrt_ggn": (SqrtGGNExact, SqrtGGNMC)}
+
+
+def factor_extension(family: str, subsampling: Optional[List[int]], mc_samples: int, **kwargs):
+    """The exact member of an extension family when ``mc_samples`` is zero, its Monte-Carlo member
+    otherwise (the switch of ``vivit/linalg/utils.py:11-28`` and ``vivit/optim/utils.py:8-25``)."""
+    exact, sampled = _FACTOR_FAMILIES[family]
+    if mc_samples:
+        return sampled(mc_samples=mc_samples, subsampling=subsampling, **kwargs)
+    return exact(subsampling=subsampling, **kwargs)
+
+
 # --------------------------------------------------------------------------
 # first-order: per-sample gradients
 # --------------------------------------------------------------------------

@@ -2,26 +2,20 @@
 
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Union
+from typing import Callable, Dict, List, Optional
 
 import torch
 from torch import Tensor
 from torch.nn import Module
 
 from vivit_b200 import kernels
-from vivit_b200.backprop.extensions import ViViTGGNExact, ViViTGGNMC
+from vivit_b200.backprop.extensions import factor_extension
 
 
-def get_vivit_extension(
-    subsampling: Union[None, List[int]], mc_samples: int, shard=None
-) -> Union[ViViTGGNMC, ViViTGGNExact]:
-    """``ViViTGGNExact`` for ``mc_samples == 0`` else ``ViViTGGNMC``
-    (``vivit/linalg/utils.py:11-28``)."""
-    ext = (
-        ViViTGGNExact(subsampling=subsampling)
-        if mc_samples == 0
-        else ViViTGGNMC(subsampling=subsampling, mc_samples=mc_samples)
-    )
+def get_vivit_extension(subsampling, mc_samples, shard=None):
+    """``ViViTGGNExact`` / ``ViViTGGNMC`` by ``mc_samples`` (``vivit/linalg/utils.py:11-28``); ``shard`` =
+    ``(rank, world)`` restricts every parameter to this rank's dim-0 slice (``vivit_b200.dist``)."""
+    ext = factor_extension("vivit", subsampling, mc_samples)
     ext._shard = shard
     return ext
 
