@@ -1,6 +1,10 @@
-"""Directional derivatives and damped Newton steps along GGN eigenvectors."""
+"""Per-sample directional derivatives along the leading GGN eigenvectors, and the damped Newton step
+assembled from them."""
 
-from vivit_b200.optim.directional_damped_newton import DirectionalDampedNewtonComputation
-from vivit_b200.optim.directional_derivatives import DirectionalDerivativesComputation
+from vivit_b200.optim import directional_damped_newton as _newton
+from vivit_b200.optim import directional_derivatives as _derivatives
 
-__all__ = ["DirectionalDampedNewtonComputation", "DirectionalDerivativesComputation"]
+DirectionalDerivativesComputation = _derivatives.DirectionalDerivativesComputation
+DirectionalDampedNewtonComputation = _newton.DirectionalDampedNewtonComputation
+
+__all__ = ["DirectionalDerivativesComputation", "DirectionalDampedNewtonComputation"]
