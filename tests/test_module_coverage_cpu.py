@@ -113,3 +113,18 @@ def test_pad_and_slicing_error_contract():
     model = nn.Sequential(nn.Linear(6, 4), Slicing((slice(0, 4, 1), slice(0, 2))), nn.Linear(2, 2))
     with pytest.raises(NotImplementedError):
         run_backward(model, nn.CrossEntropyLoss(), x, y, [SqrtGGNExact()], None)
+
+
+def test_inplace_activation_returns_its_input_object():
+    """``ReLU(inplace=True)`` hands back the tensor it was given, like ``Identity``: factors and per-sample
+    gradients still match autograd."""
+    from oracle.autograd_ggn import AutogradGGN
+    from vivit_b200 import BatchGrad
+
+    torch.manual_seed(4)
+    model = nn.Sequential(nn.Linear(5, 4), nn.ReLU(inplace=True), nn.Linear(4, 3)).double()
+    x, y = torch.rand(3, 5, dtype=torch.float64), torch.randint(0, 3, (3,))
+    _sqrt_ggn_matches_autograd(model, nn.CrossEntropyLoss(), x, y)
+    run_backward(model, nn.CrossEntropyLoss(), x, y, [BatchGrad()], None)
+    got = torch.cat([p.grad_batch.flatten(1) for p in model.parameters()], 1)
+    assert torch.allclose(got, AutogradGGN(model, nn.CrossEntropyLoss(), x, y).batch_grad(), rtol=1e-10, atol=1e-13)
