@@ -247,6 +247,8 @@ def jac_t_mat_prod(
         return mat.reshape(v, n, *inp.shape[1:])
     if isinstance(module, nn.Identity):
         return mat
+    if type(module).__name__ == "ScaleModule" and isinstance(getattr(module, "weight", None), float):
+        return mat * module.weight  # [external] ScaleModuleDerivatives
     if type(module).__name__ == "Pad" and hasattr(module, "pad"):
         # [external] PadDerivatives: constant padding (any fill value) has a zero Jacobian on the border
         if module.mode != "constant":

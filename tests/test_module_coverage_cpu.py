@@ -128,3 +128,24 @@ def test_inplace_activation_returns_its_input_object():
     run_backward(model, nn.CrossEntropyLoss(), x, y, [BatchGrad()], None)
     got = torch.cat([p.grad_batch.flatten(1) for p in model.parameters()], 1)
     assert torch.allclose(got, AutogradGGN(model, nn.CrossEntropyLoss(), x, y).batch_grad(), rtol=1e-10, atol=1e-13)
+
+
+def test_scale_module_in_a_weighted_skip_connection():
+    """``ScaleModule`` ([BackPACK] maps it and ``Identity`` to the same handler, ``__init__.py:118-119``):
+    host code against autograd, oracle against autograd."""
+    from oracle import reference_path as ref
+    from oracle.autograd_ggn import AutogradGGN
+    from vivit_b200.custom_module import Parallel, ScaleModule
+
+    torch.manual_seed(5)
+    model = nn.Sequential(
+        nn.Linear(5, 4),
+        Parallel(ScaleModule(0.5), nn.Sequential(nn.Linear(4, 4), nn.Tanh(), ScaleModule(-2.0)), ScaleModule()),
+        nn.Linear(4, 3),
+    ).double()
+    x, y = torch.rand(4, 5, dtype=torch.float64), torch.randint(0, 3, (4,))
+    _sqrt_ggn_matches_autograd(model, nn.CrossEntropyLoss(), x, y)
+    gram, _ = ref.gram_sqrt_ggn(model, nn.CrossEntropyLoss(), x, y)
+    ggn = AutogradGGN(model, nn.CrossEntropyLoss(), x, y).ggn()
+    n = min(gram.shape[0], ggn.shape[0])
+    assert torch.allclose(torch.linalg.eigvalsh(gram)[-n:], torch.linalg.eigvalsh(ggn)[-n:], rtol=1e-8, atol=1e-12)

@@ -15,7 +15,7 @@ Module coverage: ``CrossEntropyLoss``, ``MSELoss``, ``Linear`` (also with additi
 dimensions), ``Conv2d``, ``BatchNorm1d/2d/3d`` (evaluation mode), ``ReLU``, ``Sigmoid``, ``Tanh``,
 ``LeakyReLU``, ``ELU``, ``SELU``, ``LogSigmoid``, ``MaxPool2d``, ``AvgPool2d``, ``ZeroPad2d``,
 ``Flatten``, ``Dropout``, ``Identity``, and the branching modules of ``vivit_b200.custom_module``
-(``Parallel`` / ``SumModule``, ``Pad``, ``Slicing``).
+(``Parallel`` / ``SumModule``, ``ScaleModule``, ``Pad``, ``Slicing``).
 Anything else raises ``NotImplementedError`` (the reference's ``fail_mode="ERROR"``,
 ``__init__.py:83``).
 """
@@ -30,7 +30,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from vivit_b200 import kernels
-from vivit_b200.custom_module import Pad, Slicing, SumModule
+from vivit_b200.custom_module import Pad, ScaleModule, Slicing, SumModule
 from vivit_b200.factors import DenseFactor, DenseGrad, Factor, LinearWeightFactor, LinearWeightGrad
 
 
@@ -369,6 +369,13 @@ def _factor_slicing(ext, module: Slicing, S, need_in):
     return S_in
 
 
+def _factor_scale(ext, module: ScaleModule, S, need_in):
+    """``d (w x) / dx = w I`` ([BackPACK] ``ScaleModuleDerivatives``)."""
+    if not need_in or module.weight == 1.0:
+        return S if need_in else None
+    return kernels.scale_(S.clone(memory_format=torch.contiguous_format), module.weight)
+
+
 def _factor_sum(ext, module, S, need_in):  # dispatched in _apply: every summand receives S
     return S
 
@@ -438,6 +445,7 @@ _FACTOR_HANDLERS = {
     nn.MaxPool2d: _factor_maxpool2d,
     nn.AvgPool2d: _factor_avgpool2d,
     Pad: _factor_pad,
+    ScaleModule: _factor_scale,
     Slicing: _factor_slicing,
     SumModule: _factor_sum,
 }

@@ -5,6 +5,7 @@ last fixture (``test/settings.py:160-181``, a skip connection around ``Linear ->
 behind a ``Pad``) is built from them.  They are ordinary ``torch.nn`` modules; the factor
 back-propagation through them lives in ``vivit_b200.backprop.extensions``:
 
+* ``ScaleModule`` -- the factor is scaled by the same constant;
 * ``SumModule``   -- the factor reaches every summand unchanged;
 * ``Parallel``    -- container: every branch sees the same input, the outputs are merged
   (summed); the input's factor is the SUM of the branches' factors
@@ -19,6 +20,22 @@ from typing import Sequence, Tuple, Union
 
 import torch.nn.functional as F
 from torch import Tensor, nn
+
+
+class ScaleModule(nn.Module):
+    """Multiply the input by a constant ([BackPACK] ``custom_module.scale_module.ScaleModule``)."""
+
+    def __init__(self, weight: float = 1.0):
+        super().__init__()
+        if not isinstance(weight, (int, float)):
+            raise ValueError(f"weight must be a number, got {type(weight)}")
+        self.weight = float(weight)
+
+    def forward(self, input: Tensor) -> Tensor:
+        return input * self.weight
+
+    def extra_repr(self) -> str:
+        return f"weight={self.weight}"
 
 
 class SumModule(nn.Module):
