@@ -275,6 +275,23 @@ def test_linear_weight_factor_against_the_reference_run(dtype):
         close(got.reshape(case["V_t_mat_prod"].shape), case["V_t_mat_prod"], dtype, "V_t_mat_prod")
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name", ["mlp", "cnn"])
+def test_empirical_ntk_use_case(name, dtype):
+    """``example_ntk_functorch.py:140-190``: the NTK from ``vivit_ggn_exact["gram_mat"]()`` accumulated in
+    an extension hook, against autograd Jacobians (float64 on the CPU, same weights)."""
+    from tests.test_ntk_cpu import NETS, autograd_ntk, empirical_ntk
+
+    torch.manual_seed(0)
+    make_net, make_x = NETS[name]
+    cnet = make_net().to(dtype)
+    x1, x2 = make_x(3).to(dtype), make_x(4).to(dtype)
+    gnet = copy.deepcopy(cnet).to(DEV)
+    got = empirical_ntk(gnet, x1.to(DEV), x2.to(DEV))
+    want = autograd_ntk(copy.deepcopy(cnet).double(), x1.double(), x2.double())
+    close(got, want, dtype, "ntk")
+
+
 def mlp_c1():
     return nn.Sequential(nn.Linear(784, 64), nn.ReLU(), nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 10))
 
