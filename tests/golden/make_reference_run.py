@@ -25,6 +25,8 @@ the hook and group bookkeeping) is the reference's own code in ``vivit/{linalg,o
 * ``ViViTGGNLinear.weight`` (``linear.py:29-81``), the structured closures of a Linear weight, runs on
   seeded tensors (``"__linear_closures__"``; ``backpack.utils.subsampling.subsample`` is the one helper
   given a body: keep the listed samples);
+* ``vivit/utils/eig.py`` (``symeig_psd``, ``symeig`` with its zero-eigenvalue filter, ``shift_diag``) runs on the
+  matrices of the reference's ``test_stable_symeig.py`` and on a rank-deficient Gram matrix (``"__eig_utils__"``);
 * ``vivit/hessianfree/lanczos.py`` and ``utils.py`` need no BackPACK: they run on a seeded dense symmetric
   matrix with ``numpy.random.seed`` fixed and explicit spectrum boundaries (``"__lanczos__"``).
 
@@ -240,6 +242,34 @@ def linear_closures():
     return out
 
 
+def eig_utils():
+    """``vivit/utils/eig.py:6-134`` (``symeig_psd``, ``symeig``, ``remove_zero_evals``, ``shift_diag``) on the
+    matrices of ``test/utils/test_stable_symeig.py:9-24`` and on a seeded rank-deficient Gram matrix."""
+    from vivit.utils import eig as ref_eig
+
+    gen = torch.Generator().manual_seed(0)
+    B = torch.randn(12, 5, generator=gen, dtype=torch.float64)
+    mats = {
+        "diagonal": torch.diag(torch.tensor([1.1, 2.2, 9.9], dtype=torch.float64)),
+        "dense": torch.tensor([[1.1, 2.2, 3.3], [4.4, 5.5, 6.6], [7.7, 8.8, 2.2]], dtype=torch.float64),
+        "low_rank": B @ B.t(),
+    }
+    out = {}
+    for name, A in mats.items():
+        case = {"A": A}
+        for upper in (True, False):
+            for shift in (0.0, 0.1, 10.0):
+                case[("symeig_psd", upper, shift)] = ref_eig.symeig_psd(
+                    A.clone(), eigenvectors=True, upper=upper, shift=shift, shift_inplace=False
+                )
+            case[("symeig", upper)] = ref_eig.symeig(A.clone(), eigenvectors=True, upper=upper)
+            case[("symeig_values_only", upper)] = ref_eig.symeig(A.clone(), eigenvectors=False, upper=upper)
+        out[name] = case
+    rect = torch.tensor([[1.0, 1.0], [2.0, 2.0], [3.0, 4.0]], dtype=torch.float64)
+    out["shift_diag_rectangular"] = {"input": rect, "shift": 1.5, "result": ref_eig.shift_diag(rect, 1.5)}
+    return out
+
+
 def lanczos_vectors():
     """``vivit/hessianfree/lanczos.py:13-270`` and ``utils.py:7-57`` on a fixed symmetric matrix."""
     import importlib.util
@@ -359,9 +389,10 @@ def main():
     out["__gram_hooks__"] = gram_hooks(vivit)
     out["__lanczos__"] = lanczos_vectors()
     out["__linear_closures__"] = linear_closures()
+    out["__eig_utils__"] = eig_utils()
     out["__meta__"] = {"batch_sizes": {p.name: p.make()[2].shape[0] for p in PROBLEMS}, "torch": str(torch.__version__)}
     torch.save(out, os.path.join(HERE, "reference_run.pt"))
-    print(f"wrote {len(out) - 4} cases + gram hooks + lanczos + linear closures")
+    print(f"wrote {len(out) - 5} cases + gram hooks + lanczos + linear closures + eig utils")
 
 
 if __name__ == "__main__":

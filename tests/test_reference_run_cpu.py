@@ -260,3 +260,66 @@ def test_linear_weight_closures_reproduce_the_reference_run(monkeypatch):
             close(got.reshape(case["V_mat_prod"].shape), case["V_mat_prod"], what="V_mat_prod")
         for got in (fns["V_t_mat_prod"](mat_vt), factor.vt_mat_prod(mat_vt)):
             close(got.reshape(case["V_t_mat_prod"].shape), case["V_t_mat_prod"], what="V_t_mat_prod")
+
+
+# ---- vivit/utils/eig.py: shifted / filtered decompositions ----------------------------
+
+
+def _same_pairs(got, want, what):
+    (evals, evecs), (w_evals, w_evecs) = got, want
+    close(evals, w_evals, what=what + " evals")
+    assert evecs.shape == w_evecs.shape, (what, evecs.shape, w_evecs.shape)
+    if w_evecs.numel():
+        # columns up to sign where the eigenvalue is simple; the numerically-zero ones span a degenerate
+        # space, compared through its projector
+        simple = w_evals.abs() > 1e-8 * w_evals.abs().max()
+        a, b = evecs[:, simple], w_evecs[:, simple]
+        close(a * torch.sign((a * b).sum(0)), b, tol=1e-8, what=what + " evecs")
+        a, b = evecs[:, ~simple], w_evecs[:, ~simple]
+        assert (a @ a.t() - b @ b.t()).abs().max().item() <= 1e-8, what + " null space"
+
+
+def test_eig_utils_reproduce_the_reference_run(monkeypatch):
+    from vivit_b200.utils import eig
+
+    double.install(monkeypatch)
+    run = RUN["__eig_utils__"]
+    for name in ("diagonal", "dense", "low_rank"):
+        case = run[name]
+        for key, want in case.items():
+            if key == "A":
+                continue
+            A = case["A"].clone()
+            if key[0] == "symeig_psd":
+                got = eig.symeig_psd(A, eigenvectors=True, upper=key[1], shift=key[2])
+            elif key[0] == "symeig":
+                got = eig.symeig(A, eigenvectors=True, upper=key[1])
+            else:
+                got = eig.symeig(A, eigenvectors=False, upper=key[1])
+                assert got[1].numel() == 0
+            _same_pairs(got, want, f"{name} {key}")
+            assert torch.equal(A, case["A"])  # the input is left alone
+    rect = run["shift_diag_rectangular"]
+    assert torch.equal(eig.shift_diag(rect["input"], rect["shift"]), rect["result"])
+    assert eig.shift_diag(rect["input"], 0.0) is rect["input"]
+
+
+def test_eig_utils_contract(monkeypatch):
+    """``test/utils/test_stable_symeig.py:49-76,102-122`` and the error contract of ``utils/eig.py``."""
+    from vivit_b200.utils import eig
+
+    double.install(monkeypatch)
+    A = RUN["__eig_utils__"]["low_rank"]["A"]
+    backup = A.clone()
+    eig.symeig_psd(A, shift=1.0, shift_inplace=False)
+    assert torch.equal(A, backup)
+    eig.symeig_psd(A, shift=1.0, shift_inplace=True)  # shifted and shifted back: equal up to rounding
+    assert torch.allclose(A, backup, atol=1e-12)
+    evals, evecs = eig.symeig(backup, eigenvectors=True)
+    assert evals.numel() == 5 and evecs.shape == (12, 5)  # rank 5: seven numerically-zero pairs dropped
+    with pytest.raises(ValueError):
+        eig.symeig_psd(torch.zeros(2, 2, 2))
+    with pytest.raises(ValueError):
+        eig.symeig(torch.zeros(4))
+    with pytest.raises(RuntimeError, match="NaN"):
+        eig.symeig(torch.full((2, 2), float("nan"), dtype=torch.float64))
