@@ -27,6 +27,8 @@ the hook and group bookkeeping) is the reference's own code in ``vivit/{linalg,o
   given a body: keep the listed samples);
 * ``vivit/utils/eig.py`` (``symeig_psd``, ``symeig`` with its zero-eigenvalue filter, ``shift_diag``) runs on the
   matrices of the reference's ``test_stable_symeig.py`` and on a rank-deficient Gram matrix (``"__eig_utils__"``);
+* ``vivit/utils/gram.py`` and ``vivit/utils/ggn.py`` (``pairwise_dot``, ``partial_contract``, ``compute_gram_mat``,
+  ``sqrt_gram_mat_prod``, ``mVp``, ``Vmp``, ``V_mat_prod`` ...) run on seeded tensors (``"__gram_utils__"``);
 * ``vivit/hessianfree/lanczos.py`` and ``utils.py`` need no BackPACK: they run on a seeded dense symmetric
   matrix with ``numpy.random.seed`` fixed and explicit spectrum boundaries (``"__lanczos__"``).
 
@@ -270,6 +272,41 @@ def eig_utils():
     return out
 
 
+def gram_utils():
+    """``vivit/utils/gram.py`` and ``vivit/utils/ggn.py`` on seeded per-parameter tensors: two "parameters"
+    of shapes ``[4, 3]`` and ``[5]`` carrying ``V^T [C=3, N=4, *shape]`` and per-sample gradients ``[N, *shape]``."""
+    from vivit.utils import ggn as ref_ggn
+    from vivit.utils import gram as ref_gram
+
+    gen = torch.Generator().manual_seed(0)
+    rand = lambda *shape: torch.randn(*shape, generator=gen, dtype=torch.float64)  # noqa: E731
+    shapes = [(4, 3), (5,)]
+    params = [types.SimpleNamespace(shape=s, vt=rand(3, 4, *s), gb=rand(4, *s)) for s in shapes]
+    mat_cn, mat_sqrt = rand(2, 3, 4), rand(12, 6)
+    mats_p = [rand(2, *s) for s in shapes]
+    other = rand(7, 4, 3)
+    out = {
+        "shapes": shapes, "vt": [p.vt for p in params], "gb": [p.gb for p in params],
+        "mat_cn": mat_cn, "mat_sqrt": mat_sqrt, "mats_p": mats_p, "other": other,
+        "pairwise_dot_1": ref_gram.pairwise_dot(params[0].gb, start_dim=1),
+        "pairwise_dot_2": ref_gram.pairwise_dot(params[0].vt, start_dim=2),
+        "pairwise_dot_2_unflattened": ref_gram.pairwise_dot(params[0].vt, start_dim=2, flatten=False),
+        "partial_contract": ref_gram.partial_contract(params[0].vt, other, (2, 1)),
+        "reshape_as_square": ref_gram.reshape_as_square(ref_gram.pairwise_dot(params[1].vt, 2, flatten=False)),
+        "compute_gram_mat": ref_gram.compute_gram_mat(params, "vt", 2),
+        "compute_gram_mat_unflattened": ref_gram.compute_gram_mat(params, "vt", 2, flatten=False),
+        "compute_gram_mat_grad": ref_gram.compute_gram_mat(params, "gb", 1),
+        "sqrt_gram_mat_prod": ref_gram.sqrt_gram_mat_prod(mat_sqrt, params, "vt", 2),
+        "sqrt_gram_mat_prod_concat": ref_gram.sqrt_gram_mat_prod(mat_sqrt, params, "vt", 2, concat=True),
+        "mVp": [ref_gram.mVp(p.vt, m, 2) for p, m in zip(params, mats_p)],
+        "Vmp": [ref_ggn.Vmp(p.vt, mat_cn, 2) for p in params],
+        "V_mat_prod": ref_ggn.V_mat_prod(mat_cn, params, "vt"),
+        "V_mat_prod_concat": ref_ggn.V_mat_prod(mat_cn, params, "vt", concat=True),
+        "V_mat_prod_sub": ref_ggn.V_mat_prod(mat_cn[:, :, :2].contiguous(), params, "vt", subsampling=[3, 1]),
+    }
+    return out
+
+
 def lanczos_vectors():
     """``vivit/hessianfree/lanczos.py:13-270`` and ``utils.py:7-57`` on a fixed symmetric matrix."""
     import importlib.util
@@ -390,9 +427,10 @@ def main():
     out["__lanczos__"] = lanczos_vectors()
     out["__linear_closures__"] = linear_closures()
     out["__eig_utils__"] = eig_utils()
+    out["__gram_utils__"] = gram_utils()
     out["__meta__"] = {"batch_sizes": {p.name: p.make()[2].shape[0] for p in PROBLEMS}, "torch": str(torch.__version__)}
     torch.save(out, os.path.join(HERE, "reference_run.pt"))
-    print(f"wrote {len(out) - 5} cases + gram hooks + lanczos + linear closures + eig utils")
+    print(f"wrote {len(out) - 6} cases + gram hooks + lanczos + linear closures + eig / gram / ggn utils")
 
 
 if __name__ == "__main__":

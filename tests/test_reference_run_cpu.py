@@ -323,3 +323,51 @@ def test_eig_utils_contract(monkeypatch):
         eig.symeig(torch.zeros(4))
     with pytest.raises(RuntimeError, match="NaN"):
         eig.symeig(torch.full((2, 2), float("nan"), dtype=torch.float64))
+
+
+# ---- vivit/utils/gram.py and vivit/utils/ggn.py ------------------------------------
+
+
+def test_gram_and_ggn_utils_reproduce_the_reference_run(monkeypatch):
+    import types
+
+    from vivit_b200.utils import ggn, gram
+
+    double.install(monkeypatch)
+    want = RUN["__gram_utils__"]
+    params = [types.SimpleNamespace(shape=s, vt=vt, gb=gb) for s, vt, gb in zip(want["shapes"], want["vt"], want["gb"])]
+    mat_cn, mat_sqrt = want["mat_cn"], want["mat_sqrt"]
+
+    def same(got, key):
+        w = want[key]
+        if isinstance(w, (list, tuple)):
+            assert len(got) == len(w)
+            for g, ww in zip(got, w):
+                close(g, ww, what=key)
+        else:
+            close(got, w, what=key)
+
+    same(gram.pairwise_dot(params[0].gb, start_dim=1), "pairwise_dot_1")
+    same(gram.pairwise_dot(params[0].vt, start_dim=2), "pairwise_dot_2")
+    same(gram.pairwise_dot(params[0].vt, start_dim=2, flatten=False), "pairwise_dot_2_unflattened")
+    same(gram.partial_contract(params[0].vt, want["other"], (2, 1)), "partial_contract")
+    same(gram.reshape_as_square(gram.pairwise_dot(params[1].vt, 2, flatten=False)), "reshape_as_square")
+    same(gram.compute_gram_mat(params, "vt", 2), "compute_gram_mat")
+    same(gram.compute_gram_mat(params, "vt", 2, flatten=False), "compute_gram_mat_unflattened")
+    same(gram.compute_gram_mat(params, "gb", 1), "compute_gram_mat_grad")
+    same(gram.sqrt_gram_mat_prod(mat_sqrt, params, "vt", 2), "sqrt_gram_mat_prod")
+    same(gram.sqrt_gram_mat_prod(mat_sqrt, params, "vt", 2, concat=True), "sqrt_gram_mat_prod_concat")
+    same([gram.mVp(p.vt, m, 2) for p, m in zip(params, want["mats_p"])], "mVp")
+    same([ggn.Vmp(p.vt, mat_cn, 2) for p in params], "Vmp")
+    same(ggn.V_mat_prod(mat_cn, params, "vt"), "V_mat_prod")
+    same(ggn.V_mat_prod(mat_cn, params, "vt", concat=True), "V_mat_prod_concat")
+    same(ggn.V_mat_prod(mat_cn[:, :, :2].contiguous(), params, "vt", subsampling=[3, 1]), "V_mat_prod_sub")
+
+    with pytest.raises(ValueError):
+        gram.partial_contract(params[0].vt, want["other"], (2, 2))
+    with pytest.raises(NotImplementedError):
+        gram.sqrt_gram_mat_prod(mat_cn, params, "vt", 2)
+    with pytest.raises(ValueError):
+        list(gram.split_list([1, 2, 3], [1, 1]))
+    assert list(gram.split_list("abcde", [2, 3])) == ["ab", "cde"]
+    assert gram.compute_gram_mat([], "vt", 2) is None
