@@ -294,6 +294,14 @@ def jac_t_mat_prod(
         left, right, top, bottom = module.padding
         h, w = mat.shape[-2:]
         return mat[..., top : h - bottom, left : w - right]
+    if isinstance(module, (nn.Conv1d, nn.MaxPool1d, nn.AvgPool1d)):
+        # [external] Conv1DDerivatives / MaxPool1DDerivatives / AvgPool1DDerivatives: transposed Jacobian of
+        # the layer at its forward input, by autograd of the layer itself on the V*N "virtual batch"
+        x = inp.repeat(v, *([1] * (inp.dim() - 1))).detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            y = module(x)
+            (res,) = torch.autograd.grad(y, x, mat.reshape(v * n, *mat.shape[2:]))
+        return res.reshape(v, n, *inp.shape[1:])
     if isinstance(module, _BATCHNORM):
         # [external] BatchNormNdDerivatives._jac_t_mat_prod in evaluation mode: the layer is an affine map
         # per channel, its Jacobian is diag(weight / sqrt(running_var + eps))
@@ -333,6 +341,21 @@ def param_mjp(
         )  # [N, J, X]
         vt = einsum("vnox,njx->vnoj", mat.reshape(v, n, co, -1), cols)
         return vt.reshape(v, n, *module.weight.shape)
+    if isinstance(module, nn.Conv1d):
+        # [external] Conv1DDerivatives.param_mjp: the layer is linear in its parameters, so the product is
+        # the gradient of <mat[v, n], layer(x_n)> -- one autograd call per (v, n), fine at oracle sizes
+        if name == "bias":
+            return mat.sum(3)
+        v, n = mat.shape[:2]
+        rows = []
+        for vi in range(v):
+            for ni in range(n):
+                w = module.weight.detach().clone().requires_grad_(True)
+                with torch.enable_grad():
+                    y = F.conv1d(inp[ni : ni + 1], w, None, module.stride, module.padding, module.dilation, module.groups)
+                    (g,) = torch.autograd.grad(y, w, mat[vi, ni][None])
+                rows.append(g)
+        return torch.stack(rows).reshape(v, n, *module.weight.shape)
     if isinstance(module, _BATCHNORM):
         # [external] BatchNormNdDerivatives._weight_jac_t_mat_prod / _bias_jac_t_mat_prod (evaluation mode),
         # wired by ``vivit/extensions/secondorder/vivit/batchnormnd.py:8-13`` (params=["bias", "weight"])

@@ -149,3 +149,47 @@ def test_scale_module_in_a_weighted_skip_connection():
     ggn = AutogradGGN(model, nn.CrossEntropyLoss(), x, y).ggn()
     n = min(gram.shape[0], ggn.shape[0])
     assert torch.allclose(torch.linalg.eigvalsh(gram)[-n:], torch.linalg.eigvalsh(ggn)[-n:], rtol=1e-8, atol=1e-12)
+
+
+def test_one_dimensional_convolution_and_pooling():
+    """``Conv1d`` / ``MaxPool1d`` / ``AvgPool1d`` (module map ``secondorder/vivit/__init__.py:90-101``) run on the
+    2-d kernels over feature maps of unit height: factors and per-sample gradients against autograd."""
+    from oracle.autograd_ggn import AutogradGGN
+    from vivit_b200 import BatchGrad
+
+    torch.manual_seed(6)
+    model = nn.Sequential(
+        nn.Conv1d(2, 3, 3, stride=2, padding=1),
+        nn.ReLU(),
+        nn.MaxPool1d(2, stride=1),
+        nn.Conv1d(3, 4, 2, dilation=2, bias=False),
+        nn.Tanh(),
+        nn.AvgPool1d(2, stride=2, padding=1),
+        nn.Flatten(),
+        nn.Linear(4 * 3, 3),
+    ).double()
+    x, y = torch.rand(3, 2, 13, dtype=torch.float64), torch.randint(0, 3, (3,))
+    assert model(x).shape == (3, 3)
+    _sqrt_ggn_matches_autograd(model, nn.CrossEntropyLoss(), x, y)
+    run_backward(model, nn.CrossEntropyLoss(), x, y, [BatchGrad()], None)
+    got = torch.cat([p.grad_batch.flatten(1) for p in model.parameters()], 1)
+    assert torch.allclose(got, AutogradGGN(model, nn.CrossEntropyLoss(), x, y).batch_grad(), rtol=1e-10, atol=1e-13)
+
+
+def test_one_dimensional_layers_oracle_and_computation_agree():
+    """The same 1-d net through ``EigvalshComputation`` (host code) and the oracle restatement."""
+    from oracle import reference_path as ref
+    from vivit_b200 import EigvalshComputation
+
+    torch.manual_seed(7)
+    model = nn.Sequential(
+        nn.Conv1d(2, 3, 3, padding=1), nn.Sigmoid(), nn.MaxPool1d(2), nn.Conv1d(3, 2, 2, stride=2),
+        nn.AvgPool1d(2, stride=1), nn.Flatten(), nn.Linear(2 * 2, 3),
+    ).double()
+    x, y = torch.rand(4, 2, 12, dtype=torch.float64), torch.randint(0, 3, (4,))
+    for sub in (None, [2, 0]):
+        groups = [{"params": list(model.parameters())}]
+        comp = EigvalshComputation(subsampling=sub)
+        run_backward(model, nn.CrossEntropyLoss(), x, y, [comp.get_extension()], comp.get_extension_hook(groups))
+        (want,) = ref.eigvalsh(model, nn.CrossEntropyLoss(), x, y, groups, subsampling=sub)
+        assert torch.allclose(comp.get_result(groups[0]), want, rtol=1e-8, atol=1e-11)

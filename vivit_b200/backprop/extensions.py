@@ -12,8 +12,9 @@ Public classes mirror what the reference hands to ``with backpack(...)``:
   ``GradFactor`` object instead of the materialised tensor.
 
 Module coverage: ``CrossEntropyLoss``, ``MSELoss``, ``Linear`` (also with additional input
-dimensions), ``Conv2d``, ``BatchNorm1d/2d/3d`` (evaluation mode), ``ReLU``, ``Sigmoid``, ``Tanh``,
-``LeakyReLU``, ``ELU``, ``SELU``, ``LogSigmoid``, ``MaxPool2d``, ``AvgPool2d``, ``ZeroPad2d``,
+dimensions), ``Conv2d``, ``Conv1d``, ``BatchNorm1d/2d/3d`` (evaluation mode), ``ReLU``, ``Sigmoid``, ``Tanh``,
+``LeakyReLU``, ``ELU``, ``SELU``, ``LogSigmoid``, ``MaxPool2d``, ``AvgPool2d``, ``MaxPool1d``, ``AvgPool1d``
+(1-d layers run on the 2-d kernels over feature maps of unit height), ``ZeroPad2d``,
 ``Flatten``, ``Dropout``, ``Identity``, and the branching modules of ``vivit_b200.custom_module``
 (``Parallel`` / ``SumModule``, ``ScaleModule``, ``Pad``, ``Slicing``).
 Anything else raises ``NotImplementedError`` (the reference's ``fail_mode="ERROR"``,
@@ -249,28 +250,40 @@ def _factor_linear(ext: _SqrtFactorExtension, module: nn.Linear, S: Tensor, need
     return kernels.sqrt_backprop_linear(S, module.weight.detach()) if need_in else None
 
 
-def _conv_check(module: nn.Conv2d):
+def _conv_check(module):
     if module.groups != 1:
-        raise NotImplementedError("grouped Conv2d is not supported")
+        raise NotImplementedError("grouped convolutions are not supported")
     if module.padding_mode != "zeros" or isinstance(module.padding, str):
-        raise NotImplementedError("Conv2d needs numeric zero padding")
+        raise NotImplementedError("convolutions need numeric zero padding")
+
+
+def _conv_geometry(module):
+    """``(kernel, stride, padding, dilation)`` as 2-d pairs; a 1-d convolution is a 2-d one of unit height."""
+    if isinstance(module, nn.Conv1d):
+        return ((1, module.kernel_size[0]), (1, module.stride[0]), (0, module.padding[0]), (1, module.dilation[0]))
+    return (_pair(module.kernel_size), _pair(module.stride), _pair(module.padding), _pair(module.dilation))
 
 
 def _factor_conv2d(ext: _SqrtFactorExtension, module: nn.Conv2d, S: Tensor, need_in: bool):
     _conv_check(module)
+    one_d = isinstance(module, nn.Conv1d)
     x = ext._subsample(module.input0.detach())
+    if one_d:  # [V, N, Co, L'] / [N, Ci, L] -> unit-height feature maps
+        S, x = S.unsqueeze(3), x.unsqueeze(2)
     w, b = _trainable(module, "weight"), _trainable(module, "bias")
-    geom = (_pair(module.stride), _pair(module.padding), _pair(module.dilation))
+    kernel, *geom = _conv_geometry(module)
     lo, hi = ext._own(S.shape[2])
     S_own = S if hi - lo == S.shape[2] else S[:, :, lo:hi].contiguous()
     if b is not None:
         ext._save(b, DenseFactor(kernels.v_emit_bias(S_own), (hi - lo,)))
     if w is not None:
-        Vt = kernels.v_emit_conv2d(S_own, x, _pair(module.kernel_size), *geom)
+        Vt = kernels.v_emit_conv2d(S_own, x, kernel, *geom)
         ext._save(w, DenseFactor(Vt, (hi - lo, *w.shape[1:])))
     if not need_in:
         return None
-    return kernels.sqrt_backprop_conv2d(S, module.weight.detach(), tuple(x.shape[2:]), *geom)
+    weight = module.weight.detach()
+    S_in = kernels.sqrt_backprop_conv2d(S, weight.unsqueeze(2) if one_d else weight, tuple(x.shape[2:]), *geom)
+    return S_in.squeeze(3) if one_d else S_in
 
 
 def _factor_act(act, use_output, scale_of=None):
@@ -425,9 +438,37 @@ def _factor_avgpool2d(ext, module: nn.AvgPool2d, S, need_in):
     return kernels.sqrt_backprop_avgpool2d(S, tuple(x.shape[2:]), k, s, _pair(module.padding))
 
 
+def _one(v) -> int:
+    return v if isinstance(v, int) else v[0]
+
+
+def _factor_maxpool1d(ext, module: nn.MaxPool1d, S, need_in):
+    """A 1-d pooling layer is the 2-d one over feature maps of unit height."""
+    if not need_in:
+        return None
+    x = ext._subsample(module.input0.detach()).unsqueeze(2)
+    stride = module.stride if module.stride is not None else module.kernel_size
+    k, s = (1, _one(module.kernel_size)), (1, _one(stride))
+    p, d = (0, _one(module.padding)), (1, _one(module.dilation))
+    _, idx = F.max_pool2d(x, k, s, p, d, module.ceil_mode, return_indices=True)
+    return kernels.sqrt_backprop_maxpool2d(S.unsqueeze(3), idx, tuple(x.shape[2:]), k, s, p, d).squeeze(3)
+
+
+def _factor_avgpool1d(ext, module: nn.AvgPool1d, S, need_in):
+    if not need_in:
+        return None
+    if module.ceil_mode or not module.count_include_pad:
+        raise NotImplementedError("AvgPool1d: ceil_mode / count_include_pad=False")
+    stride = module.stride if module.stride is not None else module.kernel_size
+    k, s, p = (1, _one(module.kernel_size)), (1, _one(stride)), (0, _one(module.padding))
+    length = module.input0.shape[2]
+    return kernels.sqrt_backprop_avgpool2d(S.unsqueeze(3), (1, length), k, s, p).squeeze(3)
+
+
 _FACTOR_HANDLERS = {
     nn.Linear: _factor_linear,
     nn.Conv2d: _factor_conv2d,
+    nn.Conv1d: _factor_conv2d,
     nn.ReLU: _factor_act(kernels.ACT_RELU, use_output=False),
     nn.Sigmoid: _factor_act(kernels.ACT_SIGMOID, use_output=True),
     nn.Tanh: _factor_act(kernels.ACT_TANH, use_output=True),
@@ -444,6 +485,8 @@ _FACTOR_HANDLERS = {
     nn.Identity: _factor_identity,
     nn.MaxPool2d: _factor_maxpool2d,
     nn.AvgPool2d: _factor_avgpool2d,
+    nn.MaxPool1d: _factor_maxpool1d,
+    nn.AvgPool1d: _factor_avgpool1d,
     Pad: _factor_pad,
     ScaleModule: _factor_scale,
     Slicing: _factor_slicing,
@@ -533,7 +576,7 @@ class BatchGrad(Extension):
                 self._save(b, DenseGrad(g, (hi - lo,)))
             if w is not None:
                 self._save(w, LinearWeightGrad(g, z.contiguous()))
-        elif isinstance(module, nn.Conv2d):
+        elif isinstance(module, (nn.Conv2d, nn.Conv1d)):
             w, b = _trainable(module, "weight"), _trainable(module, "bias")
             if w is None and b is None:
                 return
@@ -542,13 +585,12 @@ class BatchGrad(Extension):
             lo, hi = self._own(g.shape[1])
             g = g[:, lo:hi].contiguous()[None]  # one "class": [1, N, Co, Ho, Wo]
             x = self._subsample(module.input0.detach())
+            if isinstance(module, nn.Conv1d):  # unit-height feature maps
+                g, x = g.unsqueeze(3), x.unsqueeze(2)
             if b is not None:
                 self._save(b, DenseGrad(kernels.v_emit_bias(g)[0], (hi - lo,)))
             if w is not None:
-                gw = kernels.v_emit_conv2d(
-                    g, x, _pair(module.kernel_size), _pair(module.stride), _pair(module.padding),
-                    _pair(module.dilation),
-                )[0]
+                gw = kernels.v_emit_conv2d(g, x, *_conv_geometry(module))[0]
                 self._save(w, DenseGrad(gw, (hi - lo, *w.shape[1:])))
         elif isinstance(module, _BATCHNORM):
             w, b = _trainable(module, "weight"), _trainable(module, "bias")
