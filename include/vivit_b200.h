@@ -220,19 +220,26 @@ int vvt_axpy(void* Y, const void* X, int64_t numel, double alpha, int dtype, voi
  * ------------------------------------------------------------------------ */
 
 int64_t vvt_syevj_workspace_bytes(int64_t R, int jobz, int dtype);
+int64_t vvt_syevj_batched_workspace_bytes(int64_t R, int64_t batch, int jobz, int dtype);
 
-/* Eigendecomposition of the symmetric matrix G [R, R] (upper triangle is read, as symeig(upper=True)).
- * evals: [R] ascending; evecs: [R, R] with eigenvectors as COLUMNS (ignored if jobz == 0).
- * G is not modified.  info_host (host int[2], may be NULL): {sweeps used, converged flag}.
+/* Eigendecomposition of the symmetric POSITIVE SEMI-DEFINITE matrix G [R, R] (a Gram matrix; the upper triangle
+ * is read, as symeig(upper=True)).  The solver is one-sided: it works on a Cholesky factor of G + eps I, so an
+ * indefinite input is outside its contract (vivit_b200/utils/eig.py shifts such a matrix by a Gershgorin bound
+ * first).  evals: [R] ascending; evecs: [R, R] with eigenvectors as COLUMNS (ignored if jobz == 0).
+ * G is not modified.  info_host (host int[2], may be NULL): {sweeps used, converged flag}; converged == 0 means
+ * the sweep limit was reached (the reference's symeig raises in that case, and so do the Python callers).
  * Replaces Tensor.symeig at eigh.py:248, eigvalsh.py:221, directional_derivatives.py:291,
- * directional_damped_newton.py:315.  Synchronises `stream` (convergence is checked on the host). */
+ * directional_damped_newton.py:315.  Convergence is decided on the device; the host reads it through pinned
+ * memory one sweep late, so the stream is never drained between sweeps. */
 int vvt_syevj(void* evals, void* evecs, const void* G, int64_t R, int jobz, void* workspace,
               int64_t workspace_bytes, int* info_host, int dtype, void* stream);
 
-/* same, for `batch` matrices given as host arrays of device pointers (block-diagonal groups) */
-int vvt_syevj_batched(void* const* evals, void* const* evecs, const void* const* G,
-                      const int64_t* R, int64_t batch, int jobz, void* workspace,
-                      int64_t workspace_bytes, int* info_host, int dtype, void* stream);
+/* The same for `batch` independent matrices of one size, G [batch, R, R] -> evals [batch, R],
+ * evecs [batch, R, R]: the per-group Grams of block-diagonal param_groups (groups are independent,
+ * vivit/utils/hooks.py:214-219, and share R = C * N).  The problem index is a grid dimension of every kernel,
+ * each problem stops on its own convergence flag.  info_host: int[2 * batch]. */
+int vvt_syevj_batched(void* evals, void* evecs, const void* G, int64_t R, int64_t batch, int jobz,
+                      void* workspace, int64_t workspace_bytes, int* info_host, int dtype, void* stream);
 
 /* mask[i] = !isclose(evals[i], 0, rtol, atol) = |evals[i]| > atol  (vivit/utils/eig.py:111-134);
  * mask: uint8 [R]; count_host (host, may be NULL) receives the number kept (synchronises). */

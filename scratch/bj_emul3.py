@@ -75,7 +75,9 @@ def run(W, OB, variant, label, tol=1e-5, max_sweeps=24, inner_sweeps=1):
 which, variant = sys.argv[1], sys.argv[2]
 OB = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 isw = int(sys.argv[4]) if len(sys.argv) > 4 else 1
-A = G + 1e-3 * nrm * np.eye(R)
+import os
+SHIFT = float(os.environ.get("SHIFT", "1e-3"))
+A = G + SHIFT * nrm * np.eye(R)
 if which == 'L': W = np.linalg.cholesky(A)
 elif which == 'Ls':
     o = np.argsort(-np.diag(A)); W = np.linalg.cholesky(A[np.ix_(o, o)])

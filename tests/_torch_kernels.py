@@ -26,12 +26,11 @@ NAMES = [
     "sqrt_backprop_linear", "sqrt_backprop_conv2d", "sqrt_backprop_elementwise",
     "sqrt_backprop_maxpool2d", "sqrt_backprop_avgpool2d", "v_emit_conv2d", "v_emit_bias",
     "v_emit_linear", "gemm", "gram_dense_accum", "gram_cross_accum", "gram_linear_accum",
-    "gram_cross_linear_accum", "syevj", "filter_nonzero", "backtransform_dense",
+    "gram_cross_linear_accum", "syevj", "syevj_batched", "filter_nonzero", "backtransform_dense",
     "backtransform_linear", "vt_mat_prod_linear", "scale_rows_rsqrt", "dirderiv_epilogue",
     "newton_coeff", "v_apply_dense", "v_apply_linear", "launch_count", "center_rows",
 ]
 
-last_syevj_info = {"sweeps": 0, "converged": True}
 
 
 def launch_count():
@@ -192,11 +191,24 @@ def gram_cross_linear_accum(X, S, Z, Dl, Zg, with_bias):
     return X
 
 
-def syevj(G, vectors=True):
+class SyevjNotConverged(RuntimeError):
+    pass
+
+
+def syevj(G, vectors=True, return_info=False):
     sym = torch.triu(G) + torch.triu(G, 1).t()
+    info = ({"sweeps": 0, "converged": True},) if return_info else ()
     if vectors:
-        return torch.linalg.eigh(sym)
-    return torch.linalg.eigvalsh(sym), None
+        return tuple(torch.linalg.eigh(sym)) + info
+    return (torch.linalg.eigvalsh(sym), None) + info
+
+
+def syevj_batched(G, vectors=True, return_info=False):
+    sym = torch.triu(G) + torch.triu(G, 1).transpose(-1, -2)
+    infos = ([{"sweeps": 0, "converged": True} for _ in range(G.shape[0])],) if return_info else ()
+    if vectors:
+        return tuple(torch.linalg.eigh(sym)) + infos
+    return (torch.linalg.eigvalsh(sym), None) + infos
 
 
 def filter_nonzero(evals, atol=1e-7, rtol=1e-5):

@@ -253,3 +253,36 @@ def test_no_context_no_side_effects():
     model = extend(nn.Linear(3, 2))
     model(torch.rand(2, 3)).sum().backward()
     assert not hasattr(model.weight, "vivit_ggn_exact")
+
+
+def test_criterion_results_follow_the_reference_indexing():
+    """``evals[keep]`` semantics of the reference (``vivit/linalg/eigh.py:252-265``): positions, negative
+    positions, boolean masks (a mask used to be cast to 0/1 positions)."""
+    from vivit_b200.utils import keep_indices
+
+    ev = torch.tensor([0.0, 1e-9, 0.5, 2.0, 3.0])
+    assert keep_indices([2, 4], ev).tolist() == [2, 4]
+    assert keep_indices([-1], ev).tolist() == [4]
+    assert keep_indices(torch.tensor([-2, 0]), ev).tolist() == [3, 0]
+    assert keep_indices(ev > 1e-6, ev).tolist() == [2, 3, 4]
+    assert keep_indices([True, False, False, False, True], ev).tolist() == [0, 4]
+    assert keep_indices([], ev).tolist() == []
+    for bad in ([5], [-6], [0.5], torch.tensor([True, False])):
+        with pytest.raises(IndexError):
+            keep_indices(bad, ev)
+
+
+def test_boolean_mask_criterion_end_to_end():
+    """A criterion returning ``evals > tol`` keeps exactly the eigenpairs the same criterion written with
+    positions keeps."""
+    import vivit_b200 as vv
+
+    results = []
+    for crit in (lambda ev: ev > 1e-6, lambda ev: [i for i in range(ev.numel()) if ev[i] > 1e-6]):
+        model, loss_fn, x, y = PROBLEMS[0].make()
+        groups = [{"params": list(model.parameters()), "criterion": crit}]
+        comp = vv.EighComputation()
+        run_backward(model, loss_fn, x, y, [comp.get_extension()], comp.get_extension_hook(groups))
+        results.append(comp.get_result(groups[0]))
+    assert results[0][0].numel() == results[1][0].numel() > 0
+    assert torch.allclose(results[0][0], results[1][0])

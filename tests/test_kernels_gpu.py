@@ -233,8 +233,8 @@ def _psd(R, rank, dtype, seed=0):
 @pytest.mark.parametrize("R,rank", [(1, 1), (5, 5), (32, 3), (33, 33), (100, 40), (320, 288), (640, 64), (1280, 1152)])
 def test_syevj(k, dtype, R, rank):
     G = _psd(R, rank, dtype, seed=R)
-    evals, evecs = k.syevj(G, True)
-    assert k.last_syevj_info["converged"]
+    evals, evecs, info = k.syevj(G, True, return_info=True)
+    assert info["converged"]
     want = torch.linalg.eigvalsh(G.double())
     tol = 2e-5 if dtype == torch.float32 else 1e-11
     assert (evals.double() - want).abs().max() <= tol * want.abs().max(), (evals.double() - want).abs().max()
@@ -244,10 +244,166 @@ def test_syevj(k, dtype, R, rank):
     orth = (U.t() @ U - eye).abs().max().item()
     resid = (G.double() @ U - U * evals.double()[None]).norm().item() / max(G.double().norm().item(), 1e-30)
     lim = 5e-5 if dtype == torch.float32 else 1e-11
-    assert orth <= lim and resid <= lim, (orth, resid, k.last_syevj_info)
+    assert orth <= lim and resid <= lim, (orth, resid, info)
     ev_only, none = k.syevj(G, False)
     assert none is None
     assert (ev_only.double() - want).abs().max() <= tol * want.abs().max()
+
+
+def _wide_round(L, rnd_idx):
+    """One round of the two-level solver through the library's test hook (not in the public header)."""
+    import ctypes
+
+    from vivit_b200 import _lib
+
+    lib = _lib.load()
+    fn = lib.vvt_dbg_wide_round
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+    Np = L.shape[0]
+    pairs = Np // 128
+    H = torch.zeros(pairs, 128, 128, device=L.device)
+    Qt = torch.zeros(pairs, 128, 128, device=L.device)
+    flag = torch.zeros(pairs, dtype=torch.int32, device=L.device)
+    st = fn(L.data_ptr(), H.data_ptr(), Qt.data_ptr(), flag.data_ptr(), Np, rnd_idx,
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(st, "vvt_dbg_wide_round")
+    torch.cuda.synchronize()
+    return H, Qt, flag
+
+
+def _rr_pair(n, rnd_idx, idx):
+    m = n - 1
+    if idx == 0:
+        return rnd_idx, m
+    return (rnd_idx + idx) % m, (rnd_idx - idx + m) % m
+
+
+@pytest.mark.parametrize("Np,rnd_idx", [(256, -1), (256, 0), (512, 2), (1280, -1), (1280, 7)])
+def test_wide_round_kernels(k, Np, rnd_idx):
+    """The three kernels of a wide round, one by one: pair Grams on tcgen05 with MN-major operands (against
+    float64 ``P^T P``), the rotation kernel (``Q`` orthogonal, rotated pairs closer to diagonal), the tcgen05
+    apply (``P <- P Q`` in place, untouched columns bit-identical)."""
+    g = torch.Generator(device="cpu").manual_seed(Np + rnd_idx)
+    L0 = torch.tril(torch.randn(Np, Np, generator=g, dtype=torch.float64)) / math.sqrt(Np)
+    L0 = (L0 * torch.logspace(0, -2, Np, dtype=torch.float64)[None, :]).float().to(dev())
+    L0 = L0 / L0.norm()
+    L = L0.clone()
+    H, Qt, flag = _wide_round(L, rnd_idx)
+    nbw, pairs = Np // 64, Np // 128
+    for pr in range(pairs):
+        wa, wb = (2 * pr, 2 * pr + 1) if rnd_idx < 0 else _rr_pair(nbw, rnd_idx, pr)
+        cols = torch.cat([torch.arange(wa * 64, wa * 64 + 64), torch.arange(wb * 64, wb * 64 + 64)]).to(dev())
+        P = L0[:, cols].double()
+        want = P.t() @ P
+        scale = want.abs().max().item()
+        assert (H[pr].double() - want).abs().max().item() <= 2e-6 * scale, ("gram", pr)
+        Pn = L[:, cols].double()
+        if flag[pr].item() == 0:
+            assert torch.equal(L[:, cols], L0[:, cols])
+            continue
+        Q = Qt[pr].double().t()
+        eye = torch.eye(128, dtype=torch.float64, device=dev())
+        assert (Q.t() @ Q - eye).abs().max().item() <= 2e-5, ("orthogonal", pr)
+        assert (Pn - P @ Q).abs().max().item() <= 2e-6 * P.abs().max().item(), ("apply", pr)
+        # the rotations made the visited column pairs (nearly) orthogonal: cross block for a cross round
+        Hn = Pn.t() @ Pn
+        d = Hn.diagonal().clamp_min(1e-300).sqrt()
+        cosn = (Hn / d[:, None] / d[None, :]).abs()
+        cos0 = (want / want.diagonal().sqrt()[:, None] / want.diagonal().sqrt()[None, :]).abs()
+        if rnd_idx >= 0:
+            assert cosn[:64, 64:].max().item() <= 0.5 * cos0[:64, 64:].max().item() + 1e-5
+        else:
+            off = ~torch.eye(64, dtype=torch.bool, device=dev())
+            assert cosn[:64, :64][off].max().item() <= 0.5 * cos0[:64, :64][off].max().item() + 1e-5
+    if pairs * 128 < Np:  # (never: Np is a multiple of 128)
+        raise AssertionError
+
+
+@pytest.mark.parametrize("R,rank", [(2048, 1800), (2560, 2304), (5120, 4608)])
+def test_syevj_two_level(k, R, rank):
+    """fp32 problems of 2048 columns and more run the two-level (wide, tcgen05) rounds."""
+    G = _psd(R, rank, torch.float32, seed=R)
+    evals, evecs, info = k.syevj(G, True, return_info=True)
+    assert info["converged"], info
+    want = torch.linalg.eigvalsh(G.double())
+    assert (evals.double() - want).abs().max() <= 2e-5 * want.abs().max()
+    assert (evals[1:] >= evals[:-1]).all()
+    U = evecs.double()
+    eye = torch.eye(R, dtype=torch.float64, device=dev())
+    orth = (U.t() @ U - eye).abs().max().item()
+    resid = (G.double() @ U - U * evals.double()[None]).norm().item() / G.double().norm().item()
+    assert orth <= 1e-4 and resid <= 5e-5, (orth, resid, info)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,R", [(1, 33), (3, 64), (4, 320), (7, 100), (2, 1280)])
+def test_syevj_batched(k, dtype, B, R):
+    """Batched solve (the per-group Grams of block-diagonal groups): every problem matches its own single
+    solve and float64 eigvalsh within tolerance; problems of very different scale converge independently."""
+    Gs = torch.stack([_psd(R, max(1, R - 7 * b - 3), dtype, seed=R + b) * (10.0 ** b) for b in range(B)])
+    evals, evecs, infos = k.syevj_batched(Gs, True, return_info=True)
+    assert all(i["converged"] for i in infos), infos
+    for b in range(B):
+        want = torch.linalg.eigvalsh(Gs[b].double())
+        tol = 2e-5 if dtype == torch.float32 else 1e-11
+        assert (evals[b].double() - want).abs().max() <= tol * want.abs().max()
+        U = evecs[b].double()
+        resid = (Gs[b].double() @ U - U * evals[b].double()[None]).norm().item() / Gs[b].double().norm().item()
+        lim = 5e-5 if dtype == torch.float32 else 1e-11
+        assert resid <= lim, (b, resid)
+        single_vals, _ = k.syevj(Gs[b].contiguous(), True)
+        assert (single_vals.double() - evals[b].double()).abs().max() <= tol * want.abs().max()
+    ev_only, none = k.syevj_batched(Gs, False)
+    assert none is None
+    assert torch.allclose(ev_only.double(), evals.double(), rtol=1e-4 if dtype == torch.float32 else 1e-9, atol=0)
+
+
+def test_syevj_batched_two_level(k):
+    Gs = torch.stack([_psd(2048, 1500 + 200 * b, torch.float32, seed=b) for b in range(2)])
+    evals, evecs = k.syevj_batched(Gs, True)
+    for b in range(2):
+        want = torch.linalg.eigvalsh(Gs[b].double())
+        assert (evals[b].double() - want).abs().max() <= 2e-5 * want.abs().max()
+        U = evecs[b].double()
+        assert (Gs[b].double() @ U - U * evals[b].double()[None]).norm() / Gs[b].double().norm() <= 5e-5
+
+
+def test_symeig_indefinite_matrix(k):
+    """``vivit/utils/eig.py`` ``symeig`` takes any symmetric matrix; the one-sided kernel is for PSD input, so
+    the wrapper shifts by a Gershgorin bound."""
+    from vivit_b200.utils.eig import symeig, symeig_psd
+
+    g = torch.Generator(device="cpu").manual_seed(5)
+    A = torch.randn(60, 60, generator=g, dtype=torch.float64)
+    A = ((A + A.t()) / 2).to(dev())  # indefinite
+    for dtype, tol in ((torch.float64, 1e-10), (torch.float32, 2e-5)):
+        M = A.to(dtype)
+        evals, evecs = symeig_psd(M, eigenvectors=True)
+        want = torch.linalg.eigvalsh(M.double())
+        assert (evals.double() - want).abs().max() <= tol * want.abs().max()
+        U = evecs.double()
+        assert (M.double() @ U - U * evals.double()[None]).abs().max() <= 10 * tol * want.abs().max()
+        nz_evals, _ = symeig(M, eigenvectors=False)
+        assert nz_evals.numel() == 60 and (nz_evals < 0).any()
+
+
+def test_mixed_dtype_operands_are_rejected(k):
+    S, W = rnd(4, 6, dtype=torch.float32), rnd(6, 3, dtype=torch.float64)
+    with pytest.raises(TypeError):
+        k.sqrt_backprop_linear(S, W)
+    with pytest.raises(TypeError):
+        k.gram_dense_accum(torch.zeros(4, 4, device=dev(), dtype=torch.float64), S)
+
+
+def test_newton_coeff_many_directions(k):
+    """More directions than one 48 KB shared-memory tile of coefficients (K = 7000 > 6144)."""
+    R, K = 7000, 7000
+    U = rnd(R, K, dtype=torch.float64, scale=1e-2)
+    gam, lam = rnd(3, K, dtype=torch.float64), rnd(2, K, dtype=torch.float64).abs() + 1.0
+    dl, ev = torch.ones(K, dtype=torch.float64, device=dev()), rnd(K, dtype=torch.float64).abs() + 0.5
+    got = k.newton_coeff(U, gam, lam, dl, ev, 1.5)
+    close(got, ref.newton_coeff(U, gam, lam, dl, ev, 1.5), torch.float64, "newton_coeff K=7000")
 
 
 def test_syevj_reads_upper_triangle_and_keeps_input(k):
@@ -266,8 +422,7 @@ def test_syevj_lapack_killer(k):
 
     path = os.path.join(os.path.dirname(__file__), "golden", "symeig_killer.pt")
     G = torch.load(path).to(dev())
-    evals, evecs = k.syevj(G, True)
-    assert k.last_syevj_info["converged"]
+    evals, evecs = k.syevj(G, True)  # raises if the sweep limit is hit
     top = evals[-1].double().item()
     Gd = G.double()
     sym = torch.triu(Gd) + torch.triu(Gd, 1).t()

@@ -58,16 +58,42 @@ inline int launched(const char* where) {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+// Function attributes and SM counts are per DEVICE: one process may drive several GPUs.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev < 0 || dev >= kMaxDevices) ? 0 : dev;
 }
+
+inline int num_sms() {
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+// Largest dynamic shared-memory size configured so far for one kernel, per device.  Usage:
+//   static SmemOptIn opt;  VVT_TRY(opt.ensure(kernel, bytes, "where"));
+struct SmemOptIn {
+  std::atomic<size_t> done[kMaxDevices];
+  template <typename K>
+  int ensure(K kern, size_t bytes, const char* where) {
+    const int dev = current_device();
+    if (done[dev].load(std::memory_order_acquire) >= bytes) return VVT_OK;
+    const cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    if (e != cudaSuccess) return fail(VVT_ERR_CUDA, "%s: %s", where, cudaGetErrorString(e));
+    size_t cur = done[dev].load(std::memory_order_relaxed);
+    while (cur < bytes && !done[dev].compare_exchange_weak(cur, bytes, std::memory_order_release)) {}
+    return VVT_OK;
+  }
+};
 
 template <typename T>
 __host__ __device__ constexpr T vmax(T a, T b) { return a > b ? a : b; }

@@ -77,15 +77,23 @@ struct Eps<double> {
   static constexpr double tol = 1e-13;
 };
 
-struct JacobiScalars {
+struct JacobiScalars {           // one per problem of a batch
   double norm2;                  // ||G||_F^2
   unsigned long long rotations;  // clusters that rotated in the current sweep
   unsigned long long evmax_bits; // bit pattern of max |eigenvalue| as a double (atomicMax on non-negatives)
+  int converged;                 // set on the device at the end of the sweep that rotated (almost) nothing:
+                                 // every later round kernel of this problem exits at once
+  int sweeps;                    // sweeps this problem has run
+  unsigned long long last_rotations;
   long long t[8];                // VVT_SYEVJ_DEBUG: phase time stamps of CTA 0 (last launch)
+};
+// element strides between the problems of a batch (blockIdx.y = problem index in every kernel of this file)
+struct BatchStrides {
+  int64_t y, marks, dc, done;
 };
 #define VVT_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) sc->t[i] = clock64(); } while (0)
 __device__ long long g_dbg[16];
-#define VVT_DSTAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_dbg[i] = clock64(); } while (0)
+#define VVT_DSTAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_dbg[i] = clock64(); } while (0)
 
 // ---- small vector helpers (16-byte shared/global accesses, packed fp32 FMA) ----------------------
 __device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
@@ -131,6 +139,7 @@ __device__ __forceinline__ T* y_ptr(T* Y, int Np, int blk, int row) {
 template <typename T>
 __global__ void onesided_sym_kernel(T* Gs, const T* G, int64_t R, JacobiScalars* sc) {
   const int64_t total = R * R;
+  Gs += blockIdx.y * total, G += blockIdx.y * total, sc += blockIdx.y;
   double s = 0.0;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
@@ -152,8 +161,9 @@ __global__ void onesided_sym_kernel(T* Gs, const T* G, int64_t R, JacobiScalars*
 
 // W = Gs / ||G||_F zero-padded to Np (the solver squares magnitudes: keep them near 1), J = I
 template <typename T>
-__global__ void onesided_init_kernel(T* Y, const T* Gs, int64_t R, int Np, const JacobiScalars* sc) {
+__global__ void onesided_init_kernel(T* Y, const T* Gs, int64_t R, int Np, const JacobiScalars* sc, int64_t y_stride) {
   const int64_t total = int64_t(Np) * Np;
+  Y += blockIdx.y * y_stride, Gs += blockIdx.y * R * R, sc += blockIdx.y;
   const double n2 = sc->norm2;
   const T scale = n2 > 0.0 ? T(1.0 / sqrt(n2)) : T(0);
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
@@ -733,8 +743,10 @@ __device__ __forceinline__ void signal_blocks(unsigned* done, int ba, int bb, in
 template <typename T>
 __global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
 onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc,
-                               int* marks, int now, T* Dc, unsigned* done) {
+                               int* marks, int now, T* Dc, unsigned* done, BatchStrides bs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  Y += blockIdx.y * bs.y, sc += blockIdx.y, marks += blockIdx.y * bs.marks, Dc += blockIdx.y * bs.dc;
+  if (done) done += blockIdx.y * bs.done;
   RotSmem<T>& rs = *reinterpret_cast<RotSmem<T>*>(smem_raw);
   T* P = reinterpret_cast<T*>(smem_raw + ((sizeof(RotSmem<T>) + 15) / 16) * 16);  // [parts * rows][LDP]: W rows(, J rows)
   cg::cluster_group cluster = cg::this_cluster();
@@ -751,6 +763,9 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
   // block in griddepcontrol.wait until this grid has completed and its stores are visible)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (intra || !done) asm volatile("griddepcontrol.wait;" ::: "memory");  // first launch of a sweep: after memsets / init
+  // a finished problem of the batch (flag written by sweep_end_kernel, which the intra round has waited for;
+  // it only changes between sweeps): nothing left to do, and none of its later CTAs waits for done[]
+  if (*reinterpret_cast<const volatile int*>(&sc->converged)) return;
   if (done) wait_blocks(done, ba, bb, unsigned(CL) * unsigned(now - 1), tid);
   if (pair_is_clean(marks, nb, ba, bb, intra)) {  // same decision in every CTA of the cluster
     if (done) signal_blocks(done, ba, bb, tid);
@@ -872,9 +887,11 @@ __device__ __forceinline__ void load_chunk(T (*dst)[LDP], const T* Y, int Np, in
 template <typename T>
 __global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
 onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc,
-                             int* marks, int now, T* Dc, unsigned* done) {
+                             int* marks, int now, T* Dc, unsigned* done, BatchStrides bs) {
   (void)Dc;  // the streaming variant recomputes the whole panel Gram in every round
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  Y += blockIdx.y * bs.y, sc += blockIdx.y, marks += blockIdx.y * bs.marks;
+  if (done) done += blockIdx.y * bs.done;
   StreamSmem<T>& sm = *reinterpret_cast<StreamSmem<T>*>(smem_raw);
   RotSmem<T>& rs = sm.rs;
   cg::cluster_group cluster = cg::this_cluster();
@@ -890,6 +907,7 @@ onesided_round_stream_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, 
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (intra || !done) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (*reinterpret_cast<const volatile int*>(&sc->converged)) return;
   if (done) wait_blocks(done, ba, bb, unsigned(CL) * unsigned(now - 1), tid);
   if (pair_is_clean(marks, nb, ba, bb, intra)) {
     if (done) signal_blocks(done, ba, bb, tid);
@@ -1032,6 +1050,7 @@ __device__ __forceinline__ void chol_diag_warp(T (*D)[LDD], T* dinv, T floor_piv
 template <typename T>
 __global__ void __launch_bounds__(CROWS) chol_panel_kernel(T* A, int64_t R, int k, int b, const JacobiScalars* sc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  A += blockIdx.y * R * R, sc += blockIdx.y;
   T(*D)[LDD] = reinterpret_cast<T(*)[LDD]>(smem_raw);
   T* dinv = reinterpret_cast<T*>(smem_raw) + CB * LDD;  // 1 / L_jj
   T(*X)[CB + 1] = reinterpret_cast<T(*)[CB + 1]>(dinv + CB);
@@ -1105,6 +1124,7 @@ static size_t chol_smem_bytes() {
 template <typename T>
 __global__ void chol_prepare_kernel(T* A, const T* Gs, int64_t R, const JacobiScalars* sc) {
   const int64_t total = R * R;
+  A += blockIdx.y * total, Gs += blockIdx.y * total, sc += blockIdx.y;
   const T eps = chol_shift<T>(sc);
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x)
@@ -1113,8 +1133,10 @@ __global__ void chol_prepare_kernel(T* A, const T* Gs, int64_t R, const JacobiSc
 
 // W = L / ||L||_F (lower triangle of A, zero above and in the padding); ||L||_F^2 = tr(G) + R eps <= sqrt(R) ||G||_F + R eps
 template <typename T>
-__global__ void onesided_init_chol_kernel(T* Y, const T* A, int64_t R, int Np, const JacobiScalars* sc) {
+__global__ void onesided_init_chol_kernel(T* Y, const T* A, int64_t R, int Np, const JacobiScalars* sc,
+                                          int64_t y_stride) {
   const int64_t total = int64_t(Np) * Np;
+  Y += blockIdx.y * y_stride, A += blockIdx.y * R * R, sc += blockIdx.y;
   // any scale of the right magnitude will do (the rotations are scale free; thresholds assume O(1) columns)
   const double bound = sqrt(double(R)) * sqrt(sc->norm2) + double(R) * double(chol_shift<T>(sc));
   const T scale = bound > 0.0 ? T(1.0 / sqrt(bound)) : T(0);
@@ -1128,8 +1150,9 @@ __global__ void onesided_init_chol_kernel(T* Y, const T* A, int64_t R, int Np, c
 
 // inv[c] = 1 / ||W[:, c]||  (one warp per column)
 template <typename T>
-__global__ void onesided_colnorm_kernel(T* inv, const T* Y, int64_t R, int Np) {
+__global__ void onesided_colnorm_kernel(T* inv, const T* Y, int64_t R, int Np, int64_t y_stride) {
   const int lane = threadIdx.x & 31;
+  inv += blockIdx.y * R, Y += blockIdx.y * y_stride;
   const int64_t c = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (c >= R) return;
   double s = 0.0;
@@ -1143,8 +1166,10 @@ __global__ void onesided_colnorm_kernel(T* inv, const T* Y, int64_t R, int Np) {
 
 // Jm[r][c] and Jt[c][r] <- normalised columns of the W part of Y
 template <typename T>
-__global__ void onesided_gather_w_kernel(T* Jm, T* Jt, const T* Y, const T* inv, int64_t R, int Np) {
+__global__ void onesided_gather_w_kernel(T* Jm, T* Jt, const T* Y, const T* inv, int64_t R, int Np,
+                                         int64_t y_stride) {
   const int64_t total = R * R;
+  Jm += blockIdx.y * total, Jt += blockIdx.y * total, Y += blockIdx.y * y_stride, inv += blockIdx.y * R;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
     const int r = int(idx / R), c = int(idx % R);
@@ -1156,8 +1181,9 @@ __global__ void onesided_gather_w_kernel(T* Jm, T* Jt, const T* Y, const T* inv,
 
 // Jm[r][c] (row-major) and Jt[c][r] (its transpose) <- J part of Y
 template <typename T>
-__global__ void onesided_gather_j_kernel(T* Jm, T* Jt, const T* Y, int64_t R, int Np) {
+__global__ void onesided_gather_j_kernel(T* Jm, T* Jt, const T* Y, int64_t R, int Np, int64_t y_stride) {
   const int64_t total = R * R;
+  Jm += blockIdx.y * total, Jt += blockIdx.y * total, Y += blockIdx.y * y_stride;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
     const int r = int(idx / R), c = int(idx % R);
@@ -1172,6 +1198,7 @@ __global__ void onesided_gather_j_kernel(T* Jm, T* Jt, const T* Y, int64_t R, in
 template <typename T>
 __global__ void onesided_rayleigh_kernel(T* ev, const T* Jt, const T* Tt, int64_t R, JacobiScalars* sc) {
   const int lane = threadIdx.x & 31;
+  ev += blockIdx.y * R, Jt += blockIdx.y * R * R, Tt += blockIdx.y * R * R, sc += blockIdx.y;
   const int64_t c = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (c >= R) return;
   double num = 0.0, den = 0.0;
@@ -1199,6 +1226,7 @@ template <typename T>
 __global__ void onesided_refine_coeff_kernel(T* Et, const T* S, const T* Mm, const T* ev, int64_t R,
                                              const JacobiScalars* sc) {
   const int64_t total = R * R;
+  Et += blockIdx.y * total, S += blockIdx.y * total, Mm += blockIdx.y * total, ev += blockIdx.y * R, sc += blockIdx.y;
   // eigenvalue gaps below the rounding noise of S carry no information about the eigenvectors
   const T gap_min = T(256.0 * double(Eps<T>::v) * __longlong_as_double((long long)sc->evmax_bits));
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
@@ -1226,6 +1254,7 @@ __global__ void onesided_refine_coeff_kernel(T* Et, const T* S, const T* Mm, con
 template <typename T>
 __global__ void jacobi_rank_kernel(int* rank, const T* ev, int64_t R) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  rank += blockIdx.y * R, ev += blockIdx.y * R;
   if (i >= R) return;
   const T vi = ev[i];
   int r = 0;
@@ -1244,6 +1273,8 @@ __global__ void jacobi_rank_kernel(int* rank, const T* ev, int64_t R) {
 template <typename T>
 __global__ void jacobi_permute_kernel(T* evals, T* evecs, const T* ev, const T* Jt, const int* rank, int64_t R) {
   const int64_t total = evecs ? R * R : R;
+  evals += blockIdx.y * R, ev += blockIdx.y * R, Jt += blockIdx.y * R * R, rank += blockIdx.y * R;
+  if (evecs) evecs += blockIdx.y * R * R;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
     const int64_t r = idx / R, i = idx % R;
@@ -1253,35 +1284,74 @@ __global__ void jacobi_permute_kernel(T* evals, T* evecs, const T* ev, const T* 
   }
 }
 
+
+// end of a sweep, one thread per problem: a sweep that rotated (almost) nothing ends the iteration of its
+// problem -- the last few block pairs only carry cosines barely above the threshold, which the refinement step
+// removes anyway.  The decision is taken on the device; the host only reads it (asynchronously).
+__global__ void sweep_end_kernel(JacobiScalars* sc, int batch, unsigned long long thresh, int* state) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  if (!sc[b].converged) {
+    sc[b].sweeps += 1;
+    sc[b].last_rotations = sc[b].rotations;
+    if (sc[b].rotations <= thresh) sc[b].converged = 1;
+  }
+  sc[b].rotations = 0;
+  state[2 * b] = sc[b].sweeps;
+  state[2 * b + 1] = sc[b].converged;
+}
+
+}  // namespace vvt
+
+#include "eig_wide.cuh"
+
+namespace vvt {
+
+constexpr int64_t kMaxBatch = 1024;  // problems per call (larger batches are processed in chunks)
+
+static bool wide_enabled(int64_t R, int dtype) {
+  static const int64_t min_r = getenv("VVT_SYEVJ_WIDE_MIN") ? atoll(getenv("VVT_SYEVJ_WIDE_MIN")) : 2048;
+  return dtype == VVT_F32 && R >= min_r && tc::encode_fn() != nullptr;
+}
+
 struct JacobiLayout {
-  int64_t Np, nb, off_Y, off_Gs, off_Jm, off_Jt, off_Tt, off_S, off_M, off_Et, off_ev, off_cn, off_rank, off_sc, off_marks, off_dc, off_done, off_gemm, gemm_bytes, total;
+  int64_t Np, nb, y_elems;  // regular path: padded size, 16-column blocks, elements of Y per problem
+  bool wide;
+  wide::WidePlan wp;
+  int64_t off_Y, off_Gs, off_Jm, off_Jt, off_Tt, off_S, off_M, off_Et, off_ev, off_cn, off_rank, off_sc, off_marks,
+      off_dc, off_done, off_state, off_gemm, gemm_bytes, total;
 };
 
-static JacobiLayout jacobi_layout(int64_t R, int64_t es, int dtype) {
+static JacobiLayout jacobi_layout(int64_t R, int64_t B, int64_t es, int dtype) {
   JacobiLayout L;
   L.Np = align_up(R, OP);
   L.nb = L.Np / OB;
+  L.wide = wide_enabled(R, dtype);
+  L.wp = wide::wide_plan(R, B);
+  L.y_elems = L.nb * 2 * L.Np * OB;
+  if (L.wide) L.y_elems = vmax<int64_t>(L.y_elems, int64_t(L.wp.Np) * L.wp.Np);
   int64_t o = 0;
   auto take = [&](int64_t bytes) {
     const int64_t at = o;
     o += align_up(bytes, 256);
     return at;
   };
-  L.off_Y = take(L.nb * 2 * L.Np * OB * es);
-  L.off_Gs = take(R * R * es);
-  L.off_Jm = take(R * R * es);
-  L.off_Jt = take(R * R * es);
-  L.off_Tt = take(R * R * es);
-  L.off_S = take(R * R * es);
-  L.off_M = take(R * R * es);
-  L.off_Et = L.off_Y;  // Y is dead once J has been gathered (nb * 2 * Np * OB >= R * R elements)
-  L.off_ev = take(R * es);
-  L.off_cn = take(R * es);
-  L.off_rank = take(R * 4);
-  L.off_sc = take(sizeof(JacobiScalars));
-  L.off_marks = take((L.nb + L.nb * L.nb) * 4);
-  L.off_dc = take(L.nb * OB * OB * es);
-  L.off_done = take(L.nb * 4);
+  L.off_Y = take(B * L.y_elems * es);
+  L.off_Gs = take(B * R * R * es);
+  L.off_Jm = take(B * R * R * es);
+  L.off_Jt = take(B * R * R * es);
+  L.off_Tt = take(vmax<int64_t>(B * R * R * es, L.wide ? L.wp.part_bytes : 0));  // wide path: split-K partial Grams
+  L.off_S = take(vmax<int64_t>(B * R * R * es, L.wide ? L.wp.q_bytes : 0));      // wide path: Q^T of every pair
+  L.off_M = take(vmax<int64_t>(B * R * R * es, L.wide ? L.wp.flag_bytes : 0));   // wide path: "rotated" flags
+  L.off_Et = L.off_Y;  // Y is dead once J has been gathered (y_elems >= R * R)
+  L.off_ev = take(B * R * es);
+  L.off_cn = take(B * R * es);
+  L.off_rank = take(B * R * 4);
+  L.off_sc = take(B * sizeof(JacobiScalars));
+  L.off_marks = take(B * (L.nb + L.nb * L.nb) * 4);
+  L.off_dc = take(B * L.nb * OB * OB * es);
+  L.off_done = take(B * L.nb * 4);
+  L.off_state = take(B * 2 * 4);
   L.gemm_bytes = vvt_gram_workspace_bytes(R, R, R, dtype);
   L.off_gemm = take(L.gemm_bytes);
   L.total = o;
@@ -1296,21 +1366,18 @@ static size_t resident_smem_bytes(int rows_per_cta, int parts) {
 
 template <typename T>
 static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_cta, int parts, bool resident,
-                        JacobiScalars* sc, int* marks, int now, T* Dc, unsigned* done, cudaStream_t s) {
+                        JacobiScalars* sc, int* marks, int now, T* Dc, unsigned* done, BatchStrides bs, int batch,
+                        cudaStream_t s) {
   auto kern = resident ? onesided_round_resident_kernel<T> : onesided_round_stream_kernel<T>;
   size_t smem = resident ? resident_smem_bytes<T>(rows_per_cta, parts) : sizeof(StreamSmem<T>);
   // a round that fits on the GPU with one CTA per SM asks for more than half of an SM's shared memory, so
   // that no two CTAs share an SM (and its tensor pipe) while other SMs idle
   static const bool no_pad = getenv("VVT_SYEVJ_NOPAD") != nullptr;  // experiments
-  if (!no_pad && int64_t(nb / 2) * CL <= num_sms()) smem = vmax<size_t>(smem, size_t(116) * 1024);
-  static size_t attr_done[2] = {0, 0};  // per instantiation: largest size configured so far
-  if (attr_done[resident] < smem) {
-    VVT_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
-                       "vvt_syevj(attr)"));
-    attr_done[resident] = smem;
-  }
+  if (!no_pad && int64_t(nb / 2) * CL * batch <= num_sms()) smem = vmax<size_t>(smem, size_t(116) * 1024);
+  static SmemOptIn opt_in[2];  // per instantiation and kernel variant
+  VVT_TRY(opt_in[resident].ensure(kern, smem, "vvt_syevj(attr)"));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(unsigned(nb / 2 * CL));
+  cfg.gridDim = dim3(unsigned(nb / 2 * CL), unsigned(batch));
   cfg.blockDim = dim3(OT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
@@ -1324,210 +1391,37 @@ static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_ct
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
-  VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, parts, sc, marks, now, Dc, done), "vvt_syevj(round)"));
+  VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, parts, sc, marks, now, Dc, done, bs),
+                     "vvt_syevj(round)"));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return VVT_OK;
 }
 
-// ======================================================================================================
-// EXPERIMENTAL wide stage (VVT_SYEVJ_WIDE=1; fp32, R a multiple of 128, Cholesky variant) -- DESIGN 5.1.
-// NOT enabled by default and not yet run on a GPU (written at the end of round 1 without GPU time left).
-// Column blocks of 64 (four of the 16-column blocks of Y) are paired by the same round-robin tournament;
-// one round is three launches over ALL pairs: (1) pair Grams H = P^T P (128 x 128, split-K over the rows,
-// the generic mma.sync GEMM with panel loaders), (2) one CTA per pair runs `inner_sweeps` cyclic sweeps of
-// scalar two-sided rotations on H in shared memory and leaves the accumulated Q, (3) P <- P Q (the same
-// GEMM, in place: a CTA owns 128 rows and has read them before its epilogue writes).  A sweep moves the
-// factor R / 64 times instead of R / 16 times.  When few pairs still rotate, the 16-wide kernel above
-// finishes the job (its intra round rebuilds the diagonal-block cache first), so accuracy and the
-// convergence test stay those of the default path.  scratch/two_level_emul.py is the numpy model.
-// ======================================================================================================
-constexpr int WB = 64;       // wide block (columns)
-constexpr int WP = 2 * WB;   // pair panel
-constexpr int LDW = WP + 1;  // padded pitch of the 128 x 128 matrices in shared memory
-
-struct WidePanel {
-  float* Y;
-  int Np, nbw, round;
-  // element (row, c) of the panel [P_a | P_b] of wide pair `pair`, c in [0, 128)
-  __device__ __forceinline__ float* at(int pair, int row, int c) const {
-    int wa, wb;
-    rr_pair(nbw, round, pair, wa, wb);
-    const int w = c < WB ? wa : wb, cc = c & (WB - 1);
-    return y_ptr(Y, Np, w * (WB / OB) + cc / OB, row) + (cc & (OB - 1));
-  }
+// Host-visible convergence state without stalling the GPU: after every sweep the device writes
+// {sweeps, converged} per problem, an async copy brings it to pinned memory and an event marks its arrival.
+// The host enqueues sweep s + 1 BEFORE it waits for the state of sweep s: if that sweep turns out to have been
+// the last one, the kernels of the speculative sweep exit on their first instruction (converged flag).
+struct HostState {
+  int* pinned = nullptr;  // [2 slots][2 * kMaxBatch]
+  cudaEvent_t ev[2] = {nullptr, nullptr};
 };
-
-struct WideGramLoader {  // operand of H = P^T P: A(m, k) = P[k][m]
-  static constexpr bool kContigK = false;
-  WidePanel p;
-  __device__ __forceinline__ float operator()(int b, int64_t m, int64_t k) const {
-    return (m < WP && k < p.Np) ? *p.at(b, int(k), int(m)) : 0.f;
+static int host_state(HostState** out) {
+  static thread_local HostState st[kMaxDevices];
+  HostState& h = st[current_device()];
+  if (!h.pinned) {
+    VVT_TRY(check_cuda(cudaHostAlloc(reinterpret_cast<void**>(&h.pinned), 2 * 2 * kMaxBatch * sizeof(int), cudaHostAllocDefault),
+                       "vvt_syevj(pinned)"));
+    for (int i = 0; i < 2; ++i)
+      VVT_TRY(check_cuda(cudaEventCreateWithFlags(&h.ev[i], cudaEventDisableTiming), "vvt_syevj(event)"));
   }
-};
-
-struct WideGramStore {  // raw split-K partial sums: part[split][pair][128][128]
-  float* part;
-  int pairs;
-  __device__ __forceinline__ void operator()(int b, int64_t r, int64_t c, float v, int split) const {
-    part[((int64_t(split) * pairs + b) * WP + r) * WP + c] = v;
-  }
-};
-
-struct WideApplyLoaderP {  // A(m, k) = P[m][k]
-  static constexpr bool kContigK = true;
-  WidePanel p;
-  __device__ __forceinline__ float operator()(int b, int64_t m, int64_t k) const {
-    return (m < p.Np && k < WP) ? *p.at(b, int(m), int(k)) : 0.f;
-  }
-};
-
-struct WideApplyLoaderQ {  // B(n, k) = Q[k][n]
-  static constexpr bool kContigK = false;
-  const float* Q;
-  __device__ __forceinline__ float operator()(int b, int64_t n, int64_t k) const {
-    return (n < WP && k < WP) ? Q[(int64_t(b) * WP + k) * WP + n] : 0.f;
-  }
-};
-
-struct WideApplyStore {  // in place; pairs whose Gram was already diagonal are left alone
-  WidePanel p;
-  const int* flag;
-  __device__ __forceinline__ void operator()(int b, int64_t r, int64_t c, float v, int) const {
-    if (flag[b]) *p.at(b, int(r), int(c)) = v;
-  }
-};
-
-// One CTA per pair: H = sum of the split-K partials (fixed order), symmetrised; cyclic sweeps of scalar
-// rotations (round-robin over the 128 columns, 64 disjoint rotations per round); Q to global memory.
-__global__ void __launch_bounds__(256) wide_inner_kernel(float* Q, int* flag, const float* part, int pairs, int splits,
-                                                         int inner_sweeps, JacobiScalars* sc) {
-  extern __shared__ __align__(16) unsigned char wide_smem[];
-  float(*H)[LDW] = reinterpret_cast<float(*)[LDW]>(wide_smem);
-  float(*Qs)[LDW] = reinterpret_cast<float(*)[LDW]>(wide_smem + sizeof(float) * WP * LDW);
-  __shared__ float cs[WB][2];
-  __shared__ int pq[WB][2];
-  const int pair = blockIdx.x, tid = threadIdx.x;
-  for (int idx = tid; idx < WP * WP; idx += 256) {
-    const int r = idx / WP, c = idx % WP;
-    float sum = 0.f;
-    for (int k = 0; k < splits; ++k) sum += part[((int64_t(k) * pairs + pair) * WP + r) * WP + c];
-    H[r][c] = sum;
-    Qs[r][c] = (r == c) ? 1.f : 0.f;
-  }
-  __syncthreads();
-  for (int idx = tid; idx < WP * WP; idx += 256) {  // the two triangles differ in the last bits
-    const int r = idx / WP, c = idx % WP;
-    if (r < c) {
-      const float m = 0.5f * (H[r][c] + H[c][r]);
-      H[r][c] = m;
-      H[c][r] = m;
-    }
-  }
-  __syncthreads();
-  const float tol2 = Eps<float>::tol * Eps<float>::tol, abs2 = Eps<float>::v * Eps<float>::v;
-  int need = 0;
-  for (int idx = tid; idx < WP * WP; idx += 256) {
-    const int r = idx / WP, c = idx % WP;
-    if (r < c && needs_rotation(H[r][r], H[c][c], H[r][c], tol2, abs2)) need = 1;
-  }
-  if (__syncthreads_or(need) == 0) {
-    if (tid == 0) flag[pair] = 0;
-    return;
-  }
-  if (tid == 0) {
-    flag[pair] = 1;
-    atomicAdd(&sc->rotations, 1ull);
-  }
-  for (int sw = 0; sw < inner_sweeps; ++sw) {
-    for (int r = 0; r < WP - 1; ++r) {
-      if (tid < WB) {
-        int x, y;
-        rr_pair(WP, r, tid, x, y);
-        const int p = min(x, y), q = max(x, y);
-        float c, s;
-        make_rotation(H[p][p], H[q][q], H[p][q], tol2, abs2, c, s);
-        cs[tid][0] = c;
-        cs[tid][1] = s;
-        pq[tid][0] = p;
-        pq[tid][1] = q;
-      }
-      __syncthreads();
-      for (int it = tid; it < WB * WP; it += 256) {  // columns p, q of H and of Q: [x_p x_q] <- [x_p x_q] R
-        const int i = it / WP, k = it % WP;
-        const float c = cs[i][0], s = cs[i][1];
-        const int p = pq[i][0], q = pq[i][1];
-        const float hp = H[k][p], hq = H[k][q];
-        H[k][p] = c * hp - s * hq;
-        H[k][q] = s * hp + c * hq;
-        const float qp = Qs[k][p], qq = Qs[k][q];
-        Qs[k][p] = c * qp - s * qq;
-        Qs[k][q] = s * qp + c * qq;
-      }
-      __syncthreads();
-      for (int it = tid; it < WB * WP; it += 256) {  // rows p, q of H: H <- R^T H
-        const int i = it / WP, k = it % WP;
-        const float c = cs[i][0], s = cs[i][1];
-        const int p = pq[i][0], q = pq[i][1];
-        const float hp = H[p][k], hq = H[q][k];
-        H[p][k] = c * hp - s * hq;
-        H[q][k] = s * hp + c * hq;
-      }
-      __syncthreads();
-    }
-  }
-  for (int idx = tid; idx < WP * WP; idx += 256) Q[int64_t(pair) * WP * WP + idx] = Qs[idx / WP][idx % WP];
-}
-
-// Runs wide sweeps on Y until few pairs still rotate (or `max_sweeps`); scratch: part (splits * pairs * 128 * 128
-// floats), Q (pairs * 128 * 128 floats), flag (pairs ints).  Returns the number of wide sweeps in *done_sweeps.
-static int wide_stage(float* Y, int Np, float* part, float* Qg, int* flag, JacobiScalars* sc, int inner_sweeps,
-                      int max_sweeps, int* done_sweeps, cudaStream_t s) {
-  const int nbw = Np / WB, pairs = nbw / 2;
-  int splits = int(vmax<int64_t>(1, vmin<int64_t>(8, ceil_div(2 * int64_t(num_sms()), pairs))));
-  const int64_t k_per_split = align_up(ceil_div(Np, splits), MmaCfg<float>::BK);
-  splits = int(ceil_div(Np, k_per_split));
-  auto gram_kern = gemm_kernel<float, WideGramLoader, WideGramLoader, WideGramStore>;
-  const size_t inner_smem = sizeof(float) * 2 * WP * LDW;
-  static bool attr_done = false;
-  if (!attr_done) {
-    VVT_TRY(check_cuda(cudaFuncSetAttribute(gram_kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            int(gemm_smem_bytes<float>())), "vvt_syevj(wide gram attr)"));
-    VVT_TRY(check_cuda(cudaFuncSetAttribute(wide_inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            int(inner_smem)), "vvt_syevj(wide inner attr)"));
-    attr_done = true;
-  }
-  int sweeps = 0;
-  while (sweeps < max_sweeps) {
-    VVT_TRY(check_cuda(cudaMemsetAsync(&sc->rotations, 0, sizeof(unsigned long long), s), "vvt_syevj(wide)"));
-    for (int round = 0; round < nbw - 1; ++round) {
-      const WidePanel panel{Y, Np, nbw, round};
-      gram_kern<<<dim3(1, unsigned(splits), unsigned(pairs)), kGemmThreads, gemm_smem_bytes<float>(), s>>>(
-          WideGramLoader{panel}, WideGramLoader{panel}, WideGramStore{part, pairs}, WP, WP, Np, 1, 0, k_per_split);
-      VVT_TRY(launched("vvt_syevj(wide gram)"));
-      wide_inner_kernel<<<unsigned(pairs), 256, inner_smem, s>>>(Qg, flag, part, pairs, splits, inner_sweeps, sc);
-      VVT_TRY(launched("vvt_syevj(wide inner)"));
-      VVT_TRY((launch_gemm_custom<float>(WideApplyLoaderP{panel}, WideApplyLoaderQ{Qg}, WideApplyStore{panel, flag},
-                                         int64_t(Np), int64_t(WP), int64_t(WP), int64_t(pairs), s,
-                                         "vvt_syevj(wide apply)")));
-    }
-    ++sweeps;
-    unsigned long long rot = 0;
-    VVT_TRY(check_cuda(cudaMemcpyAsync(&rot, &sc->rotations, sizeof(rot), cudaMemcpyDeviceToHost, s), "vvt_syevj(wide)"));
-    VVT_TRY(check_cuda(cudaStreamSynchronize(s), "vvt_syevj(wide)"));
-    if (getenv("VVT_SYEVJ_DEBUG"))
-      fprintf(stderr, "[vvt_syevj] wide sweep %d: %llu of %d pair visits rotated (splits %d)\n", sweeps, rot,
-              pairs * (nbw - 1), splits);
-    if (rot <= (unsigned long long)(pairs) * (nbw - 1) / 8) break;  // the 16-wide kernel finishes the tail
-  }
-  *done_sweeps = sweeps;
+  *out = &h;
   return VVT_OK;
 }
 
-
 template <typename T>
-static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char* ws, int* info, int dtype,
+static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int jobz, char* ws, int* info, int dtype,
                       cudaStream_t s) {
-  const JacobiLayout L = jacobi_layout(R, sizeof(T), dtype);
+  const JacobiLayout L = jacobi_layout(R, B, sizeof(T), dtype);
   T* Y = (T*)(ws + L.off_Y);
   T* Gs = (T*)(ws + L.off_Gs);
   T* Jm = (T*)(ws + L.off_Jm);
@@ -1537,86 +1431,93 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   T* Mm = (T*)(ws + L.off_M);
   T* Et = (T*)(ws + L.off_Et);
   T* ev = (T*)(ws + L.off_ev);
+  T* cn = (T*)(ws + L.off_cn);
   int* rank = (int*)(ws + L.off_rank);
   JacobiScalars* sc = (JacobiScalars*)(ws + L.off_sc);
+  int* marks = (int*)(ws + L.off_marks);
+  int* state = (int*)(ws + L.off_state);
   const int Np = int(L.Np), nb = int(L.nb), pairs = nb / 2;
+  const unsigned UB = unsigned(B);
+  const int64_t RR = R * R;
+  HostState* hs = nullptr;
+  VVT_TRY(host_state(&hs));
 
   // Cholesky-preconditioned variant (default): rotate the columns of L, no J; VVT_SYEVJ_NOCHOL=1 selects
-  // the plain W = G J variant
-  static const bool use_chol = getenv("VVT_SYEVJ_NOCHOL") == nullptr;
+  // the plain W = G J variant (16-wide path only)
+  static const bool chol_env = getenv("VVT_SYEVJ_NOCHOL") == nullptr;
+  const bool use_chol = chol_env || L.wide;
   const int parts = use_chol ? 1 : 2;
-  T* cn = (T*)(ws + L.off_cn);
 
-  // rows of the panel are split over the CTAs of a cluster: as many as leave >= 16 rows per CTA
-  // (few CTAs per cluster: every CTA repeats the rotation rounds, and the cluster barriers of the Gram
-  // reduction are the main cost of a round; 640 rows per CTA measured best at R = 1280)
-  // A CTA's time is mostly fixed cost (barriers, rotation rounds, latencies: ~11 us + ~4 ns per row, fp32), so
-  // once a round no longer fits on the GPU the fewest CTAs win: the smallest cluster whose rows still fit in
-  // shared memory (resident variant: 1072 rows fp32, 588 rows fp64).  Measured (fp32, ms): R=2560 CL 3/4/5 =
-  // 94/113/132, R=3840 CL 4/5/8 = 330/360/488, R=5120 CL 5/6/8 = 836/909/1083; fp64 R=2560 CL 4/8 = 458/775.
+  // rows of the panel are split over the CTAs of a cluster.  A CTA's time is mostly fixed cost (barriers,
+  // rotation rounds, latencies: ~11 us + ~4 ns per row, fp32), so once a round no longer fits on the GPU the
+  // fewest CTAs win: the smallest cluster whose rows still fit in shared memory (resident variant: 1072 rows
+  // fp32, 588 rows fp64).  Measured (fp32, ms): R=2560 CL 3/4/5 = 94/113/132, R=3840 CL 4/5/8 = 330/360/488,
+  // R=5120 CL 5/6/8 = 836/909/1083; fp64 R=2560 CL 4/8 = 458/775.
   int CL = 1;
   const int max_rows = sizeof(T) == 4 ? 1024 : 576;
   const int fill_rows = sizeof(T) == 4 ? 80 : 160;  // fp32: R=320 CL 1/4 = 3.8/3.4 ms, R=640 CL 2/4 = 8.6/8.0 ms
   const int fill_max = sizeof(T) == 4 ? 4 : 8;
   while (CL < 8 && ceil_div(Np, CL) > max_rows) ++CL;
-  // SMs left idle by a round (pairs * CL < #SMs) are put to work with a larger, possibly odd cluster, as long
-  // as a CTA keeps enough rows for the Gram / apply phases to outweigh the cluster reduction (R = 1280, fp32:
-  // 3 CTAs x 427 rows on 120 SMs, 16.3 ms against 17.7 ms with 2 x 640 on 80 SMs)
-  while (CL < fill_max && int64_t(pairs) * (CL + 1) <= num_sms() && Np / (CL + 1) >= fill_rows) ++CL;
+  // SMs left idle by a round (pairs * CL * batch < #SMs) are put to work with a larger, possibly odd cluster,
+  // as long as a CTA keeps enough rows for the Gram / apply phases to outweigh the cluster reduction (R = 1280,
+  // fp32: 3 CTAs x 427 rows on 120 SMs, 16.3 ms against 17.7 ms with 2 x 640 on 80 SMs)
+  while (CL < fill_max && int64_t(pairs) * (CL + 1) * B <= num_sms() && Np / (CL + 1) >= fill_rows) ++CL;
   if (const char* e = getenv("VVT_SYEVJ_CL")) CL = vmax(1, vmin(8, atoi(e)));  // experiments
   while (CL > 1 && Np / CL < 16) CL /= 2;
   const int rows_per_cta = int(ceil_div(Np, CL));
   const bool resident = resident_smem_bytes<T>(rows_per_cta, parts) <= size_t(200) * 1024;
 
-  VVT_TRY(check_cuda(cudaMemsetAsync(sc, 0, sizeof(JacobiScalars), s), "vvt_syevj"));
-  int* marks = (int*)(ws + L.off_marks);
-  VVT_TRY(check_cuda(cudaMemsetAsync(marks, 0, size_t(nb + nb * nb) * 4, s), "vvt_syevj"));
-  VVT_TRY(check_cuda(cudaMemsetAsync(ws + L.off_done, 0, size_t(nb) * 4, s), "vvt_syevj"));
+  VVT_TRY(check_cuda(cudaMemsetAsync(sc, 0, size_t(B) * sizeof(JacobiScalars), s), "vvt_syevj"));
+  VVT_TRY(check_cuda(cudaMemsetAsync(marks, 0, size_t(B) * size_t(nb + nb * nb) * 4, s), "vvt_syevj"));
+  VVT_TRY(check_cuda(cudaMemsetAsync(ws + L.off_done, 0, size_t(B) * nb * 4, s), "vvt_syevj"));
   const bool debug = getenv("VVT_SYEVJ_DEBUG") != nullptr;
-  const int init_blocks = int(vmin<int64_t>(ceil_div(L.Np * L.Np, 256), 8 * num_sms()));
-  const int rr_blocks = int(vmin<int64_t>(ceil_div(R * R, 256), 8 * num_sms()));
-  onesided_sym_kernel<T><<<rr_blocks, 256, 0, s>>>(Gs, G, R, sc);
+  const int init_blocks = int(vmin<int64_t>(ceil_div(L.y_elems / 2, 256), 8 * num_sms()));
+  const int rr_blocks = int(vmin<int64_t>(ceil_div(RR, 256), 8 * num_sms()));
+  // one GEMM per problem on the tcgen05 / DMMA kernel when the problems are large, one batched launch otherwise
+  const bool loop_gemm = B == 1 || R >= 1024;
+  auto gemm_batched = [&](T* C, const T* A, const T* Bm, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                          int64_t ldc, double alpha, double beta) -> int {
+    if (loop_gemm) {
+      for (int64_t b = 0; b < B; ++b)
+        VVT_TRY(vvt_gemm(C + b * RR, A + b * RR, Bm + b * RR, M, N, K, 0, 0, lda, ldb, ldc, alpha, beta, 1, 0, 0, 0,
+                         ws + L.off_gemm, L.gemm_bytes, dtype, (void*)s));
+      return VVT_OK;
+    }
+    return vvt_gemm(C, A, Bm, M, N, K, 0, 0, lda, ldb, ldc, alpha, beta, B, RR, RR, RR, nullptr, 0, dtype, (void*)s);
+  };
+
+  onesided_sym_kernel<T><<<dim3(rr_blocks, UB), 256, 0, s>>>(Gs, G, R, sc);
   VVT_TRY(launched("vvt_syevj(sym)"));
   if (use_chol) {
     T* A = Jm;  // free until the gather
-    chol_prepare_kernel<T><<<rr_blocks, 256, 0, s>>>(A, Gs, R, sc);
+    chol_prepare_kernel<T><<<dim3(rr_blocks, UB), 256, 0, s>>>(A, Gs, R, sc);
     VVT_TRY(launched("vvt_syevj(chol prepare)"));
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
-      VVT_TRY(check_cuda(cudaFuncSetAttribute(chol_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              int(chol_smem_bytes<T>())),
-                         "vvt_syevj(chol attr)"));
-      attr_done = true;
-    }
+    static SmemOptIn chol_opt;  // per instantiation
+    VVT_TRY(chol_opt.ensure(chol_panel_kernel<T>, chol_smem_bytes<T>(), "vvt_syevj(chol attr)"));
     for (int64_t k = 0; k < R; k += CB) {
       const int b = int(vmin<int64_t>(CB, R - k));
       const int64_t below = R - k - b;
       const unsigned ctas = unsigned(vmax<int64_t>(1, ceil_div(below, CROWS)));
-      chol_panel_kernel<T><<<ctas, CROWS, chol_smem_bytes<T>(), s>>>(A, R, int(k), b, sc);
+      chol_panel_kernel<T><<<dim3(ctas, UB), CROWS, chol_smem_bytes<T>(), s>>>(A, R, int(k), b, sc);
       VVT_TRY(launched("vvt_syevj(chol panel)"));
       if (below > 0) {  // A22 -= L21 L21^T
         T* A22 = A + (k + b) * R + (k + b);
         const T* L21 = A + (k + b) * R + k;
-        VVT_TRY(vvt_gemm(A22, L21, L21, below, below, b, 0, 0, R, R, R, -1.0, 1.0, 1, 0, 0, 0, ws + L.off_gemm,
-                         L.gemm_bytes, dtype, (void*)s));
+        VVT_TRY(gemm_batched(A22, L21, L21, below, below, b, R, R, R, -1.0, 1.0));
       }
     }
-    onesided_init_chol_kernel<T><<<init_blocks, 256, 0, s>>>(Y, A, R, Np, sc);
-    VVT_TRY(launched("vvt_syevj(init)"));
-  } else {
-    onesided_init_kernel<T><<<init_blocks, 256, 0, s>>>(Y, Gs, R, Np, sc);
-    VVT_TRY(launched("vvt_syevj(init)"));
-  }
-
-  // experimental wide stage (off unless VVT_SYEVJ_WIDE is set; see the block comment above wide_stage)
-  if constexpr (sizeof(T) == 4) {
-    static const char* wide_env = getenv("VVT_SYEVJ_WIDE");
-    if (wide_env && use_chol && Np % WP == 0 && R >= 1024) {
-      const int inner = vmax(1, atoi(wide_env));
-      int wide_sweeps = 0;
-      // scratch in regions that are idle until the gather: Tt (partials), S (Q), M (flags)
-      VVT_TRY(wide_stage((float*)Y, Np, (float*)Tt, (float*)Sm, (int*)Mm, sc, vmin(inner, 4), 16, &wide_sweeps, s));
+    if (L.wide) {
+      if constexpr (sizeof(T) == 4) {
+        wide::wide_init_chol_kernel<<<dim3(init_blocks, UB), 256, 0, s>>>((float*)Y, (const float*)A, R, L.wp.Np, sc);
+        VVT_TRY(launched("vvt_syevj(wide init)"));
+      }
+    } else {
+      onesided_init_chol_kernel<T><<<dim3(init_blocks, UB), 256, 0, s>>>(Y, A, R, Np, sc, L.y_elems);
+      VVT_TRY(launched("vvt_syevj(init)"));
     }
+  } else {
+    onesided_init_kernel<T><<<dim3(init_blocks, UB), 256, 0, s>>>(Y, Gs, R, Np, sc, L.y_elems);
+    VVT_TRY(launched("vvt_syevj(init)"));
   }
 
   // per-block dependencies between rounds (wait_blocks) or the grid-wide dependency of griddepcontrol.wait
@@ -1624,75 +1525,101 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int jobz, char*
   // round fits on the GPU a few times over (measured: R=2560 fp32 131 -> 115 ms, R=1280 fp64 110 -> 74 ms,
   // R=1280 fp32 unchanged) and cost ~7% once a round is many waves (R=5120: 1280 CTAs).
   static const bool block_deps_env = getenv("VVT_SYEVJ_GRIDDEP") == nullptr;
-  const bool block_deps = block_deps_env && int64_t(pairs) * CL <= 4 * int64_t(num_sms());
-  int sweeps = 0, converged = 0;
-  for (; sweeps < kMaxSweeps;) {
-    VVT_TRY(check_cuda(cudaMemsetAsync(&sc->rotations, 0, sizeof(unsigned long long), s), "vvt_syevj"));
-    for (int round = -1; round < nb - 1; ++round)
-      VVT_TRY(launch_round<T>(Y, Np, nb, round, CL, rows_per_cta, parts, resident, sc, marks, sweeps * nb + round + 2,
-                              (T*)(ws + L.off_dc), block_deps ? (unsigned*)(ws + L.off_done) : nullptr, s));
-    ++sweeps;
-    unsigned long long rot = 0;
-    VVT_TRY(check_cuda(cudaMemcpyAsync(&rot, &sc->rotations, sizeof(rot), cudaMemcpyDeviceToHost, s),
-                       "vvt_syevj"));
-    VVT_TRY(check_cuda(cudaStreamSynchronize(s), "vvt_syevj"));
+  const bool block_deps = block_deps_env && int64_t(pairs) * CL * B <= 4 * int64_t(num_sms());
+  const BatchStrides bs{L.y_elems, int64_t(nb + nb * nb), int64_t(nb) * OB * OB, int64_t(nb)};
+  static const int stop_div = getenv("VVT_SYEVJ_STOPDIV") ? vmax(1, atoi(getenv("VVT_SYEVJ_STOPDIV"))) : 256;
+  // both paths count the 16-column block pairs that still rotated; a sweep visits nb16 / 2 * nb16 of them
+  const int64_t nb16 = L.wide ? L.wp.Np / OB : nb;
+  const unsigned long long thresh = (unsigned long long)((nb16 / 2) * nb16) / stop_div;
+  wide::WideMaps maps;
+  if (L.wide) VVT_TRY(wide::wide_make_maps(&maps, (const float*)Y, (const float*)Sm, L.wp, B));
+
+  auto enqueue_sweep = [&](int sweep) -> int {
+    if (L.wide) {
+      if constexpr (sizeof(T) == 4) {
+        for (int round = -1; round < L.wp.nbw - 1; ++round)
+          VVT_TRY(wide::wide_round((float*)Y, (float*)Tt, (float*)Sm, (int*)Mm, sc, L.wp, maps, round, B, s));
+      }
+    } else {
+      for (int round = -1; round < nb - 1; ++round)
+        VVT_TRY(launch_round<T>(Y, Np, nb, round, CL, rows_per_cta, parts, resident, sc, marks, sweep * nb + round + 2,
+                                (T*)(ws + L.off_dc), block_deps ? (unsigned*)(ws + L.off_done) : nullptr, bs, int(B), s));
+    }
+    sweep_end_kernel<<<unsigned(ceil_div(B, 128)), 128, 0, s>>>(sc, int(B), thresh, state);
+    VVT_TRY(launched("vvt_syevj(sweep end)"));
+    int* slot = hs->pinned + (sweep & 1) * 2 * kMaxBatch;
+    VVT_TRY(check_cuda(cudaMemcpyAsync(slot, state, size_t(B) * 2 * sizeof(int), cudaMemcpyDeviceToHost, s), "vvt_syevj"));
+    VVT_TRY(check_cuda(cudaEventRecord(hs->ev[sweep & 1], s), "vvt_syevj"));
+    return VVT_OK;
+  };
+  auto all_converged = [&](int sweep) -> int {  // waits for the state of `sweep`; 1 = every problem is done
+    if (cudaEventSynchronize(hs->ev[sweep & 1]) != cudaSuccess) return -1;
+    const int* slot = hs->pinned + (sweep & 1) * 2 * kMaxBatch;
+    int all = 1;
+    for (int64_t b = 0; b < B; ++b) {
+      all &= slot[2 * b + 1];
+      if (info) info[2 * b] = slot[2 * b], info[2 * b + 1] = slot[2 * b + 1];
+    }
     if (debug) {
       JacobiScalars h;
       cudaMemcpy(&h, sc, sizeof(h), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[vvt_syevj] R=%lld CL=%d sweep %d: %llu of %d block pairs rotated; CTA0 clocks:", (long long)R,
-              CL, sweeps, rot, pairs * nb);
-      for (int i = 1; i < 7; ++i) fprintf(stderr, " %lld", h.t[i] - h.t[i - 1]);
-      long long d[16];
-      cudaMemcpyFromSymbol(d, g_dbg, sizeof(d));
-      fprintf(stderr, " | gram: loop %lld stage %lld bar %lld sum %lld | apply: qfrag %lld (from t5 %lld)", d[1] - d[0],
-              d[2] - d[1], d[3] - d[2], d[4] - d[3], d[6] - d[5], d[5] - h.t[5]);
-      fprintf(stderr, " | reduce: barrier %lld sum %lld", d[7] - h.t[2], d[8] - d[7]);
-      fprintf(stderr, " | chol panel (first): load %lld factor %lld store %lld solve %lld store %lld", d[10] - d[9],
-              d[11] - d[10], d[12] - d[11], d[13] - d[12], d[14] - d[13]);
-      fprintf(stderr, "\n");
+      fprintf(stderr, "[vvt_syevj] R=%lld batch=%lld %s CL=%d sweep %d: %llu of %lld block pairs rotated (problem 0)\n",
+              (long long)R, (long long)B, L.wide ? "wide" : "16-wide", CL, sweep + 1, h.last_rotations,
+              (long long)((nb16 / 2) * nb16));
     }
-    // a sweep that rotated (almost) nothing ends the iteration: the last few block pairs only carry
-    // cosines barely above the threshold, which the refinement step below removes anyway
-    static const int stop_div = getenv("VVT_SYEVJ_STOPDIV") ? vmax(1, atoi(getenv("VVT_SYEVJ_STOPDIV"))) : 256;
-    if (rot <= (unsigned long long)(pairs * nb) / stop_div) {
-      converged = 1;
-      break;
+    return all;
+  };
+  {
+    int sweep = 0, done_flag = 0;
+    VVT_TRY(enqueue_sweep(0));
+    while (true) {
+      const bool more = sweep + 1 < kMaxSweeps;
+      if (more) VVT_TRY(enqueue_sweep(sweep + 1));  // speculative: exits at once if `sweep` was the last one
+      done_flag = all_converged(sweep);
+      if (done_flag < 0) return fail(VVT_ERR_CUDA, "%s: %s", "vvt_syevj", cudaGetErrorString(cudaGetLastError()));
+      if (done_flag || !more) break;
+      ++sweep;
+    }
+    if (!done_flag && sweep + 1 < kMaxSweeps) {  // (not reached: the loop only leaves early when converged)
     }
   }
-  const int gblocks = int(vmin<int64_t>(ceil_div(R * R, 256), 8 * num_sms()));
-  if (use_chol) {
-    onesided_colnorm_kernel<T><<<unsigned(ceil_div(R * 32, 256)), 256, 0, s>>>(cn, Y, R, Np);
+
+  const int gblocks = int(vmin<int64_t>(ceil_div(RR, 256), 8 * num_sms()));
+  if (L.wide) {
+    if constexpr (sizeof(T) == 4) {
+      wide::wide_colnorm_kernel<<<dim3(unsigned(ceil_div(R, 32)), UB), 256, 0, s>>>((float*)cn, (const float*)Y, R, L.wp.Np);
+      VVT_TRY(launched("vvt_syevj(colnorm)"));
+      wide::wide_gather_kernel<<<dim3(unsigned(ceil_div(R, 32)), unsigned(ceil_div(R, 32)), UB), 256, 0, s>>>(
+          (float*)Jm, (float*)Jt, (const float*)Y, (const float*)cn, R, L.wp.Np);
+    }
+  } else if (use_chol) {
+    onesided_colnorm_kernel<T><<<dim3(unsigned(ceil_div(R * 32, 256)), UB), 256, 0, s>>>(cn, Y, R, Np, L.y_elems);
     VVT_TRY(launched("vvt_syevj(colnorm)"));
-    onesided_gather_w_kernel<T><<<gblocks, 256, 0, s>>>(Jm, Jt, Y, cn, R, Np);
+    onesided_gather_w_kernel<T><<<dim3(gblocks, UB), 256, 0, s>>>(Jm, Jt, Y, cn, R, Np, L.y_elems);
   } else {
-    onesided_gather_j_kernel<T><<<gblocks, 256, 0, s>>>(Jm, Jt, Y, R, Np);
+    onesided_gather_j_kernel<T><<<dim3(gblocks, UB), 256, 0, s>>>(Jm, Jt, Y, R, Np, L.y_elems);
   }
   VVT_TRY(launched("vvt_syevj(gather)"));
   // every product below is C = A B^T with K-contiguous operands: the tcgen05 (fp32) / DMMA (fp64) GEMM
-  auto gemm_nt = [&](T* C, const T* A, const T* B, double beta) {
-    return vvt_gemm(C, A, B, R, R, R, 0, 0, R, R, R, 1.0, beta, 1, 0, 0, 0, ws + L.off_gemm, L.gemm_bytes, dtype,
-                    (void*)s);
+  auto gemm_nt = [&](T* C, const T* A, const T* Bm, double beta) {
+    return gemm_batched(C, A, Bm, R, R, R, R, R, R, 1.0, beta);
   };
   VVT_TRY(gemm_nt(Tt, Jt, Gs, 0.0));  // Tt = J^T G   (G symmetric)
-  onesided_rayleigh_kernel<T><<<unsigned(ceil_div(R * 32, 256)), 256, 0, s>>>(ev, Jt, Tt, R, sc);
+  onesided_rayleigh_kernel<T><<<dim3(unsigned(ceil_div(R * 32, 256)), UB), 256, 0, s>>>(ev, Jt, Tt, R, sc);
   VVT_TRY(launched("vvt_syevj(rayleigh)"));
   if (jobz) {
     VVT_TRY(gemm_nt(Sm, Jt, Tt, 0.0));  // S = J^T G J
     VVT_TRY(gemm_nt(Mm, Jt, Jt, 0.0));  // M = J^T J
-    onesided_refine_coeff_kernel<T><<<gblocks, 256, 0, s>>>(Et, Sm, Mm, ev, R, sc);
+    onesided_refine_coeff_kernel<T><<<dim3(gblocks, UB), 256, 0, s>>>(Et, Sm, Mm, ev, R, sc);
     VVT_TRY(launched("vvt_syevj(refine)"));
     VVT_TRY(gemm_nt(Jt, Et, Jm, 1.0));  // J^T += E^T J^T
   }
-  jacobi_rank_kernel<T><<<unsigned(ceil_div(R, 128)), 128, 0, s>>>(rank, ev, R);
+  jacobi_rank_kernel<T><<<dim3(unsigned(ceil_div(R, 128)), UB), 128, 0, s>>>(rank, ev, R);
   VVT_TRY(launched("vvt_syevj(rank)"));
-  const int64_t total = jobz ? R * R : R;
+  const int64_t total = jobz ? RR : R;
   const int pblocks = int(vmin<int64_t>(ceil_div(total, 256), 8 * num_sms()));
-  jacobi_permute_kernel<T><<<pblocks, 256, 0, s>>>(evals, jobz ? evecs : nullptr, ev, Jt, rank, R);
+  jacobi_permute_kernel<T><<<dim3(pblocks, UB), 256, 0, s>>>(evals, jobz ? evecs : nullptr, ev, Jt, rank, R);
   VVT_TRY(launched("vvt_syevj(permute)"));
-  if (info) {
-    info[0] = sweeps;
-    info[1] = converged;
-  }
   return VVT_OK;
 }
 
@@ -1702,37 +1629,65 @@ using namespace vvt;
 
 extern "C" {
 
-int64_t vvt_syevj_workspace_bytes(int64_t R, int jobz, int dtype) {
+int64_t vvt_syevj_batched_workspace_bytes(int64_t R, int64_t batch, int jobz, int dtype) {
   (void)jobz;
-  if (R <= 0) return 0;
-  return jacobi_layout(R, dtype == VVT_F32 ? 4 : 8, dtype).total;
+  if (R <= 0 || batch <= 0) return 0;
+  return jacobi_layout(R, vmin<int64_t>(batch, kMaxBatch), dtype == VVT_F32 ? 4 : 8, dtype).total;
+}
+
+int64_t vvt_syevj_workspace_bytes(int64_t R, int jobz, int dtype) {
+  return vvt_syevj_batched_workspace_bytes(R, 1, jobz, dtype);
+}
+
+int vvt_syevj_batched(void* evals, void* evecs, const void* G, int64_t R, int64_t batch, int jobz, void* workspace,
+                      int64_t workspace_bytes, int* info_host, int dtype, void* stream) {
+  VVT_REQUIRE(R >= 0 && batch >= 0, "negative size");
+  if (info_host)
+    for (int64_t b = 0; b < batch; ++b) info_host[2 * b] = 0, info_host[2 * b + 1] = 1;
+  if (R == 0 || batch == 0) return VVT_OK;
+  VVT_REQUIRE(R <= (int64_t(1) << 15), "matrix too large");
+  VVT_REQUIRE(evals && G && workspace && (!jobz || evecs), "null pointer");
+  if (workspace_bytes < vvt_syevj_batched_workspace_bytes(R, batch, jobz, dtype))
+    return fail(VVT_ERR_WORKSPACE, "%s: workspace too small", __func__);
+  VVT_DISPATCH(dtype, {
+    for (int64_t b0 = 0; b0 < batch; b0 += kMaxBatch) {
+      const int64_t nb = vmin<int64_t>(kMaxBatch, batch - b0);
+      VVT_TRY(syevj_impl<T>((T*)evals + b0 * R, jobz ? (T*)evecs + b0 * R * R : nullptr, (const T*)G + b0 * R * R, R, nb,
+                            jobz, (char*)workspace, info_host ? info_host + 2 * b0 : nullptr, dtype, as_stream(stream)));
+    }
+    return VVT_OK;
+  });
 }
 
 int vvt_syevj(void* evals, void* evecs, const void* G, int64_t R, int jobz, void* workspace,
               int64_t workspace_bytes, int* info_host, int dtype, void* stream) {
-  VVT_REQUIRE(R >= 0, "negative size");
-  if (info_host) info_host[0] = 0, info_host[1] = 1;
-  if (R == 0) return VVT_OK;
-  VVT_REQUIRE(R <= (int64_t(1) << 15), "matrix too large");
-  VVT_REQUIRE(evals && G && workspace && (!jobz || evecs), "null pointer");
-  if (workspace_bytes < vvt_syevj_workspace_bytes(R, jobz, dtype))
-    return fail(VVT_ERR_WORKSPACE, "%s: workspace too small", __func__);
-  VVT_DISPATCH(dtype, {
-    return syevj_impl<T>((T*)evals, (T*)evecs, (const T*)G, R, jobz, (char*)workspace, info_host, dtype,
-                         as_stream(stream));
-  });
+  return vvt_syevj_batched(evals, evecs, G, R, 1, jobz, workspace, workspace_bytes, info_host, dtype, stream);
 }
 
-int vvt_syevj_batched(void* const* evals, void* const* evecs, const void* const* G,
-                      const int64_t* R, int64_t batch, int jobz, void* workspace,
-                      int64_t workspace_bytes, int* info_host, int dtype, void* stream) {
-  VVT_REQUIRE(batch >= 0, "negative size");
-  VVT_REQUIRE(batch == 0 || (evals && G && R), "null pointer");
-  for (int64_t b = 0; b < batch; ++b) {
-    VVT_TRY(vvt_syevj(evals[b], jobz ? evecs[b] : nullptr, G[b], R[b], jobz, workspace,
-                      workspace_bytes, info_host ? info_host + 2 * b : nullptr, dtype, stream));
+// Test hook (not part of include/vivit_b200.h): ONE wide round of the two-level solver on a caller-provided
+// row-major factor L [Np, Np] (Np a multiple of 128), so that tests can check the three kernels one by one:
+// H_out [pairs, 128, 128] = the pair Grams (split-K partials summed), Qt_out [pairs, 128, 128] = Q^T of every
+// pair, flag_out [pairs], and L updated in place.  Allocates its own scratch (debug only).
+__attribute__((visibility("default"))) int vvt_dbg_wide_round(float* L, float* H_out, float* Qt_out, int* flag_out, int64_t Np, int round, void* stream) {
+  VVT_REQUIRE(L && H_out && Qt_out && flag_out && Np > 0 && Np % wide::WP == 0, "bad arguments");
+  cudaStream_t s = as_stream(stream);
+  const wide::WidePlan p = wide::wide_plan(Np, 1);
+  char* scratch = nullptr;
+  VVT_TRY(check_cuda(cudaMalloc(&scratch, size_t(p.part_bytes + 256)), __func__));
+  float* part = (float*)scratch;
+  JacobiScalars* sc = (JacobiScalars*)(scratch + p.part_bytes);
+  int st = check_cuda(cudaMemsetAsync(sc, 0, sizeof(JacobiScalars), s), __func__);
+  wide::WideMaps maps;
+  if (st == VVT_OK) st = wide::wide_make_maps(&maps, L, Qt_out, p, 1);
+  if (st == VVT_OK) st = wide::wide_round(L, part, Qt_out, flag_out, sc, p, maps, round, 1, s);
+  if (st == VVT_OK) {
+    for (int k = 0; k < p.splits && st == VVT_OK; ++k)
+      st = vvt_axpy(H_out, part + size_t(k) * p.pairs * wide::WP * wide::WP, int64_t(p.pairs) * wide::WP * wide::WP, 1.0,
+                    VVT_F32, stream);
   }
-  return VVT_OK;
+  cudaStreamSynchronize(s);
+  cudaFree(scratch);
+  return st;
 }
 
 }  // extern "C"

@@ -1,0 +1,657 @@
+// Two-level ("wide") rounds of the one-sided block Jacobi eigensolver for large fp32 problems (R >= 2048).
+//
+// With 16-column blocks a sweep moves the whole R x R factor R / 16 times and every block pair pays the fixed
+// latency chain of a round; beyond a few thousand columns that is what the solver's time is made of
+// (R = 5120: 449 ms, R = 10240: 5.96 s in round 1).  Here the columns are cut into WIDE blocks of 64; a round
+// pairs the wide blocks (the same round-robin tournament) and is three launches over ALL pairs and all
+// problems of a batch:
+//
+//   1. wide_tc_kernel<GRAM>   H = P^T P of every 128-column pair panel P = [L_a | L_b]   (128 x 128 x R)
+//        tcgen05.mma kind::tf32 with MN-MAJOR operands: the factor stays row-major [row][column], a k-block is
+//        four TMA boxes of 32 rows x 32 columns (128-byte swizzle) which land exactly in the canonical
+//        MN-major SWIZZLE_128B layout (32 contiguous M/N elements x 8 K rows per 1 KB atom, atoms 4 KB apart
+//        along M/N, 1 KB apart along K).  3xTF32 split by the converter warps, split-K over the rows, raw
+//        partial sums to global memory (summed in a fixed order by the next kernel: deterministic).
+//   2. wide_rot_kernel        one CTA (1024 threads) per pair: sums the partials, then diagonalises H by
+//        cyclic-by-blocks two-sided Jacobi on its eight 16-column sub-blocks: four groups of 256 threads run
+//        the scalar rotation rounds of the 16-wide kernel (rotation_rounds, named barriers) on four disjoint
+//        sub-block pairs at a time, then all threads apply the four 32 x 32 rotations to H (both sides) and to
+//        the accumulated Q (128 x 128).  Cross rounds rotate every column of a against every column of b;
+//        the intra round (once per sweep) rotates inside the two wide blocks.  Emits Q^T and a "rotated" flag.
+//   3. wide_tc_kernel<APPLY>  P <- P Q in place: tcgen05, K-major operands (rows of the factor / rows of
+//        Q^T), one CTA per 128 rows x pair, staged coalesced stores.
+//
+// A sweep moves the factor R / 64 times instead of R / 16, all O(R) work is tensor-core GEMM, and the scalar
+// part works on 128 x 128 matrices in shared memory.  Thresholds, rotation formulas and the convergence
+// statistic (16-column block pairs that still rotated) are those of the 16-wide kernel.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace vvt {
+namespace wide {
+
+constexpr int WB = 64;             // wide block (columns)
+constexpr int WP = 2 * WB;         // pair panel
+constexpr int NSUB = WP / OB;      // 16-column sub-blocks of a panel (8)
+constexpr int LDW = WP + 1;        // padded pitch of the 128 x 128 matrices in shared memory
+constexpr int RT = 1024;           // threads of the rotation kernel
+constexpr int NGRP = RT / OT;      // groups of 256 threads (4)
+enum { GRAM = 0, APPLY = 1 };
+
+__host__ __device__ inline void wide_blocks(int nbw, int round, int pair, int& wa, int& wb) {
+  if (round < 0) {
+    wa = 2 * pair;
+    wb = 2 * pair + 1;
+  } else {
+    rr_pair(nbw, round, pair, wa, wb);
+  }
+}
+
+struct WideArgs {
+  float* out;               // GRAM: partial sums [problem][split][pair][128][128];  APPLY: the factor
+  const int* flag;          // APPLY: [problem][pair], 0 = the pair's Gram was already diagonal
+  const JacobiScalars* sc;  // [problem]
+  int64_t l_stride;         // elements between the factors of two problems
+  int Np, nbw, round, pairs, splits, kblocks_total, kblocks_per_split;
+};
+
+// MN-major operand tile: element (mn, k) at  (mn / 32) * 4096 + (k / 8) * 1024 + (k % 8) * 128 + (mn % 32) * 4
+// bytes (before the 128-byte swizzle).  sbo_lbo_swapped: experiments only.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);  // start address
+  d |= uint64_t(4096 >> 4) << 16;             // leading byte offset: 32-element chunks along M/N
+  d |= uint64_t(1024 >> 4) << 32;             // stride byte offset: 8-row groups along K
+  d |= uint64_t(1) << 46;                     // descriptor version (Blackwell)
+  d |= uint64_t(2) << 61;                     // SWIZZLE_128B
+  return d;
+}
+constexpr uint32_t kIdescMN = tc::kIdesc | (1u << 15) | (1u << 16);  // A and B MN-major
+
+template <int MODE>
+__global__ void __launch_bounds__(tc::THREADS, 1)
+wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapQ, WideArgs a) {
+  using namespace tc;
+  extern __shared__ unsigned char smem_raw[];
+  const int prob = blockIdx.z;
+  if (*reinterpret_cast<const volatile int*>(&a.sc[prob].converged)) return;  // uniform over the CTA
+  const int pair = MODE == GRAM ? blockIdx.x : blockIdx.y;
+  const int split = MODE == GRAM ? blockIdx.y : 0;
+  const int rtile = MODE == GRAM ? 0 : blockIdx.x;
+  if (MODE == APPLY && a.flag[prob * a.pairs + pair] == 0) return;
+  int wa, wb;
+  wide_blocks(a.nbw, a.round, pair, wa, wb);
+  constexpr bool diag = MODE == GRAM;  // one operand tile serves as A and B
+  const int kb0 = MODE == GRAM ? split * a.kblocks_per_split : 0;
+  const int nkb = MODE == GRAM ? min(a.kblocks_total, kb0 + a.kblocks_per_split) - kb0 : WP / BK;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  auto bar_tma = [&](int s) { return bars + 8u * s; };
+  auto bar_conv = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto bar_empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  auto bar_acc_full = [&](int b) { return bars + 8u * (3 * STAGES + b); };
+  auto bar_acc_empty = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_tma(s), 1);
+      mbar_init(bar_conv(s), 128);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full(b), 1);
+      mbar_init(bar_acc_empty(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto panel_col = [&](int chunk) {  // first column of the chunk-th group of 32 panel columns
+    return chunk < 2 ? wa * WB + chunk * 32 : wb * WB + (chunk - 2) * 32;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, use = i / STAGES;
+        if (use > 0) mbar_wait(bar_empty(s), (use - 1) & 1);
+        const uint32_t stage = base + s * STAGE_BYTES;
+        if (MODE == GRAM) {  // 32 rows of the factor x the 128 panel columns: four boxes of 32 x 32
+          mbar_expect_tx(bar_tma(s), TILE_BYTES);
+          const int r0 = (kb0 + i) * BK;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_3d(stage + j * 4096, &mapL, bar_tma(s), panel_col(j), r0, prob);
+        } else {  // 128 rows x 32 panel columns of the factor; 128 rows x 32 columns of Q^T
+          mbar_expect_tx(bar_tma(s), 2 * TILE_BYTES);
+          tma_load_3d(stage, &mapL, bar_tma(s), panel_col(i), rtile * BM, prob);
+          tma_load_3d(stage + TILE_BYTES, &mapQ, bar_tma(s), i * BK, 0, prob * a.pairs + pair);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, use = i / STAGES;
+        const int grp = i / PROMOTE, first = (i % PROMOTE) == 0;
+        const uint32_t acc = tmem_base + uint32_t((grp & 1) * BN);
+        const uint32_t stage = base + s * STAGE_BYTES;
+        const uint32_t a_hi = stage, b_hi = diag ? stage : stage + TILE_BYTES;
+        const uint32_t a_lo = stage + 2 * TILE_BYTES, b_lo = diag ? a_lo : stage + 3 * TILE_BYTES;
+        if (first && grp >= 2) {
+          mbar_wait(bar_acc_empty(grp & 1), ((grp >> 1) - 1) & 1);
+          tcgen05_fence_after();
+        }
+        mbar_wait(bar_tma(s), use & 1);
+        tcgen05_fence_after();
+        if (MODE == GRAM) {  // MN-major: 8 rows (K) = one 1 KB atom row group
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)
+            umma_tf32(acc, make_desc_mn(a_hi + 1024 * k), make_desc_mn(b_hi + 1024 * k), kIdescMN, !(first && k == 0));
+          mbar_wait(bar_conv(s), use & 1);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            umma_tf32(acc, make_desc_mn(a_hi + 1024 * k), make_desc_mn(b_lo + 1024 * k), kIdescMN, 1);
+            umma_tf32(acc, make_desc_mn(a_lo + 1024 * k), make_desc_mn(b_hi + 1024 * k), kIdescMN, 1);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)
+            umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_hi + 32 * k), kIdesc, !(first && k == 0));
+          mbar_wait(bar_conv(s), use & 1);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_lo + 32 * k), kIdesc, 1);
+            umma_tf32(acc, make_desc(a_lo + 32 * k), make_desc(b_hi + 32 * k), kIdesc, 1);
+          }
+        }
+        umma_commit(bar_empty(s));
+        if ((i % PROMOTE) == PROMOTE - 1 || i == nkb - 1) umma_commit(bar_acc_full(grp & 1));
+      }
+    }
+  } else {
+    // ===== converters (lo tiles), promotion of finished accumulator groups, epilogue =====
+    const int ct = threadIdx.x - 64;  // 0..127
+    constexpr int n_vec = (diag ? 1 : 2) * (TILE_BYTES / 16);
+    const int lane_grp = warp & 3;
+    const int n_groups = (nkb + PROMOTE - 1) / PROMOTE;
+    float total[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) total[j] = 0.f;
+    auto drain = [&](int grp) {
+      mbar_wait(bar_acc_full(grp & 1), (grp >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t((grp & 1) * BN + c0), r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) total[c0 + j] += __uint_as_float(r[j]);
+      }
+      tcgen05_fence_before();
+      mbar_arrive(bar_acc_empty(grp & 1));
+    };
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES, use = i / STAGES;
+      unsigned char* stage = base_ptr + s * STAGE_BYTES;
+      mbar_wait(bar_tma(s), use & 1);
+#pragma unroll 4
+      for (int v = ct; v < n_vec; v += 128) {
+        const float4 x = *reinterpret_cast<const float4*>(stage + size_t(v) * 16);
+        const float e[4] = {x.x, x.y, x.z, x.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float hi = __uint_as_float(__float_as_uint(e[j]) & 0xFFFFE000u);
+          o[j] = __uint_as_float(__float_as_uint(e[j] - hi) + 0x1000u);
+        }
+        *reinterpret_cast<float4*>(stage + 2 * TILE_BYTES + size_t(v) * 16) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_conv(s));
+      if ((i % PROMOTE) == PROMOTE - 1 && i / PROMOTE >= 1) drain(i / PROMOTE - 1);
+    }
+    for (int g = (nkb % PROMOTE == 0) ? n_groups - 1 : vmax(0, n_groups - 2); g < n_groups; ++g) drain(g);
+    // epilogue: every MMA and every TMA load of this CTA has completed; the stages hold the staged tile
+    float* tile = reinterpret_cast<float*>(base_ptr);
+    const int trow = lane_grp * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < BN; ++j) tile[trow * (BN + 1) + j] = total[j];
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int cw = warp - 2;  // 0..3: this warp stores rows cw, cw + 4, ...; lanes = consecutive columns
+    if (MODE == GRAM) {
+      float* out = a.out + ((size_t(prob) * a.splits + split) * a.pairs + pair) * size_t(WP * WP);
+      for (int r = cw; r < BM; r += 4)
+#pragma unroll
+        for (int q = 0; q < BN / 32; ++q) out[r * WP + lane + 32 * q] = tile[r * (BN + 1) + lane + 32 * q];
+    } else {
+      float* L = a.out + size_t(prob) * a.l_stride + size_t(rtile) * BM * a.Np;
+      for (int r = cw; r < BM; r += 4)
+#pragma unroll
+        for (int q = 0; q < BN / 32; ++q) L[size_t(r) * a.Np + panel_col(q) + lane] = tile[r * (BN + 1) + lane + 32 * q];
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- rotation kernel ----------------------------------------------------------------------------------
+template <int BAR>
+__device__ __forceinline__ void group_sync() {  // the 256 threads of one group
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(OT) : "memory");
+}
+__device__ __forceinline__ void group_sync_dyn(int bar) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(OT) : "memory"); }
+
+struct WideRotSmem {
+  float H[WP][LDW];
+  float Q[WP][LDW];
+  RotSmem<float> rs[NGRP];
+  int sub_a[NGRP], sub_b[NGRP], rot[NGRP];
+  int warp_need[RT / 32];
+  int any;
+};
+
+// sub-block pair of group g in inner round ir (0..3) and whether it is an intra round
+__device__ __forceinline__ void sub_pair(bool intra_round, int ir, int g, int& sa, int& sb, bool& intra) {
+  intra = false;
+  if (!intra_round) {  // every sub-block of a against every sub-block of b
+    sa = g;
+    sb = NSUB / 2 + ((g + ir) & 3);
+  } else if (ir < 3) {  // tournaments inside a (groups 0, 1) and inside b (groups 2, 3)
+    int x, y;
+    rr_pair(NSUB / 2, ir, g & 1, x, y);
+    sa = (g >> 1) * (NSUB / 2) + min(x, y);
+    sb = (g >> 1) * (NSUB / 2) + max(x, y);
+  } else {  // column pairs inside each sub-block
+    sa = 2 * g;
+    sb = 2 * g + 1;
+    intra = true;
+  }
+}
+
+__device__ __forceinline__ int panel_index(int sa, int sb, int k) {  // column of the panel for index k of a sub-pair
+  return k < OB ? sa * OB + k : sb * OB + (k - OB);
+}
+
+// rotation rounds of one group on its 32 x 32 sub-Gram (same arithmetic as the 16-wide kernel; barriers are
+// the group's named barrier instead of __syncthreads)
+template <bool intra>
+__device__ __forceinline__ void group_rotation_rounds(RotSmem<float>& rs, float tol2, float abs2, int gt, int bar) {
+  const int a = gt >> 4, b = gt & 15;
+  constexpr int n_rounds = intra ? OB - 1 : OB;
+  int cur = 0;
+  for (int r = 0; r < n_rounds; ++r, cur ^= 1) {
+    float(*Hc)[LDH] = rs.H[cur];
+    float(*Hn)[LDH] = rs.H[cur ^ 1];
+    int pa, qa, pb, qb;
+    inner_pair(intra, r, a, pa, qa);
+    inner_pair(intra, r, b, pb, qb);
+    const float dpp = Hc[pb][pb], dqq = Hc[qb][qb], dpq = Hc[pb][qb];
+    const float x00 = Hc[pa][pb], x01 = Hc[pa][qb], x10 = Hc[qa][pb], x11 = Hc[qa][qb];
+    float* q0 = &rs.Q[b][0];
+    float* q1 = &rs.Q[b + OB][0];
+    const float q0p = q0[pa], q0q = q0[qa], q1p = q1[pa], q1q = q1[qa];
+    float cb, sb;
+    const bool db = make_rotation(dpp, dqq, dpq, tol2, abs2, cb, sb);
+    const float ca = __shfl_sync(0xffffffffu, cb, a), sa = __shfl_sync(0xffffffffu, sb, a);
+    const float t00 = cb * x00 - sb * x01, t01 = sb * x00 + cb * x01;
+    const float t10 = cb * x10 - sb * x11, t11 = sb * x10 + cb * x11;
+    float h00 = ca * t00 - sa * t10, h01 = ca * t01 - sa * t11;
+    float h10 = sa * t00 + ca * t10, h11 = sa * t01 + ca * t11;
+    if (a == b && db) h01 = h10 = 0.f;
+    Hn[pa][pb] = h00;
+    Hn[pa][qb] = h01;
+    Hn[qa][pb] = h10;
+    Hn[qa][qb] = h11;
+    q0[pa] = ca * q0p - sa * q0q;
+    q0[qa] = sa * q0p + ca * q0q;
+    q1[pa] = ca * q1p - sa * q1q;
+    q1[qa] = sa * q1p + ca * q1q;
+    group_sync_dyn(bar);
+  }
+}
+
+__global__ void __launch_bounds__(RT, 1)
+wide_rot_kernel(float* Qt, int* flag, const float* part, int nbw, int round, int pairs, int splits, JacobiScalars* sc) {
+  extern __shared__ __align__(16) unsigned char wide_smem[];
+  WideRotSmem& sm = *reinterpret_cast<WideRotSmem*>(wide_smem);
+  const int pair = blockIdx.x, prob = blockIdx.y, tid = threadIdx.x;
+  sc += prob;
+  if (*reinterpret_cast<const volatile int*>(&sc->converged)) return;
+  const bool intra_round = round < 0;
+  (void)nbw;
+  const float tol2 = Eps<float>::tol * Eps<float>::tol, abs2 = Eps<float>::v * Eps<float>::v;
+  // H = sum of the split-K partial sums in a fixed order, Q = I
+  {
+    const float* p0 = part + (size_t(prob) * splits * pairs + pair) * size_t(WP * WP);
+    const size_t split_stride = size_t(pairs) * WP * WP;
+    for (int idx = tid; idx < WP * WP / 4; idx += RT) {
+      float4 s4 = *reinterpret_cast<const float4*>(p0 + size_t(idx) * 4);
+      for (int k = 1; k < splits; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(p0 + k * split_stride + size_t(idx) * 4);
+        s4.x += v.x, s4.y += v.y, s4.z += v.z, s4.w += v.w;
+      }
+      const int r = (idx * 4) / WP, c = (idx * 4) % WP;
+      sm.H[r][c] = s4.x, sm.H[r][c + 1] = s4.y, sm.H[r][c + 2] = s4.z, sm.H[r][c + 3] = s4.w;
+      sm.Q[r][c] = r == c ? 1.f : 0.f;
+      sm.Q[r][c + 1] = r == c + 1 ? 1.f : 0.f;
+      sm.Q[r][c + 2] = r == c + 2 ? 1.f : 0.f;
+      sm.Q[r][c + 3] = r == c + 3 ? 1.f : 0.f;
+    }
+    if (tid == 0) sm.any = 0;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < WP * WP; idx += RT) {  // the two triangles differ in the last bits
+    const int r = idx / WP, c = idx % WP;
+    if (r < c) {
+      const float m = 0.5f * (sm.H[r][c] + sm.H[c][r]);
+      sm.H[r][c] = m;
+      sm.H[c][r] = m;
+    }
+  }
+  __syncthreads();
+
+  const int g = tid >> 8, gt = tid & (OT - 1), bar = 1 + g;  // named barriers 1..4 (0 = __syncthreads)
+  RotSmem<float>& rs = sm.rs[g];
+  for (int ir = 0; ir < 4; ++ir) {
+    int sa, sb;
+    bool intra;
+    sub_pair(intra_round, ir, g, sa, sb, intra);
+    // ---- this group's 32 x 32 sub-Gram, Q_sub = I
+    {
+      const int i = gt >> 3, j = (gt & 7) * 4;
+      const int pi = panel_index(sa, sb, i);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        rs.H[0][i][j + e] = sm.H[pi][panel_index(sa, sb, j + e)];
+        rs.Q[i][j + e] = (i == j + e) ? 1.f : 0.f;
+      }
+    }
+    group_sync_dyn(bar);
+    // does any column pair of this visit still need a rotation?  (uniform over the group)
+    {
+      const int i = gt >> 4, j = gt & 15;
+      bool need;
+      if (!intra) {
+        need = needs_rotation(rs.H[0][i][i], rs.H[0][OB + j][OB + j], rs.H[0][i][OB + j], tol2, abs2);
+      } else {
+        need = i < j && (needs_rotation(rs.H[0][i][i], rs.H[0][j][j], rs.H[0][i][j], tol2, abs2) ||
+                         needs_rotation(rs.H[0][OB + i][OB + i], rs.H[0][OB + j][OB + j], rs.H[0][OB + i][OB + j],
+                                        tol2, abs2));
+      }
+      const unsigned w = __ballot_sync(0xffffffffu, need);
+      if ((tid & 31) == 0) sm.warp_need[tid >> 5] = w != 0;
+    }
+    group_sync_dyn(bar);
+    bool rotate = false;
+#pragma unroll
+    for (int w = 0; w < OT / 32; ++w) rotate |= sm.warp_need[g * (OT / 32) + w] != 0;
+    if (rotate) {
+      if (intra) group_rotation_rounds<true>(rs, tol2, abs2, gt, bar);
+      else group_rotation_rounds<false>(rs, tol2, abs2, gt, bar);
+    }
+    if (gt == 0) {
+      sm.sub_a[g] = sa, sm.sub_b[g] = sb, sm.rot[g] = rotate;
+      if (rotate) {
+        atomicAdd(&sc->rotations, 1ull);
+        sm.any = 1;
+      }
+    }
+    __syncthreads();
+    // ---- columns {sa, sb} of H and of Q:  X[:, cols] <- X[:, cols] Q_sub.  Per sub-pair 2 matrices x 128 rows
+    //      x 32 columns of output; a thread owns 4 rows (lane, lane + 32, ...) x 8 columns, a warp one
+    //      (matrix, column group): the Q_sub reads are broadcasts, the X reads conflict-free.  The products stay
+    //      in registers until every thread has read its inputs.
+    {
+      const int ug = tid >> 8, u = tid & 255, v = u & 127, cg = v >> 5, ln = v & 31;
+      const bool on = sm.rot[ug] != 0;
+      float(*X)[LDW] = (u >> 7) ? sm.Q : sm.H;
+      const int sa_u = sm.sub_a[ug], sb_u = sm.sub_b[ug];
+      float acc[4][8];
+      if (on) {
+        const RotSmem<float>& qs = sm.rs[ug];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < OP; ++k) {
+          const int pc = panel_index(sa_u, sb_u, k);
+          const float4 q0 = *reinterpret_cast<const float4*>(&qs.Q[k][8 * cg]);
+          const float4 q1 = *reinterpret_cast<const float4*>(&qs.Q[k][8 * cg + 4]);
+          const float2 qa = make_float2(q0.x, q0.y), qb = make_float2(q0.z, q0.w);
+          const float2 qc = make_float2(q1.x, q1.y), qd = make_float2(q1.z, q1.w);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x = X[ln + 32 * i][pc];
+            const float2 xx = make_float2(x, x);
+            const float2 r0 = __ffma2_rn(xx, qa, make_float2(acc[i][0], acc[i][1]));
+            const float2 r1 = __ffma2_rn(xx, qb, make_float2(acc[i][2], acc[i][3]));
+            const float2 r2 = __ffma2_rn(xx, qc, make_float2(acc[i][4], acc[i][5]));
+            const float2 r3 = __ffma2_rn(xx, qd, make_float2(acc[i][6], acc[i][7]));
+            acc[i][0] = r0.x, acc[i][1] = r0.y, acc[i][2] = r1.x, acc[i][3] = r1.y;
+            acc[i][4] = r2.x, acc[i][5] = r2.y, acc[i][6] = r3.x, acc[i][7] = r3.y;
+          }
+        }
+      }
+      __syncthreads();
+      if (on) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int pc = panel_index(sa_u, sb_u, 8 * cg + j);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) X[ln + 32 * i][pc] = acc[i][j];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- rows {sa, sb} of H:  H[rows, :] <- Q_sub^T H[rows, :].  Per sub-pair 32 rows x 128 columns of output;
+    //      threads 0..127 of the group own 8 rows x 4 columns (lane, lane + 32, ...), a warp one row group.
+    {
+      const int ug = tid >> 8, u = tid & 255, pg = (u >> 5) & 3, ln = u & 31;
+      const bool on = sm.rot[ug] != 0 && u < 128;
+      const int sa_u = sm.sub_a[ug], sb_u = sm.sub_b[ug];
+      float acc[8][4];
+      if (on) {
+        const RotSmem<float>& qs = sm.rs[ug];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < OP; ++k) {
+          const int pr = panel_index(sa_u, sb_u, k);
+          const float4 q0 = *reinterpret_cast<const float4*>(&qs.Q[k][8 * pg]);
+          const float4 q1 = *reinterpret_cast<const float4*>(&qs.Q[k][8 * pg + 4]);
+          const float q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+          const float2 h01 = make_float2(sm.H[pr][ln], sm.H[pr][ln + 32]);
+          const float2 h23 = make_float2(sm.H[pr][ln + 64], sm.H[pr][ln + 96]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 qq = make_float2(q[i], q[i]);
+            const float2 r0 = __ffma2_rn(qq, h01, make_float2(acc[i][0], acc[i][1]));
+            const float2 r1 = __ffma2_rn(qq, h23, make_float2(acc[i][2], acc[i][3]));
+            acc[i][0] = r0.x, acc[i][1] = r0.y, acc[i][2] = r1.x, acc[i][3] = r1.y;
+          }
+        }
+      }
+      __syncthreads();  // every read of the old rows precedes the first write
+      if (on) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int pr = panel_index(sa_u, sb_u, 8 * pg + i);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sm.H[pr][ln + 32 * j] = acc[i][j];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // Q^T to global memory (the apply kernel's B operand: rows = output columns, K-contiguous)
+  const int any = sm.any;
+  if (tid == 0) flag[prob * pairs + pair] = any;
+  if (any) {
+    float* dst = Qt + (size_t(prob) * pairs + pair) * size_t(WP * WP);
+    for (int idx = tid; idx < WP * WP; idx += RT) {
+      const int n = idx / WP, k = idx % WP;
+      dst[idx] = sm.Q[k][n];
+    }
+  }
+}
+
+// ---- layout conversion at both ends ---------------------------------------------------------------------
+// Lw [Np][Np] row-major <- lower triangle of the Cholesky factor A [R][R], scaled, zero elsewhere
+__global__ void wide_init_chol_kernel(float* Lw, const float* A, int64_t R, int Np, const JacobiScalars* sc) {
+  const int64_t total = int64_t(Np) * Np;
+  Lw += blockIdx.y * total, A += blockIdx.y * R * R, sc += blockIdx.y;
+  const double bound = sqrt(double(R)) * sqrt(sc->norm2) + double(R) * double(chol_shift<float>(sc));
+  const float scale = bound > 0.0 ? float(1.0 / sqrt(bound)) : 0.f;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int i = int(idx / Np), j = int(idx % Np);
+    Lw[idx] = (i < R && j <= i) ? A[int64_t(i) * R + j] * scale : 0.f;
+  }
+}
+
+// inv[c] = 1 / ||Lw[:, c]||: a block owns 32 columns, its 8 warps split the rows (coalesced), fixed-order sum
+__global__ void __launch_bounds__(256) wide_colnorm_kernel(float* inv, const float* Lw, int64_t R, int Np) {
+  __shared__ double red[8][32];
+  Lw += blockIdx.y * int64_t(Np) * Np, inv += blockIdx.y * R;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t c = int64_t(blockIdx.x) * 32 + lane;
+  double s = 0.0;
+  if (c < R)
+    for (int64_t r = w; r < R; r += 8) {
+      const double v = double(Lw[r * Np + c]);
+      s += v * v;
+    }
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && c < R) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    inv[c] = t > 0.0 ? float(1.0 / sqrt(t)) : 0.f;
+  }
+}
+
+// Jm[r][c] = Lw[r][c] * inv[c] and its transpose Jt[c][r] (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256) wide_gather_kernel(float* Jm, float* Jt, const float* Lw, const float* inv,
+                                                          int64_t R, int Np) {
+  __shared__ float tile[32][33];
+  Lw += blockIdx.z * int64_t(Np) * Np, inv += blockIdx.z * R, Jm += blockIdx.z * R * R, Jt += blockIdx.z * R * R;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c0 = int64_t(blockIdx.x) * 32, r0 = int64_t(blockIdx.y) * 32;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < R) {
+      v = Lw[r * Np + c] * inv[c];
+      Jm[r * R + c] = v;
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t c = c0 + i, r = r0 + tx;
+    if (r < R && c < R) Jt[c * R + r] = tile[tx][i];
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+struct WidePlan {
+  int Np, nbw, pairs, splits, kblocks, kblocks_per_split;
+  int64_t part_bytes, q_bytes, flag_bytes;
+};
+
+static inline WidePlan wide_plan(int64_t R, int64_t batch) {
+  WidePlan p;
+  p.Np = int(align_up(R, WP));
+  p.nbw = p.Np / WB;
+  p.pairs = p.nbw / 2;
+  p.kblocks = p.Np / tc::BK;
+  // split-K so that pairs x splits x batch fills the SMs about twice, at least 8 k-blocks per CTA
+  int64_t want = ceil_div(2 * int64_t(num_sms()), int64_t(p.pairs) * batch);
+  want = vmax<int64_t>(1, vmin<int64_t>(want, p.kblocks / 8));
+  p.kblocks_per_split = int(ceil_div(p.kblocks, want));
+  p.splits = int(ceil_div(p.kblocks, p.kblocks_per_split));
+  p.part_bytes = align_up(batch * p.splits * p.pairs * int64_t(WP * WP) * 4, 256);
+  p.q_bytes = align_up(batch * p.pairs * int64_t(WP * WP) * 4, 256);
+  p.flag_bytes = align_up(batch * p.pairs * 4, 256);
+  return p;
+}
+
+static inline bool make_map_box(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int64_t batch,
+                                int64_t batch_stride, int box_rows) {
+  tc::EncodeTiledFn fn = tc::encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {cuuint64_t(cols), cuuint64_t(rows), cuuint64_t(batch)};
+  const cuuint64_t strides[2] = {cuuint64_t(ld) * 4, cuuint64_t(batch_stride) * 4};
+  const cuuint32_t box[3] = {tc::BK, cuuint32_t(box_rows), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct WideMaps {
+  CUtensorMap gram, apply, q;
+};
+
+static inline int wide_make_maps(WideMaps* m, const float* Lw, const float* Qt, const WidePlan& p, int64_t batch) {
+  const int64_t ls = int64_t(p.Np) * p.Np;
+  if (!make_map_box(&m->gram, Lw, p.Np, p.Np, p.Np, batch, ls, 32) ||
+      !make_map_box(&m->apply, Lw, p.Np, p.Np, p.Np, batch, ls, tc::BM) ||
+      !make_map_box(&m->q, Qt, WP, WP, WP, batch * p.pairs, int64_t(WP) * WP, tc::BN))
+    return fail(VVT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", "vvt_syevj(wide)");
+  return VVT_OK;
+}
+
+// one round (all pairs, all problems): Gram, rotations, apply
+static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, JacobiScalars* sc, const WidePlan& p,
+                             const WideMaps& m, int round, int64_t batch, cudaStream_t s) {
+  static SmemOptIn opt_g, opt_a, opt_r;
+  VVT_TRY(opt_g.ensure(wide_tc_kernel<GRAM>, tc::SMEM_BYTES, "vvt_syevj(wide gram)"));
+  VVT_TRY(opt_a.ensure(wide_tc_kernel<APPLY>, tc::SMEM_BYTES, "vvt_syevj(wide apply)"));
+  VVT_TRY(opt_r.ensure(wide_rot_kernel, sizeof(WideRotSmem), "vvt_syevj(wide rot)"));
+  WideArgs a;
+  a.flag = flag;
+  a.sc = sc;
+  a.l_stride = int64_t(p.Np) * p.Np;
+  a.Np = p.Np, a.nbw = p.nbw, a.round = round, a.pairs = p.pairs, a.splits = p.splits;
+  a.kblocks_total = p.kblocks, a.kblocks_per_split = p.kblocks_per_split;
+  a.out = part;
+  wide_tc_kernel<GRAM><<<dim3(unsigned(p.pairs), unsigned(p.splits), unsigned(batch)), tc::THREADS, tc::SMEM_BYTES, s>>>(
+      m.gram, m.q, a);
+  VVT_TRY(launched("vvt_syevj(wide gram)"));
+  wide_rot_kernel<<<dim3(unsigned(p.pairs), unsigned(batch)), RT, sizeof(WideRotSmem), s>>>(Qt, flag, part, p.nbw, round,
+                                                                                            p.pairs, p.splits, sc);
+  VVT_TRY(launched("vvt_syevj(wide rot)"));
+  a.out = Lw;
+  wide_tc_kernel<APPLY><<<dim3(unsigned(p.Np / tc::BM), unsigned(p.pairs), unsigned(batch)), tc::THREADS, tc::SMEM_BYTES, s>>>(
+      m.apply, m.q, a);
+  VVT_TRY(launched("vvt_syevj(wide apply)"));
+  return VVT_OK;
+}
+
+}  // namespace wide
+}  // namespace vvt

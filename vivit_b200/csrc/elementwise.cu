@@ -446,26 +446,32 @@ __global__ void filter_nonzero_kernel(uint8_t* mask, const T* ev, int64_t R, T a
 }
 
 // coef[k] = -mean(gammas[:,k]) / (mean(lambdas[:,k]) + deltas[k]) / sqrt(evals[k]);  v = corr * U coef
+// One row of U per thread; the coefficients pass through shared memory in tiles of kCoefTile, so that any
+// number of directions fits.
+constexpr int kCoefTile = 2048;
 template <typename T>
 __global__ void newton_coeff_kernel(T* v, const T* U, const T* gam, const T* lam, const T* del,
                                     const T* ev, int64_t R, int64_t K, int64_t n_g, int64_t n_l, T corr) {
-  extern __shared__ unsigned char sm[];
-  T* coef = reinterpret_cast<T*>(sm);
-  for (int64_t k = threadIdx.x; k < K; k += blockDim.x) {
-    T g = 0, l = 0;
-    for (int64_t m = 0; m < n_g; ++m) g += gam[m * K + k];
-    for (int64_t n = 0; n < n_l; ++n) l += lam[n * K + k];
-    g /= T(n_g);
-    l /= T(n_l);
-    coef[k] = -g / (l + del[k]) / sqrt(ev[k]);
+  __shared__ T coef[kCoefTile];
+  const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  T acc = 0;
+  for (int64_t k0 = 0; k0 < K; k0 += kCoefTile) {
+    const int64_t kn = vmin<int64_t>(kCoefTile, K - k0);
+    __syncthreads();
+    for (int64_t kk = threadIdx.x; kk < kn; kk += blockDim.x) {
+      const int64_t k = k0 + kk;
+      T g = 0, l = 0;
+      for (int64_t m = 0; m < n_g; ++m) g += gam[m * K + k];
+      for (int64_t n = 0; n < n_l; ++n) l += lam[n * K + k];
+      g /= T(n_g);
+      l /= T(n_l);
+      coef[kk] = -g / (l + del[k]) / sqrt(ev[k]);
+    }
+    __syncthreads();
+    if (r < R)
+      for (int64_t kk = 0; kk < kn; ++kk) acc += U[r * K + k0 + kk] * coef[kk];
   }
-  __syncthreads();
-  for (int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; r < R;
-       r += int64_t(gridDim.x) * blockDim.x) {
-    T acc = 0;
-    for (int64_t k = 0; k < K; ++k) acc += U[r * K + k] * coef[k];
-    v[r] = acc * corr;
-  }
+  if (r < R) v[r] = acc * corr;
 }
 
 }  // namespace vvt
@@ -719,10 +725,9 @@ int vvt_newton_coeff(void* v, const void* U, const void* gammas, const void* lam
   VVT_REQUIRE(R >= 0 && K >= 0 && n_g > 0 && N_ggn > 0, "bad size");
   if (R == 0) return VVT_OK;
   VVT_REQUIRE(v && U && gammas && lambdas && deltas && evals, "null pointer");
-  VVT_REQUIRE(K * 8 <= 48 * 1024, "too many directions for the coefficient kernel");
   VVT_DISPATCH(dtype, {
-    const int blocks = int(vmax<int64_t>(1, vmin<int64_t>(ceil_div(R, 256), num_sms())));
-    newton_coeff_kernel<T><<<blocks, 256, size_t(K) * sizeof(T), as_stream(stream)>>>(
+    const unsigned blocks = unsigned(ceil_div(R, 256));
+    newton_coeff_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(
         (T*)v, (const T*)U, (const T*)gammas, (const T*)lambdas, (const T*)deltas, (const T*)evals, R,
         K, n_g, N_ggn, T(corr));
     return launched(__func__);

@@ -392,13 +392,8 @@ inline int launch_gemm_custom(LA la, LB lb, ST st, int64_t M, int64_t N, int64_t
   using Cfg = MmaCfg<T>;
   if (M <= 0 || N <= 0 || batch <= 0) return VVT_OK;
   auto kern = gemm_kernel<T, LA, LB, ST>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    VVT_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            int(gemm_smem_bytes<T>())),
-                       what));
-    attr_done = true;
-  }
+  static SmemOptIn opt_in;  // per template instantiation
+  VVT_TRY(opt_in.ensure(kern, gemm_smem_bytes<T>(), what));
   const int tiles_m = int(ceil_div(M, Cfg::BM)), tiles_n = int(ceil_div(N, Cfg::BN));
   const int64_t k_all = align_up(vmax<int64_t>(K, 1), Cfg::BK);
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {  // gridDim.z limit
@@ -419,13 +414,8 @@ inline int launch_gemm_std(LA la, LB lb, StdStore<T> st, int64_t M, int64_t N, i
   if (M <= 0 || N <= 0 || batch <= 0) return VVT_OK;
   GemmPlan p = plan_gemm<T>(M, N, K, symmetric, batch, workspace ? workspace_bytes : 0);
   auto kern = gemm_kernel<T, LA, LB, StdStore<T>>;
-  static bool attr_done = false;  // per template instantiation
-  if (!attr_done) {
-    VVT_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            int(gemm_smem_bytes<T>())),
-                       what));
-    attr_done = true;
-  }
+  static SmemOptIn opt_in;  // per template instantiation
+  VVT_TRY(opt_in.ensure(kern, gemm_smem_bytes<T>(), what));
   st.N = N;
   st.slab = M * N;
   StdStore<T> kst = st;

@@ -426,11 +426,8 @@ inline int launch_gemm_tc_batched(const float* A, const float* B, ST st, int64_t
                                   const char* what) {
   if (M <= 0 || N <= 0 || batch <= 0) return VVT_OK;
   auto kern = gram_tc_kernel<ST, COL_LANES>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    VVT_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)), what));
-    attr_done = true;
-  }
+  static SmemOptIn opt_in;  // per instantiation
+  VVT_TRY(opt_in.ensure(kern, SMEM_BYTES, what));
   const int tiles_m = int(ceil_div(M, BM)), tiles_n = int(ceil_div(N, BN));
   const int64_t kblocks = vmax<int64_t>(1, ceil_div(K, BK));
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {  // gridDim.z limit

@@ -43,11 +43,8 @@ int launch_gram_tc(const float* A, const float* B, StdStore<float> st, int64_t M
                    const char* what) {
   using namespace tc;
   auto kern = gram_tc_kernel<StdStore<float>, true>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    VVT_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)), what));
-    attr_done = true;
-  }
+  static SmemOptIn opt_in;
+  VVT_TRY(opt_in.ensure(kern, SMEM_BYTES, what));
   CUtensorMap mapA, mapB;
   if (!make_map(&mapA, A, M, K, lda, 1, 0) || !make_map(&mapB, B, N, K, ldb, 1, 0))
     return fail(VVT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", what);

@@ -35,10 +35,21 @@ def _dt(t: Tensor) -> int:
 
 
 def _chk(*tensors: Optional[Tensor]) -> None:
+    """Operands of one kernel call: CUDA, contiguous, one device, ONE floating dtype (the C ABI takes a
+    single dtype enum per call: a float32 factor against a float64 weight would be reinterpreted bitwise),
+    integer operands int64 (index arrays) or uint8 (masks)."""
     dev = None
+    fdt = None
     for t in tensors:
         if t is None:
             continue
+        if t.is_floating_point():
+            if fdt is None:
+                fdt = t.dtype
+            elif t.dtype != fdt:
+                raise TypeError(f"kernel operands have different floating dtypes: {fdt} and {t.dtype}")
+        elif t.dtype not in (torch.int64, torch.uint8, torch.bool):
+            raise TypeError(f"integer kernel operands must be int64 (indices), got {t.dtype}")
         if not t.is_cuda:
             raise _lib.KernelLibraryError(
                 "vivit_b200 kernels run on CUDA tensors only (there is no CPU fallback)"
@@ -410,29 +421,52 @@ def gram_cross_linear_accum(
 # (3) eigensolver
 # --------------------------------------------------------------------------
 
-last_syevj_info = {"sweeps": 0, "converged": True}
+class SyevjNotConverged(RuntimeError):
+    """``vvt_syevj`` ran out of sweeps (the reference's ``Tensor.symeig`` raises ``RuntimeError`` too)."""
 
 
-def syevj(G: Tensor, vectors: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
-    """Ascending eigenvalues (and eigenvectors as columns) of symmetric ``G [R, R]``."""
+def syevj(G: Tensor, vectors: bool = True, return_info: bool = False):
+    """Ascending eigenvalues (and eigenvectors as columns) of symmetric positive semi-definite
+    ``G [R, R]`` (upper triangle read).  Raises ``SyevjNotConverged`` when the sweep limit is hit;
+    ``return_info=True`` appends ``{"sweeps", "converged"}`` and leaves the decision to the caller."""
+    evals, evecs, infos = syevj_batched(G.unsqueeze(0), vectors=vectors, return_info=True, _check=False)
+    info = infos[0]
+    if return_info:
+        return evals[0], (evecs[0] if vectors else None), info
+    if not info["converged"]:
+        raise SyevjNotConverged(f"vvt_syevj did not converge in {info['sweeps']} sweeps (R = {G.shape[0]})")
+    return evals[0], (evecs[0] if vectors else None)
+
+
+def syevj_batched(G: Tensor, vectors: bool = True, return_info: bool = False, _check: bool = True):
+    """Eigendecompositions of ``B`` independent symmetric PSD matrices ``G [B, R, R]`` in ONE call
+    (the per-group Grams of block-diagonal ``param_groups``, ``vivit/utils/hooks.py:214-219``): the batch
+    index is part of every kernel's grid.  Returns ``evals [B, R]`` ascending, ``evecs [B, R, R]``
+    (columns) or ``None``."""
     G = _c(G)
     _chk(G)
-    R = G.shape[0]
-    evals = torch.empty(R, dtype=G.dtype, device=G.device)
-    evecs = torch.empty(R, R, dtype=G.dtype, device=G.device) if vectors else None
-    if R == 0:
-        return evals, evecs
+    if G.dim() != 3 or G.shape[1] != G.shape[2]:
+        raise ValueError(f"expected [B, R, R], got {tuple(G.shape)}")
+    B, R = G.shape[0], G.shape[1]
+    evals = torch.empty(B, R, dtype=G.dtype, device=G.device)
+    evecs = torch.empty(B, R, R, dtype=G.dtype, device=G.device) if vectors else None
+    infos = [{"sweeps": 0, "converged": True} for _ in range(B)]
+    if R == 0 or B == 0:
+        return (evals, evecs, infos) if return_info else (evals, evecs)
     lib = _lib.load()
-    ws = _ws(lib.vvt_syevj_workspace_bytes(R, int(vectors), _dt(G)), G)
-    info = (ctypes.c_int * 2)()
+    ws = _ws(lib.vvt_syevj_batched_workspace_bytes(R, B, int(vectors), _dt(G)), G)
+    info = (ctypes.c_int * (2 * B))()
     with torch.cuda.device(G.device):
-        st = lib.vvt_syevj(
-            _p(evals), _p(evecs), _p(G), R, int(vectors), _p(ws), ws.numel(), info,
+        st = lib.vvt_syevj_batched(
+            _p(evals), _p(evecs), _p(G), R, B, int(vectors), _p(ws), ws.numel(), info,
             _dt(G), _stream(G),
         )
-    _lib.check(st, "vvt_syevj")
-    last_syevj_info["sweeps"], last_syevj_info["converged"] = int(info[0]), bool(info[1])
-    return evals, evecs
+    _lib.check(st, "vvt_syevj_batched")
+    for b in range(B):
+        infos[b] = {"sweeps": int(info[2 * b]), "converged": bool(info[2 * b + 1])}
+    if _check and not return_info and not all(i["converged"] for i in infos):
+        raise SyevjNotConverged(f"vvt_syevj_batched did not converge (R = {R}, batch = {B}): {infos}")
+    return (evals, evecs, infos) if return_info else (evals, evecs)
 
 
 def filter_nonzero(evals: Tensor, atol: float = 1e-7, rtol: float = 1e-5) -> Tensor:
@@ -456,7 +490,8 @@ def filter_nonzero(evals: Tensor, atol: float = 1e-7, rtol: float = 1e-5) -> Ten
 def backtransform_dense(U: Tensor, V: Tensor, norm2: Optional[Tensor]) -> Tensor:
     """``E [K, D] = U [K, R] @ V [R, D]``; adds row squared norms into ``norm2`` (float64 ``[K]``)."""
     U, V = _c(U), _c(V)
-    _chk(U, V, norm2)
+    _chk(U, V)
+    _chk(norm2)  # float64 accumulator whatever the compute dtype
     K, R = U.shape
     D = V.shape[1]
     E = torch.empty(K, D, dtype=V.dtype, device=V.device)
@@ -473,7 +508,8 @@ def backtransform_dense(U: Tensor, V: Tensor, norm2: Optional[Tensor]) -> Tensor
 def backtransform_linear(U: Tensor, S: Tensor, Z: Tensor, norm2: Optional[Tensor]) -> Tensor:
     """``E[k,o,i] = sum_{c,n} U[k,c,n] S[c,n,o] Z[n,i]`` -> ``[K, out, in]``."""
     U, S, Z = _c(U), _c(S), _c(Z)
-    _chk(U, S, Z, norm2)
+    _chk(U, S, Z)
+    _chk(norm2)
     K = U.shape[0]
     C, N, n_out = S.shape
     n_in = Z.shape[1]
@@ -510,7 +546,8 @@ def vt_mat_prod_linear(S: Tensor, Z: Tensor, M: Tensor) -> Tensor:
 
 def scale_rows_rsqrt(E: Tensor, norm2: Tensor) -> Tensor:
     """``E[k] /= sqrt(norm2[k])`` in place (``norm2`` float64)."""
-    _chk(E, norm2)
+    _chk(E)
+    _chk(norm2)
     K = E.shape[0]
     if E.numel() == 0:
         return E
@@ -601,7 +638,7 @@ TIMED = [
     "sqrt_backprop_linear", "sqrt_backprop_conv2d", "sqrt_backprop_elementwise",
     "sqrt_backprop_maxpool2d", "sqrt_backprop_avgpool2d", "v_emit_conv2d", "v_emit_bias",
     "v_emit_linear", "gemm", "gram_dense_accum", "gram_cross_accum", "gram_linear_accum",
-    "gram_cross_linear_accum", "syevj", "filter_nonzero", "backtransform_dense",
+    "gram_cross_linear_accum", "syevj", "syevj_batched", "filter_nonzero", "backtransform_dense",
     "backtransform_linear", "vt_mat_prod_linear", "scale_rows_rsqrt", "dirderiv_epilogue",
     "newton_coeff", "v_apply_dense", "v_apply_linear", "center_rows",
 ]

@@ -12,7 +12,7 @@ from torch.nn import Module, Parameter
 from vivit_b200 import kernels
 from vivit_b200.linalg.eigvalsh import _accumulate_gram, _make_dist
 from vivit_b200.linalg.utils import get_hook_store_batch_size, get_vivit_extension, normalize
-from vivit_b200.utils import delete_savefield
+from vivit_b200.utils import delete_savefield, keep_indices
 from vivit_b200.utils.checks import check_key_exists, check_subsampling_unique, check_unique_params
 from vivit_b200.utils.hooks import ParameterGroupsHook
 
@@ -105,7 +105,7 @@ class EighComputation:
             gram_evals, gram_evecs = kernels.syevj(gram, vectors=True)  # eigh.py:248
 
             keep = group["criterion"](gram_evals)  # eigh.py:252-253
-            keep_idx = torch.as_tensor(keep, dtype=torch.int64, device=gram_evals.device)
+            keep_idx = keep_indices(keep, gram_evals)
             gram_evals = gram_evals.index_select(0, keep_idx)
             if warn_small_eigvals and (gram_evals.abs() < warn_small_eigvals).any():
                 warn(

@@ -17,7 +17,7 @@ from vivit_b200.factors import Factor, GradFactor
 from vivit_b200.linalg.eigvalsh import _make_dist
 from vivit_b200.linalg.utils import get_hook_store_batch_size
 from vivit_b200.optim.utils import get_sqrt_ggn_extension
-from vivit_b200.utils import delete_savefield
+from vivit_b200.utils import delete_savefield, keep_indices
 from vivit_b200.utils.checks import check_key_exists, check_subsampling_unique, check_unique_params
 from vivit_b200.utils.hooks import ParameterGroupsHook
 
@@ -168,9 +168,9 @@ class DirectionalDerivativesComputation:
         evals, evecs = kernels.syevj(gram, vectors=True)  # :291
 
         keep = group["criterion"](evals)  # :293
+        keep_idx = keep_indices(keep, evals)
         if verbose:
-            print(f"Group {gid}: Filter directions ({len(evals)} → {len(keep)})")
-        keep_idx = torch.as_tensor(keep, dtype=torch.int64, device=evals.device)
+            print(f"Group {gid}: Filter directions ({len(evals)} → {keep_idx.numel()})")
         evals = evals.index_select(0, keep_idx)
         evecs = evecs.index_select(1, keep_idx).contiguous()  # [R, K]
 

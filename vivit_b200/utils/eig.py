@@ -40,9 +40,23 @@ def _decompose(matrix: Tensor, eigenvectors: bool, upper: bool) -> Tuple[Tensor,
     if torch.isnan(matrix).any():
         raise RuntimeError("Tensor contains NaNs: True")
     # vvt_syevj reads the upper triangle; the lower one of A is the upper one of A^T
-    evals, evecs = kernels.syevj(matrix if upper else matrix.t().contiguous(), vectors=eigenvectors)
-    if not kernels.last_syevj_info["converged"]:
-        raise RuntimeError("vvt_syevj did not converge. Tensor contains NaNs: False")
+    matrix = matrix if upper else matrix.t().contiguous()
+    # vvt_syevj is a one-sided method for positive semi-definite matrices (Grams); the reference's
+    # ``Tensor.symeig`` takes any symmetric matrix.  A Gershgorin lower bound of the spectrum decides: when
+    # it is negative the decomposition runs on ``A - bound * I`` (positive semi-definite by construction, same
+    # eigenvectors) and the shift is taken off the eigenvalues again.
+    tri = torch.triu(matrix)
+    radius = (tri.abs().sum(0) + tri.abs().sum(1)) - 2 * tri.diagonal().abs()
+    bound = float((tri.diagonal() - radius).min()) if matrix.numel() else 0.0
+    gershgorin = -bound * (1.0 + 1e-6) if bound < 0.0 else 0.0
+    if gershgorin:
+        matrix = shift_diag(matrix, gershgorin)
+    try:
+        evals, evecs = kernels.syevj(matrix, vectors=eigenvectors)
+    except kernels.SyevjNotConverged as e:
+        raise RuntimeError(f"{e}. Tensor contains NaNs: False") from e
+    if gershgorin:
+        evals = evals - gershgorin
     if evecs is None:
         evecs = torch.empty(0, dtype=matrix.dtype, device=matrix.device)
     return evals, evecs
