@@ -1,0 +1,13 @@
+mkdir -p gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name regex:wide -c 90 --csv --log-file gpurun_out/ncu_wide.csv python scratch/eig_time.py 2560 > gpurun_out/ncu_wide.log 2>&1
+tail -3 gpurun_out/ncu_wide.log
+python - <<'PY'
+import csv, collections
+rows = list(csv.reader(open('gpurun_out/ncu_wide.csv')))
+hdr = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
+h = rows[hdr]; ki = h.index('Kernel Name'); vi = h.index('Metric Value'); ui = h.index('Metric Unit')
+agg = collections.defaultdict(list)
+for r in rows[hdr + 1:]:
+    if len(r) > vi: agg[r[ki][:60]].append(float(r[vi].replace(',', '')))
+for k, v in agg.items(): print(k, len(v), 'mean', sum(v) / len(v), 'min', min(v), 'max', max(v), rows[hdr+1][ui])
+PY

@@ -1310,7 +1310,10 @@ namespace vvt {
 constexpr int64_t kMaxBatch = 1024;  // problems per call (larger batches are processed in chunks)
 
 static bool wide_enabled(int64_t R, int dtype) {
-  static const int64_t min_r = getenv("VVT_SYEVJ_WIDE_MIN") ? atoll(getenv("VVT_SYEVJ_WIDE_MIN")) : 2048;
+  // measured (fp32, synthetic spectrum, ms): R = 2560 wide 130 / 16-wide 97, R = 5120 wide 449 / 16-wide 838,
+  // R = 10240 wide 2671 / 16-wide > 6000.  Read per call: tests force the wide path on smaller problems.
+  const char* env = getenv("VVT_SYEVJ_WIDE_MIN");
+  const int64_t min_r = env ? atoll(env) : 4096;
   return dtype == VVT_F32 && R >= min_r && tc::encode_fn() != nullptr;
 }
 

@@ -8,9 +8,9 @@
 //
 //   1. wide_tc_kernel<GRAM>   H = P^T P of every 128-column pair panel P = [L_a | L_b]   (128 x 128 x R)
 //        tcgen05.mma kind::tf32 with MN-MAJOR operands: the factor stays row-major [row][column], a k-block is
-//        four TMA boxes of 32 rows x 32 columns (128-byte swizzle) which land exactly in the canonical
-//        MN-major SWIZZLE_128B layout (32 contiguous M/N elements x 8 K rows per 1 KB atom, atoms 4 KB apart
-//        along M/N, 1 KB apart along K).  3xTF32 split by the converter warps, split-K over the rows, raw
+//        four TMA boxes of 32 rows x 32 columns (128-byte swizzle with 32-byte atoms) which land exactly in
+//        the canonical MN-major SWIZZLE_128B_BASE32B layout, the only one the tensor core takes for MN-major
+//        tf32 (see make_desc_mn).  3xTF32 split by the converter warps, split-K over the rows, raw
 //        partial sums to global memory (summed in a fixed order by the next kernel: deterministic).
 //   2. wide_rot_kernel        one CTA (1024 threads) per pair: sums the partials, then diagonalises H by
 //        cyclic-by-blocks two-sided Jacobi on its eight 16-column sub-blocks: four groups of 256 threads run
@@ -53,17 +53,25 @@ struct WideArgs {
   const JacobiScalars* sc;  // [problem]
   int64_t l_stride;         // elements between the factors of two problems
   int Np, nbw, round, pairs, splits, kblocks_total, kblocks_per_split;
+  int variant;  // experiments (VVT_WIDE_DESC): descriptor encodings of the MN-major Gram operands
 };
 
-// MN-major operand tile: element (mn, k) at  (mn / 32) * 4096 + (k / 8) * 1024 + (k % 8) * 128 + (mn % 32) * 4
-// bytes (before the 128-byte swizzle).  sbo_lbo_swapped: experiments only.
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+// MN-major fp32 (tf32) operands have ONE legal shared-memory layout on sm_100: 128-byte swizzle with 32-byte
+// atomicity (UMMA layout type SWIZZLE_128B_BASE32B = 1, TMA swizzle CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; with
+// the plain SWIZZLE_128B type the tensor core returns zeros -- measured).  Canonical form
+// ((4,8,m),(4,k)) : ((1,4,LBO),(32,SBO)) in elements: 32 contiguous M/N elements (128 bytes) x 4 K rows of 128
+// bytes per 512-byte atom, 32-byte chunks XOR-ed with the row index mod 4.  A TMA box of 32 rows x 32 columns
+// of the row-major factor lands in exactly this form: K groups of 4 rows 512 bytes apart (SBO), the four
+// 32-column chunks of a panel are separate boxes 4096 bytes apart (LBO).  One MMA (K = 8) spans two K groups;
+// the next k-step starts 1024 bytes further.  variant: experiments only.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, int variant = 0) {
+  const uint32_t lbo = variant == 1 ? 512 : 4096, sbo = variant == 1 ? 4096 : (variant == 4 ? 1024 : 512);
   uint64_t d = 0;
   d |= uint64_t((smem_addr & 0x3FFFF) >> 4);  // start address
-  d |= uint64_t(4096 >> 4) << 16;             // leading byte offset: 32-element chunks along M/N
-  d |= uint64_t(1024 >> 4) << 32;             // stride byte offset: 8-row groups along K
+  d |= uint64_t(lbo >> 4) << 16;              // leading byte offset: 32-element chunks along M/N
+  d |= uint64_t(sbo >> 4) << 32;              // stride byte offset: 4-row groups along K
   d |= uint64_t(1) << 46;                     // descriptor version (Blackwell)
-  d |= uint64_t(2) << 61;                     // SWIZZLE_128B
+  d |= uint64_t(1) << 61;                     // SWIZZLE_128B_BASE32B
   return d;
 }
 constexpr uint32_t kIdescMN = tc::kIdesc | (1u << 15) | (1u << 16);  // A and B MN-major
@@ -156,16 +164,24 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
         }
         mbar_wait(bar_tma(s), use & 1);
         tcgen05_fence_after();
-        if (MODE == GRAM) {  // MN-major: 8 rows (K) = one 1 KB atom row group
+        if (MODE == GRAM && a.variant >= 2) {  // experiments: K-major descriptors on the MN-major data
+          const uint32_t id = a.variant == 2 ? kIdescMN : kIdesc;
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k)
-            umma_tf32(acc, make_desc_mn(a_hi + 1024 * k), make_desc_mn(b_hi + 1024 * k), kIdescMN, !(first && k == 0));
+            umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_hi + 32 * k), id, !(first && k == 0));
+          mbar_wait(bar_conv(s), use & 1);
+          tcgen05_fence_after();
+        } else if (MODE == GRAM) {  // MN-major: 8 rows (K) = one 1 KB atom row group
+          const int vr = a.variant;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)
+            umma_tf32(acc, make_desc_mn(a_hi + 1024 * k, vr), make_desc_mn(b_hi + 1024 * k, vr), kIdescMN, !(first && k == 0));
           mbar_wait(bar_conv(s), use & 1);
           tcgen05_fence_after();
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
-            umma_tf32(acc, make_desc_mn(a_hi + 1024 * k), make_desc_mn(b_lo + 1024 * k), kIdescMN, 1);
-            umma_tf32(acc, make_desc_mn(a_lo + 1024 * k), make_desc_mn(b_hi + 1024 * k), kIdescMN, 1);
+            umma_tf32(acc, make_desc_mn(a_hi + 1024 * k, vr), make_desc_mn(b_lo + 1024 * k, vr), kIdescMN, 1);
+            umma_tf32(acc, make_desc_mn(a_lo + 1024 * k, vr), make_desc_mn(b_hi + 1024 * k, vr), kIdescMN, 1);
           }
         } else {
 #pragma unroll
@@ -328,6 +344,99 @@ __device__ __forceinline__ void group_rotation_rounds(RotSmem<float>& rs, float 
   }
 }
 
+// The two update phases are separate NON-INLINED functions: the kernel runs 1024 threads (64 registers each)
+// and keeps a dozen values live across its inner rounds; inlined, the 32 accumulators of a phase ended up in
+// local memory (measured: 570 us per launch instead of ~40).  Inside a call they have the register file to
+// themselves.
+//
+// Columns {sa, sb} of H and of Q:  X[:, cols] <- X[:, cols] Q_sub.  Per sub-pair 2 matrices x 128 rows x 32
+// columns of output; a thread owns 4 rows (lane, lane + 32, ...) x 8 columns, a warp one (matrix, column group):
+// the Q_sub reads are broadcasts, the X reads conflict-free.  The products stay in registers until every thread
+// has read its inputs (barrier inside).
+__device__ __noinline__ void update_columns(WideRotSmem& sm, int tid) {
+  const int ug = tid >> 8, u = tid & 255, v = u & 127, cg = v >> 5, ln = v & 31;
+  const bool on = sm.rot[ug] != 0;
+  float(*X)[LDW] = (u >> 7) ? sm.Q : sm.H;
+  const int sa_u = sm.sub_a[ug], sb_u = sm.sub_b[ug];
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  if (on) {
+    const float* q = &sm.rs[ug].Q[0][8 * cg];
+#pragma unroll 2
+    for (int k = 0; k < OP; ++k) {
+      const int pc = panel_index(sa_u, sb_u, k);
+      const float4 q0 = *reinterpret_cast<const float4*>(q + k * LDQ);
+      const float4 q1 = *reinterpret_cast<const float4*>(q + k * LDQ + 4);
+      const float2 qa = make_float2(q0.x, q0.y), qb = make_float2(q0.z, q0.w);
+      const float2 qc = make_float2(q1.x, q1.y), qd = make_float2(q1.z, q1.w);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x = X[ln + 32 * i][pc];
+        const float2 xx = make_float2(x, x);
+        const float2 r0 = __ffma2_rn(xx, qa, make_float2(acc[i][0], acc[i][1]));
+        const float2 r1 = __ffma2_rn(xx, qb, make_float2(acc[i][2], acc[i][3]));
+        const float2 r2 = __ffma2_rn(xx, qc, make_float2(acc[i][4], acc[i][5]));
+        const float2 r3 = __ffma2_rn(xx, qd, make_float2(acc[i][6], acc[i][7]));
+        acc[i][0] = r0.x, acc[i][1] = r0.y, acc[i][2] = r1.x, acc[i][3] = r1.y;
+        acc[i][4] = r2.x, acc[i][5] = r2.y, acc[i][6] = r3.x, acc[i][7] = r3.y;
+      }
+    }
+  }
+  __syncthreads();
+  if (on) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int pc = panel_index(sa_u, sb_u, 8 * cg + j);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) X[ln + 32 * i][pc] = acc[i][j];
+    }
+  }
+}
+
+// Rows {sa, sb} of H:  H[rows, :] <- Q_sub^T H[rows, :].  Per sub-pair 32 rows x 128 columns of output; threads
+// 0..127 of the group own 8 rows x 4 columns (lane, lane + 32, ...), a warp one row group.
+__device__ __noinline__ void update_rows(WideRotSmem& sm, int tid) {
+  const int ug = tid >> 8, u = tid & 255, pg = (u >> 5) & 3, ln = u & 31;
+  const bool on = sm.rot[ug] != 0 && u < 128;
+  const int sa_u = sm.sub_a[ug], sb_u = sm.sub_b[ug];
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  if (on) {
+    const float* q = &sm.rs[ug].Q[0][8 * pg];
+#pragma unroll 2
+    for (int k = 0; k < OP; ++k) {
+      const int pr = panel_index(sa_u, sb_u, k);
+      const float4 q0 = *reinterpret_cast<const float4*>(q + k * LDQ);
+      const float4 q1 = *reinterpret_cast<const float4*>(q + k * LDQ + 4);
+      const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      const float2 h01 = make_float2(sm.H[pr][ln], sm.H[pr][ln + 32]);
+      const float2 h23 = make_float2(sm.H[pr][ln + 64], sm.H[pr][ln + 96]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 qq = make_float2(qv[i], qv[i]);
+        const float2 r0 = __ffma2_rn(qq, h01, make_float2(acc[i][0], acc[i][1]));
+        const float2 r1 = __ffma2_rn(qq, h23, make_float2(acc[i][2], acc[i][3]));
+        acc[i][0] = r0.x, acc[i][1] = r0.y, acc[i][2] = r1.x, acc[i][3] = r1.y;
+      }
+    }
+  }
+  __syncthreads();  // every read of the old rows precedes the first write
+  if (on) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int pr = panel_index(sa_u, sb_u, 8 * pg + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sm.H[pr][ln + 32 * j] = acc[i][j];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(RT, 1)
 wide_rot_kernel(float* Qt, int* flag, const float* part, int nbw, int round, int pairs, int splits, JacobiScalars* sc) {
   extern __shared__ __align__(16) unsigned char wide_smem[];
@@ -415,93 +524,9 @@ wide_rot_kernel(float* Qt, int* flag, const float* part, int nbw, int round, int
       }
     }
     __syncthreads();
-    // ---- columns {sa, sb} of H and of Q:  X[:, cols] <- X[:, cols] Q_sub.  Per sub-pair 2 matrices x 128 rows
-    //      x 32 columns of output; a thread owns 4 rows (lane, lane + 32, ...) x 8 columns, a warp one
-    //      (matrix, column group): the Q_sub reads are broadcasts, the X reads conflict-free.  The products stay
-    //      in registers until every thread has read its inputs.
-    {
-      const int ug = tid >> 8, u = tid & 255, v = u & 127, cg = v >> 5, ln = v & 31;
-      const bool on = sm.rot[ug] != 0;
-      float(*X)[LDW] = (u >> 7) ? sm.Q : sm.H;
-      const int sa_u = sm.sub_a[ug], sb_u = sm.sub_b[ug];
-      float acc[4][8];
-      if (on) {
-        const RotSmem<float>& qs = sm.rs[ug];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll 1
-        for (int k = 0; k < OP; ++k) {
-          const int pc = panel_index(sa_u, sb_u, k);
-          const float4 q0 = *reinterpret_cast<const float4*>(&qs.Q[k][8 * cg]);
-          const float4 q1 = *reinterpret_cast<const float4*>(&qs.Q[k][8 * cg + 4]);
-          const float2 qa = make_float2(q0.x, q0.y), qb = make_float2(q0.z, q0.w);
-          const float2 qc = make_float2(q1.x, q1.y), qd = make_float2(q1.z, q1.w);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float x = X[ln + 32 * i][pc];
-            const float2 xx = make_float2(x, x);
-            const float2 r0 = __ffma2_rn(xx, qa, make_float2(acc[i][0], acc[i][1]));
-            const float2 r1 = __ffma2_rn(xx, qb, make_float2(acc[i][2], acc[i][3]));
-            const float2 r2 = __ffma2_rn(xx, qc, make_float2(acc[i][4], acc[i][5]));
-            const float2 r3 = __ffma2_rn(xx, qd, make_float2(acc[i][6], acc[i][7]));
-            acc[i][0] = r0.x, acc[i][1] = r0.y, acc[i][2] = r1.x, acc[i][3] = r1.y;
-            acc[i][4] = r2.x, acc[i][5] = r2.y, acc[i][6] = r3.x, acc[i][7] = r3.y;
-          }
-        }
-      }
-      __syncthreads();
-      if (on) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int pc = panel_index(sa_u, sb_u, 8 * cg + j);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) X[ln + 32 * i][pc] = acc[i][j];
-        }
-      }
-    }
+    update_columns(sm, tid);
     __syncthreads();
-    // ---- rows {sa, sb} of H:  H[rows, :] <- Q_sub^T H[rows, :].  Per sub-pair 32 rows x 128 columns of output;
-    //      threads 0..127 of the group own 8 rows x 4 columns (lane, lane + 32, ...), a warp one row group.
-    {
-      const int ug = tid >> 8, u = tid & 255, pg = (u >> 5) & 3, ln = u & 31;
-      const bool on = sm.rot[ug] != 0 && u < 128;
-      const int sa_u = sm.sub_a[ug], sb_u = sm.sub_b[ug];
-      float acc[8][4];
-      if (on) {
-        const RotSmem<float>& qs = sm.rs[ug];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 1
-        for (int k = 0; k < OP; ++k) {
-          const int pr = panel_index(sa_u, sb_u, k);
-          const float4 q0 = *reinterpret_cast<const float4*>(&qs.Q[k][8 * pg]);
-          const float4 q1 = *reinterpret_cast<const float4*>(&qs.Q[k][8 * pg + 4]);
-          const float q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-          const float2 h01 = make_float2(sm.H[pr][ln], sm.H[pr][ln + 32]);
-          const float2 h23 = make_float2(sm.H[pr][ln + 64], sm.H[pr][ln + 96]);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 qq = make_float2(q[i], q[i]);
-            const float2 r0 = __ffma2_rn(qq, h01, make_float2(acc[i][0], acc[i][1]));
-            const float2 r1 = __ffma2_rn(qq, h23, make_float2(acc[i][2], acc[i][3]));
-            acc[i][0] = r0.x, acc[i][1] = r0.y, acc[i][2] = r1.x, acc[i][3] = r1.y;
-          }
-        }
-      }
-      __syncthreads();  // every read of the old rows precedes the first write
-      if (on) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int pr = panel_index(sa_u, sb_u, 8 * pg + i);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) sm.H[pr][ln + 32 * j] = acc[i][j];
-        }
-      }
-    }
+    update_rows(sm, tid);
     __syncthreads();
   }
   // Q^T to global memory (the apply kernel's B operand: rows = output columns, K-contiguous)
@@ -589,11 +614,20 @@ static inline WidePlan wide_plan(int64_t R, int64_t batch) {
   p.nbw = p.Np / WB;
   p.pairs = p.nbw / 2;
   p.kblocks = p.Np / tc::BK;
-  // split-K so that pairs x splits x batch fills the SMs about twice, at least 8 k-blocks per CTA
-  int64_t want = ceil_div(2 * int64_t(num_sms()), int64_t(p.pairs) * batch);
-  want = vmax<int64_t>(1, vmin<int64_t>(want, p.kblocks / 8));
-  p.kblocks_per_split = int(ceil_div(p.kblocks, want));
-  p.splits = int(ceil_div(p.kblocks, p.kblocks_per_split));
+  // split-K over the rows: one CTA per SM is resident, so the kernel runs in waves of num_sms CTAs; take the
+  // split count (at least 4 k-blocks per CTA) that minimises waves x (k-blocks per CTA + prologue / epilogue)
+  {
+    const int64_t sms = num_sms(), tiles = int64_t(p.pairs) * batch;
+    int64_t best = 1, best_cost = INT64_MAX;
+    for (int64_t sp = 1; sp <= vmax<int64_t>(1, p.kblocks / 4); ++sp) {
+      const int64_t per = ceil_div(p.kblocks, sp);
+      const int64_t ctas = tiles * ceil_div(p.kblocks, per);
+      const int64_t cost = ceil_div(ctas, sms) * (per + 8);
+      if (cost < best_cost) best_cost = cost, best = sp;
+    }
+    p.kblocks_per_split = int(ceil_div(p.kblocks, best));
+    p.splits = int(ceil_div(p.kblocks, p.kblocks_per_split));
+  }
   p.part_bytes = align_up(batch * p.splits * p.pairs * int64_t(WP * WP) * 4, 256);
   p.q_bytes = align_up(batch * p.pairs * int64_t(WP * WP) * 4, 256);
   p.flag_bytes = align_up(batch * p.pairs * 4, 256);
@@ -601,7 +635,7 @@ static inline WidePlan wide_plan(int64_t R, int64_t batch) {
 }
 
 static inline bool make_map_box(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int64_t batch,
-                                int64_t batch_stride, int box_rows) {
+                                int64_t batch_stride, int box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   tc::EncodeTiledFn fn = tc::encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[3] = {cuuint64_t(cols), cuuint64_t(rows), cuuint64_t(batch)};
@@ -609,7 +643,7 @@ static inline bool make_map_box(CUtensorMap* map, const float* ptr, int64_t rows
   const cuuint32_t box[3] = {tc::BK, cuuint32_t(box_rows), 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -619,7 +653,9 @@ struct WideMaps {
 
 static inline int wide_make_maps(WideMaps* m, const float* Lw, const float* Qt, const WidePlan& p, int64_t batch) {
   const int64_t ls = int64_t(p.Np) * p.Np;
-  if (!make_map_box(&m->gram, Lw, p.Np, p.Np, p.Np, batch, ls, 32) ||
+  const int variant = getenv("VVT_WIDE_DESC") ? atoi(getenv("VVT_WIDE_DESC")) : 0;
+  if (!make_map_box(&m->gram, Lw, p.Np, p.Np, p.Np, batch, ls, 32,
+                    variant >= 2 && variant != 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
       !make_map_box(&m->apply, Lw, p.Np, p.Np, p.Np, batch, ls, tc::BM) ||
       !make_map_box(&m->q, Qt, WP, WP, WP, batch * p.pairs, int64_t(WP) * WP, tc::BN))
     return fail(VVT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", "vvt_syevj(wide)");
@@ -639,6 +675,7 @@ static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, Jacob
   a.l_stride = int64_t(p.Np) * p.Np;
   a.Np = p.Np, a.nbw = p.nbw, a.round = round, a.pairs = p.pairs, a.splits = p.splits;
   a.kblocks_total = p.kblocks, a.kblocks_per_split = p.kblocks_per_split;
+  a.variant = getenv("VVT_WIDE_DESC") ? atoi(getenv("VVT_WIDE_DESC")) : 0;
   a.out = part;
   wide_tc_kernel<GRAM><<<dim3(unsigned(p.pairs), unsigned(p.splits), unsigned(batch)), tc::THREADS, tc::SMEM_BYTES, s>>>(
       m.gram, m.q, a);
