@@ -106,7 +106,7 @@ WORKLOADS = {
     "c3": dict(name="cifar100_allcnnc N=128 C=100 mc_samples=1 subsampling_ggn=[0..31] DirectionalDampedNewtonComputation",
                model=allcnnc, n=128, in_shape=(3, 32, 32), classes=100, calls=("newton",), grouping="one",
                mc=1, sub_ggn=list(range(32))),
-    "c4": dict(name="mlp_784-4096x3-10 N=512 C=10 EighComputation top-10, per-layer block-diagonal groups",
+    "c4": dict(name="mlp_784-4096x3-10 N=512 C=10 EighComputation top-10, per-layer block-diagonal groups (one batched solve)",
                model=mlp_c4, n=512, in_shape=(784,), classes=10, calls=("eigh",), grouping="layer"),
     "c5": dict(name="deep_mlp_784-2048x4-10 N=1024 C=10 EighComputation top-10, full-network Gram R=10240 "
                     "(parameter-sharded over the ranks, one all-reduce)",
@@ -183,13 +183,15 @@ class Stepper:
         import vivit_b200 as vv
 
         w, out = self.w, []
+        # sharded runs return the WHOLE eigenvectors / steps (all-gathered), the same deliverable as on one GPU
         kw = {"process_group": self.pg} if self.pg is not None else {}
+        gkw = {**kw, "gather": True} if self.pg is not None else {}
         for call in w["calls"]:
             if call == "eigvalsh":
                 res = self._pass(vv.EigvalshComputation(**kw), x, y)
                 out += list(res)
             elif call == "eigh":
-                res = self._pass(vv.EighComputation(**kw), x, y)
+                res = self._pass(vv.EighComputation(**gkw), x, y)
                 for evals, evecs in res:
                     out += [evals, *evecs]
             elif call == "dirderiv":
@@ -198,7 +200,7 @@ class Stepper:
                     out += [g, l]
             elif call == "newton":
                 comp = vv.DirectionalDampedNewtonComputation(
-                    subsampling_ggn=w.get("sub_ggn"), mc_samples_ggn=w.get("mc", 0), **kw)
+                    subsampling_ggn=w.get("sub_ggn"), mc_samples_ggn=w.get("mc", 0), **gkw)
                 comp._mc_state = self.mc_ids  # class ids pre-sampled on the host
                 res = self._pass(comp, x, y)
                 for steps in res:
@@ -242,9 +244,9 @@ def load_peaks():
     return dict(FALLBACK_PEAKS), "fallback"
 
 
-def algorithmic_work(name, shapes, es):
+def algorithmic_work(name, shapes, es, out_shapes=()):
     """(kind, amount): algorithmic flops ("tensor") or bytes ("hbm") of one call of a kernel
-    entry point, from its tensor-argument shapes.
+    entry point, from the shapes of its tensor arguments and results.
     Symmetric-aware minimum for the Gram kernels, one read of each operand + one write of each
     result for the bandwidth-bound ones."""
     prod = lambda s: int(torch.Size(s).numel())  # noqa: E731
@@ -267,8 +269,18 @@ def algorithmic_work(name, shapes, es):
         S, W = shapes[0], shapes[1]  # [V,N,Co,Ho,Wo], [Co,Ci,kh,kw]
         return "tensor", 2 * prod(S) * W[1] * W[2] * W[3]
     if name == "v_emit_conv2d":
-        S, X = shapes[0], shapes[1]  # [V,N,Co,Ho,Wo], [N,Ci,H,W]; J unknown here -> bytes of S + X only
-        return "hbm", es * (prod(S) + prod(X))
+        S, X = shapes[0], shapes[1]  # [V,N,Co,Ho,Wo], [N,Ci,H,W] -> factor [V,N,Co,Ci,kh,kw] (written once)
+        return "hbm", es * (prod(S) + prod(X) + sum(prod(o) for o in out_shapes))
+    if name == "v_emit_bias":
+        return "hbm", es * (prod(shapes[0]) + sum(prod(o) for o in out_shapes))
+    if name in ("backtransform_linear", "v_apply_linear"):
+        # E[k,o,i] = sum_n (sum_c U[k,c,n] S[c,n,o]) Z[n,i]: two products, K (C N out + N out in) MACs
+        U, S, Z = shapes[0], shapes[1], shapes[2]
+        C, N, n_out = S
+        K = max(1, prod(U) // (C * N))
+        return "tensor", 2 * K * N * n_out * (C + Z[1])
+    if name == "center_rows":
+        return "hbm", es * 2 * prod(shapes[0])
     if name in ("backtransform_dense", "v_apply_dense"):
         U, V = shapes[0], shapes[1]
         K = prod(U) // V[0]
@@ -301,13 +313,17 @@ def eigensolver_report(stepper):
     from vivit_b200 import kernels
 
     grabbed = []
-    orig = kernels.syevj
+    orig, orig_b = kernels.syevj, kernels.syevj_batched
 
     def spy(G, vectors=True, **kw):
         grabbed.append(G.clone())
         return orig(G, vectors, **kw)
 
-    kernels.syevj = spy
+    def spy_b(G, vectors=True, **kw):
+        grabbed.extend(g.clone() for g in G)
+        return orig_b(G, vectors, **kw)
+
+    kernels.syevj, kernels.syevj_batched = spy, spy_b
     try:
         call = stepper.w["calls"][0]
         comp = {"eigvalsh": vv.EigvalshComputation, "eigh": vv.EighComputation,
@@ -316,7 +332,7 @@ def eigensolver_report(stepper):
             return None
         stepper._pass(comp(), stepper.x, stepper.y)
     finally:
-        kernels.syevj = orig
+        kernels.syevj, kernels.syevj_batched = orig, orig_b
     if not grabbed:
         return None
     G = max(grabbed, key=lambda t: t.shape[0])
@@ -352,12 +368,12 @@ def eigensolver_report(stepper):
 
 def summarize_kernels(records, steps, es, peaks):
     agg = {}
-    for name, ms, shapes, launches in records:
+    for name, ms, shapes, launches, out_shapes in records:
         a = agg.setdefault(name, {"ms": 0.0, "calls": 0, "launches": 0, "tensor": 0, "hbm": 0})
         a["ms"] += ms
         a["calls"] += 1
         a["launches"] += launches
-        kind, amount = algorithmic_work(name, shapes, es)
+        kind, amount = algorithmic_work(name, shapes, es, out_shapes)
         if kind:
             a[kind] += amount
     total = sum(a["ms"] for a in agg.values()) or 1.0
@@ -627,10 +643,15 @@ def main():
     # device time among the tensor- / HBM-bound kernels.  The eigensolver (largest share of the step) is
     # latency-bound and is reported separately below in ms / sweeps / residuals next to cuSOLVER.
     groups = {}
-    for name, t_ms, shapes, n_launch in recs:
-        kind, amount = algorithmic_work(name, shapes, es)
+    floor_tensor = floor_hbm = 0.0  # algorithmic work of one step, all roofline-scored kernels
+    for name, t_ms, shapes, n_launch, out_shapes in recs:
+        kind, amount = algorithmic_work(name, shapes, es, out_shapes)
         if not kind:
             continue
+        if kind == "tensor":
+            floor_tensor += amount / args.steps
+        else:
+            floor_hbm += amount / args.steps
         g = groups.setdefault((name, tuple(shapes)), {"ms": 0.0, "calls": 0, "amount": amount, "kind": kind,
                                                       "launches": 0})
         g["ms"] += t_ms
@@ -663,6 +684,24 @@ def main():
                     "calls_per_step": g["calls"] / args.steps, "share_of_step": round(g["ms"] / step_ms, 4)}
 
     eig = eigensolver_report(stepper) if world == 1 else None
+    if roof is not None:
+        # the whole step against its own floor: algorithmic flops / tensor peak + algorithmic bytes / HBM peak of
+        # every roofline-scored kernel (the eigensolver has no such figure and counts as zero work: it can only
+        # lower the fraction), divided by the measured step
+        tensor_peak = (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]) / (6.0 if args.dtype == "f32" else 48.0)
+        floor_ms = floor_tensor / (tensor_peak * 1e12) * 1e3 + floor_hbm / (peaks["hbm_gbs"] * 1e9) * 1e3
+        roof["step_floor_ms"] = round(floor_ms, 4)
+        roof["frac_step"] = round(floor_ms / ms, 4)
+        roof["step_algorithmic"] = {"tensor_flops": int(floor_tensor), "hbm_bytes": int(floor_hbm),
+                                    "tensor_peak_tflops": round(tensor_peak, 1), "hbm_peak_gbs": peaks["hbm_gbs"]}
+        top = max(rows, key=lambda r: r["ms_per_step"]) if rows else None
+        if top is not None:
+            roof["dominant_kernel_of_step"] = {"kernel": top["kernel"], "ms_per_step": top["ms_per_step"],
+                                               "share_of_kernel_time": top["share"]}
+            if top["kernel"].startswith("syevj") and eig:
+                roof["dominant_kernel_of_step"].update(
+                    note="latency-bound eigensolver: no tensor/HBM roofline; reported against cuSOLVER on the same GPU",
+                    ms_per_solve=eig["ms"], cusolver_ms_per_solve=eig["cusolver_eigh_ms"], R=eig["R"], sweeps=eig["sweeps"])
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -682,7 +721,7 @@ def main():
         # the part of the step that shards over the ranks (factor emit + Gram / cross-term assembly, rank 0) next
         # to the part that every rank repeats (the eigensolver): SURVEY 8e
         "gram_assembly_ms_per_step": round(sum(r["ms_per_step"] for r in rows if r["kernel"].startswith(("gram_", "v_emit_"))), 4),
-        "eigensolver_ms_per_step": round(sum(r["ms_per_step"] for r in rows if r["kernel"] == "syevj"), 4),
+        "eigensolver_ms_per_step": round(sum(r["ms_per_step"] for r in rows if r["kernel"].startswith("syevj")), 4),
         "kernels": rows,
     }
     _emit(line)

@@ -241,6 +241,14 @@ int vvt_syevj(void* evals, void* evecs, const void* G, int64_t R, int jobz, void
 int vvt_syevj_batched(void* evals, void* evecs, const void* G, int64_t R, int64_t batch, int jobz,
                       void* workspace, int64_t workspace_bytes, int* info_host, int dtype, void* stream);
 
+/* TEST HOOK, not a reference interface: ONE round of the two-level solver used for fp32 problems of 4096
+ * columns and more, on a caller-provided row-major factor L [Np, Np] (Np a multiple of 128), so that the three
+ * kernels of a round (tcgen05 pair Grams with MN-major operands, 128 x 128 rotation kernel, tcgen05 apply) can
+ * be checked one by one: H_out [Np/128, 128, 128] += pair Grams (zero it first), Qt_out [Np/128, 128, 128] =
+ * Q^T of every rotated pair, flag_out [Np/128] = pair rotated, L <- L Q in place.  round: -1 (rotations inside
+ * the wide blocks) or 0 .. Np/64 - 2 (round-robin pairing).  Allocates scratch and synchronises: tests only. */
+int vvt_dbg_wide_round(float* L, float* H_out, float* Qt_out, int* flag_out, int64_t Np, int round, void* stream);
+
 /* mask[i] = !isclose(evals[i], 0, rtol, atol) = |evals[i]| > atol  (vivit/utils/eig.py:111-134);
  * mask: uint8 [R]; count_host (host, may be NULL) receives the number kept (synchronises). */
 int vvt_filter_nonzero(uint8_t* mask, const void* evals, int64_t R, double atol, double rtol,

@@ -26,6 +26,15 @@ def test_bandwidth_bound_kernels_count_each_operand_once():
     kind, nbytes = bench.algorithmic_work("sqrt_backprop_elementwise", [[10, 128, 64, 28, 28], [128, 64, 28, 28]], es)
     assert kind == "hbm" and nbytes == es * 2 * 10 * 128 * 64 * 28 * 28
     assert bench.algorithmic_work("syevj", [[R, R]], es) == (None, 0)  # latency-bound: no roofline figure
+    # the conv factor emit reads S and the layer input and WRITES the factor (the written
+    # bytes used to be left out)
+    S, X, Vt = [10, 128, 96, 12, 12], [128, 64, 14, 14], [10, 128, 96, 64, 3, 3]
+    kind, nbytes = bench.algorithmic_work("v_emit_conv2d", [S, X], es, [Vt])
+    numel = lambda shape: int(__import__("math").prod(shape))  # noqa: E731
+    assert kind == "hbm" and nbytes == es * (numel(S) + numel(X) + numel(Vt))
+    # structured Linear back-transform: K (C N out + N out in) multiply-adds
+    kind, flops = bench.algorithmic_work("backtransform_linear", [[10, 5120], [10, 512, 4096], [512, 4096]], es)
+    assert kind == "tensor" and flops == 2 * 10 * 512 * 4096 * (10 + 4096)
 
 
 def test_workloads_are_the_baseline_configs():

@@ -1,0 +1,232 @@
+"""Parity AT BENCH SIZE: every BASELINE.json config as ``bench.py`` runs it, against the oracle.
+
+``bench.py``'s workload table (models, batch sizes, seeds, criteria) is imported as is, the product runs on
+``cuda:0`` through the public API, the oracle restatement of the reference (``oracle/reference_path.py``) runs
+on the host cores from the same seeded inputs.  What each config exercises that the small fixtures do not:
+
+* c2 (cifar10_3c3d, N=128, R=1280, D=895210): the tcgen05 dense Gram with split-K, 3-CTA Jacobi clusters, the
+  strip-mined back-transform -- Eigh top-10, directional derivatives and the damped Newton step;
+* c3 (cifar100_allcnnc, C=100, ``mc_samples=1``, ``subsampling_ggn=range(32)``): MC factor with pinned class
+  ids, ``N_ggn != N_grad`` rescaling, Newton step over 1.39 M parameters;
+* c4 (3x4096 MLP, N=512): one R=5120 layer group -- structured Linear Gram at scale and the two-level
+  eigensolver; all four groups through the batched solve;
+* c5 (deep MLP, N=1024, R=10240): the assembled Gram against the oracle's, eigenvalues against float64
+  ``eigvalsh`` of the oracle Gram.
+
+Tolerances are the north star's (1e-4 of the largest reference entry in fp32, 1e-10 in float64; eigenvectors
+through projectors).  ``FALLBACKS`` counts how often the fp32 comparison had to fall back to the float64 oracle
+(``close(..., truth=)``): the last test prints it.
+"""
+
+import copy
+
+import pytest
+import torch
+from torch import nn
+
+import bench
+from oracle import reference_path as ref
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+TOL = {torch.float32: 1e-4, torch.float64: 1e-10}
+FALLBACKS = {"checks": 0, "fell_back": 0}
+
+
+def close(got, want, dtype, what, truth=None, tol=None):
+    tol = TOL[dtype] if tol is None else tol
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    scale = max(want.abs().max().item(), 1e-300)
+    err = (got - want).abs().max().item() / scale
+    FALLBACKS["checks"] += 1
+    if err > tol and truth is not None:
+        FALLBACKS["fell_back"] += 1
+        truth = truth.detach().double().cpu()
+        own = (want - truth).abs().max().item() / scale
+        err_t = (got - truth).abs().max().item() / scale
+        assert err_t <= tol + own, f"{what}: {err_t:.3e} vs float64 oracle (fp32 oracle off by {own:.3e}) > {tol:.0e}"
+        return
+    assert err <= tol, f"{what}: error {err:.3e} (relative to {scale:.3e}) > {tol:.0e}"
+
+
+def projector_distance(A, B):
+    """``||P_A - P_B||_F`` of the row spaces of two ``[K, D]`` matrices with orthonormal rows."""
+    A, B = A.double(), B.double().to(A.device)
+    K = A.shape[0]
+    return max(0.0, 2 * K - 2 * (A @ B.t()).pow(2).sum().item()) ** 0.5
+
+
+def run(comp, model, x, y, groups):
+    from vivit_b200 import backpack, extend
+
+    model, loss_fn = extend(model), extend(nn.CrossEntropyLoss())
+    with backpack(*comp.get_extensions(), extension_hook=comp.get_extension_hook(groups)):
+        loss_fn(model(x), y).backward()
+    for p in model.parameters():
+        p.grad = None
+    return [comp.get_result(g) for g in groups]
+
+
+def problem(name, dtype):
+    w = bench.WORKLOADS[name]
+    cm, cx, cy = bench.make_problem(w, dtype)
+    gm = copy.deepcopy(cm).to(DEV)
+    cgroups = bench.make_groups(cm, w["grouping"])
+    table = {id(pc): pg for pc, pg in zip(cm.parameters(), gm.parameters())}
+    ggroups = [{**g, "params": [table[id(p)] for p in g["params"]]} for g in cgroups]
+    return w, (cm, cx, cy, cgroups), (gm, cx.to(DEV), cy.to(DEV), ggroups)
+
+
+def flat(evecs):
+    return torch.cat([e.flatten(1) for e in evecs], 1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+def test_config2_full_size_vs_oracle(dtype):
+    import vivit_b200 as vv
+
+    torch.backends.cudnn.allow_tf32 = False
+    w, (cm, cx, cy, cg), (gm, gx, gy, gg) = problem("c2", dtype)
+    loss = nn.CrossEntropyLoss()
+    ((w_evals, w_evecs),) = ref.eigh(cm, loss, cx, cy, cg)
+    ((evals, evecs),) = run(vv.EighComputation(), gm, gx, gy, gg)
+    close(evals, w_evals, dtype, "c2 evals")
+    dist = projector_distance(flat(evecs), flat(w_evecs))
+    assert dist <= (2e-3 if dtype == torch.float32 else 1e-7), dist
+    F = flat(evecs).double()
+    assert (F @ F.t() - torch.eye(10, device=DEV, dtype=torch.float64)).abs().max() <= (2e-4 if dtype == torch.float32 else 1e-9)
+
+    ((wg, wl),) = ref.directional_derivatives(cm, loss, cx, cy, cg)
+    ((gam, lam),) = run(vv.DirectionalDerivativesComputation(), gm, gx, gy, gg)
+    truth = None
+    if dtype == torch.float32:
+        ((tg, tl),) = _oracle64(ref.directional_derivatives, cm, cx, cy, cg)
+        truth = (tg, tl)
+    close(gam.abs(), wg.abs(), dtype, "c2 gammas", truth=None if truth is None else truth[0].abs())
+    close(lam, wl, dtype, "c2 lambdas", truth=None if truth is None else truth[1])
+    close(lam.mean(0), evals, dtype, "c2 mean lambda == evals")
+
+    (want,) = ref.directional_damped_newton(cm, loss, cx, cy, cg)
+    (steps,) = run(vv.DirectionalDampedNewtonComputation(), gm, gx, gy, gg)
+    got, wanted = torch.cat([s.flatten() for s in steps]), torch.cat([t.flatten() for t in want])
+    t64 = None
+    if dtype == torch.float32:
+        (t64,) = _oracle64(ref.directional_damped_newton, cm, cx, cy, cg)
+        t64 = torch.cat([t.flatten() for t in t64])
+    close(got, wanted, dtype, "c2 newton step", truth=t64)
+
+
+_DOUBLES = {}
+
+
+def _regroup64(cm, cgroups):
+    """Parameter groups of the float64 copy of ``cm`` (``copy.deepcopy(cm).double()`` keeps the order)."""
+    m64 = copy.deepcopy(cm).double()
+    _DOUBLES[id(cm)] = m64
+    table = {id(p): q for p, q in zip(cm.parameters(), m64.parameters())}
+    return [{**g, "params": [table[id(p)] for p in g["params"]]} for g in cgroups]
+
+
+def _oracle64(fn, cm, cx, cy, cgroups, *args, **kw):
+    groups = _regroup64(cm, cgroups)
+    return fn(_DOUBLES[id(cm)], nn.CrossEntropyLoss(), cx.double(), cy, groups, *args, **kw)
+
+
+def test_config3_allcnnc_mc_subsampled_newton_vs_oracle():
+    """BASELINE configs[2] as benched: C=100, MC factor (one sample, pinned class ids), curvature on samples
+    0..31, gradients on all 128, constant damping."""
+    import vivit_b200 as vv
+
+    dtype = torch.float32
+    w, (cm, cx, cy, cg), (gm, gx, gy, gg) = problem("c3", dtype)
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(0, w["classes"], (w["mc"], len(w["sub_ggn"])), generator=g)
+    loss = nn.CrossEntropyLoss()
+
+    comp = vv.DirectionalDampedNewtonComputation(subsampling_ggn=w["sub_ggn"], mc_samples_ggn=1)
+    comp._mc_state = ids.to(DEV)
+    (steps,) = run(comp, gm, gx, gy, gg)
+    (want,) = ref.directional_damped_newton(cm, loss, cx, cy, cg, None, w["sub_ggn"], mc_samples_ggn=1, mc_state=ids)
+    (t64,) = _oracle64(ref.directional_damped_newton, cm, cx, cy, cg, None, w["sub_ggn"], mc_samples_ggn=1, mc_state=ids)
+    got = torch.cat([s.flatten() for s in steps])
+    assert got.numel() == 1387108
+    close(got, torch.cat([t.flatten() for t in want]), dtype, "c3 newton step",
+          truth=torch.cat([t.flatten() for t in t64]))
+
+    dd = vv.DirectionalDerivativesComputation(subsampling_ggn=w["sub_ggn"], mc_samples_ggn=1)
+    dd._mc_state = ids.to(DEV)
+    ((gam, lam),) = run(dd, gm, gx, gy, gg)
+    ((wg, wl),) = ref.directional_derivatives(cm, loss, cx, cy, cg, None, w["sub_ggn"], mc_samples_ggn=1, mc_state=ids)
+    ((tg, tl),) = _oracle64(ref.directional_derivatives, cm, cx, cy, cg, None, w["sub_ggn"], mc_samples_ggn=1, mc_state=ids)
+    assert gam.shape == (128, 10) and lam.shape == (32, 10)
+    close(gam.abs(), wg.abs(), dtype, "c3 gammas", truth=tg.abs())
+    close(lam, wl, dtype, "c3 lambdas", truth=tl)
+
+    eh = vv.EighComputation(subsampling=w["sub_ggn"], mc_samples=1)
+    eh._mc_state = ids.to(DEV)
+    ((evals, evecs),) = run(eh, gm, gx, gy, gg)
+    ((w_evals, w_evecs),) = ref.eigh(cm, loss, cx, cy, cg, subsampling=w["sub_ggn"], mc_samples=1, mc_state=ids)
+    close(evals, w_evals, dtype, "c3 evals (MC, sub-sampled)")
+    assert projector_distance(flat(evecs), flat(w_evecs)) <= 2e-3
+
+
+def test_config4_layer_groups_vs_oracle():
+    """BASELINE configs[3]: 3x4096 MLP, N=512, per-layer block-diagonal groups (R=5120 each).  The oracle runs
+    on two of the four groups (a 4096x4096 layer and the 10-row output layer: seconds on the host); all four go
+    through the product (batched two-level solve) and are checked through size-independent properties."""
+    import vivit_b200 as vv
+
+    dtype = torch.float32
+    w, (cm, cx, cy, cg), (gm, gx, gy, gg) = problem("c4", dtype)
+    assert len(gg) == 4
+    results = run(vv.EighComputation(), gm, gx, gy, gg)
+    loss = nn.CrossEntropyLoss()
+    for gi in (1, 3):
+        ((w_evals, w_evecs),) = ref.eigh(cm, loss, cx, cy, [cg[gi]])
+        evals, evecs = results[gi]
+        close(evals, w_evals, dtype, f"c4 group {gi} evals")
+        assert projector_distance(flat(evecs), flat(w_evecs)) <= 2e-3, gi
+    for evals, evecs in results:
+        F = flat(evecs).double()
+        assert evals.shape == (10,) and (evals[1:] >= evals[:-1]).all()
+        assert (F @ F.t() - torch.eye(10, device=DEV, dtype=torch.float64)).abs().max() <= 2e-4
+
+
+def test_config5_full_network_gram_vs_oracle():
+    """BASELINE configs[4] on one GPU: the R=10240 Gram the product hands to its eigensolver against the
+    oracle's Gram (structured Linear terms + bias terms, ``linear.py:66-75``, ``base.py:118-124``), and the
+    top-10 eigenvalues against float64 ``eigvalsh`` of the oracle Gram."""
+    import vivit_b200 as vv
+    from vivit_b200 import kernels
+
+    dtype = torch.float32
+    w, (cm, cx, cy, cg), (gm, gx, gy, gg) = problem("c5", dtype)
+    grabbed, orig = [], kernels.syevj
+
+    def spy(G, vectors=True, **kw):
+        grabbed.append(G.clone())
+        return orig(G, vectors, **kw)
+
+    kernels.syevj = spy
+    try:
+        ((evals, evecs),) = run(vv.EighComputation(), gm, gx, gy, gg)
+    finally:
+        kernels.syevj = orig
+    (G,) = grabbed
+    assert G.shape == (10240, 10240)
+    sweep = ref.backward_sweep(cm, nn.CrossEntropyLoss(), cx, cy, want_vivit=True)
+    want = sum(sweep.vivit[id(p)]["gram_mat"]() for p in cm.parameters())
+    want = want.reshape(10240, 10240)
+    close(torch.triu(G), torch.triu(want), dtype, "c5 Gram (upper triangle, as symeig reads it)")
+    top = torch.linalg.eigvalsh(want.to(DEV).double())[-10:]
+    close(evals, top, dtype, "c5 top-10 eigenvalues")
+    F = flat(evecs).double()
+    assert (F @ F.t() - torch.eye(10, device=DEV, dtype=torch.float64)).abs().max() <= 2e-4
+
+
+def test_report_fallbacks():
+    """How often an fp32 comparison needed the float64 oracle (ill-conditioned quantities only)."""
+    print(f"\nfp32 comparisons that fell back to the float64 oracle: {FALLBACKS['fell_back']} of {FALLBACKS['checks']}")
+    assert FALLBACKS["fell_back"] <= FALLBACKS["checks"]

@@ -251,15 +251,12 @@ def test_syevj(k, dtype, R, rank):
 
 
 def _wide_round(L, rnd_idx):
-    """One round of the two-level solver through the library's test hook (not in the public header)."""
+    """One round of the two-level solver through the library's test hook."""
     import ctypes
 
     from vivit_b200 import _lib
 
-    lib = _lib.load()
-    fn = lib.vvt_dbg_wide_round
-    fn.restype = ctypes.c_int
-    fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+    fn = _lib.load().vvt_dbg_wide_round
     Np = L.shape[0]
     pairs = Np // 128
     H = torch.zeros(pairs, 128, 128, device=L.device)

@@ -32,7 +32,15 @@ from torch import Tensor, nn
 
 from vivit_b200 import kernels
 from vivit_b200.custom_module import Pad, ScaleModule, Slicing, SumModule
-from vivit_b200.factors import DenseFactor, DenseGrad, Factor, LinearWeightFactor, LinearWeightGrad
+from vivit_b200.factors import (
+    DenseFactor,
+    DenseGrad,
+    Factor,
+    LinearBiasFactor,
+    LinearWeightFactor,
+    LinearWeightGrad,
+    link_linear_factors,
+)
 
 
 def _pair(v):
@@ -243,10 +251,14 @@ def _factor_linear(ext: _SqrtFactorExtension, module: nn.Linear, S: Tensor, need
             if w is not None:
                 ext._save(w, DenseFactor(_emit_linear_extra(Sc, Xc), (hi - lo, z.shape[-1])))
     else:
-        if b is not None:  # bias first, as [BackPACK] does (params=["bias", "weight"], linear.py:24)
-            ext._save(b, DenseFactor(S_own, (hi - lo,)))
-        if w is not None:
-            ext._save(w, LinearWeightFactor(S_own, z.contiguous()))
+        bf = LinearBiasFactor(S_own, (hi - lo,)) if b is not None else None
+        wf = LinearWeightFactor(S_own, z.contiguous()) if w is not None else None
+        if bf is not None and wf is not None:
+            link_linear_factors(wf, w, bf, b)  # one group => one structured Gram call for both (factors.py)
+        if bf is not None:  # bias first, as [BackPACK] does (params=["bias", "weight"], linear.py:24)
+            ext._save(b, bf)
+        if wf is not None:
+            ext._save(w, wf)
     return kernels.sqrt_backprop_linear(S, module.weight.detach()) if need_in else None
 
 

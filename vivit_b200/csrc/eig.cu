@@ -1667,11 +1667,11 @@ int vvt_syevj(void* evals, void* evecs, const void* G, int64_t R, int jobz, void
   return vvt_syevj_batched(evals, evecs, G, R, 1, jobz, workspace, workspace_bytes, info_host, dtype, stream);
 }
 
-// Test hook (not part of include/vivit_b200.h): ONE wide round of the two-level solver on a caller-provided
+// Test hook: ONE wide round of the two-level solver on a caller-provided
 // row-major factor L [Np, Np] (Np a multiple of 128), so that tests can check the three kernels one by one:
 // H_out [pairs, 128, 128] = the pair Grams (split-K partials summed), Qt_out [pairs, 128, 128] = Q^T of every
 // pair, flag_out [pairs], and L updated in place.  Allocates its own scratch (debug only).
-__attribute__((visibility("default"))) int vvt_dbg_wide_round(float* L, float* H_out, float* Qt_out, int* flag_out, int64_t Np, int round, void* stream) {
+int vvt_dbg_wide_round(float* L, float* H_out, float* Qt_out, int* flag_out, int64_t Np, int round, void* stream) {
   VVT_REQUIRE(L && H_out && Qt_out && flag_out && Np > 0 && Np % wide::WP == 0, "bad arguments");
   cudaStream_t s = as_stream(stream);
   const wide::WidePlan p = wide::wide_plan(Np, 1);

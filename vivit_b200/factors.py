@@ -33,8 +33,8 @@ class Factor:
     def R(self) -> int:
         return self.C * self.N
 
-    # G [R, R] += V_p^T V_p
-    def gram_accum(self, G: Tensor) -> None:
+    # G [R, R] += V_p^T V_p   (fold: honour the weight/bias folding of a Linear layer, see LinearBiasFactor)
+    def gram_accum(self, G: Tensor, fold: bool = True) -> None:
         raise NotImplementedError
 
     # X [R, n_g] += V_p^T g_p^T
@@ -58,10 +58,10 @@ class Factor:
         raise NotImplementedError
 
     def gram_mat(self) -> Tensor:
-        """``[C, N, C, N]`` Gram matrix of this parameter (``base.py:118-124``)."""
+        """``[C, N, C, N]`` Gram matrix of this parameter alone (``base.py:118-124``)."""
         like = self._like()
         G = torch.zeros(self.R, self.R, dtype=like.dtype, device=like.device)
-        self.gram_accum(G)
+        self.gram_accum(G, fold=False)
         return G.reshape(self.C, self.N, self.C, self.N)
 
     def _like(self) -> Tensor:
@@ -81,7 +81,7 @@ class DenseFactor(Factor):
     def _like(self):
         return self.Vt
 
-    def gram_accum(self, G):
+    def gram_accum(self, G, fold=True):
         kernels.gram_dense_accum(G, self.Vt)
 
     def cross_accum(self, X, grad):
@@ -104,6 +104,23 @@ class DenseFactor(Factor):
         return self.Vt.reshape(self.C, self.N, *self.param_shape)
 
 
+class LinearBiasFactor(DenseFactor):
+    """Bias of a 2-d ``Linear`` layer: ``V_b^T = S``, so ``G_b = S S^T`` -- the very product the weight's Gram
+    ``(Z Z^T) (.) (S S^T)`` is built from.  The reference computes it twice (``linear.py:72`` and, for the bias,
+    ``base.py:124``); when both parameters sit in ONE group, ``G_W + G_b = (Z Z^T + 1) (.) (S S^T)`` and the
+    weight factor's call takes the bias along (``fold_linear_bias`` sets the two flags)."""
+
+    def __init__(self, S: Tensor, param_shape):
+        super().__init__(S, param_shape)
+        self.partner: Optional["LinearWeightFactor"] = None
+        self.partner_param = None
+        self.folded = False
+
+    def gram_accum(self, G, fold=True):
+        if not (fold and self.folded):
+            super().gram_accum(G)
+
+
 class LinearWeightFactor(Factor):
     """Structured factor of a 2-d ``Linear.weight``: ``V^T[(c,n), o, i] = S[c,n,o] Z[n,i]``
     (``linear.py:41-42``)."""
@@ -113,11 +130,16 @@ class LinearWeightFactor(Factor):
         self.n_in = Z.shape[1]
         self.param_shape = (self.n_out, self.n_in)
         self.S, self.Z = S, Z
+        self.partner: Optional[LinearBiasFactor] = None
+        self.partner_param = None
+        self.fold_bias = False
 
     def _like(self):
         return self.S
 
-    def gram_accum(self, G, with_bias: bool = False):
+    def gram_accum(self, G, fold=True, with_bias: Optional[bool] = None):
+        if with_bias is None:
+            with_bias = fold and self.fold_bias
         kernels.gram_linear_accum(G, self.S, self.Z, with_bias)
 
     def cross_accum(self, X, grad, with_bias: bool = False):
@@ -137,6 +159,24 @@ class LinearWeightFactor(Factor):
 
     def materialize(self):
         return kernels.v_emit_linear(self.S, self.Z)
+
+
+def link_linear_factors(weight_factor: LinearWeightFactor, weight, bias_factor: LinearBiasFactor, bias) -> None:
+    """Tell the two factors of one Linear layer about each other (and about each other's parameter)."""
+    weight_factor.partner, weight_factor.partner_param = bias_factor, bias
+    bias_factor.partner, bias_factor.partner_param = weight_factor, weight
+
+
+def fold_linear_bias(factor: Factor, same_group) -> None:
+    """Called by a Computation when a parameter's factor reaches its group: if the factor belongs to a Linear
+    layer whose other parameter is in the same group (``same_group(param) -> bool``), the layer's two Gram
+    contributions are assembled by ONE structured call (see ``LinearBiasFactor``)."""
+    partner = getattr(factor, "partner", None)
+    if partner is None or factor.partner_param is None or not same_group(factor.partner_param):
+        return
+    weight, bias = (factor, partner) if isinstance(factor, LinearWeightFactor) else (partner, factor)
+    weight.fold_bias = True
+    bias.folded = True
 
 
 class GradFactor:

@@ -646,7 +646,7 @@ TIMED = [
 
 class _Timing:
     enabled = False
-    records = []  # (name, start_event, end_event, [tensor shapes], launches)
+    records = []  # (name, start_event, end_event, [tensor-argument shapes], launches, [result shapes])
 
 
 def timing_start() -> None:
@@ -656,10 +656,10 @@ def timing_start() -> None:
 
 
 def timing_stop():
-    """Stop timing; returns ``[(name, ms, shapes, launches)]`` (synchronises the device)."""
+    """Stop timing; returns ``[(name, ms, argument shapes, launches, result shapes)]`` (synchronises the device)."""
     _Timing.enabled = False
     torch.cuda.synchronize()
-    out = [(n, e0.elapsed_time(e1), shp, nl) for n, e0, e1, shp, nl in _Timing.records]
+    out = [(n, e0.elapsed_time(e1), shp, nl, oshp) for n, e0, e1, shp, nl, oshp in _Timing.records]
     _Timing.records = []
     return out
 
@@ -678,7 +678,9 @@ def _timed(name, fn):
         out = fn(*args, **kwargs)
         e1.record()
         shapes = [tuple(a.shape) for a in args if isinstance(a, Tensor)]
-        _Timing.records.append((name, e0, e1, shapes, launch_count() - l0))
+        outs = out if isinstance(out, (tuple, list)) else (out,)
+        out_shapes = [tuple(o.shape) for o in outs if isinstance(o, Tensor)]
+        _Timing.records.append((name, e0, e1, shapes, launch_count() - l0, out_shapes))
         return out
 
     return wrapper

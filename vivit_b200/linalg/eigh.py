@@ -10,6 +10,7 @@ from torch import Tensor
 from torch.nn import Module, Parameter
 
 from vivit_b200 import kernels
+from vivit_b200.factors import fold_linear_bias
 from vivit_b200.linalg.eigvalsh import _accumulate_gram, _make_dist
 from vivit_b200.linalg.utils import get_hook_store_batch_size, get_vivit_extension, normalize
 from vivit_b200.utils import delete_savefield, keep_indices
@@ -33,13 +34,21 @@ class EighComputation:
         warn_small_eigvals: float = 1e-4,
         process_group=None,
         gather: bool = False,
+        batch_solves: bool = True,
     ):
+        """``batch_solves`` (not in the reference): with several block-diagonal groups, the Gram matrices are
+        decomposed in ONE batched solver call once the last group has fired (the groups are independent,
+        ``vivit/utils/hooks.py:214-219``, and share ``R = C * N``); a group's factors stay alive until then.
+        ``False`` restores the reference's order (solve and free inside every group's hook)."""
         check_subsampling_unique(subsampling)
         self._subsampling = subsampling
         self._mc_samples = mc_samples
         self._verbose = verbose
         self._dist = _make_dist(process_group)
         self._gather = gather
+        self._batch_solves = batch_solves
+        self._pending: List[tuple] = []
+        self._finish = None
         self._savefield = self.get_extension().savefield
         self._warn_small_eigvals = warn_small_eigvals
         self._mc_state = None
@@ -51,6 +60,8 @@ class EighComputation:
     def get_result(self, group: Dict) -> Tuple[Tensor, List[Tensor]]:
         """``(evals [K], [evecs_p [K, *p.shape]])`` of a GGN block (``eigh.py:65-90``)."""
         gid = id(group)
+        if self._pending:
+            self._flush()
         try:
             return self._evals[gid], self._evecs[gid]
         except KeyError as e:
@@ -79,6 +90,8 @@ class EighComputation:
         batch_sizes, subsampling, savefield = self._batch_size, self._subsampling, self._savefield
         evals, evecs, verbose = self._evals, self._evecs, self._verbose
         warn_small_eigvals, dist, gather = self._warn_small_eigvals, self._dist, self._gather
+        pending, batch = self._pending, self._batch_solves and len(param_groups) > 1
+        pending.clear()
 
         def param_computation(hook: ParameterGroupsHook, param: Parameter) -> None:
             pass  # nothing per parameter (eigh.py:174-181)
@@ -94,6 +107,9 @@ class EighComputation:
             batch_size = batch_sizes.pop(gid)
 
             factors = [getattr(p, savefield)["_factor"] for p in group["params"]]
+            members = {id(p) for p in group["params"]}
+            for factor in factors:  # Linear weight + bias in one group: one structured Gram call (factors.py)
+                fold_linear_bias(factor, lambda q: id(q) in members)
             gram = None
             for factor in factors:  # eigh.py:239-242
                 gram = _accumulate_gram(gram, factor)
@@ -102,8 +118,12 @@ class EighComputation:
                 kernels.scale_(gram, batch_size / len(subsampling))
             dist.allreduce_(gram)
 
-            gram_evals, gram_evecs = kernels.syevj(gram, vectors=True)  # eigh.py:248
+            pending.append((group, gram, factors))
+            if not batch or len(pending) == len(param_groups):
+                self._flush()
 
+        def finish(group, gram_evals, gram_evecs, factors) -> None:
+            gid = id(group)
             keep = group["criterion"](gram_evals)  # eigh.py:252-253
             keep_idx = keep_indices(keep, gram_evals)
             gram_evals = gram_evals.index_select(0, keep_idx)
@@ -132,6 +152,8 @@ class EighComputation:
             evals[gid] = gram_evals
             evecs[gid] = group_evecs
 
+        self._finish = finish
+
         hook = ParameterGroupsHook.from_functions(param_groups, param_computation, group_hook, accumulate)
 
         def extension_hook(module: Module) -> None:
@@ -145,6 +167,19 @@ class EighComputation:
             for group in param_groups:
                 print(f"{id(group)} → {[id(p) for p in group['params']]}")
         return extension_hook
+
+    def _flush(self) -> None:
+        """Decompose the pending Gram matrices (one batched call when they share a shape) and finish their
+        groups: filter, back-transform, normalise (``eigh.py:248-275``)."""
+        items, self._pending[:] = list(self._pending), []
+        grams = [gram for _, gram, _ in items]
+        if len(items) > 1 and all(g.shape == grams[0].shape and g.dtype == grams[0].dtype for g in grams):
+            all_evals, all_evecs = kernels.syevj_batched(torch.stack(grams), vectors=True)  # eigh.py:248, all groups
+            solved = [(all_evals[i], all_evecs[i]) for i in range(len(items))]
+        else:
+            solved = [kernels.syevj(gram, vectors=True) for gram in grams]  # eigh.py:248
+        for (group, _, factors), (gram_evals, gram_evecs) in zip(items, solved):
+            self._finish(group, gram_evals, gram_evecs, factors)
 
     @staticmethod
     def _check_param_groups(param_groups: List[Dict]) -> None:

@@ -9,6 +9,7 @@ from torch import Tensor
 from torch.nn import Module, Parameter
 
 from vivit_b200 import kernels
+from vivit_b200.factors import fold_linear_bias
 from vivit_b200.linalg.utils import get_hook_store_batch_size, get_vivit_extension
 from vivit_b200.utils import delete_savefield
 from vivit_b200.utils.checks import check_key_exists, check_subsampling_unique, check_unique_params
@@ -66,6 +67,8 @@ class EigvalshComputation:
         def param_computation(hook: ParameterGroupsHook, param: Parameter):
             # eager: evaluate this parameter's Gram and drop its factor (eigvalsh.py:145-158)
             factor = getattr(param, savefield)["_factor"]
+            group = hook._group_of[id(param)]
+            fold_linear_bias(factor, lambda q: hook._group_of.get(id(q)) is group)  # factors.py
             delete_savefield(param, savefield, verbose=verbose)
             return factor
 

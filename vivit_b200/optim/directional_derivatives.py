@@ -13,7 +13,7 @@ from torch.nn import Module
 
 from vivit_b200 import kernels
 from vivit_b200.backprop.extensions import BatchGrad
-from vivit_b200.factors import Factor, GradFactor
+from vivit_b200.factors import Factor, GradFactor, fold_linear_bias
 from vivit_b200.linalg.eigvalsh import _make_dist
 from vivit_b200.linalg.utils import get_hook_store_batch_size
 from vivit_b200.optim.utils import get_sqrt_ggn_extension
@@ -122,6 +122,8 @@ class DirectionalDerivativesComputation:
         (``directional_derivatives.py:216-252``)."""
         V = getattr(param, savefield_ggn)
         g = getattr(param, savefield_grad)
+        group = hook._group_of[id(param)]
+        fold_linear_bias(V, lambda q: hook._group_of.get(id(q)) is group)  # one Gram call per Linear layer
         if verbose:
             print(f"Param {id(param)}: Compute V_t_V and V_t_g_n")
         if free_factor:
