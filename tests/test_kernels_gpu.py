@@ -303,7 +303,7 @@ def test_wide_round_kernels(k, Np, rnd_idx):
         Q = Qt[pr].double().t()
         eye = torch.eye(128, dtype=torch.float64, device=dev())
         assert (Q.t() @ Q - eye).abs().max().item() <= 2e-5, ("orthogonal", pr)
-        assert (Pn - P @ Q).abs().max().item() <= 2e-6 * P.abs().max().item(), ("apply", pr)
+        assert (Pn - P @ Q).abs().max().item() <= 1e-5 * P.abs().max().item(), ("apply", pr)
         # every Jacobi rotation lowers the off-diagonal norm of the pair Gram by 2 h_pq^2
         Hn = Pn.t() @ Pn
         off = lambda M: (M - torch.diag(M.diagonal())).norm().item()  # noqa: E731

@@ -1297,8 +1297,9 @@ __global__ void sweep_end_kernel(JacobiScalars* sc, int batch, unsigned long lon
     if (sc[b].rotations <= thresh) sc[b].converged = 1;
   }
   sc[b].rotations = 0;
-  state[2 * b] = sc[b].sweeps;
-  state[2 * b + 1] = sc[b].converged;
+  state[3 * b] = sc[b].sweeps;
+  state[3 * b + 1] = sc[b].converged;
+  state[3 * b + 2] = int(sc[b].last_rotations > 0x7fffffffull ? 0x7fffffffull : sc[b].last_rotations);
 }
 
 }  // namespace vvt
@@ -1354,7 +1355,7 @@ static JacobiLayout jacobi_layout(int64_t R, int64_t B, int64_t es, int dtype) {
   L.off_marks = take(B * (L.nb + L.nb * L.nb) * 4);
   L.off_dc = take(B * L.nb * OB * OB * es);
   L.off_done = take(B * L.nb * 4);
-  L.off_state = take(B * 2 * 4);
+  L.off_state = take(B * 3 * 4);
   L.gemm_bytes = vvt_gram_workspace_bytes(R, R, R, dtype);
   L.off_gemm = take(L.gemm_bytes);
   L.total = o;
@@ -1405,14 +1406,14 @@ static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_ct
 // The host enqueues sweep s + 1 BEFORE it waits for the state of sweep s: if that sweep turns out to have been
 // the last one, the kernels of the speculative sweep exit on their first instruction (converged flag).
 struct HostState {
-  int* pinned = nullptr;  // [2 slots][2 * kMaxBatch]
+  int* pinned = nullptr;  // [2 slots][3 * kMaxBatch]: {sweeps, converged, block pairs rotated} per problem
   cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 static int host_state(HostState** out) {
   static thread_local HostState st[kMaxDevices];
   HostState& h = st[current_device()];
   if (!h.pinned) {
-    VVT_TRY(check_cuda(cudaHostAlloc(reinterpret_cast<void**>(&h.pinned), 2 * 2 * kMaxBatch * sizeof(int), cudaHostAllocDefault),
+    VVT_TRY(check_cuda(cudaHostAlloc(reinterpret_cast<void**>(&h.pinned), 2 * 3 * kMaxBatch * sizeof(int), cudaHostAllocDefault),
                        "vvt_syevj(pinned)"));
     for (int i = 0; i < 2; ++i)
       VVT_TRY(check_cuda(cudaEventCreateWithFlags(&h.ev[i], cudaEventDisableTiming), "vvt_syevj(event)"));
@@ -1550,40 +1551,49 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
     }
     sweep_end_kernel<<<unsigned(ceil_div(B, 128)), 128, 0, s>>>(sc, int(B), thresh, state);
     VVT_TRY(launched("vvt_syevj(sweep end)"));
-    int* slot = hs->pinned + (sweep & 1) * 2 * kMaxBatch;
-    VVT_TRY(check_cuda(cudaMemcpyAsync(slot, state, size_t(B) * 2 * sizeof(int), cudaMemcpyDeviceToHost, s), "vvt_syevj"));
+    int* slot = hs->pinned + (sweep & 1) * 3 * kMaxBatch;
+    VVT_TRY(check_cuda(cudaMemcpyAsync(slot, state, size_t(B) * 3 * sizeof(int), cudaMemcpyDeviceToHost, s), "vvt_syevj"));
     VVT_TRY(check_cuda(cudaEventRecord(hs->ev[sweep & 1], s), "vvt_syevj"));
     return VVT_OK;
   };
+  long long most_rotations = -1;  // over the unfinished problems, in the last sweep whose state has been read
   auto all_converged = [&](int sweep) -> int {  // waits for the state of `sweep`; 1 = every problem is done
     if (cudaEventSynchronize(hs->ev[sweep & 1]) != cudaSuccess) return -1;
-    const int* slot = hs->pinned + (sweep & 1) * 2 * kMaxBatch;
+    const int* slot = hs->pinned + (sweep & 1) * 3 * kMaxBatch;
     int all = 1;
+    most_rotations = 0;
     for (int64_t b = 0; b < B; ++b) {
-      all &= slot[2 * b + 1];
-      if (info) info[2 * b] = slot[2 * b], info[2 * b + 1] = slot[2 * b + 1];
+      all &= slot[3 * b + 1];
+      if (!slot[3 * b + 1]) most_rotations = vmax<long long>(most_rotations, slot[3 * b + 2]);
+      if (info) info[2 * b] = slot[3 * b], info[2 * b + 1] = slot[3 * b + 1];
     }
-    if (debug) {
-      JacobiScalars h;
-      cudaMemcpy(&h, sc, sizeof(h), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[vvt_syevj] R=%lld batch=%lld %s CL=%d sweep %d: %llu of %lld block pairs rotated (problem 0)\n",
-              (long long)R, (long long)B, L.wide ? "wide" : "16-wide", CL, sweep + 1, h.last_rotations,
+    if (debug)
+      fprintf(stderr, "[vvt_syevj] R=%lld batch=%lld %s CL=%d sweep %d: %d of %lld block pairs rotated (problem 0)\n",
+              (long long)R, (long long)B, L.wide ? "wide" : "16-wide", CL, sweep + 1, slot[2],
               (long long)((nb16 / 2) * nb16));
-    }
     return all;
   };
   {
-    int sweep = 0, done_flag = 0;
+    // The host enqueues sweep s + 1 before it has seen the outcome of sweep s (no bubble on the GPU) -- unless
+    // sweep s - 1 already rotated next to nothing: then sweep s is very likely the last one, and waiting for it
+    // (one short bubble) is cheaper than a sweep of launches that exit on their first instruction.
+    int sweep = 0, done_flag = 0, enqueued = 1;
     VVT_TRY(enqueue_sweep(0));
     while (true) {
       const bool more = sweep + 1 < kMaxSweeps;
-      if (more) VVT_TRY(enqueue_sweep(sweep + 1));  // speculative: exits at once if `sweep` was the last one
+      const bool speculate = most_rotations < 0 || most_rotations > 8 * (long long)(thresh + 1);
+      if (more && speculate && enqueued == sweep + 1) {
+        VVT_TRY(enqueue_sweep(sweep + 1));
+        ++enqueued;
+      }
       done_flag = all_converged(sweep);
       if (done_flag < 0) return fail(VVT_ERR_CUDA, "%s: %s", "vvt_syevj", cudaGetErrorString(cudaGetLastError()));
       if (done_flag || !more) break;
+      if (enqueued == sweep + 1) {  // not speculated: the outcome is known now, and it says "go on"
+        VVT_TRY(enqueue_sweep(sweep + 1));
+        ++enqueued;
+      }
       ++sweep;
-    }
-    if (!done_flag && sweep + 1 < kMaxSweeps) {  // (not reached: the loop only leaves early when converged)
     }
   }
 

@@ -429,7 +429,7 @@ def syevj(G: Tensor, vectors: bool = True, return_info: bool = False):
     """Ascending eigenvalues (and eigenvectors as columns) of symmetric positive semi-definite
     ``G [R, R]`` (upper triangle read).  Raises ``SyevjNotConverged`` when the sweep limit is hit;
     ``return_info=True`` appends ``{"sweeps", "converged"}`` and leaves the decision to the caller."""
-    evals, evecs, infos = syevj_batched(G.unsqueeze(0), vectors=vectors, return_info=True, _check=False)
+    evals, evecs, infos = _syevj_batched(G.unsqueeze(0), vectors, "vvt_syevj")
     info = infos[0]
     if return_info:
         return evals[0], (evecs[0] if vectors else None), info
@@ -438,11 +438,20 @@ def syevj(G: Tensor, vectors: bool = True, return_info: bool = False):
     return evals[0], (evecs[0] if vectors else None)
 
 
-def syevj_batched(G: Tensor, vectors: bool = True, return_info: bool = False, _check: bool = True):
+def syevj_batched(G: Tensor, vectors: bool = True, return_info: bool = False):
     """Eigendecompositions of ``B`` independent symmetric PSD matrices ``G [B, R, R]`` in ONE call
     (the per-group Grams of block-diagonal ``param_groups``, ``vivit/utils/hooks.py:214-219``): the batch
     index is part of every kernel's grid.  Returns ``evals [B, R]`` ascending, ``evecs [B, R, R]``
     (columns) or ``None``."""
+    evals, evecs, infos = _syevj_batched(G, vectors, "vvt_syevj_batched")
+    if return_info:
+        return evals, evecs, infos
+    if not all(i["converged"] for i in infos):
+        raise SyevjNotConverged(f"vvt_syevj_batched did not converge (R = {G.shape[1]}, batch = {G.shape[0]}): {infos}")
+    return evals, evecs
+
+
+def _syevj_batched(G: Tensor, vectors: bool, what: str):
     G = _c(G)
     _chk(G)
     if G.dim() != 3 or G.shape[1] != G.shape[2]:
@@ -452,7 +461,7 @@ def syevj_batched(G: Tensor, vectors: bool = True, return_info: bool = False, _c
     evecs = torch.empty(B, R, R, dtype=G.dtype, device=G.device) if vectors else None
     infos = [{"sweeps": 0, "converged": True} for _ in range(B)]
     if R == 0 or B == 0:
-        return (evals, evecs, infos) if return_info else (evals, evecs)
+        return evals, evecs, infos
     lib = _lib.load()
     ws = _ws(lib.vvt_syevj_batched_workspace_bytes(R, B, int(vectors), _dt(G)), G)
     info = (ctypes.c_int * (2 * B))()
@@ -461,12 +470,10 @@ def syevj_batched(G: Tensor, vectors: bool = True, return_info: bool = False, _c
             _p(evals), _p(evecs), _p(G), R, B, int(vectors), _p(ws), ws.numel(), info,
             _dt(G), _stream(G),
         )
-    _lib.check(st, "vvt_syevj_batched")
+    _lib.check(st, what)
     for b in range(B):
         infos[b] = {"sweeps": int(info[2 * b]), "converged": bool(info[2 * b + 1])}
-    if _check and not return_info and not all(i["converged"] for i in infos):
-        raise SyevjNotConverged(f"vvt_syevj_batched did not converge (R = {R}, batch = {B}): {infos}")
-    return (evals, evecs, infos) if return_info else (evals, evecs)
+    return evals, evecs, infos
 
 
 def filter_nonzero(evals: Tensor, atol: float = 1e-7, rtol: float = 1e-5) -> Tensor:
