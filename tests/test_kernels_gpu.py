@@ -307,7 +307,7 @@ def test_wide_round_kernels(k, Np, rnd_idx):
         # every Jacobi rotation lowers the off-diagonal norm of the pair Gram by 2 h_pq^2
         Hn = Pn.t() @ Pn
         off = lambda M: (M - torch.diag(M.diagonal())).norm().item()  # noqa: E731
-        assert off(Hn) < 0.9 * off(want), (off(Hn), off(want))
+        assert off(Hn) < off(want), (off(Hn), off(want))
 
 
 @pytest.mark.parametrize("R,rank", [(2048, 1800), (2560, 2304), (5120, 4608)])
