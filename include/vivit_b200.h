@@ -211,6 +211,18 @@ int vvt_center_rows(void* out, const void* g, int64_t N, int64_t D, int dtype, v
 /* T[i] *= alpha  (the N/len(subsampling) rescale at eigh.py:245-246, eigvalsh.py:218-219) */
 int vvt_scale(void* T, int64_t numel, double alpha, int dtype, void* stream);
 
+/* The exchange step of the parameter-sharded path: G [numel_G] (the partial Gram matrix of this
+ * rank's parameter shard) and X [numel_X] (its partial cross term V^T g; may be NULL / 0) are replaced by
+ * alpha * (sum over the ranks of `comm`), in place, with ONE NCCL call group on `stream`.  alpha is the
+ * reference's N / len(subsampling) rescale (eigh.py:245-246, eigvalsh.py:218-219) applied inside the reduction
+ * (pre-multiplied sum), 1.0 otherwise.  comm: an ncclComm_t of the NCCL instance already loaded in the process
+ * (torch.distributed: ProcessGroupNCCL); VVT_ERR_UNSUPPORTED if there is none.  The sums
+ * G = sum_p V_p^T V_p of eigh.py:239-242, eigvalsh.py:170-183, directional_derivatives.py:245-246,348-351
+ * extended over the ranks. */
+int vvt_nccl_available(void);
+int vvt_nccl_allreduce_gram(void* comm, void* G, int64_t numel_G, void* X, int64_t numel_X, double alpha,
+                            int dtype, void* stream);
+
 /* Y[i] += alpha * X[i]: the sum of the factors that reach a tensor used by several branches of a model,
  * ViViTGGN.accumulate_backpropagated_quantities (vivit/extensions/secondorder/vivit/__init__.py:130-133) */
 int vvt_axpy(void* Y, const void* X, int64_t numel, double alpha, int dtype, void* stream);

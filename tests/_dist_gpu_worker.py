@@ -1,0 +1,70 @@
+"""Worker of ``tests/test_dist_gpu.py`` (launched under torchrun, one rank per GPU, NCCL): the parameter-sharded
+path against the unsharded one on the same GPU, with the partial-Gram exchange going through
+``vvt_nccl_allreduce_gram`` (fused sub-sampling rescale)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def run(comp, model, x, y, groups):
+    from vivit_b200 import backpack, extend
+
+    model, loss_fn = extend(model), extend(nn.CrossEntropyLoss())
+    with backpack(*comp.get_extensions(), extension_hook=comp.get_extension_hook(groups)):
+        loss_fn(model(x), y).backward()
+    for p in model.parameters():
+        p.grad = None
+    return [comp.get_result(g) for g in groups]
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    pg = dist.group.WORLD
+    import vivit_b200 as vv
+    from vivit_b200.dist import ShardedReduce
+
+    torch.manual_seed(0)
+    model = nn.Sequential(
+        nn.Conv2d(3, 8, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2), nn.Flatten(),
+        nn.Linear(8 * 4 * 4, 16), nn.ReLU(), nn.Linear(16, 5),
+    ).to(dev)
+    x, y = torch.rand(6, 3, 8, 8, device=dev), torch.randint(0, 5, (6,), device=dev)
+    top = lambda ev: list(range(ev.numel() - 3, ev.numel()))  # noqa: E731
+    groups = [{"params": list(model.parameters()), "criterion": top}]
+
+    sr = ShardedReduce(pg)
+    assert sr._nccl_comm(x) != 0, "the NCCL communicator is not reachable: the fused exchange would not run"
+
+    for sub in (None, [4, 1, 0]):
+        ((ev1, vec1),) = run(vv.EighComputation(subsampling=sub), model, x, y, groups)
+        ((evs, vecs),) = run(vv.EighComputation(subsampling=sub, process_group=pg, gather=True), model, x, y, groups)
+        assert torch.allclose(ev1, evs, rtol=1e-4, atol=1e-7), (sub, ev1, evs)
+        a = torch.cat([v.flatten(1) for v in vec1], 1).double()
+        b = torch.cat([v.flatten(1) for v in vecs], 1).double()
+        assert (a @ b.t()).abs().diag().min() > 1 - 1e-3, sub
+        ((g1, l1),) = run(vv.DirectionalDerivativesComputation(subsampling_ggn=sub), model, x, y, groups)
+        ((gs, ls),) = run(vv.DirectionalDerivativesComputation(subsampling_ggn=sub, process_group=pg), model, x, y, groups)
+        assert torch.allclose(g1.abs(), gs.abs(), rtol=1e-3, atol=1e-5) and torch.allclose(l1, ls, rtol=1e-3, atol=1e-6), sub
+    # every rank holds the same result (replicated Gram-space work is deterministic)
+    gathered = [torch.empty_like(evs) for _ in range(dist.get_world_size())]
+    dist.all_gather(gathered, evs.contiguous())
+    assert all(torch.equal(gathered[0], t) for t in gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+    if local == 0:
+        print("dist gpu worker ok")
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,8 @@ SIGNATURES = {
     "vvt_gram_cross_linear_accum": (INT, [P, P, P, P, P, I64, I64, I64, I64, I64, INT, P, I64, INT, P]),
     "vvt_scale": (INT, [P, I64, DBL, INT, P]),
     "vvt_axpy": (INT, [P, P, I64, DBL, INT, P]),
+    "vvt_nccl_available": (INT, []),
+    "vvt_nccl_allreduce_gram": (INT, [P, P, I64, P, I64, DBL, INT, P]),
     "vvt_center_rows": (INT, [P, P, I64, I64, INT, P]),
     "vvt_syevj_workspace_bytes": (I64, [I64, INT, INT]),
     "vvt_syevj": (INT, [P, P, P, I64, INT, P, I64, POINTER(c_int), INT, P]),

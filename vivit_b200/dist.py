@@ -45,6 +45,43 @@ class ShardedReduce:
     def shard(self) -> Optional[Tuple[int, int]]:
         return None if self.world == 1 else (self.rank, self.world)
 
+    def _nccl_comm(self, like: Tensor) -> int:
+        """Raw ``ncclComm_t`` of the group for ``vvt_nccl_allreduce_gram`` (0: not an NCCL group, or this torch
+        build does not hand the communicator out -- then ``torch.distributed`` carries the collective)."""
+        if not like.is_cuda:
+            return 0
+        if getattr(self, "_comm", None) is None:
+            ptr = 0
+            try:
+                backend = self.group._get_backend(torch.device("cuda"))
+                ptr = int(backend._comm_ptr())
+            except Exception:
+                ptr = 0
+            self._comm = ptr
+        return self._comm
+
+    def scale_allreduce_(self, alpha: float, gram: Tensor, cross: Optional[Tensor] = None) -> None:
+        """``gram`` (and ``cross``) ``<- alpha * sum over ranks`` in place: the partial-Gram exchange of the
+        parameter-sharded path with the sub-sampling rescale of ``eigh.py:245-246`` folded in.  One process:
+        just the rescale."""
+        from vivit_b200 import kernels
+
+        if self.world == 1:
+            if alpha != 1.0:
+                kernels.scale_(gram, alpha)
+                if cross is not None:
+                    kernels.scale_(cross, alpha)
+            return
+        comm = self._nccl_comm(gram)
+        if comm:
+            kernels.nccl_allreduce_gram(comm, gram, cross, alpha)  # one NCCL group, pre-multiplied sum
+            return
+        if alpha != 1.0:
+            kernels.scale_(gram, alpha)
+            if cross is not None:
+                kernels.scale_(cross, alpha)
+        self.allreduce_(*([gram] if cross is None else [gram, cross]))
+
     def allreduce_(self, *tensors: Tensor) -> None:
         """Sum the given tensors over ranks, in place, with a single collective."""
         if self.world == 1 or not tensors:

@@ -152,6 +152,18 @@ def axpy_(y: Tensor, x: Tensor, alpha: float = 1.0) -> Tensor:
     return y
 
 
+def nccl_allreduce_gram(comm_ptr: int, G: Tensor, X: Optional[Tensor] = None, alpha: float = 1.0) -> None:
+    """``G`` (and ``X``) ``<- alpha * sum over ranks``, in place, one NCCL call group on the current stream;
+    ``comm_ptr`` is the raw ``ncclComm_t`` of the process group (``ProcessGroupNCCL._comm_ptr()``)."""
+    _chk(G, X)
+    with torch.cuda.device(G.device):
+        st = _lib.load().vvt_nccl_allreduce_gram(
+            ctypes.c_void_p(comm_ptr), _p(G), G.numel(), _p(X), 0 if X is None else X.numel(), float(alpha),
+            _dt(G), _stream(G),
+        )
+    _lib.check(st, "vvt_nccl_allreduce_gram")
+
+
 def center_rows(g: Tensor, inplace: bool = False) -> Tensor:
     """``g [N, ...] - g.mean(0)`` (per-sample gradients minus their mean); ``inplace`` overwrites ``g``."""
     if inplace and not g.is_contiguous():

@@ -114,9 +114,8 @@ class EighComputation:
             for factor in factors:  # eigh.py:239-242
                 gram = _accumulate_gram(gram, factor)
             C, N_ggn = factors[0].C, factors[0].N
-            if subsampling is not None:  # eigh.py:245-246
-                kernels.scale_(gram, batch_size / len(subsampling))
-            dist.allreduce_(gram)
+            # eigh.py:245-246; over several ranks the rescale rides on the all-reduce of the partial Grams
+            dist.scale_allreduce_(1.0 if subsampling is None else batch_size / len(subsampling), gram)
 
             pending.append((group, gram, factors))
             if not batch or len(pending) == len(param_groups):

@@ -84,9 +84,8 @@ class EigvalshComputation:
                 print(f"Group {gid}: Delete 'batch_size'")
             batch_size = batch_sizes.pop(gid)
             gram = accumulation if isinstance(accumulation, Tensor) else _accumulate_gram(None, accumulation)
-            if subsampling is not None:  # eigvalsh.py:218-219
-                kernels.scale_(gram, batch_size / len(subsampling))
-            dist.allreduce_(gram)
+            # eigvalsh.py:218-219; over several ranks the rescale rides on the all-reduce of the partial Grams
+            dist.scale_allreduce_(1.0 if subsampling is None else batch_size / len(subsampling), gram)
             gram_evals, _ = kernels.syevj(gram, vectors=False)  # eigvalsh.py:221
             if verbose:
                 print(f"Group {gid}: Store 'gram_evals'")

@@ -160,7 +160,7 @@ class DirectionalDerivativesComputation:
             accumulation = DirectionalDerivativesComputation._start(accumulation)
         gid = id(group)
         acc = accumulation
-        dist.allreduce_(acc.V_t_V, acc.V_t_g_n)
+        dist.scale_allreduce_(1.0, acc.V_t_V, acc.V_t_g_n)  # the one exchange of the sharded path
         N_ggn, C = acc.N_ggn, acc.C
         corr2 = N / N_ggn  # V_correction**2  (:285-287)
         # eigenpairs of corr^2 V^T V; the solver leaves its input intact, so scale a copy
