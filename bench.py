@@ -139,6 +139,7 @@ class Stepper:
         from vivit_b200 import extend
 
         self.w, self.device, self.pg = w, device, process_group
+        self.calls = tuple(w["calls"])
         model, x, y = make_problem(w, dtype)
         self.model = extend(model.to(device))
         self.loss_fn = extend(nn.CrossEntropyLoss())
@@ -148,7 +149,24 @@ class Stepper:
             import torch.distributed as dist
 
             world = dist.get_world_size(process_group)
-            if w["grouping"] == "layer":
+            rank = dist.get_rank(process_group)
+            self.calls = tuple(w["calls"])
+            if w["grouping"] != "layer" and len(w["calls"]) == 2:
+                # the step is two independent computations (two backward passes in the reference):
+                # they run side by side on the two halves of the ranks; a half of more than one rank shards the
+                # parameter dimension of its pass.  (The eigensolver of a pass is latency-bound at R = 1280 and
+                # does not shard: without this split every rank would repeat both solves.)
+                half = world // 2
+                halves = [dist.new_group(list(range(half))), dist.new_group(list(range(half, world)))]
+                mine = 0 if rank < half else 1
+                self.calls = (w["calls"][mine],)
+                size = half if mine == 0 else world - half
+                self.pg = halves[mine] if size > 1 else None
+                self.parallelism = (
+                    f"{w['calls'][0]} on ranks 0..{half - 1} next to {w['calls'][1]} on ranks {half}..{world - 1}; "
+                    f"inside a half the Gram is parameter-sharded (one NCCL all-reduce per group), results stay on "
+                    f"the half that computed them")
+            elif w["grouping"] == "layer":
                 # block-diagonal groups are independent: whole groups per rank, no collective
                 from vivit_b200.dist import local_groups
 
@@ -186,7 +204,7 @@ class Stepper:
         # sharded runs return the WHOLE eigenvectors / steps (all-gathered), the same deliverable as on one GPU
         kw = {"process_group": self.pg} if self.pg is not None else {}
         gkw = {**kw, "gather": True} if self.pg is not None else {}
-        for call in w["calls"]:
+        for call in self.calls:
             if call == "eigvalsh":
                 res = self._pass(vv.EigvalshComputation(**kw), x, y)
                 out += list(res)

@@ -1686,18 +1686,23 @@ int vvt_dbg_wide_round(float* L, float* H_out, float* Qt_out, int* flag_out, int
   cudaStream_t s = as_stream(stream);
   const wide::WidePlan p = wide::wide_plan(Np, 1);
   char* scratch = nullptr;
-  VVT_TRY(check_cuda(cudaMalloc(&scratch, size_t(p.part_bytes + 256)), __func__));
+  const size_t l_bytes = size_t(Np) * Np * 4;
+  VVT_TRY(check_cuda(cudaMalloc(&scratch, size_t(p.part_bytes + 256) + l_bytes), __func__));
   float* part = (float*)scratch;
   JacobiScalars* sc = (JacobiScalars*)(scratch + p.part_bytes);
+  float* Lw = (float*)(scratch + p.part_bytes + 256);  // the solver's wide-block-major layout
+  const int blocks = int(vmin<int64_t>(ceil_div(int64_t(Np) * Np, 256), 8 * num_sms()));
   int st = check_cuda(cudaMemsetAsync(sc, 0, sizeof(JacobiScalars), s), __func__);
+  wide::wide_relayout_kernel<<<blocks, 256, 0, s>>>(Lw, L, int(Np), 1);
   wide::WideMaps maps;
-  if (st == VVT_OK) st = wide::wide_make_maps(&maps, L, Qt_out, p, 1);
-  if (st == VVT_OK) st = wide::wide_round(L, part, Qt_out, flag_out, sc, p, maps, round, 1, s);
+  if (st == VVT_OK) st = wide::wide_make_maps(&maps, Lw, Qt_out, p, 1);
+  if (st == VVT_OK) st = wide::wide_round(Lw, part, Qt_out, flag_out, sc, p, maps, round, 1, s);
   if (st == VVT_OK) {
     for (int k = 0; k < p.splits && st == VVT_OK; ++k)
       st = vvt_axpy(H_out, part + size_t(k) * p.pairs * wide::WP * wide::WP, int64_t(p.pairs) * wide::WP * wide::WP, 1.0,
                     VVT_F32, stream);
   }
+  wide::wide_relayout_kernel<<<blocks, 256, 0, s>>>(L, Lw, int(Np), 0);
   cudaStreamSynchronize(s);
   cudaFree(scratch);
   return st;

@@ -7,7 +7,8 @@
 // problems of a batch:
 //
 //   1. wide_tc_kernel<GRAM>   H = P^T P of every 128-column pair panel P = [L_a | L_b]   (128 x 128 x R)
-//        tcgen05.mma kind::tf32 with MN-MAJOR operands: the factor stays row-major [row][column], a k-block is
+//        tcgen05.mma kind::tf32 with MN-MAJOR operands: rows are the contraction index and are not contiguous
+//        (the factor is stored wide-block-major, [wide block][row][64 columns]); a k-block is
 //        four TMA boxes of 32 rows x 32 columns (128-byte swizzle with 32-byte atoms) which land exactly in
 //        the canonical MN-major SWIZZLE_128B_BASE32B layout, the only one the tensor core takes for MN-major
 //        tf32 (see make_desc_mn).  3xTF32 split by the converter warps, split-K over the rows, raw
@@ -125,9 +126,9 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto panel_col = [&](int chunk) {  // first column of the chunk-th group of 32 panel columns
-    return chunk < 2 ? wa * WB + chunk * 32 : wb * WB + (chunk - 2) * 32;
-  };
+  // the chunk-th group of 32 panel columns: wide block (third TMA coordinate) and first column inside it
+  auto chunk_blk = [&](int chunk) { return prob * a.nbw + (chunk < 2 ? wa : wb); };
+  auto chunk_c0 = [&](int chunk) { return (chunk & 1) * 32; };
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -140,55 +141,57 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
           mbar_expect_tx(bar_tma(s), TILE_BYTES);
           const int r0 = (kb0 + i) * BK;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_3d(stage + j * 4096, &mapL, bar_tma(s), panel_col(j), r0, prob);
+          for (int j = 0; j < 4; ++j) tma_load_3d(stage + j * 4096, &mapL, bar_tma(s), chunk_c0(j), r0, chunk_blk(j));
         } else {  // 128 rows x 32 panel columns of the factor; 128 rows x 32 columns of Q^T
           mbar_expect_tx(bar_tma(s), 2 * TILE_BYTES);
-          tma_load_3d(stage, &mapL, bar_tma(s), panel_col(i), rtile * BM, prob);
+          tma_load_3d(stage, &mapL, bar_tma(s), chunk_c0(i), rtile * BM, chunk_blk(i));
           tma_load_3d(stage + TILE_BYTES, &mapQ, bar_tma(s), i * BK, 0, prob * a.pairs + pair);
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer (software-pipelined by one k-block, see gemm_tc.cuh) =====
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
+      const int vr = a.variant;
+      auto stage_of = [&](int i) { return base + (i % STAGES) * STAGE_BYTES; };
+      auto issue_hi = [&](int i) {
         const int s = i % STAGES, use = i / STAGES;
         const int grp = i / PROMOTE, first = (i % PROMOTE) == 0;
         const uint32_t acc = tmem_base + uint32_t((grp & 1) * BN);
-        const uint32_t stage = base + s * STAGE_BYTES;
-        const uint32_t a_hi = stage, b_hi = diag ? stage : stage + TILE_BYTES;
-        const uint32_t a_lo = stage + 2 * TILE_BYTES, b_lo = diag ? a_lo : stage + 3 * TILE_BYTES;
+        const uint32_t a_hi = stage_of(i), b_hi = diag ? a_hi : a_hi + TILE_BYTES;
         if (first && grp >= 2) {
           mbar_wait(bar_acc_empty(grp & 1), ((grp >> 1) - 1) & 1);
           tcgen05_fence_after();
         }
         mbar_wait(bar_tma(s), use & 1);
         tcgen05_fence_after();
-        if (MODE == GRAM && a.variant >= 2) {  // experiments: K-major descriptors on the MN-major data
-          const uint32_t id = a.variant == 2 ? kIdescMN : kIdesc;
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k)
-            umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_hi + 32 * k), id, !(first && k == 0));
-          mbar_wait(bar_conv(s), use & 1);
-          tcgen05_fence_after();
-        } else if (MODE == GRAM) {  // MN-major: 8 rows (K) = one 1 KB atom row group
-          const int vr = a.variant;
+        if (MODE == GRAM && vr < 2) {  // MN-major: one MMA (K = 8) = two 4-row groups, next k-step 1 KB further
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k)
             umma_tf32(acc, make_desc_mn(a_hi + 1024 * k, vr), make_desc_mn(b_hi + 1024 * k, vr), kIdescMN, !(first && k == 0));
-          mbar_wait(bar_conv(s), use & 1);
-          tcgen05_fence_after();
+        } else {
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)
+            umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_hi + 32 * k), kIdesc, !(first && k == 0));
+        }
+      };
+      issue_hi(0);
+      for (int i = 0; i < nkb; ++i) {
+        if (i + 1 < nkb) issue_hi(i + 1);
+        const int s = i % STAGES, use = i / STAGES;
+        const int grp = i / PROMOTE;
+        const uint32_t acc = tmem_base + uint32_t((grp & 1) * BN);
+        const uint32_t a_hi = stage_of(i), b_hi = diag ? a_hi : a_hi + TILE_BYTES;
+        const uint32_t a_lo = a_hi + 2 * TILE_BYTES, b_lo = diag ? a_lo : a_hi + 3 * TILE_BYTES;
+        mbar_wait(bar_conv(s), use & 1);
+        tcgen05_fence_after();
+        if (MODE == GRAM && vr < 2) {
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             umma_tf32(acc, make_desc_mn(a_hi + 1024 * k, vr), make_desc_mn(b_lo + 1024 * k, vr), kIdescMN, 1);
             umma_tf32(acc, make_desc_mn(a_lo + 1024 * k, vr), make_desc_mn(b_hi + 1024 * k, vr), kIdescMN, 1);
           }
         } else {
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k)
-            umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_hi + 32 * k), kIdesc, !(first && k == 0));
-          mbar_wait(bar_conv(s), use & 1);
-          tcgen05_fence_after();
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_lo + 32 * k), kIdesc, 1);
@@ -255,10 +258,217 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
 #pragma unroll
         for (int q = 0; q < BN / 32; ++q) out[r * WP + lane + 32 * q] = tile[r * (BN + 1) + lane + 32 * q];
     } else {
-      float* L = a.out + size_t(prob) * a.l_stride + size_t(rtile) * BM * a.Np;
       for (int r = cw; r < BM; r += 4)
 #pragma unroll
-        for (int q = 0; q < BN / 32; ++q) L[size_t(r) * a.Np + panel_col(q) + lane] = tile[r * (BN + 1) + lane + 32 * q];
+        for (int q = 0; q < BN / 32; ++q)
+          a.out[(size_t(chunk_blk(q)) * a.Np + size_t(rtile) * BM + r) * WB + chunk_c0(q) + lane] = tile[r * (BN + 1) + lane + 32 * q];
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- persistent apply kernel ----------------------------------------------------------------------------
+// P <- P Q for all pairs of a round: K = 128 only, so a CTA per output tile (wide_tc_kernel<APPLY>) spends its
+// life in prologue and epilogue (measured: 8.4 us per 128 x 128 tile, 1.6 us of which are MMAs).  Here a CTA
+// walks a contiguous range of (pair, row tile) work items: Q^T (hi and lo, 128 KB) stays in shared memory while
+// the pair does not change, the rows of the factor stream through a 3-deep ring of k-blocks, two TMEM
+// accumulators alternate between the MMA warp and four epilogue warps that store straight from registers
+// (every thread owns one output row: 4 x 128 contiguous bytes).
+//   warp 0: TMA producer   warp 1: MMA issuer   warps 2-5: converters (lo tiles)   warps 6-9: epilogue
+constexpr int AP_STAGES = 3;
+constexpr int AP_THREADS = 320;
+constexpr int AP_Q_BYTES = 8 * tc::TILE_BYTES;      // 4 k-blocks x (hi | lo)
+constexpr int AP_STAGE_BYTES = 2 * tc::TILE_BYTES;  // one k-block of P: raw | lo
+constexpr size_t AP_SMEM = size_t(AP_Q_BYTES) + AP_STAGES * AP_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(AP_THREADS, 1)
+wide_apply_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapQ, WideArgs a) {
+  using namespace tc;
+  extern __shared__ unsigned char smem_raw[];
+  const int prob = blockIdx.y;
+  if (*reinterpret_cast<const volatile int*>(&a.sc[prob].converged)) return;
+  const int row_tiles = a.Np / BM, total = a.pairs * row_tiles;
+  const int per = (total + int(gridDim.x) - 1) / int(gridDim.x);
+  const int it0 = blockIdx.x * per, it1 = min(total, it0 + per);
+  const int* flag = a.flag + prob * a.pairs;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t qbase = base, abase = base + AP_Q_BYTES;
+  const uint32_t bars = abase + AP_STAGES * AP_STAGE_BYTES;
+  auto bar_a_tma = [&](int s) { return bars + 8u * s; };
+  auto bar_a_conv = [&](int s) { return bars + 8u * (AP_STAGES + s); };
+  auto bar_a_empty = [&](int s) { return bars + 8u * (2 * AP_STAGES + s); };
+  const uint32_t bar_q_tma = bars + 8u * (3 * AP_STAGES), bar_q_conv = bar_q_tma + 8, bar_q_empty = bar_q_tma + 16;
+  auto bar_acc_full = [&](int b) { return bars + 8u * (3 * AP_STAGES + 3 + b); };
+  auto bar_acc_empty = [&](int b) { return bars + 8u * (3 * AP_STAGES + 5 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + AP_Q_BYTES + AP_STAGES * AP_STAGE_BYTES + 8 * (3 * AP_STAGES + 7));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < AP_STAGES; ++s) {
+      mbar_init(bar_a_tma(s), 1);
+      mbar_init(bar_a_conv(s), 128);
+      mbar_init(bar_a_empty(s), 1);
+    }
+    mbar_init(bar_q_tma, 1);
+    mbar_init(bar_q_conv, 128);
+    mbar_init(bar_q_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full(b), 1);
+      mbar_init(bar_acc_empty(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto q_hi = [&](int j) { return qbase + uint32_t(j) * 2 * TILE_BYTES; };
+  auto a_raw = [&](int s) { return abase + uint32_t(s) * AP_STAGE_BYTES; };
+  auto blk_of = [&](int pair, int chunk) {  // wide block (third TMA coordinate) of the chunk-th 32 panel columns
+    int wa, wb;
+    wide_blocks(a.nbw, a.round, pair, wa, wb);
+    return prob * a.nbw + (chunk < 2 ? wa : wb);
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int kbc = 0, qgen = 0, last_pair = -1;
+      for (int it = it0; it < it1; ++it) {
+        const int pair = it / row_tiles, rtile = it % row_tiles;
+        if (!flag[pair]) continue;
+        if (pair != last_pair) {
+          if (qgen > 0) mbar_wait(bar_q_empty, (qgen - 1) & 1);  // every MMA that read the old Q has completed
+          mbar_expect_tx(bar_q_tma, 4 * TILE_BYTES);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_3d(q_hi(j), &mapQ, bar_q_tma, j * BK, 0, prob * a.pairs + pair);
+          ++qgen;
+          last_pair = pair;
+        }
+        for (int j = 0; j < 4; ++j, ++kbc) {
+          const int s = kbc % AP_STAGES, use = kbc / AP_STAGES;
+          if (use > 0) mbar_wait(bar_a_empty(s), (use - 1) & 1);
+          mbar_expect_tx(bar_a_tma(s), TILE_BYTES);
+          tma_load_3d(a_raw(s), &mapL, bar_a_tma(s), (j & 1) * 32, rtile * BM, blk_of(pair, j));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int kbc = 0, qgen = 0, last_pair = -1, n = 0;
+      for (int it = it0; it < it1; ++it) {
+        const int pair = it / row_tiles;
+        if (!flag[pair]) continue;
+        if (pair != last_pair) {
+          if (last_pair >= 0) umma_commit(bar_q_empty);  // fires when every MMA issued so far has completed
+          mbar_wait(bar_q_tma, qgen & 1);
+          mbar_wait(bar_q_conv, qgen & 1);
+          tcgen05_fence_after();
+          ++qgen;
+          last_pair = pair;
+        }
+        const int buf = n & 1;
+        if (n >= 2) {
+          mbar_wait(bar_acc_empty(buf), ((n >> 1) - 1) & 1);
+          tcgen05_fence_after();
+        }
+        const uint32_t acc = tmem_base + uint32_t(buf * BN);
+        for (int j = 0; j < 4; ++j, ++kbc) {
+          const int s = kbc % AP_STAGES, use = kbc / AP_STAGES;
+          const uint32_t p_hi = a_raw(s), p_lo = p_hi + TILE_BYTES, qh = q_hi(j), ql = qh + TILE_BYTES;
+          mbar_wait(bar_a_tma(s), use & 1);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)
+            umma_tf32(acc, make_desc(p_hi + 32 * k), make_desc(qh + 32 * k), kIdesc, !(j == 0 && k == 0));
+          mbar_wait(bar_a_conv(s), use & 1);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            umma_tf32(acc, make_desc(p_hi + 32 * k), make_desc(ql + 32 * k), kIdesc, 1);
+            umma_tf32(acc, make_desc(p_lo + 32 * k), make_desc(qh + 32 * k), kIdesc, 1);
+          }
+          umma_commit(bar_a_empty(s));
+        }
+        umma_commit(bar_acc_full(buf));
+        ++n;
+      }
+    }
+  } else if (warp < 6) {
+    // ===== converters: lo = rna_tf32(x - trunc_tf32(x)) of Q^T (once per pair) and of every k-block of P =====
+    const int ct = threadIdx.x - 64;  // 0..127
+    auto convert = [&](unsigned char* src, unsigned char* dst, int n_vec) {
+#pragma unroll 4
+      for (int v = ct; v < n_vec; v += 128) {
+        const float4 x = *reinterpret_cast<const float4*>(src + size_t(v) * 16);
+        const float e[4] = {x.x, x.y, x.z, x.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float hi = __uint_as_float(__float_as_uint(e[j]) & 0xFFFFE000u);
+          o[j] = __uint_as_float(__float_as_uint(e[j] - hi) + 0x1000u);
+        }
+        *reinterpret_cast<float4*>(dst + size_t(v) * 16) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    };
+    int kbc = 0, qgen = 0, last_pair = -1;
+    for (int it = it0; it < it1; ++it) {
+      const int pair = it / row_tiles;
+      if (!flag[pair]) continue;
+      if (pair != last_pair) {
+        mbar_wait(bar_q_tma, qgen & 1);
+        for (int j = 0; j < 4; ++j)
+          convert(base_ptr + size_t(j) * 2 * TILE_BYTES, base_ptr + size_t(j) * 2 * TILE_BYTES + TILE_BYTES, TILE_BYTES / 16);
+        fence_proxy_async();
+        mbar_arrive(bar_q_conv);
+        ++qgen;
+        last_pair = pair;
+      }
+      for (int j = 0; j < 4; ++j, ++kbc) {
+        const int s = kbc % AP_STAGES, use = kbc / AP_STAGES;
+        unsigned char* st = base_ptr + AP_Q_BYTES + size_t(s) * AP_STAGE_BYTES;
+        mbar_wait(bar_a_tma(s), use & 1);
+        convert(st, st + TILE_BYTES, TILE_BYTES / 16);
+        fence_proxy_async();
+        mbar_arrive(bar_a_conv(s));
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global (thread = one output row of the tile) =====
+    const int lane_grp = warp & 3;  // a warp may only touch TMEM lanes 32 * (warp % 4) .. + 31
+    const int row = lane_grp * 32 + lane;
+    int n = 0;
+    for (int it = it0; it < it1; ++it) {
+      const int pair = it / row_tiles, rtile = it % row_tiles;
+      if (!flag[pair]) continue;
+      const int buf = n & 1;
+      mbar_wait(bar_acc_full(buf), (n >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t(buf * BN + 32 * c), r);
+        float4* dst = reinterpret_cast<float4*>(a.out + (size_t(blk_of(pair, c)) * a.Np + size_t(rtile) * BM + row) * WB + (c & 1) * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                               __uint_as_float(r[4 * q + 3]));
+      }
+      tcgen05_fence_before();
+      mbar_arrive(bar_acc_empty(buf));
+      ++n;
     }
   }
   tcgen05_fence_before();
@@ -542,29 +752,52 @@ wide_rot_kernel(float* Qt, int* flag, const float* part, int nbw, int round, int
 }
 
 // ---- layout conversion at both ends ---------------------------------------------------------------------
-// Lw [Np][Np] row-major <- lower triangle of the Cholesky factor A [R][R], scaled, zero elsewhere
+// The factor is stored WIDE-BLOCK-MAJOR: Lw[problem][wide block][row][64 columns].  A panel operation touches
+// two wide blocks, each one contiguous piece of memory (row-major storage made every 128-byte row segment of a
+// TMA box its own DRAM page: measured 2.0 - 2.4 TB/s for the Gram and apply kernels at R = 5120).
+__device__ __forceinline__ size_t wide_index(int Np, int nbw, int prob, int row, int col) {
+  return ((size_t(prob) * nbw + col / WB) * Np + row) * WB + (col % WB);
+}
+
+// Lw <- lower triangle of the Cholesky factor A [R][R], scaled, zero elsewhere
 __global__ void wide_init_chol_kernel(float* Lw, const float* A, int64_t R, int Np, const JacobiScalars* sc) {
   const int64_t total = int64_t(Np) * Np;
-  Lw += blockIdx.y * total, A += blockIdx.y * R * R, sc += blockIdx.y;
+  const int prob = blockIdx.y, nbw = Np / WB;
+  A += prob * R * R, sc += prob;
   const double bound = sqrt(double(R)) * sqrt(sc->norm2) + double(R) * double(chol_shift<float>(sc));
   const float scale = bound > 0.0 ? float(1.0 / sqrt(bound)) : 0.f;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
-    const int i = int(idx / Np), j = int(idx % Np);
-    Lw[idx] = (i < R && j <= i) ? A[int64_t(i) * R + j] * scale : 0.f;
+    // idx enumerates the destination: (wide block, row, column in block)
+    const int w = int(idx / (int64_t(Np) * WB)), rem = int(idx % (int64_t(Np) * WB));
+    const int i = rem / WB, j = w * WB + rem % WB;
+    Lw[size_t(prob) * total + idx] = (i < R && j <= i) ? A[int64_t(i) * R + j] * scale : 0.f;
+  }
+}
+
+// row-major [Np][Np] <-> wide-block-major (test hook only)
+__global__ void wide_relayout_kernel(float* dst, const float* src, int Np, int to_blocks) {
+  const int64_t total = int64_t(Np) * Np;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int r = int(idx / Np), c = int(idx % Np);
+    const size_t b = wide_index(Np, Np / WB, 0, r, c);
+    if (to_blocks) dst[b] = src[idx];
+    else dst[idx] = src[b];
   }
 }
 
 // inv[c] = 1 / ||Lw[:, c]||: a block owns 32 columns, its 8 warps split the rows (coalesced), fixed-order sum
 __global__ void __launch_bounds__(256) wide_colnorm_kernel(float* inv, const float* Lw, int64_t R, int Np) {
   __shared__ double red[8][32];
-  Lw += blockIdx.y * int64_t(Np) * Np, inv += blockIdx.y * R;
+  const int prob = blockIdx.y, nbw = Np / WB;
+  inv += prob * R;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t c = int64_t(blockIdx.x) * 32 + lane;
   double s = 0.0;
   if (c < R)
     for (int64_t r = w; r < R; r += 8) {
-      const double v = double(Lw[r * Np + c]);
+      const double v = double(Lw[wide_index(Np, nbw, prob, int(r), int(c))]);
       s += v * v;
     }
   red[w][lane] = s;
@@ -581,7 +814,8 @@ __global__ void __launch_bounds__(256) wide_colnorm_kernel(float* inv, const flo
 __global__ void __launch_bounds__(256) wide_gather_kernel(float* Jm, float* Jt, const float* Lw, const float* inv,
                                                           int64_t R, int Np) {
   __shared__ float tile[32][33];
-  Lw += blockIdx.z * int64_t(Np) * Np, inv += blockIdx.z * R, Jm += blockIdx.z * R * R, Jt += blockIdx.z * R * R;
+  const int prob = blockIdx.z, nbw = Np / WB;
+  inv += prob * R, Jm += prob * R * R, Jt += prob * R * R;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c0 = int64_t(blockIdx.x) * 32, r0 = int64_t(blockIdx.y) * 32;
 #pragma unroll
@@ -589,7 +823,7 @@ __global__ void __launch_bounds__(256) wide_gather_kernel(float* Jm, float* Jt, 
     const int64_t r = r0 + i, c = c0 + tx;
     float v = 0.f;
     if (r < R && c < R) {
-      v = Lw[r * Np + c] * inv[c];
+      v = Lw[wide_index(Np, nbw, prob, int(r), int(c))] * inv[c];
       Jm[r * R + c] = v;
     }
     tile[i][tx] = v;
@@ -652,11 +886,12 @@ struct WideMaps {
 };
 
 static inline int wide_make_maps(WideMaps* m, const float* Lw, const float* Qt, const WidePlan& p, int64_t batch) {
-  const int64_t ls = int64_t(p.Np) * p.Np;
   const int variant = getenv("VVT_WIDE_DESC") ? atoi(getenv("VVT_WIDE_DESC")) : 0;
-  if (!make_map_box(&m->gram, Lw, p.Np, p.Np, p.Np, batch, ls, 32,
+  // the factor as [problem * wide block][row][64 columns]
+  const int64_t blocks = batch * p.nbw, bs = int64_t(p.Np) * WB;
+  if (!make_map_box(&m->gram, Lw, p.Np, WB, WB, blocks, bs, 32,
                     variant >= 2 && variant != 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
-      !make_map_box(&m->apply, Lw, p.Np, p.Np, p.Np, batch, ls, tc::BM) ||
+      !make_map_box(&m->apply, Lw, p.Np, WB, WB, blocks, bs, tc::BM) ||
       !make_map_box(&m->q, Qt, WP, WP, WP, batch * p.pairs, int64_t(WP) * WP, tc::BN))
     return fail(VVT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", "vvt_syevj(wide)");
   return VVT_OK;
@@ -684,8 +919,17 @@ static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, Jacob
                                                                                             p.pairs, p.splits, sc);
   VVT_TRY(launched("vvt_syevj(wide rot)"));
   a.out = Lw;
-  wide_tc_kernel<APPLY><<<dim3(unsigned(p.Np / tc::BM), unsigned(p.pairs), unsigned(batch)), tc::THREADS, tc::SMEM_BYTES, s>>>(
-      m.apply, m.q, a);
+  static const bool per_tile = getenv("VVT_WIDE_APPLY_PER_TILE") != nullptr;  // experiments: one CTA per output tile
+  if (per_tile) {
+    wide_tc_kernel<APPLY><<<dim3(unsigned(p.Np / tc::BM), unsigned(p.pairs), unsigned(batch)), tc::THREADS, tc::SMEM_BYTES, s>>>(
+        m.apply, m.q, a);
+  } else {
+    static SmemOptIn opt_p;
+    VVT_TRY(opt_p.ensure(wide_apply_kernel, AP_SMEM, "vvt_syevj(wide apply)"));
+    const int64_t items = int64_t(p.pairs) * (p.Np / tc::BM);
+    const unsigned ctas = unsigned(vmax<int64_t>(1, vmin<int64_t>(items, num_sms() / vmin<int64_t>(batch, num_sms()))));
+    wide_apply_kernel<<<dim3(ctas, unsigned(batch)), AP_THREADS, AP_SMEM, s>>>(m.apply, m.q, a);
+  }
   VVT_TRY(launched("vvt_syevj(wide apply)"));
   return VVT_OK;
 }

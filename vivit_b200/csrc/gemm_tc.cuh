@@ -195,14 +195,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    // Software-pipelined by one k-block: hi*hi of block i + 1 is issued BEFORE the lo terms of block i, so the
+    // tensor pipe has work while the converter warps are still writing the lo tile of block i (the raw tile
+    // doubles as the hi operand and is usable the moment the TMA lands).
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
+      auto issue_hi = [&](int i) {
         const int s = i % STAGES, use = i / STAGES;
         const int grp = i / PROMOTE, first = (i % PROMOTE) == 0;
         const uint32_t acc = tmem_base + uint32_t((grp & 1) * BN);
         const uint32_t stage = base + s * STAGE_BYTES;
         const uint32_t a_hi = stage, b_hi = diag ? stage : stage + TILE_BYTES;
-        const uint32_t a_lo = stage + 2 * TILE_BYTES, b_lo = diag ? a_lo : stage + 3 * TILE_BYTES;
         if (first && grp >= 2) {  // the buffer was drained two groups ago?
           mbar_wait(bar_acc_empty(grp & 1), ((grp >> 1) - 1) & 1);
           tcgen05_fence_after();
@@ -212,6 +214,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k)  // 8 tf32 = 32 bytes per MMA along K
           umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_hi + 32 * k), kIdesc, !(first && k == 0));
+      };
+      issue_hi(0);
+      for (int i = 0; i < nkb; ++i) {
+        if (i + 1 < nkb) issue_hi(i + 1);
+        const int s = i % STAGES, use = i / STAGES;
+        const int grp = i / PROMOTE;
+        const uint32_t acc = tmem_base + uint32_t((grp & 1) * BN);
+        const uint32_t stage = base + s * STAGE_BYTES;
+        const uint32_t a_hi = stage, b_hi = diag ? stage : stage + TILE_BYTES;
+        const uint32_t a_lo = stage + 2 * TILE_BYTES, b_lo = diag ? a_lo : stage + 3 * TILE_BYTES;
         mbar_wait(bar_conv(s), use & 1);
         tcgen05_fence_after();
 #pragma unroll
