@@ -12,4 +12,5 @@ for r in rows[hdr + 1:]:
     if len(r) > vi: agg[r[ki][:60]].append(float(r[vi].replace(',', '')))
 for k, v in agg.items(): print(k, len(v), 'mean', sum(v) / len(v), 'min', min(v), 'max', max(v), rows[hdr+1][ui])
 PY
-VVT_WIDE_APPLY_PER_TILE=1 timeout 300 python scratch/eig_time.py 5120 > gpurun_out/eig_time_pertile.log 2>&1; grep "^R=" gpurun_out/eig_time_pertile.log
+timeout 600 python bench.py --workload c4 --steps 2 --no-cpu-baseline > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; python -c "
+import json; d=json.loads(open('gpurun_out/bench_c4.json').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['eigensolver']); [print(r) for r in d['kernels'][:4]]"

@@ -751,6 +751,223 @@ wide_rot_kernel(float* Qt, int* flag, const float* part, int nbw, int round, int
   }
 }
 
+// ---- rotation kernel, one CLUSTER of four CTAs per pair -------------------------------------------------------
+// wide_rot_kernel above keeps the whole 128 x 128 problem in one SM: measured 106 us per launch, 70 % of that
+// SM's shared-memory bandwidth (the two-sided update of H and the update of Q), 40 of 148 SMs busy at R = 5120.
+// Here the four sub-block pairs that rotate concurrently belong to four CTAs of a cluster:
+//   * CTA g owns the 32 ROWS of H of its current sub-pair (all 128 columns) and, for good, rows 32 g .. 32 g + 31
+//     of the accumulated Q.  Its 32 x 32 sub-Gram is a slice of its own rows; the scalar rotation rounds are the
+//     16-wide kernel's (rotation_rounds, the CTA has its SM's barrier to itself);
+//   * after the rotations the four Q_sub travel through distributed shared memory (one cluster barrier); every
+//     CTA applies all four to the COLUMNS of its rows of H and of Q (rows are independent) and its own Q_sub to
+//     its ROWS of H -- a quarter of the update work per SM;
+//   * between inner rounds the sub-blocks re-pair: a CTA fetches the 2 x 16 rows of its next sub-pair from the
+//     two CTAs that hold them (double-buffered: one more cluster barrier per inner round).
+constexpr int CR = 4;
+
+struct RotCta {
+  float Hrows[2][OP][LDW];     // rows of H of the current sub-pair (16 of sub-block sa, 16 of sb), double-buffered
+  float Qown[OP][LDW];         // rows 32 g .. 32 g + 31 of the accumulated Q
+  RotSmem<float> rs;           // rotation rounds: H_sub (double-buffered), Q_sub
+  float Qsubs[CR][OP][LDQ];    // the four Q_sub of the inner round
+  int my_rot;                  // did my sub-pair rotate?  (read by the other CTAs)
+  int rot[CR];
+};
+
+__device__ __forceinline__ void holder_of(bool intra_round, int ir, int x, int& h, int& half) {  // who holds sub-block x?
+  h = 0, half = 0;
+#pragma unroll
+  for (int g = 0; g < CR; ++g) {
+    int sa, sb;
+    bool intra;
+    sub_pair(intra_round, ir, g, sa, sb, intra);
+    if (sa == x) h = g, half = 0;
+    if (sb == x) h = g, half = 1;
+  }
+}
+
+__global__ void __launch_bounds__(OT, 2)
+wide_rot_cluster_kernel(float* Qt, int* flag, const float* part, int nbw, int round, int pairs, int splits,
+                        JacobiScalars* sc) {
+  extern __shared__ __align__(16) unsigned char wide_smem[];
+  RotCta& sm = *reinterpret_cast<RotCta*>(wide_smem);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int g = int(cluster.block_rank()), pair = blockIdx.x / CR, prob = blockIdx.y, tid = threadIdx.x;
+  sc += prob;
+  if (*reinterpret_cast<const volatile int*>(&sc->converged)) return;  // uniform over the cluster
+  (void)nbw;
+  const bool intra_round = round < 0;
+  const float tol2 = Eps<float>::tol * Eps<float>::tol, abs2 = Eps<float>::v * Eps<float>::v;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  // ---- my rows of H (sum of the split-K partial sums in a fixed order, symmetrised), my rows of Q = I
+  {
+    int sa, sb;
+    bool intra;
+    sub_pair(intra_round, 0, g, sa, sb, intra);
+    const float* p0 = part + (size_t(prob) * splits * pairs + pair) * size_t(WP * WP);
+    const size_t split_stride = size_t(pairs) * WP * WP;
+    for (int idx = tid; idx < OP * WP; idx += OT) {
+      const int i = idx / WP, c = idx % WP;
+      const int r = panel_index(sa, sb, i);
+      float a = 0.f, b = 0.f;
+      for (int k = 0; k < splits; ++k) {
+        a += p0[k * split_stride + size_t(r) * WP + c];
+        b += p0[k * split_stride + size_t(c) * WP + r];
+      }
+      sm.Hrows[0][i][c] = r == c ? a : 0.5f * (a + b);  // the two triangles differ in the last bits
+      sm.Qown[i][c] = (32 * g + i == c) ? 1.f : 0.f;
+    }
+  }
+  int any = 0, cur = 0;
+  __syncthreads();
+
+  for (int ir = 0; ir < 4; ++ir, cur ^= 1) {
+    int sa, sb;
+    bool intra;
+    sub_pair(intra_round, ir, g, sa, sb, intra);
+    float(*H)[LDW] = sm.Hrows[cur];
+    // ---- 32 x 32 sub-Gram = my rows at the columns of my sub-pair; Q_sub = I
+    {
+      const int i = tid >> 3, j = (tid & 7) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sm.rs.H[0][i][j + e] = H[i][panel_index(sa, sb, j + e)];
+        sm.rs.Q[i][j + e] = (i == j + e) ? 1.f : 0.f;
+      }
+    }
+    __syncthreads();
+    const bool rotate = any_rotation_needed<float>(sm.rs, intra, tol2, abs2, tid);
+    if (rotate) {
+      if (intra) rotation_rounds<float, true>(sm.rs, tol2, abs2, tid);
+      else rotation_rounds<float, false>(sm.rs, tol2, abs2, tid);
+    }
+    if (tid == 0) {
+      sm.my_rot = rotate;
+      if (rotate) atomicAdd(&sc->rotations, 1ull);
+    }
+    // ---- the four Q_sub of the round, through distributed shared memory
+    cluster_arrive();
+    cluster_wait();
+    for (int u = 0; u < CR; ++u) {
+      const RotCta* remote = cluster.map_shared_rank(&sm, u);
+      for (int idx = tid; idx < OP * LDQ / 4; idx += OT)
+        reinterpret_cast<float4*>(&sm.Qsubs[u][0][0])[idx] = reinterpret_cast<const float4*>(&remote->rs.Q[0][0])[idx];
+      if (tid == 0) sm.rot[u] = remote->my_rot;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < CR; ++u) any |= sm.rot[u];
+    // ---- columns: X[:, cols(u)] <- X[:, cols(u)] Q_sub(u) for my rows of H and of Q.  A warp owns one
+    //      (sub-pair, matrix): 32 rows x 32 columns, a thread 4 rows x 8 columns of it.
+    {
+      const int u = warp >> 1, rg = lane >> 2, cgp = lane & 3;
+      float(*X)[LDW] = (warp & 1) ? sm.Qown : H;
+      int ua, ub;
+      bool dummy;
+      sub_pair(intra_round, ir, u, ua, ub, dummy);
+      if (sm.rot[u]) {  // warp-uniform
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        const float* q = &sm.Qsubs[u][0][8 * cgp];
+#pragma unroll 2
+        for (int k = 0; k < OP; ++k) {
+          const int pc = panel_index(ua, ub, k);
+          const float4 q0 = *reinterpret_cast<const float4*>(q + k * LDQ);
+          const float4 q1 = *reinterpret_cast<const float4*>(q + k * LDQ + 4);
+          const float2 qa = make_float2(q0.x, q0.y), qb = make_float2(q0.z, q0.w);
+          const float2 qc = make_float2(q1.x, q1.y), qd = make_float2(q1.z, q1.w);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x = X[4 * rg + i][pc];
+            const float2 xx = make_float2(x, x);
+            const float2 r0 = __ffma2_rn(xx, qa, make_float2(acc[i][0], acc[i][1]));
+            const float2 r1 = __ffma2_rn(xx, qb, make_float2(acc[i][2], acc[i][3]));
+            const float2 r2 = __ffma2_rn(xx, qc, make_float2(acc[i][4], acc[i][5]));
+            const float2 r3 = __ffma2_rn(xx, qd, make_float2(acc[i][6], acc[i][7]));
+            acc[i][0] = r0.x, acc[i][1] = r0.y, acc[i][2] = r1.x, acc[i][3] = r1.y;
+            acc[i][4] = r2.x, acc[i][5] = r2.y, acc[i][6] = r3.x, acc[i][7] = r3.y;
+          }
+        }
+        __syncwarp();  // the warp owns these 32 x 32 entries: all reads precede the writes
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int pc = panel_index(ua, ub, 8 * cgp + j);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) X[4 * rg + i][pc] = acc[i][j];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- rows: H[my rows, :] <- Q_sub(g)^T H[my rows, :]; a thread owns 4 rows x 4 columns
+    {
+      const bool on = sm.rot[g] != 0;
+      float acc[4][4];
+      if (on) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        const float* q = &sm.Qsubs[g][0][4 * warp];
+#pragma unroll 4
+        for (int k = 0; k < OP; ++k) {
+          const float4 qv = *reinterpret_cast<const float4*>(q + k * LDQ);
+          const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
+          const float2 h01 = make_float2(H[k][lane], H[k][lane + 32]);
+          const float2 h23 = make_float2(H[k][lane + 64], H[k][lane + 96]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 q2 = make_float2(qq[i], qq[i]);
+            const float2 r0 = __ffma2_rn(q2, h01, make_float2(acc[i][0], acc[i][1]));
+            const float2 r1 = __ffma2_rn(q2, h23, make_float2(acc[i][2], acc[i][3]));
+            acc[i][0] = r0.x, acc[i][1] = r0.y, acc[i][2] = r1.x, acc[i][3] = r1.y;
+          }
+        }
+      }
+      __syncthreads();  // every read of the old rows precedes the first write
+      if (on) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) H[4 * warp + i][lane + 32 * j] = acc[i][j];
+      }
+    }
+    // ---- re-pair: fetch the rows of my next sub-pair from the CTAs that hold them
+    cluster_arrive();
+    cluster_wait();
+    if (ir < 3) {
+      int na, nb_;
+      bool dummy;
+      sub_pair(intra_round, ir + 1, g, na, nb_, dummy);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        int h, half;
+        holder_of(intra_round, ir, hh ? nb_ : na, h, half);
+        const RotCta* remote = cluster.map_shared_rank(&sm, h);
+        for (int idx = tid; idx < OB * WP; idx += OT) {
+          const int i = idx / WP, c = idx % WP;
+          sm.Hrows[cur ^ 1][OB * hh + i][c] = remote->Hrows[cur][OB * half + i][c];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- Q^T of my rows to global memory (rows of Q^T = output columns n; my slice is k = 32 g ..)
+  if (g == 0 && tid == 0) flag[prob * pairs + pair] = any;
+  if (any) {
+    float* dst = Qt + (size_t(prob) * pairs + pair) * size_t(WP * WP);
+    for (int idx = tid; idx < OP * WP; idx += OT) {
+      const int n = idx / OP, i = idx % OP;
+      dst[size_t(n) * WP + 32 * g + i] = sm.Qown[i][n];
+    }
+  }
+  // nobody may exit while a neighbour can still read its shared memory: the last remote reads (Q_sub of the
+  // fourth inner round) precede the cluster barrier that follows them
+}
+
 // ---- layout conversion at both ends ---------------------------------------------------------------------
 // The factor is stored WIDE-BLOCK-MAJOR: Lw[problem][wide block][row][64 columns].  A panel operation touches
 // two wide blocks, each one contiguous piece of memory (row-major storage made every 128-byte row segment of a
@@ -915,9 +1132,30 @@ static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, Jacob
   wide_tc_kernel<GRAM><<<dim3(unsigned(p.pairs), unsigned(p.splits), unsigned(batch)), tc::THREADS, tc::SMEM_BYTES, s>>>(
       m.gram, m.q, a);
   VVT_TRY(launched("vvt_syevj(wide gram)"));
-  wide_rot_kernel<<<dim3(unsigned(p.pairs), unsigned(batch)), RT, sizeof(WideRotSmem), s>>>(Qt, flag, part, p.nbw, round,
-                                                                                            p.pairs, p.splits, sc);
-  VVT_TRY(launched("vvt_syevj(wide rot)"));
+  static const bool one_cta = getenv("VVT_WIDE_ROT_ONE_CTA") != nullptr;  // experiments: the single-CTA kernel
+  if (one_cta) {
+    wide_rot_kernel<<<dim3(unsigned(p.pairs), unsigned(batch)), RT, sizeof(WideRotSmem), s>>>(Qt, flag, part, p.nbw, round,
+                                                                                              p.pairs, p.splits, sc);
+    VVT_TRY(launched("vvt_syevj(wide rot)"));
+  } else {
+    static SmemOptIn opt_c;
+    VVT_TRY(opt_c.ensure(wide_rot_cluster_kernel, sizeof(RotCta), "vvt_syevj(wide rot)"));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(p.pairs * CR), unsigned(batch));
+    cfg.blockDim = dim3(OT);
+    cfg.dynamicSmemBytes = sizeof(RotCta);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CR;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, wide_rot_cluster_kernel, Qt, flag, part, p.nbw, round, p.pairs, p.splits, sc),
+                       "vvt_syevj(wide rot)"));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   a.out = Lw;
   static const bool per_tile = getenv("VVT_WIDE_APPLY_PER_TILE") != nullptr;  // experiments: one CTA per output tile
   if (per_tile) {
