@@ -304,7 +304,9 @@ def algorithmic_work(name, shapes, es, out_shapes=()):
         K = prod(U) // V[0]
         return "hbm", es * (prod(V) + prod(U) + K * V[1])
     if name in ("sqrt_backprop_elementwise", "sqrt_backprop_maxpool2d", "sqrt_backprop_avgpool2d"):
-        return "hbm", es * 2 * prod(shapes[0])
+        # one read of the incoming factor, one write of the outgoing one (pools: the larger, un-pooled map)
+        out_elems = sum(prod(o) for o in out_shapes) or prod(shapes[0])
+        return "hbm", es * (prod(shapes[0]) + out_elems)
     if name == "scale_rows_rsqrt":
         return "hbm", es * 2 * prod(shapes[0])
     return None, 0

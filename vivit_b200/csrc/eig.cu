@@ -1371,13 +1371,15 @@ static size_t resident_smem_bytes(int rows_per_cta, int parts) {
 template <typename T>
 static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_cta, int parts, bool resident,
                         JacobiScalars* sc, int* marks, int now, T* Dc, unsigned* done, BatchStrides bs, int batch,
-                        cudaStream_t s) {
+                        bool share_sms, cudaStream_t s) {
   auto kern = resident ? onesided_round_resident_kernel<T> : onesided_round_stream_kernel<T>;
   size_t smem = resident ? resident_smem_bytes<T>(rows_per_cta, parts) : sizeof(StreamSmem<T>);
   // a round that fits on the GPU with one CTA per SM asks for more than half of an SM's shared memory, so
   // that no two CTAs share an SM (and its tensor pipe) while other SMs idle
+  // (share_sms: late sweeps, in which few pairs still rotate -- most CTAs exit at once, and with two CTAs per SM
+  // the next rounds' CTAs are resident early and start the moment their two blocks are done)
   static const bool no_pad = getenv("VVT_SYEVJ_NOPAD") != nullptr;  // experiments
-  if (!no_pad && int64_t(nb / 2) * CL * batch <= num_sms()) smem = vmax<size_t>(smem, size_t(116) * 1024);
+  if (!no_pad && !share_sms && int64_t(nb / 2) * CL * batch <= num_sms()) smem = vmax<size_t>(smem, size_t(116) * 1024);
   static SmemOptIn opt_in[2];  // per instantiation and kernel variant
   VVT_TRY(opt_in[resident].ensure(kern, smem, "vvt_syevj(attr)"));
   cudaLaunchConfig_t cfg = {};
@@ -1538,7 +1540,10 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
   wide::WideMaps maps;
   if (L.wide) VVT_TRY(wide::wide_make_maps(&maps, (const float*)Y, (const float*)Sm, L.wp, B));
 
+  long long most_rotations = -1;  // over the unfinished problems, in the last sweep whose state has been read
+  static const int share_div = getenv("VVT_SYEVJ_SHAREDIV") ? atoi(getenv("VVT_SYEVJ_SHAREDIV")) : 3;
   auto enqueue_sweep = [&](int sweep) -> int {
+    const bool share_sms = share_div > 0 && most_rotations >= 0 && most_rotations * share_div < (nb16 / 2) * nb16;
     if (L.wide) {
       if constexpr (sizeof(T) == 4) {
         for (int round = -1; round < L.wp.nbw - 1; ++round)
@@ -1547,7 +1552,8 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
     } else {
       for (int round = -1; round < nb - 1; ++round)
         VVT_TRY(launch_round<T>(Y, Np, nb, round, CL, rows_per_cta, parts, resident, sc, marks, sweep * nb + round + 2,
-                                (T*)(ws + L.off_dc), block_deps ? (unsigned*)(ws + L.off_done) : nullptr, bs, int(B), s));
+                                (T*)(ws + L.off_dc), block_deps ? (unsigned*)(ws + L.off_done) : nullptr, bs, int(B), share_sms,
+                                s));
     }
     sweep_end_kernel<<<unsigned(ceil_div(B, 128)), 128, 0, s>>>(sc, int(B), thresh, state);
     VVT_TRY(launched("vvt_syevj(sweep end)"));
@@ -1556,7 +1562,6 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
     VVT_TRY(check_cuda(cudaEventRecord(hs->ev[sweep & 1], s), "vvt_syevj"));
     return VVT_OK;
   };
-  long long most_rotations = -1;  // over the unfinished problems, in the last sweep whose state has been read
   auto all_converged = [&](int sweep) -> int {  // waits for the state of `sweep`; 1 = every problem is done
     if (cudaEventSynchronize(hs->ev[sweep & 1]) != cudaSuccess) return -1;
     const int* slot = hs->pinned + (sweep & 1) * 3 * kMaxBatch;

@@ -460,11 +460,13 @@ wide_apply_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t(buf * BN + 32 * c), r);
-        float4* dst = reinterpret_cast<float4*>(a.out + (size_t(blk_of(pair, c)) * a.Np + size_t(rtile) * BM + row) * WB + (c & 1) * 32);
+        float* dst = a.out + (size_t(blk_of(pair, c)) * a.Np + size_t(rtile) * BM + row) * WB + (c & 1) * 32;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                               __uint_as_float(r[4 * q + 3]));
+        for (int q = 0; q < 4; ++q)  // 256-bit stores: every thread writes whole 32-byte sectors of its row
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * q), "r"(r[8 * q]),
+                       "r"(r[8 * q + 1]), "r"(r[8 * q + 2]), "r"(r[8 * q + 3]), "r"(r[8 * q + 4]), "r"(r[8 * q + 5]),
+                       "r"(r[8 * q + 6]), "r"(r[8 * q + 7])
+                       : "memory");
       }
       tcgen05_fence_before();
       mbar_arrive(bar_acc_empty(buf));

@@ -78,25 +78,60 @@ __global__ void axpy_kernel(T* y, const T* x, int64_t n, T alpha) {
 
 // ---- element-wise Jacobians -------------------------------------------------
 template <typename T>
+__device__ __forceinline__ T act_derivative(T r, int act, T scale) {
+  switch (act) {
+    case VVT_ACT_RELU: return r > T(0) ? T(1) : T(0);
+    case VVT_ACT_SIGMOID: return r * (T(1) - r);
+    case VVT_ACT_TANH: return T(1) - r * r;
+    case VVT_ACT_DROPOUT: return r != T(0) ? scale : T(0);
+    case VVT_ACT_LEAKY_RELU: return r > T(0) ? T(1) : scale;
+    case VVT_ACT_ELU: return r > T(0) ? T(1) : scale * exp(r);
+    case VVT_ACT_SELU:
+      return T(1.0507009873554804934193349852946) * (r > T(0) ? T(1) : T(1.6732632423543772848170429916717) * exp(r));
+    case VVT_ACT_LOGSIGMOID: return T(1) / (T(1) + exp(r));
+    default: return r;
+  }
+}
+
+template <typename T>
 __global__ void act_kernel(T* out, const T* S, const T* ref, int64_t V, int64_t nf, int act, T scale) {
   const int64_t total = V * nf;
-  GRID_STRIDE(i, total) {
-    const T r = ldg(ref + i % nf);
-    T d;
-    switch (act) {
-      case VVT_ACT_RELU: d = r > T(0) ? T(1) : T(0); break;
-      case VVT_ACT_SIGMOID: d = r * (T(1) - r); break;
-      case VVT_ACT_TANH: d = T(1) - r * r; break;
-      case VVT_ACT_DROPOUT: d = r != T(0) ? scale : T(0); break;
-      case VVT_ACT_LEAKY_RELU: d = r > T(0) ? T(1) : scale; break;
-      case VVT_ACT_ELU: d = r > T(0) ? T(1) : scale * exp(r); break;
-      case VVT_ACT_SELU:
-        d = T(1.0507009873554804934193349852946) * (r > T(0) ? T(1) : T(1.6732632423543772848170429916717) * exp(r));
-        break;
-      case VVT_ACT_LOGSIGMOID: d = T(1) / (T(1) + exp(r)); break;
-      default: d = r;
+  GRID_STRIDE(i, total) out[i] = S[i] * act_derivative(ldg(ref + i % nf), act, scale);
+}
+
+// Streaming form (16-byte aligned rows): a thread owns one 16-byte group of features, evaluates the derivative
+// ONCE and streams the V rows of the factor through it, UNROLL rows in flight: `ref` is read once instead of V
+// times, no division per element, 16-byte accesses.
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(256) act_rows_kernel(T* out, const T* S, const T* ref, int64_t V, int64_t nf, int act,
+                                                       T scale) {
+  constexpr int VW = 16 / int(sizeof(T));
+  const int64_t groups = nf / VW;
+  for (int64_t gidx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; gidx < groups;
+       gidx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t f = gidx * VW;
+    T d[VW];
+    {
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(ref + f));
+      const T* r = reinterpret_cast<const T*>(&r4);
+#pragma unroll
+      for (int e = 0; e < VW; ++e) d[e] = act_derivative(r[e], act, scale);
     }
-    out[i] = S[i] * d;
+    const int64_t v_lo = blockIdx.y * int64_t(UNROLL);
+    for (int64_t v0 = v_lo; v0 < V; v0 += int64_t(gridDim.y) * UNROLL) {
+      float4 x[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (v0 + u < V) x[u] = __ldcs(reinterpret_cast<const float4*>(S + (v0 + u) * nf + f));
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (v0 + u < V) {
+          T* xe = reinterpret_cast<T*>(&x[u]);
+#pragma unroll
+          for (int e = 0; e < VW; ++e) xe[e] *= d[e];
+          *reinterpret_cast<float4*>(out + (v0 + u) * nf + f) = x[u];
+        }
+    }
   }
 }
 
@@ -136,41 +171,68 @@ maxpool_bwd_kernel(T* out, const T* S, const int64_t* argmax, int64_t planes, in
   }
 }
 
-// Fast path: the argmax map is shared by the V rows of a sample (S is [V, N, ch, ho, wo]), so one block
-// takes one (n, c) plane, resolves for every input position which of its (at most 2 x 2) candidate windows
-// chose it ONCE, and then streams the V output planes: per element one coalesced store and up to four
-// predicated loads from a map that sits in L1.  Windows with ceil(k / stride) <= 2 and no dilation.
-template <typename T>
+// Fast path: the argmax map is shared by the V rows of a sample (S is [V, N, ch, ho, wo]), so one block takes one
+// (n, c) plane, resolves for every input position which of its (at most 2 x 2) candidate windows chose it ONCE,
+// and then streams the V output planes.  The pooled planes of a chunk of rows are brought to shared memory with
+// coalesced loads (every pooled value is wanted by exactly one input position, so reading them from global
+// memory position by position fetched a 32-byte sector per 4-byte value); the scatter then reads shared memory
+// and the stores are coalesced along the position.  Windows with ceil(k / stride) <= 2, no dilation, input
+// planes of at most PMAX * 256 positions.
+constexpr int kPoolRows = 8;  // rows of the factor staged per pass
+template <typename T, int PMAX>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_shared_kernel(T* out, const T* S, const int64_t* argmax, int64_t V, int64_t N, int64_t ch, int ho, int wo,
                           int hi, int wi, int kh, int kw, int sh, int sw, int ph, int pw) {
+  extern __shared__ __align__(16) unsigned char pool_smem[];
+  T* sS = reinterpret_cast<T*>(pool_smem);  // [kPoolRows][hw_out]
   const int hw_in = hi * wi, hw_out = ho * wo;
   const int64_t planes = N * ch;
   for (int64_t pl = blockIdx.x; pl < planes; pl += gridDim.x) {
     const int64_t* am = argmax + pl * hw_out;
-    for (int pos = threadIdx.x; pos < hw_in; pos += blockDim.x) {
-      const int y = pos / wi, x = pos - y * wi;
-      const int ay = y + ph, ax = x + pw;
-      const int oy_hi = min(ho - 1, ay / sh), ox_hi = min(wo - 1, ax / sw);
-      const int by = ay - (kh - 1), bx = ax - (kw - 1);
-      const int oy_lo = by > 0 ? (by + sh - 1) / sh : 0, ox_lo = bx > 0 ? (bx + sw - 1) / sw : 0;
-      int off[4];
+    int off[PMAX][4];
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
+    for (int p = 0; p < PMAX; ++p) {
+      const int pos = threadIdx.x + p * 256;
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int oy = oy_lo + dy, ox = ox_lo + dx;
-          const bool hit = oy <= oy_hi && ox <= ox_hi && int(am[oy * wo + ox]) == pos;
-          off[2 * dy + dx] = hit ? oy * wo + ox : -1;
+      for (int j = 0; j < 4; ++j) off[p][j] = -1;
+      if (pos < hw_in) {
+        const int y = pos / wi, x = pos - y * wi;
+        const int ay = y + ph, ax = x + pw;
+        const int oy_hi = min(ho - 1, ay / sh), ox_hi = min(wo - 1, ax / sw);
+        const int by = ay - (kh - 1), bx = ax - (kw - 1);
+        const int oy_lo = by > 0 ? (by + sh - 1) / sh : 0, ox_lo = bx > 0 ? (bx + sw - 1) / sw : 0;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int oy = oy_lo + dy, ox = ox_lo + dx;
+            const bool hit = oy <= oy_hi && ox <= ox_hi && int(am[oy * wo + ox]) == pos;
+            off[p][2 * dy + dx] = hit ? oy * wo + ox : -1;
+          }
+      }
+    }
+    const int64_t s_step = planes * hw_out, o_step = planes * hw_in;
+    for (int64_t v0 = 0; v0 < V; v0 += kPoolRows) {
+      const int vn = int(vmin<int64_t>(kPoolRows, V - v0));
+      __syncthreads();  // the previous chunk has been consumed
+      for (int idx = threadIdx.x; idx < vn * hw_out; idx += 256) {
+        const int u = idx / hw_out, i = idx - u * hw_out;
+        sS[u * hw_out + i] = __ldcs(S + (v0 + u) * s_step + pl * hw_out + i);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int p = 0; p < PMAX; ++p) {
+        const int pos = threadIdx.x + p * 256;
+        if (pos < hw_in) {
+          T* o = out + (v0 * planes + pl) * int64_t(hw_in) + pos;
+          for (int u = 0; u < vn; ++u) {
+            T acc = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (off[p][j] >= 0) acc += sS[u * hw_out + off[p][j]];
+            o[u * o_step] = acc;
+          }
         }
-      const T* s = S + pl * hw_out;
-      T* o = out + pl * hw_in + pos;
-      for (int64_t v = 0; v < V; ++v, s += planes * hw_out, o += planes * hw_in) {
-        T acc = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (off[j] >= 0) acc += s[off[j]];
-        *o = acc;
       }
     }
   }
@@ -180,12 +242,19 @@ template <typename T>
 static void launch_maxpool_bwd(T* out, const T* S, const int64_t* argmax, int64_t planes, int64_t N, int64_t ch, int ho,
                                int wo, int hi, int wi, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
                                cudaStream_t s) {
-  if (dh == 1 && dw == 1 && kh <= 2 * sh && kw <= 2 * sw && N * ch > 0) {
+  const size_t pool_smem = size_t(kPoolRows) * ho * wo * sizeof(T);
+  if (dh == 1 && dw == 1 && kh <= 2 * sh && kw <= 2 * sw && N * ch > 0 && hi * wi <= 4 * 256 && pool_smem <= 48 * 1024) {
     const int64_t V = planes / (N * ch);
     const unsigned blocks = unsigned(vmin<int64_t>(N * ch, int64_t(16) * num_sms()));
-    const int threads = int(vmin<int64_t>(256, align_up(int64_t(hi) * wi, 32)));
-    maxpool_bwd_shared_kernel<T><<<blocks, threads, 0, s>>>(out, S, argmax, V, N, ch, ho, wo, hi, wi, kh, kw, sh, sw, ph,
-                                                           pw);
+    if (hi * wi <= 256)
+      maxpool_bwd_shared_kernel<T, 1><<<blocks, 256, pool_smem, s>>>(out, S, argmax, V, N, ch, ho, wo, hi, wi, kh, kw, sh, sw,
+                                                                     ph, pw);
+    else if (hi * wi <= 512)
+      maxpool_bwd_shared_kernel<T, 2><<<blocks, 256, pool_smem, s>>>(out, S, argmax, V, N, ch, ho, wo, hi, wi, kh, kw, sh, sw,
+                                                                     ph, pw);
+    else
+      maxpool_bwd_shared_kernel<T, 4><<<blocks, 256, pool_smem, s>>>(out, S, argmax, V, N, ch, ho, wo, hi, wi, kh, kw, sh, sw,
+                                                                     ph, pw);
     return;
   }
   const int tx = int(vmin<int64_t>(256, align_up(int64_t(hi) * wi, 32))), ty = 256 / tx;
@@ -547,8 +616,20 @@ int vvt_sqrt_backprop_elementwise(void* out, const void* S, const void* ref, int
   if (V * n_feat == 0) return VVT_OK;
   VVT_REQUIRE(out && S && ref, "null pointer");
   VVT_DISPATCH(dtype, {
-    act_kernel<T><<<ew_blocks(V * n_feat), 256, 0, as_stream(stream)>>>(
-        (T*)out, (const T*)S, (const T*)ref, V, n_feat, act, T(scale));
+    constexpr int VW = 16 / int(sizeof(T));
+    const bool aligned = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(ref)) & 15) == 0;
+    if (aligned && n_feat % VW == 0 && V > 1) {
+      constexpr int UNROLL = 5;
+      const int64_t groups = n_feat / VW;
+      const unsigned bx = unsigned(vmax<int64_t>(1, vmin<int64_t>(ceil_div(groups, 256), 8 * num_sms())));
+      // enough CTAs to fill the GPU: split the rows too when there are few feature groups
+      const unsigned by = unsigned(vmax<int64_t>(1, vmin<int64_t>(ceil_div(V, UNROLL), ceil_div(4 * int64_t(num_sms()), bx))));
+      act_rows_kernel<T, UNROLL><<<dim3(bx, by), 256, 0, as_stream(stream)>>>((T*)out, (const T*)S, (const T*)ref, V, n_feat,
+                                                                              act, T(scale));
+    } else {
+      act_kernel<T><<<ew_blocks(V * n_feat), 256, 0, as_stream(stream)>>>((T*)out, (const T*)S, (const T*)ref, V, n_feat, act,
+                                                                         T(scale));
+    }
     return launched(__func__);
   });
 }
