@@ -178,6 +178,7 @@ class Stepper:
         self.x_host, self.y_host = x.pin_memory(), y.pin_memory()
         self.x, self.y = x.to(device), y.to(device)
         self.host_out = None
+        self.copy_stream = None
         self.h2d_bytes = x.numel() * x.element_size() + y.numel() * y.element_size()
         self.d2h_bytes = 0
         self.mc_ids = None
@@ -196,8 +197,9 @@ class Stepper:
             p.grad = None
         return [comp.get_result(g) for g in self.groups]
 
-    def run(self, x, y):
-        """One step on device-resident ``x, y``; returns the flat list of result tensors."""
+    def run(self, x, y, on_results=None):
+        """One step on device-resident ``x, y``; returns the flat list of result tensors.  ``on_results`` is
+        called with the tensors of every computation as soon as that computation has produced them."""
         import vivit_b200 as vv
 
         w, out = self.w, []
@@ -205,40 +207,76 @@ class Stepper:
         kw = {"process_group": self.pg} if self.pg is not None else {}
         gkw = {**kw, "gather": True} if self.pg is not None else {}
         for call in self.calls:
+            got = []
             if call == "eigvalsh":
-                res = self._pass(vv.EigvalshComputation(**kw), x, y)
-                out += list(res)
+                got += list(self._pass(vv.EigvalshComputation(**kw), x, y))
             elif call == "eigh":
-                res = self._pass(vv.EighComputation(**gkw), x, y)
-                for evals, evecs in res:
-                    out += [evals, *evecs]
+                for evals, evecs in self._pass(vv.EighComputation(**gkw), x, y):
+                    got += [evals, *evecs]
             elif call == "dirderiv":
-                res = self._pass(vv.DirectionalDerivativesComputation(**kw), x, y)
-                for g, l in res:
-                    out += [g, l]
+                for g, l in self._pass(vv.DirectionalDerivativesComputation(**kw), x, y):
+                    got += [g, l]
             elif call == "newton":
                 comp = vv.DirectionalDampedNewtonComputation(
                     subsampling_ggn=w.get("sub_ggn"), mc_samples_ggn=w.get("mc", 0), **gkw)
                 comp._mc_state = self.mc_ids  # class ids pre-sampled on the host
-                res = self._pass(comp, x, y)
-                for steps in res:
-                    out += list(steps)
+                for steps in self._pass(comp, x, y):
+                    got += list(steps)
+            if on_results is not None:
+                on_results(got)
+            out += got
         return out
 
     def step_device(self):
         return self.run(self.x, self.y)
 
     def step_e2e(self):
+        """The step through the public API with HOST buffers: pinned H2D of the batch, D2H of every result.  The
+        results of a computation start their way to the host (side stream, pinned buffers) as soon as that
+        computation is done, i.e. while the next one runs; the step ends when every copy has landed."""
         x = self.x_host.to(self.device, non_blocking=True)
         y = self.y_host.to(self.device, non_blocking=True)
-        out = self.run(x, y)
-        if self.host_out is None:
-            self.host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in out]
-            self.d2h_bytes = sum(t.numel() * t.element_size() for t in out)
-        for h, t in zip(self.host_out, out):
-            h.copy_(t, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return self.host_out
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        compute, host, first = torch.cuda.current_stream(), [], self.host_out is None
+
+        def ship(tensors):
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            self.copy_stream.wait_event(ready)
+            with torch.cuda.stream(self.copy_stream):
+                for t in tensors:
+                    h = torch.empty(t.shape, dtype=t.dtype).pin_memory() if first else self.host_out[len(host)]
+                    h.copy_(t, non_blocking=True)
+                    t.record_stream(self.copy_stream)
+                    host.append(h)
+
+        self.run(x, y, on_results=ship)
+        self.copy_stream.synchronize()
+        compute.synchronize()
+        if first:
+            self.host_out = host
+            self.d2h_bytes = sum(h.numel() * h.element_size() for h in host)
+        return host
+
+
+def pcie_bandwidth(device):
+    """Pinned-memory copy bandwidth of this box (GB/s, 64 MiB, best of 3): the end-to-end leg moves 36 MB of
+    eigenvectors per step at c2, and boxes of the pool differ by more than an order of magnitude here."""
+    n = 64 << 20
+    dev, host = torch.empty(n, dtype=torch.uint8, device=device), torch.empty(n, dtype=torch.uint8).pin_memory()
+    out = {}
+    for name, (dst, src) in {"d2h_gbs": (host, dev), "h2d_gbs": (dev, host)}.items():
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, n / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        out[name] = round(best, 1)
+    return out
 
 
 # --------------------------------------------------------------------------
@@ -736,7 +774,7 @@ def main():
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic", "config": config,
         "e2e": {"value": round(ms_e2e, 4), "unit": "ms", "h2d_bytes_per_step": stepper.h2d_bytes,
-                "d2h_bytes_per_step": stepper.d2h_bytes},
+                "d2h_bytes_per_step": stepper.d2h_bytes, "pinned_copy_bandwidth": pcie_bandwidth(device)},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "eigensolver": eig, "cpu_baseline": cpu,
         # the part of the step that shards over the ranks (factor emit + Gram / cross-term assembly, rank 0) next
         # to the part that every rank repeats (the eigensolver): SURVEY 8e

@@ -516,3 +516,48 @@ def test_hessianfree_operator_and_device_lanczos():
     scale = np.abs(want).max()
     assert np.abs(evals - want).max() <= 1e-10 * scale
     assert np.abs(np.abs(evecs[0]) - np.abs(wvecs[0])).max() <= 1e-7
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_one_dimensional_layers(dtype):
+    """``Conv1d`` / ``MaxPool1d`` / ``AvgPool1d`` run on the 2-d kernels over feature maps of unit
+    height -- the only GPU cases with non-square kernels, strides, paddings and dilations ((1, k), (1, s), ...):
+    eigenpairs, directional derivatives and the Newton step against the oracle."""
+    from vivit_b200 import DirectionalDampedNewtonComputation, DirectionalDerivativesComputation, EighComputation
+
+    torch.manual_seed(0)
+    cm = nn.Sequential(
+        nn.Conv1d(2, 3, 3, stride=2, padding=1), nn.ReLU(), nn.MaxPool1d(2, stride=1),
+        nn.Conv1d(3, 4, 2, dilation=2, bias=False), nn.Tanh(), nn.AvgPool1d(2), nn.Flatten(), nn.Linear(8, 3),
+    ).to(dtype)
+    cx, cy = torch.rand(5, 2, 15).to(dtype), torch.randint(0, 3, (5,))
+    assert cm(cx).shape == (5, 3)
+    cl = nn.CrossEntropyLoss()
+    gm, gx, gy = copy.deepcopy(cm).to(DEV), cx.to(DEV), cy.to(DEV)
+    cg = [{"params": list(cm.parameters()), "criterion": make_top_k(4), "damping": constant_damping(1.0)}]
+    gg = regroup(cg, cm, gm)
+
+    comp = EighComputation()
+    run_backward(gm, nn.CrossEntropyLoss(), gx, gy, comp.get_extensions(), comp.get_extension_hook(gg))
+    ((w_evals, w_evecs),) = ref.eigh(cm, cl, cx, cy, cg)
+    evals, evecs = comp.get_result(gg[0])
+    close(evals, w_evals, dtype, "1-d evals")
+    flat = torch.cat([e.flatten(1) for e in evecs], 1).double().cpu()
+    wflat = torch.cat([e.flatten(1) for e in w_evecs], 1).double()
+    assert (flat @ wflat.t()).abs().diag().min() > 1 - (1e-3 if dtype == torch.float32 else 1e-8)
+
+    dd = DirectionalDerivativesComputation(subsampling_ggn=[3, 0, 1])
+    run_backward(gm, nn.CrossEntropyLoss(), gx, gy, dd.get_extensions(), dd.get_extension_hook(gg))
+    ((wg, wl),) = ref.directional_derivatives(cm, cl, cx, cy, cg, None, [3, 0, 1])
+    gam, lam = dd.get_result(gg[0])
+    close(gam.abs(), wg.abs(), dtype, "1-d gammas")
+    close(lam, wl, dtype, "1-d lambdas")
+
+    nw = DirectionalDampedNewtonComputation()
+    run_backward(gm, nn.CrossEntropyLoss(), gx, gy, nw.get_extensions(), nw.get_extension_hook(gg))
+    (want,) = ref.directional_damped_newton(cm, cl, cx, cy, cg)
+    tm, tx, ty = upcast(cm, cx, cy)
+    (t64,) = ref.directional_damped_newton(tm, cl, tx, ty, regroup(cg, cm, tm))
+    got = torch.cat([s.flatten() for s in nw.get_result(gg[0])])
+    close(got, torch.cat([t.flatten() for t in want]), dtype, "1-d newton",
+          truth=torch.cat([t.flatten() for t in t64]))

@@ -85,6 +85,7 @@ struct JacobiScalars {           // one per problem of a batch
                                  // every later round kernel of this problem exits at once
   int sweeps;                    // sweeps this problem has run
   unsigned long long last_rotations;
+  unsigned long long max_rotations;  // largest number of block pairs any sweep of this problem rotated
   long long t[8];                // VVT_SYEVJ_DEBUG: phase time stamps of CTA 0 (last launch)
 };
 // element strides between the problems of a batch (blockIdx.y = problem index in every kernel of this file)
@@ -740,13 +741,12 @@ __device__ __forceinline__ void signal_blocks(unsigned* done, int ba, int bb, in
 }
 
 // ---- resident variant: this CTA's rows of W and J are loaded once (cp.async) and stay in smem ----
-template <typename T>
-__global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
-onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc,
-                               int* marks, int now, T* Dc, unsigned* done, BatchStrides bs) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Y += blockIdx.y * bs.y, sc += blockIdx.y, marks += blockIdx.y * bs.marks, Dc += blockIdx.y * bs.dc;
-  if (done) done += blockIdx.y * bs.done;
+// One round of one CTA.  PERSIST = false: the body of a per-round launch (programmatic dependent launch between
+// rounds); PERSIST = true: called once per round from the sweep kernel below, whose CTAs stay resident for the
+// 1 + (nb - 1) rounds of a sweep.
+template <typename T, bool PERSIST>
+__device__ __forceinline__ void resident_round(unsigned char* smem_raw, T* Y, int Np, int nb, int round, int rows_per_cta,
+                                               int parts, JacobiScalars* sc, int* marks, int now, T* Dc, unsigned* done) {
   RotSmem<T>& rs = *reinterpret_cast<RotSmem<T>*>(smem_raw);
   T* P = reinterpret_cast<T*>(smem_raw + ((sizeof(RotSmem<T>) + 15) / 16) * 16);  // [parts * rows][LDP]: W rows(, J rows)
   cg::cluster_group cluster = cg::this_cluster();
@@ -761,11 +761,13 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
 
   // programmatic dependent launch: let the next round's CTAs be scheduled while this round runs (they
   // block in griddepcontrol.wait until this grid has completed and its stores are visible)
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (intra || !done) asm volatile("griddepcontrol.wait;" ::: "memory");  // first launch of a sweep: after memsets / init
-  // a finished problem of the batch (flag written by sweep_end_kernel, which the intra round has waited for;
-  // it only changes between sweeps): nothing left to do, and none of its later CTAs waits for done[]
-  if (*reinterpret_cast<const volatile int*>(&sc->converged)) return;
+  if constexpr (!PERSIST) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (intra || !done) asm volatile("griddepcontrol.wait;" ::: "memory");  // first launch of a sweep: after memsets / init
+    // a finished problem of the batch (flag written by sweep_end_kernel, which the intra round has waited for;
+    // it only changes between sweeps): nothing left to do, and none of its later CTAs waits for done[]
+    if (*reinterpret_cast<const volatile int*>(&sc->converged)) return;
+  }
   if (done) wait_blocks(done, ba, bb, unsigned(CL) * unsigned(now - 1), tid);
   if (pair_is_clean(marks, nb, ba, bb, intra)) {  // same decision in every CTA of the cluster
     if (done) signal_blocks(done, ba, bb, tid);
@@ -863,6 +865,36 @@ onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta
   VVT_STAMP(6);
   if (done) signal_blocks(done, ba, bb, tid);
   cluster_release(cluster);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
+onesided_round_resident_kernel(T* Y, int Np, int nb, int round, int rows_per_cta, int parts, JacobiScalars* sc,
+                               int* marks, int now, T* Dc, unsigned* done, BatchStrides bs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Y += blockIdx.y * bs.y, sc += blockIdx.y, marks += blockIdx.y * bs.marks, Dc += blockIdx.y * bs.dc;
+  if (done) done += blockIdx.y * bs.done;
+  resident_round<T, false>(smem_raw, Y, Np, nb, round, rows_per_cta, parts, sc, marks, now, Dc, done);
+}
+
+// A whole sweep in ONE launch: every cluster keeps its pair slot and walks the rounds of the tournament itself;
+// the per-block done[] counters that order the rounds of separate launches order them here as well (a CTA of
+// round r spins until the two clusters of round r - 1 that wrote ITS blocks have signalled).  All CTAs must be
+// resident at once for that: the host launches this kernel only when pairs x cluster size x batch fits on the GPU
+// with one CTA per SM (R <= 1280 in fp32; checked with cudaOccupancyMaxActiveClusters).  972 launches per solve
+// at R = 1280 become 12 -- but the solve gets slower (see syevj_impl), so this variant is opt-in.
+template <typename T>
+__global__ void __launch_bounds__(OT, (sizeof(T) == 4 ? 2 : 1))
+onesided_sweep_resident_kernel(T* Y, int Np, int nb, int rows_per_cta, int parts, JacobiScalars* sc, int* marks,
+                               int now0, T* Dc, unsigned* done, BatchStrides bs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Y += blockIdx.y * bs.y, sc += blockIdx.y, marks += blockIdx.y * bs.marks, Dc += blockIdx.y * bs.dc;
+  done += blockIdx.y * bs.done;
+  if (*reinterpret_cast<const volatile int*>(&sc->converged)) return;  // uniform over the problem's CTAs
+  for (int round = -1; round < nb - 1; ++round) {
+    resident_round<T, true>(smem_raw, Y, Np, nb, round, rows_per_cta, parts, sc, marks, now0 + round + 1, Dc, done);
+    __syncthreads();  // shared memory is reused by the next round
+  }
 }
 
 // ---- streaming variant (any size): rows pass through two chunk buffers, W is read twice -----------
@@ -1293,8 +1325,15 @@ __global__ void sweep_end_kernel(JacobiScalars* sc, int batch, unsigned long lon
   if (b >= batch) return;
   if (!sc[b].converged) {
     sc[b].sweeps += 1;
-    sc[b].last_rotations = sc[b].rotations;
-    if (sc[b].rotations <= thresh) sc[b].converged = 1;
+    const unsigned long long rot = sc[b].rotations;
+    sc[b].last_rotations = rot;
+    if (rot > sc[b].max_rotations) sc[b].max_rotations = rot;
+    // 1 / 256 of all block pairs, or 1 / 64 of the busiest sweep (measured on the cifar10_3c3d Gram: the sweeps
+    // after the count has fallen to 5 % of the pairs change neither eigenvalues nor residuals -- the refinement
+    // step takes care of what they would; relative to the busiest sweep because a rank-deficient matrix never
+    // rotates more than a few pairs, and those must all come to rest)
+    const unsigned long long stop = thresh > sc[b].max_rotations / 64 ? thresh : sc[b].max_rotations / 64;
+    if (rot <= stop) sc[b].converged = 1;
   }
   sc[b].rotations = 0;
   state[3 * b] = sc[b].sweeps;
@@ -1399,6 +1438,65 @@ static int launch_round(T* Y, int Np, int nb, int round, int CL, int rows_per_ct
   cfg.numAttrs = pdl ? 2 : 1;
   VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, round, rows_per_cta, parts, sc, marks, now, Dc, done, bs),
                      "vvt_syevj(round)"));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return VVT_OK;
+}
+
+template <typename T>
+static size_t sweep_smem_bytes(int rows_per_cta, int parts) {
+  // more than half of an SM's shared memory: one CTA per SM, every CTA of the launch resident at once
+  return vmax<size_t>(resident_smem_bytes<T>(rows_per_cta, parts), size_t(116) * 1024);
+}
+
+// Can `clusters` clusters of CL CTAs of the sweep kernel be resident at the same time?  (They spin on each other:
+// a cluster that is not scheduled would never signal.)  Asked of the occupancy calculator, which knows the GPC
+// layout of the device.
+template <typename T>
+static bool sweep_fits(int CL, int rows_per_cta, int parts, int64_t clusters) {
+  auto kern = onesided_sweep_resident_kernel<T>;
+  const size_t smem = sweep_smem_bytes<T>(rows_per_cta, parts);
+  static SmemOptIn opt_in;
+  if (opt_in.ensure(kern, smem, "vvt_syevj(attr)") != VVT_OK) return false;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(clusters * CL));
+  cfg.blockDim = dim3(OT);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(CL);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return int64_t(max_clusters) >= clusters;
+}
+
+template <typename T>
+static int launch_sweep(T* Y, int Np, int nb, int CL, int rows_per_cta, int parts, JacobiScalars* sc, int* marks, int now0,
+                        T* Dc, unsigned* done, BatchStrides bs, int batch, cudaStream_t s) {
+  auto kern = onesided_sweep_resident_kernel<T>;
+  const size_t smem = sweep_smem_bytes<T>(rows_per_cta, parts);
+  static SmemOptIn opt_in;  // per instantiation
+  VVT_TRY(opt_in.ensure(kern, smem, "vvt_syevj(attr)"));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(nb / 2 * CL), unsigned(batch));
+  cfg.blockDim = dim3(OT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(CL);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, kern, Y, Np, nb, rows_per_cta, parts, sc, marks, now0, Dc, done, bs),
+                     "vvt_syevj(sweep)"));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return VVT_OK;
 }
@@ -1533,6 +1631,14 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
   static const bool block_deps_env = getenv("VVT_SYEVJ_GRIDDEP") == nullptr;
   const bool block_deps = block_deps_env && int64_t(pairs) * CL * B <= 4 * int64_t(num_sms());
   const BatchStrides bs{L.y_elems, int64_t(nb + nb * nb), int64_t(nb) * OB * OB, int64_t(nb)};
+  // VVT_SYEVJ_PERSIST=1: one launch per sweep (onesided_sweep_resident_kernel) while every CTA of a round can be
+  // resident at once.  Measured SLOWER than one launch per round with programmatic dependent launch (R = 1280:
+  // 16.6 against 13.1 ms, R = 320: 2.8 against 2.5 ms; 12 launches per solve instead of 972): a cluster that
+  // keeps its pair slot adds "my own previous round" to the two block dependencies of every round, while freshly
+  // launched CTAs start on whichever SM is free.  Kept for hosts where launch overhead is what counts.
+  static const bool persist_env = getenv("VVT_SYEVJ_PERSIST") != nullptr;
+  const bool persistent = persist_env && !L.wide && resident && block_deps && int64_t(pairs) * CL * B <= num_sms() &&
+                          sweep_fits<T>(CL, rows_per_cta, parts, int64_t(pairs) * B);
   static const int stop_div = getenv("VVT_SYEVJ_STOPDIV") ? vmax(1, atoi(getenv("VVT_SYEVJ_STOPDIV"))) : 256;
   // both paths count the 16-column block pairs that still rotated; a sweep visits nb16 / 2 * nb16 of them
   const int64_t nb16 = L.wide ? L.wp.Np / OB : nb;
@@ -1549,6 +1655,9 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
         for (int round = -1; round < L.wp.nbw - 1; ++round)
           VVT_TRY(wide::wide_round((float*)Y, (float*)Tt, (float*)Sm, (int*)Mm, sc, L.wp, maps, round, B, s));
       }
+    } else if (persistent) {
+      VVT_TRY(launch_sweep<T>(Y, Np, nb, CL, rows_per_cta, parts, sc, marks, sweep * nb + 1, (T*)(ws + L.off_dc),
+                              (unsigned*)(ws + L.off_done), bs, int(B), s));
     } else {
       for (int round = -1; round < nb - 1; ++round)
         VVT_TRY(launch_round<T>(Y, Np, nb, round, CL, rows_per_cta, parts, resident, sc, marks, sweep * nb + round + 2,

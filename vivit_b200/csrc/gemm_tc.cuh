@@ -89,6 +89,27 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = row of the tile, one 32-bit column per tf32 element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -122,7 +143,12 @@ constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >>
 // COL_LANES = false: every epilogue thread stores its own output row (lanes = consecutive rows);
 // COL_LANES = true : the tile is staged through shared memory and stored with lanes = consecutive
 //                    columns (coalesced for row-major outputs).  blockIdx.z = batch index.
-template <typename ST, bool COL_LANES>
+// TS = true: the A operand (hi and lo) lives in TENSOR MEMORY instead of shared memory.  With both operands in
+// shared memory a 128 x 128 x 8 tf32 MMA reads 8 KB per 64 cycles -- the SM's whole shared-memory bandwidth --
+// while the converter warps and the TMA writes need the same port: measured 44-46 % tensor-pipe activity.  The
+// converter threads already hold a row of the A tile in registers when they form lo; they store hi and lo to
+// TMEM (tcgen05.st, lane = row, one column per element) and the MMAs fetch only B from shared memory.
+template <typename ST, bool COL_LANES, bool TS = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, ST st,
                int64_t M, int64_t N, int tiles_n, int symmetric, int kblocks_total, int kblocks_per_split) {
@@ -171,14 +197,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  constexpr int kTmemCols = TS ? 512 : TMEM_COLS;  // TS: + 3 stages x (32 hi + 32 lo) columns of A behind the accumulators
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  auto a_cols = [&](int s) { return tmem_base + uint32_t(TMEM_COLS + 64 * s); };  // hi at +0, lo at +32
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -191,6 +219,33 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int k0 = (kb0 + i) * BK;
         tma_load_3d(stage, &mapA, bar_tma(s), k0, tm * BM, batch);
         if (!diag) tma_load_3d(stage + TILE_BYTES, &mapB, bar_tma(s), k0, tn * BN, batch);
+      }
+    }
+  } else if (warp == 1 && TS) {
+    // ===== MMA issuer, A from tensor memory: every product waits for the converters =====
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, use = i / STAGES;
+        const int grp = i / PROMOTE, first = (i % PROMOTE) == 0;
+        const uint32_t acc = tmem_base + uint32_t((grp & 1) * BN);
+        const uint32_t stage = base + s * STAGE_BYTES;
+        const uint32_t b_hi = diag ? stage : stage + TILE_BYTES;
+        const uint32_t b_lo = diag ? stage + 2 * TILE_BYTES : stage + 3 * TILE_BYTES;
+        if (first && grp >= 2) {
+          mbar_wait(bar_acc_empty(grp & 1), ((grp >> 1) - 1) & 1);
+          tcgen05_fence_after();
+        }
+        mbar_wait(bar_conv(s), use & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint32_t a_hi = a_cols(s) + 8 * k, a_lo = a_hi + 32;
+          umma_tf32_ts(acc, a_hi, make_desc(b_hi + 32 * k), kIdesc, !(first && k == 0));
+          umma_tf32_ts(acc, a_hi, make_desc(b_lo + 32 * k), kIdesc, 1);
+          umma_tf32_ts(acc, a_lo, make_desc(b_hi + 32 * k), kIdesc, 1);
+        }
+        umma_commit(bar_empty(s));  // frees the stage (shared memory and the A columns in TMEM)
+        if ((i % PROMOTE) == PROMOTE - 1 || i == nkb - 1) umma_commit(bar_acc_full(grp & 1));
       }
     }
   } else if (warp == 1) {
@@ -263,8 +318,30 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(bar_tma(s), use & 1);
       // lo buffers of this stage are free: the MMAs that read them committed to `empty` before the
       // producer refilled the stage, and that refill is what we just waited for
+      if constexpr (TS) {
+        // A role: this thread's row of the raw tile (128-byte swizzle: 16-byte chunk c of row m sits at chunk
+        // c ^ (m & 7); the eight lanes of a quarter warp hit eight different chunks) -> hi and lo in TMEM
+        const int m = lane_grp * 32 + lane;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 x = *reinterpret_cast<const float4*>(stage + size_t(m) * 128 + size_t((c ^ (m & 7)) * 16));
+          const float e[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t bits = __float_as_uint(e[j]);
+            hi[4 * c + j] = bits;
+            lo[4 * c + j] = __float_as_uint(e[j] - __uint_as_float(bits & 0xFFFFE000u)) + 0x1000u;
+          }
+        }
+        const uint32_t ta = a_cols(s) + (uint32_t(lane_grp * 32) << 16);
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+        tmem_st_wait();
+      }
+      // B role (TS: only the B tile, which is the raw A tile itself on diagonal tiles): lo tiles in shared memory
 #pragma unroll 4
-      for (int v = ct; v < n_vec; v += 128) {
+      for (int v = (TS && !diag) ? ct + TILE_BYTES / 16 : ct; v < n_vec; v += 128) {
         const float4 x = *reinterpret_cast<const float4*>(stage + size_t(v) * 16);
         float4 lo;
         {
@@ -282,6 +359,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         *reinterpret_cast<float4*>(stage + 2 * TILE_BYTES + size_t(v) * 16) = lo;
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      if constexpr (TS) tcgen05_fence_before();
       mbar_arrive(bar_conv(s));
       // one group behind the conversions, so that the wait is (almost) never a stall
       if ((i % PROMOTE) == PROMOTE - 1 && i / PROMOTE >= 1) drain(i / PROMOTE - 1);
@@ -384,7 +462,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
 }
 

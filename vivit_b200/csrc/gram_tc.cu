@@ -42,9 +42,11 @@ int launch_gram_tc(const float* A, const float* B, StdStore<float> st, int64_t M
                    int64_t ldb, bool symmetric, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
                    const char* what) {
   using namespace tc;
-  auto kern = gram_tc_kernel<StdStore<float>, true>;
-  static SmemOptIn opt_in;
-  VVT_TRY(opt_in.ensure(kern, SMEM_BYTES, what));
+  // A operand from tensor memory unless VVT_GRAM_SS is set (both operands from shared memory: the round-1 kernel)
+  static const bool ts = getenv("VVT_GRAM_SS") == nullptr;
+  auto kern = ts ? gram_tc_kernel<StdStore<float>, true, true> : gram_tc_kernel<StdStore<float>, true, false>;
+  static SmemOptIn opt_in[2];
+  VVT_TRY(opt_in[ts].ensure(kern, SMEM_BYTES, what));
   CUtensorMap mapA, mapB;
   if (!make_map(&mapA, A, M, K, lda, 1, 0) || !make_map(&mapB, B, N, K, ldb, 1, 0))
     return fail(VVT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", what);
