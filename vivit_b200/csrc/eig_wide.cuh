@@ -76,6 +76,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, int variant
   return d;
 }
 constexpr uint32_t kIdescMN = tc::kIdesc | (1u << 15) | (1u << 16);  // A and B MN-major
+constexpr uint32_t kIdescBMN = tc::kIdesc | (1u << 16);               // A from tensor memory, B MN-major
 
 template <int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1)
@@ -117,14 +118,19 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // GRAM: the A operand (hi and lo) lives in tensor memory behind the two accumulators, 64 columns per stage
+  // (see gram_tc_kernel<.., TS = true>: the MMAs then fetch only B from shared memory)
+  constexpr bool TS = MODE == GRAM;
+  constexpr int kTmemCols = TS ? 512 : TMEM_COLS;
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  auto a_cols = [&](int s) { return tmem_base + uint32_t(TMEM_COLS + 64 * s); };  // hi at +0, lo at +32
 
   // the chunk-th group of 32 panel columns: wide block (third TMA coordinate) and first column inside it
   auto chunk_blk = [&](int chunk) { return prob * a.nbw + (chunk < 2 ? wa : wb); };
@@ -149,31 +155,50 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer (software-pipelined by one k-block, see gemm_tc.cuh) =====
+  } else if (warp == 1 && TS) {
+    // ===== MMA issuer, GRAM: A from tensor memory, B = the MN-major panel tile (raw / lo) in shared memory =====
     if (lane == 0) {
       const int vr = a.variant;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, use = i / STAGES;
+        const int grp = i / PROMOTE, first = (i % PROMOTE) == 0;
+        const uint32_t acc = tmem_base + uint32_t((grp & 1) * BN);
+        const uint32_t b_hi = base + s * STAGE_BYTES, b_lo = b_hi + 2 * TILE_BYTES;
+        if (first && grp >= 2) {
+          mbar_wait(bar_acc_empty(grp & 1), ((grp >> 1) - 1) & 1);
+          tcgen05_fence_after();
+        }
+        mbar_wait(bar_conv(s), use & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {  // one MMA (K = 8) = two 4-row groups of B, next k-step 1 KB further
+          const uint32_t a_hi = a_cols(s) + 8 * k, a_lo = a_hi + 32;
+          umma_tf32_ts(acc, a_hi, make_desc_mn(b_hi + 1024 * k, vr), kIdescBMN, !(first && k == 0));
+          umma_tf32_ts(acc, a_hi, make_desc_mn(b_lo + 1024 * k, vr), kIdescBMN, 1);
+          umma_tf32_ts(acc, a_lo, make_desc_mn(b_hi + 1024 * k, vr), kIdescBMN, 1);
+        }
+        umma_commit(bar_empty(s));
+        if ((i % PROMOTE) == PROMOTE - 1 || i == nkb - 1) umma_commit(bar_acc_full(grp & 1));
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer, per-tile APPLY (software-pipelined by one k-block, see gemm_tc.cuh) =====
+    if (lane == 0) {
       auto stage_of = [&](int i) { return base + (i % STAGES) * STAGE_BYTES; };
       auto issue_hi = [&](int i) {
         const int s = i % STAGES, use = i / STAGES;
         const int grp = i / PROMOTE, first = (i % PROMOTE) == 0;
         const uint32_t acc = tmem_base + uint32_t((grp & 1) * BN);
-        const uint32_t a_hi = stage_of(i), b_hi = diag ? a_hi : a_hi + TILE_BYTES;
+        const uint32_t a_hi = stage_of(i), b_hi = a_hi + TILE_BYTES;
         if (first && grp >= 2) {
           mbar_wait(bar_acc_empty(grp & 1), ((grp >> 1) - 1) & 1);
           tcgen05_fence_after();
         }
         mbar_wait(bar_tma(s), use & 1);
         tcgen05_fence_after();
-        if (MODE == GRAM && vr < 2) {  // MN-major: one MMA (K = 8) = two 4-row groups, next k-step 1 KB further
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k)
-            umma_tf32(acc, make_desc_mn(a_hi + 1024 * k, vr), make_desc_mn(b_hi + 1024 * k, vr), kIdescMN, !(first && k == 0));
-        } else {
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k)
-            umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_hi + 32 * k), kIdesc, !(first && k == 0));
-        }
+        for (int k = 0; k < BK / 8; ++k)
+          umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_hi + 32 * k), kIdesc, !(first && k == 0));
       };
       issue_hi(0);
       for (int i = 0; i < nkb; ++i) {
@@ -181,22 +206,14 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
         const int s = i % STAGES, use = i / STAGES;
         const int grp = i / PROMOTE;
         const uint32_t acc = tmem_base + uint32_t((grp & 1) * BN);
-        const uint32_t a_hi = stage_of(i), b_hi = diag ? a_hi : a_hi + TILE_BYTES;
-        const uint32_t a_lo = a_hi + 2 * TILE_BYTES, b_lo = diag ? a_lo : a_hi + 3 * TILE_BYTES;
+        const uint32_t a_hi = stage_of(i), b_hi = a_hi + TILE_BYTES;
+        const uint32_t a_lo = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
         mbar_wait(bar_conv(s), use & 1);
         tcgen05_fence_after();
-        if (MODE == GRAM && vr < 2) {
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            umma_tf32(acc, make_desc_mn(a_hi + 1024 * k, vr), make_desc_mn(b_lo + 1024 * k, vr), kIdescMN, 1);
-            umma_tf32(acc, make_desc_mn(a_lo + 1024 * k, vr), make_desc_mn(b_hi + 1024 * k, vr), kIdescMN, 1);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_lo + 32 * k), kIdesc, 1);
-            umma_tf32(acc, make_desc(a_lo + 32 * k), make_desc(b_hi + 32 * k), kIdesc, 1);
-          }
+        for (int k = 0; k < BK / 8; ++k) {
+          umma_tf32(acc, make_desc(a_hi + 32 * k), make_desc(b_lo + 32 * k), kIdesc, 1);
+          umma_tf32(acc, make_desc(a_lo + 32 * k), make_desc(b_hi + 32 * k), kIdesc, 1);
         }
         umma_commit(bar_empty(s));
         if ((i % PROMOTE) == PROMOTE - 1 || i == nkb - 1) umma_commit(bar_acc_full(grp & 1));
@@ -228,6 +245,25 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
       const int s = i % STAGES, use = i / STAGES;
       unsigned char* stage = base_ptr + s * STAGE_BYTES;
       mbar_wait(bar_tma(s), use & 1);
+      if constexpr (TS) {
+        // A role: panel column m = this thread's TMEM lane; its 32 rows (K) of the MN-major tile: chunk m / 32 at
+        // 4096 bytes, 4-row group k / 4 at 512, row k % 4 at 128, 32-byte chunk (m % 32) / 8 XOR k % 4
+        const int m = lane_grp * 32 + lane;
+        const unsigned char* col = stage + size_t(m >> 5) * 4096 + size_t(m & 7) * 4;
+        const int c32 = (m & 31) >> 3;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float x = *reinterpret_cast<const float*>(col + (k >> 2) * 512 + (k & 3) * 128 + ((c32 ^ (k & 3)) << 5));
+          const uint32_t bits = __float_as_uint(x);
+          hi[k] = bits;
+          lo[k] = __float_as_uint(x - __uint_as_float(bits & 0xFFFFE000u)) + 0x1000u;
+        }
+        const uint32_t ta = a_cols(s) + (uint32_t(lane_grp * 32) << 16);
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+        tmem_st_wait();
+      }
 #pragma unroll 4
       for (int v = ct; v < n_vec; v += 128) {
         const float4 x = *reinterpret_cast<const float4*>(stage + size_t(v) * 16);
@@ -241,6 +277,7 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
         *reinterpret_cast<float4*>(stage + 2 * TILE_BYTES + size_t(v) * 16) = make_float4(o[0], o[1], o[2], o[3]);
       }
       fence_proxy_async();
+      if constexpr (TS) tcgen05_fence_before();
       mbar_arrive(bar_conv(s));
       if ((i % PROMOTE) == PROMOTE - 1 && i / PROMOTE >= 1) drain(i / PROMOTE - 1);
     }
@@ -267,7 +304,7 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
 }
 
@@ -275,14 +312,16 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
 // P <- P Q for all pairs of a round: K = 128 only, so a CTA per output tile (wide_tc_kernel<APPLY>) spends its
 // life in prologue and epilogue (measured: 8.4 us per 128 x 128 tile, 1.6 us of which are MMAs).  Here a CTA
 // walks a contiguous range of (pair, row tile) work items: Q^T (hi and lo, 128 KB) stays in shared memory while
-// the pair does not change, the rows of the factor stream through a 3-deep ring of k-blocks, two TMEM
+// the pair does not change, the rows of the factor stream through a 4-deep ring of k-blocks, two TMEM
 // accumulators alternate between the MMA warp and four epilogue warps that store straight from registers
-// (every thread owns one output row: 4 x 128 contiguous bytes).
+// (every thread owns one output row: 4 x 128 contiguous bytes).  The A operand (rows of P, hi and lo) is handed to
+// the tensor core through TENSOR MEMORY by the converter warps, so the MMAs read only Q^T from shared memory.
 //   warp 0: TMA producer   warp 1: MMA issuer   warps 2-5: converters (lo tiles)   warps 6-9: epilogue
-constexpr int AP_STAGES = 3;
+constexpr int AP_STAGES = 4;
 constexpr int AP_THREADS = 320;
-constexpr int AP_Q_BYTES = 8 * tc::TILE_BYTES;      // 4 k-blocks x (hi | lo)
-constexpr int AP_STAGE_BYTES = 2 * tc::TILE_BYTES;  // one k-block of P: raw | lo
+constexpr int AP_Q_BYTES = 8 * tc::TILE_BYTES;  // 4 k-blocks x (hi | lo)
+constexpr int AP_STAGE_BYTES = tc::TILE_BYTES;  // one k-block of P, raw (hi and lo of it go to tensor memory)
+constexpr int AP_TMEM_COLS = 512;               // two accumulators (2 x 128) + AP_STAGES x (32 hi + 32 lo) columns of P
 constexpr size_t AP_SMEM = size_t(AP_Q_BYTES) + AP_STAGES * AP_STAGE_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(AP_THREADS, 1)
@@ -325,13 +364,14 @@ wide_apply_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(AP_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  auto p_cols = [&](int s) { return tmem_base + uint32_t(TMEM_COLS + 64 * s); };  // hi at +0, lo at +32
 
   auto q_hi = [&](int j) { return qbase + uint32_t(j) * 2 * TILE_BYTES; };
   auto a_raw = [&](int s) { return abase + uint32_t(s) * AP_STAGE_BYTES; };
@@ -387,20 +427,17 @@ wide_apply_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
         const uint32_t acc = tmem_base + uint32_t(buf * BN);
         for (int j = 0; j < 4; ++j, ++kbc) {
           const int s = kbc % AP_STAGES, use = kbc / AP_STAGES;
-          const uint32_t p_hi = a_raw(s), p_lo = p_hi + TILE_BYTES, qh = q_hi(j), ql = qh + TILE_BYTES;
-          mbar_wait(bar_a_tma(s), use & 1);
-          tcgen05_fence_after();
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k)
-            umma_tf32(acc, make_desc(p_hi + 32 * k), make_desc(qh + 32 * k), kIdesc, !(j == 0 && k == 0));
-          mbar_wait(bar_a_conv(s), use & 1);
+          const uint32_t qh = q_hi(j), ql = qh + TILE_BYTES;
+          mbar_wait(bar_a_conv(s), use & 1);  // hi and lo of the k-block are in tensor memory
           tcgen05_fence_after();
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
-            umma_tf32(acc, make_desc(p_hi + 32 * k), make_desc(ql + 32 * k), kIdesc, 1);
-            umma_tf32(acc, make_desc(p_lo + 32 * k), make_desc(qh + 32 * k), kIdesc, 1);
+            const uint32_t p_hi = p_cols(s) + 8 * k, p_lo = p_hi + 32;
+            umma_tf32_ts(acc, p_hi, make_desc(qh + 32 * k), kIdesc, !(j == 0 && k == 0));
+            umma_tf32_ts(acc, p_hi, make_desc(ql + 32 * k), kIdesc, 1);
+            umma_tf32_ts(acc, p_lo, make_desc(qh + 32 * k), kIdesc, 1);
           }
-          umma_commit(bar_a_empty(s));
+          umma_commit(bar_a_empty(s));  // frees the stage: shared memory and the columns in tensor memory
         }
         umma_commit(bar_acc_full(buf));
         ++n;
@@ -438,10 +475,27 @@ wide_apply_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
       }
       for (int j = 0; j < 4; ++j, ++kbc) {
         const int s = kbc % AP_STAGES, use = kbc / AP_STAGES;
-        unsigned char* st = base_ptr + AP_Q_BYTES + size_t(s) * AP_STAGE_BYTES;
+        const unsigned char* st = base_ptr + AP_Q_BYTES + size_t(s) * AP_STAGE_BYTES;
         mbar_wait(bar_a_tma(s), use & 1);
-        convert(st, st + TILE_BYTES, TILE_BYTES / 16);
-        fence_proxy_async();
+        // this thread's row of the k-block (128-byte swizzle: chunk c of row m sits at chunk c ^ (m & 7)) -> TMEM
+        const int lane_grp = warp & 3, m = lane_grp * 32 + lane;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 x = *reinterpret_cast<const float4*>(st + size_t(m) * 128 + size_t((c ^ (m & 7)) * 16));
+          const float e[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t bits = __float_as_uint(e[q]);
+            hi[4 * c + q] = bits;
+            lo[4 * c + q] = __float_as_uint(e[q] - __uint_as_float(bits & 0xFFFFE000u)) + 0x1000u;
+          }
+        }
+        const uint32_t ta = p_cols(s) + (uint32_t(lane_grp * 32) << 16);
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+        tmem_st_wait();
+        tcgen05_fence_before();
         mbar_arrive(bar_a_conv(s));
       }
     }
@@ -476,7 +530,7 @@ wide_apply_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(AP_TMEM_COLS) : "memory");
   }
 }
 
