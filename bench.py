@@ -247,8 +247,7 @@ class Stepper:
             with torch.cuda.stream(self.copy_stream):
                 for t in tensors:
                     h = torch.empty(t.shape, dtype=t.dtype).pin_memory() if first else self.host_out[len(host)]
-                    h.copy_(t, non_blocking=True)
-                    t.record_stream(self.copy_stream)
+                    h.copy_(t, non_blocking=True)  # `t` stays referenced by run()'s result list until the copies have landed
                     host.append(h)
 
         self.run(x, y, on_results=ship)

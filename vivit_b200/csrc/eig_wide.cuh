@@ -863,16 +863,20 @@ wide_rot_cluster_kernel(float* Qt, int* flag, const float* part, int nbw, int ro
     sub_pair(intra_round, 0, g, sa, sb, intra);
     const float* p0 = part + (size_t(prob) * splits * pairs + pair) * size_t(WP * WP);
     const size_t split_stride = size_t(pairs) * WP * WP;
-    for (int idx = tid; idx < OP * WP; idx += OT) {
-      const int i = idx / WP, c = idx % WP;
+    // (rows only, coalesced: the tensor core forms both triangles of P^T P from the same operands, they differ in
+    // the last bits at most -- the order of the hi*lo / lo*hi terms -- and the rotation angles do not care;
+    // reading the mirrored entries as well, column-wise, cost 18 % of this kernel)
+    for (int idx = tid; idx < OP * WP / 4; idx += OT) {
+      const int i = (idx * 4) / WP, c = (idx * 4) % WP;
       const int r = panel_index(sa, sb, i);
-      float a = 0.f, b = 0.f;
-      for (int k = 0; k < splits; ++k) {
-        a += p0[k * split_stride + size_t(r) * WP + c];
-        b += p0[k * split_stride + size_t(c) * WP + r];
+      float4 a = *reinterpret_cast<const float4*>(p0 + size_t(r) * WP + c);
+      for (int k = 1; k < splits; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(p0 + k * split_stride + size_t(r) * WP + c);
+        a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
       }
-      sm.Hrows[0][i][c] = r == c ? a : 0.5f * (a + b);  // the two triangles differ in the last bits
-      sm.Qown[i][c] = (32 * g + i == c) ? 1.f : 0.f;
+      sm.Hrows[0][i][c] = a.x, sm.Hrows[0][i][c + 1] = a.y, sm.Hrows[0][i][c + 2] = a.z, sm.Hrows[0][i][c + 3] = a.w;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sm.Qown[i][c + e] = (32 * g + i == c + e) ? 1.f : 0.f;
     }
   }
   int any = 0, cur = 0;
