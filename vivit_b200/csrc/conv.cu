@@ -158,6 +158,65 @@ struct EmitStoreTc {
   }
 };
 
+// The same store for the 4-d operand form (no re-layout of the factor): the GEMM's row index is padded,
+// m' = tile * 128 + r with tile = v_chunk * o_chunks + o_chunk and r = o_local + 32 v_local (the order in which a
+// TMA box {32 x, 32 o, 1 n, 4 v} of S[v][n][o][x] lands in shared memory); rows outside (V, Co) are skipped.
+struct EmitStoreTc4 {
+  float* Vt;
+  int64_t N, c_out, J, batch0, V;
+  int o_chunks;
+  __device__ __forceinline__ int64_t row_offset(int n, int64_t m) const {
+    const int64_t tile = m >> 7;
+    const int r = int(m & 127);
+    const int64_t v = (tile / o_chunks) * 4 + (r >> 5), o = (tile % o_chunks) * 32 + (r & 31);
+    return (v < V && o < c_out) ? ((v * N + (batch0 + n)) * c_out + o) * J : int64_t(-1);
+  }
+  __device__ __forceinline__ void store(int64_t off, int64_t, int64_t j, float val, int) const {
+    if (off >= 0) Vt[off + j] = val;
+  }
+  __device__ __forceinline__ float fetch(int64_t, int64_t, int64_t) const { return 0.f; }
+  __device__ __forceinline__ void commit(int64_t off, int64_t, int64_t j, float val, float, int) const {
+    if (off >= 0) Vt[off + j] = val;
+  }
+  __device__ __forceinline__ void operator()(int n, int64_t m, int64_t j, float val, int) const {
+    const int64_t off = row_offset(n, m);
+    if (off >= 0) Vt[off + j] = val;
+  }
+};
+
+// A[b] = rows (v, o) of sample b of S[v][n][o][x], read in place through a 4-d tensor map; B[b] = Un[b] [J][Xp]
+static int launch_emit_tc_4d(const float* S, const float* Un, float* Vt, int64_t V, int64_t N, int64_t c_out, int64_t J,
+                             int64_t X, int64_t Xp, cudaStream_t stream, const char* what) {
+  using namespace tc;
+  auto kern = gram_tc_kernel<EmitStoreTc4, true, false, true>;
+  static SmemOptIn opt_in;
+  VVT_TRY(opt_in.ensure(kern, SMEM_BYTES, what));
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(VVT_ERR_CUDA, "%s: cuTensorMapEncodeTiled unavailable", what);
+  const int o_chunks = int(ceil_div(c_out, 32)), v_chunks = int(ceil_div(V, 4));
+  const int64_t Mp = int64_t(o_chunks) * v_chunks * BM;
+  const int tiles_n = int(ceil_div(J, BN));
+  const int64_t kblocks = vmax<int64_t>(1, ceil_div(X, BK));
+  for (int64_t b0 = 0; b0 < N; b0 += 65535) {
+    const int64_t nb = vmin<int64_t>(65535, N - b0);
+    CUtensorMap mapA, mapB;
+    const cuuint64_t dims[4] = {cuuint64_t(X), cuuint64_t(c_out), cuuint64_t(nb), cuuint64_t(V)};
+    const cuuint64_t strides[3] = {cuuint64_t(X) * 4, cuuint64_t(c_out) * X * 4, cuuint64_t(N) * c_out * X * 4};
+    const cuuint32_t box[4] = {BK, 32, 1, 4};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (fn(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(S + b0 * c_out * X), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+        !make_map(&mapB, Un + b0 * J * Xp, J, X, Xp, nb, J * Xp))
+      return fail(VVT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", what);
+    EmitStoreTc4 st{Vt, N, c_out, J, b0, V, o_chunks};
+    dim3 grid(unsigned(o_chunks * v_chunks * tiles_n), 1, unsigned(nb));
+    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, st, Mp, J, tiles_n, 0, int(kblocks), int(kblocks), o_chunks);
+    VVT_TRY(launched(what));
+  }
+  return VVT_OK;
+}
+
 // St[(r, x)][o] (row pitch Cop) <- S[r][o][x]: one 32x32 tile per block, transposed through shared memory
 __global__ void __launch_bounds__(256) dgrad_transpose_kernel(float* St, const float* S, int Co, int X, int Cop) {
   __shared__ float tile[32][33];
@@ -306,12 +365,22 @@ int vvt_v_emit_conv2d(void* Vt, const void* S, const void* X, int64_t V, int64_t
     float* Sn = (float*)((char*)workspace + w.a);
     float* Un = (float*)((char*)workspace + w.b);
     cudaStream_t s = as_stream(stream);
+    im2col_kernel<<<ew_blocks(N * J * Xp), 256, 0, s>>>(Un, (const float*)X, g, int(N), int(J), int(Xn), int(Xp));
+    VVT_TRY(launched("vvt_v_emit_conv2d(im2col)"));
+    // The factor is read in place when TMA can address it: rows (v, o) of one sample through a 4-d tensor map
+    // (V >= 4: a tile is 32 channels x 4 rows v), or as it is when there is a single row v per sample.  Only
+    // spatial extents that are not a multiple of 4 floats (16-byte TMA strides) go through the re-layout copy.
+    static const bool relayout = getenv("VVT_EMIT_PERMUTE") != nullptr;  // experiments: always copy
+    const bool aligned = Xp == Xn && (reinterpret_cast<uintptr_t>(S) & 15) == 0;
+    if (aligned && V >= 4 && !relayout)
+      return launch_emit_tc_4d((const float*)S, Un, (float*)Vt, V, N, c_out, J, Xn, Xp, s, "vvt_v_emit_conv2d");
+    EmitStoreTc st{(float*)Vt, N, c_out, J, 0};
+    if (aligned && V == 1 && !relayout)  // S [1][N][Co][X] is already [n][(v, o)][x]
+      return tc::launch_gemm_tc_batched<EmitStoreTc, true>((const float*)S, Un, st, M, J, Xn, Xp, Xp, N, M * Xp, J * Xp, s,
+                                                           "vvt_v_emit_conv2d");
     emit_permute_kernel<<<ew_blocks(N * M * Xp), 256, 0, s>>>(Sn, (const float*)S, int(V), int(N), int(c_out),
                                                              int(Xn), int(Xp));
     VVT_TRY(launched("vvt_v_emit_conv2d(permute)"));
-    im2col_kernel<<<ew_blocks(N * J * Xp), 256, 0, s>>>(Un, (const float*)X, g, int(N), int(J), int(Xn), int(Xp));
-    VVT_TRY(launched("vvt_v_emit_conv2d(im2col)"));
-    EmitStoreTc st{(float*)Vt, N, c_out, J, 0};
     return tc::launch_gemm_tc_batched<EmitStoreTc, true>(Sn, Un, st, M, J, Xn, Xp, Xp, N, M * Xp, J * Xp, s,
                                                          "vvt_v_emit_conv2d");
   }

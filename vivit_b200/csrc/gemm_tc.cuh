@@ -77,6 +77,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -148,10 +154,15 @@ constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >>
 // while the converter warps and the TMA writes need the same port: measured 44-46 % tensor-pipe activity.  The
 // converter threads already hold a row of the A tile in registers when they form lo; they store hi and lo to
 // TMEM (tcgen05.st, lane = row, one column per element) and the MMAs fetch only B from shared memory.
-template <typename ST, bool COL_LANES, bool TS = false>
+// A4D = true: the rows of an A tile are a 32 x 4 box of TWO row indices (a 4-d tensor map {k, i, batch, j}, box
+// {32, 32, 1, 4}: tile row r = i_local + 32 j_local); row tile tm covers i-chunk tm % a4_chunks and j-chunk
+// tm / a4_chunks.  Used by the conv factor emit, whose rows (v, o) of a sample are not equidistant in memory: the
+// store functor decodes the padded row index (see EmitStoreTc4 in conv.cu).
+template <typename ST, bool COL_LANES, bool TS = false, bool A4D = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, ST st,
-               int64_t M, int64_t N, int tiles_n, int symmetric, int kblocks_total, int kblocks_per_split) {
+               int64_t M, int64_t N, int tiles_n, int symmetric, int kblocks_total, int kblocks_per_split,
+               int a4_chunks = 1) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // tiles must be 1024-byte aligned
   unsigned char* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -217,7 +228,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t stage = base + s * STAGE_BYTES;
         mbar_expect_tx(bar_tma(s), diag ? TILE_BYTES : 2 * TILE_BYTES);
         const int k0 = (kb0 + i) * BK;
-        tma_load_3d(stage, &mapA, bar_tma(s), k0, tm * BM, batch);
+        if constexpr (A4D) tma_load_4d(stage, &mapA, bar_tma(s), k0, (tm % a4_chunks) * 32, batch, (tm / a4_chunks) * 4);
+        else tma_load_3d(stage, &mapA, bar_tma(s), k0, tm * BM, batch);
         if (!diag) tma_load_3d(stage + TILE_BYTES, &mapB, bar_tma(s), k0, tn * BN, batch);
       }
     }
@@ -528,7 +540,7 @@ inline int launch_gemm_tc_batched(const float* A, const float* B, ST st, int64_t
     ST stb = st;
     stb.batch0 = b0;
     dim3 grid(unsigned(tiles_m * tiles_n), 1, unsigned(nb));
-    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, stb, M, N, tiles_n, 0, int(kblocks), int(kblocks));
+    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, stb, M, N, tiles_n, 0, int(kblocks), int(kblocks), 1);
     VVT_TRY(launched(what));
   }
   return VVT_OK;

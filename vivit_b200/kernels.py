@@ -70,8 +70,29 @@ def _stream(t: Tensor):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+# Workspace arena: one byte buffer per (device, stream), grown on demand and reused by every kernel entry point that
+# needs scratch memory.  Calls on one stream execute in order, so a later call may overwrite the scratch of an earlier
+# one; nothing a caller receives ever aliases it.  (Fresh ``torch.empty`` workspaces of 50 MB ... 3 GB per call made
+# the caching allocator split and re-allocate blocks: a step of config 3 took 16 or 41 ms depending on the
+# allocator's history.)  ``release_workspaces()`` hands the memory back.
+_WORKSPACES = {}
+
+
 def _ws(nbytes: int, like: Tensor) -> Tensor:
-    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=like.device)
+    nbytes = max(int(nbytes), 16)
+    key = (like.device.index, torch.cuda.current_stream(like.device).cuda_stream)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _WORKSPACES.pop(key, None)
+        buf = None  # free the old block before asking for the larger one
+        buf = torch.empty(nbytes + nbytes // 8, dtype=torch.uint8, device=like.device)
+        _WORKSPACES[key] = buf
+    return buf[:nbytes]
+
+
+def release_workspaces() -> None:
+    """Drop the cached scratch buffers (they are re-created on demand)."""
+    _WORKSPACES.clear()
 
 
 def _c(t: Tensor) -> Tensor:
