@@ -644,7 +644,14 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps, with_kernels=False):
+        # Python's cyclic garbage collector is kept out of the timed region (collected before, switched off inside):
+        # a generation-2 pass in the middle of a step frees gigabytes of factor tensors at once and showed up as a
+        # single 60 ... 200 ms step among 42 ms ones (scratch/e2e_steps.py), i.e. as noise of the mean over K steps
+        import gc
+
         evs = []
+        gc.collect()
+        gc.disable()
         barrier()
         if with_kernels:
             kernels.timing_start()
@@ -658,6 +665,7 @@ def main():
             e1.record()
             evs.append((e0, e1))
         barrier()
+        gc.enable()
         wall = (time.time() - t0) * 1e3 / steps
         launches = kernels.launch_count() - l0
         recs = kernels.timing_stop() if with_kernels else []
@@ -682,7 +690,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     ms, wall, launches, recs = timed(stepper.step_device, args.steps, with_kernels=True)
     clocks = sampler.stop() if sampler else None
-    for _ in range(2):
+    for _ in range(3):  # the first call also allocates the pinned result buffers
         stepper.step_e2e()
     ms_e2e, _, _, _ = timed(stepper.step_e2e, args.steps)
 

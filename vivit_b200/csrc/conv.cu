@@ -3,7 +3,7 @@
 //   * data gradient of the factor ("virtual batch" of V*N maps)
 #include <cstdlib>
 
-#include "gemm_tc.cuh"
+#include "gemm_smallk.cuh"
 
 namespace vvt {
 
@@ -182,6 +182,22 @@ struct EmitStoreTc4 {
     const int64_t off = row_offset(n, m);
     if (off >= 0) Vt[off + j] = val;
   }
+  // persistent small-K kernel: 32 (or fewer) consecutive columns of one row, from registers
+  __device__ __forceinline__ void store_chunk(int64_t off, int64_t, int64_t col0, int ncols, const uint32_t (&r)[32]) const {
+    float* dst = Vt + off + col0;
+    if (ncols == 32 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)  // 256-bit stores: whole 32-byte sectors
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * q), "r"(r[8 * q]),
+                     "r"(r[8 * q + 1]), "r"(r[8 * q + 2]), "r"(r[8 * q + 3]), "r"(r[8 * q + 4]), "r"(r[8 * q + 5]),
+                     "r"(r[8 * q + 6]), "r"(r[8 * q + 7])
+                     : "memory");
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < ncols) dst[i] = __uint_as_float(r[i]);
+    }
+  }
 };
 
 // A[b] = rows (v, o) of sample b of S[v][n][o][x], read in place through a 4-d tensor map; B[b] = Un[b] [J][Xp]
@@ -210,6 +226,10 @@ static int launch_emit_tc_4d(const float* S, const float* Un, float* Vt, int64_t
         !make_map(&mapB, Un + b0 * J * Xp, J, X, Xp, nb, J * Xp))
       return fail(VVT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", what);
     EmitStoreTc4 st{Vt, N, c_out, J, b0, V, o_chunks};
+    if (smallk::worthwhile(Mp, J, X, nb)) {  // a few k-blocks per tile: the persistent form (gemm_smallk.cuh)
+      VVT_TRY((smallk::launch<EmitStoreTc4, true>(mapA, mapB, st, Mp, J, X, nb, o_chunks * v_chunks, o_chunks, stream, what)));
+      continue;
+    }
     dim3 grid(unsigned(o_chunks * v_chunks * tiles_n), 1, unsigned(nb));
     kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, st, Mp, J, tiles_n, 0, int(kblocks), int(kblocks), o_chunks);
     VVT_TRY(launched(what));
@@ -256,6 +276,13 @@ struct DgradStoreTc {
   __device__ __forceinline__ void commit(int64_t off, int64_t, int64_t j, float val, float, int) const { T2[off + j * X] = val; }
   __device__ __forceinline__ void operator()(int b, int64_t m, int64_t j, float val, int) const {
     T2[row_offset(b, m) + j * X] = val;
+  }
+  // persistent small-K kernel: lanes are consecutive rows m = (r, x), i.e. consecutive x: coalesced per column
+  __device__ __forceinline__ void store_chunk(int64_t off, int64_t, int64_t col0, int ncols, const uint32_t (&r)[32]) const {
+    float* dst = T2 + off + col0 * X;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols) dst[int64_t(i) * X] = __uint_as_float(r[i]);
   }
 };
 
@@ -423,8 +450,16 @@ int vvt_sqrt_backprop_conv2d(void* out, const void* S, const void* W, int64_t ro
     weight_transpose_kernel<<<ew_blocks(Jd * Cop), 256, 0, s>>>(Wt, (const float*)W, int(c_out), int(Jd), int(Cop));
     VVT_TRY(launched("vvt_sqrt_backprop_conv2d(weights)"));
     DgradStoreTc st{T2, Xo, Jd, 0};
-    VVT_TRY((tc::launch_gemm_tc_batched<DgradStoreTc, false>(St, Wt, st, rows * Xo, Jd, c_out, Cop, Cop, 1, 0, 0, s,
-                                                             "vvt_sqrt_backprop_conv2d")));
+    if (smallk::worthwhile(rows * Xo, Jd, c_out, 1)) {  // K = c_out: a few k-blocks per tile (gemm_smallk.cuh)
+      CUtensorMap mapA, mapB;
+      if (!tc::make_map(&mapA, St, rows * Xo, c_out, Cop, 1, 0) || !tc::make_map(&mapB, Wt, Jd, c_out, Cop, 1, 0))
+        return fail(VVT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", "vvt_sqrt_backprop_conv2d");
+      VVT_TRY((smallk::launch<DgradStoreTc, false>(mapA, mapB, st, rows * Xo, Jd, c_out, 1, int(ceil_div(rows * Xo, tc::BM)), 1,
+                                                   s, "vvt_sqrt_backprop_conv2d")));
+    } else {
+      VVT_TRY((tc::launch_gemm_tc_batched<DgradStoreTc, false>(St, Wt, st, rows * Xo, Jd, c_out, Cop, Cop, 1, 0, 0, s,
+                                                               "vvt_sqrt_backprop_conv2d")));
+    }
     col2im_kernel<<<ew_blocks(M * c_in), 256, 0, s>>>((float*)out, T2, g, rows, int(Jd), int(Xo));
     return launched("vvt_sqrt_backprop_conv2d(col2im)");
   }
