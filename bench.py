@@ -644,14 +644,14 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps, with_kernels=False):
-        # Python's cyclic garbage collector is kept out of the timed region (collected before, switched off inside):
-        # a generation-2 pass in the middle of a step frees gigabytes of factor tensors at once and showed up as a
-        # single 60 ... 200 ms step among 42 ms ones (scratch/e2e_steps.py), i.e. as noise of the mean over K steps
+        # one collection up front, so a generation-2 pass over leftovers of the warm-up does not land in the timed
+        # region.  (The product itself leaves nothing for the cyclic collector: the hook/closure and factor-partner
+        # reference cycles that used to keep gigabytes of factor tensors alive across steps -- one 60 ... 200 ms step
+        # among 42 ms ones, scratch/e2e_steps.py -- are gone, tests/test_host_cpu.py::test_step_leaves_no_garbage.)
         import gc
 
         evs = []
         gc.collect()
-        gc.disable()
         barrier()
         if with_kernels:
             kernels.timing_start()
@@ -665,7 +665,6 @@ def main():
             e1.record()
             evs.append((e0, e1))
         barrier()
-        gc.enable()
         wall = (time.time() - t0) * 1e3 / steps
         launches = kernels.launch_count() - l0
         recs = kernels.timing_stop() if with_kernels else []

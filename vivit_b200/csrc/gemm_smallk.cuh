@@ -251,8 +251,10 @@ smallk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 static inline bool worthwhile(int64_t M, int64_t N, int64_t K, int64_t batch) {
   static const bool off = getenv("VVT_NO_SMALLK") != nullptr;
   if (off || K > int64_t(MAX_KB) * tc::BK) return false;
+  // (a CTA loads and converts a B tile before its first MMA: below about six tiles per SM the per-tile kernel,
+  // which spreads the tiles over more CTAs, is as fast or faster -- measured on the All-CNN-C layers)
   const int64_t tiles = ceil_div(M, tc::BM) * ceil_div(N, tc::BN) * batch;
-  return tiles >= 2 * int64_t(num_sms());
+  return tiles >= 6 * int64_t(num_sms());
 }
 
 template <typename ST, bool A4D>

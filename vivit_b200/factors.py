@@ -162,9 +162,13 @@ class LinearWeightFactor(Factor):
 
 
 def link_linear_factors(weight_factor: LinearWeightFactor, weight, bias_factor: LinearBiasFactor, bias) -> None:
-    """Tell the two factors of one Linear layer about each other (and about each other's parameter)."""
-    weight_factor.partner, weight_factor.partner_param = bias_factor, bias
-    bias_factor.partner, bias_factor.partner_param = weight_factor, weight
+    """Tell the two factors of one Linear layer about each other (and about each other's parameter).  Weak
+    references: the two objects hold the layer's ``S`` and ``Z``, and a reference cycle would keep those alive until
+    the cyclic garbage collector runs."""
+    import weakref
+
+    weight_factor.partner, weight_factor.partner_param = weakref.ref(bias_factor), bias
+    bias_factor.partner, bias_factor.partner_param = weakref.ref(weight_factor), weight
 
 
 def fold_linear_bias(factor: Factor, same_group) -> None:
@@ -172,6 +176,7 @@ def fold_linear_bias(factor: Factor, same_group) -> None:
     layer whose other parameter is in the same group (``same_group(param) -> bool``), the layer's two Gram
     contributions are assembled by ONE structured call (see ``LinearBiasFactor``)."""
     partner = getattr(factor, "partner", None)
+    partner = partner() if partner is not None else None  # weak reference (link_linear_factors)
     if partner is None or factor.partner_param is None or not same_group(factor.partner_param):
         return
     weight, bias = (factor, partner) if isinstance(factor, LinearWeightFactor) else (partner, factor)

@@ -18,7 +18,6 @@ parameters is never reset (``hooks.py:45,73``); mint a new hook per backward pas
 
 from __future__ import annotations
 
-import types
 from typing import Any, Callable, Dict, List
 
 from torch.nn import Module, Parameter, Sequential
@@ -99,11 +98,28 @@ class ParameterGroupsHook:
     ) -> "ParameterGroupsHook":
         """Build a hook from three free functions taking the hook as first argument
         (``hooks.py:361-390``)."""
-        hook = cls(param_groups)
-        hook.param_computation = types.MethodType(param_computation_fn, hook)
-        hook.group_hook = types.MethodType(group_hook_fn, hook)
-        hook.accumulate = types.MethodType(accumulate_fn, hook)
+        # (the functions are kept as plain attributes and called with the hook as first argument: binding them as
+        # methods of the instance would tie the hook, the closures and everything they capture -- the computation
+        # object with its results, factors with their activations -- into a reference cycle that only the cyclic
+        # garbage collector frees, gigabytes and several steps later)
+        hook = _FunctionHook(param_groups)
+        hook._fns = (param_computation_fn, group_hook_fn, accumulate_fn)
         return hook
+
+
+class _FunctionHook(ParameterGroupsHook):
+    """``ParameterGroupsHook`` whose three operations are free functions taking the hook as first argument."""
+
+    _fns = (None, None, None)
+
+    def param_computation(self, param: Parameter) -> Any:
+        return self._fns[0](self, param)
+
+    def group_hook(self, accumulation: Any, group: Dict[str, Any]) -> Any:
+        return self._fns[1](self, accumulation, group)
+
+    def accumulate(self, existing: Any, update: Any) -> Any:
+        return self._fns[2](self, existing, update)
 
 
 class ModuleHook:
