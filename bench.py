@@ -140,6 +140,7 @@ class Stepper:
 
         self.w, self.device, self.pg = w, device, process_group
         self.calls = tuple(w["calls"])
+        self.batch_solves = True
         model, x, y = make_problem(w, dtype)
         self.model = extend(model.to(device))
         self.loss_fn = extend(nn.CrossEntropyLoss())
@@ -186,7 +187,7 @@ class Stepper:
             g = torch.Generator().manual_seed(1)
             self.mc_ids = torch.randint(0, w["classes"], (w["mc"], len(w["sub_ggn"])), generator=g).to(device)
 
-    def _pass(self, comp, x, y):
+    def _backward(self, comp, x, y):
         from vivit_b200 import backpack
 
         hook = comp.get_extension_hook(self.groups)
@@ -195,6 +196,9 @@ class Stepper:
             self.loss_fn(self.model(x), y).backward()
         for p in self.model.parameters():
             p.grad = None
+
+    def _pass(self, comp, x, y):
+        self._backward(comp, x, y)
         return [comp.get_result(g) for g in self.groups]
 
     def run(self, x, y, on_results=None):
@@ -206,26 +210,44 @@ class Stepper:
         # sharded runs return the WHOLE eigenvectors / steps (all-gathered), the same deliverable as on one GPU
         kw = {"process_group": self.pg} if self.pg is not None else {}
         gkw = {**kw, "gather": True} if self.pg is not None else {}
+        # several computations of one step (c2: eigenpairs, then directional derivatives -- two backward passes, as
+        # in the reference) share a SolveQueue: their Gram matrices are decomposed by ONE batched solver call when
+        # the first result is read.  --sequential-solves restores the reference's order (solve inside each hook).
+        queue = vv.SolveQueue() if self.batch_solves and len(self.calls) > 1 else None
+        qkw = {"solve_queue": queue} if queue is not None else {}
+        comps = []
         for call in self.calls:
-            got = []
             if call == "eigvalsh":
-                got += list(self._pass(vv.EigvalshComputation(**kw), x, y))
+                comp = vv.EigvalshComputation(**kw)
             elif call == "eigh":
-                for evals, evecs in self._pass(vv.EighComputation(**gkw), x, y):
-                    got += [evals, *evecs]
+                comp = vv.EighComputation(**gkw, **qkw)
             elif call == "dirderiv":
-                for g, l in self._pass(vv.DirectionalDerivativesComputation(**kw), x, y):
-                    got += [g, l]
+                comp = vv.DirectionalDerivativesComputation(**kw, **qkw)
             elif call == "newton":
                 comp = vv.DirectionalDampedNewtonComputation(
                     subsampling_ggn=w.get("sub_ggn"), mc_samples_ggn=w.get("mc", 0), **gkw)
                 comp._mc_state = self.mc_ids  # class ids pre-sampled on the host
-                for steps in self._pass(comp, x, y):
-                    got += list(steps)
-            if on_results is not None:
-                on_results(got)
-            out += got
+            self._backward(comp, x, y)
+            comps.append((call, comp))
+            if queue is None:
+                out += self._collect(call, comp, on_results)
+        if queue is not None:
+            for call, comp in comps:
+                out += self._collect(call, comp, on_results)
         return out
+
+    def _collect(self, call, comp, on_results):
+        got = []
+        for res in (comp.get_result(g) for g in self.groups):
+            if call == "eigvalsh":
+                got.append(res)
+            elif call == "eigh":
+                got += [res[0], *res[1]]
+            else:  # (gammas, lambdas) / Newton steps per parameter
+                got += list(res)
+        if on_results is not None:
+            on_results(got)
+        return got
 
     def step_device(self):
         return self.run(self.x, self.y)
@@ -363,7 +385,7 @@ def lookup_traffic(name, shapes):
     return entry["dram_bytes_per_launch"] if entry else None
 
 
-def eigensolver_report(stepper):
+def eigensolver_report(stepper, batch=1):
     """The per-group Gram of the workload solved by ``vvt_syevj`` and, beside it, by cuSOLVER through
     ``torch.linalg.eigh`` on the same GPU: ms (CUDA events, 3 repetitions), sweeps, residuals."""
     import vivit_b200 as vv
@@ -410,6 +432,11 @@ def eigensolver_report(stepper):
     sweeps = sinfo["sweeps"]
     lib_ms, (wv, _) = ms_of(lambda: torch.linalg.eigh(G))
     lib_vals_ms, _ = ms_of(lambda: torch.linalg.eigvalsh(G))
+    batched = None
+    if batch > 1:  # what the shared SolveQueue of the step asks for: `batch` such matrices in one call
+        GG = torch.stack([G] * batch).contiguous()
+        b_ms, _ = ms_of(lambda: orig_b(GG, True, return_info=True))
+        batched = {"batch": batch, "ms": round(b_ms, 3)}
     Gd, Ud, evd = G.double(), U.double(), ev.double()
     want = torch.linalg.eigvalsh(Gd)
     scale = want.abs().max().item() or 1.0
@@ -418,7 +445,7 @@ def eigensolver_report(stepper):
         "eigenvalue_error_rel_max": float((evd - want).abs().max().item() / scale),
         "residual_fro": float(((Gd @ Ud - Ud * evd[None]).norm() / Gd.norm()).item()),
         "orthogonality_max_abs": float((Ud.t() @ Ud - torch.eye(R, dtype=torch.float64, device=G.device)).abs().max().item()),
-        "cusolver_eigh_ms": round(lib_ms, 3), "cusolver_eigvalsh_ms": round(lib_vals_ms, 3),
+        "cusolver_eigh_ms": round(lib_ms, 3), "cusolver_eigvalsh_ms": round(lib_vals_ms, 3), "batched": batched,
         "note": "vvt_syevj: Cholesky-preconditioned one-sided block Jacobi + one refinement step, all on the GPU",
     }
 
@@ -587,6 +614,9 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--sequential-solves", action="store_true",
+                    help="decompose every Gram matrix inside the hook that assembled it (the reference's order) "
+                         "instead of one batched solve per step for the computations of the step")
     ap.add_argument("--ncu-step", action="store_true",
                     help="warm up, run ONE step between cudaProfilerStart/Stop and exit "
                          "(for `ncu --profile-from-start off`; prints no bench line)")
@@ -633,7 +663,14 @@ def main():
     from vivit_b200 import kernels
 
     stepper = Stepper(w, dtype, device, pg)
+    stepper.batch_solves = not args.sequential_solves
     config["parallelism"] = stepper.parallelism
+    shared_queue = stepper.batch_solves and len(stepper.calls) > 1
+    if len(stepper.calls) > 1:
+        config["solves"] = (
+            "the computations of the step (one backward pass each, as in the reference) share a SolveQueue: their "
+            "Gram matrices are decomposed by one batched vvt_syevj_batched call" if shared_queue else
+            "every Gram matrix decomposed inside the hook that assembled it (the reference's order)")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
 
     def barrier():
@@ -692,6 +729,15 @@ def main():
     for _ in range(3):  # the first call also allocates the pinned result buffers
         stepper.step_e2e()
     ms_e2e, _, _, _ = timed(stepper.step_e2e, args.steps)
+    sequential = None
+    if shared_queue:  # the same step in the reference's order, for the record
+        stepper.batch_solves = False
+        for _ in range(3):
+            stepper.step_device()
+        seq_ms, _, seq_launches, _ = timed(stepper.step_device, args.steps)
+        sequential = {"ms_per_step": round(seq_ms, 4), "gpu_launches": seq_launches,
+                      "note": "--sequential-solves: each computation decomposes its Gram matrix inside its own hook"}
+        stepper.batch_solves = True
 
     if rank != 0:
         if world > 1:
@@ -747,7 +793,7 @@ def main():
                     "traffic": traffic, "peak_source": f"{peak_src} HBM copy", "ms_per_call": round(per_call_ms, 4),
                     "calls_per_step": g["calls"] / args.steps, "share_of_step": round(g["ms"] / step_ms, 4)}
 
-    eig = eigensolver_report(stepper) if world == 1 else None
+    eig = eigensolver_report(stepper, len(stepper.calls) if shared_queue else 1) if world == 1 else None
     if roof is not None:
         # the whole step against its own floor: algorithmic flops / tensor peak + algorithmic bytes / HBM peak of
         # every roofline-scored kernel (the eigensolver has no such figure and counts as zero work: it can only
@@ -765,7 +811,8 @@ def main():
             if top["kernel"].startswith("syevj") and eig:
                 roof["dominant_kernel_of_step"].update(
                     note="latency-bound eigensolver: no tensor/HBM roofline; reported against cuSOLVER on the same GPU",
-                    ms_per_solve=eig["ms"], cusolver_ms_per_solve=eig["cusolver_eigh_ms"], R=eig["R"], sweeps=eig["sweeps"])
+                    ms_per_solve=eig["ms"], cusolver_ms_per_solve=eig["cusolver_eigh_ms"], R=eig["R"], sweeps=eig["sweeps"],
+                    batched=eig["batched"])
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -782,6 +829,7 @@ def main():
         "e2e": {"value": round(ms_e2e, 4), "unit": "ms", "h2d_bytes_per_step": stepper.h2d_bytes,
                 "d2h_bytes_per_step": stepper.d2h_bytes, "pinned_copy_bandwidth": pcie_bandwidth(device)},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "eigensolver": eig, "cpu_baseline": cpu,
+        "sequential_solves": sequential,
         # the part of the step that shards over the ranks (factor emit + Gram / cross-term assembly, rank 0) next
         # to the part that every rank repeats (the eigensolver): SURVEY 8e
         "gram_assembly_ms_per_step": round(sum(r["ms_per_step"] for r in rows if r["kernel"].startswith(("gram_", "v_emit_"))), 4),

@@ -333,3 +333,40 @@ def test_step_leaves_no_garbage():
         if was_enabled:
             gc.enable()
     assert not tensors, (len(tensors), kinds)
+
+
+@pytest.mark.parametrize("grouping", GROUPINGS, ids=GROUPING_IDS)
+def test_shared_solve_queue_gives_the_immediate_results(grouping, monkeypatch):
+    """``EighComputation`` and ``DirectionalDerivativesComputation`` on ONE ``SolveQueue``: two backward passes,
+    nothing decomposed until the first ``get_result``, then one batched call per matrix shape -- and the results
+    of the immediate order (``eigh.py:248``, ``directional_derivatives.py:291``)."""
+    import vivit_b200 as vv
+    from vivit_b200 import kernels
+
+    problem = PROBLEMS[0]
+    calls = []
+    single, batched = kernels.syevj, kernels.syevj_batched
+    monkeypatch.setattr(kernels, "syevj", lambda G, *a, **k: (calls.append(1), single(G, *a, **k))[1])
+    monkeypatch.setattr(kernels, "syevj_batched", lambda G, *a, **k: (calls.append(G.shape[0]), batched(G, *a, **k))[1])
+
+    def both(queue):
+        model, loss_fn, x, y = problem.make()
+        groups = grouping(model, criterion=keep_nonzero)
+        kw = {} if queue is None else {"solve_queue": queue}
+        eigh, dirs = vv.EighComputation(**kw), vv.DirectionalDerivativesComputation(**kw)
+        run_backward(model, loss_fn, x, y, [eigh.get_extension()], eigh.get_extension_hook(groups))
+        run_backward(model, loss_fn, x, y, dirs.get_extensions(), dirs.get_extension_hook(groups))
+        if queue is not None:
+            assert len(queue) == 2 * len(groups) and not calls
+        return [(eigh.get_result(g), dirs.get_result(g)) for g in groups]
+
+    want = both(None)
+    del calls[:]
+    got = both(vv.SolveQueue())
+    assert sum(calls) == 2 * len(want) and len(calls) < sum(calls)  # batched
+    for ((ev0, vecs0), (g0, l0)), ((ev1, vecs1), (g1, l1)) in zip(want, got):
+        close(ev0, ev1)
+        close(g0, g1)
+        close(l0, l1)
+        for a, b in zip(vecs0, vecs1):
+            close(a, b)

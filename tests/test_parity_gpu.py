@@ -561,3 +561,37 @@ def test_one_dimensional_layers(dtype):
     got = torch.cat([s.flatten() for s in nw.get_result(gg[0])])
     close(got, torch.cat([t.flatten() for t in want]), dtype, "1-d newton",
           truth=torch.cat([t.flatten() for t in t64]))
+
+
+@pytest.mark.gpu
+def test_shared_solve_queue_on_the_gpu():
+    """Two Computations on one ``SolveQueue`` (``linalg/solve_queue.py``): one ``vvt_syevj_batched`` call for both
+    Gram matrices, results equal to the immediate order (``eigh.py:248``, ``directional_derivatives.py:291``) up
+    to the solver's own tolerance."""
+    import vivit_b200 as vv
+    from vivit_b200 import kernels
+
+    problem = PROBLEMS[0]
+
+    def both(queue):
+        model, loss_fn, x, y = problem.make(torch.float64, "cuda")
+        model, loss_fn = vv.extend(model), vv.extend(loss_fn)
+        groups = [{"params": list(model.parameters()), "criterion": keep_nonzero}]
+        kw = {} if queue is None else {"solve_queue": queue}
+        eigh, dirs = vv.EighComputation(**kw), vv.DirectionalDerivativesComputation(**kw)
+        for comp in (eigh, dirs):
+            with vv.backpack(*comp.get_extensions(), extension_hook=comp.get_extension_hook(groups)):
+                loss_fn(model(x), y).backward()
+        if queue is not None:
+            assert len(queue) == 2
+        return eigh.get_result(groups[0]), dirs.get_result(groups[0])
+
+    (ev0, vecs0), (g0, l0) = both(None)
+    before = kernels.launch_count()
+    (ev1, vecs1), (g1, l1) = both(vv.SolveQueue())
+    assert kernels.launch_count() > before
+    assert torch.allclose(ev0, ev1, rtol=1e-10, atol=1e-12 * ev0.abs().max().item())
+    assert torch.allclose(l0, l1, rtol=1e-8, atol=1e-12)
+    assert torch.allclose(g0.abs(), g1.abs(), rtol=1e-6, atol=1e-10)  # sign of a direction is free
+    for a, b in zip(vecs0, vecs1):
+        assert a.shape == b.shape

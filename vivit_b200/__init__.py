@@ -24,7 +24,7 @@ from vivit_b200.backprop import (
     extend,
 )
 from vivit_b200 import custom_module, extensions, hessianfree
-from vivit_b200.linalg import EighComputation, EigvalshComputation
+from vivit_b200.linalg import EighComputation, EigvalshComputation, SolveQueue
 from vivit_b200.optim import DirectionalDampedNewtonComputation, DirectionalDerivativesComputation
 
 __version__ = "0.1.0"
@@ -37,6 +37,7 @@ __all__ = [
     "EighComputation",
     "DirectionalDerivativesComputation",
     "DirectionalDampedNewtonComputation",
+    "SolveQueue",
     "ViViTGGNExact",
     "ViViTGGNMC",
     "SqrtGGNExact",

@@ -30,6 +30,7 @@
 // method; the path never produces such matrices (Grams are PSD up to rounding).
 #include <cooperative_groups.h>
 
+#include <chrono>
 #include <cstdlib>
 
 #include "gemm_core.cuh"
@@ -1681,10 +1682,16 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
       if (!slot[3 * b + 1]) most_rotations = vmax<long long>(most_rotations, slot[3 * b + 2]);
       if (info) info[2 * b] = slot[3 * b], info[2 * b + 1] = slot[3 * b + 1];
     }
-    if (debug)
-      fprintf(stderr, "[vvt_syevj] R=%lld batch=%lld %s CL=%d sweep %d: %d of %lld block pairs rotated (problem 0)\n",
+    if (debug) {  // host time at which the state of this sweep arrived: differences are the sweeps' GPU times
+      static thread_local std::chrono::steady_clock::time_point last;
+      const auto now = std::chrono::steady_clock::now();
+      const double us = sweep == 0 ? 0.0 : std::chrono::duration<double, std::micro>(now - last).count();
+      last = now;
+      fprintf(stderr,
+              "[vvt_syevj] R=%lld batch=%lld %s CL=%d sweep %d: %d of %lld block pairs rotated (problem 0), +%.0f us\n",
               (long long)R, (long long)B, L.wide ? "wide" : "16-wide", CL, sweep + 1, slot[2],
-              (long long)((nb16 / 2) * nb16));
+              (long long)((nb16 / 2) * nb16), us);
+    }
     return all;
   };
   {

@@ -12,6 +12,7 @@ from torch.nn import Module, Parameter
 from vivit_b200 import kernels
 from vivit_b200.factors import fold_linear_bias
 from vivit_b200.linalg.eigvalsh import _accumulate_gram, _make_dist
+from vivit_b200.linalg.solve_queue import SolveQueue
 from vivit_b200.linalg.utils import get_hook_store_batch_size, get_vivit_extension, normalize
 from vivit_b200.utils import delete_savefield, keep_indices
 from vivit_b200.utils.checks import check_key_exists, check_subsampling_unique, check_unique_params
@@ -35,11 +36,16 @@ class EighComputation:
         process_group=None,
         gather: bool = False,
         batch_solves: bool = True,
+        solve_queue: Optional[SolveQueue] = None,
     ):
         """``batch_solves`` (not in the reference): with several block-diagonal groups, the Gram matrices are
         decomposed in ONE batched solver call once the last group has fired (the groups are independent,
         ``vivit/utils/hooks.py:214-219``, and share ``R = C * N``); a group's factors stay alive until then.
-        ``False`` restores the reference's order (solve and free inside every group's hook)."""
+        ``False`` restores the reference's order (solve and free inside every group's hook).
+
+        ``solve_queue`` (not in the reference): a ``SolveQueue`` shared with other Computations.  The Gram
+        matrices are handed to it and decomposed, together with everything else in the queue, when the first
+        result is asked for (``linalg/solve_queue.py``)."""
         check_subsampling_unique(subsampling)
         self._subsampling = subsampling
         self._mc_samples = mc_samples
@@ -47,8 +53,8 @@ class EighComputation:
         self._dist = _make_dist(process_group)
         self._gather = gather
         self._batch_solves = batch_solves
-        self._pending: List[tuple] = []
-        self._finish = None
+        self._shared_queue = solve_queue
+        self._queue = solve_queue if solve_queue is not None else SolveQueue()
         self._savefield = self.get_extension().savefield
         self._warn_small_eigvals = warn_small_eigvals
         self._mc_state = None
@@ -60,8 +66,8 @@ class EighComputation:
     def get_result(self, group: Dict) -> Tuple[Tensor, List[Tensor]]:
         """``(evals [K], [evecs_p [K, *p.shape]])`` of a GGN block (``eigh.py:65-90``)."""
         gid = id(group)
-        if self._pending:
-            self._flush()
+        if gid not in self._evals and len(self._queue):
+            self._queue.flush()
         try:
             return self._evals[gid], self._evecs[gid]
         except KeyError as e:
@@ -90,8 +96,10 @@ class EighComputation:
         batch_sizes, subsampling, savefield = self._batch_size, self._subsampling, self._savefield
         evals, evecs, verbose = self._evals, self._evecs, self._verbose
         warn_small_eigvals, dist, gather = self._warn_small_eigvals, self._dist, self._gather
-        pending, batch = self._pending, self._batch_solves and len(param_groups) > 1
-        pending.clear()
+        queue, shared = self._queue, self._shared_queue is not None
+        batch, fired = self._batch_solves and len(param_groups) > 1, []
+        if not shared:
+            queue.clear()  # leftovers of a backward pass that did not reach its last group
 
         def param_computation(hook: ParameterGroupsHook, param: Parameter) -> None:
             pass  # nothing per parameter (eigh.py:174-181)
@@ -117,9 +125,11 @@ class EighComputation:
             # eigh.py:245-246; over several ranks the rescale rides on the all-reduce of the partial Grams
             dist.scale_allreduce_(1.0 if subsampling is None else batch_size / len(subsampling), gram)
 
-            pending.append((group, gram, factors))
-            if not batch or len(pending) == len(param_groups):
-                self._flush()
+            queue.submit(gram, lambda gram_evals, gram_evecs: finish(group, gram_evals, gram_evecs, factors))
+            fired.append(gid)
+            if not shared and (not batch or len(fired) == len(param_groups)):
+                del fired[:]
+                queue.flush()  # eigh.py:248 (all groups of this pass in one call)
 
         def finish(group, gram_evals, gram_evecs, factors) -> None:
             gid = id(group)
@@ -151,8 +161,6 @@ class EighComputation:
             evals[gid] = gram_evals
             evecs[gid] = group_evecs
 
-        self._finish = finish
-
         hook = ParameterGroupsHook.from_functions(param_groups, param_computation, group_hook, accumulate)
 
         def extension_hook(module: Module) -> None:
@@ -166,19 +174,6 @@ class EighComputation:
             for group in param_groups:
                 print(f"{id(group)} → {[id(p) for p in group['params']]}")
         return extension_hook
-
-    def _flush(self) -> None:
-        """Decompose the pending Gram matrices (one batched call when they share a shape) and finish their
-        groups: filter, back-transform, normalise (``eigh.py:248-275``)."""
-        items, self._pending[:] = list(self._pending), []
-        grams = [gram for _, gram, _ in items]
-        if len(items) > 1 and all(g.shape == grams[0].shape and g.dtype == grams[0].dtype for g in grams):
-            all_evals, all_evecs = kernels.syevj_batched(torch.stack(grams), vectors=True)  # eigh.py:248, all groups
-            solved = [(all_evals[i], all_evecs[i]) for i in range(len(items))]
-        else:
-            solved = [kernels.syevj(gram, vectors=True) for gram in grams]  # eigh.py:248
-        for (group, _, factors), (gram_evals, gram_evecs) in zip(items, solved):
-            self._finish(group, gram_evals, gram_evecs, factors)
 
     @staticmethod
     def _check_param_groups(param_groups: List[Dict]) -> None:

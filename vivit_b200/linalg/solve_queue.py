@@ -1,0 +1,71 @@
+"""Deferred, batched eigendecompositions shared by several Computations (not in the reference).
+
+The reference decomposes a group's Gram matrix inside the hook that assembled it (``vivit/linalg/eigh.py:248``,
+``vivit/optim/directional_derivatives.py:291``).  The solver of this package is latency-bound at the sizes of the
+path (``R = C * N`` of a thousand or so: a round of the block Jacobi is a chain of barriers and reductions that
+keeps ~120 of the 148 SMs busy with very little work each), and a batch of such problems costs far less than the
+sum of its members: two ``R = 1280`` matrices take 16.9 ms together and 13.2 ms each.  A ``SolveQueue`` collects
+the matrices of every Computation it was handed to and decomposes them in ONE ``vvt_syevj_batched`` call when the
+first result is asked for:
+
+    queue = SolveQueue()
+    eigh = EighComputation(solve_queue=queue)
+    dirs = DirectionalDerivativesComputation(solve_queue=queue)
+    with backpack(eigh.get_extension(), extension_hook=eigh.get_extension_hook(groups)):
+        loss_fn(model(x), y).backward()
+    with backpack(*dirs.get_extensions(), extension_hook=dirs.get_extension_hook(groups)):
+        loss_fn(model(x), y).backward()
+    evals, evecs = eigh.get_result(groups[0])      # <- both Gram matrices are decomposed here, together
+    gammas, lambdas = dirs.get_result(groups[0])
+
+Results are those of the immediate order (same kernels, and the batched solver treats its problems
+independently); what changes is when they exist and that a group's factors stay alive until then.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, List, Tuple
+
+import torch
+from torch import Tensor
+
+from vivit_b200 import kernels
+
+
+class SolveQueue:
+    """Symmetric eigenproblems waiting for one batched solve."""
+
+    def __init__(self) -> None:
+        self._items: List[Tuple[Tensor, Callable[[Tensor, Tensor], None]]] = []
+
+    def __len__(self) -> int:
+        return len(self._items)
+
+    def clear(self) -> None:
+        """Forget what was submitted (without solving)."""
+        self._items = []
+
+    def submit(self, gram: Tensor, done: Callable[[Tensor, Tensor], None]) -> None:
+        """``done(evals, evecs)`` is called by ``flush`` with the ascending eigenvalues ``[R]`` and the
+        eigenvectors ``[R, R]`` (columns) of ``gram``.  ``gram`` must not be modified until then."""
+        self._items.append((gram, done))
+
+    def flush(self) -> None:
+        """Decompose everything submitted so far -- matrices of one shape, dtype and device in one batched call --
+        and run the callbacks in submission order."""
+        items, self._items = self._items, []
+        if not items:
+            return
+        solved: List = [None] * len(items)
+        buckets = {}
+        for i, (gram, _) in enumerate(items):
+            buckets.setdefault((tuple(gram.shape), gram.dtype, gram.device), []).append(i)
+        for members in buckets.values():
+            if len(members) == 1:
+                solved[members[0]] = kernels.syevj(items[members[0]][0], vectors=True)
+                continue
+            evals, evecs = kernels.syevj_batched(torch.stack([items[i][0] for i in members]), vectors=True)
+            for slot, i in enumerate(members):
+                solved[i] = (evals[slot], evecs[slot])
+        for (_, done), (evals, evecs) in zip(items, solved):
+            done(evals, evecs)

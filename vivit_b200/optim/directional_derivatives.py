@@ -15,6 +15,7 @@ from vivit_b200 import kernels
 from vivit_b200.backprop.extensions import BatchGrad
 from vivit_b200.factors import Factor, GradFactor, fold_linear_bias
 from vivit_b200.linalg.eigvalsh import _make_dist
+from vivit_b200.linalg.solve_queue import SolveQueue
 from vivit_b200.linalg.utils import get_hook_store_batch_size
 from vivit_b200.optim.utils import get_sqrt_ggn_extension
 from vivit_b200.utils import delete_savefield, keep_indices
@@ -49,9 +50,15 @@ class DirectionalDerivativesComputation:
         verbose: Optional[bool] = False,
         warn_small_eigvals: float = 1e-4,
         process_group=None,
+        solve_queue: Optional[SolveQueue] = None,
     ):
+        """``solve_queue`` (not in the reference): a ``SolveQueue`` shared with other Computations; the group's
+        Gram matrix is decomposed, together with everything else in the queue, when the first result is asked
+        for (``linalg/solve_queue.py``).  Only ``V^T V`` and ``V^T g`` wait for it, the factors are freed as
+        in the immediate order."""
         check_subsampling_unique(subsampling_grad)
         check_subsampling_unique(subsampling_ggn)
+        self._queue = solve_queue
         self._mc_samples_ggn = mc_samples_ggn
         if self._mc_samples_ggn != 0:
             assert mc_samples_ggn == 1  # directional_derivatives.py:73-74
@@ -71,6 +78,8 @@ class DirectionalDerivativesComputation:
     def get_result(self, group: Dict) -> Tuple[Tensor, Tensor]:
         """``(gammas [N_grad, K], lambdas [N_ggn, K])`` (``directional_derivatives.py:94-117``)."""
         gid = id(group)
+        if gid not in self._gammas and self._queue is not None:
+            self._queue.flush()
         try:
             return self._gammas[gid], self._lambdas[gid]
         except KeyError as e:
@@ -99,7 +108,7 @@ class DirectionalDerivativesComputation:
             ),
             lambda hook, accumulation, group: self._group_hook(
                 hook, accumulation, group, self._batch_size, self._gammas, self._lambdas,
-                self._verbose, self._warn_small_eigvals, self._dist,
+                self._verbose, self._warn_small_eigvals, self._dist, self._queue,
             ),
             lambda hook, existing, update: self._accumulate(hook, existing, update, self._verbose),
         )
@@ -153,22 +162,22 @@ class DirectionalDerivativesComputation:
         return acc
 
     @staticmethod
-    def _directions(accumulation, group, N, verbose, warn_small_eigvals, dist):
-        """Eigendecompose the Gram matrix, filter, evaluate ``gamma`` and ``lambda``
-        (``directional_derivatives.py:281-325`` == ``directional_damped_newton.py:304-351``)."""
+    def _gram_space(accumulation, N, dist):
+        """Finished Gram-space quantities of a group and the matrix to decompose, ``corr^2 V^T V``
+        (``directional_derivatives.py:281-291``)."""
         if not isinstance(accumulation, _GramSpace):
             accumulation = DirectionalDerivativesComputation._start(accumulation)
-        gid = id(group)
         acc = accumulation
         dist.scale_allreduce_(1.0, acc.V_t_V, acc.V_t_g_n)  # the one exchange of the sharded path
-        N_ggn, C = acc.N_ggn, acc.C
-        corr2 = N / N_ggn  # V_correction**2  (:285-287)
+        corr2 = N / acc.N_ggn  # V_correction**2  (:285-287)
         # eigenpairs of corr^2 V^T V; the solver leaves its input intact, so scale a copy
         gram = acc.V_t_V if corr2 == 1.0 else kernels.scale_(acc.V_t_V.clone(), corr2)
-        if verbose:
-            print(f"Group {gid}: Eigen-decompose Gram matrix")
-        evals, evecs = kernels.syevj(gram, vectors=True)  # :291
+        return acc, gram, corr2
 
+    @staticmethod
+    def _filter_and_evaluate(acc, evals, evecs, group, N, verbose, warn_small_eigvals):
+        """Filter the directions, evaluate ``gamma`` and ``lambda`` (``directional_derivatives.py:293-325``)."""
+        gid = id(group)
         keep = group["criterion"](evals)  # :293
         keep_idx = keep_indices(keep, evals)
         if verbose:
@@ -186,19 +195,45 @@ class DirectionalDerivativesComputation:
         if verbose:
             print(f"Group {gid}: Compute gammas and lambdas")
         gammas, lambdas = kernels.dirderiv_epilogue(
-            acc.V_t_V, acc.V_t_g_n, evecs, evals, C, N_ggn, N
+            acc.V_t_V, acc.V_t_g_n, evecs, evals, acc.C, acc.N_ggn, N
         )  # :302-325
-        return evals, evecs, gammas, lambdas, math.sqrt(corr2), C, N_ggn
+        return evals, evecs, gammas, lambdas
 
     @staticmethod
-    def _group_hook(hook, accumulation, group, batch_size, gammas, lambdas, verbose, warn_small_eigvals, dist):
+    def _directions(accumulation, group, N, verbose, warn_small_eigvals, dist):
+        """Eigendecompose the Gram matrix, filter, evaluate ``gamma`` and ``lambda``
+        (``directional_derivatives.py:281-325`` == ``directional_damped_newton.py:304-351``)."""
+        cls = DirectionalDerivativesComputation
+        acc, gram, corr2 = cls._gram_space(accumulation, N, dist)
+        if verbose:
+            print(f"Group {id(group)}: Eigen-decompose Gram matrix")
+        evals, evecs = kernels.syevj(gram, vectors=True)  # :291
+        evals, evecs, gammas, lambdas = cls._filter_and_evaluate(
+            acc, evals, evecs, group, N, verbose, warn_small_eigvals
+        )
+        return evals, evecs, gammas, lambdas, math.sqrt(corr2), acc.C, acc.N_ggn
+
+    @staticmethod
+    def _group_hook(
+        hook, accumulation, group, batch_size, gammas, lambdas, verbose, warn_small_eigvals, dist, queue=None
+    ):
         """Store ``gamma[n, k]`` and ``lambda[n, k]`` of the group (``directional_derivatives.py:255-325``)."""
+        cls = DirectionalDerivativesComputation
         gid = id(group)
         N = batch_size.pop(gid)
-        _, _, g, l, _, _, _ = DirectionalDerivativesComputation._directions(
-            accumulation, group, N, verbose, warn_small_eigvals, dist
-        )
-        gammas[gid], lambdas[gid] = g, l
+        if queue is None:
+            _, _, gammas[gid], lambdas[gid], _, _, _ = cls._directions(
+                accumulation, group, N, verbose, warn_small_eigvals, dist
+            )
+            return
+        acc, gram, _ = cls._gram_space(accumulation, N, dist)
+
+        def done(evals, evecs):
+            _, _, gammas[gid], lambdas[gid] = cls._filter_and_evaluate(
+                acc, evals, evecs, group, N, verbose, warn_small_eigvals
+            )
+
+        queue.submit(gram, done)
 
     @staticmethod
     def _check_param_groups(param_groups: List[Dict]) -> None:
