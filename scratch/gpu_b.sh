@@ -1,9 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_parity_gpu.py -q -k "solve_queue" 2>&1 | tail -5
-timeout 600 python bench.py --no-cpu-baseline > gpurun_out/b_c2.json 2> gpurun_out/b_c2.err; tail -3 gpurun_out/b_c2.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/b_c2.json').read().strip().splitlines()[-1])
-print('c2', d['ms_per_step'], d['e2e']['value'], d['gpu_launches'], d['sequential_solves'])
-print(d['eigensolver'])
-for k in d['kernels'][:6]: print(' ', k['kernel'], k['ms_per_step'])
-PY
+timeout 900 python -m pytest tests/test_kernels_gpu.py -q -x -k "wide or two_level or batched" 2>&1 | tail -12
+timeout 300 python scratch/eig_time.py 5120 10240 2>&1 | grep "^R="
+VVT_WIDE_FULL_GRAM=1 timeout 300 python scratch/eig_time.py 5120 2>&1 | grep "^R="

@@ -8,6 +8,7 @@ result scale), fp64 kernels 1e-10.
 """
 
 import math
+import os
 
 import pytest
 import torch
@@ -295,7 +296,10 @@ def test_wide_round_kernels(k, Np, rnd_idx):
         want = P.t() @ P
         scale = want.abs().max().item()
         # (the tensor core adds into its accumulator with truncation: a bias of about -3e-6 on sums of squares)
-        assert (H[pr].double() - want).abs().max().item() <= 1e-5 * scale, ("gram", pr)
+        # (VVT_WIDE_CROSS_GRAM=1: cross rounds form only the columns of b, H_ab and H_bb; H_aa comes from the
+        # solver's diagonal-block cache)
+        part = slice(64, None) if rnd_idx >= 0 and os.environ.get("VVT_WIDE_CROSS_GRAM") else slice(None)
+        assert (H[pr][:, part].double() - want[:, part]).abs().max().item() <= 1e-5 * scale, ("gram", pr)
         Pn = L[:, cols].double()
         if flag[pr].item() == 0:
             assert torch.equal(L[:, cols], L0[:, cols])

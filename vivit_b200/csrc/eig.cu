@@ -1386,7 +1386,8 @@ static JacobiLayout jacobi_layout(int64_t R, int64_t B, int64_t es, int dtype) {
   L.off_Jt = take(B * R * R * es);
   L.off_Tt = take(vmax<int64_t>(B * R * R * es, L.wide ? L.wp.part_bytes : 0));  // wide path: split-K partial Grams
   L.off_S = take(vmax<int64_t>(B * R * R * es, L.wide ? L.wp.q_bytes : 0));      // wide path: Q^T of every pair
-  L.off_M = take(vmax<int64_t>(B * R * R * es, L.wide ? L.wp.flag_bytes : 0));   // wide path: "rotated" flags
+  // wide path: "rotated" flags, then the diagonal-block cache
+  L.off_M = take(vmax<int64_t>(B * R * R * es, L.wide ? L.wp.flag_bytes + L.wp.diag_bytes : 0));
   L.off_Et = L.off_Y;  // Y is dead once J has been gathered (y_elems >= R * R)
   L.off_ev = take(B * R * es);
   L.off_cn = take(B * R * es);
@@ -1654,7 +1655,8 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
     if (L.wide) {
       if constexpr (sizeof(T) == 4) {
         for (int round = -1; round < L.wp.nbw - 1; ++round)
-          VVT_TRY(wide::wide_round((float*)Y, (float*)Tt, (float*)Sm, (int*)Mm, sc, L.wp, maps, round, B, s));
+          VVT_TRY(wide::wide_round((float*)Y, (float*)Tt, (float*)Sm, (int*)Mm, (float*)((char*)Mm + L.wp.flag_bytes), sc,
+                                   L.wp, maps, round, B, s));
       }
     } else if (persistent) {
       VVT_TRY(launch_sweep<T>(Y, Np, nb, CL, rows_per_cta, parts, sc, marks, sweep * nb + 1, (T*)(ws + L.off_dc),
@@ -1691,6 +1693,13 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
               "[vvt_syevj] R=%lld batch=%lld %s CL=%d sweep %d: %d of %lld block pairs rotated (problem 0), +%.0f us\n",
               (long long)R, (long long)B, L.wide ? "wide" : "16-wide", CL, sweep + 1, slot[2],
               (long long)((nb16 / 2) * nb16), us);
+      if (L.wide) {
+        long long w[9];
+        if (cudaMemcpyFromSymbol(w, wide::g_wdbg, sizeof(w)) == cudaSuccess)
+          fprintf(stderr, "[vvt_syevj]   rotation kernel, CTA 0, last launch (cycles): sum partials %lld | rotations %lld | "
+                  "cluster barrier %lld | Q_sub exchange %lld | columns %lld | rows %lld | cluster barrier %lld | re-pair %lld | "
+                  "store %lld\n", w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8]);
+      }
     }
     return all;
   };
@@ -1808,16 +1817,21 @@ int vvt_dbg_wide_round(float* L, float* H_out, float* Qt_out, int* flag_out, int
   const wide::WidePlan p = wide::wide_plan(Np, 1);
   char* scratch = nullptr;
   const size_t l_bytes = size_t(Np) * Np * 4;
-  VVT_TRY(check_cuda(cudaMalloc(&scratch, size_t(p.part_bytes + 256) + l_bytes), __func__));
+  VVT_TRY(check_cuda(cudaMalloc(&scratch, size_t(p.part_bytes + 256 + p.diag_bytes) + l_bytes), __func__));
   float* part = (float*)scratch;
   JacobiScalars* sc = (JacobiScalars*)(scratch + p.part_bytes);
-  float* Lw = (float*)(scratch + p.part_bytes + 256);  // the solver's wide-block-major layout
+  float* diag = (float*)(scratch + p.part_bytes + 256);
+  float* Lw = (float*)(scratch + p.part_bytes + 256 + p.diag_bytes);  // the solver's wide-block-major layout
   const int blocks = int(vmin<int64_t>(ceil_div(int64_t(Np) * Np, 256), 8 * num_sms()));
   int st = check_cuda(cudaMemsetAsync(sc, 0, sizeof(JacobiScalars), s), __func__);
+  // (a cross round writes only the columns of b of every pair Gram: the rest of H_out reads as zero)
+  if (st == VVT_OK) st = check_cuda(cudaMemsetAsync(part, 0, size_t(p.part_bytes), s), __func__);
   wide::wide_relayout_kernel<<<blocks, 256, 0, s>>>(Lw, L, int(Np), 1);
+  // the diagonal-block cache a cross round expects (in the solver the intra round of the sweep has filled it)
+  wide::wide_diag_kernel<<<p.nbw, 256, 0, s>>>(diag, Lw, int(Np));
   wide::WideMaps maps;
   if (st == VVT_OK) st = wide::wide_make_maps(&maps, Lw, Qt_out, p, 1);
-  if (st == VVT_OK) st = wide::wide_round(Lw, part, Qt_out, flag_out, sc, p, maps, round, 1, s);
+  if (st == VVT_OK) st = wide::wide_round(Lw, part, Qt_out, flag_out, diag, sc, p, maps, round, 1, s);
   if (st == VVT_OK) {
     for (int k = 0; k < p.splits && st == VVT_OK; ++k)
       st = vvt_axpy(H_out, part + size_t(k) * p.pairs * wide::WP * wide::WP, int64_t(p.pairs) * wide::WP * wide::WP, 1.0,

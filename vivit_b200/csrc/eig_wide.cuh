@@ -55,6 +55,7 @@ struct WideArgs {
   int64_t l_stride;         // elements between the factors of two problems
   int Np, nbw, round, pairs, splits, kblocks_total, kblocks_per_split;
   int variant;  // experiments (VVT_WIDE_DESC): descriptor encodings of the MN-major Gram operands
+  int cross_only;  // GRAM, cross rounds: only the 128 x 64 block H[:, b] (the diagonal block of a comes from a cache)
 };
 
 // MN-major fp32 (tf32) operands have ONE legal shared-memory layout on sm_100: 128-byte swizzle with 32-byte
@@ -77,6 +78,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, int variant
 }
 constexpr uint32_t kIdescMN = tc::kIdesc | (1u << 15) | (1u << 16);  // A and B MN-major
 constexpr uint32_t kIdescBMN = tc::kIdesc | (1u << 16);               // A from tensor memory, B MN-major
+constexpr uint32_t kIdescBMN64 = (kIdescBMN & ~(0x3Fu << 17)) | (uint32_t(WB >> 3) << 17);  // the same with N = 64
 
 template <int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1)
@@ -92,6 +94,11 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
   int wa, wb;
   wide_blocks(a.nbw, a.round, pair, wa, wb);
   constexpr bool diag = MODE == GRAM;  // one operand tile serves as A and B
+  // Cross rounds need only H[:, b] = P^T P_b (H_ab and H_bb): H_aa is kept up to date by the rotation kernel (the
+  // diagonal-block cache, as in the 16-wide path) and H_ba = H_ab^T.  N = 64 instead of 128: half the MMA time and
+  // half the shared-memory operand traffic; the operand loads from global memory stay (A = the whole panel).
+  const bool cross = MODE == GRAM && a.cross_only != 0 && a.round >= 0;
+  const int bn = cross ? WB : BN;
   const int kb0 = MODE == GRAM ? split * a.kblocks_per_split : 0;
   const int nkb = MODE == GRAM ? min(a.kblocks_total, kb0 + a.kblocks_per_split) - kb0 : WP / BK;
 
@@ -159,11 +166,13 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
     // ===== MMA issuer, GRAM: A from tensor memory, B = the MN-major panel tile (raw / lo) in shared memory =====
     if (lane == 0) {
       const int vr = a.variant;
+      const uint32_t idesc = cross ? kIdescBMN64 : kIdescBMN;
+      const uint32_t b_off = cross ? 2u * 4096u : 0u;  // the two 32-column chunks of b
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES, use = i / STAGES;
         const int grp = i / PROMOTE, first = (i % PROMOTE) == 0;
         const uint32_t acc = tmem_base + uint32_t((grp & 1) * BN);
-        const uint32_t b_hi = base + s * STAGE_BYTES, b_lo = b_hi + 2 * TILE_BYTES;
+        const uint32_t b_hi = base + s * STAGE_BYTES + b_off, b_lo = b_hi + 2 * TILE_BYTES;
         if (first && grp >= 2) {
           mbar_wait(bar_acc_empty(grp & 1), ((grp >> 1) - 1) & 1);
           tcgen05_fence_after();
@@ -173,9 +182,9 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {  // one MMA (K = 8) = two 4-row groups of B, next k-step 1 KB further
           const uint32_t a_hi = a_cols(s) + 8 * k, a_lo = a_hi + 32;
-          umma_tf32_ts(acc, a_hi, make_desc_mn(b_hi + 1024 * k, vr), kIdescBMN, !(first && k == 0));
-          umma_tf32_ts(acc, a_hi, make_desc_mn(b_lo + 1024 * k, vr), kIdescBMN, 1);
-          umma_tf32_ts(acc, a_lo, make_desc_mn(b_hi + 1024 * k, vr), kIdescBMN, 1);
+          umma_tf32_ts(acc, a_hi, make_desc_mn(b_hi + 1024 * k, vr), idesc, !(first && k == 0));
+          umma_tf32_ts(acc, a_hi, make_desc_mn(b_lo + 1024 * k, vr), idesc, 1);
+          umma_tf32_ts(acc, a_lo, make_desc_mn(b_hi + 1024 * k, vr), idesc, 1);
         }
         umma_commit(bar_empty(s));
         if ((i % PROMOTE) == PROMOTE - 1 || i == nkb - 1) umma_commit(bar_acc_full(grp & 1));
@@ -233,10 +242,12 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
       tcgen05_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t((grp & 1) * BN + c0), r);
+        if (c0 < bn) {  // uniform
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t((grp & 1) * BN + c0), r);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) total[c0 + j] += __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) total[c0 + j] += __uint_as_float(r[j]);
+        }
       }
       tcgen05_fence_before();
       mbar_arrive(bar_acc_empty(grp & 1));
@@ -265,7 +276,7 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
         tmem_st_wait();
       }
 #pragma unroll 4
-      for (int v = ct; v < n_vec; v += 128) {
+      for (int v = (cross ? n_vec / 2 : 0) + ct; v < n_vec; v += 128) {  // (cross: only the chunks of b are a B operand)
         const float4 x = *reinterpret_cast<const float4*>(stage + size_t(v) * 16);
         const float e[4] = {x.x, x.y, x.z, x.w};
         float o[4];
@@ -291,9 +302,15 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
     const int cw = warp - 2;  // 0..3: this warp stores rows cw, cw + 4, ...; lanes = consecutive columns
     if (MODE == GRAM) {
       float* out = a.out + ((size_t(prob) * a.splits + split) * a.pairs + pair) * size_t(WP * WP);
-      for (int r = cw; r < BM; r += 4)
+      if (cross) {  // columns 64 .. 127 of the pair Gram
+        for (int r = cw; r < BM; r += 4)
 #pragma unroll
-        for (int q = 0; q < BN / 32; ++q) out[r * WP + lane + 32 * q] = tile[r * (BN + 1) + lane + 32 * q];
+          for (int q = 0; q < WB / 32; ++q) out[r * WP + WB + lane + 32 * q] = tile[r * (BN + 1) + lane + 32 * q];
+      } else {
+        for (int r = cw; r < BM; r += 4)
+#pragma unroll
+          for (int q = 0; q < BN / 32; ++q) out[r * WP + lane + 32 * q] = tile[r * (BN + 1) + lane + 32 * q];
+      }
     } else {
       for (int r = cw; r < BM; r += 4)
 #pragma unroll
@@ -842,19 +859,38 @@ __device__ __forceinline__ void holder_of(bool intra_round, int ir, int x, int& 
   }
 }
 
+__device__ long long g_wdbg[16];
+
 __global__ void __launch_bounds__(OT, 2)
 wide_rot_cluster_kernel(float* Qt, int* flag, const float* part, int nbw, int round, int pairs, int splits,
-                        JacobiScalars* sc) {
+                        JacobiScalars* sc, float* diag, int cross_only) {
   extern __shared__ __align__(16) unsigned char wide_smem[];
   RotCta& sm = *reinterpret_cast<RotCta*>(wide_smem);
   cg::cluster_group cluster = cg::this_cluster();
   const int g = int(cluster.block_rank()), pair = blockIdx.x / CR, prob = blockIdx.y, tid = threadIdx.x;
   sc += prob;
   if (*reinterpret_cast<const volatile int*>(&sc->converged)) return;  // uniform over the cluster
-  (void)nbw;
   const bool intra_round = round < 0;
+  // Diagonal-block cache (cross_only): diag[problem][wide block][64][64] holds P_w^T P_w of every wide block, written
+  // here after every rotation (the diagonal blocks of Q^T H Q) and recomputed from the factor by the intra round of
+  // every sweep.  In cross rounds the Gram kernel then forms only H[:, b]; H_aa comes from the cache, H_ba = H_ab^T.
+  const bool cached = cross_only != 0 && !intra_round;
+  int wa, wb;
+  wide_blocks(nbw, round, pair, wa, wb);
+  float* const diag_a = diag + (size_t(prob) * nbw + wa) * size_t(WB * WB);
+  float* const diag_b = diag + (size_t(prob) * nbw + wb) * size_t(WB * WB);
   const float tol2 = Eps<float>::tol * Eps<float>::tol, abs2 = Eps<float>::v * Eps<float>::v;
   const int warp = tid >> 5, lane = tid & 31;
+  // VVT_SYEVJ_DEBUG: cycles of CTA 0 per phase, summed over the inner rounds (g_wdbg, read by the host)
+  const bool stamp = blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+  long long t_last = stamp ? clock64() : 0, t_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  auto lap = [&](int i) {
+    if (stamp) {
+      const long long now = clock64();
+      t_acc[i] += now - t_last;
+      t_last = now;
+    }
+  };
 
   // ---- my rows of H (sum of the split-K partial sums in a fixed order, symmetrised), my rows of Q = I
   {
@@ -866,21 +902,93 @@ wide_rot_cluster_kernel(float* Qt, int* flag, const float* part, int nbw, int ro
     // (rows only, coalesced: the tensor core forms both triangles of P^T P from the same operands, they differ in
     // the last bits at most -- the order of the hi*lo / lo*hi terms -- and the rotation angles do not care;
     // reading the mirrored entries as well, column-wise, cost 18 % of this kernel)
-    for (int idx = tid; idx < OP * WP / 4; idx += OT) {
-      const int i = (idx * 4) / WP, c = (idx * 4) % WP;
-      const int r = panel_index(sa, sb, i);
-      float4 a = *reinterpret_cast<const float4*>(p0 + size_t(r) * WP + c);
-      for (int k = 1; k < splits; ++k) {
-        const float4 v = *reinterpret_cast<const float4*>(p0 + k * split_stride + size_t(r) * WP + c);
-        a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
-      }
-      sm.Hrows[0][i][c] = a.x, sm.Hrows[0][i][c + 1] = a.y, sm.Hrows[0][i][c + 2] = a.z, sm.Hrows[0][i][c + 3] = a.w;
+    if (!cached) {
+      // (a thread's four vectors of one split are loaded before any of them is added: one L2 round trip per split
+      // instead of four)
+      constexpr int NV = OP * WP / 4 / OT;  // 4
+      float4 acc4[NV];
+      size_t off[NV];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) sm.Qown[i][c + e] = (32 * g + i == c + e) ? 1.f : 0.f;
+      for (int j = 0; j < NV; ++j) {
+        const int idx = tid + j * OT;
+        off[j] = size_t(panel_index(sa, sb, (idx * 4) / WP)) * WP + (idx * 4) % WP;
+        acc4[j] = *reinterpret_cast<const float4*>(p0 + off[j]);
+      }
+      for (int k = 1; k < splits; ++k) {
+        float4 v[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = *reinterpret_cast<const float4*>(p0 + k * split_stride + off[j]);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) acc4[j].x += v[j].x, acc4[j].y += v[j].y, acc4[j].z += v[j].z, acc4[j].w += v[j].w;
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int idx = tid + j * OT;
+        const int i = (idx * 4) / WP, c = (idx * 4) % WP;
+        const float4 a = acc4[j];
+        sm.Hrows[0][i][c] = a.x, sm.Hrows[0][i][c + 1] = a.y, sm.Hrows[0][i][c + 2] = a.z, sm.Hrows[0][i][c + 3] = a.w;
+      }
+    } else {
+      // cross round (sa in a, sb in b): columns of b for all 32 rows from the partial sums (two vectors per thread);
+      // columns of a: my 16 rows of a from the cache, my 16 rows of b as the transposed entries H[c][r] of H_ab
+      float4 right[2], left;
+      size_t off_r[2], off_l;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int idx = tid + j * OT;  // 32 rows x 16 vectors
+        off_r[j] = size_t(panel_index(sa, sb, idx / 16)) * WP + WB + (idx % 16) * 4;
+        right[j] = *reinterpret_cast<const float4*>(p0 + off_r[j]);
+      }
+      // threads 0 .. 127: 16 rows x 8 pieces (8 floats) of the cache; threads 128 .. 255: 64 columns x 2 pieces of H_ab
+      const bool from_cache = tid < OT / 2;
+      const int t2 = tid - OT / 2;
+      off_l = from_cache ? size_t((sa * OB + tid / 8) * WB + (tid % 8) * 8)
+                         : size_t(t2 / 2) * WP + size_t(sb * OB + (t2 % 2) * 8);
+      float4 left2;
+      if (from_cache) {
+        left = *reinterpret_cast<const float4*>(diag_a + off_l);
+        left2 = *reinterpret_cast<const float4*>(diag_a + off_l + 4);
+      } else {
+        left = *reinterpret_cast<const float4*>(p0 + off_l);
+        left2 = *reinterpret_cast<const float4*>(p0 + off_l + 4);
+      }
+      for (int k = 1; k < splits; ++k) {
+        float4 v[2], w = make_float4(0.f, 0.f, 0.f, 0.f), w2 = w;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) v[j] = *reinterpret_cast<const float4*>(p0 + k * split_stride + off_r[j]);
+        if (!from_cache) {
+          w = *reinterpret_cast<const float4*>(p0 + k * split_stride + off_l);
+          w2 = *reinterpret_cast<const float4*>(p0 + k * split_stride + off_l + 4);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) right[j].x += v[j].x, right[j].y += v[j].y, right[j].z += v[j].z, right[j].w += v[j].w;
+        left.x += w.x, left.y += w.y, left.z += w.z, left.w += w.w;
+        left2.x += w2.x, left2.y += w2.y, left2.z += w2.z, left2.w += w2.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int idx = tid + j * OT;
+        const int i = idx / 16, c = WB + (idx % 16) * 4;
+        sm.Hrows[0][i][c] = right[j].x, sm.Hrows[0][i][c + 1] = right[j].y;
+        sm.Hrows[0][i][c + 2] = right[j].z, sm.Hrows[0][i][c + 3] = right[j].w;
+      }
+      if (from_cache) {
+        const int i = tid / 8, c = (tid % 8) * 8;
+        sm.Hrows[0][i][c] = left.x, sm.Hrows[0][i][c + 1] = left.y, sm.Hrows[0][i][c + 2] = left.z, sm.Hrows[0][i][c + 3] = left.w;
+        sm.Hrows[0][i][c + 4] = left2.x, sm.Hrows[0][i][c + 5] = left2.y;
+        sm.Hrows[0][i][c + 6] = left2.z, sm.Hrows[0][i][c + 7] = left2.w;
+      } else {  // column c of a, eight of my rows of b
+        const int c = t2 / 2, i0 = OB + (t2 % 2) * 8;
+        sm.Hrows[0][i0][c] = left.x, sm.Hrows[0][i0 + 1][c] = left.y, sm.Hrows[0][i0 + 2][c] = left.z, sm.Hrows[0][i0 + 3][c] = left.w;
+        sm.Hrows[0][i0 + 4][c] = left2.x, sm.Hrows[0][i0 + 5][c] = left2.y;
+        sm.Hrows[0][i0 + 6][c] = left2.z, sm.Hrows[0][i0 + 7][c] = left2.w;
+      }
     }
+    for (int idx = tid; idx < OP * WP; idx += OT) sm.Qown[idx / WP][idx % WP] = (32 * g + idx / WP == idx % WP) ? 1.f : 0.f;
   }
   int any = 0, cur = 0;
   __syncthreads();
+  lap(0);
 
   for (int ir = 0; ir < 4; ++ir, cur ^= 1) {
     int sa, sb;
@@ -907,15 +1015,35 @@ wide_rot_cluster_kernel(float* Qt, int* flag, const float* part, int nbw, int ro
       if (rotate) atomicAdd(&sc->rotations, 1ull);
     }
     // ---- the four Q_sub of the round, through distributed shared memory
+    lap(1);
     cluster_arrive();
     cluster_wait();
-    for (int u = 0; u < CR; ++u) {
-      const RotCta* remote = cluster.map_shared_rank(&sm, u);
-      for (int idx = tid; idx < OP * LDQ / 4; idx += OT)
-        reinterpret_cast<float4*>(&sm.Qsubs[u][0][0])[idx] = reinterpret_cast<const float4*>(&remote->rs.Q[0][0])[idx];
-      if (tid == 0) sm.rot[u] = remote->my_rot;
+    lap(2);
+    {
+      // (every remote read is issued before the first local write: the compiler cannot prove that the two do not
+      // alias and would otherwise wait out one distributed-shared-memory round trip per vector)
+      constexpr int QV = OP * LDQ / 4;             // float4 per Q_sub (288)
+      constexpr int QN = (CR * QV + OT - 1) / OT;  // per thread (5)
+      float4 v[QN];
+#pragma unroll
+      for (int j = 0; j < QN; ++j) {
+        const int idx = tid + j * OT;
+        if (idx < CR * QV) {
+          const RotCta* remote = cluster.map_shared_rank(&sm, idx / QV);
+          v[j] = reinterpret_cast<const float4*>(&remote->rs.Q[0][0])[idx % QV];
+        }
+      }
+      int rflag = 0;
+      if (tid < CR) rflag = cluster.map_shared_rank(&sm, tid)->my_rot;
+#pragma unroll
+      for (int j = 0; j < QN; ++j) {
+        const int idx = tid + j * OT;
+        if (idx < CR * QV) reinterpret_cast<float4*>(&sm.Qsubs[idx / QV][0][0])[idx % QV] = v[j];
+      }
+      if (tid < CR) sm.rot[tid] = rflag;
     }
     __syncthreads();
+    lap(3);
 #pragma unroll
     for (int u = 0; u < CR; ++u) any |= sm.rot[u];
     // ---- columns: X[:, cols(u)] <- X[:, cols(u)] Q_sub(u) for my rows of H and of Q.  A warp owns one
@@ -962,6 +1090,7 @@ wide_rot_cluster_kernel(float* Qt, int* flag, const float* part, int nbw, int ro
       }
     }
     __syncthreads();
+    lap(4);
     // ---- rows: H[my rows, :] <- Q_sub(g)^T H[my rows, :]; a thread owns 4 rows x 4 columns
     {
       const bool on = sm.rot[g] != 0;
@@ -996,23 +1125,51 @@ wide_rot_cluster_kernel(float* Qt, int* flag, const float* part, int nbw, int ro
       }
     }
     // ---- re-pair: fetch the rows of my next sub-pair from the CTAs that hold them
+    lap(5);
     cluster_arrive();
     cluster_wait();
+    lap(6);
     if (ir < 3) {
       int na, nb_;
       bool dummy;
       sub_pair(intra_round, ir + 1, g, na, nb_, dummy);
+      constexpr int RN = OB * WP / OT;  // 8 elements per thread and sub-block
+      float v[2][RN];
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
+      for (int hh = 0; hh < 2; ++hh) {  // all remote reads first (see the Q_sub exchange)
         int h, half;
         holder_of(intra_round, ir, hh ? nb_ : na, h, half);
         const RotCta* remote = cluster.map_shared_rank(&sm, h);
-        for (int idx = tid; idx < OB * WP; idx += OT) {
-          const int i = idx / WP, c = idx % WP;
-          sm.Hrows[cur ^ 1][OB * hh + i][c] = remote->Hrows[cur][OB * half + i][c];
+#pragma unroll
+        for (int j = 0; j < RN; ++j) {
+          const int idx = tid + j * OT;
+          v[hh][j] = remote->Hrows[cur][OB * half + idx / WP][idx % WP];
         }
       }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) {
+          const int idx = tid + j * OT;
+          sm.Hrows[cur ^ 1][OB * hh + idx / WP][idx % WP] = v[hh][j];
+        }
       __syncthreads();
+    }
+    lap(7);
+  }
+  // ---- diagonal-block cache: the rows I hold at the end (sub-pair of the last inner round) are final rows of
+  //      Q^T H Q; their entries inside their own wide block are P_w^T P_w after the apply.  (Nothing rotated and no
+  //      fresh Gram: the cache is still right.)
+  if (cross_only != 0 && (any || intra_round)) {
+    int sa, sb;
+    bool dummy;
+    sub_pair(intra_round, 3, g, sa, sb, dummy);
+    const float(*H)[LDW] = sm.Hrows[cur ^ 1];  // the buffer of inner round 3
+    for (int idx = tid; idx < OP * WB; idx += OT) {
+      const int i = idx / WB, c = idx % WB;
+      const int r = panel_index(sa, sb, i);  // panel row: wide block r / 64, local row r % 64
+      float* dst = r < WB ? diag_a : diag_b;
+      dst[(r % WB) * WB + c] = H[i][(r / WB) * WB + c];
     }
   }
   // ---- Q^T of my rows to global memory (rows of Q^T = output columns n; my slice is k = 32 g ..)
@@ -1024,6 +1181,9 @@ wide_rot_cluster_kernel(float* Qt, int* flag, const float* part, int nbw, int ro
       dst[size_t(n) * WP + 32 * g + i] = sm.Qown[i][n];
     }
   }
+  lap(8);
+  if (stamp)
+    for (int i = 0; i < 9; ++i) g_wdbg[i] = t_acc[i];
   // nobody may exit while a neighbour can still read its shared memory: the last remote reads (Q_sub of the
   // fourth inner round) precede the cluster barrier that follows them
 }
@@ -1113,10 +1273,30 @@ __global__ void __launch_bounds__(256) wide_gather_kernel(float* Jm, float* Jt, 
   }
 }
 
+// diag[w] = P_w^T P_w of every wide block, plain FFMA (test hook only: the solver's intra rounds fill the cache)
+__global__ void __launch_bounds__(256) wide_diag_kernel(float* diag, const float* Lw, int Np) {
+  const int w = blockIdx.x, i0 = (threadIdx.x / 16) * 4, j0 = (threadIdx.x % 16) * 4;
+  const float* P = Lw + size_t(w) * Np * WB;
+  float acc[4][4] = {};
+  for (int r = 0; r < Np; ++r) {
+    const float4 a = *reinterpret_cast<const float4*>(P + size_t(r) * WB + i0);
+    const float4 b = *reinterpret_cast<const float4*>(P + size_t(r) * WB + j0);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) diag[(size_t(w) * WB + i0 + i) * WB + j0 + j] = acc[i][j];
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 struct WidePlan {
   int Np, nbw, pairs, splits, kblocks, kblocks_per_split;
-  int64_t part_bytes, q_bytes, flag_bytes;
+  int64_t part_bytes, q_bytes, flag_bytes, diag_bytes;  // diag: the diagonal-block cache, behind the flags
 };
 
 static inline WidePlan wide_plan(int64_t R, int64_t batch) {
@@ -1142,6 +1322,7 @@ static inline WidePlan wide_plan(int64_t R, int64_t batch) {
   p.part_bytes = align_up(batch * p.splits * p.pairs * int64_t(WP * WP) * 4, 256);
   p.q_bytes = align_up(batch * p.pairs * int64_t(WP * WP) * 4, 256);
   p.flag_bytes = align_up(batch * p.pairs * 4, 256);
+  p.diag_bytes = align_up(batch * p.nbw * int64_t(WB * WB) * 4, 256);
   return p;
 }
 
@@ -1175,7 +1356,7 @@ static inline int wide_make_maps(WideMaps* m, const float* Lw, const float* Qt, 
 }
 
 // one round (all pairs, all problems): Gram, rotations, apply
-static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, JacobiScalars* sc, const WidePlan& p,
+static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, float* diag, JacobiScalars* sc, const WidePlan& p,
                              const WideMaps& m, int round, int64_t batch, cudaStream_t s) {
   static SmemOptIn opt_g, opt_a, opt_r;
   VVT_TRY(opt_g.ensure(wide_tc_kernel<GRAM>, tc::SMEM_BYTES, "vvt_syevj(wide gram)"));
@@ -1189,10 +1370,16 @@ static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, Jacob
   a.kblocks_total = p.kblocks, a.kblocks_per_split = p.kblocks_per_split;
   a.variant = getenv("VVT_WIDE_DESC") ? atoi(getenv("VVT_WIDE_DESC")) : 0;
   a.out = part;
+  static const bool one_cta = getenv("VVT_WIDE_ROT_ONE_CTA") != nullptr;  // experiments: the single-CTA kernel
+  // VVT_WIDE_CROSS_GRAM=1: cross rounds form only H[:, b] (N = 64) and take H_aa from the diagonal-block cache.
+  // Measured: the Gram kernel is bound by its converter warps and the operand loads, not by the MMAs -- 2.5 % per
+  // sweep at R = 5120, 6 % at R = 10240, and one sweep more on both (24 / 27 instead of 23 / 26) -- so it is off.
+  static const bool cross_gram = getenv("VVT_WIDE_CROSS_GRAM") != nullptr;
+  const int cross_only = !one_cta && cross_gram;
+  a.cross_only = cross_only;
   wide_tc_kernel<GRAM><<<dim3(unsigned(p.pairs), unsigned(p.splits), unsigned(batch)), tc::THREADS, tc::SMEM_BYTES, s>>>(
       m.gram, m.q, a);
   VVT_TRY(launched("vvt_syevj(wide gram)"));
-  static const bool one_cta = getenv("VVT_WIDE_ROT_ONE_CTA") != nullptr;  // experiments: the single-CTA kernel
   if (one_cta) {
     wide_rot_kernel<<<dim3(unsigned(p.pairs), unsigned(batch)), RT, sizeof(WideRotSmem), s>>>(Qt, flag, part, p.nbw, round,
                                                                                               p.pairs, p.splits, sc);
@@ -1212,7 +1399,8 @@ static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, Jacob
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, wide_rot_cluster_kernel, Qt, flag, part, p.nbw, round, p.pairs, p.splits, sc),
+    VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, wide_rot_cluster_kernel, Qt, flag, part, p.nbw, round, p.pairs, p.splits, sc,
+                                          diag, cross_only),
                        "vvt_syevj(wide rot)"));
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
