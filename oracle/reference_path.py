@@ -294,9 +294,10 @@ def jac_t_mat_prod(
         left, right, top, bottom = module.padding
         h, w = mat.shape[-2:]
         return mat[..., top : h - bottom, left : w - right]
-    if isinstance(module, (nn.Conv1d, nn.MaxPool1d, nn.AvgPool1d)):
-        # [external] Conv1DDerivatives / MaxPool1DDerivatives / AvgPool1DDerivatives: transposed Jacobian of
-        # the layer at its forward input, by autograd of the layer itself on the V*N "virtual batch"
+    if isinstance(module, (nn.Conv1d, nn.MaxPool1d, nn.AvgPool1d, nn.Conv3d, *_CONV_TRANSPOSE)):
+        # [external] Conv1D/3DDerivatives / ConvTransposeNDDerivatives / MaxPool1DDerivatives /
+        # AvgPool1DDerivatives: transposed Jacobian of the layer at its forward input, by autograd of the layer
+        # itself on the V*N "virtual batch"
         x = inp.repeat(v, *([1] * (inp.dim() - 1))).detach().clone().requires_grad_(True)
         with torch.enable_grad():
             y = module(x)
@@ -341,18 +342,19 @@ def param_mjp(
         )  # [N, J, X]
         vt = einsum("vnox,njx->vnoj", mat.reshape(v, n, co, -1), cols)
         return vt.reshape(v, n, *module.weight.shape)
-    if isinstance(module, nn.Conv1d):
-        # [external] Conv1DDerivatives.param_mjp: the layer is linear in its parameters, so the product is
-        # the gradient of <mat[v, n], layer(x_n)> -- one autograd call per (v, n), fine at oracle sizes
+    if isinstance(module, (nn.Conv1d, nn.Conv3d, *_CONV_TRANSPOSE)):
+        # [external] Conv1D/3DDerivatives.param_mjp, ConvTransposeNDDerivatives.param_mjp: the layer is linear in
+        # its parameters, so the product is the gradient of <mat[v, n], layer(x_n)> -- one autograd call per
+        # (v, n), fine at oracle sizes
         if name == "bias":
-            return mat.sum(3)
+            return mat.sum(tuple(range(3, mat.dim())))
         v, n = mat.shape[:2]
         rows = []
         for vi in range(v):
             for ni in range(n):
                 w = module.weight.detach().clone().requires_grad_(True)
                 with torch.enable_grad():
-                    y = F.conv1d(inp[ni : ni + 1], w, None, module.stride, module.padding, module.dilation, module.groups)
+                    y = torch.func.functional_call(module, {"weight": w}, (inp[ni : ni + 1],))
                     (g,) = torch.autograd.grad(y, w, mat[vi, ni][None])
                 rows.append(g)
         return torch.stack(rows).reshape(v, n, *module.weight.shape)
@@ -370,6 +372,7 @@ def param_mjp(
 
 
 _BATCHNORM = (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)
+_CONV_TRANSPOSE = (nn.ConvTranspose1d, nn.ConvTranspose2d, nn.ConvTranspose3d)
 
 
 def _bn_require_eval(module: nn.Module) -> None:

@@ -216,6 +216,59 @@ PROBLEMS: List[Problem] = [
     ),
 ]
 
+# Conv3d and transposed convolutions (module map ``secondorder/vivit/__init__.py:84-101``; no reference fixture
+# contains one): ``name -> (model, input shape)``, three classes
+def _conv3d_net():
+    return nn.Sequential(
+        nn.Conv3d(2, 3, (2, 3, 2), stride=(1, 2, 1), padding=(1, 1, 0)),
+        nn.Tanh(),
+        nn.Conv3d(3, 2, 2, dilation=(2, 1, 1), bias=False),
+        nn.Sigmoid(),
+        nn.Flatten(),
+        nn.Linear(36, 3),
+    ), (3, 2, 4, 6, 5)
+
+
+def _conv_transpose2d_net():
+    return nn.Sequential(
+        nn.Conv2d(2, 3, 3, stride=2),
+        nn.ReLU(),
+        nn.ConvTranspose2d(3, 2, 3, stride=2, padding=1, output_padding=1),
+        nn.Tanh(),
+        nn.ConvTranspose2d(2, 2, (2, 3), dilation=(2, 1), bias=False),
+        nn.Sigmoid(),
+        nn.Flatten(),
+        nn.Linear(2 * 8 * 8, 3),
+    ), (3, 2, 7, 7)
+
+
+def _conv_transpose1d_net():
+    return nn.Sequential(
+        nn.ConvTranspose1d(2, 3, 3, stride=2, padding=2),
+        nn.Tanh(),
+        nn.ConvTranspose1d(3, 2, 2, stride=3, output_padding=2, bias=False),
+        nn.Flatten(),
+        nn.Linear(2 * 22, 3),
+    ), (4, 2, 5)
+
+
+def _conv_transpose3d_net():
+    return nn.Sequential(
+        nn.ConvTranspose3d(2, 2, (2, 3, 2), stride=(2, 1, 2), padding=(0, 1, 1)),
+        nn.Sigmoid(),
+        nn.Conv3d(2, 2, 2, stride=2),
+        nn.Flatten(),
+        nn.Linear(2 * 2 * 1 * 1, 3),
+    ), (3, 2, 2, 3, 2)
+
+
+ND_NETS = {
+    "conv3d": _conv3d_net,
+    "conv-transpose2d": _conv_transpose2d_net,
+    "conv-transpose1d": _conv_transpose1d_net,
+    "conv-transpose3d": _conv_transpose3d_net,
+}
+
 # test/settings.py:36-41 -- only used at the extension level (the Computations
 # require reduction='mean', see eigh.py:33-34)
 PROBLEM_SUM = Problem(

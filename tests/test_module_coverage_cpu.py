@@ -5,6 +5,7 @@ import torch
 from torch import nn
 
 import tests._torch_kernels as double
+from tests.problems import ND_NETS
 from tests.test_host_cpu import run_backward
 
 
@@ -193,3 +194,57 @@ def test_one_dimensional_layers_oracle_and_computation_agree():
         run_backward(model, nn.CrossEntropyLoss(), x, y, [comp.get_extension()], comp.get_extension_hook(groups))
         (want,) = ref.eigvalsh(model, nn.CrossEntropyLoss(), x, y, groups, subsampling=sub)
         assert torch.allclose(comp.get_result(groups[0]), want, rtol=1e-8, atol=1e-11)
+
+
+@pytest.mark.parametrize("name", sorted(ND_NETS))
+def test_conv3d_and_transposed_convolutions(name):
+    """``Conv3d`` / ``ConvTranspose1d/2d/3d`` (module map ``secondorder/vivit/__init__.py:84-101``) are composed from
+    the 2-d kernels (``backprop/conv_nd.py``): factors and per-sample gradients against autograd, eigenvalues
+    through ``EigvalshComputation`` against the oracle restatement (with and without sub-sampling)."""
+    from oracle import reference_path as ref
+    from oracle.autograd_ggn import AutogradGGN
+    from vivit_b200 import BatchGrad, EigvalshComputation
+
+    torch.manual_seed(8)
+    model, in_shape = ND_NETS[name]()
+    model = model.double()
+    x, y = torch.rand(*in_shape, dtype=torch.float64), torch.randint(0, 3, (in_shape[0],))
+    assert model(x).shape == (in_shape[0], 3)
+    _sqrt_ggn_matches_autograd(model, nn.CrossEntropyLoss(), x, y)
+    run_backward(model, nn.CrossEntropyLoss(), x, y, [BatchGrad()], None)
+    got = torch.cat([p.grad_batch.flatten(1) for p in model.parameters()], 1)
+    assert torch.allclose(got, AutogradGGN(model, nn.CrossEntropyLoss(), x, y).batch_grad(), rtol=1e-10, atol=1e-13)
+    for sub in (None, [2, 0]):
+        groups = [{"params": list(model.parameters())}]
+        comp = EigvalshComputation(subsampling=sub)
+        run_backward(model, nn.CrossEntropyLoss(), x, y, [comp.get_extension()], comp.get_extension_hook(groups))
+        (want,) = ref.eigvalsh(model, nn.CrossEntropyLoss(), x, y, groups, subsampling=sub)
+        assert torch.allclose(comp.get_result(groups[0]), want, rtol=1e-8, atol=1e-11)
+
+
+@pytest.mark.parametrize("name", sorted(ND_NETS))
+def test_conv3d_and_transposed_convolutions_sharded(name):
+    """Parameter sharding (``process_group=``) of these layers: a rank owns a dim-0 slice of every parameter --
+    output channels of a ``Conv3d`` weight, INPUT channels of a transposed-convolution weight -- and the slices
+    of two ranks put together are the unsharded factor and per-sample gradients."""
+    from vivit_b200 import BatchGrad, SqrtGGNExact
+
+    torch.manual_seed(9)
+    model, in_shape = ND_NETS[name]()
+    model = model.double()
+    x, y = torch.rand(*in_shape, dtype=torch.float64), torch.randint(0, 3, (in_shape[0],))
+
+    def collect(shard):
+        exts = [SqrtGGNExact(), BatchGrad()]
+        for e in exts:
+            e._shard = shard
+        run_backward(model, nn.CrossEntropyLoss(), x, y, exts, None)
+        out = [(p.sqrt_ggn_exact, p.grad_batch) for p in model.parameters()]
+        for p in model.parameters():
+            del p.sqrt_ggn_exact, p.grad_batch
+        return out
+
+    full, parts = collect(None), [collect((r, 2)) for r in range(2)]
+    for i, (V, g) in enumerate(full):
+        assert torch.allclose(torch.cat([parts[0][i][0], parts[1][i][0]], 2), V, rtol=1e-12, atol=1e-14)
+        assert torch.allclose(torch.cat([parts[0][i][1], parts[1][i][1]], 1), g, rtol=1e-12, atol=1e-14)

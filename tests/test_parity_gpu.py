@@ -20,6 +20,7 @@ from tests.problems import (
     GROUPING_IDS,
     GROUPINGS,
     IDS,
+    ND_NETS,
     PROBLEMS,
     constant_damping,
     keep_nonzero,
@@ -560,6 +561,50 @@ def test_one_dimensional_layers(dtype):
     (t64,) = ref.directional_damped_newton(tm, cl, tx, ty, regroup(cg, cm, tm))
     got = torch.cat([s.flatten() for s in nw.get_result(gg[0])])
     close(got, torch.cat([t.flatten() for t in want]), dtype, "1-d newton",
+          truth=torch.cat([t.flatten() for t in t64]))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name", sorted(ND_NETS))
+def test_conv3d_and_transposed_convolutions(name, dtype):
+    """``Conv3d`` / ``ConvTranspose1d/2d/3d`` are composed from the 2-d kernels
+    (``backprop/conv_nd.py``: depth taps as sums of 2-d problems; transposed convolutions as the 2-d kernels with
+    their operands swapped, every factor row its own "sample"): eigenpairs, directional derivatives (which also
+    exercise the per-sample gradients) and the Newton step against the oracle."""
+    from vivit_b200 import DirectionalDampedNewtonComputation, DirectionalDerivativesComputation, EighComputation
+
+    torch.manual_seed(0)
+    cm, in_shape = ND_NETS[name]()
+    cm = cm.to(dtype)
+    cx, cy = torch.rand(*in_shape).to(dtype), torch.randint(0, 3, (in_shape[0],))
+    cl = nn.CrossEntropyLoss()
+    gm, gx, gy = copy.deepcopy(cm).to(DEV), cx.to(DEV), cy.to(DEV)
+    cg = [{"params": list(cm.parameters()), "criterion": make_top_k(3), "damping": constant_damping(1.0)}]
+    gg = regroup(cg, cm, gm)
+
+    comp = EighComputation()
+    run_backward(gm, nn.CrossEntropyLoss(), gx, gy, comp.get_extensions(), comp.get_extension_hook(gg))
+    ((w_evals, w_evecs),) = ref.eigh(cm, cl, cx, cy, cg)
+    evals, evecs = comp.get_result(gg[0])
+    close(evals, w_evals, dtype, name + " evals")
+    flat = torch.cat([e.flatten(1) for e in evecs], 1).double().cpu()
+    wflat = torch.cat([e.flatten(1) for e in w_evecs], 1).double()
+    assert (flat @ wflat.t()).abs().diag().min() > 1 - (1e-3 if dtype == torch.float32 else 1e-8)
+
+    dd = DirectionalDerivativesComputation(subsampling_ggn=[2, 0])
+    run_backward(gm, nn.CrossEntropyLoss(), gx, gy, dd.get_extensions(), dd.get_extension_hook(gg))
+    ((wg, wl),) = ref.directional_derivatives(cm, cl, cx, cy, cg, None, [2, 0])
+    gam, lam = dd.get_result(gg[0])
+    close(gam.abs(), wg.abs(), dtype, name + " gammas")
+    close(lam, wl, dtype, name + " lambdas")
+
+    nw = DirectionalDampedNewtonComputation()
+    run_backward(gm, nn.CrossEntropyLoss(), gx, gy, nw.get_extensions(), nw.get_extension_hook(gg))
+    (want,) = ref.directional_damped_newton(cm, cl, cx, cy, cg)
+    tm, tx, ty = upcast(cm, cx, cy)
+    (t64,) = ref.directional_damped_newton(tm, cl, tx, ty, regroup(cg, cm, tm))
+    got = torch.cat([s.flatten() for s in nw.get_result(gg[0])])
+    close(got, torch.cat([t.flatten() for t in want]), dtype, name + " newton",
           truth=torch.cat([t.flatten() for t in t64]))
 
 

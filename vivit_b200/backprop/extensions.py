@@ -12,7 +12,8 @@ Public classes mirror what the reference hands to ``with backpack(...)``:
   ``GradFactor`` object instead of the materialised tensor.
 
 Module coverage: ``CrossEntropyLoss``, ``MSELoss``, ``Linear`` (also with additional input
-dimensions), ``Conv2d``, ``Conv1d``, ``BatchNorm1d/2d/3d`` (evaluation mode), ``ReLU``, ``Sigmoid``, ``Tanh``,
+dimensions), ``Conv2d``, ``Conv1d``, ``Conv3d`` and ``ConvTranspose1d/2d/3d`` (composed from the 2-d kernels,
+``backprop/conv_nd.py``), ``BatchNorm1d/2d/3d`` (evaluation mode), ``ReLU``, ``Sigmoid``, ``Tanh``,
 ``LeakyReLU``, ``ELU``, ``SELU``, ``LogSigmoid``, ``MaxPool2d``, ``AvgPool2d``, ``MaxPool1d``, ``AvgPool1d``
 (1-d layers run on the 2-d kernels over feature maps of unit height), ``ZeroPad2d``,
 ``Flatten``, ``Dropout``, ``Identity``, and the branching modules of ``vivit_b200.custom_module``
@@ -31,6 +32,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from vivit_b200 import kernels
+from vivit_b200.backprop import conv_nd
 from vivit_b200.custom_module import Pad, ScaleModule, Slicing, SumModule
 from vivit_b200.factors import (
     DenseFactor,
@@ -298,6 +300,62 @@ def _factor_conv2d(ext: _SqrtFactorExtension, module: nn.Conv2d, S: Tensor, need
     return S_in.squeeze(3) if one_d else S_in
 
 
+_CONV_TRANSPOSE = (nn.ConvTranspose1d, nn.ConvTranspose2d, nn.ConvTranspose3d)
+
+
+def _conv3d_operands(module, S: Tensor, x: Tensor):
+    """Factor, input, weight and geometry of a ``Conv3d`` / ``ConvTransposeNd`` layer in the 3-d form of
+    ``backprop/conv_nd.py`` (1-d and 2-d layers get unit depth / height)."""
+    nd = x.dim() - 2
+    geom = (
+        conv_nd.triple(module.kernel_size, nd, 1),
+        conv_nd.triple(module.stride, nd, 1),
+        conv_nd.triple(module.padding, nd, 0),
+        conv_nd.triple(module.dilation, nd, 1),
+    )
+    return conv_nd.lift_to_3d(S, nd), conv_nd.lift_to_3d(x, nd), conv_nd.lift_to_3d(module.weight.detach(), nd), nd, geom
+
+
+def _unlift(t: Tensor, nd: int) -> Tensor:
+    """Inverse of ``conv_nd.lift_to_3d`` on ``[V, N, C, D, H, W]``."""
+    for _ in range(3 - nd):
+        t = t.squeeze(3)
+    return t
+
+
+def _factor_conv3d(ext: _SqrtFactorExtension, module: nn.Conv3d, S: Tensor, need_in: bool):
+    """``Conv3d`` as a sum of 2-d problems over the depth taps (``backprop/conv_nd.py``)."""
+    _conv_check(module)
+    S, x, weight, nd, (kernel, *geom) = _conv3d_operands(module, S, ext._subsample(module.input0.detach()))
+    w, b = _trainable(module, "weight"), _trainable(module, "bias")
+    lo, hi = ext._own(S.shape[2])
+    S_own = S if hi - lo == S.shape[2] else S[:, :, lo:hi].contiguous()
+    if b is not None:
+        ext._save(b, DenseFactor(kernels.v_emit_bias(S_own), (hi - lo,)))
+    if w is not None:
+        ext._save(w, DenseFactor(conv_nd.conv3d_emit(S_own, x, kernel, *geom), (hi - lo, *w.shape[1:])))
+    return conv_nd.conv3d_backprop(S, weight, tuple(x.shape[2:]), *geom) if need_in else None
+
+
+def _factor_conv_transpose(ext: _SqrtFactorExtension, module, S: Tensor, need_in: bool):
+    """``ConvTranspose1d/2d/3d``: the 2-d kernels with the roles of their operands swapped
+    (``backprop/conv_nd.py``).  The weight is ``[C_in, C_out, *k]``: a rank owns a slice of ``C_in`` of it and
+    a slice of ``C_out`` of the bias."""
+    _conv_check(module)
+    S, x, weight, nd, (kernel, *geom) = _conv3d_operands(module, S, ext._subsample(module.input0.detach()))
+    w, b = _trainable(module, "weight"), _trainable(module, "bias")
+    if b is not None:
+        lo, hi = ext._own(S.shape[2])
+        ext._save(b, DenseFactor(kernels.v_emit_bias(S[:, :, lo:hi].contiguous()), (hi - lo,)))
+    if w is not None:
+        lo, hi = ext._own(x.shape[1])
+        Vt = conv_nd.conv_transpose3d_emit(S, x[:, lo:hi].contiguous(), kernel, *geom)
+        ext._save(w, DenseFactor(Vt, (hi - lo, *w.shape[1:])))
+    if not need_in:
+        return None
+    return _unlift(conv_nd.conv_transpose3d_backprop(S, weight, tuple(x.shape[2:]), *geom), nd)
+
+
 def _factor_act(act, use_output, scale_of=None):
     def handler(ext, module, S, need_in):
         if not need_in:
@@ -481,6 +539,10 @@ _FACTOR_HANDLERS = {
     nn.Linear: _factor_linear,
     nn.Conv2d: _factor_conv2d,
     nn.Conv1d: _factor_conv2d,
+    nn.Conv3d: _factor_conv3d,
+    nn.ConvTranspose1d: _factor_conv_transpose,
+    nn.ConvTranspose2d: _factor_conv_transpose,
+    nn.ConvTranspose3d: _factor_conv_transpose,
     nn.ReLU: _factor_act(kernels.ACT_RELU, use_output=False),
     nn.Sigmoid: _factor_act(kernels.ACT_SIGMOID, use_output=True),
     nn.Tanh: _factor_act(kernels.ACT_TANH, use_output=True),
@@ -603,6 +665,26 @@ class BatchGrad(Extension):
                 self._save(b, DenseGrad(kernels.v_emit_bias(g)[0], (hi - lo,)))
             if w is not None:
                 gw = kernels.v_emit_conv2d(g, x, *_conv_geometry(module))[0]
+                self._save(w, DenseGrad(gw, (hi - lo, *w.shape[1:])))
+        elif isinstance(module, (nn.Conv3d, *_CONV_TRANSPOSE)):
+            w, b = _trainable(module, "weight"), _trainable(module, "bias")
+            if w is None and b is None:
+                return
+            _conv_check(module)
+            g, x, _, _, (kernel, *geom) = _conv3d_operands(
+                module, self._subsample(g_out.detach())[None], self._subsample(module.input0.detach())
+            )  # one "class": [1, N, Co, D', H', W']
+            transposed = isinstance(module, _CONV_TRANSPOSE)
+            if b is not None:
+                lo, hi = self._own(g.shape[2])
+                self._save(b, DenseGrad(kernels.v_emit_bias(g[:, :, lo:hi].contiguous())[0], (hi - lo,)))
+            if w is not None and transposed:
+                lo, hi = self._own(x.shape[1])
+                gw = conv_nd.conv_transpose3d_emit(g, x[:, lo:hi].contiguous(), kernel, *geom)[0]
+                self._save(w, DenseGrad(gw, (hi - lo, *w.shape[1:])))
+            elif w is not None:
+                lo, hi = self._own(g.shape[2])
+                gw = conv_nd.conv3d_emit(g[:, :, lo:hi].contiguous(), x, kernel, *geom)[0]
                 self._save(w, DenseGrad(gw, (hi - lo, *w.shape[1:])))
         elif isinstance(module, _BATCHNORM):
             w, b = _trainable(module, "weight"), _trainable(module, "bias")
