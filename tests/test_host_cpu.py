@@ -370,3 +370,27 @@ def test_shared_solve_queue_gives_the_immediate_results(grouping, monkeypatch):
         close(l0, l1)
         for a, b in zip(vecs0, vecs1):
             close(a, b)
+
+
+def test_solve_queue_keeps_the_other_results_when_a_callback_raises():
+    """A criterion that raises inside the deferred half of one Computation's hook is reported once, by the
+    ``get_result`` that flushed the queue, and does not cost the other Computation its results."""
+    import vivit_b200 as vv
+
+    def broken(evals):
+        raise RuntimeError("criterion failed")
+
+    model, loss_fn, x, y = PROBLEMS[0].make()
+    good = [{"params": list(model.parameters()), "criterion": keep_nonzero}]
+    bad = [{"params": list(model.parameters()), "criterion": broken}]
+    queue = vv.SolveQueue()
+    eigh, dirs = vv.EighComputation(solve_queue=queue), vv.DirectionalDerivativesComputation(solve_queue=queue)
+    run_backward(model, loss_fn, x, y, [eigh.get_extension()], eigh.get_extension_hook(bad))
+    run_backward(model, loss_fn, x, y, dirs.get_extensions(), dirs.get_extension_hook(good))
+    with pytest.raises(RuntimeError, match="criterion failed"):
+        eigh.get_result(bad[0])
+    assert len(queue) == 0
+    gammas, lambdas = dirs.get_result(good[0])
+    assert gammas.shape[1] == lambdas.shape[1] > 0
+    with pytest.raises(KeyError):
+        eigh.get_result(bad[0])

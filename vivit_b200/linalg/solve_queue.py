@@ -67,5 +67,13 @@ class SolveQueue:
             evals, evecs = kernels.syevj_batched(torch.stack([items[i][0] for i in members]), vectors=True)
             for slot, i in enumerate(members):
                 solved[i] = (evals[slot], evecs[slot])
+        # every callback runs, also after one of them has raised (a criterion of one Computation must not cost the
+        # others their results); the first exception is re-raised at the end
+        failed = None
         for (_, done), (evals, evecs) in zip(items, solved):
-            done(evals, evecs)
+            try:
+                done(evals, evecs)
+            except Exception as e:  # noqa: BLE001
+                failed = failed or e
+        if failed is not None:
+            raise failed
