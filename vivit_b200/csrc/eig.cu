@@ -1581,11 +1581,12 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
   const int rr_blocks = int(vmin<int64_t>(ceil_div(RR, 256), 8 * num_sms()));
   // one GEMM per problem on the tcgen05 / DMMA kernel when the problems are large, one batched launch otherwise
   const bool loop_gemm = B == 1 || R >= 1024;
-  // (short contractions -- the trailing updates of the Cholesky factor, K = 64 -- run on the mma.sync kernel in any
-  // case: one launch for all problems)
+  // (the trailing updates of the Cholesky factor, K = 64, of problems up to 2048 columns are latency-bound: one
+  // mma.sync launch for all problems, 16.9 -> 16.7 ms for two R = 1280 problems; larger ones are worth a tcgen05
+  // launch each -- batching them cost 24 ms at 2 x R = 5120)
   auto gemm_batched = [&](T* C, const T* A, const T* Bm, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                           int64_t ldc, double alpha, double beta) -> int {
-    if (loop_gemm && (B == 1 || K > CB)) {
+    if (loop_gemm && (B == 1 || K > CB || R > 2048)) {
       for (int64_t b = 0; b < B; ++b)
         VVT_TRY(vvt_gemm(C + b * RR, A + b * RR, Bm + b * RR, M, N, K, 0, 0, lda, ldb, ldc, alpha, beta, 1, 0, 0, 0,
                          ws + L.off_gemm, L.gemm_bytes, dtype, (void*)s));
