@@ -115,6 +115,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -158,8 +166,15 @@ constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >>
 // {32, 32, 1, 4}: tile row r = i_local + 32 j_local); row tile tm covers i-chunk tm % a4_chunks and j-chunk
 // tm / a4_chunks.  Used by the conv factor emit, whose rows (v, o) of a sample are not equidistant in memory: the
 // store functor decodes the padded row index (see EmitStoreTc4 in conv.cu).
+// TS kernels run EIGHT converter / epilogue warps (THREADS_TS): two per quarter of the tensor-memory lanes, the
+// second set takes columns 16..31 of every k-block of A, the second half of the lo tile of B and columns 64..127 of the
+// accumulators, so that every scheduler has two warps to hide the shared-memory, ALU and tcgen05.wait latencies of
+// the conversion behind, and the epilogue has twice the threads.  Measured: nothing at R = 1280, D = 110592
+// (178.5 TFLOP/s before and after: the main loop is not conversion-bound), 4.5 % over the twelve Gram calls of a c2
+// step (3.51 -> 3.35 ms: the short ones are prologue / epilogue).
+constexpr int THREADS_TS = 320;
 template <typename ST, bool COL_LANES, bool TS = false, bool A4D = false>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(TS ? THREADS_TS : THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, ST st,
                int64_t M, int64_t N, int tiles_n, int symmetric, int kblocks_total, int kblocks_per_split,
                int a4_chunks = 1) {
@@ -195,16 +210,19 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int kb0 = split * kblocks_per_split, kb1 = min(kblocks_total, kb0 + kblocks_per_split);
   const int nkb = kb1 - kb0;  // >= 1 (host guarantees)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NCONV = (TS ? THREADS_TS : THREADS) - 64;  // converter / epilogue threads
+  constexpr int NW = NCONV / 32;                            // ... warps (4 or 8)
+  constexpr int BNT = BN * 4 / NW;                          // accumulator columns per thread (128 or 64)
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_tma(s), 1);
-      mbar_init(bar_conv(s), 128);
+      mbar_init(bar_conv(s), NCONV);
       mbar_init(bar_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full(b), 1);
-      mbar_init(bar_acc_empty(b), 128);
+      mbar_init(bar_acc_empty(b), NCONV);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -304,20 +322,22 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else {
     // ===== converters: lo = rna_tf32(x - trunc_tf32(x)); promotion of finished accumulator groups =====
-    const int ct = threadIdx.x - 64;  // 0..127
+    const int ct = threadIdx.x - 64;  // 0..NCONV-1
     const int n_vec = (diag ? 1 : 2) * (TILE_BYTES / 16);
     const int lane_grp = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+    const int half = (warp - 2) >> 2;  // 0, or 1 for the second set of converter warps (TS)
+    const int cbase = half * BNT;      // first accumulator column of this thread
     const int n_groups = (nkb + PROMOTE - 1) / PROMOTE;
-    float total[BN];  // this thread's row of the output tile, summed with round-to-nearest adds
+    float total[BNT];  // this thread's part of its row of the output tile, summed with round-to-nearest adds
 #pragma unroll
-    for (int j = 0; j < BN; ++j) total[j] = 0.f;
+    for (int j = 0; j < BNT; ++j) total[j] = 0.f;
     auto drain = [&](int grp) {
       mbar_wait(bar_acc_full(grp & 1), (grp >> 1) & 1);
       tcgen05_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < BNT; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t((grp & 1) * BN + c0), r);
+        tmem_ld32(tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t((grp & 1) * BN + cbase + c0), r);
 #pragma unroll
         for (int j = 0; j < 32; ++j) total[c0 + j] += __uint_as_float(r[j]);
       }
@@ -333,11 +353,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if constexpr (TS) {
         // A role: this thread's row of the raw tile (128-byte swizzle: 16-byte chunk c of row m sits at chunk
         // c ^ (m & 7); the eight lanes of a quarter warp hit eight different chunks) -> hi and lo in TMEM
+        // (the two threads of a row take 16 of its 32 columns each)
         const int m = lane_grp * 32 + lane;
-        uint32_t hi[32], lo[32];
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 x = *reinterpret_cast<const float4*>(stage + size_t(m) * 128 + size_t((c ^ (m & 7)) * 16));
+        for (int c = 0; c < 4; ++c) {
+          const int cc = 4 * half + c;
+          const float4 x = *reinterpret_cast<const float4*>(stage + size_t(m) * 128 + size_t((cc ^ (m & 7)) * 16));
           const float e[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -346,14 +368,14 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             lo[4 * c + j] = __float_as_uint(e[j] - __uint_as_float(bits & 0xFFFFE000u)) + 0x1000u;
           }
         }
-        const uint32_t ta = a_cols(s) + (uint32_t(lane_grp * 32) << 16);
-        tmem_st32(ta, hi);
-        tmem_st32(ta + 32, lo);
+        const uint32_t ta = a_cols(s) + (uint32_t(lane_grp * 32) << 16) + uint32_t(16 * half);
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 32, lo);
         tmem_st_wait();
       }
       // B role (TS: only the B tile, which is the raw A tile itself on diagonal tiles): lo tiles in shared memory
 #pragma unroll 4
-      for (int v = (TS && !diag) ? ct + TILE_BYTES / 16 : ct; v < n_vec; v += 128) {
+      for (int v = (TS && !diag) ? ct + TILE_BYTES / 16 : ct; v < n_vec; v += NCONV) {
         const float4 x = *reinterpret_cast<const float4*>(stage + size_t(v) * 16);
         float4 lo;
         {
@@ -388,24 +410,24 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       float* tile = reinterpret_cast<float*>(base_ptr);
       const int trow = lane_grp * 32 + lane;
 #pragma unroll
-      for (int j = 0; j < BN; ++j) tile[trow * (BN + 1) + j] = total[j];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int cw = warp - 2;  // 0..3
+      for (int j = 0; j < BNT; ++j) tile[trow * (BN + 1) + cbase + j] = total[j];
+      asm volatile("bar.sync 1, %0;" ::"n"(NCONV) : "memory");
+      const int cw = warp - 2;  // 0..NW-1
       const int64_t row0 = int64_t(tm) * BM, col0 = int64_t(tn) * BN;
       if constexpr (COL_LANES) {
-        // lanes = consecutive columns (row-major outputs): this warp stores rows cw, cw + 4, ...;
-        // lane l prepares the offset of row cw + 4 l, the others fetch it by shuffle.  Rows go in batches of
+        // lanes = consecutive columns (row-major outputs): this warp stores rows cw, cw + NW, ...;
+        // lane l prepares the offset of row cw + NW l, the others fetch it by shuffle.  Rows go in batches of
         // 4: the 16 old values an accumulating store needs are fetched before the first store.
-        const int64_t my_row = row0 + cw + 4 * lane;
-        const int64_t my_off = my_row < M ? st.row_offset(batch, my_row) : 0;
-        for (int i0 = 0; i0 < BM / 4; i0 += 4) {
-          if (row0 + cw + 4 * i0 >= M) break;  // warp-uniform
+        const int64_t my_row = row0 + cw + NW * lane;
+        const int64_t my_off = (NW * lane < BM && my_row < M) ? st.row_offset(batch, my_row) : 0;
+        for (int i0 = 0; i0 < BM / NW; i0 += 4) {
+          if (row0 + cw + NW * i0 >= M) break;  // warp-uniform
           int64_t off[4];
           float old[4][BN / 32];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             off[u] = __shfl_sync(0xffffffffu, my_off, i0 + u);
-            const int64_t row = row0 + cw + 4 * (i0 + u);
+            const int64_t row = row0 + cw + NW * (i0 + u);
 #pragma unroll
             for (int q = 0; q < BN / 32; ++q) {
               const int64_t col = col0 + lane + 32 * q;
@@ -414,7 +436,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int r = cw + 4 * (i0 + u);
+            const int r = cw + NW * (i0 + u);
             const int64_t row = row0 + r;
 #pragma unroll
             for (int q = 0; q < BN / 32; ++q) {
@@ -433,7 +455,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const int64_t row = row0 + lane + 32 * c;
           offs[c] = row < M ? st.row_offset(batch, row) : 0;
         }
-        for (int j = cw; j < BN; j += 4) {
+        for (int j = cw; j < BN; j += NW) {
           const int64_t col = col0 + j;
           if (col >= N) break;  // warp-uniform
 #pragma unroll
@@ -444,12 +466,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       }
       if (symmetric && !diag) {  // mirrored entries (col, row): lanes = consecutive rows -> coalesced
-        for (int j0 = cw; j0 < BN; j0 += 16) {  // columns j0, j0 + 4, j0 + 8, j0 + 12 per batch
+        for (int j0 = cw; j0 < BN; j0 += 4 * NW) {  // columns j0, j0 + NW, j0 + 2 NW, j0 + 3 NW per batch
           if (col0 + j0 >= N) break;             // warp-uniform
           float old[4][BM / 32];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int64_t col = col0 + j0 + 4 * u;
+            const int64_t col = col0 + j0 + NW * u;
 #pragma unroll
             for (int c = 0; c < BM / 32; ++c) {
               const int64_t row = row0 + lane + 32 * c;
@@ -458,7 +480,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int j = j0 + 4 * u;
+            const int j = j0 + NW * u;
             const int64_t col = col0 + j;
 #pragma unroll
             for (int c = 0; c < BM / 32; ++c) {

@@ -62,7 +62,8 @@ int launch_gram_tc(const float* A, const float* B, StdStore<float> st, int64_t M
   StdStore<float> kst = st;
   kst.partial = splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
   dim3 grid(unsigned(tiles), unsigned(splits), 1);
-  kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, kst, M, N, tiles_n, symmetric ? 1 : 0, int(kblocks), int(per), 1);
+  kern<<<grid, ts ? THREADS_TS : THREADS, SMEM_BYTES, stream>>>(mapA, mapB, kst, M, N, tiles_n, symmetric ? 1 : 0, int(kblocks),
+                                                               int(per), 1);
   VVT_TRY(launched(what));
   if (splits > 1) {
     const int64_t total = M * N;
