@@ -303,23 +303,30 @@ struct StdStore {
   T padd;
   T* partial;    // non-null => split-K partial slabs [splits][M*N]
   int64_t slab, N;
-  __device__ __forceinline__ T weight(int64_t r, int64_t c) const {
-    return P ? ldg(P + (r % pr) * ldp + (c % pc)) + padd : T(1);
+  // index of the Hadamard factor: r % pr, c % pc -- in 32-bit arithmetic whenever the numbers allow it (a 64-bit
+  // remainder is ~60 instructions; two of them per output element were most of the epilogue of the structured
+  // Linear Gram at R = 10240)
+  __device__ __forceinline__ static int64_t wrap(int64_t x, int64_t m) {
+    return ((x | m) >> 32) == 0 ? int64_t(uint32_t(x) % uint32_t(m)) : x % m;
   }
-  // forms used by the tcgen05 epilogue: row_offset (nothing to precompute here), and the accumulate split
-  // into fetch (the old value of C, if beta needs it) and commit, so that a batch of independent loads can be
-  // in flight before the first store (one dependent global load per element made small-K products -- the
-  // Cholesky trailing updates -- latency bound: 75 us per launch)
-  __device__ __forceinline__ int64_t row_offset(int, int64_t r) const { return r; }
+  __device__ __forceinline__ T weight(int64_t r, int64_t c) const {
+    return P ? ldg(P + wrap(r, pr) * ldp + wrap(c, pc)) + padd : T(1);
+  }
+  // forms used by the tcgen05 epilogue: row_offset (the row of the Hadamard factor, computed once per output row),
+  // and the accumulate split into fetch (the old value of C, if beta needs it) and commit, so that a batch of
+  // independent loads can be in flight before the first store (one dependent global load per element made small-K
+  // products -- the Cholesky trailing updates -- latency bound: 75 us per launch)
+  __device__ __forceinline__ int64_t row_offset(int, int64_t r) const { return P ? wrap(r, pr) * ldp : 0; }
   __device__ __forceinline__ T fetch(int64_t, int64_t r, int64_t c) const {
     return (partial || beta == T(0)) ? T(0) : C[r * ldc + c];
   }
-  __device__ __forceinline__ void commit(int64_t, int64_t r, int64_t c, T v, T old, int split) const {
+  __device__ __forceinline__ void commit(int64_t prow, int64_t r, int64_t c, T v, T old, int split) const {
     if (partial) {
       partial[int64_t(split) * slab + r * N + c] = v;
       return;
     }
-    C[r * ldc + c] = beta * old + alpha * v * weight(r, c);  // old = 0 when beta = 0
+    const T w = P ? ldg(P + prow + wrap(c, pc)) + padd : T(1);
+    C[r * ldc + c] = beta * old + alpha * v * w;  // old = 0 when beta = 0
   }
   __device__ __forceinline__ void store(int64_t, int64_t r, int64_t c, T v, int split) const {
     (*this)(0, r, c, v, split);

@@ -469,13 +469,15 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int j0 = cw; j0 < BN; j0 += 4 * NW) {  // columns j0, j0 + NW, j0 + 2 NW, j0 + 3 NW per batch
           if (col0 + j0 >= N) break;             // warp-uniform
           float old[4][BM / 32];
+          int64_t moff[4];  // the mirrored entry's row is this tile's column: one offset per column
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int64_t col = col0 + j0 + NW * u;
+            moff[u] = col < N ? st.row_offset(batch, col) : 0;
 #pragma unroll
             for (int c = 0; c < BM / 32; ++c) {
               const int64_t row = row0 + lane + 32 * c;
-              old[u][c] = (col < N && row < M) ? st.fetch(st.row_offset(batch, col), col, row) : 0.f;
+              old[u][c] = (col < N && row < M) ? st.fetch(moff[u], col, row) : 0.f;
             }
           }
 #pragma unroll
@@ -485,8 +487,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int c = 0; c < BM / 32; ++c) {
               const int r = lane + 32 * c;
-              if (col < N && row0 + r < M)
-                st.commit(st.row_offset(batch, col), col, row0 + r, tile[r * (BN + 1) + j], old[u][c], split);
+              if (col < N && row0 + r < M) st.commit(moff[u], col, row0 + r, tile[r * (BN + 1) + j], old[u][c], split);
             }
           }
         }
