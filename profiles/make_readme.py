@@ -110,7 +110,7 @@ def main():
         if os.path.exists(kept_json):
             d = json.load(open(kept_json))
             one = json.load(open(os.path.join(OUT, f"{ROUND}_bench_{w}.json")))
-            multi.append(f"| {w} | {n} | {d['config'].get('parallelism', 'parameter-sharded Gram, one all-reduce per group')} | "
+            multi.append(f"| {w} | {n} | {(d.get('schedule') or d['config']).get('parallelism', 'parameter-sharded Gram, one all-reduce per group')} | "
                          f"{one['value']} | {d['value']} | {d['e2e']['value']} | {d.get('gram_assembly_ms_per_step')} "
                          f"(1 GPU: {one.get('gram_assembly_ms_per_step')}) | {d.get('eigensolver_ms_per_step')} |")
     if multi:
