@@ -12,6 +12,7 @@ directions.
 
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import math
 from typing import Optional, Tuple
@@ -66,8 +67,28 @@ def _p(t: Optional[Tensor]):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_NO_SWITCH = contextlib.nullcontext()
+
+
+def _stream_handle(device: torch.device) -> int:
+    """``cudaStream_t`` of torch's current stream on ``device``.  (The raw query is ~20x cheaper than building a
+    ``torch.cuda.Stream`` object; a curvature step makes a few hundred kernel calls and the GPU idles at the start
+    of a step while the host catches up.)"""
+    if _raw_stream is not None and device.index is not None:
+        return _raw_stream(device.index)
+    return torch.cuda.current_stream(device).cuda_stream
+
+
 def _stream(t: Tensor):
-    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return ctypes.c_void_p(_stream_handle(t.device))
+
+
+def _on(device: torch.device):
+    """Context that makes ``device`` current for a kernel call -- nothing to do when it already is."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(device)
 
 
 # Workspace arena: one byte buffer per (device, stream), grown on demand and reused by every kernel entry point that
@@ -80,7 +101,7 @@ _WORKSPACES = {}
 
 def _ws(nbytes: int, like: Tensor) -> Tensor:
     nbytes = max(int(nbytes), 16)
-    key = (like.device.index, torch.cuda.current_stream(like.device).cuda_stream)
+    key = (like.device.index, _stream_handle(like.device))
     buf = _WORKSPACES.get(key)
     if buf is None or buf.numel() < nbytes:
         _WORKSPACES.pop(key, None)
@@ -117,7 +138,7 @@ def loss_sqrt_hessian_ce(logits: Tensor, sub: Optional[Tensor], mean: bool) -> T
     n_sub = n_total if sub is None else sub.numel()
     S = torch.empty(C, n_sub, C, dtype=logits.dtype, device=logits.device)
     scale = 1.0 / math.sqrt(n_total) if mean else 1.0
-    with torch.cuda.device(logits.device):
+    with _on(logits.device):
         st = _lib.load().vvt_loss_sqrt_hessian_ce(
             _p(S), _p(logits), _p(sub), n_total, n_sub, C, scale, _dt(logits), _stream(logits)
         )
@@ -135,7 +156,7 @@ def loss_sqrt_hessian_ce_mc(
     M, n_sub = class_ids.shape
     S = torch.empty(M, n_sub, C, dtype=logits.dtype, device=logits.device)
     scale = 1.0 / math.sqrt(M) / (math.sqrt(n_total) if mean else 1.0)
-    with torch.cuda.device(logits.device):
+    with _on(logits.device):
         st = _lib.load().vvt_loss_sqrt_hessian_ce_mc(
             _p(S), _p(logits), _p(sub), _p(class_ids), n_total, n_sub, C, M, scale,
             _dt(logits), _stream(logits),
@@ -148,7 +169,7 @@ def loss_sqrt_hessian_mse(n_sub: int, C: int, scale: float, like: Tensor) -> Ten
     """``[C, N_sub, C]`` with ``S[v,n,c] = scale * delta_vc``."""
     _chk(like)
     S = torch.empty(C, n_sub, C, dtype=like.dtype, device=like.device)
-    with torch.cuda.device(like.device):
+    with _on(like.device):
         st = _lib.load().vvt_loss_sqrt_hessian_mse(_p(S), n_sub, C, scale, _dt(like), _stream(like))
     _lib.check(st, "vvt_loss_sqrt_hessian_mse")
     return S
@@ -156,7 +177,7 @@ def loss_sqrt_hessian_mse(n_sub: int, C: int, scale: float, like: Tensor) -> Ten
 
 def scale_(t: Tensor, alpha: float) -> Tensor:
     _chk(t)
-    with torch.cuda.device(t.device):
+    with _on(t.device):
         st = _lib.load().vvt_scale(_p(t), t.numel(), float(alpha), _dt(t), _stream(t))
     _lib.check(st, "vvt_scale")
     return t
@@ -167,7 +188,7 @@ def axpy_(y: Tensor, x: Tensor, alpha: float = 1.0) -> Tensor:
     _chk(y, x)
     if y.shape != x.shape or not (y.is_contiguous() and x.is_contiguous()):
         raise ValueError("axpy_ needs contiguous tensors of one shape")
-    with torch.cuda.device(y.device):
+    with _on(y.device):
         st = _lib.load().vvt_axpy(_p(y), _p(x), y.numel(), float(alpha), _dt(y), _stream(y))
     _lib.check(st, "vvt_axpy")
     return y
@@ -177,7 +198,7 @@ def nccl_allreduce_gram(comm_ptr: int, G: Tensor, X: Optional[Tensor] = None, al
     """``G`` (and ``X``) ``<- alpha * sum over ranks``, in place, one NCCL call group on the current stream;
     ``comm_ptr`` is the raw ``ncclComm_t`` of the process group (``ProcessGroupNCCL._comm_ptr()``)."""
     _chk(G, X)
-    with torch.cuda.device(G.device):
+    with _on(G.device):
         st = _lib.load().vvt_nccl_allreduce_gram(
             ctypes.c_void_p(comm_ptr), _p(G), G.numel(), _p(X), 0 if X is None else X.numel(), float(alpha),
             _dt(G), _stream(G),
@@ -194,7 +215,7 @@ def center_rows(g: Tensor, inplace: bool = False) -> Tensor:
     out = g if inplace else torch.empty_like(g)
     N = g.shape[0]
     D = g.numel() // N if N else 0
-    with torch.cuda.device(g.device):
+    with _on(g.device):
         st = _lib.load().vvt_center_rows(_p(out), _p(g), N, D, _dt(g), _stream(g))
     _lib.check(st, "vvt_center_rows")
     return out
@@ -212,7 +233,7 @@ def sqrt_backprop_linear(S: Tensor, W: Tensor) -> Tensor:
     n_out, n_in = W.shape
     rows = S.numel() // n_out
     out = torch.empty(*S.shape[:-1], n_in, dtype=S.dtype, device=S.device)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = _lib.load().vvt_sqrt_backprop_linear(
             _p(out), _p(S), _p(W), rows, n_out, n_in, _dt(S), _stream(S)
         )
@@ -232,7 +253,7 @@ def sqrt_backprop_conv2d(
     out = torch.empty(V, N, ci, h, w, dtype=S.dtype, device=S.device)
     lib = _lib.load()
     ws = _ws(lib.vvt_conv2d_workspace_bytes(1, V, N, co, ho, wo, ci, kh, kw, _dt(S)), S)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = lib.vvt_sqrt_backprop_conv2d(
             _p(out), _p(S), _p(W), V * N, co, ho, wo, ci, h, w, kh, kw,
             stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1],
@@ -249,7 +270,7 @@ def sqrt_backprop_elementwise(S: Tensor, ref: Tensor, act: int, scale: float = 1
     n_feat = ref.numel()
     V = S.numel() // n_feat
     out = torch.empty_like(S)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = _lib.load().vvt_sqrt_backprop_elementwise(
             _p(out), _p(S), _p(ref), V, n_feat, act, float(scale), _dt(S), _stream(S)
         )
@@ -266,7 +287,7 @@ def sqrt_backprop_maxpool2d(
     V, N, ch, ho, wo = S.shape
     h, w = in_hw
     out = torch.empty(V, N, ch, h, w, dtype=S.dtype, device=S.device)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = _lib.load().vvt_sqrt_backprop_maxpool2d(
             _p(out), _p(S), _p(argmax), V, N, ch, ho, wo, h, w, kernel[0], kernel[1],
             stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1],
@@ -282,7 +303,7 @@ def sqrt_backprop_avgpool2d(S: Tensor, in_hw, kernel, stride, padding) -> Tensor
     V, N, ch, ho, wo = S.shape
     h, w = in_hw
     out = torch.empty(V, N, ch, h, w, dtype=S.dtype, device=S.device)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = _lib.load().vvt_sqrt_backprop_avgpool2d(
             _p(out), _p(S), V * N, ch, ho, wo, h, w, kernel[0], kernel[1],
             stride[0], stride[1], padding[0], padding[1], _dt(S), _stream(S),
@@ -308,7 +329,7 @@ def v_emit_conv2d(S: Tensor, X: Tensor, kernel, stride, padding, dilation) -> Te
         return Vt
     lib = _lib.load()
     ws = _ws(lib.vvt_conv2d_workspace_bytes(0, V, N, co, ho, wo, ci, kh, kw, _dt(S)), S)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = lib.vvt_v_emit_conv2d(
             _p(Vt), _p(S), _p(X), V, N, co, ho, wo, ci, h, w, kh, kw,
             stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1],
@@ -327,7 +348,7 @@ def v_emit_bias(S: Tensor) -> Tensor:
     if Vt.numel() == 0:  # an empty shard of the output channels
         return Vt
     spatial = S.numel() // (V * N * co)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = _lib.load().vvt_v_emit_bias(_p(Vt), _p(S), V * N, co, spatial, _dt(S), _stream(S))
     _lib.check(st, "vvt_v_emit_bias")
     return Vt
@@ -340,7 +361,7 @@ def v_emit_linear(S: Tensor, Z: Tensor) -> Tensor:
     V, N, n_out = S.shape
     n_in = Z.shape[1]
     Vt = torch.empty(V, N, n_out, n_in, dtype=S.dtype, device=S.device)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = _lib.load().vvt_v_emit_linear(
             _p(Vt), _p(S), _p(Z), V, N, n_out, n_in, _dt(S), _stream(S)
         )
@@ -373,7 +394,7 @@ def gemm(
     _chk(A, B, out)
     lib = _lib.load()
     ws = _ws(lib.vvt_gram_workspace_bytes(M, N, K, _dt(A)) if batch == 1 else 0, A)
-    with torch.cuda.device(A.device):
+    with _on(A.device):
         st = lib.vvt_gemm(
             _p(out), _p(A), _p(B), M, N, K, int(trans_a), int(trans_b),
             a2[1], b2[1], N, float(alpha), float(beta), batch,
@@ -391,7 +412,7 @@ def gram_dense_accum(G: Tensor, V: Tensor) -> Tensor:
     R, D = V.shape
     lib = _lib.load()
     ws = _ws(lib.vvt_gram_workspace_bytes(R, R, D, _dt(V)), V)
-    with torch.cuda.device(V.device):
+    with _on(V.device):
         st = lib.vvt_gram_dense_accum(_p(G), _p(V), R, D, _p(ws), ws.numel(), _dt(V), _stream(V))
     _lib.check(st, "vvt_gram_dense_accum")
     return G
@@ -405,7 +426,7 @@ def gram_cross_accum(X: Tensor, V: Tensor, g: Tensor) -> Tensor:
     n_g = g.shape[0]
     lib = _lib.load()
     ws = _ws(lib.vvt_gram_workspace_bytes(R, n_g, D, _dt(V)), V)
-    with torch.cuda.device(V.device):
+    with _on(V.device):
         st = lib.vvt_gram_cross_accum(
             _p(X), _p(V), _p(g), R, n_g, D, _p(ws), ws.numel(), _dt(V), _stream(V)
         )
@@ -421,7 +442,7 @@ def gram_linear_accum(G: Tensor, S: Tensor, Z: Tensor, with_bias: bool) -> Tenso
     n_in = Z.shape[1]
     lib = _lib.load()
     ws = _ws(lib.vvt_gram_linear_workspace_bytes(C, N, n_out, n_in, 0, _dt(S)), S)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = lib.vvt_gram_linear_accum(
             _p(G), _p(S), _p(Z), C, N, n_out, n_in, int(with_bias), _p(ws), ws.numel(),
             _dt(S), _stream(S),
@@ -441,7 +462,7 @@ def gram_cross_linear_accum(
     n_g = Dl.shape[0]
     lib = _lib.load()
     ws = _ws(lib.vvt_gram_linear_workspace_bytes(C, N, n_out, n_in, n_g, _dt(S)), S)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = lib.vvt_gram_cross_linear_accum(
             _p(X), _p(S), _p(Z), _p(Dl), _p(Zg), C, N, n_g, n_out, n_in, int(with_bias),
             _p(ws), ws.numel(), _dt(S), _stream(S),
@@ -498,7 +519,7 @@ def _syevj_batched(G: Tensor, vectors: bool, what: str):
     lib = _lib.load()
     ws = _ws(lib.vvt_syevj_batched_workspace_bytes(R, B, int(vectors), _dt(G)), G)
     info = (ctypes.c_int * (2 * B))()
-    with torch.cuda.device(G.device):
+    with _on(G.device):
         st = lib.vvt_syevj_batched(
             _p(evals), _p(evecs), _p(G), R, B, int(vectors), _p(ws), ws.numel(), info,
             _dt(G), _stream(G),
@@ -514,7 +535,7 @@ def filter_nonzero(evals: Tensor, atol: float = 1e-7, rtol: float = 1e-5) -> Ten
     evals = _c(evals)
     _chk(evals)
     mask = torch.empty(evals.numel(), dtype=torch.uint8, device=evals.device)
-    with torch.cuda.device(evals.device):
+    with _on(evals.device):
         st = _lib.load().vvt_filter_nonzero(
             _p(mask), _p(evals), evals.numel(), atol, rtol, None, _dt(evals), _stream(evals)
         )
@@ -537,7 +558,7 @@ def backtransform_dense(U: Tensor, V: Tensor, norm2: Optional[Tensor]) -> Tensor
     E = torch.empty(K, D, dtype=V.dtype, device=V.device)
     if K == 0 or D == 0:
         return E
-    with torch.cuda.device(V.device):
+    with _on(V.device):
         st = _lib.load().vvt_backtransform_dense(
             _p(E), _p(norm2), _p(U), _p(V), K, R, D, _dt(V), _stream(V)
         )
@@ -557,7 +578,7 @@ def backtransform_linear(U: Tensor, S: Tensor, Z: Tensor, norm2: Optional[Tensor
     if K == 0:
         return E
     ws = _ws(K * N * n_out * S.element_size(), S)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = _lib.load().vvt_backtransform_linear(
             _p(E), _p(None), _p(norm2), _p(U), _p(S), _p(Z), K, C, N, n_out, n_in,
             _p(ws), ws.numel(), _dt(S), _stream(S),
@@ -575,7 +596,7 @@ def vt_mat_prod_linear(S: Tensor, Z: Tensor, M: Tensor) -> Tensor:
     F_ = M.shape[0]
     out = torch.empty(F_, C, N, dtype=S.dtype, device=S.device)
     ws = _ws(F_ * N * n_out * S.element_size(), S)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = _lib.load().vvt_vt_mat_prod_linear(
             _p(out), _p(S), _p(Z), _p(M), F_, C, N, n_out, n_in, _p(ws), ws.numel(),
             _dt(S), _stream(S),
@@ -591,7 +612,7 @@ def scale_rows_rsqrt(E: Tensor, norm2: Tensor) -> Tensor:
     K = E.shape[0]
     if E.numel() == 0:
         return E
-    with torch.cuda.device(E.device):
+    with _on(E.device):
         st = _lib.load().vvt_scale_rows_rsqrt(
             _p(E), _p(norm2), K, E.numel() // K, _dt(E), _stream(E)
         )
@@ -612,7 +633,7 @@ def dirderiv_epilogue(
     if K == 0:
         return gammas, lambdas
     ws = _ws(R * K * G.element_size() + 4096 + _lib.load().vvt_gram_workspace_bytes(R, K, R, _dt(G)), G)
-    with torch.cuda.device(G.device):
+    with _on(G.device):
         st = _lib.load().vvt_dirderiv_epilogue(
             _p(gammas), _p(lambdas), _p(G), _p(X), _p(U), _p(evals), C, N_ggn, n_g, K, N,
             _p(ws), ws.numel(), _dt(G), _stream(G),
@@ -631,7 +652,7 @@ def newton_coeff(
     v = torch.zeros(R, dtype=U.dtype, device=U.device)
     if K == 0:
         return v
-    with torch.cuda.device(U.device):
+    with _on(U.device):
         st = _lib.load().vvt_newton_coeff(
             _p(v), _p(U), _p(gammas), _p(lambdas), _p(deltas), _p(evals), R, K,
             gammas.shape[0], lambdas.shape[0], float(corr), _dt(U), _stream(U),
@@ -646,7 +667,7 @@ def v_apply_dense(v: Tensor, V: Tensor) -> Tensor:
     _chk(v, V)
     R, D = V.shape
     step = torch.empty(D, dtype=V.dtype, device=V.device)
-    with torch.cuda.device(V.device):
+    with _on(V.device):
         st = _lib.load().vvt_v_apply_dense(_p(step), _p(v), _p(V), R, D, _dt(V), _stream(V))
     _lib.check(st, "vvt_v_apply_dense")
     return step
@@ -660,7 +681,7 @@ def v_apply_linear(v: Tensor, S: Tensor, Z: Tensor) -> Tensor:
     n_in = Z.shape[1]
     step = torch.empty(n_out, n_in, dtype=S.dtype, device=S.device)
     ws = _ws(N * n_out * S.element_size(), S)
-    with torch.cuda.device(S.device):
+    with _on(S.device):
         st = _lib.load().vvt_v_apply_linear(
             _p(step), _p(None), _p(v), _p(S), _p(Z), C, N, n_out, n_in, _p(ws), ws.numel(),
             _dt(S), _stream(S),
