@@ -337,7 +337,8 @@ def test_step_leaves_no_garbage():
 
 @pytest.mark.parametrize("grouping", GROUPINGS, ids=GROUPING_IDS)
 def test_shared_solve_queue_gives_the_immediate_results(grouping, monkeypatch):
-    """``EighComputation`` and ``DirectionalDerivativesComputation`` on ONE ``SolveQueue``: two backward passes,
+    """``EighComputation``, ``DirectionalDerivativesComputation`` and ``DirectionalDampedNewtonComputation`` on ONE
+    ``SolveQueue``: three backward passes,
     nothing decomposed until the first ``get_result``, then one batched call per matrix shape -- and the results
     of the immediate order (``eigh.py:248``, ``directional_derivatives.py:291``)."""
     import vivit_b200 as vv
@@ -351,24 +352,26 @@ def test_shared_solve_queue_gives_the_immediate_results(grouping, monkeypatch):
 
     def both(queue):
         model, loss_fn, x, y = problem.make()
-        groups = grouping(model, criterion=keep_nonzero)
+        groups = grouping(model, criterion=keep_nonzero, damping=constant_damping(1.0))
         kw = {} if queue is None else {"solve_queue": queue}
         eigh, dirs = vv.EighComputation(**kw), vv.DirectionalDerivativesComputation(**kw)
+        newton = vv.DirectionalDampedNewtonComputation(**kw)
         run_backward(model, loss_fn, x, y, [eigh.get_extension()], eigh.get_extension_hook(groups))
         run_backward(model, loss_fn, x, y, dirs.get_extensions(), dirs.get_extension_hook(groups))
+        run_backward(model, loss_fn, x, y, newton.get_extensions(), newton.get_extension_hook(groups))
         if queue is not None:
-            assert len(queue) == 2 * len(groups) and not calls
-        return [(eigh.get_result(g), dirs.get_result(g)) for g in groups]
+            assert len(queue) == 3 * len(groups) and not calls
+        return [(eigh.get_result(g), dirs.get_result(g), newton.get_result(g)) for g in groups]
 
     want = both(None)
     del calls[:]
     got = both(vv.SolveQueue())
-    assert sum(calls) == 2 * len(want) and len(calls) < sum(calls)  # batched
-    for ((ev0, vecs0), (g0, l0)), ((ev1, vecs1), (g1, l1)) in zip(want, got):
+    assert sum(calls) == 3 * len(want) and len(calls) < sum(calls)  # batched
+    for ((ev0, vecs0), (g0, l0), s0), ((ev1, vecs1), (g1, l1), s1) in zip(want, got):
         close(ev0, ev1)
         close(g0, g1)
         close(l0, l1)
-        for a, b in zip(vecs0, vecs1):
+        for a, b in zip(list(vecs0) + list(s0), list(vecs1) + list(s1)):
             close(a, b)
 
 

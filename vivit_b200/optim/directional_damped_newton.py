@@ -2,6 +2,7 @@
 
 from __future__ import annotations
 
+import math
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -11,6 +12,7 @@ from torch.nn import Module
 from vivit_b200 import kernels
 from vivit_b200.backprop.extensions import BatchGrad
 from vivit_b200.linalg.eigvalsh import _make_dist
+from vivit_b200.linalg.solve_queue import SolveQueue
 from vivit_b200.linalg.utils import get_hook_store_batch_size
 from vivit_b200.optim.directional_derivatives import DirectionalDerivativesComputation as _DD
 from vivit_b200.optim.utils import get_sqrt_ggn_extension
@@ -33,8 +35,13 @@ class DirectionalDampedNewtonComputation:
         warn_small_eigvals: float = 1e-4,
         process_group=None,
         gather: bool = False,
+        solve_queue: Optional[SolveQueue] = None,
     ):
+        """``solve_queue`` (not in the reference): a ``SolveQueue`` shared with other Computations; the group's Gram
+        matrix is decomposed, together with everything else in the queue, when the first result is asked for
+        (``linalg/solve_queue.py``).  The group's factors stay alive until then (the step applies ``V``)."""
         check_subsampling_unique(subsampling_grad)
+        self._queue = solve_queue
         check_subsampling_unique(subsampling_ggn)
         self._mc_samples_ggn = mc_samples_ggn
         if self._mc_samples_ggn != 0:
@@ -55,6 +62,8 @@ class DirectionalDampedNewtonComputation:
     def get_result(self, group: Dict) -> Tuple[Tensor]:
         """Damped Newton step in the format of ``group['params']``
         (``directional_damped_newton.py:101-120``)."""
+        if id(group) not in self._newton_steps and self._queue is not None:
+            self._queue.flush()
         try:
             return self._newton_steps[id(group)]
         except KeyError as e:
@@ -90,7 +99,7 @@ class DirectionalDampedNewtonComputation:
             param_computation,
             lambda hook, accumulation, group: self._group_hook(
                 hook, accumulation, group, self._batch_size, factors, self._newton_steps,
-                self._verbose, self._warn_small_eigvals, self._dist, self._gather,
+                self._verbose, self._warn_small_eigvals, self._dist, self._gather, self._queue,
             ),
             lambda hook, existing, update: _DD._accumulate(hook, existing, update, self._verbose),
         )
@@ -109,25 +118,35 @@ class DirectionalDampedNewtonComputation:
 
     @staticmethod
     def _group_hook(hook, accumulation, group, batch_size, factors, newton_steps, verbose,
-                    warn_small_eigvals, dist, gather):
+                    warn_small_eigvals, dist, gather, queue=None):
         """Directions, directional derivatives, dampings, coefficients in Gram space, then one
         application of ``V`` per parameter (``directional_damped_newton.py:263-379``)."""
         gid = id(group)
         N = batch_size.pop(gid)
-        evals, evecs, gammas, lambdas, corr, C, N_ggn = _DD._directions(
-            accumulation, group, N, verbose, warn_small_eigvals, dist
-        )
-        deltas = group["damping"](evals, evecs, gammas, lambdas)  # :353
-        deltas = torch.as_tensor(deltas, dtype=evals.dtype, device=evals.device).reshape(-1)
-        # coefficients, weighting in Gram space and the V_correction rescale (:354-366)
-        v = kernels.newton_coeff(evecs, gammas, lambdas, deltas, evals, corr)
-        steps = []
-        for param in group["params"]:  # :368-377
-            step = factors.pop(id(param)).v_apply(v)
-            if gather:
-                step = dist.allgather_dim0(step[None], param.shape[0])[0]
-            steps.append(step)
-        newton_steps[gid] = steps
+        acc, gram, corr2 = _DD._gram_space(accumulation, N, dist)
+
+        def finish(evals, evecs):
+            evals, evecs, gammas, lambdas = _DD._filter_and_evaluate(
+                acc, evals, evecs, group, N, verbose, warn_small_eigvals
+            )
+            deltas = group["damping"](evals, evecs, gammas, lambdas)  # :353
+            deltas = torch.as_tensor(deltas, dtype=evals.dtype, device=evals.device).reshape(-1)
+            # coefficients, weighting in Gram space and the V_correction rescale (:354-366)
+            v = kernels.newton_coeff(evecs, gammas, lambdas, deltas, evals, math.sqrt(corr2))
+            steps = []
+            for param in group["params"]:  # :368-377
+                step = factors.pop(id(param)).v_apply(v)
+                if gather:
+                    step = dist.allgather_dim0(step[None], param.shape[0])[0]
+                steps.append(step)
+            newton_steps[gid] = steps
+
+        if queue is not None:
+            queue.submit(gram, finish)
+            return
+        if verbose:
+            print(f"Group {gid}: Eigen-decompose Gram matrix")
+        finish(*kernels.syevj(gram, vectors=True))  # :315
 
     @staticmethod
     def _check_param_groups(param_groups: List[Dict]) -> None:
