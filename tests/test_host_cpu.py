@@ -180,7 +180,7 @@ def test_hook_fires_group_when_last_param_arrives():
     x, y = torch.rand(4, 5, dtype=torch.float64), torch.randint(0, 3, (4,))
     layers = [model[0], model[2]]
     groups = [{"params": list(l.parameters())} for l in layers]
-    comp = EigvalshComputation()
+    comp = EigvalshComputation(batch_solves=False)  # the reference's order: decompose inside every group's hook
     hook = comp.get_extension_hook(groups)
     seen = []
 
@@ -397,3 +397,36 @@ def test_solve_queue_keeps_the_other_results_when_a_callback_raises():
     assert gammas.shape[1] == lambdas.shape[1] > 0
     with pytest.raises(KeyError):
         eigh.get_result(bad[0])
+
+
+def test_solve_queue_buckets_by_shape_and_by_vectors():
+    """Matrices of different sizes, and eigenvalue-only requests (``EigvalshComputation``), share a queue but not a
+    batched call; every Computation gets the results of its immediate order."""
+    import vivit_b200 as vv
+    from vivit_b200 import kernels
+
+    queue = vv.SolveQueue()
+    done = {}
+    g = torch.Generator().manual_seed(0)
+    mats = []
+    for i, n in enumerate((5, 7, 5, 5)):
+        a = torch.randn(n, n + 2, generator=g, dtype=torch.float64)
+        mats.append(a @ a.t())
+    for i, m in enumerate(mats):
+        queue.submit(m, lambda ev, vec, i=i: done.__setitem__(i, (ev, vec)), vectors=i != 3)
+    assert len(queue) == 4
+    queue.flush()
+    assert len(queue) == 0 and sorted(done) == [0, 1, 2, 3]
+    for i, m in enumerate(mats):
+        ev, vec = done[i]
+        close(ev, torch.linalg.eigvalsh(m), rtol=1e-8, atol=1e-10)
+        assert (vec is None) == (i == 3)
+
+    model, loss_fn, x, y = PROBLEMS[0].make()
+    groups = GROUPINGS[1](model, criterion=keep_nonzero)
+    plain, queued = vv.EigvalshComputation(), vv.EigvalshComputation(solve_queue=queue)
+    run_backward(model, loss_fn, x, y, [plain.get_extension()], plain.get_extension_hook(groups))
+    run_backward(model, loss_fn, x, y, [queued.get_extension()], queued.get_extension_hook(groups))
+    assert len(queue) == len(groups)
+    for grp in groups:
+        close(queued.get_result(grp), plain.get_result(grp))

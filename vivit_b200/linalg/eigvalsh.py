@@ -10,6 +10,7 @@ from torch.nn import Module, Parameter
 
 from vivit_b200 import kernels
 from vivit_b200.factors import fold_linear_bias
+from vivit_b200.linalg.solve_queue import SolveQueue
 from vivit_b200.linalg.utils import get_hook_store_batch_size, get_vivit_extension
 from vivit_b200.utils import delete_savefield
 from vivit_b200.utils.checks import check_key_exists, check_subsampling_unique, check_unique_params
@@ -26,12 +27,20 @@ class EigvalshComputation:
         mc_samples: int = 0,
         verbose: bool = False,
         process_group=None,
+        batch_solves: bool = True,
+        solve_queue: Optional[SolveQueue] = None,
     ):
+        """``batch_solves`` / ``solve_queue`` (not in the reference) as for ``EighComputation``: the Gram matrices of
+        several block-diagonal groups are decomposed by one batched call once the last group has fired, or -- with
+        a shared ``SolveQueue`` -- together with those of other Computations when the first result is read."""
         check_subsampling_unique(subsampling)
         self._subsampling = subsampling
         self._mc_samples = mc_samples
         self._verbose = verbose
         self._dist = _make_dist(process_group)
+        self._batch_solves = batch_solves
+        self._shared_queue = solve_queue
+        self._queue = solve_queue if solve_queue is not None else SolveQueue()
         self._savefield = self.get_extension().savefield
         self._mc_state = None  # tests may pin the MC draw
         # filled during the backward pass, keys are group ids
@@ -40,6 +49,8 @@ class EigvalshComputation:
 
     def get_result(self, group: Dict) -> Tensor:
         """Ascending Gram eigenvalues of the group's GGN block (``eigvalsh.py:53-68``)."""
+        if id(group) not in self._evals and len(self._queue):
+            self._queue.flush()
         try:
             return self._evals[id(group)]
         except KeyError as e:
@@ -63,6 +74,10 @@ class EigvalshComputation:
         )
         savefield, verbose = self._savefield, self._verbose
         subsampling, batch_sizes, evals, dist = self._subsampling, self._batch_size, self._evals, self._dist
+        queue, shared = self._queue, self._shared_queue is not None
+        batch, fired = self._batch_solves and len(param_groups) > 1, []
+        if not shared:
+            queue.clear()  # leftovers of a backward pass that did not reach its last group
 
         def param_computation(hook: ParameterGroupsHook, param: Parameter):
             # eager: evaluate this parameter's Gram and drop its factor (eigvalsh.py:145-158)
@@ -86,10 +101,17 @@ class EigvalshComputation:
             gram = accumulation if isinstance(accumulation, Tensor) else _accumulate_gram(None, accumulation)
             # eigvalsh.py:218-219; over several ranks the rescale rides on the all-reduce of the partial Grams
             dist.scale_allreduce_(1.0 if subsampling is None else batch_size / len(subsampling), gram)
-            gram_evals, _ = kernels.syevj(gram, vectors=False)  # eigvalsh.py:221
-            if verbose:
-                print(f"Group {gid}: Store 'gram_evals'")
-            evals[gid] = gram_evals
+
+            def store(gram_evals, _):
+                if verbose:
+                    print(f"Group {gid}: Store 'gram_evals'")
+                evals[gid] = gram_evals
+
+            queue.submit(gram, store, vectors=False)  # eigvalsh.py:221
+            fired.append(gid)
+            if not shared and (not batch or len(fired) == len(param_groups)):
+                del fired[:]
+                queue.flush()
 
         hook = ParameterGroupsHook.from_functions(param_groups, param_computation, group_hook, accumulate)
 

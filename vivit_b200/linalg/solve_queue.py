@@ -24,7 +24,7 @@ independently); what changes is when they exist and that a group's factors stay 
 
 from __future__ import annotations
 
-from typing import Callable, List, Tuple
+from typing import Callable, List, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -36,7 +36,7 @@ class SolveQueue:
     """Symmetric eigenproblems waiting for one batched solve."""
 
     def __init__(self) -> None:
-        self._items: List[Tuple[Tensor, Callable[[Tensor, Tensor], None]]] = []
+        self._items: List[Tuple[Tensor, Callable[[Tensor, Optional[Tensor]], None], bool]] = []
 
     def __len__(self) -> int:
         return len(self._items)
@@ -45,32 +45,34 @@ class SolveQueue:
         """Forget what was submitted (without solving)."""
         self._items = []
 
-    def submit(self, gram: Tensor, done: Callable[[Tensor, Tensor], None]) -> None:
+    def submit(self, gram: Tensor, done: Callable[[Tensor, Optional[Tensor]], None], vectors: bool = True) -> None:
         """``done(evals, evecs)`` is called by ``flush`` with the ascending eigenvalues ``[R]`` and the
-        eigenvectors ``[R, R]`` (columns) of ``gram``.  ``gram`` must not be modified until then."""
-        self._items.append((gram, done))
+        eigenvectors ``[R, R]`` (columns; ``None`` with ``vectors=False``) of ``gram``.  ``gram`` must not be
+        modified until then."""
+        self._items.append((gram, done, vectors))
 
     def flush(self) -> None:
-        """Decompose everything submitted so far -- matrices of one shape, dtype and device in one batched call --
+        """Decompose everything submitted so far -- matrices of one shape, dtype and device (and one kind of request: with or without eigenvectors) in one batched
+        call --
         and run the callbacks in submission order."""
         items, self._items = self._items, []
         if not items:
             return
         solved: List = [None] * len(items)
         buckets = {}
-        for i, (gram, _) in enumerate(items):
-            buckets.setdefault((tuple(gram.shape), gram.dtype, gram.device), []).append(i)
-        for members in buckets.values():
+        for i, (gram, _, vectors) in enumerate(items):
+            buckets.setdefault((tuple(gram.shape), gram.dtype, gram.device, vectors), []).append(i)
+        for (_, _, _, vectors), members in buckets.items():
             if len(members) == 1:
-                solved[members[0]] = kernels.syevj(items[members[0]][0], vectors=True)
+                solved[members[0]] = kernels.syevj(items[members[0]][0], vectors=vectors)
                 continue
-            evals, evecs = kernels.syevj_batched(torch.stack([items[i][0] for i in members]), vectors=True)
+            evals, evecs = kernels.syevj_batched(torch.stack([items[i][0] for i in members]), vectors=vectors)
             for slot, i in enumerate(members):
-                solved[i] = (evals[slot], evecs[slot])
+                solved[i] = (evals[slot], evecs[slot] if vectors else None)
         # every callback runs, also after one of them has raised (a criterion of one Computation must not cost the
         # others their results); the first exception is re-raised at the end
         failed = None
-        for (_, done), (evals, evecs) in zip(items, solved):
+        for (_, done, _), (evals, evecs) in zip(items, solved):
             try:
                 done(evals, evecs)
             except Exception as e:  # noqa: BLE001
