@@ -48,6 +48,15 @@ __host__ __device__ inline void wide_blocks(int nbw, int round, int pair, int& w
   }
 }
 
+// The three kernels of a round are launched with programmatic stream serialization: a kernel lets its successor be
+// scheduled at once (launch_dependents) and blocks in griddepcontrol.wait until its predecessor has completed and
+// flushed, so that the launch latency of a kernel (3 - 5 us, three per round, ~1100 rounds per solve at R = 5120)
+// hides behind the tail of the one before it.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 struct WideArgs {
   float* out;               // GRAM: partial sums [problem][split][pair][128][128];  APPLY: the factor
   const int* flag;          // APPLY: [problem][pair], 0 = the pair's Gram was already diagonal
@@ -85,6 +94,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
 wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapQ, WideArgs a) {
   using namespace tc;
   extern __shared__ unsigned char smem_raw[];
+  pdl_enter();
   const int prob = blockIdx.z;
   if (*reinterpret_cast<const volatile int*>(&a.sc[prob].converged)) return;  // uniform over the CTA
   const int pair = MODE == GRAM ? blockIdx.x : blockIdx.y;
@@ -345,6 +355,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
 wide_apply_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapQ, WideArgs a) {
   using namespace tc;
   extern __shared__ unsigned char smem_raw[];
+  pdl_enter();
   const int prob = blockIdx.y;
   if (*reinterpret_cast<const volatile int*>(&a.sc[prob].converged)) return;
   const int row_tiles = a.Np / BM, total = a.pairs * row_tiles;
@@ -867,6 +878,7 @@ wide_rot_cluster_kernel(float* Qt, int* flag, const float* part, int nbw, int ro
   extern __shared__ __align__(16) unsigned char wide_smem[];
   RotCta& sm = *reinterpret_cast<RotCta*>(wide_smem);
   cg::cluster_group cluster = cg::this_cluster();
+  pdl_enter();
   const int g = int(cluster.block_rank()), pair = blockIdx.x / CR, prob = blockIdx.y, tid = threadIdx.x;
   sc += prob;
   if (*reinterpret_cast<const volatile int*>(&sc->converged)) return;  // uniform over the cluster
@@ -1377,9 +1389,21 @@ static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, float
   static const bool cross_gram = getenv("VVT_WIDE_CROSS_GRAM") != nullptr;
   const int cross_only = !one_cta && cross_gram;
   a.cross_only = cross_only;
-  wide_tc_kernel<GRAM><<<dim3(unsigned(p.pairs), unsigned(p.splits), unsigned(batch)), tc::THREADS, tc::SMEM_BYTES, s>>>(
-      m.gram, m.q, a);
-  VVT_TRY(launched("vvt_syevj(wide gram)"));
+  static const bool pdl = getenv("VVT_WIDE_NOPDL") == nullptr;
+  cudaLaunchAttribute pdl_attr[2];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(p.pairs), unsigned(p.splits), unsigned(batch));
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+    cfg.stream = s;
+    cfg.attrs = pdl_attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, wide_tc_kernel<GRAM>, m.gram, m.q, a), "vvt_syevj(wide gram)"));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   if (one_cta) {
     wide_rot_kernel<<<dim3(unsigned(p.pairs), unsigned(batch)), RT, sizeof(WideRotSmem), s>>>(Qt, flag, part, p.nbw, round,
                                                                                               p.pairs, p.splits, sc);
@@ -1392,13 +1416,14 @@ static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, float
     cfg.blockDim = dim3(OT);
     cfg.dynamicSmemBytes = sizeof(RotCta);
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CR;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1] = pdl_attr[0];
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl ? 2 : 1;
     VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, wide_rot_cluster_kernel, Qt, flag, part, p.nbw, round, p.pairs, p.splits, sc,
                                           diag, cross_only),
                        "vvt_syevj(wide rot)"));
@@ -1414,7 +1439,16 @@ static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, float
     VVT_TRY(opt_p.ensure(wide_apply_kernel, AP_SMEM, "vvt_syevj(wide apply)"));
     const int64_t items = int64_t(p.pairs) * (p.Np / tc::BM);
     const unsigned ctas = unsigned(vmax<int64_t>(1, vmin<int64_t>(items, num_sms() / vmin<int64_t>(batch, num_sms()))));
-    wide_apply_kernel<<<dim3(ctas, unsigned(batch)), AP_THREADS, AP_SMEM, s>>>(m.apply, m.q, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas, unsigned(batch));
+    cfg.blockDim = dim3(AP_THREADS);
+    cfg.dynamicSmemBytes = AP_SMEM;
+    cfg.stream = s;
+    cfg.attrs = pdl_attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, wide_apply_kernel, m.apply, m.q, a), "vvt_syevj(wide apply)"));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return VVT_OK;
   }
   VVT_TRY(launched("vvt_syevj(wide apply)"));
   return VVT_OK;
