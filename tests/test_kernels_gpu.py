@@ -331,6 +331,25 @@ def test_syevj_two_level(k, R, rank, monkeypatch):
     assert orth <= 1e-4 and resid <= 5e-5, (orth, resid, info)
 
 
+@pytest.mark.parametrize("R", [1279, 2047, 4607])
+def test_syevj_sizes_that_are_not_a_multiple_of_four(k, R):
+    """Row pitches that are not a multiple of 16 bytes keep the GEMMs of the refinement step off the TMA-fed tcgen05
+    kernel (they run on ``mma.sync``, whose tensor-core accumulation is not promoted to round-to-nearest adds): the
+    eigenvalue error is 3-6x that of the neighbouring aligned size (3.5e-5 against 6e-6 of the largest eigenvalue at
+    R = 4607 / 4608) and stays inside the north star's 1e-4.  R = 4607 also runs the two-level rounds on a padded
+    panel (4608 columns)."""
+    G = _psd(R, int(0.8 * R), torch.float32, seed=R)
+    evals, evecs, info = k.syevj(G, True, return_info=True)
+    assert info["converged"], info
+    want = torch.linalg.eigvalsh(G.double())
+    assert (evals.double() - want).abs().max() <= 1e-4 * want.abs().max()
+    U = evecs.double()
+    eye = torch.eye(R, dtype=torch.float64, device=dev())
+    orth = (U.t() @ U - eye).abs().max().item()
+    resid = (G.double() @ U - U * evals.double()[None]).norm().item() / G.double().norm().item()
+    assert orth <= 1e-3 and resid <= 1e-4, (orth, resid, info)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("B,R", [(1, 33), (3, 64), (4, 320), (7, 100), (2, 1280)])
 def test_syevj_batched(k, dtype, B, R):
