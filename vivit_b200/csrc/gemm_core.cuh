@@ -375,6 +375,11 @@ inline GemmPlan plan_gemm(int64_t M, int64_t N, int64_t K, bool symmetric, int64
   if (batch == 1) {
     const int64_t want = ceil_div(2 * int64_t(num_sms()), p.tiles);
     splits = min(want, vmax<int64_t>(1, ksteps / 4));
+    // fp32: an mma.sync accumulator is updated with truncation, a bias that grows with the length of the
+    // contraction (3.5e-5 of the largest eigenvalue through the refinement GEMMs of an R = 4607 solve); slabs of at
+    // most 2048 are summed with round-to-nearest adds by the reduction kernel, as the tcgen05 kernel promotes its
+    // accumulator groups
+    if (sizeof(T) == 4) splits = vmax<int64_t>(splits, ceil_div(K, 2048));
     splits = vmin<int64_t>(splits, 64);
     const int64_t fit = workspace_bytes / vmax<int64_t>(1, M * N * int64_t(sizeof(T)));
     splits = vmax<int64_t>(1, min(splits, fit));
