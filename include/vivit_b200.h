@@ -253,6 +253,22 @@ int vvt_syevj(void* evals, void* evecs, const void* G, int64_t R, int jobz, void
 int vvt_syevj_batched(void* evals, void* evecs, const void* G, int64_t R, int64_t batch, int jobz,
                       void* workspace, int64_t workspace_bytes, int* info_host, int dtype, void* stream);
 
+/* The same solve with the ROUNDS of the two-level path distributed over the ranks of an NCCL communicator (the
+ * GPUs of one box): every rank passes the same G (the all-reduced Gram of the parameter-sharded path, SURVEY 8e:
+ * the full-network Gram of one group, R = C * N = 10240 at config 5) and receives the same evals / evecs.  The
+ * block pairs of a round are independent, so rank g works on a contiguous slice of the pair index; between two
+ * rounds of the round-robin tournament a rank hands one 64-column block to each neighbour (grouped ncclSend /
+ * ncclRecv between the block slots of the factor, on `stream`), the sweep's rotation count is summed with an
+ * 8-byte all-reduce so that every rank takes the same convergence decision, and the rotated factor is put
+ * together again by one all-reduce before the (replicated) Rayleigh quotients and refinement step.  Problems off
+ * the two-level path (fp64, R < 4096) are solved by every rank for itself -- same results, no exchange.
+ * comm: an ncclComm_t of the NCCL instance already loaded in the process (as vvt_nccl_allreduce_gram); rank and
+ * size are read from it.  Collective: every rank of the communicator must call it, with the same R / jobz / dtype.
+ * Not in the reference (single process); it replaces the same Tensor.symeig call sites as vvt_syevj. */
+int64_t vvt_syevj_dist_workspace_bytes(int64_t R, int jobz, int dtype, int world);
+int vvt_syevj_dist(void* comm, void* evals, void* evecs, const void* G, int64_t R, int jobz, void* workspace,
+                   int64_t workspace_bytes, int* info_host, int dtype, void* stream);
+
 /* TEST HOOK, not a reference interface: ONE round of the two-level solver used for fp32 problems of 4096
  * columns and more, on a caller-provided row-major factor L [Np, Np] (Np a multiple of 128), so that the three
  * kernels of a round (tcgen05 pair Grams with MN-major operands, 128 x 128 rotation kernel, tcgen05 apply) can

@@ -25,6 +25,45 @@ def run(comp, model, x, y, groups):
     return [comp.get_result(g) for g in groups]
 
 
+def check_distributed_solver(dev, sr):
+    """``vvt_syevj_dist``: the rounds of the two-level eigensolver distributed over the ranks against the same
+    solver on one GPU and against float64 LAPACK-style truth (``torch.linalg.eigvalsh`` in double).  The two-level
+    path is forced on small matrices (``VVT_SYEVJ_WIDE_MIN``); 1088 columns give nine block pairs per round, an
+    uneven split over two ranks."""
+    from vivit_b200 import kernels
+
+    os.environ["VVT_SYEVJ_WIDE_MIN"] = "512"
+    try:
+        comm = sr.solver_comm(torch.empty(2048, 2048, device=dev))
+        assert comm != 0
+        for R in (1024, 1088, 2048):
+            gen = torch.Generator(device="cpu").manual_seed(R)
+            rank = int(0.8 * R)
+            B = torch.randn(R, rank, dtype=torch.float64, generator=gen) * torch.logspace(0, -3, rank, dtype=torch.float64)
+            G = (B @ B.t()).float().to(dev)
+            ev1, U1, info1 = kernels.syevj(G, True, return_info=True)
+            evd, Ud, infod = kernels.syevj_dist(comm, sr.world, G, True, return_info=True)
+            assert info1["converged"] and infod["converged"], (R, info1, infod)
+            want = torch.linalg.eigvalsh(G.double())
+            scale = want.abs().max()
+            assert (evd.double() - want).abs().max() <= 1e-5 * scale, (R, (evd.double() - want).abs().max() / scale)
+            assert (evd - ev1).abs().max() <= 1e-5 * scale
+            Q = Ud.double()
+            eye = torch.eye(R, dtype=torch.float64, device=dev)
+            assert (Q.t() @ Q - eye).abs().max() < 5e-4, (R, (Q.t() @ Q - eye).abs().max())
+            resid = (G.double() @ Q - Q * evd.double()[None]).norm() / G.double().norm()
+            assert resid < 5e-5, (R, resid)
+            # every rank holds the same eigenpairs, bit for bit
+            both = [torch.empty_like(Ud) for _ in range(sr.world)]
+            dist.all_gather(both, Ud.contiguous())
+            assert all(torch.equal(both[0], t) for t in both), R
+            # eigenvalues only
+            ev0, none, _ = kernels.syevj_dist(comm, sr.world, G, False, return_info=True)
+            assert none is None and (ev0 - evd).abs().max() <= 1e-6 * scale
+    finally:
+        del os.environ["VVT_SYEVJ_WIDE_MIN"]
+
+
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -60,6 +99,7 @@ def main():
     gathered = [torch.empty_like(evs) for _ in range(dist.get_world_size())]
     dist.all_gather(gathered, evs.contiguous())
     assert all(torch.equal(gathered[0], t) for t in gathered)
+    check_distributed_solver(dev, sr)
     dist.barrier()
     dist.destroy_process_group()
     if local == 0:

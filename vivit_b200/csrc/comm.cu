@@ -7,58 +7,7 @@
 // NCCL is not linked: the communicator belongs to the caller (torch.distributed's ProcessGroupNCCL hands out
 // its ncclComm_t), so the calls must go to the NCCL instance that is already loaded in the process.  It is
 // looked up with dlopen(RTLD_NOLOAD); without it the entry point reports VVT_ERR_UNSUPPORTED.
-#include <dlfcn.h>
-
-#include "common.cuh"
-
-namespace vvt {
-namespace {
-
-typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-typedef int (*PreMulFn)(int*, void*, int, int, void*);
-typedef int (*OpDestroyFn)(int, void*);
-typedef int (*GroupFn)(void);
-typedef const char* (*ErrStrFn)(int);
-
-struct Nccl {
-  AllReduceFn all_reduce = nullptr;
-  PreMulFn premul = nullptr;
-  OpDestroyFn op_destroy = nullptr;
-  GroupFn group_start = nullptr, group_end = nullptr;
-  ErrStrFn err = nullptr;
-  bool ok = false;
-};
-
-const Nccl& nccl() {
-  static Nccl n = [] {
-    Nccl r;
-    void* h = nullptr;
-    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-      h = dlopen(name, RTLD_LAZY | RTLD_NOLOAD);
-      if (h) break;
-    }
-    if (!h) return r;
-    r.all_reduce = reinterpret_cast<AllReduceFn>(dlsym(h, "ncclAllReduce"));
-    r.premul = reinterpret_cast<PreMulFn>(dlsym(h, "ncclRedOpCreatePreMulSum"));
-    r.op_destroy = reinterpret_cast<OpDestroyFn>(dlsym(h, "ncclRedOpDestroy"));
-    r.group_start = reinterpret_cast<GroupFn>(dlsym(h, "ncclGroupStart"));
-    r.group_end = reinterpret_cast<GroupFn>(dlsym(h, "ncclGroupEnd"));
-    r.err = reinterpret_cast<ErrStrFn>(dlsym(h, "ncclGetErrorString"));
-    r.ok = r.all_reduce && r.premul && r.op_destroy && r.group_start && r.group_end;
-    return r;
-  }();
-  return n;
-}
-
-constexpr int kNcclSum = 0, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclScalarHostImmediate = 1;
-
-int check_nccl(int status, const char* where) {
-  if (status == 0) return VVT_OK;
-  return fail(VVT_ERR_CUDA, "%s: NCCL: %s", where, nccl().err ? nccl().err(status) : "error");
-}
-
-}  // namespace
-}  // namespace vvt
+#include "nccl_dyn.cuh"
 
 using namespace vvt;
 

@@ -33,7 +33,10 @@
 #include <chrono>
 #include <cstdlib>
 
+#include <vector>
+
 #include "gemm_core.cuh"
+#include "nccl_dyn.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -1366,12 +1369,12 @@ struct JacobiLayout {
       off_dc, off_done, off_state, off_gemm, gemm_bytes, total;
 };
 
-static JacobiLayout jacobi_layout(int64_t R, int64_t B, int64_t es, int dtype) {
+static JacobiLayout jacobi_layout(int64_t R, int64_t B, int64_t es, int dtype, int world = 1) {
   JacobiLayout L;
   L.Np = align_up(R, OP);
   L.nb = L.Np / OB;
   L.wide = wide_enabled(R, dtype);
-  L.wp = wide::wide_plan(R, B);
+  L.wp = wide::wide_plan(R, B, world);
   L.y_elems = L.nb * 2 * L.Np * OB;
   if (L.wide) L.y_elems = vmax<int64_t>(L.y_elems, int64_t(L.wp.Np) * L.wp.Np);
   int64_t o = 0;
@@ -1524,10 +1527,65 @@ static int host_state(HostState** out) {
   return VVT_OK;
 }
 
+// Distributed two-level rounds (vvt_syevj_dist): the pairs of a wide round are independent -- disjoint column blocks
+// -- so rank g of `world` takes the contiguous slice [pairs g / world, pairs (g + 1) / world) of the pair index and
+// runs the three kernels of the round on it.  In the round-robin tournament pair i of round r + 1 takes its first
+// block from pair i + 1 and its second from pair i - 1 of round r, so between two cross rounds a rank hands ONE block
+// to each neighbour (Np x 64 floats, 2.6 MB at R = 10240) and receives one from each: grouped ncclSend / ncclRecv
+// straight between the block slots of the factor, on the compute stream.  The intra round of a sweep pairs blocks
+// (2i, 2i + 1): a general permutation, once per sweep.  `owner[w]` is the rank that holds the valid copy of wide block
+// w (-1: every rank, the replicated state after the Cholesky factor); all ranks compute the same transfer lists.
+struct DistCtx {
+  void* comm;
+  int rank, world;
+};
+
+static int dist_exchange(float* Lw, const wide::WidePlan& p, int round, const DistCtx& d, std::vector<int>& owner,
+                         cudaStream_t s) {
+  const Nccl& n = nccl();
+  const size_t blk = size_t(p.Np) * wide::WB;
+  bool open = false;
+  int st = VVT_OK;
+  for (int pair = 0; pair < p.pairs && st == VVT_OK; ++pair) {
+    int w[2];
+    wide::wide_blocks(p.nbw, round, pair, w[0], w[1]);
+    int owner_rank = 0;
+    while (int64_t(p.pairs) * (owner_rank + 1) / d.world <= pair) ++owner_rank;  // pair in [lo, hi) of owner_rank
+    for (int k = 0; k < 2 && st == VVT_OK; ++k) {
+      const int src = owner[w[k]];
+      owner[w[k]] = owner_rank;
+      if (src < 0 || src == owner_rank || (d.rank != src && d.rank != owner_rank)) continue;
+      if (!open) {
+        st = check_nccl(n.group_start(), "vvt_syevj_dist");
+        open = true;
+        if (st != VVT_OK) break;
+      }
+      float* ptr = Lw + size_t(w[k]) * blk;
+      st = d.rank == src ? check_nccl(n.send(ptr, blk, kNcclFloat32, owner_rank, d.comm, s), "vvt_syevj_dist(send)")
+                         : check_nccl(n.recv(ptr, blk, kNcclFloat32, src, d.comm, s), "vvt_syevj_dist(recv)");
+    }
+  }
+  if (open) {
+    const int e = check_nccl(n.group_end(), "vvt_syevj_dist");
+    if (st == VVT_OK) st = e;
+  }
+  return st;
+}
+
 template <typename T>
 static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int jobz, char* ws, int* info, int dtype,
-                      cudaStream_t s) {
-  const JacobiLayout L = jacobi_layout(R, B, sizeof(T), dtype);
+                      cudaStream_t s, const DistCtx* dist_in = nullptr) {
+  const JacobiLayout L = jacobi_layout(R, B, sizeof(T), dtype, dist_in ? dist_in->world : 1);
+  // the rounds are distributed for one fp32 problem on the two-level path; anything else is solved by every rank
+  // for itself (identical results: the solver is deterministic)
+  const DistCtx* dist = dist_in && dist_in->world > 1 && L.wide && B == 1 && sizeof(T) == 4 ? dist_in : nullptr;
+  std::vector<int> owner;
+  int pair_lo = 0, pair_hi = L.wp.pairs;
+  if (dist) {
+    owner.assign(size_t(L.wp.nbw), -1);
+    pair_lo = int(int64_t(L.wp.pairs) * dist->rank / dist->world);
+    pair_hi = int(int64_t(L.wp.pairs) * (dist->rank + 1) / dist->world);
+  }
   T* Y = (T*)(ws + L.off_Y);
   T* Gs = (T*)(ws + L.off_Gs);
   T* Jm = (T*)(ws + L.off_Jm);
@@ -1595,6 +1653,17 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
     return vvt_gemm(C, A, Bm, M, N, K, 0, 0, lda, ldb, ldc, alpha, beta, B, RR, RR, RR, nullptr, 0, dtype, (void*)s);
   };
 
+  // VVT_SYEVJ_DEBUG: host time stamps behind stream drains (factor / sweeps / gather + refinement)
+  auto phase_clock = std::chrono::steady_clock::now();
+  auto phase = [&](const char* what) {
+    if (!debug) return;
+    cudaStreamSynchronize(s);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[vvt_syevj] R=%lld %s%s: %.2f ms\n", (long long)R, dist ? "distributed " : "", what,
+            std::chrono::duration<double, std::milli>(now - phase_clock).count());
+    phase_clock = now;
+  };
+  phase("start");
   onesided_sym_kernel<T><<<dim3(rr_blocks, UB), 256, 0, s>>>(Gs, G, R, sc);
   VVT_TRY(launched("vvt_syevj(sym)"));
   if (use_chol) {
@@ -1651,15 +1720,23 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
   wide::WideMaps maps;
   if (L.wide) VVT_TRY(wide::wide_make_maps(&maps, (const float*)Y, (const float*)Sm, L.wp, B));
 
+  phase("symmetrise, Cholesky factor, init");
   long long most_rotations = -1;  // over the unfinished problems, in the last sweep whose state has been read
   static const int share_div = getenv("VVT_SYEVJ_SHAREDIV") ? atoi(getenv("VVT_SYEVJ_SHAREDIV")) : 3;
   auto enqueue_sweep = [&](int sweep) -> int {
     const bool share_sms = share_div > 0 && most_rotations >= 0 && most_rotations * share_div < (nb16 / 2) * nb16;
     if (L.wide) {
       if constexpr (sizeof(T) == 4) {
-        for (int round = -1; round < L.wp.nbw - 1; ++round)
+        for (int round = -1; round < L.wp.nbw - 1; ++round) {
+          if (dist) VVT_TRY(dist_exchange((float*)Y, L.wp, round, *dist, owner, s));
           VVT_TRY(wide::wide_round((float*)Y, (float*)Tt, (float*)Sm, (int*)Mm, (float*)((char*)Mm + L.wp.flag_bytes), sc,
-                                   L.wp, maps, round, B, s));
+                                   L.wp, maps, round, B, s, pair_lo, pair_hi - pair_lo));
+        }
+        // the sweep's count of block pairs that rotated, summed over the ranks: sweep_end_kernel then takes the same
+        // decision everywhere (and the hosts, which read it, enqueue the same sweeps)
+        if (dist)
+          VVT_TRY(check_nccl(nccl().all_reduce(&sc->rotations, &sc->rotations, 1, kNcclUint64, kNcclSum, dist->comm, s),
+                             "vvt_syevj_dist(rotations)"));
       }
     } else if (persistent) {
       VVT_TRY(launch_sweep<T>(Y, Np, nb, CL, rows_per_cta, parts, sc, marks, sweep * nb + 1, (T*)(ws + L.off_dc),
@@ -1730,7 +1807,18 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
     }
   }
 
+  phase("sweeps");
   const int gblocks = int(vmin<int64_t>(ceil_div(RR, 256), 8 * num_sms()));
+  if (dist) {
+    // every rank gets the whole rotated factor back: blocks held elsewhere are zeroed, one all-reduce sums
+    // x + 0 + ... + 0 (exact), and from here on the ranks hold identical data again
+    const size_t blk = size_t(L.wp.Np) * wide::WB;
+    for (int w = 0; w < L.wp.nbw; ++w)
+      if (owner[size_t(w)] >= 0 && owner[size_t(w)] != dist->rank)
+        VVT_TRY(check_cuda(cudaMemsetAsync((float*)Y + size_t(w) * blk, 0, blk * sizeof(float), s), "vvt_syevj_dist"));
+    VVT_TRY(check_nccl(nccl().all_reduce(Y, Y, size_t(L.wp.nbw) * blk, kNcclFloat32, kNcclSum, dist->comm, s),
+                       "vvt_syevj_dist(gather)"));
+  }
   if (L.wide) {
     if constexpr (sizeof(T) == 4) {
       wide::wide_colnorm_kernel<<<dim3(unsigned(ceil_div(R, 32)), UB), 256, 0, s>>>((float*)cn, (const float*)Y, R, L.wp.Np);
@@ -1766,6 +1854,7 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
   const int pblocks = int(vmin<int64_t>(ceil_div(total, 256), 8 * num_sms()));
   jacobi_permute_kernel<T><<<dim3(pblocks, UB), 256, 0, s>>>(evals, jobz ? evecs : nullptr, ev, Jt, rank, R);
   VVT_TRY(launched("vvt_syevj(permute)"));
+  phase("gather, Rayleigh quotients, refinement, sort");
   return VVT_OK;
 }
 
@@ -1808,6 +1897,33 @@ int vvt_syevj_batched(void* evals, void* evecs, const void* G, int64_t R, int64_
 int vvt_syevj(void* evals, void* evecs, const void* G, int64_t R, int jobz, void* workspace,
               int64_t workspace_bytes, int* info_host, int dtype, void* stream) {
   return vvt_syevj_batched(evals, evecs, G, R, 1, jobz, workspace, workspace_bytes, info_host, dtype, stream);
+}
+
+int64_t vvt_syevj_dist_workspace_bytes(int64_t R, int jobz, int dtype, int world) {
+  (void)jobz;
+  if (R <= 0) return 0;
+  return jacobi_layout(R, 1, dtype == VVT_F32 ? 4 : 8, dtype, vmax(1, world)).total;
+}
+
+int vvt_syevj_dist(void* comm, void* evals, void* evecs, const void* G, int64_t R, int jobz, void* workspace,
+                   int64_t workspace_bytes, int* info_host, int dtype, void* stream) {
+  VVT_REQUIRE(R >= 0, "negative size");
+  VVT_REQUIRE(comm != nullptr, "null communicator");
+  if (info_host) info_host[0] = 0, info_host[1] = 1;
+  if (R == 0) return VVT_OK;
+  VVT_REQUIRE(R <= (int64_t(1) << 15), "matrix too large");
+  VVT_REQUIRE(evals && G && workspace && (!jobz || evecs), "null pointer");
+  const Nccl& n = nccl();
+  if (!n.ok) return fail(VVT_ERR_UNSUPPORTED, "%s: no NCCL library is loaded in this process", __func__);
+  DistCtx d{comm, 0, 1};
+  VVT_TRY(check_nccl(n.comm_count(comm, &d.world), __func__));
+  VVT_TRY(check_nccl(n.comm_rank(comm, &d.rank), __func__));
+  if (workspace_bytes < vvt_syevj_dist_workspace_bytes(R, jobz, dtype, d.world))
+    return fail(VVT_ERR_WORKSPACE, "%s: workspace too small", __func__);
+  VVT_DISPATCH(dtype, {
+    return syevj_impl<T>((T*)evals, jobz ? (T*)evecs : nullptr, (const T*)G, R, 1, jobz, (char*)workspace, info_host, dtype,
+                         as_stream(stream), &d);
+  });
 }
 
 // Test hook: ONE wide round of the two-level solver on a caller-provided

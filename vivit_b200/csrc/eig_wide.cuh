@@ -63,6 +63,8 @@ struct WideArgs {
   const JacobiScalars* sc;  // [problem]
   int64_t l_stride;         // elements between the factors of two problems
   int Np, nbw, round, pairs, splits, kblocks_total, kblocks_per_split;
+  int pair0, pairs_local;  // this launch covers pairs pair0 .. pair0 + pairs_local - 1 of the round (all of them on
+                           // one GPU; a rank's share when the pairs of a round are distributed, vvt_syevj_dist)
   int variant;  // experiments (VVT_WIDE_DESC): descriptor encodings of the MN-major Gram operands
   int cross_only;  // GRAM, cross rounds: only the 128 x 64 block H[:, b] (the diagonal block of a comes from a cache)
 };
@@ -97,7 +99,7 @@ wide_tc_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__
   pdl_enter();
   const int prob = blockIdx.z;
   if (*reinterpret_cast<const volatile int*>(&a.sc[prob].converged)) return;  // uniform over the CTA
-  const int pair = MODE == GRAM ? blockIdx.x : blockIdx.y;
+  const int pair = a.pair0 + int(MODE == GRAM ? blockIdx.x : blockIdx.y);
   const int split = MODE == GRAM ? blockIdx.y : 0;
   const int rtile = MODE == GRAM ? 0 : blockIdx.x;
   if (MODE == APPLY && a.flag[prob * a.pairs + pair] == 0) return;
@@ -358,9 +360,10 @@ wide_apply_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
   pdl_enter();
   const int prob = blockIdx.y;
   if (*reinterpret_cast<const volatile int*>(&a.sc[prob].converged)) return;
-  const int row_tiles = a.Np / BM, total = a.pairs * row_tiles;
-  const int per = (total + int(gridDim.x) - 1) / int(gridDim.x);
-  const int it0 = blockIdx.x * per, it1 = min(total, it0 + per);
+  // items are (pair, 128-row tile) with the pair index of the whole round; this launch owns pairs_local of them
+  const int row_tiles = a.Np / BM, first = a.pair0 * row_tiles, total = first + a.pairs_local * row_tiles;
+  const int per = (a.pairs_local * row_tiles + int(gridDim.x) - 1) / int(gridDim.x);
+  const int it0 = first + blockIdx.x * per, it1 = min(total, it0 + per);
   const int* flag = a.flag + prob * a.pairs;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -732,10 +735,11 @@ __device__ __noinline__ void update_rows(WideRotSmem& sm, int tid) {
 }
 
 __global__ void __launch_bounds__(RT, 1)
-wide_rot_kernel(float* Qt, int* flag, const float* part, int nbw, int round, int pairs, int splits, JacobiScalars* sc) {
+wide_rot_kernel(float* Qt, int* flag, const float* part, int nbw, int round, int pairs, int splits, JacobiScalars* sc,
+                int pair0) {
   extern __shared__ __align__(16) unsigned char wide_smem[];
   WideRotSmem& sm = *reinterpret_cast<WideRotSmem*>(wide_smem);
-  const int pair = blockIdx.x, prob = blockIdx.y, tid = threadIdx.x;
+  const int pair = pair0 + int(blockIdx.x), prob = blockIdx.y, tid = threadIdx.x;
   sc += prob;
   if (*reinterpret_cast<const volatile int*>(&sc->converged)) return;
   const bool intra_round = round < 0;
@@ -874,12 +878,12 @@ __device__ long long g_wdbg[16];
 
 __global__ void __launch_bounds__(OT, 2)
 wide_rot_cluster_kernel(float* Qt, int* flag, const float* part, int nbw, int round, int pairs, int splits,
-                        JacobiScalars* sc, float* diag, int cross_only) {
+                        JacobiScalars* sc, float* diag, int cross_only, int pair0) {
   extern __shared__ __align__(16) unsigned char wide_smem[];
   RotCta& sm = *reinterpret_cast<RotCta*>(wide_smem);
   cg::cluster_group cluster = cg::this_cluster();
   pdl_enter();
-  const int g = int(cluster.block_rank()), pair = blockIdx.x / CR, prob = blockIdx.y, tid = threadIdx.x;
+  const int g = int(cluster.block_rank()), pair = pair0 + int(blockIdx.x) / CR, prob = blockIdx.y, tid = threadIdx.x;
   sc += prob;
   if (*reinterpret_cast<const volatile int*>(&sc->converged)) return;  // uniform over the cluster
   const bool intra_round = round < 0;
@@ -1311,7 +1315,9 @@ struct WidePlan {
   int64_t part_bytes, q_bytes, flag_bytes, diag_bytes;  // diag: the diagonal-block cache, behind the flags
 };
 
-static inline WidePlan wide_plan(int64_t R, int64_t batch) {
+// `world` > 1: the pairs of a round are distributed over that many GPUs (vvt_syevj_dist); the split-K plan is the
+// one of a rank's share, the buffers stay indexed by the pair index of the whole round
+static inline WidePlan wide_plan(int64_t R, int64_t batch, int world = 1) {
   WidePlan p;
   p.Np = int(align_up(R, WP));
   p.nbw = p.Np / WB;
@@ -1320,7 +1326,7 @@ static inline WidePlan wide_plan(int64_t R, int64_t batch) {
   // split-K over the rows: one CTA per SM is resident, so the kernel runs in waves of num_sms CTAs; take the
   // split count (at least 4 k-blocks per CTA) that minimises waves x (k-blocks per CTA + prologue / epilogue)
   {
-    const int64_t sms = num_sms(), tiles = int64_t(p.pairs) * batch;
+    const int64_t sms = num_sms(), tiles = ceil_div(int64_t(p.pairs), int64_t(vmax(1, world))) * batch;
     int64_t best = 1, best_cost = INT64_MAX;
     for (int64_t sp = 1; sp <= vmax<int64_t>(1, p.kblocks / 4); ++sp) {
       const int64_t per = ceil_div(p.kblocks, sp);
@@ -1369,7 +1375,10 @@ static inline int wide_make_maps(WideMaps* m, const float* Lw, const float* Qt, 
 
 // one round (all pairs, all problems): Gram, rotations, apply
 static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, float* diag, JacobiScalars* sc, const WidePlan& p,
-                             const WideMaps& m, int round, int64_t batch, cudaStream_t s) {
+                             const WideMaps& m, int round, int64_t batch, cudaStream_t s, int pair0 = 0,
+                             int pairs_local = -1) {
+  if (pairs_local < 0) pairs_local = p.pairs;
+  if (pairs_local == 0) return VVT_OK;
   static SmemOptIn opt_g, opt_a, opt_r;
   VVT_TRY(opt_g.ensure(wide_tc_kernel<GRAM>, tc::SMEM_BYTES, "vvt_syevj(wide gram)"));
   VVT_TRY(opt_a.ensure(wide_tc_kernel<APPLY>, tc::SMEM_BYTES, "vvt_syevj(wide apply)"));
@@ -1380,6 +1389,7 @@ static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, float
   a.l_stride = int64_t(p.Np) * p.Np;
   a.Np = p.Np, a.nbw = p.nbw, a.round = round, a.pairs = p.pairs, a.splits = p.splits;
   a.kblocks_total = p.kblocks, a.kblocks_per_split = p.kblocks_per_split;
+  a.pair0 = pair0, a.pairs_local = pairs_local;
   a.variant = getenv("VVT_WIDE_DESC") ? atoi(getenv("VVT_WIDE_DESC")) : 0;
   a.out = part;
   static const bool one_cta = getenv("VVT_WIDE_ROT_ONE_CTA") != nullptr;  // experiments: the single-CTA kernel
@@ -1395,7 +1405,7 @@ static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, float
   pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
   {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(unsigned(p.pairs), unsigned(p.splits), unsigned(batch));
+    cfg.gridDim = dim3(unsigned(pairs_local), unsigned(p.splits), unsigned(batch));
     cfg.blockDim = dim3(tc::THREADS);
     cfg.dynamicSmemBytes = tc::SMEM_BYTES;
     cfg.stream = s;
@@ -1405,14 +1415,14 @@ static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, float
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   if (one_cta) {
-    wide_rot_kernel<<<dim3(unsigned(p.pairs), unsigned(batch)), RT, sizeof(WideRotSmem), s>>>(Qt, flag, part, p.nbw, round,
-                                                                                              p.pairs, p.splits, sc);
+    wide_rot_kernel<<<dim3(unsigned(pairs_local), unsigned(batch)), RT, sizeof(WideRotSmem), s>>>(Qt, flag, part, p.nbw, round,
+                                                                                                  p.pairs, p.splits, sc, pair0);
     VVT_TRY(launched("vvt_syevj(wide rot)"));
   } else {
     static SmemOptIn opt_c;
     VVT_TRY(opt_c.ensure(wide_rot_cluster_kernel, sizeof(RotCta), "vvt_syevj(wide rot)"));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(unsigned(p.pairs * CR), unsigned(batch));
+    cfg.gridDim = dim3(unsigned(pairs_local * CR), unsigned(batch));
     cfg.blockDim = dim3(OT);
     cfg.dynamicSmemBytes = sizeof(RotCta);
     cfg.stream = s;
@@ -1425,19 +1435,19 @@ static inline int wide_round(float* Lw, float* part, float* Qt, int* flag, float
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 2 : 1;
     VVT_TRY(check_cuda(cudaLaunchKernelEx(&cfg, wide_rot_cluster_kernel, Qt, flag, part, p.nbw, round, p.pairs, p.splits, sc,
-                                          diag, cross_only),
+                                          diag, cross_only, pair0),
                        "vvt_syevj(wide rot)"));
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   a.out = Lw;
   static const bool per_tile = getenv("VVT_WIDE_APPLY_PER_TILE") != nullptr;  // experiments: one CTA per output tile
   if (per_tile) {
-    wide_tc_kernel<APPLY><<<dim3(unsigned(p.Np / tc::BM), unsigned(p.pairs), unsigned(batch)), tc::THREADS, tc::SMEM_BYTES, s>>>(
+    wide_tc_kernel<APPLY><<<dim3(unsigned(p.Np / tc::BM), unsigned(pairs_local), unsigned(batch)), tc::THREADS, tc::SMEM_BYTES, s>>>(
         m.apply, m.q, a);
   } else {
     static SmemOptIn opt_p;
     VVT_TRY(opt_p.ensure(wide_apply_kernel, AP_SMEM, "vvt_syevj(wide apply)"));
-    const int64_t items = int64_t(p.pairs) * (p.Np / tc::BM);
+    const int64_t items = int64_t(pairs_local) * (p.Np / tc::BM);
     const unsigned ctas = unsigned(vmax<int64_t>(1, vmin<int64_t>(items, num_sms() / vmin<int64_t>(batch, num_sms()))));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas, unsigned(batch));

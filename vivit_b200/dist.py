@@ -60,6 +60,18 @@ class ShardedReduce:
             self._comm = ptr
         return self._comm
 
+    def solver_comm(self, gram: Tensor) -> int:
+        """``ncclComm_t`` for the distributed eigensolver rounds (``vvt_syevj_dist``), 0 = solve on every rank:
+        one process, not an NCCL group, or a problem off the two-level path (fp64, fewer than 4096 columns), which
+        every rank solves for itself anyway.  ``VVT_SYEVJ_DIST=0`` switches the distribution off."""
+        import os
+
+        if self.world == 1 or gram.dtype != torch.float32 or gram.shape[0] < int(os.environ.get("VVT_SYEVJ_WIDE_MIN", 4096)):
+            return 0
+        if os.environ.get("VVT_SYEVJ_DIST", "1") == "0":
+            return 0
+        return self._nccl_comm(gram)
+
     def scale_allreduce_(self, alpha: float, gram: Tensor, cross: Optional[Tensor] = None) -> None:
         """``gram`` (and ``cross``) ``<- alpha * sum over ranks`` in place: the partial-Gram exchange of the
         parameter-sharded path with the sub-sampling rescale of ``eigh.py:245-246`` folded in.  One process:

@@ -505,6 +505,35 @@ def syevj_batched(G: Tensor, vectors: bool = True, return_info: bool = False):
     return evals, evecs
 
 
+def syevj_dist(comm_ptr: int, world: int, G: Tensor, vectors: bool = True, return_info: bool = False):
+    """``syevj`` with the rounds of the two-level path distributed over the ranks of an NCCL communicator
+    (``vvt_syevj_dist``): every rank passes the same ``G [R, R]`` and gets the same results.  ``comm_ptr`` is the raw
+    ``ncclComm_t`` (``ProcessGroupNCCL._comm_ptr()``), ``world`` its size.  Collective call."""
+    G = _c(G)
+    _chk(G)
+    if G.dim() != 2 or G.shape[0] != G.shape[1]:
+        raise ValueError(f"expected [R, R], got {tuple(G.shape)}")
+    R = G.shape[0]
+    evals = torch.empty(R, dtype=G.dtype, device=G.device)
+    evecs = torch.empty(R, R, dtype=G.dtype, device=G.device) if vectors else None
+    info = (ctypes.c_int * 2)(0, 1)
+    if R > 0:
+        lib = _lib.load()
+        ws = _ws(lib.vvt_syevj_dist_workspace_bytes(R, int(vectors), _dt(G), int(world)), G)
+        with _on(G.device):
+            st = lib.vvt_syevj_dist(
+                ctypes.c_void_p(comm_ptr), _p(evals), _p(evecs), _p(G), R, int(vectors), _p(ws), ws.numel(), info,
+                _dt(G), _stream(G),
+            )
+        _lib.check(st, "vvt_syevj_dist")
+    result = {"sweeps": int(info[0]), "converged": bool(info[1])}
+    if return_info:
+        return evals, evecs, result
+    if not result["converged"]:
+        raise SyevjNotConverged(f"vvt_syevj_dist did not converge in {result['sweeps']} sweeps (R = {R})")
+    return evals, evecs
+
+
 def _syevj_batched(G: Tensor, vectors: bool, what: str):
     G = _c(G)
     _chk(G)
@@ -699,7 +728,7 @@ TIMED = [
     "sqrt_backprop_linear", "sqrt_backprop_conv2d", "sqrt_backprop_elementwise",
     "sqrt_backprop_maxpool2d", "sqrt_backprop_avgpool2d", "v_emit_conv2d", "v_emit_bias",
     "v_emit_linear", "gemm", "gram_dense_accum", "gram_cross_accum", "gram_linear_accum",
-    "gram_cross_linear_accum", "syevj", "syevj_batched", "filter_nonzero", "backtransform_dense",
+    "gram_cross_linear_accum", "syevj", "syevj_batched", "syevj_dist", "filter_nonzero", "backtransform_dense",
     "backtransform_linear", "vt_mat_prod_linear", "scale_rows_rsqrt", "dirderiv_epilogue",
     "newton_coeff", "v_apply_dense", "v_apply_linear", "center_rows",
 ]

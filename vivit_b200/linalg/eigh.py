@@ -125,7 +125,7 @@ class EighComputation:
             # eigh.py:245-246; over several ranks the rescale rides on the all-reduce of the partial Grams
             dist.scale_allreduce_(1.0 if subsampling is None else batch_size / len(subsampling), gram)
 
-            queue.submit(gram, lambda gram_evals, gram_evecs: finish(group, gram_evals, gram_evecs, factors))
+            queue.submit(gram, lambda gram_evals, gram_evecs: finish(group, gram_evals, gram_evecs, factors), dist=dist)
             fired.append(gid)
             if not shared and (not batch or len(fired) == len(param_groups)):
                 del fired[:]

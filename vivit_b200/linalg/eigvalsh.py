@@ -107,7 +107,7 @@ class EigvalshComputation:
                     print(f"Group {gid}: Store 'gram_evals'")
                 evals[gid] = gram_evals
 
-            queue.submit(gram, store, vectors=False)  # eigvalsh.py:221
+            queue.submit(gram, store, vectors=False, dist=dist)  # eigvalsh.py:221
             fired.append(gid)
             if not shared and (not batch or len(fired) == len(param_groups)):
                 del fired[:]

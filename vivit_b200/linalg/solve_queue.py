@@ -36,7 +36,7 @@ class SolveQueue:
     """Symmetric eigenproblems waiting for one batched solve."""
 
     def __init__(self) -> None:
-        self._items: List[Tuple[Tensor, Callable[[Tensor, Optional[Tensor]], None], bool]] = []
+        self._items: List[Tuple[Tensor, Callable[[Tensor, Optional[Tensor]], None], bool, object]] = []
 
     def __len__(self) -> int:
         return len(self._items)
@@ -45,11 +45,14 @@ class SolveQueue:
         """Forget what was submitted (without solving)."""
         self._items = []
 
-    def submit(self, gram: Tensor, done: Callable[[Tensor, Optional[Tensor]], None], vectors: bool = True) -> None:
+    def submit(self, gram: Tensor, done: Callable[[Tensor, Optional[Tensor]], None], vectors: bool = True,
+               dist=None) -> None:
         """``done(evals, evecs)`` is called by ``flush`` with the ascending eigenvalues ``[R]`` and the
         eigenvectors ``[R, R]`` (columns; ``None`` with ``vectors=False``) of ``gram``.  ``gram`` must not be
-        modified until then."""
-        self._items.append((gram, done, vectors))
+        modified until then.  ``dist``: the ``ShardedReduce`` of a parameter-sharded Computation -- every rank
+        submits the same (all-reduced) matrix, and a matrix that is solved on its own has the rounds of the
+        two-level solver distributed over the ranks (``kernels.syevj_dist``)."""
+        self._items.append((gram, done, vectors, dist))
 
     def flush(self) -> None:
         """Decompose everything submitted so far -- matrices of one shape, dtype and device (and one kind of request: with or without eigenvectors) in one batched
@@ -60,11 +63,16 @@ class SolveQueue:
             return
         solved: List = [None] * len(items)
         buckets = {}
-        for i, (gram, _, vectors) in enumerate(items):
+        for i, (gram, _, vectors, _) in enumerate(items):
             buckets.setdefault((tuple(gram.shape), gram.dtype, gram.device, vectors), []).append(i)
         for (_, _, _, vectors), members in buckets.items():
             if len(members) == 1:
-                solved[members[0]] = kernels.syevj(items[members[0]][0], vectors=vectors)
+                gram, dist = items[members[0]][0], items[members[0]][3]
+                comm = dist.solver_comm(gram) if dist is not None else 0
+                if comm:
+                    solved[members[0]] = kernels.syevj_dist(comm, dist.world, gram, vectors=vectors)
+                else:
+                    solved[members[0]] = kernels.syevj(gram, vectors=vectors)
                 continue
             evals, evecs = kernels.syevj_batched(torch.stack([items[i][0] for i in members]), vectors=vectors)
             for slot, i in enumerate(members):
@@ -72,7 +80,7 @@ class SolveQueue:
         # every callback runs, also after one of them has raised (a criterion of one Computation must not cost the
         # others their results); the first exception is re-raised at the end
         failed = None
-        for (_, done, _), (evals, evecs) in zip(items, solved):
+        for (_, done, _, _), (evals, evecs) in zip(items, solved):
             try:
                 done(evals, evecs)
             except Exception as e:  # noqa: BLE001

@@ -142,7 +142,7 @@ class DirectionalDampedNewtonComputation:
             newton_steps[gid] = steps
 
         if queue is not None:
-            queue.submit(gram, finish)
+            queue.submit(gram, finish, dist=dist)
             return
         if verbose:
             print(f"Group {gid}: Eigen-decompose Gram matrix")

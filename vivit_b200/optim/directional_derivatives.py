@@ -233,7 +233,7 @@ class DirectionalDerivativesComputation:
                 acc, evals, evecs, group, N, verbose, warn_small_eigvals
             )
 
-        queue.submit(gram, done)
+        queue.submit(gram, done, dist=dist)
 
     @staticmethod
     def _check_param_groups(param_groups: List[Dict]) -> None:
