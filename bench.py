@@ -175,7 +175,10 @@ class Stepper:
                 self.pg = None
                 self.parallelism = f"{len(owner)} block-diagonal groups assigned to {world} ranks, no collective"
             else:
-                self.parallelism = f"parameter-sharded Gram over {world} ranks, one all-reduce per group"
+                self.parallelism = (
+                    f"parameter-sharded Gram over {world} ranks, one all-reduce per group; the block pairs of every "
+                    f"round of the two-level eigensolver (fp32, R >= 4096) distributed over the same ranks, blocks "
+                    f"changing owner through peer memory (vvt_syevj_dist)")
         self.x_host, self.y_host = x.pin_memory(), y.pin_memory()
         self.x, self.y = x.to(device), y.to(device)
         self.host_out = None

@@ -263,11 +263,27 @@ int vvt_syevj_batched(void* evals, void* evecs, const void* G, int64_t R, int64_
  * together again by one all-reduce before the (replicated) Rayleigh quotients and refinement step.  Problems off
  * the two-level path (fp64, R < 4096) are solved by every rank for itself -- same results, no exchange.
  * comm: an ncclComm_t of the NCCL instance already loaded in the process (as vvt_nccl_allreduce_gram); rank and
- * size are read from it.  Collective: every rank of the communicator must call it, with the same R / jobz / dtype.
+ * size are read from it.  p2p != 0: the peer-memory arenas below are mapped for exactly the ranks of comm (same
+ * rank order) -- blocks then change owner by direct stores.  Collective: every rank of the communicator must call
+ * it, with the same R / jobz / p2p / dtype.
  * Not in the reference (single process); it replaces the same Tensor.symeig call sites as vvt_syevj. */
 int64_t vvt_syevj_dist_workspace_bytes(int64_t R, int jobz, int dtype, int world);
+
+/* Peer-memory arena of vvt_syevj_dist (optional; without it the blocks travel by ncclSend / ncclRecv).  One per
+ * process and device: vvt_dist_arena_alloc allocates `bytes` (vvt_dist_arena_bytes_for(R) holds the factor of an
+ * R-column problem) and writes the 64-byte CUDA IPC handle of the allocation to handle_out; the caller gathers the
+ * handles of all ranks (any transport) and passes them, in rank order, to vvt_dist_arena_open, which maps the peers'
+ * arenas.  With the arenas mapped a rank WRITES the blocks that change owner into the next owner's factor over
+ * NVLink from its own kernel and raises a flag there; the receiver's stream waits on the flag -- no NCCL call per
+ * round.  To grow or drop an arena: vvt_dist_arena_close_peers on every rank, a barrier, vvt_dist_arena_free. */
+int64_t vvt_dist_arena_bytes_for(int64_t R);
+int64_t vvt_dist_arena_bytes(void);
+int vvt_dist_arena_alloc(int64_t bytes, void* handle_out);
+int vvt_dist_arena_open(const void* handles, int world, int rank);
+int vvt_dist_arena_close_peers(void);
+int vvt_dist_arena_free(void);
 int vvt_syevj_dist(void* comm, void* evals, void* evecs, const void* G, int64_t R, int jobz, void* workspace,
-                   int64_t workspace_bytes, int* info_host, int dtype, void* stream);
+                   int64_t workspace_bytes, int* info_host, int p2p, int dtype, void* stream);
 
 /* TEST HOOK, not a reference interface: ONE round of the two-level solver used for fp32 problems of 4096
  * columns and more, on a caller-provided row-major factor L [Np, Np] (Np a multiple of 128), so that the three

@@ -26,14 +26,17 @@ for R in Rs:
     comm = sr.solver_comm(G)
     ms1, (ev1, U1, info1) = ms_of(lambda: k.syevj(G, True, return_info=True))
     del U1
-    msd, (ev, U, info) = ms_of(lambda: k.syevj_dist(comm, sr.world, G, True, return_info=True))
+    msn, (evn, Un, infon) = ms_of(lambda: k.syevj_dist(comm, sr.world, G, True, return_info=True))
+    del Un
+    p2p = sr.solver_arena(G)
+    msd, (ev, U, info) = ms_of(lambda: k.syevj_dist(comm, sr.world, G, True, return_info=True, p2p=p2p))
     want = torch.linalg.eigvalsh(G.double())
     err = (ev.double() - want).abs().max().item() / want.abs().max().item()
     Ud = U.double()
     orth = (Ud.t() @ Ud - torch.eye(R, device=dev, dtype=torch.float64)).abs().max().item()
     resid = (G.double() @ Ud - Ud * ev.double()[None]).norm().item() / G.double().norm().item()
     if local == 0:
-        print(f"R={R} world={sr.world}: one GPU {ms1:.1f} ms {info1} | distributed {msd:.1f} ms {info} "
+        print(f"R={R} world={sr.world}: one GPU {ms1:.1f} ms {info1} | NCCL hand-over {msn:.1f} ms {infon} | peer memory ({p2p}) {msd:.1f} ms {info} "
               f"evalerr={err:.2e} orth={orth:.2e} resid={resid:.2e}", flush=True)
     del U, Ud, want
 dist.barrier(); dist.destroy_process_group()

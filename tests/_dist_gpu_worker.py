@@ -42,7 +42,12 @@ def check_distributed_solver(dev, sr):
             B = torch.randn(R, rank, dtype=torch.float64, generator=gen) * torch.logspace(0, -3, rank, dtype=torch.float64)
             G = (B @ B.t()).float().to(dev)
             ev1, U1, info1 = kernels.syevj(G, True, return_info=True)
-            evd, Ud, infod = kernels.syevj_dist(comm, sr.world, G, True, return_info=True)
+            evd, Ud, infod = kernels.syevj_dist(comm, sr.world, G, True, return_info=True)  # blocks by ncclSend / ncclRecv
+            # ... and pushed into the next owner's factor through peer memory (CUDA IPC arenas): the same rotations
+            # in the same order, so the same bits
+            assert sr.solver_arena(G), "the peer-memory arena could not be mapped"
+            evp, Up, infop = kernels.syevj_dist(comm, sr.world, G, True, return_info=True, p2p=True)
+            assert infop == infod and torch.equal(evp, evd) and torch.equal(Up, Ud), (R, infop, infod)
             assert info1["converged"] and infod["converged"], (R, info1, infod)
             want = torch.linalg.eigvalsh(G.double())
             scale = want.abs().max()

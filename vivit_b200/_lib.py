@@ -50,7 +50,13 @@ SIGNATURES = {
     "vvt_syevj_batched_workspace_bytes": (I64, [I64, I64, INT, INT]),
     "vvt_syevj_batched": (INT, [P, P, P, I64, I64, INT, P, I64, POINTER(c_int), INT, P]),
     "vvt_syevj_dist_workspace_bytes": (I64, [I64, INT, INT, INT]),
-    "vvt_syevj_dist": (INT, [P, P, P, P, I64, INT, P, I64, POINTER(c_int), INT, P]),
+    "vvt_dist_arena_bytes_for": (I64, [I64]),
+    "vvt_dist_arena_bytes": (I64, []),
+    "vvt_dist_arena_alloc": (INT, [I64, P]),
+    "vvt_dist_arena_open": (INT, [P, INT, INT]),
+    "vvt_dist_arena_close_peers": (INT, []),
+    "vvt_dist_arena_free": (INT, []),
+    "vvt_syevj_dist": (INT, [P, P, P, P, I64, INT, P, I64, POINTER(c_int), INT, INT, P]),
     "vvt_dbg_wide_round": (INT, [P, P, P, P, I64, INT, P]),
     "vvt_filter_nonzero": (INT, [P, P, I64, DBL, DBL, POINTER(I64), INT, P]),
     "vvt_backtransform_dense": (INT, [P, P, P, P, I64, I64, I64, INT, P]),

@@ -33,6 +33,7 @@
 #include <chrono>
 #include <cstdlib>
 
+#include <cstring>
 #include <vector>
 
 #include "gemm_core.cuh"
@@ -1538,7 +1539,126 @@ static int host_state(HostState** out) {
 struct DistCtx {
   void* comm;
   int rank, world;
+  bool p2p;  // the caller vouches that the peer-memory arena of this device is mapped for the ranks of comm
 };
+
+// ---- peer-memory arena: the block hand-over without NCCL -----------------------------------------------------
+// Every rank allocates one arena (cudaMalloc; flags in the first 4 KB, the factor of the two-level solver behind
+// them), exports it with cudaIpcGetMemHandle and maps the arenas of its peers (vvt_dist_arena_alloc / _open; the
+// handles travel through torch.distributed in vivit_b200/dist.py).  A rank then WRITES the blocks that change owner
+// straight into the next owner's factor over NVLink (push_blocks_kernel: 16-byte stores, fence), raises a
+// monotonically increasing per-sender flag in the receiver's arena and waits for its own senders' flags
+// (signal_wait_kernel) -- ~10 us per round instead of ~35 us for a grouped ncclSend / ncclRecv of 2 x 2.6 MB.
+// Hazards: a slot is overwritten by a peer only after that peer has waited for this rank's flag of the round
+// before, which this rank raises after its own last read of the slot (its push of that block).
+constexpr int kMaxPeers = 16, kArenaHeader = 4096, kMaxPush = 96;
+struct DistArena {
+  char* base = nullptr;
+  int64_t bytes = 0;  // of the factor region
+  char* peer[kMaxPeers] = {};
+  int world = 0, rank = -1;
+  unsigned long long seq = 0;  // rounds signalled so far: identical on every rank (all ranks enqueue the same rounds)
+};
+static DistArena& arena() {
+  static DistArena a[kMaxDevices];
+  return a[current_device()];
+}
+
+struct PushArgs {
+  float* dst[kMaxPush];
+  const float* src[kMaxPush];
+  int n;
+};
+__global__ void __launch_bounds__(256) push_blocks_kernel(PushArgs a, int64_t vec4) {
+  const float4* src = reinterpret_cast<const float4*>(a.src[blockIdx.y]);
+  float4* dst = reinterpret_cast<float4*>(a.dst[blockIdx.y]);
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < vec4; i += 4 * stride) {  // four loads in flight per thread
+    const float4 v0 = src[i], v1 = src[i + stride], v2 = src[i + 2 * stride], v3 = src[i + 3 * stride];
+    dst[i] = v0, dst[i + stride] = v1, dst[i + 2 * stride] = v2, dst[i + 3 * stride] = v3;
+  }
+  for (; i < vec4; i += stride) dst[i] = src[i];
+  __threadfence_system();
+}
+struct SignalArgs {
+  unsigned long long* raise[kMaxPeers];  // this rank's flag slot in the arena of a rank that was sent something
+  const unsigned long long* wait[kMaxPeers];  // local slots of the ranks that sent something here
+  unsigned long long seq;
+};
+__global__ void signal_wait_kernel(SignalArgs a) {
+  const int t = threadIdx.x;
+  if (t >= kMaxPeers) return;
+  if (a.raise[t]) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.raise[t]), "l"(a.seq) : "memory");
+  }
+  if (a.wait[t]) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait[t]) : "memory");
+    } while (v < a.seq);
+  }
+}
+
+// every rank has reached this point of its stream (flags only): before the first block is pushed, every rank must
+// have finished writing its own copy of the initial factor
+static int dist_barrier_p2p(const DistCtx& d, cudaStream_t s) {
+  DistArena& ar = arena();
+  SignalArgs sig = {};
+  for (int r = 0; r < d.world; ++r) {
+    if (r == d.rank) continue;
+    sig.raise[r] = reinterpret_cast<unsigned long long*>(ar.peer[r]) + d.rank;
+    sig.wait[r] = reinterpret_cast<const unsigned long long*>(ar.base) + r;
+  }
+  sig.seq = ++ar.seq;
+  signal_wait_kernel<<<1, 32, 0, s>>>(sig);
+  return launched("vvt_syevj_dist(barrier)");
+}
+
+static int dist_exchange_p2p(float* Lw, const wide::WidePlan& p, int round, const DistCtx& d, std::vector<int>& owner,
+                             cudaStream_t s) {
+  DistArena& ar = arena();
+  const size_t blk = size_t(p.Np) * wide::WB;
+  PushArgs push;
+  push.n = 0;
+  SignalArgs sig = {};
+  bool any = false;
+  auto flush_push = [&]() -> int {
+    if (push.n == 0) return VVT_OK;
+    const unsigned per = unsigned(vmax(1, vmin(num_sms() / push.n, 64)));
+    push_blocks_kernel<<<dim3(per, unsigned(push.n)), 256, 0, s>>>(push, int64_t(blk / 4));
+    push.n = 0;
+    return launched("vvt_syevj_dist(push)");
+  };
+  for (int pair = 0; pair < p.pairs; ++pair) {
+    int w[2];
+    wide::wide_blocks(p.nbw, round, pair, w[0], w[1]);
+    int to = 0;
+    while (int64_t(p.pairs) * (to + 1) / d.world <= pair) ++to;
+    for (int k = 0; k < 2; ++k) {
+      const int src = owner[size_t(w[k])];
+      owner[size_t(w[k])] = to;
+      if (src < 0 || src == to || (d.rank != src && d.rank != to)) continue;
+      any = true;
+      if (d.rank == src) {
+        const size_t off = size_t(kArenaHeader) + (size_t(w[k]) * blk) * sizeof(float);
+        push.src[push.n] = Lw + size_t(w[k]) * blk;
+        push.dst[push.n] = reinterpret_cast<float*>(ar.peer[to] + off);
+        if (++push.n == kMaxPush) VVT_TRY(flush_push());
+        sig.raise[to] = reinterpret_cast<unsigned long long*>(ar.peer[to]) + d.rank;
+      } else {
+        sig.wait[src] = reinterpret_cast<const unsigned long long*>(ar.base) + src;
+      }
+    }
+  }
+  ++ar.seq;  // every rank counts every round, also the ones it takes no part in
+  if (!any) return VVT_OK;
+  VVT_TRY(flush_push());
+  sig.seq = ar.seq;
+  signal_wait_kernel<<<1, 32, 0, s>>>(sig);
+  return launched("vvt_syevj_dist(signal)");
+}
 
 static int dist_exchange(float* Lw, const wide::WidePlan& p, int round, const DistCtx& d, std::vector<int>& owner,
                          cudaStream_t s) {
@@ -1572,6 +1692,8 @@ static int dist_exchange(float* Lw, const wide::WidePlan& p, int round, const Di
   return st;
 }
 
+static bool debug_env() { return getenv("VVT_SYEVJ_DEBUG") != nullptr; }
+
 template <typename T>
 static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int jobz, char* ws, int* info, int dtype,
                       cudaStream_t s, const DistCtx* dist_in = nullptr) {
@@ -1581,12 +1703,24 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
   const DistCtx* dist = dist_in && dist_in->world > 1 && L.wide && B == 1 && sizeof(T) == 4 ? dist_in : nullptr;
   std::vector<int> owner;
   int pair_lo = 0, pair_hi = L.wp.pairs;
+  // blocks change owner through peer memory when every rank has mapped the others' arenas (vvt_dist_arena_open)
+  // and the factor fits; through grouped ncclSend / ncclRecv otherwise (VVT_SYEVJ_P2P=0 forces that)
+  bool p2p = false;
+  if (dist) {
+    const DistArena& ar = arena();
+    const char* env = getenv("VVT_SYEVJ_P2P");
+    p2p = dist->p2p && !(env && atoi(env) == 0) && ar.base && ar.world == dist->world && ar.rank == dist->rank &&
+          ar.bytes >= int64_t(L.wp.Np) * L.wp.Np * 4;
+    if (debug_env())
+      fprintf(stderr, "[vvt_syevj] rank %d of %d: blocks change owner through %s\n", dist->rank, dist->world,
+              p2p ? "peer memory" : "NCCL send / recv");
+  }
   if (dist) {
     owner.assign(size_t(L.wp.nbw), -1);
     pair_lo = int(int64_t(L.wp.pairs) * dist->rank / dist->world);
     pair_hi = int(int64_t(L.wp.pairs) * (dist->rank + 1) / dist->world);
   }
-  T* Y = (T*)(ws + L.off_Y);
+  T* Y = p2p ? (T*)(arena().base + kArenaHeader) : (T*)(ws + L.off_Y);  // the factor lives where the peers can write
   T* Gs = (T*)(ws + L.off_Gs);
   T* Jm = (T*)(ws + L.off_Jm);
   T* Jt = (T*)(ws + L.off_Jt);
@@ -1688,6 +1822,7 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
       if constexpr (sizeof(T) == 4) {
         wide::wide_init_chol_kernel<<<dim3(init_blocks, UB), 256, 0, s>>>((float*)Y, (const float*)A, R, L.wp.Np, sc);
         VVT_TRY(launched("vvt_syevj(wide init)"));
+        if (dist && p2p) VVT_TRY(dist_barrier_p2p(*dist, s));
       }
     } else {
       onesided_init_chol_kernel<T><<<dim3(init_blocks, UB), 256, 0, s>>>(Y, A, R, Np, sc, L.y_elems);
@@ -1728,7 +1863,7 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
     if (L.wide) {
       if constexpr (sizeof(T) == 4) {
         for (int round = -1; round < L.wp.nbw - 1; ++round) {
-          if (dist) VVT_TRY(dist_exchange((float*)Y, L.wp, round, *dist, owner, s));
+          if (dist) VVT_TRY((p2p ? dist_exchange_p2p : dist_exchange)((float*)Y, L.wp, round, *dist, owner, s));
           VVT_TRY(wide::wide_round((float*)Y, (float*)Tt, (float*)Sm, (int*)Mm, (float*)((char*)Mm + L.wp.flag_bytes), sc,
                                    L.wp, maps, round, B, s, pair_lo, pair_hi - pair_lo));
         }
@@ -1899,6 +2034,73 @@ int vvt_syevj(void* evals, void* evecs, const void* G, int64_t R, int jobz, void
   return vvt_syevj_batched(evals, evecs, G, R, 1, jobz, workspace, workspace_bytes, info_host, dtype, stream);
 }
 
+int64_t vvt_dist_arena_bytes_for(int64_t R) {
+  if (R <= 0) return 0;
+  const int64_t Np = align_up(R, wide::WP);
+  return Np * Np * 4;
+}
+
+int64_t vvt_dist_arena_bytes(void) { return arena().base ? arena().bytes : 0; }
+
+int vvt_dist_arena_alloc(int64_t bytes, void* handle_out) {
+  VVT_REQUIRE(bytes > 0 && handle_out, "bad arguments");
+  DistArena& ar = arena();
+  VVT_REQUIRE(ar.base == nullptr, "an arena exists already (vvt_dist_arena_free first)");
+  void* ptr = nullptr;
+  VVT_TRY(check_cuda(cudaMalloc(&ptr, size_t(bytes) + kArenaHeader), __func__));
+  cudaIpcMemHandle_t h;
+  if (cudaMemset(ptr, 0, kArenaHeader) != cudaSuccess || cudaIpcGetMemHandle(&h, ptr) != cudaSuccess) {
+    const cudaError_t e = cudaGetLastError();
+    cudaFree(ptr);
+    return fail(VVT_ERR_CUDA, "%s: %s", __func__, cudaGetErrorString(e));
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  memcpy(handle_out, &h, sizeof(h));
+  ar = DistArena();
+  ar.base = static_cast<char*>(ptr);
+  ar.bytes = bytes;
+  return VVT_OK;
+}
+
+int vvt_dist_arena_open(const void* handles, int world, int rank) {
+  VVT_REQUIRE(handles && world > 1 && world <= kMaxPeers && rank >= 0 && rank < world, "bad arguments");
+  DistArena& ar = arena();
+  VVT_REQUIRE(ar.base != nullptr && ar.world == 0, "vvt_dist_arena_alloc first (once)");
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      ar.peer[r] = ar.base;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + size_t(r) * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    VVT_TRY(check_cuda(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess), __func__));
+    ar.peer[r] = static_cast<char*>(ptr);
+  }
+  ar.world = world;
+  ar.rank = rank;
+  ar.seq = 0;
+  return VVT_OK;
+}
+
+int vvt_dist_arena_close_peers(void) {
+  DistArena& ar = arena();
+  for (int r = 0; r < ar.world; ++r)
+    if (r != ar.rank && ar.peer[r]) cudaIpcCloseMemHandle(ar.peer[r]);
+  for (int r = 0; r < kMaxPeers; ++r) ar.peer[r] = nullptr;
+  ar.world = 0;
+  ar.rank = -1;
+  return VVT_OK;
+}
+
+int vvt_dist_arena_free(void) {
+  DistArena& ar = arena();
+  VVT_REQUIRE(ar.world == 0, "vvt_dist_arena_close_peers first (on every rank, then a barrier)");
+  if (ar.base) cudaFree(ar.base);
+  ar = DistArena();
+  return VVT_OK;
+}
+
 int64_t vvt_syevj_dist_workspace_bytes(int64_t R, int jobz, int dtype, int world) {
   (void)jobz;
   if (R <= 0) return 0;
@@ -1906,7 +2108,7 @@ int64_t vvt_syevj_dist_workspace_bytes(int64_t R, int jobz, int dtype, int world
 }
 
 int vvt_syevj_dist(void* comm, void* evals, void* evecs, const void* G, int64_t R, int jobz, void* workspace,
-                   int64_t workspace_bytes, int* info_host, int dtype, void* stream) {
+                   int64_t workspace_bytes, int* info_host, int p2p, int dtype, void* stream) {
   VVT_REQUIRE(R >= 0, "negative size");
   VVT_REQUIRE(comm != nullptr, "null communicator");
   if (info_host) info_host[0] = 0, info_host[1] = 1;
@@ -1915,7 +2117,7 @@ int vvt_syevj_dist(void* comm, void* evals, void* evecs, const void* G, int64_t 
   VVT_REQUIRE(evals && G && workspace && (!jobz || evecs), "null pointer");
   const Nccl& n = nccl();
   if (!n.ok) return fail(VVT_ERR_UNSUPPORTED, "%s: no NCCL library is loaded in this process", __func__);
-  DistCtx d{comm, 0, 1};
+  DistCtx d{comm, 0, 1, p2p != 0};
   VVT_TRY(check_nccl(n.comm_count(comm, &d.world), __func__));
   VVT_TRY(check_nccl(n.comm_rank(comm, &d.rank), __func__));
   if (workspace_bytes < vvt_syevj_dist_workspace_bytes(R, jobz, dtype, d.world))

@@ -18,8 +18,14 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import ctypes
+
 import torch
 from torch import Tensor
+
+
+_ARENA_OWNER: Dict[int, object] = {}  # device index -> process group its peer-memory arena is mapped for
+_NO_ARENA = object()
 
 
 def shard_bounds(size: int, rank: int, world: int) -> Tuple[int, int]:
@@ -71,6 +77,69 @@ class ShardedReduce:
         if os.environ.get("VVT_SYEVJ_DIST", "1") == "0":
             return 0
         return self._nccl_comm(gram)
+
+    def solver_arena(self, gram: Tensor) -> bool:
+        """Peer-memory arena for the distributed solver (``vvt_dist_arena_*``): every rank allocates one, the CUDA IPC
+        handles are all-gathered over this group and the peers' arenas mapped, after which blocks change owner by
+        direct stores over NVLink instead of ``ncclSend`` / ``ncclRecv``.  Collective; ``True`` when the arena of this
+        process is mapped for THIS group and holds an ``R``-column factor.  A process has one arena per device: a
+        second group on the same device keeps the NCCL hand-over.  ``VVT_SYEVJ_P2P=0`` switches it off."""
+        import os
+        import warnings
+
+        import torch.distributed as dist
+
+        from vivit_b200 import _lib
+
+        if os.environ.get("VVT_SYEVJ_P2P", "1") == "0" or self.world == 1 or self.world > 16 or not gram.is_cuda:
+            return False
+        dev = gram.device.index if gram.device.index is not None else torch.cuda.current_device()
+        bound = _ARENA_OWNER.get(dev)
+        if bound is not None and bound is not self.group:
+            return False  # also after a failed attempt (bound to the sentinel)
+        lib = _lib.load()
+        need = int(lib.vvt_dist_arena_bytes_for(int(gram.shape[0])))
+        with torch.cuda.device(gram.device):
+            if bound is self.group and int(lib.vvt_dist_arena_bytes()) >= need:
+                return True
+            ok = True
+            try:
+                if bound is self.group:  # grow: nobody may write into the old arena any more
+                    torch.cuda.synchronize()
+                    _lib.check(lib.vvt_dist_arena_close_peers(), "vvt_dist_arena_close_peers")
+                    dist.barrier(group=self.group)
+                    _lib.check(lib.vvt_dist_arena_free(), "vvt_dist_arena_free")
+                handle = (ctypes.c_ubyte * 64)()
+                _lib.check(lib.vvt_dist_arena_alloc(need, handle), "vvt_dist_arena_alloc")
+            except Exception as e:  # noqa: BLE001
+                ok, why = False, str(e)
+            mine = torch.tensor(list(bytes(handle)) if ok else [0] * 64, dtype=torch.uint8, device=gram.device)
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=gram.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()):
+                every = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(every, mine, group=self.group)
+                handles = b"".join(t.cpu().numpy().tobytes() for t in every)
+                try:
+                    _lib.check(lib.vvt_dist_arena_open(handles, self.world, self.rank), "vvt_dist_arena_open")
+                except Exception as e:  # noqa: BLE001
+                    ok, why = False, str(e)
+                flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=gram.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()):
+                _ARENA_OWNER[dev] = self.group
+                return True
+            # some rank could not export or map its arena: every rank drops its own and keeps the NCCL hand-over
+            lib.vvt_dist_arena_close_peers()
+            dist.barrier(group=self.group)
+            lib.vvt_dist_arena_free()
+            _ARENA_OWNER[dev] = _NO_ARENA
+            warnings.warn(
+                "vivit_b200: CUDA IPC peer mapping is not available ("
+                + (why if not ok else "on another rank")
+                + "); the distributed eigensolver hands blocks over with ncclSend / ncclRecv"
+            )
+            return False
 
     def scale_allreduce_(self, alpha: float, gram: Tensor, cross: Optional[Tensor] = None) -> None:
         """``gram`` (and ``cross``) ``<- alpha * sum over ranks`` in place: the partial-Gram exchange of the

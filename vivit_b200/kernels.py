@@ -505,10 +505,13 @@ def syevj_batched(G: Tensor, vectors: bool = True, return_info: bool = False):
     return evals, evecs
 
 
-def syevj_dist(comm_ptr: int, world: int, G: Tensor, vectors: bool = True, return_info: bool = False):
+def syevj_dist(comm_ptr: int, world: int, G: Tensor, vectors: bool = True, return_info: bool = False,
+               p2p: bool = False):
     """``syevj`` with the rounds of the two-level path distributed over the ranks of an NCCL communicator
     (``vvt_syevj_dist``): every rank passes the same ``G [R, R]`` and gets the same results.  ``comm_ptr`` is the raw
-    ``ncclComm_t`` (``ProcessGroupNCCL._comm_ptr()``), ``world`` its size.  Collective call."""
+    ``ncclComm_t`` (``ProcessGroupNCCL._comm_ptr()``), ``world`` its size.  ``p2p``: the peer-memory arenas of
+    exactly these ranks are mapped (``ShardedReduce.solver_arena``), so blocks change owner by direct stores over
+    NVLink; otherwise by ``ncclSend`` / ``ncclRecv``.  Collective call."""
     G = _c(G)
     _chk(G)
     if G.dim() != 2 or G.shape[0] != G.shape[1]:
@@ -523,7 +526,7 @@ def syevj_dist(comm_ptr: int, world: int, G: Tensor, vectors: bool = True, retur
         with _on(G.device):
             st = lib.vvt_syevj_dist(
                 ctypes.c_void_p(comm_ptr), _p(evals), _p(evecs), _p(G), R, int(vectors), _p(ws), ws.numel(), info,
-                _dt(G), _stream(G),
+                int(bool(p2p)), _dt(G), _stream(G),
             )
         _lib.check(st, "vvt_syevj_dist")
     result = {"sweeps": int(info[0]), "converged": bool(info[1])}

@@ -70,7 +70,9 @@ class SolveQueue:
                 gram, dist = items[members[0]][0], items[members[0]][3]
                 comm = dist.solver_comm(gram) if dist is not None else 0
                 if comm:
-                    solved[members[0]] = kernels.syevj_dist(comm, dist.world, gram, vectors=vectors)
+                    solved[members[0]] = kernels.syevj_dist(
+                        comm, dist.world, gram, vectors=vectors, p2p=dist.solver_arena(gram)
+                    )
                 else:
                     solved[members[0]] = kernels.syevj(gram, vectors=vectors)
                 continue
