@@ -1402,6 +1402,8 @@ static JacobiLayout jacobi_layout(int64_t R, int64_t B, int64_t es, int dtype, i
   L.off_done = take(B * L.nb * 4);
   L.off_state = take(B * 3 * 4);
   L.gemm_bytes = vvt_gram_workspace_bytes(R, R, R, dtype);
+  if (world > 1)  // the products of the refinement step are split by rows over the ranks
+    L.gemm_bytes = vmax<int64_t>(L.gemm_bytes, vvt_gram_workspace_bytes(ceil_div(R, int64_t(world)), R, R, dtype));
   L.off_gemm = take(L.gemm_bytes);
   L.total = o;
   return L;
@@ -1970,8 +1972,17 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
   }
   VVT_TRY(launched("vvt_syevj(gather)"));
   // every product below is C = A B^T with K-contiguous operands: the tcgen05 (fp32) / DMMA (fp64) GEMM
-  auto gemm_nt = [&](T* C, const T* A, const T* Bm, double beta) {
-    return gemm_batched(C, A, Bm, R, R, R, R, R, R, 1.0, beta);
+  // distributed solve: a rank forms R / world rows of every product and one all-gather puts the matrix together
+  // again (every row is computed by exactly one rank, so all ranks keep identical data)
+  const bool split_rows = dist && R % dist->world == 0 && getenv("VVT_SYEVJ_DIST_REPLICATED_GEMM") == nullptr;
+  auto gemm_nt = [&](T* C, const T* A, const T* Bm, double beta) -> int {
+    if (!split_rows) return gemm_batched(C, A, Bm, R, R, R, R, R, R, 1.0, beta);
+    const int64_t rows = R / dist->world, r0 = rows * dist->rank;
+    VVT_TRY(vvt_gemm(C + r0 * R, A + r0 * R, Bm, rows, R, R, 0, 0, R, R, R, 1.0, beta, 1, 0, 0, 0, ws + L.off_gemm,
+                     L.gemm_bytes, dtype, (void*)s));
+    return check_nccl(nccl().all_gather(C + r0 * R, C, size_t(rows * R), sizeof(T) == 4 ? kNcclFloat32 : kNcclFloat64,
+                                        dist->comm, s),
+                      "vvt_syevj_dist(all-gather)");
   };
   VVT_TRY(gemm_nt(Tt, Jt, Gs, 0.0));  // Tt = J^T G   (G symmetric)
   onesided_rayleigh_kernel<T><<<dim3(unsigned(ceil_div(R * 32, 256)), UB), 256, 0, s>>>(ev, Jt, Tt, R, sc);

@@ -9,6 +9,7 @@
 namespace vvt {
 
 typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*NcclSendFn)(const void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*NcclRecvFn)(void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*NcclPreMulFn)(int*, void*, int, int, void*);
@@ -19,6 +20,7 @@ typedef const char* (*NcclErrStrFn)(int);
 
 struct Nccl {
   NcclAllReduceFn all_reduce = nullptr;
+  NcclAllGatherFn all_gather = nullptr;
   NcclSendFn send = nullptr;
   NcclRecvFn recv = nullptr;
   NcclPreMulFn premul = nullptr;
@@ -39,6 +41,7 @@ inline const Nccl& nccl() {
     }
     if (!h) return r;
     r.all_reduce = reinterpret_cast<NcclAllReduceFn>(dlsym(h, "ncclAllReduce"));
+    r.all_gather = reinterpret_cast<NcclAllGatherFn>(dlsym(h, "ncclAllGather"));
     r.send = reinterpret_cast<NcclSendFn>(dlsym(h, "ncclSend"));
     r.recv = reinterpret_cast<NcclRecvFn>(dlsym(h, "ncclRecv"));
     r.premul = reinterpret_cast<NcclPreMulFn>(dlsym(h, "ncclRedOpCreatePreMulSum"));
@@ -48,7 +51,7 @@ inline const Nccl& nccl() {
     r.comm_count = reinterpret_cast<NcclCommIntFn>(dlsym(h, "ncclCommCount"));
     r.comm_rank = reinterpret_cast<NcclCommIntFn>(dlsym(h, "ncclCommUserRank"));
     r.err = reinterpret_cast<NcclErrStrFn>(dlsym(h, "ncclGetErrorString"));
-    r.ok = r.all_reduce && r.send && r.recv && r.premul && r.op_destroy && r.group_start && r.group_end && r.comm_count &&
+    r.ok = r.all_reduce && r.all_gather && r.send && r.recv && r.premul && r.op_destroy && r.group_start && r.group_end && r.comm_count &&
            r.comm_rank;
     return r;
   }();
