@@ -285,6 +285,14 @@ int vvt_dist_arena_free(void);
 int vvt_syevj_dist(void* comm, void* evals, void* evecs, const void* G, int64_t R, int jobz, void* workspace,
                    int64_t workspace_bytes, int* info_host, int p2p, int dtype, void* stream);
 
+/* TEST HOOK, not a reference interface (host logic only, no GPU needed): the block hand-over plan of
+ * vvt_syevj_dist before round `round` (-1: the intra round, 0 .. nbw - 2: the tournament) for nbw wide blocks over
+ * `world` ranks.  owner [nbw] (in / out): rank holding each block, -1 = every rank; moves_out [3 * max_moves]:
+ * {block, from, to} triples in the order every rank issues them; pair_rank_out [nbw / 2] (may be NULL): the rank
+ * that works on each pair of the round. */
+int vvt_dbg_dist_plan(int nbw, int world, int round, int* owner, int* moves_out, int max_moves, int* n_moves_out,
+                      int* pair_rank_out);
+
 /* TEST HOOK, not a reference interface: ONE round of the two-level solver used for fp32 problems of 4096
  * columns and more, on a caller-provided row-major factor L [Np, Np] (Np a multiple of 128), so that the three
  * kernels of a round (tcgen05 pair Grams with MN-major operands, 128 x 128 rotation kernel, tcgen05 apply) can

@@ -56,6 +56,7 @@ SIGNATURES = {
     "vvt_dist_arena_open": (INT, [P, INT, INT]),
     "vvt_dist_arena_close_peers": (INT, []),
     "vvt_dist_arena_free": (INT, []),
+    "vvt_dbg_dist_plan": (INT, [INT, INT, INT, POINTER(c_int), POINTER(c_int), INT, POINTER(c_int), POINTER(c_int)]),
     "vvt_syevj_dist": (INT, [P, P, P, P, I64, INT, P, I64, POINTER(c_int), INT, INT, P]),
     "vvt_dbg_wide_round": (INT, [P, P, P, P, I64, INT, P]),
     "vvt_filter_nonzero": (INT, [P, P, I64, DBL, DBL, POINTER(I64), INT, P]),

@@ -1544,6 +1544,34 @@ struct DistCtx {
   bool p2p;  // the caller vouches that the peer-memory arena of this device is mapped for the ranks of comm
 };
 
+// rank that works on pair `pair` of a round: contiguous, balanced slices of the pair index
+static inline int dist_rank_of_pair(int pairs, int world, int pair) {
+  int r = 0;
+  while (int64_t(pairs) * (r + 1) / world <= pair) ++r;
+  return r;
+}
+
+struct BlockMove {
+  int block, src, dst;
+};
+// Blocks that must change owner before round `round` can start, in a fixed order every rank derives alike (pair by
+// pair, first block then second); updates owner[] to the ownership during that round.  Host logic only: also
+// reachable through the test hook vvt_dbg_dist_plan.
+static void dist_plan_round(int nbw, int world, int round, std::vector<int>& owner, std::vector<BlockMove>& moves) {
+  moves.clear();
+  const int pairs = nbw / 2;
+  for (int pair = 0; pair < pairs; ++pair) {
+    int w[2];
+    wide::wide_blocks(nbw, round, pair, w[0], w[1]);
+    const int to = dist_rank_of_pair(pairs, world, pair);
+    for (int k = 0; k < 2; ++k) {
+      const int src = owner[size_t(w[k])];
+      owner[size_t(w[k])] = to;
+      if (src >= 0 && src != to) moves.push_back({w[k], src, to});
+    }
+  }
+}
+
 // ---- peer-memory arena: the block hand-over without NCCL -----------------------------------------------------
 // Every rank allocates one arena (cudaMalloc; flags in the first 4 KB, the factor of the two-level solver behind
 // them), exports it with cudaIpcGetMemHandle and maps the arenas of its peers (vvt_dist_arena_alloc / _open; the
@@ -1633,25 +1661,19 @@ static int dist_exchange_p2p(float* Lw, const wide::WidePlan& p, int round, cons
     push.n = 0;
     return launched("vvt_syevj_dist(push)");
   };
-  for (int pair = 0; pair < p.pairs; ++pair) {
-    int w[2];
-    wide::wide_blocks(p.nbw, round, pair, w[0], w[1]);
-    int to = 0;
-    while (int64_t(p.pairs) * (to + 1) / d.world <= pair) ++to;
-    for (int k = 0; k < 2; ++k) {
-      const int src = owner[size_t(w[k])];
-      owner[size_t(w[k])] = to;
-      if (src < 0 || src == to || (d.rank != src && d.rank != to)) continue;
-      any = true;
-      if (d.rank == src) {
-        const size_t off = size_t(kArenaHeader) + (size_t(w[k]) * blk) * sizeof(float);
-        push.src[push.n] = Lw + size_t(w[k]) * blk;
-        push.dst[push.n] = reinterpret_cast<float*>(ar.peer[to] + off);
-        if (++push.n == kMaxPush) VVT_TRY(flush_push());
-        sig.raise[to] = reinterpret_cast<unsigned long long*>(ar.peer[to]) + d.rank;
-      } else {
-        sig.wait[src] = reinterpret_cast<const unsigned long long*>(ar.base) + src;
-      }
+  std::vector<BlockMove> moves;
+  dist_plan_round(p.nbw, d.world, round, owner, moves);
+  for (const BlockMove& m : moves) {
+    if (d.rank != m.src && d.rank != m.dst) continue;
+    any = true;
+    if (d.rank == m.src) {
+      const size_t off = size_t(kArenaHeader) + (size_t(m.block) * blk) * sizeof(float);
+      push.src[push.n] = Lw + size_t(m.block) * blk;
+      push.dst[push.n] = reinterpret_cast<float*>(ar.peer[m.dst] + off);
+      if (++push.n == kMaxPush) VVT_TRY(flush_push());
+      sig.raise[m.dst] = reinterpret_cast<unsigned long long*>(ar.peer[m.dst]) + d.rank;
+    } else {
+      sig.wait[m.src] = reinterpret_cast<const unsigned long long*>(ar.base) + m.src;
     }
   }
   ++ar.seq;  // every rank counts every round, also the ones it takes no part in
@@ -1668,24 +1690,19 @@ static int dist_exchange(float* Lw, const wide::WidePlan& p, int round, const Di
   const size_t blk = size_t(p.Np) * wide::WB;
   bool open = false;
   int st = VVT_OK;
-  for (int pair = 0; pair < p.pairs && st == VVT_OK; ++pair) {
-    int w[2];
-    wide::wide_blocks(p.nbw, round, pair, w[0], w[1]);
-    int owner_rank = 0;
-    while (int64_t(p.pairs) * (owner_rank + 1) / d.world <= pair) ++owner_rank;  // pair in [lo, hi) of owner_rank
-    for (int k = 0; k < 2 && st == VVT_OK; ++k) {
-      const int src = owner[w[k]];
-      owner[w[k]] = owner_rank;
-      if (src < 0 || src == owner_rank || (d.rank != src && d.rank != owner_rank)) continue;
-      if (!open) {
-        st = check_nccl(n.group_start(), "vvt_syevj_dist");
-        open = true;
-        if (st != VVT_OK) break;
-      }
-      float* ptr = Lw + size_t(w[k]) * blk;
-      st = d.rank == src ? check_nccl(n.send(ptr, blk, kNcclFloat32, owner_rank, d.comm, s), "vvt_syevj_dist(send)")
-                         : check_nccl(n.recv(ptr, blk, kNcclFloat32, src, d.comm, s), "vvt_syevj_dist(recv)");
+  std::vector<BlockMove> moves;
+  dist_plan_round(p.nbw, d.world, round, owner, moves);
+  for (const BlockMove& m : moves) {
+    if (st != VVT_OK) break;
+    if (d.rank != m.src && d.rank != m.dst) continue;
+    if (!open) {
+      st = check_nccl(n.group_start(), "vvt_syevj_dist");
+      open = true;
+      if (st != VVT_OK) break;
     }
+    float* ptr = Lw + size_t(m.block) * blk;
+    st = d.rank == m.src ? check_nccl(n.send(ptr, blk, kNcclFloat32, m.dst, d.comm, s), "vvt_syevj_dist(send)")
+                         : check_nccl(n.recv(ptr, blk, kNcclFloat32, m.src, d.comm, s), "vvt_syevj_dist(recv)");
   }
   if (open) {
     const int e = check_nccl(n.group_end(), "vvt_syevj_dist");
@@ -1719,7 +1736,7 @@ static int syevj_impl(T* evals, T* evecs, const T* G, int64_t R, int64_t B, int 
   }
   if (dist) {
     owner.assign(size_t(L.wp.nbw), -1);
-    pair_lo = int(int64_t(L.wp.pairs) * dist->rank / dist->world);
+    pair_lo = int(int64_t(L.wp.pairs) * dist->rank / dist->world);  // dist_rank_of_pair(pair) == rank on [lo, hi)
     pair_hi = int(int64_t(L.wp.pairs) * (dist->rank + 1) / dist->world);
   }
   T* Y = p2p ? (T*)(arena().base + kArenaHeader) : (T*)(ws + L.off_Y);  // the factor lives where the peers can write
@@ -2109,6 +2126,23 @@ int vvt_dist_arena_free(void) {
   VVT_REQUIRE(ar.world == 0, "vvt_dist_arena_close_peers first (on every rank, then a barrier)");
   if (ar.base) cudaFree(ar.base);
   ar = DistArena();
+  return VVT_OK;
+}
+
+int vvt_dbg_dist_plan(int nbw, int world, int round, int* owner, int* moves_out, int max_moves, int* n_moves_out,
+                      int* pair_rank_out) {
+  VVT_REQUIRE(nbw >= 2 && nbw % 2 == 0 && world >= 1 && round >= -1 && round < nbw - 1, "bad arguments");
+  VVT_REQUIRE(owner && n_moves_out && (moves_out || max_moves == 0), "null pointer");
+  std::vector<int> own(owner, owner + nbw);
+  std::vector<BlockMove> moves;
+  dist_plan_round(nbw, world, round, own, moves);
+  for (int w = 0; w < nbw; ++w) owner[w] = own[size_t(w)];
+  *n_moves_out = int(moves.size());
+  for (int i = 0; i < int(moves.size()) && i < max_moves; ++i)
+    moves_out[3 * i] = moves[size_t(i)].block, moves_out[3 * i + 1] = moves[size_t(i)].src,
+                  moves_out[3 * i + 2] = moves[size_t(i)].dst;
+  if (pair_rank_out)
+    for (int pair = 0; pair < nbw / 2; ++pair) pair_rank_out[pair] = dist_rank_of_pair(nbw / 2, world, pair);
   return VVT_OK;
 }
 
