@@ -116,6 +116,14 @@ int vvt_sqrt_backprop_conv2d(void* out, const void* S, const void* W, int64_t ro
 int vvt_sqrt_backprop_elementwise(void* out, const void* S, const void* ref, int64_t V,
                                   int64_t n_feat, int act, double scale, int dtype, void* stream);
 
+/* arg-max positions of a max-pool forward pass over x [planes, h_in, w_in] -> argmax [planes, h_out, w_out] (flat
+ * index into h_in * w_in), the index plumbing of [BackPACK]'s max-pool Jacobian (it re-runs
+ * max_pool2d(return_indices=True) on the layer input; reached via base.py:8,19).  torch's selection rule: windows
+ * scanned row by row, the first of equal values wins, NaN wins.  h_out / w_out are the caller's (floor or ceil mode). */
+int vvt_maxpool2d_argmax(int64_t* argmax, const void* x, int64_t planes, int64_t h_out, int64_t w_out, int64_t h_in,
+                         int64_t w_in, int64_t kh, int64_t kw, int64_t stride_h, int64_t stride_w, int64_t pad_h,
+                         int64_t pad_w, int64_t dil_h, int64_t dil_w, int dtype, void* stream);
+
 /* max-pool: out[r, ch, p] = sum over output positions q whose arg-max is p of S[r, ch, q].
  * S: [V*N, ch, h_out*w_out]; argmax: [N, ch, h_out*w_out] flat index into h_in*w_in;
  * out: [V*N, ch, h_in*w_in]; row r belongs to sample r % N. */

@@ -28,7 +28,7 @@ NAMES = [
     "v_emit_linear", "gemm", "gram_dense_accum", "gram_cross_accum", "gram_linear_accum",
     "gram_cross_linear_accum", "syevj", "syevj_batched", "filter_nonzero", "backtransform_dense",
     "backtransform_linear", "vt_mat_prod_linear", "scale_rows_rsqrt", "dirderiv_epilogue",
-    "newton_coeff", "v_apply_dense", "v_apply_linear", "launch_count", "center_rows",
+    "newton_coeff", "v_apply_dense", "v_apply_linear", "launch_count", "center_rows", "maxpool2d_argmax",
 ]
 
 
@@ -120,6 +120,10 @@ def sqrt_backprop_elementwise(S, ref, act, scale=1.0):
     else:
         d = ref
     return (S.reshape(-1, ref.numel()) * d.reshape(1, -1)).reshape(S.shape)
+
+
+def maxpool2d_argmax(x, kernel, stride, padding, dilation, ceil_mode=False):
+    return F.max_pool2d(x, kernel, stride, padding, dilation, ceil_mode, return_indices=True)[1]
 
 
 def sqrt_backprop_maxpool2d(S, argmax, in_hw, kernel, stride, padding, dilation):

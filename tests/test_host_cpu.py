@@ -430,3 +430,20 @@ def test_solve_queue_buckets_by_shape_and_by_vectors():
     assert len(queue) == len(groups)
     for grp in groups:
         close(queued.get_result(grp), plain.get_result(grp))
+
+
+def test_pool_output_size_is_torch_s():
+    """``kernels.pool_output_size`` (host arithmetic of the native arg-max kernel) against the shapes torch's pooling
+    produces, floor and ceil mode."""
+    import torch.nn.functional as F
+
+    from vivit_b200.kernels import pool_output_size
+
+    for size in (5, 8, 9, 11, 32):
+        for k, s, p, d in [(2, 2, 0, 1), (3, 2, 0, 1), (3, 2, 1, 1), (3, 1, 1, 1), (3, 3, 0, 1), (2, 1, 0, 2), (4, 3, 1, 1),
+                           (3, 2, 1, 2), (5, 4, 2, 1)]:
+            if d * (k - 1) + 1 > size + 2 * p:
+                continue
+            for ceil in (False, True):
+                want = F.max_pool2d(torch.zeros(1, 1, size, size), k, s, p, d, ceil).shape[-1]
+                assert pool_output_size(size, k, s, p, d, ceil) == want, (size, k, s, p, d, ceil)

@@ -163,11 +163,24 @@ def test_elementwise_and_pools(k, dtype):
     for kern, st, pd, ceil, dil in [(3, 2, 0, False, 1), (3, 2, 0, True, 1), (2, 2, 0, False, 1), (3, 1, 1, False, 1),
                                     (3, 2, 1, True, 1), (3, 3, 0, False, 1), (2, 1, 0, False, 2), (4, 3, 1, False, 1)]:
         y, idx = torch.nn.functional.max_pool2d(x, kern, st, pd, dil, ceil, return_indices=True)
+        # the native arg-max kernel chooses what torch chooses -- also among tied values (a ReLU in front of the pool)
+        assert torch.equal(k.maxpool2d_argmax(x, (kern, kern), (st, st), (pd, pd), (dil, dil), ceil), idx), (kern, st, pd, ceil, dil)
+        xr = torch.relu(x - 0.3)
+        assert torch.equal(k.maxpool2d_argmax(xr, (kern, kern), (st, st), (pd, pd), (dil, dil), ceil),
+                           torch.nn.functional.max_pool2d(xr, kern, st, pd, dil, ceil, return_indices=True)[1]), "ties"
         Sp = rnd(3, *y.shape, dtype=dtype, seed=5)
         a = ((9, 9), (kern, kern), (st, st), (pd, pd), (dil, dil))
         close(k.sqrt_backprop_maxpool2d(Sp, idx, *a), ref.sqrt_backprop_maxpool2d(Sp.double(), idx, *a), dtype, "maxpool")
     xb = rnd(2, 3, 30, 28, dtype=dtype, seed=8)  # a map larger than one block of threads
     y, idx = torch.nn.functional.max_pool2d(xb, 3, 2, 0, 1, True, return_indices=True)
+    assert torch.equal(k.maxpool2d_argmax(xb, (3, 3), (2, 2), (0, 0), (1, 1), True), idx)
+    xn = xb.clone()
+    xn[0, 1, 4, 5] = float("nan")  # NaN wins its windows, as in torch
+    assert torch.equal(k.maxpool2d_argmax(xn, (3, 3), (2, 2), (0, 0), (1, 1), True),
+                       torch.nn.functional.max_pool2d(xn, 3, 2, 0, 1, True, return_indices=True)[1])
+    x_rect = rnd(2, 3, 11, 6, dtype=dtype, seed=10)  # rectangular window, stride, padding and dilation
+    assert torch.equal(k.maxpool2d_argmax(x_rect, (3, 2), (2, 1), (1, 0), (2, 1), False),
+                       torch.nn.functional.max_pool2d(x_rect, (3, 2), (2, 1), (1, 0), (2, 1), False, return_indices=True)[1])
     Sp = rnd(2, *y.shape, dtype=dtype, seed=9)
     a = ((30, 28), (3, 3), (2, 2), (0, 0), (1, 1))
     close(k.sqrt_backprop_maxpool2d(Sp, idx, *a), ref.sqrt_backprop_maxpool2d(Sp.double(), idx, *a), dtype, "maxpool big")

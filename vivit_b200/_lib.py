@@ -28,6 +28,7 @@ SIGNATURES = {
     "vvt_conv2d_workspace_bytes": (I64, [INT] + [I64] * 8 + [INT]),
     "vvt_sqrt_backprop_conv2d": (INT, [P, P, P] + [I64] * 15 + [P, I64, INT, P]),
     "vvt_sqrt_backprop_elementwise": (INT, [P, P, P, I64, I64, INT, DBL, INT, P]),
+    "vvt_maxpool2d_argmax": (INT, [P, P] + [I64] * 13 + [INT, P]),
     "vvt_sqrt_backprop_maxpool2d": (INT, [P, P, P] + [I64] * 15 + [INT, P]),
     "vvt_sqrt_backprop_avgpool2d": (INT, [P, P] + [I64] * 12 + [INT, P]),
     "vvt_v_emit_conv2d": (INT, [P, P, P] + [I64] * 16 + [P, I64, INT, P]),

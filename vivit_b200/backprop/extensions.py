@@ -492,8 +492,8 @@ def _factor_maxpool2d(ext, module: nn.MaxPool2d, S, need_in):
     x = ext._subsample(module.input0.detach())
     k, s = _pair(module.kernel_size), _pair(module.stride if module.stride is not None else module.kernel_size)
     p, d = _pair(module.padding), _pair(module.dilation)
-    # arg-max positions of the forward pass (index plumbing; [BackPACK] recomputes them the same way)
-    _, idx = F.max_pool2d(x, k, s, p, d, module.ceil_mode, return_indices=True)
+    # arg-max positions of the forward pass (index plumbing; [BackPACK] recomputes them from the layer input too)
+    idx = kernels.maxpool2d_argmax(x, k, s, p, d, module.ceil_mode)
     return kernels.sqrt_backprop_maxpool2d(S, idx, tuple(x.shape[2:]), k, s, p, d)
 
 
@@ -520,7 +520,7 @@ def _factor_maxpool1d(ext, module: nn.MaxPool1d, S, need_in):
     stride = module.stride if module.stride is not None else module.kernel_size
     k, s = (1, _one(module.kernel_size)), (1, _one(stride))
     p, d = (0, _one(module.padding)), (1, _one(module.dilation))
-    _, idx = F.max_pool2d(x, k, s, p, d, module.ceil_mode, return_indices=True)
+    idx = kernels.maxpool2d_argmax(x, k, s, p, d, module.ceil_mode)
     return kernels.sqrt_backprop_maxpool2d(S.unsqueeze(3), idx, tuple(x.shape[2:]), k, s, p, d).squeeze(3)
 
 

@@ -135,6 +135,35 @@ __global__ void __launch_bounds__(256) act_rows_kernel(T* out, const T* S, const
   }
 }
 
+// Arg-max positions of a max-pool forward pass, recomputed from the layer input for the factor back-propagation
+// ([BackPACK] re-runs the pooling with return_indices=True for its Jacobian; torch's rule is restated here so the
+// same input position is chosen among tied values -- ReLU zeros tie all the time): windows are scanned row by row,
+// a value replaces the running maximum when it is GREATER (the first of equal values wins) or NaN; padding is
+// skipped, the index is flat into the h_in x w_in plane.  One thread per output position.
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_argmax_kernel(int64_t* idx, const T* x, int64_t total, int ho, int wo, int hi, int wi, int kh, int kw, int sh,
+                      int sw, int ph, int pw, int dh, int dw) {
+  const int hw_out = ho * wo;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t plane = i / hw_out;
+    const int q = int(i - plane * hw_out), oy = q / wo, ox = q - oy * wo;
+    int y0 = oy * sh - ph, x0 = ox * sw - pw;
+    const int y1 = min(y0 + (kh - 1) * dh + 1, hi), x1 = min(x0 + (kw - 1) * dw + 1, wi);
+    while (y0 < 0) y0 += dh;
+    while (x0 < 0) x0 += dw;
+    const T* xp = x + plane * int64_t(hi) * wi;
+    int best = y0 * wi + x0;
+    T vmax_ = -INFINITY;
+    for (int y = y0; y < y1; y += dh)
+      for (int xx = x0; xx < x1; xx += dw) {
+        const T v = xp[y * wi + xx];
+        if (v > vmax_ || v != v) vmax_ = v, best = y * wi + xx;
+      }
+    idx[i] = best;
+  }
+}
+
 // gather form of the max-pool scatter: every input position sums the outputs that chose it.
 // One block per (row, channel) plane (grid-stride): the plane decomposition is done once per block and
 // the strides are compile-time constants for the common cases (STRIDE = 1, 2; 0 = run-time), so the
@@ -630,6 +659,26 @@ int vvt_sqrt_backprop_elementwise(void* out, const void* S, const void* ref, int
       act_kernel<T><<<ew_blocks(V * n_feat), 256, 0, as_stream(stream)>>>((T*)out, (const T*)S, (const T*)ref, V, n_feat, act,
                                                                          T(scale));
     }
+    return launched(__func__);
+  });
+}
+
+int vvt_maxpool2d_argmax(int64_t* argmax, const void* x, int64_t planes, int64_t h_out, int64_t w_out, int64_t h_in,
+                         int64_t w_in, int64_t kh, int64_t kw, int64_t stride_h, int64_t stride_w, int64_t pad_h,
+                         int64_t pad_w, int64_t dil_h, int64_t dil_w, int dtype, void* stream) {
+  VVT_REQUIRE(planes >= 0 && h_out >= 0 && w_out >= 0 && h_in >= 0 && w_in >= 0, "negative size");
+  VVT_REQUIRE(stride_h > 0 && stride_w > 0 && dil_h > 0 && dil_w > 0 && kh > 0 && kw > 0 && pad_h >= 0 && pad_w >= 0,
+              "bad window");
+  VVT_REQUIRE(h_in * w_in < (int64_t(1) << 31) && h_out * w_out < (int64_t(1) << 31), "plane too large");
+  const int64_t total = planes * h_out * w_out;
+  if (total == 0) return VVT_OK;
+  VVT_REQUIRE(argmax && x, "null pointer");
+  // every window must contain at least one input position (torch's output-size rule guarantees it)
+  VVT_REQUIRE((h_out - 1) * stride_h - pad_h < h_in && (w_out - 1) * stride_w - pad_w < w_in, "window outside the input");
+  VVT_DISPATCH(dtype, {
+    maxpool_argmax_kernel<T><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+        argmax, (const T*)x, total, int(h_out), int(w_out), int(h_in), int(w_in), int(kh), int(kw), int(stride_h),
+        int(stride_w), int(pad_h), int(pad_w), int(dil_h), int(dil_w));
     return launched(__func__);
   });
 }

@@ -278,6 +278,36 @@ def sqrt_backprop_elementwise(S: Tensor, ref: Tensor, act: int, scale: float = 1
     return out
 
 
+def pool_output_size(size: int, kernel: int, stride: int, padding: int, dilation: int, ceil_mode: bool) -> int:
+    """Output extent of a pooling window sweep (torch's rule; in ceil mode the last window must start inside the
+    input or its left padding)."""
+    span = size + 2 * padding - dilation * (kernel - 1) - 1 + (stride - 1 if ceil_mode else 0)
+    out = span // stride + 1
+    if ceil_mode and (out - 1) * stride >= size + padding:
+        out -= 1
+    return out
+
+
+def maxpool2d_argmax(x: Tensor, kernel, stride, padding, dilation, ceil_mode: bool = False) -> Tensor:
+    """Arg-max positions ``[N, ch, Ho, Wo]`` (``int64``, flat into ``H*W``) of ``max_pool2d(x [N, ch, H, W])``,
+    chosen as torch chooses them (first of equal values).  The index plumbing of the max-pool Jacobian."""
+    x = _c(x)
+    _chk(x)
+    N, ch, h, w = x.shape
+    ho = pool_output_size(h, kernel[0], stride[0], padding[0], dilation[0], ceil_mode)
+    wo = pool_output_size(w, kernel[1], stride[1], padding[1], dilation[1], ceil_mode)
+    if ho <= 0 or wo <= 0:
+        raise ValueError(f"max-pool window {tuple(kernel)} does not fit the input {(h, w)}")
+    idx = torch.empty(N, ch, ho, wo, dtype=torch.int64, device=x.device)
+    with _on(x.device):
+        st = _lib.load().vvt_maxpool2d_argmax(
+            _p(idx), _p(x), N * ch, ho, wo, h, w, kernel[0], kernel[1], stride[0], stride[1],
+            padding[0], padding[1], dilation[0], dilation[1], _dt(x), _stream(x),
+        )
+    _lib.check(st, "vvt_maxpool2d_argmax")
+    return idx
+
+
 def sqrt_backprop_maxpool2d(
     S: Tensor, argmax: Tensor, in_hw, kernel, stride, padding, dilation
 ) -> Tensor:
@@ -729,7 +759,7 @@ def v_apply_linear(v: Tensor, S: Tensor, Z: Tensor) -> Tensor:
 TIMED = [
     "loss_sqrt_hessian_ce", "loss_sqrt_hessian_ce_mc", "loss_sqrt_hessian_mse", "scale_",
     "sqrt_backprop_linear", "sqrt_backprop_conv2d", "sqrt_backprop_elementwise",
-    "sqrt_backprop_maxpool2d", "sqrt_backprop_avgpool2d", "v_emit_conv2d", "v_emit_bias",
+    "sqrt_backprop_maxpool2d", "maxpool2d_argmax", "sqrt_backprop_avgpool2d", "v_emit_conv2d", "v_emit_bias",
     "v_emit_linear", "gemm", "gram_dense_accum", "gram_cross_accum", "gram_linear_accum",
     "gram_cross_linear_accum", "syevj", "syevj_batched", "syevj_dist", "filter_nonzero", "backtransform_dense",
     "backtransform_linear", "vt_mat_prod_linear", "scale_rows_rsqrt", "dirderiv_epilogue",
