@@ -4,8 +4,10 @@
 so each rank takes a slice of every parameter's leading (output-channel) dimension,
 assembles a partial Gram from its slice, and the partial Grams are summed with ONE
 all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests).  Everything after the
-all-reduce that lives in Gram space (eigensolver, directional derivatives, Newton
-coefficients) is computed redundantly and deterministically on every rank; results in
+all-reduce that lives in Gram space (directional derivatives, Newton coefficients, the
+eigensolver of small groups) is computed redundantly and deterministically on every rank; the
+eigensolver of a group of 4096 columns or more (fp32) is distributed over the ranks
+(``solver_comm`` / ``solver_arena``, ``vvt_syevj_dist``); results in
 parameter space (eigenvectors, Newton steps) stay sharded along dim 0 unless
 ``gather=True``.
 
