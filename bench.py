@@ -169,11 +169,19 @@ class Stepper:
                     f"the half that computed them")
             elif w["grouping"] == "layer":
                 # block-diagonal groups are independent: whole groups per rank, no collective
-                from vivit_b200.dist import local_groups
+                # (more ranks than groups: a team of ranks per group, Gram parameter-sharded and eigensolver rounds
+                # distributed inside the team)
+                from vivit_b200.dist import team_groups
 
-                self.groups, owner = local_groups(self.groups, process_group)
-                self.pg = None
-                self.parallelism = f"{len(owner)} block-diagonal groups assigned to {world} ranks, no collective"
+                n_groups = len(self.groups)
+                self.groups, self.pg, teams = team_groups(self.groups, process_group)
+                if world <= n_groups:
+                    self.parallelism = f"{n_groups} block-diagonal groups assigned to {world} ranks, no collective"
+                else:
+                    self.parallelism = (
+                        f"{n_groups} block-diagonal groups on teams of {[len(t) for t in teams]} ranks: inside a team "
+                        f"the Gram is parameter-sharded and the eigensolver rounds are distributed (vvt_syevj_dist); "
+                        f"no collective between teams")
             else:
                 self.parallelism = (
                     f"parameter-sharded Gram over {world} ranks, one all-reduce per group; the block pairs of every "

@@ -69,6 +69,43 @@ def check_distributed_solver(dev, sr):
         del os.environ["VVT_SYEVJ_WIDE_MIN"]
 
 
+def check_team_of_ranks(dev):
+    """``dist.team_groups`` with more ranks than groups: the one group of this model gets a team of both ranks -- a
+    sub-group of its own, not WORLD -- whose Gram (R = 640) is parameter-sharded inside the team and decomposed by
+    the team together (two-level path forced on the small matrix; the peer-memory arena of this device belongs to
+    WORLD already, so the blocks travel by ncclSend / ncclRecv on the team's communicator)."""
+    import vivit_b200 as vv
+    from vivit_b200.dist import team_groups
+
+    torch.manual_seed(1)
+    model = nn.Sequential(nn.Linear(20, 16), nn.ReLU(), nn.Linear(16, 10)).to(dev)
+    x, y = torch.rand(64, 20, device=dev), torch.randint(0, 10, (64,), device=dev)
+    top = lambda ev: list(range(ev.numel() - 4, ev.numel()))  # noqa: E731
+    groups = [{"params": list(model.parameters()), "criterion": top}]
+    own, team, teams = team_groups(groups, dist.group.WORLD)
+    assert own == groups and team is not None and teams == [[0, 1]]
+    ((ev1, vec1),) = run(vv.EighComputation(), model, x, y, groups)
+    os.environ["VVT_SYEVJ_WIDE_MIN"] = "512"
+    try:
+        seen = []
+        orig = vv.kernels.syevj_dist
+
+        def spy(*a, **k):
+            seen.append(k.get("p2p"))
+            return orig(*a, **k)
+
+        vv.kernels.syevj_dist = spy
+        ((evs, vecs),) = run(vv.EighComputation(process_group=team, gather=True), model, x, y, groups)
+        vv.kernels.syevj_dist = orig
+        assert seen == [False], seen  # the team's solve was distributed, over NCCL
+    finally:
+        del os.environ["VVT_SYEVJ_WIDE_MIN"]
+    assert torch.allclose(ev1, evs, rtol=1e-4, atol=1e-7), (ev1, evs)
+    a = torch.cat([v.flatten(1) for v in vec1], 1).double()
+    b = torch.cat([v.flatten(1) for v in vecs], 1).double()
+    assert (a @ b.t()).abs().diag().min() > 1 - 1e-3
+
+
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -105,6 +142,7 @@ def main():
     dist.all_gather(gathered, evs.contiguous())
     assert all(torch.equal(gathered[0], t) for t in gathered)
     check_distributed_solver(dev, sr)
+    check_team_of_ranks(dev)
     dist.barrier()
     dist.destroy_process_group()
     if local == 0:

@@ -259,3 +259,72 @@ def test_partial_grams_of_all_shards_sum_to_the_full_gram_even_with_empty_shards
     model, x, y = _problem()
     want, _ = ref.gram_sqrt_ggn(model, nn.CrossEntropyLoss(), x, y)
     assert torch.allclose(total, want, rtol=1e-9, atol=1e-12), (total - want).abs().max()
+
+
+def _worker_teams(rank, world, port, errors):
+    try:
+        if ROOT not in sys.path:
+            sys.path.insert(0, ROOT)
+        import torch.distributed as dist
+
+        import tests._torch_kernels as double
+        from oracle import reference_path as ref
+
+        double.install(_MonkeyPatch())
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        import vivit_b200 as vv
+        from vivit_b200.dist import team_groups
+
+        model, x, y = _problem()
+        groups = _groups(model, "layer")  # three groups, four ranks: one team of two, two teams of one
+        own, team, teams = team_groups(groups, dist.group.WORLD)
+        assert sorted(r for t in teams for r in t) == list(range(world)) and len(teams) == len(groups)
+        assert sorted(len(t) for t in teams) == [1, 1, 2]
+        assert len(own) == 1
+        which = next(i for i, g in enumerate(groups) if g is own[0])
+        assert rank in teams[which] and (team is not None) == (len(teams[which]) > 1)
+        kw = {"process_group": team, "gather": True} if team is not None else {}
+        comp = vv.EighComputation(**kw)
+        m, lf = vv.extend(model), vv.extend(nn.CrossEntropyLoss())
+        with vv.backpack(*comp.get_extensions(), extension_hook=comp.get_extension_hook(own)):
+            lf(m(x), y).backward()
+        model0, x0, y0 = _problem()
+        want = ref.eigh(model0, nn.CrossEntropyLoss(), x0, y0, _groups(model0, "layer"))
+        (wev, wvecs) = want[which]
+        ev, evecs = comp.get_result(own[0])
+        assert torch.allclose(ev, wev, rtol=1e-9, atol=1e-12)
+        for e, w_ in zip(evecs, wvecs):
+            assert e.shape == w_.shape  # gathered inside the team
+            for k in range(e.shape[0]):
+                sign = torch.sign((e[k] * w_[k]).sum())
+                assert torch.allclose(e[k] * sign, w_[k], rtol=1e-6, atol=1e-9)
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        errors.put((rank, traceback.format_exc()))
+
+
+def test_more_ranks_than_groups_work_in_teams():
+    """``dist.team_groups``: four ranks, three block-diagonal groups -- the costliest group gets a team of two ranks
+    (parameter-sharded inside the team), the others one rank each; no collective between teams."""
+    from vivit_b200.dist import team_sizes
+
+    assert team_sizes([1.0, 1.0, 1.0, 1.0], 8) == [2, 2, 2, 2]
+    assert team_sizes([3.0, 1.0], 4) == [3, 1] and sum(team_sizes([1.5, 1.2, 1.1], 8)) == 8
+    world, port = 4, _free_port()
+    ctx = mp.get_context("spawn")
+    errors = ctx.Queue()
+    procs = [ctx.Process(target=_worker_teams, args=(r, world, port, errors)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            pytest.fail("a rank hung")
+    msgs = []
+    while not errors.empty():
+        msgs.append(errors.get())
+    assert not msgs, "\n".join(f"rank {r}:\n{t}" for r, t in msgs)
+    assert all(p.exitcode == 0 for p in procs)

@@ -211,6 +211,54 @@ def assign_groups(costs: Sequence[float], world: int) -> List[int]:
     return owner
 
 
+def team_sizes(costs: Sequence[float], world: int) -> List[int]:
+    """Ranks per group when there are more ranks than groups: one each, the rest go one by one to the group whose
+    cost per rank is largest."""
+    sizes = [1] * len(costs)
+    for _ in range(world - len(costs)):
+        i = max(range(len(costs)), key=lambda i: costs[i] / sizes[i])
+        sizes[i] += 1
+    return sizes
+
+
+def team_groups(param_groups: Sequence[Dict], process_group=None, costs: Optional[Sequence[float]] = None):
+    """``local_groups`` for MORE ranks than block-diagonal groups: every group gets a team of consecutive ranks.
+    A team of one runs its group as ``local_groups`` would; a larger team runs the Computation with
+    ``process_group=team`` -- the group's Gram is parameter-sharded over the team (one all-reduce inside the team)
+    and a Gram of 4096 columns or more is decomposed by the team together (``vvt_syevj_dist``).  Teams never talk to
+    each other.
+
+    Returns ``(own, team, teams)``: the groups this rank works on, the ``torch.distributed`` group of its team
+    (``None`` for a team of one, or when there are at most as many ranks as groups -- then this is ``local_groups``),
+    and the list of rank lists per group.  Collective over ``process_group`` (sub-groups are created)."""
+    if process_group is None:
+        return list(param_groups), None, [[0] for _ in param_groups]
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+    if world <= len(param_groups):
+        own, owner = local_groups(param_groups, process_group, costs)
+        return own, None, [[o] for o in owner]
+    if costs is None:
+        numel = [sum(p.numel() for p in g["params"]) for g in param_groups]
+        total = float(max(sum(numel), 1))
+        costs = [1.0 + n / total for n in numel]
+    sizes = team_sizes(costs, world)
+    teams, start = [], 0
+    for size in sizes:
+        teams.append(list(range(start, start + size)))
+        start += size
+    own, mine = [], None
+    for group, members in zip(param_groups, teams):
+        # every rank of the parent group takes part in the creation of every sub-group, in the same order
+        global_ranks = [dist.get_global_rank(process_group, r) for r in members]
+        sub = dist.new_group(global_ranks) if len(members) > 1 else None
+        if rank in members:
+            own.append(group)
+            mine = sub
+    return own, mine, teams
+
+
 def local_groups(param_groups: Sequence[Dict], process_group=None, costs: Optional[Sequence[float]] = None):
     """Block-diagonal parameter groups are independent (``vivit/utils/hooks.py:214-219``): give every rank
     whole groups and run the Computations WITHOUT ``process_group`` on them -- no collective at all.
