@@ -189,6 +189,12 @@ def _worker_groups(rank, world, port, errors):
         own, owner = local_groups(groups, dist.group.WORLD)
         assert sorted(set(owner)) == list(range(world)) and len(owner) == len(groups)
         assert [g for g, o in zip(groups, owner) if o == rank] == own
+        # no more ranks than groups: team_groups is local_groups (teams of one, no sub-group)
+        from vivit_b200.dist import team_groups
+
+        own_t, team, teams = team_groups(groups, dist.group.WORLD)
+        assert team is None and teams == [[o] for o in owner] and len(own_t) == len(own)
+        assert all(a is b for a, b in zip(own_t, own))
         comp = vv.EighComputation()  # no process group: whole groups, no collective
         m, lf = vv.extend(model), vv.extend(nn.CrossEntropyLoss())
         with vv.backpack(*comp.get_extensions(), extension_hook=comp.get_extension_hook(own)):
