@@ -44,6 +44,10 @@ def test_block_hand_over_plan(nbw, world):
             assert pair_rank == sorted(pair_rank) and set(pair_rank) <= set(range(world))
             sizes = [pair_rank.count(r) for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+            # ... and they are the slices the solver launches its kernels on: [P r / W, P (r + 1) / W)
+            for r in range(world):
+                lo, hi = pairs * r // world, pairs * (r + 1) // world
+                assert [i for i, pr in enumerate(pair_rank) if pr == r] == list(range(lo, hi))
             # during the round both blocks of a pair are with the rank that works on the pair
             for (a, b), r in zip(blocks, pair_rank):
                 assert owner[a] == r and owner[b] == r
