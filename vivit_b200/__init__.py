@@ -24,6 +24,7 @@ from vivit_b200.backprop import (
     extend,
 )
 from vivit_b200 import custom_module, extensions, hessianfree
+from vivit_b200.factors import set_conv_factor_streaming
 from vivit_b200.linalg import EighComputation, EigvalshComputation, SolveQueue
 from vivit_b200.optim import DirectionalDampedNewtonComputation, DirectionalDerivativesComputation
 
@@ -38,6 +39,7 @@ __all__ = [
     "DirectionalDerivativesComputation",
     "DirectionalDampedNewtonComputation",
     "SolveQueue",
+    "set_conv_factor_streaming",
     "ViViTGGNExact",
     "ViViTGGNMC",
     "SqrtGGNExact",

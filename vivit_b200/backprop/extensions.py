@@ -41,6 +41,8 @@ from vivit_b200.factors import (
     LinearBiasFactor,
     LinearWeightFactor,
     LinearWeightGrad,
+    StreamedConvFactor,
+    conv_factor_streaming,
     link_linear_factors,
 )
 
@@ -291,8 +293,13 @@ def _factor_conv2d(ext: _SqrtFactorExtension, module: nn.Conv2d, S: Tensor, need
     if b is not None:
         ext._save(b, DenseFactor(kernels.v_emit_bias(S_own), (hi - lo,)))
     if w is not None:
-        Vt = kernels.v_emit_conv2d(S_own, x, kernel, *geom)
-        ext._save(w, DenseFactor(Vt, (hi - lo, *w.shape[1:])))
+        w_shape = (hi - lo, *w.shape[1:])
+        stream = conv_factor_streaming()
+        if stream is not None:  # opt-in: V_p^T emitted chunk by chunk at every use, never materialised as a whole
+            ext._save(w, StreamedConvFactor(S_own, x, kernel, geom, w_shape, stream))
+        else:
+            Vt = kernels.v_emit_conv2d(S_own, x, kernel, *geom)
+            ext._save(w, DenseFactor(Vt, w_shape))
     if not need_in:
         return None
     weight = module.weight.detach()

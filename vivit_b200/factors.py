@@ -104,6 +104,91 @@ class DenseFactor(Factor):
         return self.Vt.reshape(self.C, self.N, *self.param_shape)
 
 
+_CONV_STREAM_BYTES: Optional[int] = None
+
+
+def set_conv_factor_streaming(chunk_bytes: Optional[int]) -> None:
+    """``chunk_bytes`` (e.g. ``48 << 20``): conv weights get a ``StreamedConvFactor`` -- ``V_p^T`` is emitted in
+    output-channel chunks of at most that many bytes whenever it is needed and never exists as a whole.  ``None``
+    (default): the factor is materialised once (``DenseFactor``), which is faster when it is used more than once and
+    fits.  ``VVT_STREAM_CONV_FACTOR_MB`` in the environment sets the default."""
+    global _CONV_STREAM_BYTES
+    _CONV_STREAM_BYTES = None if chunk_bytes is None else max(1, int(chunk_bytes))
+
+
+def conv_factor_streaming() -> Optional[int]:
+    if _CONV_STREAM_BYTES is not None:
+        return _CONV_STREAM_BYTES
+    import os
+
+    mb = os.environ.get("VVT_STREAM_CONV_FACTOR_MB")
+    return int(float(mb) * (1 << 20)) if mb else None
+
+
+class StreamedConvFactor(Factor):
+    """``V_p^T`` of a convolution weight that is never materialised as a whole (north star (2), VERDICT n2 at the
+    host level): the factor ``S [C, N, Co, Ho, Wo]`` of the layer output and the layer input ``x`` are kept, and every
+    use emits ``V_p^T`` for a chunk of output channels (``vvt_v_emit_conv2d`` on a channel slice, the call the
+    parameter-sharded path makes per rank), consumes it (Gram / cross term / back-transform) and drops it.  A chunk
+    of a few tens of MB stays in the 126 MB L2 between the emit and its consumer.  Costs one emit per use instead of
+    one per pass -- DESIGN section 4 has the arithmetic of why the DEFAULT keeps the factor materialised; this is for
+    factors that should not occupy ``R x D_p`` of HBM (``reference: base.py:84-92`` materialises them always)."""
+
+    def __init__(self, S: Tensor, x: Tensor, kernel, geom, param_shape, chunk_bytes: int):
+        self.C, self.N = S.shape[:2]
+        self.param_shape = tuple(param_shape)  # (Co_own, Ci, kh, kw); (Co_own, Ci, k) for a 1-d convolution
+        self.S, self.x, self.kernel, self.geom = S, x, tuple(kernel), tuple(geom)
+        self.per_channel = 1
+        for d in self.param_shape[1:]:
+            self.per_channel *= d
+        row_bytes = self.C * self.N * self.per_channel * S.element_size()
+        self.step = max(1, int(chunk_bytes) // max(1, row_bytes))
+
+    def _like(self):
+        return self.S
+
+    def chunks(self):
+        """``(lo, hi, Vt [R, (hi - lo) * Ci * kh * kw])`` over the output channels."""
+        co = self.param_shape[0]
+        for lo in range(0, co, self.step):
+            hi = min(co, lo + self.step)
+            S = self.S if (lo, hi) == (0, co) else self.S[:, :, lo:hi].contiguous()
+            Vt = kernels.v_emit_conv2d(S, self.x, self.kernel, *self.geom)
+            yield lo, hi, Vt.reshape(self.R, -1)
+
+    def _cols(self, lo, hi):
+        return slice(lo * self.per_channel, hi * self.per_channel)
+
+    def gram_accum(self, G, fold=True):
+        for _, _, Vt in self.chunks():
+            kernels.gram_dense_accum(G, Vt)
+
+    def cross_accum(self, X, grad):
+        g = grad.dense()
+        for lo, hi, Vt in self.chunks():
+            kernels.gram_cross_accum(X, Vt, g[:, self._cols(lo, hi)].contiguous())
+
+    def backtransform(self, U, norm2):
+        U = U.reshape(U.shape[0], -1)
+        parts = [kernels.backtransform_dense(U, Vt, norm2) for _, _, Vt in self.chunks()]  # norm2 accumulates
+        return torch.cat(parts, dim=1).reshape(U.shape[0], *self.param_shape)
+
+    def v_apply(self, v):
+        parts = [kernels.v_apply_dense(v.reshape(-1), Vt) for _, _, Vt in self.chunks()]
+        return torch.cat(parts).reshape(self.param_shape)
+
+    def vt_mat_prod(self, M):
+        F_ = M.shape[0]
+        M = M.reshape(F_, -1)
+        out = torch.zeros(self.R, F_, dtype=self.S.dtype, device=self.S.device)
+        for lo, hi, Vt in self.chunks():
+            kernels.gram_cross_accum(out, Vt, M[:, self._cols(lo, hi)].contiguous())
+        return out.t().reshape(F_, self.C, self.N)
+
+    def materialize(self):
+        return torch.cat([Vt for _, _, Vt in self.chunks()], dim=1).reshape(self.C, self.N, *self.param_shape)
+
+
 class LinearBiasFactor(DenseFactor):
     """Bias of a 2-d ``Linear`` layer: ``V_b^T = S``, so ``G_b = S S^T`` -- the very product the weight's Gram
     ``(Z Z^T) (.) (S S^T)`` is built from.  The reference computes it twice (``linear.py:72`` and, for the bias,
